@@ -1,0 +1,135 @@
+/*
+ * pgpp.h -- C ABI of libpgpp_sm100a.so, the prebuilt B200 (sm_100a) kernel library behind the
+ * PASTA-GAN++ / StyleGAN2 synthesis ops.  It replaces the reference's ninja-JIT pybind plugins
+ * (torch_utils/custom_ops.py:46-124 -> bias_act_plugin / upfirdn2d_plugin) and the cuDNN calls
+ * behind conv2d_gradfix with plain `extern "C"` entry points: raw device pointers, sizes,
+ * strides, scalars and a CUDA stream.  No ATen / pybind / torch types appear here.
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative pgpp_status; pgpp_last_error() gives the
+ *     message of the last failure on the calling thread (the reference raises RuntimeError through
+ *     TORCH_CHECK, bias_act.cpp:35-51, upfirdn2d.cpp:19-36; the Python shim re-raises the same way)
+ *   - inputs are borrowed and never written; outputs are caller-allocated
+ *   - launches are asynchronous on `stream` (a cudaStream_t passed as void*), on the current device
+ *   - the library keeps no global device state and is re-entrant
+ */
+#ifndef PGPP_H_
+#define PGPP_H_
+
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define PGPP_API __attribute__((visibility("default")))
+#else
+#define PGPP_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum { PGPP_F32 = 0, PGPP_F16 = 1, PGPP_BF16 = 2, PGPP_F64 = 3 } pgpp_dtype;
+
+typedef enum {
+    PGPP_OK = 0,
+    PGPP_ERR_INVALID = -1,      /* bad argument (the reference's TORCH_CHECK failures) */
+    PGPP_ERR_UNSUPPORTED = -2,  /* valid but no kernel for it */
+    PGPP_ERR_CUDA = -3          /* CUDA runtime / driver error */
+} pgpp_status;
+
+/* activation indices: same numbering as `cuda_idx` in torch_utils/ops/bias_act.py:23-33 */
+typedef enum {
+    PGPP_ACT_LINEAR = 1, PGPP_ACT_RELU = 2, PGPP_ACT_LRELU = 3, PGPP_ACT_TANH = 4, PGPP_ACT_SIGMOID = 5,
+    PGPP_ACT_ELU = 6, PGPP_ACT_SELU = 7, PGPP_ACT_SOFTPLUS = 8, PGPP_ACT_SWISH = 9
+} pgpp_act;
+
+PGPP_API int pgpp_version(void);
+PGPP_API const char* pgpp_last_error(void);
+/* number of kernel launches issued through this library by the calling process (bench.py's gpu_launches) */
+PGPP_API int64_t pgpp_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * bias_act: y = clamp(act(x + b[(i / step_b) % size_b]) * gain), or its 1st / 2nd derivative.
+ * Replaces the plugin function `bias_act(x, b, xref, yref, dy, grad, dim, act, alpha, gain, clamp)`
+ * (torch_utils/ops/bias_act.cpp:32-90; kernel bias_act.cu:23-147).  All tensors are dense with the
+ * same memory layout as x and `size_x` elements; b / xref / yref / dy may be NULL ("empty tensor"
+ * in the reference, bias_act.py:39).  step_b = x.stride(dim) in elements.  clamp < 0 disables it.
+ */
+PGPP_API int pgpp_bias_act(const void* x, const void* b, const void* xref, const void* yref, const void* dy, void* y,
+                  int64_t size_x, int64_t size_b, int64_t step_b, int dtype, int grad, int act,
+                  float alpha, float gain, float clamp, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * upfirdn2d: zero-insert upsample, pad/crop, 2-D FIR, decimate.
+ * Replaces the plugin function `upfirdn2d(x, f, upx, upy, downx, downy, padx0, padx1, pady0, pady1,
+ * flip, gain)` (torch_utils/ops/upfirdn2d.cpp:16-94; kernels upfirdn2d.cu:29-200).
+ * size/stride arrays are in PyTorch order [N, C, H, W], strides in elements (NCHW-contiguous and
+ * channels_last both accepted).  f is float32 [fh, fw] with element strides f_stride_y / f_stride_x.
+ * The caller computes out_size as upfirdn2d.cpp:32-33 does; padx1 / pady1 are implied by it.
+ */
+PGPP_API int pgpp_upfirdn2d(const void* x, const float* f, void* y,
+                   const int64_t in_size[4], const int64_t in_stride[4],
+                   const int64_t out_size[4], const int64_t out_stride[4],
+                   int fw, int fh, int64_t f_stride_x, int64_t f_stride_y,
+                   int upx, int upy, int downx, int downy, int padx0, int pady0,
+                   int flip, float gain, int dtype, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Convolution family (new; replaces F.conv2d / F.conv_transpose2d / cuDNN at
+ * torch_utils/ops/conv2d_gradfix.py:38,43,112-114 and the per-sample weight algebra of
+ * training/networks.py:62-70).
+ */
+
+/* d[n,o] = rsqrt(sum_{i,ky,kx} (w[o,i,ky,kx] * s[n,i])^2 + eps)   (training/networks.py:64-68).
+ * w float32 [O, I, taps] contiguous, s float32 [N, I] contiguous, d float32 [N, O]. */
+PGPP_API int pgpp_modconv_demod_coefs(const float* w, const float* s, float* d, int n, int o, int i, int taps,
+                             float eps, void* stream);
+
+/* Pack an activation tensor for the tensor-core path: NCHW-or-any-strided x (f32/f16/bf16/f64) ->
+ * channels-innermost bf16 [parts][N][H][W][c_pad], optionally multiplied by scale[n,c] first
+ * (the style modulation x * s of training/networks.py:74).  part p holds bf16(x - sum_{q<p} part q),
+ * so parts = 1 is plain bf16 and parts = 2 / 3 carry 16 / 24 significand bits (error-compensated
+ * fp32 mode).  Channels c >= C are zero-filled. */
+PGPP_API int pgpp_pack_activations(const void* x, const int64_t size[4], const int64_t stride[4], int dtype,
+                          const float* scale, void* out, int c_pad, int parts, void* stream);
+
+/* Epilogue + geometry of one implicit-GEMM convolution launch. */
+typedef struct {
+    /* packed activations [a_parts][N][H][W][c_pad] bf16 and packed weights [b_parts][taps][o_rows][c_pad] bf16 */
+    const void* act;
+    const void* wgt;
+    int32_t a_parts, b_parts;
+    int32_t n, h, w, c_pad;         /* input geometry */
+    int32_t kh, kw;                 /* filter taps */
+    int32_t pad_y, pad_x;           /* zero padding (top / left); bottom / right implied by out size */
+    int32_t stride;                 /* 1 or 2 */
+    int32_t conv_h, conv_w;         /* conv output grid (per phase) */
+    int32_t o;                      /* logical output channels (per phase) */
+    int32_t phases;                 /* 1, or 4 for the fused up=2 polyphase form: GEMM column g = phase*o + oc,
+                                       phase = 2*py + px writes output pixel (2y+py, 2x+px) */
+    int32_t o_rows;                 /* rows per tap in wgt: >= phases*o, multiple of block_n */
+    int32_t block_n;                /* GEMM N tile: 16, 32, 64, 128 or 256 */
+    int32_t products;               /* 1 (bf16), 3 (2-part split) or 6 (3-part split) */
+    /* epilogue: v = acc * dcoef[n,oc] + noise[n?,y,x];  y = clamp(act(v + bias[oc]) * gain) */
+    const float* dcoef;             /* [N, o] or NULL */
+    const float* noise;             /* [out_h, out_w] (noise_stride_n = 0) or [N, out_h, out_w]; or NULL */
+    int64_t noise_stride_n;
+    const float* bias;              /* [o] or NULL */
+    int32_t act_fn;                 /* pgpp_act */
+    float alpha, gain, clamp;
+    /* output tensor, logical [N, o, out_h, out_w] with element strides (any layout) */
+    void* out;
+    int32_t out_dtype;              /* PGPP_F32 / PGPP_BF16 / PGPP_F16 */
+    int32_t out_h, out_w;
+    int64_t out_stride[4];
+    int32_t accumulate;             /* nonzero: out += result (used for `img = img + y`, networks.py:2190) */
+} pgpp_conv_desc;
+
+/* Implicit-GEMM convolution on the 5th-gen tensor cores (tcgen05.mma, TMEM accumulators, TMA operand
+ * loads), persistent over the SMs, with the epilogue above fused. */
+PGPP_API int pgpp_conv2d_igemm(const pgpp_conv_desc* desc, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PGPP_H_ */

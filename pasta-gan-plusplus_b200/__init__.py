@@ -1,0 +1,37 @@
+"""B200-native (sm_100a) kernels behind the PASTA-GAN++ / StyleGAN2 synthesis ops.
+
+Package layout mirrors the reference's import paths for the hot path only:
+    torch_utils/custom_ops.py            prebuilt C-ABI library loader (replaces the ninja JIT)
+    torch_utils/ops/{bias_act,upfirdn2d,conv2d_gradfix,conv2d_resample,fma}.py
+    training/networks.py                 modulated_conv2d (+ the layer classes that call it)
+    csrc/                                CUDA sources of lib/libpgpp_sm100a.so (C ABI: include/pgpp.h)
+
+The directory name is not a Python identifier; load it with `tests/conftest.py:load_pkg()` /
+`__graft_entry__.load_pkg()` (module name `pgpp_b200`) or call `install()` to alias the op modules
+over an importable reference checkout.
+"""
+import importlib
+import sys
+
+__version__ = '0.1.0'
+
+OP_MODULES = ('bias_act', 'upfirdn2d', 'conv2d_gradfix', 'conv2d_resample', 'fma')
+
+
+def install(patch_networks=True):
+    """Drop-in switch: make `torch_utils.ops.<op>` and `torch_utils.custom_ops` resolve to this package
+    and replace `training.networks.modulated_conv2d` (if that module is importable / imported).
+    Call before the reference model modules are imported."""
+    me = sys.modules[__name__]
+    ops = importlib.import_module(f'{__name__}.torch_utils.ops')
+    for name in OP_MODULES:
+        mod = importlib.import_module(f'{__name__}.torch_utils.ops.{name}')
+        sys.modules[f'torch_utils.ops.{name}'] = mod
+        parent = sys.modules.get('torch_utils.ops')
+        if parent is not None:
+            setattr(parent, name, mod)
+    sys.modules['torch_utils.custom_ops'] = importlib.import_module(f'{__name__}.torch_utils.custom_ops')
+    if patch_networks and 'training.networks' in sys.modules:
+        nets = importlib.import_module(f'{__name__}.training.networks')
+        sys.modules['training.networks'].modulated_conv2d = nets.modulated_conv2d
+    return me

@@ -1,0 +1,52 @@
+// Shared host/device helpers for libpgpp_sm100a.so (no torch, no pybind).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include <atomic>
+#include "../../include/pgpp.h"
+
+namespace pgpp {
+
+void set_error(const char* fmt, ...);
+extern std::atomic<long long> g_launches;
+
+inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+#define PGPP_REQUIRE(cond, ...)                                  \
+    do { if (!(cond)) { ::pgpp::set_error(__VA_ARGS__); return PGPP_ERR_INVALID; } } while (0)
+
+#define PGPP_CUDA_OK(expr)                                                                   \
+    do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) {                                    \
+        ::pgpp::set_error("%s failed: %s", #expr, cudaGetErrorString(e_)); return PGPP_ERR_CUDA; } } while (0)
+
+inline int sm_count() {
+    static int cached[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) return 148;
+    if (!cached[dev]) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        cached[dev] = n;
+    }
+    return cached[dev];
+}
+
+// scalar <-> storage conversions; math runs in float (double for f64), like the reference's
+// InternalType (bias_act.cu:15-18, upfirdn2d.cu:15-18)
+template <class T> struct Acc { typedef float type; };
+template <> struct Acc<double> { typedef double type; };
+
+template <class T> __device__ __forceinline__ typename Acc<T>::type to_acc(T v) { return (typename Acc<T>::type)v; }
+template <> __device__ __forceinline__ float to_acc<__half>(__half v) { return __half2float(v); }
+template <> __device__ __forceinline__ float to_acc<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+
+template <class T> __device__ __forceinline__ T from_acc(typename Acc<T>::type v) { return (T)v; }
+template <> __device__ __forceinline__ __half from_acc<__half>(float v) { return __float2half_rn(v); }
+template <> __device__ __forceinline__ __nv_bfloat16 from_acc<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+} // namespace pgpp

@@ -1,0 +1,475 @@
+// Implicit-GEMM convolution for sm_100a: tcgen05.mma with TMEM accumulators, TMA operand loads,
+// mbarrier pipeline, warp-specialised persistent CTAs, fused modulated-conv epilogue.
+//
+//   GEMM view      D[pixel, g] = sum_{tap, c} A[pixel shifted by tap, c] * B[tap][g][c]
+//   M (TMEM lanes) 128 output pixels: a TN x TH x TW block of (sample, row, column)
+//   N (columns)    block_n GEMM columns g = phase * O + oc
+//   K              taps x c_pad, walked in blocks of kb channels (kb * 2 bytes = one swizzle row)
+//
+// The A tile of a K step is one TMA box {kb, TW, TH, TN, 1} of the channels-innermost activation
+// tensor at the tap's (dx, dy) offset; rows outside the image come back as zeros (TMA out-of-bounds
+// fill), which is exactly the convolution's zero padding - no im2col buffer exists anywhere.
+// The split-precision ("fp32 parity") mode runs the same loop over products (a_part, b_part) of
+// the bf16 expansions of both operands, all accumulated in the same fp32 TMEM tile.
+//
+// Warp roles (192 threads, 1 CTA per SM):
+//   warp 0      TMA producer        (one elected lane)
+//   warp 1      TMEM owner + tcgen05.mma issuer (one elected lane)
+//   warps 2-5   epilogue: tcgen05.ld -> demod / noise / bias / activation / clamp -> global store
+// Accumulators are double-buffered in TMEM so the epilogue of tile i overlaps the MMAs of tile i+1.
+//
+// Replaces the cuDNN calls of torch_utils/ops/conv2d_gradfix.py:38,43,112-114 and the grouped-conv
+// formulation of training/networks.py:85-93 (algebraically the non-fused form, networks.py:73-82).
+#include <cuda.h>
+#include "act.cuh"
+
+namespace pgpp {
+
+constexpr int kThreads = 192;
+constexpr int kTileM = 128;
+constexpr int kMaxStages = 8;
+
+struct IgemmParams {
+    int n, h, w;
+    int conv_h, conv_w;
+    int kh, kw, pad_y, pad_x, stride;
+    int num_cb, kb;
+    int products, pa[6], pb[6];
+    int o, phases, o_rows, block_n;
+    int tw, th, tn;
+    int tiles_x, tiles_y, tiles_n, tiles_col;
+    long long total_tiles;
+    int num_stages;
+    unsigned a_bytes, b_bytes;          // bytes one TMA box delivers (armed on the full barrier)
+    unsigned b_off, stage_bytes;        // B offset inside a stage, stage pitch (1024-byte multiples)
+    unsigned layout_type, sbo_bytes;
+    unsigned idesc;
+    unsigned tmem_cols;
+    const float* dcoef; const float* noise; long long noise_stride_n; const float* bias;
+    int act_fn; float alpha, gain, clamp;
+    void* out; int out_dtype; int out_h, out_w; long long os_n, os_c, os_h, os_w;
+    int accumulate;
+    int up;     // 1, or 2 when phases == 4
+};
+
+// ------------------------------------------------------------------------------------------------
+// PTX wrappers
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred = 0;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+// Bounded wait: a broken pipeline traps (the launch fails with an error) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 4000000000LL) { printf("pgpp igemm: mbarrier timeout (block %d thread %d)\n", blockIdx.x, threadIdx.x); __trap(); }
+    }
+}
+
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3, int c4) {
+    asm volatile("cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+                 ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+// arrives on the mbarrier once every previously issued tcgen05.mma of this thread has completed
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld16(uint32_t addr, float* v) {
+    uint32_t r[16];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(addr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    #pragma unroll
+    for (int i = 0; i < 16; i++) v[i] = __uint_as_float(r[i]);
+}
+
+// shared-memory matrix descriptor, K-major operand, rows of (8 << swizzle) ... see cute/arch/mma_sm100_desc.hpp
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t layout_type, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);            // start address, bits [0,14)
+    d |= (uint64_t)1 << 16;                                 // leading byte offset (unused for swizzled K-major), bits [16,30)
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;       // stride byte offset: 8-row group pitch, bits [32,46)
+    d |= (uint64_t)1 << 46;                                 // descriptor version 1 (Blackwell)
+    d |= (uint64_t)(layout_type & 7) << 61;                 // swizzle mode
+    return d;
+}
+
+// ------------------------------------------------------------------------------------------------
+
+struct TileCoord { int n0, y0, x0, col0; };
+
+__device__ __forceinline__ TileCoord decode_tile(const IgemmParams& p, long long t) {
+    TileCoord c;
+    c.col0 = (int)(t % p.tiles_col) * p.block_n; t /= p.tiles_col;       // column tiles fastest: neighbours share A in L2
+    c.x0 = (int)(t % p.tiles_x) * p.tw; t /= p.tiles_x;
+    c.y0 = (int)(t % p.tiles_y) * p.th; t /= p.tiles_y;
+    c.n0 = (int)t * p.tn;
+    return c;
+}
+
+template <class OT> __device__ __forceinline__ OT cvt_out(float v);
+template <> __device__ __forceinline__ float cvt_out<float>(float v) { return v; }
+template <> __device__ __forceinline__ __nv_bfloat16 cvt_out<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+template <> __device__ __forceinline__ __half cvt_out<__half>(float v) { return __float2half_rn(v); }
+template <class OT> __device__ __forceinline__ float cvt_in(OT v);
+template <> __device__ __forceinline__ float cvt_in<float>(float v) { return v; }
+template <> __device__ __forceinline__ float cvt_in<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <> __device__ __forceinline__ float cvt_in<__half>(__half v) { return __half2float(v); }
+
+// Epilogue of one 128 x block_n accumulator tile for the calling warp's 32 TMEM lanes.
+template <int A, class OT>
+__device__ __forceinline__ void epilogue_tile(const IgemmParams& p, const TileCoord tc, uint32_t tmem_tile, int lane_row) {
+    // this thread's pixel
+    const int px = lane_row % p.tw;
+    const int py = (lane_row / p.tw) % p.th;
+    const int pn = lane_row / (p.tw * p.th);
+    const int x = tc.x0 + px, y = tc.y0 + py, n = tc.n0 + pn;
+    const bool pix_ok = x < p.conv_w && y < p.conv_h && n < p.n;
+    const int total_cols = p.phases * p.o;
+    OT* out = (OT*)p.out;
+    const float alpha = p.alpha, gain = p.gain, clamp = p.clamp;
+
+    for (int c0 = 0; c0 < p.block_n; c0 += 16) {
+        float v[16];
+        tmem_ld16(tmem_tile + c0, v);       // warp-collective: executed by all lanes, valid pixel or not
+        const int g0 = tc.col0 + c0;
+        if (!pix_ok || g0 >= total_cols) continue;
+        const int phase = g0 / p.o;         // a 16-column chunk never straddles phases (o % 16 == 0 when phases > 1)
+        const int oc0 = g0 - phase * p.o;
+        const int oy = y * p.up + (phase >> 1), ox = x * p.up + (phase & 1);
+        float nz = 0.f;
+        if (p.noise) nz = __ldg(p.noise + n * p.noise_stride_n + (long long)oy * p.out_w + ox);
+        const long long base = n * p.os_n + oy * p.os_h + ox * p.os_w;
+        const int valid = min(16, p.o - oc0);
+        #pragma unroll
+        for (int j = 0; j < 16; j++) {
+            if (j < valid) {
+                const int oc = oc0 + j;
+                float r = v[j];
+                if (p.dcoef) r *= __ldg(p.dcoef + (long long)n * p.o + oc);
+                r += nz;
+                if (p.bias) r += __ldg(p.bias + oc);
+                r = act_forward<A, float>(r, alpha) * gain;
+                if (clamp >= 0.f) r = fminf(fmaxf(r, -clamp), clamp);
+                v[j] = r;
+            }
+        }
+        if (p.os_c == 1 && valid == 16 && !p.accumulate && ((base + oc0) * sizeof(OT)) % 16 == 0 && ((uintptr_t)out & 15) == 0) {
+            // channels-innermost output: 16 consecutive channels of one pixel, 128-bit stores
+            __align__(16) OT tmp[16];
+            #pragma unroll
+            for (int j = 0; j < 16; j++) tmp[j] = cvt_out<OT>(v[j]);
+            int4* dst = reinterpret_cast<int4*>(out + base + oc0);
+            const int4* src = reinterpret_cast<const int4*>(tmp);
+            #pragma unroll
+            for (int q = 0; q < (int)(16 * sizeof(OT) / 16); q++) dst[q] = src[q];
+        } else {
+            // NCHW-like output: for a fixed channel the warp's lanes are consecutive pixels of a row
+            #pragma unroll
+            for (int j = 0; j < 16; j++) {
+                if (j < valid) {
+                    OT* dst = out + base + (long long)(oc0 + j) * p.os_c;
+                    float r = v[j];
+                    if (p.accumulate) r += cvt_in<OT>(*dst);
+                    *dst = cvt_out<OT>(r);
+                }
+            }
+        }
+    }
+}
+
+template <class OT>
+__device__ __forceinline__ void epilogue_dispatch(const IgemmParams& p, const TileCoord tc, uint32_t tmem_tile, int lane_row) {
+    switch (p.act_fn) {
+        case PGPP_ACT_LINEAR:   epilogue_tile<PGPP_ACT_LINEAR, OT>(p, tc, tmem_tile, lane_row); break;
+        case PGPP_ACT_RELU:     epilogue_tile<PGPP_ACT_RELU, OT>(p, tc, tmem_tile, lane_row); break;
+        case PGPP_ACT_LRELU:    epilogue_tile<PGPP_ACT_LRELU, OT>(p, tc, tmem_tile, lane_row); break;
+        case PGPP_ACT_TANH:     epilogue_tile<PGPP_ACT_TANH, OT>(p, tc, tmem_tile, lane_row); break;
+        case PGPP_ACT_SIGMOID:  epilogue_tile<PGPP_ACT_SIGMOID, OT>(p, tc, tmem_tile, lane_row); break;
+        case PGPP_ACT_ELU:      epilogue_tile<PGPP_ACT_ELU, OT>(p, tc, tmem_tile, lane_row); break;
+        case PGPP_ACT_SELU:     epilogue_tile<PGPP_ACT_SELU, OT>(p, tc, tmem_tile, lane_row); break;
+        case PGPP_ACT_SOFTPLUS: epilogue_tile<PGPP_ACT_SOFTPLUS, OT>(p, tc, tmem_tile, lane_row); break;
+        default:                epilogue_tile<PGPP_ACT_SWISH, OT>(p, tc, tmem_tile, lane_row); break;
+    }
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const IgemmParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    // carve: [stage][A | B] (1024-byte aligned), then barriers
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t stage_bytes = p.stage_bytes;
+    const uint32_t bar_base = smem_base + p.num_stages * stage_bytes;
+    // barrier i at bar_base + 8*i : full[0..S), empty[S..2S), tmem_full[2S, 2S+2), tmem_empty[2S+2, 2S+4); then tmem ptr
+    const int S = p.num_stages;
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (S + s); };
+    auto tfull_bar = [&](int b) { return bar_base + 8u * (2 * S + b); };
+    auto tempty_bar = [&](int b) { return bar_base + 8u * (2 * S + 2 + b); };
+    const uint32_t tmem_slot = bar_base + 8u * (2 * S + 4);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (warp == 0 && elect_one()) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+        for (int s = 0; s < S; s++) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        for (int b = 0; b < 2; b++) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), 4); }   // 4 epilogue warps arrive
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(p.tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+    const int taps = p.kh * p.kw;
+    const int k_iters = taps * p.num_cb * p.products;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (elect_one()) {
+            int stage = 0; uint32_t phase = 0;
+            for (long long t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+                const TileCoord tc = decode_tile(p, t);
+                for (int tap = 0; tap < taps; tap++) {
+                    const int ky = tap / p.kw, kx = tap - ky * p.kw;
+                    const int ix = tc.x0 * p.stride + kx - p.pad_x;
+                    const int iy = tc.y0 * p.stride + ky - p.pad_y;
+                    for (int cb = 0; cb < p.num_cb; cb++) {
+                        for (int pr = 0; pr < p.products; pr++) {
+                            mbar_wait(empty_bar(stage), phase ^ 1);
+                            const uint32_t a_dst = smem_base + stage * stage_bytes;
+                            const uint32_t b_dst = a_dst + p.b_off;
+                            mbar_expect_tx(full_bar(stage), p.a_bytes + p.b_bytes);
+                            tma_load_5d(a_dst, &map_a, full_bar(stage), cb * p.kb, ix, iy, tc.n0, p.pa[pr]);
+                            tma_load_3d(b_dst, &map_b, full_bar(stage), cb * p.kb, tap * p.o_rows + tc.col0, p.pb[pr]);
+                            if (++stage == S) { stage = 0; phase ^= 1; }
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (elect_one()) {
+            int stage = 0; uint32_t phase = 0;
+            int buf = 0; uint32_t buf_phase = 0;
+            const int k_steps = p.kb / 16;                  // tcgen05.mma kind::f16 has K = 16
+            for (long long t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+                mbar_wait(tempty_bar(buf), buf_phase ^ 1);  // epilogue has drained this accumulator
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + (uint32_t)(buf * p.block_n);
+                for (int it = 0; it < k_iters; it++) {
+                    mbar_wait(full_bar(stage), phase);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_base + stage * stage_bytes;
+                    const uint32_t b_addr = a_addr + p.b_off;
+                    const uint64_t da = make_smem_desc(a_addr, p.layout_type, p.sbo_bytes);
+                    const uint64_t db = make_smem_desc(b_addr, p.layout_type, p.sbo_bytes);
+                    for (int k = 0; k < k_steps; k++) {
+                        // advance 16 elements (32 bytes) along K inside the swizzle row: +2 in the >>4 address field
+                        umma_bf16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), p.idesc, (it | k) != 0);
+                    }
+                    umma_commit(empty_bar(stage));          // smem slot reusable once these MMAs retire
+                    if (++stage == S) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(tfull_bar(buf));                // accumulator complete -> epilogue
+                if (++buf == 2) { buf = 0; buf_phase ^= 1; }
+            }
+        }
+    } else {
+        // ===================== epilogue warps =====================
+        const int quarter = warp & 3;                       // TMEM lane quarter this warp may access
+        const int lane_row = quarter * 32 + lane;
+        int buf = 0; uint32_t buf_phase = 0;
+        for (long long t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+            const TileCoord tc = decode_tile(p, t);
+            mbar_wait(tfull_bar(buf), buf_phase);
+            tc_fence_after();
+            const uint32_t tmem_tile = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * p.block_n);
+            if (p.out_dtype == PGPP_F32) epilogue_dispatch<float>(p, tc, tmem_tile, lane_row);
+            else if (p.out_dtype == PGPP_BF16) epilogue_dispatch<__nv_bfloat16>(p, tc, tmem_tile, lane_row);
+            else epilogue_dispatch<__half>(p, tc, tmem_tile, lane_row);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar(buf));
+            if (++buf == 2) { buf = 0; buf_phase ^= 1; }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* sym = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPointByVersion("cuTensorMapEncodeTiled", &sym, 12000, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            return nullptr;
+        fn = (EncodeTiledFn)sym;
+    }
+    return fn;
+}
+
+static int pow2_ceil(int v) { int r = 1; while (r < v) r <<= 1; return r; }
+
+} // namespace pgpp
+
+extern "C" int pgpp_conv2d_igemm(const pgpp_conv_desc* d, void* stream) {
+    using namespace pgpp;
+    PGPP_REQUIRE(d != nullptr, "desc is NULL");
+    PGPP_REQUIRE(d->act && d->wgt && d->out, "act, wgt and out must be device pointers");
+    PGPP_REQUIRE(d->n >= 1 && d->h >= 1 && d->w >= 1 && d->conv_h >= 1 && d->conv_w >= 1, "empty problem");
+    PGPP_REQUIRE(d->c_pad >= 16 && d->c_pad % 16 == 0, "c_pad must be a positive multiple of 16");
+    PGPP_REQUIRE(d->kh >= 1 && d->kw >= 1, "filter must be at least 1x1");
+    PGPP_REQUIRE(d->stride == 1 || d->stride == 2, "stride must be 1 or 2");
+    PGPP_REQUIRE(d->phases == 1 || d->phases == 4, "phases must be 1 or 4");
+    PGPP_REQUIRE(d->phases == 1 || d->o % 16 == 0, "polyphase form needs out channels % 16 == 0");
+    PGPP_REQUIRE(d->block_n == 16 || d->block_n == 32 || d->block_n == 64 || d->block_n == 128 || d->block_n == 256,
+                 "block_n must be 16, 32, 64, 128 or 256");
+    PGPP_REQUIRE(d->o >= 1 && d->o_rows >= d->phases * d->o && d->o_rows % d->block_n == 0, "o_rows must cover phases*o and be a multiple of block_n");
+    PGPP_REQUIRE(d->products == 1 || d->products == 3 || d->products == 6, "products must be 1, 3 or 6");
+    const int need_parts = d->products == 1 ? 1 : (d->products == 3 ? 2 : 3);
+    PGPP_REQUIRE(d->a_parts >= need_parts && d->b_parts >= need_parts, "operand parts do not cover the requested products");
+    PGPP_REQUIRE(d->out_dtype == PGPP_F32 || d->out_dtype == PGPP_BF16 || d->out_dtype == PGPP_F16, "unsupported output dtype");
+    PGPP_REQUIRE(d->act_fn >= 1 && d->act_fn <= 9, "no CUDA kernel found for the specified activation func");
+    PGPP_REQUIRE(((uintptr_t)d->act & 15) == 0 && ((uintptr_t)d->wgt & 15) == 0, "packed operands must be 16-byte aligned");
+    const int up = d->phases == 4 ? 2 : 1;
+    PGPP_REQUIRE(d->out_h == d->conv_h * up && d->out_w == d->conv_w * up, "output size does not match the conv grid");
+
+    EncodeTiledFn encode = get_encode_fn();
+    if (!encode) { set_error("cuTensorMapEncodeTiled is not available from the driver"); return PGPP_ERR_CUDA; }
+
+    IgemmParams p;
+    p.n = d->n; p.h = d->h; p.w = d->w; p.conv_h = d->conv_h; p.conv_w = d->conv_w;
+    p.kh = d->kh; p.kw = d->kw; p.pad_y = d->pad_y; p.pad_x = d->pad_x; p.stride = d->stride;
+    p.kb = (d->c_pad % 64 == 0) ? 64 : ((d->c_pad % 32 == 0) ? 32 : 16);
+    p.num_cb = d->c_pad / p.kb;
+    p.products = d->products;
+    static const int PA[6] = {0, 0, 1, 1, 0, 2}, PB[6] = {0, 1, 0, 1, 2, 0};
+    if (d->products == 3) { p.pa[0] = 0; p.pb[0] = 0; p.pa[1] = 0; p.pb[1] = 1; p.pa[2] = 1; p.pb[2] = 0; }
+    else for (int i = 0; i < 6; i++) { p.pa[i] = PA[i]; p.pb[i] = PB[i]; }
+    p.o = d->o; p.phases = d->phases; p.o_rows = d->o_rows; p.block_n = d->block_n; p.up = up;
+    // pixel tile: TW x TH x TN = 128
+    p.tw = pow2_ceil(d->conv_w); if (p.tw > kTileM) p.tw = kTileM;
+    p.th = pow2_ceil(d->conv_h); if (p.th > kTileM / p.tw) p.th = kTileM / p.tw;
+    p.tn = kTileM / (p.tw * p.th);
+    p.tiles_x = (d->conv_w + p.tw - 1) / p.tw;
+    p.tiles_y = (d->conv_h + p.th - 1) / p.th;
+    p.tiles_n = (d->n + p.tn - 1) / p.tn;
+    p.tiles_col = (d->phases * d->o + d->block_n - 1) / d->block_n;
+    p.total_tiles = (long long)p.tiles_x * p.tiles_y * p.tiles_n * p.tiles_col;
+    const unsigned row_bytes = (unsigned)p.kb * 2;
+    p.a_bytes = kTileM * row_bytes;
+    p.b_bytes = (unsigned)d->block_n * row_bytes;
+    // keep every operand buffer 1024-byte aligned (swizzle atom alignment)
+    const unsigned a_al = (p.a_bytes + 1023u) & ~1023u, b_al = (p.b_bytes + 1023u) & ~1023u;
+    p.b_off = a_al;
+    p.stage_bytes = a_al + b_al;
+    p.layout_type = row_bytes == 128 ? 2u : (row_bytes == 64 ? 4u : 6u);   // SWIZZLE_128B / 64B / 32B
+    p.sbo_bytes = 8 * row_bytes;
+    // instruction descriptor (cute/arch/mma_sm100_desc.hpp InstrDescriptor): fp32 accum, bf16 A/B, K-major, M = 128
+    p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((unsigned)(d->block_n >> 3) << 17) | ((unsigned)(kTileM >> 4) << 24);
+    unsigned cols = (unsigned)pow2_ceil(2 * d->block_n); if (cols < 32) cols = 32;
+    p.tmem_cols = cols;
+    p.dcoef = d->dcoef; p.noise = d->noise; p.noise_stride_n = d->noise_stride_n; p.bias = d->bias;
+    p.act_fn = d->act_fn; p.alpha = d->alpha; p.gain = d->gain; p.clamp = d->clamp;
+    p.out = d->out; p.out_dtype = d->out_dtype; p.out_h = d->out_h; p.out_w = d->out_w;
+    p.os_n = d->out_stride[0]; p.os_c = d->out_stride[1]; p.os_h = d->out_stride[2]; p.os_w = d->out_stride[3];
+    p.accumulate = d->accumulate;
+
+    // stage count from the shared-memory budget
+    const unsigned stage_bytes = p.stage_bytes;
+    const unsigned budget = 200 * 1024;
+    int stages = (int)(budget / stage_bytes);
+    if (stages > kMaxStages) stages = kMaxStages;
+    if (stages < 2) { set_error("tile does not fit shared memory"); return PGPP_ERR_UNSUPPORTED; }
+    p.num_stages = stages;
+    const size_t smem_bytes = 1024 + (size_t)stages * stage_bytes + 8 * (2 * stages + 4) + 16;
+
+    // tensor maps
+    CUtensorMap map_a, map_b;
+    {
+        const cuuint64_t dims[5] = {(cuuint64_t)d->c_pad, (cuuint64_t)d->w, (cuuint64_t)d->h, (cuuint64_t)d->n, (cuuint64_t)d->a_parts};
+        const cuuint64_t strides[4] = {(cuuint64_t)d->c_pad * 2, (cuuint64_t)d->c_pad * 2 * d->w, (cuuint64_t)d->c_pad * 2 * d->w * d->h,
+                                       (cuuint64_t)d->c_pad * 2 * d->w * d->h * d->n};
+        const cuuint32_t box[5] = {(cuuint32_t)p.kb, (cuuint32_t)(p.tw * d->stride), (cuuint32_t)(p.th * d->stride), (cuuint32_t)p.tn, 1};
+        const cuuint32_t estr[5] = {1, (cuuint32_t)d->stride, (cuuint32_t)d->stride, 1, 1};
+        const CUtensorMapSwizzle sw = row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+        CUresult r = encode(&map_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(d->act), dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(activations) failed with CUresult %d", (int)r); return PGPP_ERR_CUDA; }
+        const cuuint64_t wdims[3] = {(cuuint64_t)d->c_pad, (cuuint64_t)d->o_rows * d->kh * d->kw, (cuuint64_t)d->b_parts};
+        const cuuint64_t wstrides[2] = {(cuuint64_t)d->c_pad * 2, (cuuint64_t)d->c_pad * 2 * d->o_rows * d->kh * d->kw};
+        const cuuint32_t wbox[3] = {(cuuint32_t)p.kb, (cuuint32_t)d->block_n, 1};
+        const cuuint32_t westr[3] = {1, 1, 1};
+        r = encode(&map_b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(d->wgt), wdims, wstrides, wbox, westr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(weights) failed with CUresult %d", (int)r); return PGPP_ERR_CUDA; }
+    }
+    PGPP_CUDA_OK(cudaFuncSetAttribute(igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    long long grid = p.total_tiles;
+    const int sms = sm_count();
+    if (grid > sms) grid = sms;
+    igemm_kernel<<<(unsigned)grid, kThreads, smem_bytes, (cudaStream_t)stream>>>(map_a, map_b, p);
+    count_launch();
+    PGPP_CUDA_OK(cudaGetLastError());
+    return PGPP_OK;
+}

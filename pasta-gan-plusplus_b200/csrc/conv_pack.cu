@@ -1,0 +1,162 @@
+// Operand preparation for the tensor-core convolution (sm_100a).
+//   pgpp_pack_activations : any-layout x (* per-(n,c) scale) -> channels-innermost bf16 parts
+//   pgpp_modconv_demod_coefs : d[n,o] = rsqrt(sum (w*s)^2 + eps)     (training/networks.py:64-68)
+// Both are small HBM-bound helpers; the heavy lifting is conv_igemm.cu.
+#include "common.cuh"
+
+namespace pgpp {
+
+struct PackArgs {
+    const void* x; const float* scale; __nv_bfloat16* out;
+    int n, c, h, w, c_pad, parts;
+    long long s_n, s_c, s_h, s_w;
+    long long part_stride;      // elements between parts = n*h*w*c_pad
+};
+
+__device__ __forceinline__ void split_store(float v, __nv_bfloat16* dst, long long part_stride, int parts) {
+    // part p = bf16(v - sum of earlier parts): 8, 16, 24 significand bits for 1, 2, 3 parts
+    #pragma unroll 3
+    for (int p = 0; p < parts; p++) {
+        const __nv_bfloat16 q = __float2bfloat16_rn(v);
+        dst[p * part_stride] = q;
+        v -= __bfloat162float(q);
+    }
+}
+
+// x has unit stride along W (NCHW-like): transpose 64 channels x 32 pixels through shared memory so
+// that both the read (along W) and the write (along C) are coalesced.
+template <class T>
+__global__ void __launch_bounds__(256) pack_nchw_kernel(PackArgs p, int w_tiles, int c_tiles) {
+    __shared__ float tile[64][33];
+    long long b = blockIdx.x;
+    const int wt = (int)(b % w_tiles); b /= w_tiles;
+    const int ct = (int)(b % c_tiles); b /= c_tiles;
+    const int y = (int)(b % p.h);
+    const int n = (int)(b / p.h);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int x0 = wt * 32, c0 = ct * 64;
+    const T* src = (const T*)p.x + n * p.s_n + y * p.s_h;
+    #pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const int c = c0 + warp * 8 + i;
+        float v = 0.f;
+        if (c < p.c && x0 + lane < p.w) {
+            v = (float)to_acc<T>(src[c * p.s_c + (x0 + lane)]);
+            if (p.scale) v *= p.scale[n * p.c + c];
+        }
+        tile[warp * 8 + i][lane] = v;
+    }
+    __syncthreads();
+    // each warp writes 4 pixels; a lane covers channels 2*lane, 2*lane+1 of the 64-channel slab
+    #pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const int px = warp * 4 + i;
+        if (x0 + px >= p.w) continue;
+        __nv_bfloat16* dst = p.out + (((long long)n * p.h + y) * p.w + (x0 + px)) * p.c_pad + c0;
+        #pragma unroll
+        for (int j = 0; j < 2; j++) {
+            const int cc = 2 * lane + j;
+            if (c0 + cc < p.c_pad) split_store(tile[cc][px], dst + cc, p.part_stride, p.parts);
+        }
+    }
+}
+
+// any strides (channels_last inputs are coalesced here): one thread per (pixel, channel)
+template <class T>
+__global__ void __launch_bounds__(256) pack_generic_kernel(PackArgs p, long long total) {
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(e % p.c_pad);
+        long long r = e / p.c_pad;
+        const int x = (int)(r % p.w); r /= p.w;
+        const int y = (int)(r % p.h);
+        const int n = (int)(r / p.h);
+        float v = 0.f;
+        if (c < p.c) {
+            v = (float)to_acc<T>(((const T*)p.x)[n * p.s_n + c * p.s_c + y * p.s_h + x * p.s_w]);
+            if (p.scale) v *= p.scale[n * p.c + c];
+        }
+        split_store(v, p.out + e, p.part_stride, p.parts);
+    }
+}
+
+template <class T>
+static int launch_pack(const PackArgs& p, cudaStream_t stream) {
+    if (p.s_w == 1 && p.s_c != 1) {
+        const int w_tiles = (p.w + 31) / 32, c_tiles = (p.c_pad + 63) / 64;
+        const long long blocks = (long long)w_tiles * c_tiles * p.h * p.n;
+        PGPP_REQUIRE(blocks <= 2147483647LL, "activation tensor too large to pack");
+        pack_nchw_kernel<T><<<(unsigned)blocks, 256, 0, stream>>>(p, w_tiles, c_tiles);
+    } else {
+        const long long total = (long long)p.n * p.h * p.w * p.c_pad;
+        long long blocks = (total + 255) / 256;
+        const long long cap = (long long)sm_count() * 16;
+        if (blocks > cap) blocks = cap;
+        pack_generic_kernel<T><<<(unsigned)blocks, 256, 0, stream>>>(p, total);
+    }
+    count_launch();
+    PGPP_CUDA_OK(cudaGetLastError());
+    return PGPP_OK;
+}
+
+// one CTA per output channel: W2[i] = sum_t w[o,i,t]^2 in shared memory, then one warp per sample
+__global__ void __launch_bounds__(256) demod_kernel(const float* __restrict__ w, const float* __restrict__ s,
+                                                    float* __restrict__ d, int n, int o, int ic, int taps, float eps) {
+    extern __shared__ float w2[];
+    const int oc = blockIdx.x;
+    const float* wp = w + (long long)oc * ic * taps;
+    for (int i = threadIdx.x; i < ic; i += blockDim.x) {
+        float a = 0.f;
+        for (int t = 0; t < taps; t++) { const float v = wp[i * taps + t]; a = fmaf(v, v, a); }
+        w2[i] = a;
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int b = warp; b < n; b += blockDim.x / 32) {
+        float a = 0.f;
+        for (int i = lane; i < ic; i += 32) { const float sv = s[(long long)b * ic + i]; a = fmaf(sv * sv, w2[i], a); }
+        #pragma unroll
+        for (int m = 16; m > 0; m >>= 1) a += __shfl_xor_sync(0xffffffffu, a, m);
+        if (lane == 0) d[(long long)b * o + oc] = rsqrtf(a + eps);
+    }
+}
+
+} // namespace pgpp
+
+extern "C" int pgpp_pack_activations(const void* x, const int64_t size[4], const int64_t stride[4], int dtype,
+                                     const float* scale, void* out, int c_pad, int parts, void* stream) {
+    using namespace pgpp;
+    PGPP_REQUIRE(x && out, "x and out must be device pointers");
+    PGPP_REQUIRE(parts >= 1 && parts <= 3, "parts must be 1, 2 or 3");
+    PGPP_REQUIRE(c_pad >= size[1] && c_pad % 16 == 0, "c_pad must be a multiple of 16 and >= C");
+    PackArgs p;
+    p.x = x; p.scale = scale; p.out = (__nv_bfloat16*)out;
+    p.n = (int)size[0]; p.c = (int)size[1]; p.h = (int)size[2]; p.w = (int)size[3];
+    p.c_pad = c_pad; p.parts = parts;
+    p.s_n = stride[0]; p.s_c = stride[1]; p.s_h = stride[2]; p.s_w = stride[3];
+    p.part_stride = (long long)p.n * p.h * p.w * c_pad;
+    if (p.part_stride == 0) return PGPP_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    switch (dtype) {
+        case PGPP_F32:  return launch_pack<float>(p, s);
+        case PGPP_F16:  return launch_pack<__half>(p, s);
+        case PGPP_BF16: return launch_pack<__nv_bfloat16>(p, s);
+        case PGPP_F64:  return launch_pack<double>(p, s);
+    }
+    set_error("unsupported dtype %d", dtype);
+    return PGPP_ERR_UNSUPPORTED;
+}
+
+extern "C" int pgpp_modconv_demod_coefs(const float* w, const float* s, float* d, int n, int o, int i, int taps,
+                                        float eps, void* stream) {
+    using namespace pgpp;
+    PGPP_REQUIRE(w && s && d, "w, s and d must be device pointers");
+    PGPP_REQUIRE(n >= 1 && o >= 1 && i >= 1 && taps >= 1, "empty problem");
+    PGPP_REQUIRE((size_t)i * sizeof(float) <= 200 * 1024, "too many input channels");
+    const size_t smem = (size_t)i * sizeof(float);
+    if (smem > 48 * 1024)
+        PGPP_CUDA_OK(cudaFuncSetAttribute(demod_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    demod_kernel<<<o, 256, smem, (cudaStream_t)stream>>>(w, s, d, n, o, i, taps, eps);
+    count_launch();
+    PGPP_CUDA_OK(cudaGetLastError());
+    return PGPP_OK;
+}

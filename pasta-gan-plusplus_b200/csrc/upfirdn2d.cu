@@ -1,0 +1,240 @@
+// upfirdn2d for sm_100a.  Replaces torch_utils/ops/upfirdn2d.cu:29-341 + upfirdn2d.cpp:16-94.
+//
+//   out[n,c,oy,ox] = gain * sum_{jy,jx} z[oy*downy + jy - pady0, ox*downx + jx - padx0] * k[jy,jx]
+//   z = x with (up-1) zeros inserted after every sample, zero outside; k = f flipped unless `flip`.
+//
+// Two kernels:
+//   * fir_tile_kernel  - the shapes that carry the traffic in the generator (up = down = 1, filter
+//     up to 4x4, unit stride along W): shared-memory halo tile, each thread produces a 4x4 patch of
+//     outputs from a sliding window of 128-bit shared loads with the taps held in registers, and
+//     writes 128-bit rows.  HBM-bound; one read and one write per element.
+//   * generic_kernel   - any up/down/pad/filter size/strides (channels_last included); one thread per
+//     4 consecutive outputs, taps from shared memory, input through the read-only path.
+#include "common.cuh"
+
+namespace pgpp {
+
+struct UpfirdnArgs {
+    const void* x; const float* f; void* y;
+    int n, c, ih, iw, oh, ow;
+    long long xs_n, xs_c, xs_h, xs_w, ys_n, ys_c, ys_h, ys_w;
+    int fw, fh; long long fs_x, fs_y;
+    int upx, upy, downx, downy, padx0, pady0, flip;
+    float gain;
+};
+
+__device__ __forceinline__ int floor_div_i(int a, int b) {   // b > 0
+    int q = a / b;
+    return (a % b != 0 && a < 0) ? q - 1 : q;
+}
+
+// ------------------------------------------------------------------------------------------
+constexpr int MAX_TAPS = 32;     // per axis, generic kernel (shared-memory filter)
+
+template <class T>
+__global__ void __launch_bounds__(256) generic_kernel(UpfirdnArgs p, long long total_quads, int quads_per_row) {
+    typedef typename Acc<T>::type S;
+    __shared__ S sk[MAX_TAPS * MAX_TAPS];
+    for (int t = threadIdx.x; t < p.fw * p.fh; t += blockDim.x) {
+        const int jy = t / p.fw, jx = t - jy * p.fw;
+        const int sy = p.flip ? jy : p.fh - 1 - jy, sx = p.flip ? jx : p.fw - 1 - jx;
+        sk[t] = (S)p.f[sy * p.fs_y + sx * p.fs_x] * (S)p.gain;
+    }
+    __syncthreads();
+    const T* x = (const T*)p.x;
+    T* y = (T*)p.y;
+    for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < total_quads; q += (long long)gridDim.x * blockDim.x) {
+        const int qx = (int)(q % quads_per_row);
+        long long r = q / quads_per_row;
+        const int oy = (int)(r % p.oh); r /= p.oh;
+        const int c = (int)(r % p.c);
+        const int n = (int)(r / p.c);
+        const T* xp = x + n * p.xs_n + c * p.xs_c;
+        T* yp = y + n * p.ys_n + c * p.ys_c + oy * p.ys_h;
+        // rows: taps jy with (base_y + jy) % upy == 0
+        const int base_y = oy * p.downy - p.pady0;
+        int jy0 = (-base_y) % p.upy; if (jy0 < 0) jy0 += p.upy;
+        const int iy0 = (base_y + jy0) / p.upy;     // exact division
+        #pragma unroll 1
+        for (int v = 0; v < 4; v++) {
+            const int ox = qx * 4 + v;
+            if (ox >= p.ow) break;
+            const int base_x = ox * p.downx - p.padx0;
+            int jx0 = (-base_x) % p.upx; if (jx0 < 0) jx0 += p.upx;
+            const int ix0 = (base_x + jx0) / p.upx;
+            S acc = 0;
+            for (int jy = jy0, iy = iy0; jy < p.fh; jy += p.upy, iy++) {
+                if (iy < 0 || iy >= p.ih) continue;
+                const T* row = xp + iy * p.xs_h;
+                for (int jx = jx0, ix = ix0; jx < p.fw; jx += p.upx, ix++) {
+                    if (ix < 0 || ix >= p.iw) continue;
+                    acc += to_acc<T>(__ldg(row + ix * p.xs_w)) * sk[jy * p.fw + jx];
+                }
+            }
+            yp[ox * p.ys_w] = from_acc<T>(acc);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// up = down = 1, fw, fh <= 4, x/y unit stride along W.
+constexpr int TILE_W = 128, TILE_H = 32, HALO = 3;
+constexpr int SM_W = TILE_W + 4;        // 131 needed; 132 keeps rows 16-byte aligned
+constexpr int SM_H = TILE_H + HALO;
+
+template <class T>
+__global__ void __launch_bounds__(256) fir_tile_kernel(UpfirdnArgs p, int tiles_x, int tiles_y, long long total_tiles) {
+    typedef float S;
+    __shared__ __align__(16) S sx[SM_H][SM_W];
+    // taps in registers, zero-padded to 4x4, already flipped and scaled by gain
+    S k[4][4];
+    #pragma unroll
+    for (int jy = 0; jy < 4; jy++)
+        #pragma unroll
+        for (int jx = 0; jx < 4; jx++) {
+            S v = 0;
+            if (jy < p.fh && jx < p.fw) {
+                const int sy = p.flip ? jy : p.fh - 1 - jy, sxx = p.flip ? jx : p.fw - 1 - jx;
+                v = p.f[sy * p.fs_y + sxx * p.fs_x] * p.gain;
+            }
+            k[jy][jx] = v;
+        }
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;      // 32 x 8 threads, 4 x 4 outputs each
+    const T* x = (const T*)p.x;
+    T* y = (T*)p.y;
+    const bool vec_store = (sizeof(T) == 4) && ((p.ys_h & 3) == 0) && ((p.ys_c & 3) == 0) && ((p.ys_n & 3) == 0) &&
+                           (((uintptr_t)p.y & 15) == 0);
+
+    for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const int bx = (int)(t % tiles_x);
+        long long r = t / tiles_x;
+        const int by = (int)(r % tiles_y); r /= tiles_y;
+        const int c = (int)(r % p.c);
+        const int n = (int)(r / p.c);
+        const int ox0 = bx * TILE_W, oy0 = by * TILE_H;
+        const int ix0 = ox0 - p.padx0, iy0 = oy0 - p.pady0;
+        const T* xp = x + n * p.xs_n + c * p.xs_c;
+        __syncthreads();        // previous tile fully consumed
+        for (int e = threadIdx.x; e < SM_H * SM_W; e += 256) {
+            const int ry = e / SM_W, rx = e - ry * SM_W;
+            const int iy = iy0 + ry, ix = ix0 + rx;
+            S v = 0;
+            if (iy >= 0 && iy < p.ih && ix >= 0 && ix < p.iw) v = to_acc<T>(__ldg(xp + iy * p.xs_h + ix));
+            sx[ry][rx] = v;
+        }
+        __syncthreads();
+        S acc[4][4];
+        #pragma unroll
+        for (int a = 0; a < 4; a++)
+            #pragma unroll
+            for (int b = 0; b < 4; b++) acc[a][b] = 0;
+        const int cx = tx * 4, cy = ty * 4;
+        #pragma unroll
+        for (int ry = 0; ry < 4 + HALO; ry++) {
+            const float4 lo = *reinterpret_cast<const float4*>(&sx[cy + ry][cx]);
+            const float4 hi = *reinterpret_cast<const float4*>(&sx[cy + ry][cx + 4]);
+            const S in[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+            #pragma unroll
+            for (int a = 0; a < 4; a++) {
+                const int jy = ry - a;          // filter row feeding output row a
+                if (jy < 0 || jy > 3) continue;
+                #pragma unroll
+                for (int b = 0; b < 4; b++)
+                    #pragma unroll
+                    for (int jx = 0; jx < 4; jx++) acc[a][b] = fmaf(in[b + jx], k[jy][jx], acc[a][b]);
+            }
+        }
+        T* yp = y + n * p.ys_n + c * p.ys_c;
+        #pragma unroll
+        for (int a = 0; a < 4; a++) {
+            const int oy = oy0 + cy + a, ox = ox0 + cx;
+            if (oy >= p.oh || ox >= p.ow) continue;
+            T* dst = yp + (long long)oy * p.ys_h + ox;
+            if (vec_store && ox + 3 < p.ow) {
+                float4 o4 = make_float4(acc[a][0], acc[a][1], acc[a][2], acc[a][3]);
+                __stcs(reinterpret_cast<float4*>(dst), o4);
+            } else {
+                #pragma unroll
+                for (int b = 0; b < 4; b++) if (ox + b < p.ow) dst[b] = from_acc<T>(acc[a][b]);
+            }
+        }
+    }
+}
+
+template <class T>
+static int launch_upfirdn(const UpfirdnArgs& p, cudaStream_t stream) {
+    const bool tile_ok = p.upx == 1 && p.upy == 1 && p.downx == 1 && p.downy == 1 && p.fw <= 4 && p.fh <= 4 &&
+                         p.xs_w == 1 && p.ys_w == 1 && sizeof(T) <= 4;
+    if (tile_ok) {
+        const int tiles_x = (p.ow + TILE_W - 1) / TILE_W, tiles_y = (p.oh + TILE_H - 1) / TILE_H;
+        const long long total = (long long)tiles_x * tiles_y * p.c * p.n;
+        long long blocks = total;
+        const long long cap = (long long)sm_count() * 6;
+        if (blocks > cap) blocks = cap;
+        fir_tile_kernel<T><<<(unsigned)blocks, 256, 0, stream>>>(p, tiles_x, tiles_y, total);
+    } else {
+        const int quads_per_row = (p.ow + 3) / 4;
+        const long long total = (long long)quads_per_row * p.oh * p.c * p.n;
+        long long blocks = (total + 255) / 256;
+        const long long cap = (long long)sm_count() * 8;
+        if (blocks > cap) blocks = cap;
+        generic_kernel<T><<<(unsigned)blocks, 256, 0, stream>>>(p, total, quads_per_row);
+    }
+    count_launch();
+    PGPP_CUDA_OK(cudaGetLastError());
+    return PGPP_OK;
+}
+
+template <>
+int launch_upfirdn<double>(const UpfirdnArgs& p, cudaStream_t stream) {
+    const int quads_per_row = (p.ow + 3) / 4;
+    const long long total = (long long)quads_per_row * p.oh * p.c * p.n;
+    long long blocks = (total + 255) / 256;
+    const long long cap = (long long)sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    generic_kernel<double><<<(unsigned)blocks, 256, 0, stream>>>(p, total, quads_per_row);
+    count_launch();
+    PGPP_CUDA_OK(cudaGetLastError());
+    return PGPP_OK;
+}
+
+} // namespace pgpp
+
+extern "C" int pgpp_upfirdn2d(const void* x, const float* f, void* y,
+                              const int64_t in_size[4], const int64_t in_stride[4],
+                              const int64_t out_size[4], const int64_t out_stride[4],
+                              int fw, int fh, int64_t f_stride_x, int64_t f_stride_y,
+                              int upx, int upy, int downx, int downy, int padx0, int pady0,
+                              int flip, float gain, int dtype, void* stream) {
+    using namespace pgpp;
+    PGPP_REQUIRE(x && f && y, "x, f and y must be device pointers");
+    PGPP_REQUIRE(fw >= 1 && fh >= 1, "f must be at least 1x1");
+    PGPP_REQUIRE(fw <= MAX_TAPS && fh <= MAX_TAPS, "f is too large (at most %d taps per axis)", MAX_TAPS);
+    PGPP_REQUIRE(upx >= 1 && upy >= 1, "upsampling factor must be at least 1");
+    PGPP_REQUIRE(downx >= 1 && downy >= 1, "downsampling factor must be at least 1");
+    PGPP_REQUIRE(out_size[2] >= 1 && out_size[3] >= 1, "output must be at least 1x1");
+    PGPP_REQUIRE(in_size[0] == out_size[0] && in_size[1] == out_size[1], "batch/channel mismatch between x and y");
+    long long in_numel = 1, out_numel = 1;
+    for (int i = 0; i < 4; i++) { in_numel *= in_size[i]; out_numel *= out_size[i]; }
+    PGPP_REQUIRE(in_numel <= 2147483647LL, "x is too large");
+    PGPP_REQUIRE(out_numel <= 2147483647LL, "output is too large");
+    if (in_numel == 0 || out_numel == 0) return PGPP_OK;
+    UpfirdnArgs p;
+    p.x = x; p.f = f; p.y = y;
+    p.n = (int)in_size[0]; p.c = (int)in_size[1]; p.ih = (int)in_size[2]; p.iw = (int)in_size[3];
+    p.oh = (int)out_size[2]; p.ow = (int)out_size[3];
+    p.xs_n = in_stride[0]; p.xs_c = in_stride[1]; p.xs_h = in_stride[2]; p.xs_w = in_stride[3];
+    p.ys_n = out_stride[0]; p.ys_c = out_stride[1]; p.ys_h = out_stride[2]; p.ys_w = out_stride[3];
+    p.fw = fw; p.fh = fh; p.fs_x = f_stride_x; p.fs_y = f_stride_y;
+    p.upx = upx; p.upy = upy; p.downx = downx; p.downy = downy; p.padx0 = padx0; p.pady0 = pady0;
+    p.flip = flip ? 1 : 0; p.gain = gain;
+    cudaStream_t s = (cudaStream_t)stream;
+    switch (dtype) {
+        case PGPP_F32:  return launch_upfirdn<float>(p, s);
+        case PGPP_F16:  return launch_upfirdn<__half>(p, s);
+        case PGPP_BF16: return launch_upfirdn<__nv_bfloat16>(p, s);
+        case PGPP_F64:  return launch_upfirdn<double>(p, s);
+    }
+    set_error("unsupported dtype %d", dtype);
+    return PGPP_ERR_UNSUPPORTED;
+}

@@ -1,0 +1,226 @@
+"""Plugin loader: hands out the PREBUILT sm_100a C-ABI library instead of JIT-compiling sources.
+
+Replaces the reference's torch_utils/custom_ops.py:46-124 (ninja JIT + importlib; broken on
+torch 2.x).  `get_plugin(name)` keeps its name and caching behaviour but returns a thin object whose
+methods have the signatures of the reference's pybind functions (bias_act.cpp:32, upfirdn2d.cpp:16)
+and forward to `extern "C"` entry points of lib/libpgpp_sm100a.so (include/pgpp.h) through ctypes.
+There is no fallback: if the library is missing or the call fails, a RuntimeError is raised.
+"""
+import ctypes
+import os
+
+import torch
+
+verbosity = 'brief'     # 'none', 'brief', 'full' -- kept for compatibility (custom_ops.py:23)
+
+_LIB_PATH = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'lib', 'libpgpp_sm100a.so')
+_lib = None
+_cached_plugins = dict()
+
+_DTYPES = {torch.float32: 0, torch.float16: 1, torch.bfloat16: 2, torch.float64: 3}
+
+c_i64x4 = ctypes.c_int64 * 4
+
+
+class ConvDesc(ctypes.Structure):
+    """mirror of pgpp_conv_desc (include/pgpp.h)"""
+    _fields_ = [
+        ('act', ctypes.c_void_p), ('wgt', ctypes.c_void_p),
+        ('a_parts', ctypes.c_int32), ('b_parts', ctypes.c_int32),
+        ('n', ctypes.c_int32), ('h', ctypes.c_int32), ('w', ctypes.c_int32), ('c_pad', ctypes.c_int32),
+        ('kh', ctypes.c_int32), ('kw', ctypes.c_int32),
+        ('pad_y', ctypes.c_int32), ('pad_x', ctypes.c_int32),
+        ('stride', ctypes.c_int32),
+        ('conv_h', ctypes.c_int32), ('conv_w', ctypes.c_int32),
+        ('o', ctypes.c_int32), ('phases', ctypes.c_int32), ('o_rows', ctypes.c_int32), ('block_n', ctypes.c_int32),
+        ('products', ctypes.c_int32),
+        ('dcoef', ctypes.c_void_p), ('noise', ctypes.c_void_p), ('noise_stride_n', ctypes.c_int64), ('bias', ctypes.c_void_p),
+        ('act_fn', ctypes.c_int32), ('alpha', ctypes.c_float), ('gain', ctypes.c_float), ('clamp', ctypes.c_float),
+        ('out', ctypes.c_void_p), ('out_dtype', ctypes.c_int32), ('out_h', ctypes.c_int32), ('out_w', ctypes.c_int32),
+        ('out_stride', ctypes.c_int64 * 4),
+        ('accumulate', ctypes.c_int32),
+    ]
+
+
+def library_path():
+    return _LIB_PATH
+
+
+def load_library():
+    """dlopen the prebuilt library and declare the C prototypes.  Raises if it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.isfile(_LIB_PATH):
+        raise RuntimeError(f'{_LIB_PATH} not found: build it with `python -c "import __graft_entry__ as g; g.build()"` '
+                           f'(or `make -C pasta-gan-plusplus_b200/csrc`). There is no fallback implementation.')
+    lib = ctypes.CDLL(_LIB_PATH)
+    vp, i64, i32, f32 = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_float
+    lib.pgpp_version.restype = i32
+    lib.pgpp_last_error.restype = ctypes.c_char_p
+    lib.pgpp_launch_count.restype = i64
+    lib.pgpp_bias_act.restype = i32
+    lib.pgpp_bias_act.argtypes = [vp, vp, vp, vp, vp, vp, i64, i64, i64, i32, i32, i32, f32, f32, f32, vp]
+    lib.pgpp_upfirdn2d.restype = i32
+    lib.pgpp_upfirdn2d.argtypes = [vp, vp, vp, c_i64x4, c_i64x4, c_i64x4, c_i64x4, i32, i32, i64, i64,
+                                   i32, i32, i32, i32, i32, i32, i32, f32, i32, vp]
+    lib.pgpp_modconv_demod_coefs.restype = i32
+    lib.pgpp_modconv_demod_coefs.argtypes = [vp, vp, vp, i32, i32, i32, i32, f32, vp]
+    lib.pgpp_pack_activations.restype = i32
+    lib.pgpp_pack_activations.argtypes = [vp, c_i64x4, c_i64x4, i32, vp, vp, i32, i32, vp]
+    lib.pgpp_conv2d_igemm.restype = i32
+    lib.pgpp_conv2d_igemm.argtypes = [ctypes.POINTER(ConvDesc), vp]
+    _lib = lib
+    return lib
+
+
+EXPORTED_SYMBOLS = ('pgpp_version', 'pgpp_last_error', 'pgpp_launch_count', 'pgpp_bias_act', 'pgpp_upfirdn2d',
+                    'pgpp_modconv_demod_coefs', 'pgpp_pack_activations', 'pgpp_conv2d_igemm')
+
+
+def launch_count():
+    return int(load_library().pgpp_launch_count())
+
+
+def _check(status):
+    if status != 0:
+        raise RuntimeError(load_library().pgpp_last_error().decode())
+
+
+def _torch_check(cond, msg):
+    if not cond:
+        raise RuntimeError(msg)
+
+
+def _stream(t):
+    return ctypes.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None and t.numel() > 0 else None
+
+
+def _same_layout(a, b):
+    if a.dim() != b.dim():
+        return False
+    return all(sa == sb and (sa < 2 or ta == tb) for sa, sb, ta, tb in zip(a.shape, b.shape, a.stride(), b.stride()))
+
+
+def dtype_code(dtype):
+    _torch_check(dtype in _DTYPES, f'unsupported dtype {dtype}')
+    return _DTYPES[dtype]
+
+
+class _BiasActPlugin:
+    """`bias_act(x, b, xref, yref, dy, grad, dim, act, alpha, gain, clamp) -> Tensor`; validation follows
+    torch_utils/ops/bias_act.cpp:35-51, empty tensors mean "absent" (bias_act.py:39)."""
+
+    @staticmethod
+    def bias_act(x, b, xref, yref, dy, grad, dim, act, alpha, gain, clamp):
+        lib = load_library()
+        _torch_check(x.is_cuda, 'x must reside on CUDA device')
+        _torch_check(b.numel() == 0 or (b.dtype == x.dtype and b.device == x.device), 'b must have the same dtype and device as x')
+        for t, name in ((xref, 'xref'), (yref, 'yref'), (dy, 'dy')):
+            _torch_check(t.numel() == 0 or (t.shape == x.shape and t.dtype == x.dtype and t.device == x.device),
+                         f'{name} must have the same shape, dtype, and device as x')
+        _torch_check(x.numel() <= 2 ** 31 - 1, 'x is too large')
+        _torch_check(b.dim() == 1, 'b must have rank 1')
+        _torch_check(b.numel() == 0 or (0 <= dim < x.dim()), 'dim is out of bounds')
+        _torch_check(b.numel() == 0 or b.numel() == x.shape[dim], 'b has wrong number of elements')
+        _torch_check(grad >= 0, 'grad must be non-negative')
+        _torch_check(x.is_non_overlapping_and_dense(), 'x must be non-overlapping and dense')
+        _torch_check(b.is_contiguous(), 'b must be contiguous')
+        for t, name in ((xref, 'xref'), (yref, 'yref'), (dy, 'dy')):
+            _torch_check(t.numel() == 0 or _same_layout(t, x), f'{name} must have the same layout as x')
+        y = torch.empty_like(x)
+        _torch_check(_same_layout(y, x), 'y must have the same layout as x')
+        step_b = x.stride(dim) if b.numel() else 1
+        with torch.cuda.device(x.device):
+            _check(lib.pgpp_bias_act(_ptr(x), _ptr(b), _ptr(xref), _ptr(yref), _ptr(dy), _ptr(y), x.numel(), b.numel(),
+                                     step_b, dtype_code(x.dtype), int(grad), int(act), float(alpha), float(gain),
+                                     float(clamp), _stream(x)))
+        return y
+
+
+class _Upfirdn2dPlugin:
+    """`upfirdn2d(x, f, upx, upy, downx, downy, padx0, padx1, pady0, pady1, flip, gain) -> Tensor`; validation
+    and output size follow torch_utils/ops/upfirdn2d.cpp:19-36."""
+
+    @staticmethod
+    def upfirdn2d(x, f, upx, upy, downx, downy, padx0, padx1, pady0, pady1, flip, gain):
+        lib = load_library()
+        _torch_check(x.is_cuda, 'x must reside on CUDA device')
+        _torch_check(f.device == x.device, 'f must reside on the same device as x')
+        _torch_check(f.dtype == torch.float32, 'f must be float32')
+        _torch_check(x.numel() <= 2 ** 31 - 1, 'x is too large')
+        _torch_check(x.dim() == 4, 'x must be rank 4')
+        _torch_check(f.dim() == 2, 'f must be rank 2')
+        _torch_check(f.shape[0] >= 1 and f.shape[1] >= 1, 'f must be at least 1x1')
+        _torch_check(upx >= 1 and upy >= 1, 'upsampling factor must be at least 1')
+        _torch_check(downx >= 1 and downy >= 1, 'downsampling factor must be at least 1')
+        n, c, h, w = x.shape
+        out_w = (w * upx + padx0 + padx1 - f.shape[1] + downx) // downx
+        out_h = (h * upy + pady0 + pady1 - f.shape[0] + downy) // downy
+        _torch_check(out_w >= 1 and out_h >= 1, 'output must be at least 1x1')
+        mf = torch.channels_last if (x.stride(1) == 1 and c > 1) else torch.contiguous_format
+        y = torch.empty([n, c, out_h, out_w], dtype=x.dtype, device=x.device, memory_format=mf)
+        _torch_check(y.numel() <= 2 ** 31 - 1, 'output is too large')
+        with torch.cuda.device(x.device):
+            _check(lib.pgpp_upfirdn2d(_ptr(x), _ptr(f), _ptr(y), c_i64x4(*x.shape), c_i64x4(*x.stride()),
+                                      c_i64x4(*y.shape), c_i64x4(*y.stride()), f.shape[1], f.shape[0],
+                                      f.stride(1), f.stride(0), int(upx), int(upy), int(downx), int(downy),
+                                      int(padx0), int(pady0), int(bool(flip)), float(gain), dtype_code(x.dtype), _stream(x)))
+        return y
+
+
+class _ConvPlugin:
+    """New entry points with no reference counterpart (they replace cuDNN calls, conv2d_gradfix.py:112-114)."""
+
+    @staticmethod
+    def demod_coefs(weight, styles, eps=1e-8):
+        lib = load_library()
+        o, i = weight.shape[0], weight.shape[1]
+        w = weight.detach().to(torch.float32).contiguous()
+        s = styles.detach().to(torch.float32).contiguous()
+        d = torch.empty([s.shape[0], o], dtype=torch.float32, device=w.device)
+        with torch.cuda.device(w.device):
+            _check(lib.pgpp_modconv_demod_coefs(_ptr(w), _ptr(s), _ptr(d), s.shape[0], o, i, w[0, 0].numel(), float(eps), _stream(w)))
+        return d
+
+    @staticmethod
+    def pack_activations(x, scale, c_pad, parts):
+        lib = load_library()
+        _torch_check(x.is_cuda and x.dim() == 4, 'x must be a rank-4 CUDA tensor')
+        n, c, h, w = x.shape
+        out = torch.empty([parts, n, h, w, c_pad], dtype=torch.bfloat16, device=x.device)
+        if scale is not None:
+            scale = scale.detach().to(torch.float32).contiguous()
+            _torch_check(tuple(scale.shape) == (n, c), 'scale must be [N, C]')
+        with torch.cuda.device(x.device):
+            _check(lib.pgpp_pack_activations(_ptr(x), c_i64x4(*x.shape), c_i64x4(*x.stride()), dtype_code(x.dtype),
+                                             _ptr(scale), _ptr(out), int(c_pad), int(parts), _stream(x)))
+        return out
+
+    @staticmethod
+    def conv2d_igemm(desc, device):
+        lib = load_library()
+        with torch.cuda.device(device):
+            stream = ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+            _check(lib.pgpp_conv2d_igemm(ctypes.byref(desc), stream))
+
+
+_PLUGINS = {'bias_act_plugin': _BiasActPlugin, 'upfirdn2d_plugin': _Upfirdn2dPlugin, 'conv2d_plugin': _ConvPlugin}
+
+
+def get_plugin(module_name, sources=None, **build_kwargs):
+    """Same call shape as the reference (`sources` / build kwargs are accepted and ignored: nothing is compiled)."""
+    assert verbosity in ['none', 'brief', 'full']
+    if module_name in _cached_plugins:
+        return _cached_plugins[module_name]
+    if module_name not in _PLUGINS:
+        raise RuntimeError(f'unknown plugin "{module_name}"; available: {sorted(_PLUGINS)}')
+    load_library()
+    if verbosity == 'full':
+        print(f'Loaded prebuilt PyTorch plugin "{module_name}" from {_LIB_PATH}')
+    _cached_plugins[module_name] = _PLUGINS[module_name]
+    return _cached_plugins[module_name]

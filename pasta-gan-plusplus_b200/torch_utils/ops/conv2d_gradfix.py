@@ -1,0 +1,395 @@
+"""conv2d / conv_transpose2d with arbitrary-order gradients, on the B200 tensor cores.
+
+Drop-in for the reference's torch_utils/ops/conv2d_gradfix.py: same `conv2d`, `conv_transpose2d`,
+`no_weight_gradients`, `enabled`, `weight_gradients_disabled`.  Where the reference wraps cuDNN
+(conv2d_gradfix.py:112-114,143-145), this module runs the implicit-GEMM tcgen05 kernel
+(csrc/conv_igemm.cu via `pgpp_conv2d_igemm`) for the forward and data-gradient convolutions.  The
+autograd structure is the reference's (conv2d_gradfix.py:95-165): the data gradient of a convolution
+is the opposite-transposed convolution and is itself differentiable, so R1's double backward works.
+
+Switches
+  enabled                    True: CUDA tensors take the sm_100a kernel (no fallback: unsupported
+                             configurations raise).  False: plain torch.nn.functional (library) calls.
+  weight_gradients_disabled  as in the reference (set by `no_weight_gradients()`).
+  fp32_precision             how float32 tensors are fed to the bf16 tensor cores:
+                             'bf16x3' 6 products of 3-term bf16 splits (~fp32 accuracy, rel 1e-6)
+                             'bf16x2' 3 products of 2-term splits (rel ~1e-5; default, within the 1e-4 bar)
+                             'bf16'   1 product (rel ~3e-3; what bf16/fp16 tensors always use)
+
+Round-1 gap: the weight gradient still calls the library (`aten::convolution_backward`); everything
+else on the path is this repo's kernels.
+"""
+import contextlib
+import ctypes
+
+import torch
+
+from .. import custom_ops
+
+enabled = True                      # the reference defaults to False and train.py flips it; here the kernel IS the path
+weight_gradients_disabled = False
+fp32_precision = 'bf16x2'
+
+_PRODUCTS = {'bf16': (1, 1), 'bf16x2': (3, 2), 'bf16x3': (6, 3)}    # name -> (products, parts)
+_ACT_IDX = {'linear': 1, 'relu': 2, 'lrelu': 3, 'tanh': 4, 'sigmoid': 5, 'elu': 6, 'selu': 7, 'softplus': 8, 'swish': 9}
+_plugin = None
+
+
+@contextlib.contextmanager
+def no_weight_gradients():
+    global weight_gradients_disabled
+    old = weight_gradients_disabled
+    weight_gradients_disabled = True
+    yield
+    weight_gradients_disabled = old
+
+
+def _init():
+    global _plugin
+    if _plugin is None:
+        _plugin = custom_ops.get_plugin('conv2d_plugin')
+    return True
+
+
+def _should_use_custom_op(input):
+    assert isinstance(input, torch.Tensor)
+    return enabled and input.device.type == 'cuda'
+
+
+def _tuple_of_ints(xs, ndim):
+    xs = tuple(xs) if isinstance(xs, (tuple, list)) else (xs,) * ndim
+    assert len(xs) == ndim
+    assert all(isinstance(x, int) for x in xs)
+    return xs
+
+
+def precision_for(dtype):
+    return fp32_precision if dtype in (torch.float32, torch.float64) else 'bf16'
+
+
+# ------------------------------------------------------------------------------------------------
+# operand packing (host logic; the packed weights are cached per parameter version)
+
+def _round_up(v, m):
+    return (v + m - 1) // m * m
+
+
+def _split_bf16(t, parts):
+    """[parts, ...] bf16 expansion of a float32 tensor: part p = bf16(t - sum of earlier parts)."""
+    out = []
+    rem = t.to(torch.float32)
+    for _ in range(parts):
+        q = rem.to(torch.bfloat16)
+        out.append(q)
+        rem = rem - q.to(torch.float32)
+    return torch.stack(out)
+
+
+class PackedWeights:
+    """[parts, taps, o_rows, c_pad] bf16, K-major rows, ready for the TMA weight map."""
+    __slots__ = ('data', 'kh', 'kw', 'o', 'phases', 'o_rows', 'c_pad', 'parts', 'pad_y', 'pad_x')
+
+
+def choose_block_n(cols, m_tiles, sms=148):
+    bn = 256
+    while bn > 16 and bn // 2 >= cols:
+        bn //= 2
+    while bn > 32 and m_tiles * ((cols + bn - 1) // bn) < sms:
+        bn //= 2
+    return bn
+
+
+def pack_weights(w_taps, o, phases, kh, kw, parts, pad_y, pad_x):
+    """w_taps: float32 [taps, phases*o, I] -> PackedWeights (rows padded to a multiple of 256 or of the
+    power-of-two >= cols, channels to a multiple of 16)."""
+    taps, cols, ic = w_taps.shape
+    c_pad = _round_up(ic, 16)
+    o_rows = _round_up(cols, 256) if cols > 128 else max(16, 1 << (cols - 1).bit_length())
+    buf = torch.zeros([taps, o_rows, c_pad], dtype=torch.float32, device=w_taps.device)
+    buf[:, :cols, :ic] = w_taps
+    pw = PackedWeights()
+    pw.data = _split_bf16(buf, parts).contiguous()
+    pw.kh, pw.kw, pw.o, pw.phases, pw.o_rows, pw.c_pad, pw.parts = kh, kw, o, phases, o_rows, c_pad, parts
+    pw.pad_y, pw.pad_x = pad_y, pad_x
+    return pw
+
+
+_weight_cache = dict()
+
+
+def _cached(key_tensor, tag, builder):
+    """Cache packed weights per (storage, version, tag); parameters bump `_version` on every optimizer step."""
+    key = (key_tensor.data_ptr(), key_tensor._version, tuple(key_tensor.shape), key_tensor.dtype, tag)
+    hit = _weight_cache.get(key)
+    if hit is None:
+        if len(_weight_cache) > 512:
+            _weight_cache.clear()
+        # keep the key tensor alive with the entry so its address cannot be recycled under the same key
+        hit = (builder(), key_tensor)
+        _weight_cache[key] = hit
+    return hit[0]
+
+
+def packed_plain(weight, flip_weight, parts, pad_y, pad_x, transpose_io=False):
+    """weight [O, I, kh, kw] used as a correlation kernel (flip_weight=True, F.conv2d semantics) or a true
+    convolution kernel (flip_weight=False).  transpose_io: weight is [I, O, kh, kw] (conv_transpose2d layout)."""
+    def build():
+        w = weight.detach().to(torch.float32)
+        if transpose_io:
+            w = w.transpose(0, 1)
+        if not flip_weight:
+            w = w.flip([2, 3])
+        o, ic, kh, kw = w.shape
+        taps = w.permute(2, 3, 0, 1).reshape(kh * kw, o, ic)
+        return pack_weights(taps, o, 1, kh, kw, parts, pad_y, pad_x)
+    return _cached(weight, ('plain', bool(flip_weight), parts, pad_y, pad_x, bool(transpose_io)), build)
+
+
+def packed_up2(weight, f, flip_weight, flip_filter, parts):
+    """Polyphase form of `conv_transpose2d(stride=2)` followed by the 4x4 FIR with gain 4
+    (conv2d_resample.py:125-139, the StyleGAN2 up=2 layer): for output pixel (2y+py, 2x+px)
+
+        out = sum_{a,b in 0..2} x[y+a-1, x+b-1] * Wp[py,px][o,i,a,b]
+        Wp[py,px][.,.,a,b] = 4 * sum_{fy,ky: py+fy-1-ky = 2(a-1)} sum_{fx,kx: px+fx-1-kx = 2(b-1)} w'[ky,kx] * k[fy,fx]
+
+    with w' the kernel as conv_transpose2d sees it and k the (flipped) FIR.  One 3x3 GEMM with 4*O columns
+    replaces the transposed convolution, its (2H+1)^2 intermediate and the blur pass."""
+    def build():
+        w = weight.detach().to(torch.float32)
+        o, ic, kh, kw = w.shape
+        assert kh == 3 and kw == 3 and tuple(f.shape) == (4, 4)
+        if flip_weight:
+            w = w.flip([2, 3])
+        k = f.to(device=w.device, dtype=torch.float32)
+        if not flip_filter:
+            k = k.flip([0, 1])
+        wp = torch.zeros([2, 2, o, ic, 3, 3], dtype=torch.float32, device=w.device)
+        for py in range(2):
+            for fy in range(4):
+                for ky in range(3):
+                    num_y = py + fy - 1 - ky
+                    if num_y % 2:
+                        continue
+                    a = num_y // 2 + 1
+                    for px in range(2):
+                        for fx in range(4):
+                            for kx in range(3):
+                                num_x = px + fx - 1 - kx
+                                if num_x % 2:
+                                    continue
+                                b = num_x // 2 + 1
+                                wp[py, px, :, :, a, b] += 4.0 * k[fy, fx] * w[:, :, ky, kx]
+        taps = wp.permute(4, 5, 0, 1, 2, 3).reshape(9, 4 * o, ic)     # [tap][phase*o + oc][i]
+        return pack_weights(taps, o, 4, 3, 3, parts, 1, 1)
+    return _cached(weight, ('up2', bool(flip_weight), bool(flip_filter), parts, f.data_ptr(), f._version), build)
+
+
+# ------------------------------------------------------------------------------------------------
+# the kernel launch
+
+def igemm_conv(x, pw, *, scale=None, stride=1, out_hw=None, dcoef=None, noise=None, bias=None, act='linear',
+               alpha=0.0, gain=1.0, clamp=-1.0, out=None, out_dtype=None, accumulate=False, precision=None,
+               memory_format=None, x_packed=None):
+    """Run one fused convolution.  x: [N, I, H, W] (any float dtype / layout) or pre-packed activations.
+    Returns [N, O, out_h, out_w]."""
+    _init()
+    n, ic, h, w = x.shape
+    precision = precision or precision_for(x.dtype)
+    products, parts = _PRODUCTS[precision]
+    assert pw.parts >= parts, 'weights were packed with fewer parts than the requested precision needs'
+    if x_packed is None:
+        x_packed = _plugin.pack_activations(x, scale, pw.c_pad, parts)
+    up = 2 if pw.phases == 4 else 1
+    if out_hw is None:
+        conv_h = (h + 2 * pw.pad_y - pw.kh) // stride + 1
+        conv_w = (w + 2 * pw.pad_x - pw.kw) // stride + 1
+    else:
+        conv_h, conv_w = out_hw
+    out_h, out_w = conv_h * up, conv_w * up
+    if out is None:
+        out_dtype = out_dtype or (x.dtype if x.dtype != torch.float64 else torch.float32)
+        if memory_format is None:
+            memory_format = torch.channels_last if (x.stride(1) == 1 and ic > 1) else torch.contiguous_format
+        out = torch.empty([n, pw.o, out_h, out_w], dtype=out_dtype, device=x.device, memory_format=memory_format)
+    assert tuple(out.shape) == (n, pw.o, out_h, out_w)
+
+    tw = min(128, 1 << (conv_w - 1).bit_length())
+    th = min(128 // tw, 1 << (conv_h - 1).bit_length())
+    tn = 128 // (tw * th)
+    m_tiles = -(-conv_w // tw) * -(-conv_h // th) * -(-n // tn)
+    block_n = choose_block_n(pw.phases * pw.o, m_tiles)
+    while pw.o_rows % block_n:
+        block_n //= 2
+
+    d = custom_ops.ConvDesc()
+    d.act = x_packed.data_ptr(); d.wgt = pw.data.data_ptr()
+    d.a_parts = x_packed.shape[0]; d.b_parts = pw.data.shape[0]
+    d.n, d.h, d.w, d.c_pad = n, h, w, pw.c_pad
+    d.kh, d.kw, d.pad_y, d.pad_x, d.stride = pw.kh, pw.kw, pw.pad_y, pw.pad_x, stride
+    d.conv_h, d.conv_w = conv_h, conv_w
+    d.o, d.phases, d.o_rows, d.block_n, d.products = pw.o, pw.phases, pw.o_rows, block_n, products
+    keep = []
+    def fptr(t):
+        if t is None:
+            return None
+        t = t.detach().to(torch.float32).contiguous()
+        keep.append(t)
+        return t.data_ptr()
+    d.dcoef = fptr(dcoef)
+    if noise is not None:
+        nz = noise.detach().to(torch.float32)
+        if nz.dim() == 4:       # [N, 1, H, W]
+            nz = nz.reshape(nz.shape[0], out_h, out_w).contiguous()
+            d.noise_stride_n = out_h * out_w if nz.shape[0] > 1 else 0
+        else:
+            nz = nz.reshape(out_h, out_w).contiguous()
+            d.noise_stride_n = 0
+        keep.append(nz)
+        d.noise = nz.data_ptr()
+    d.bias = fptr(bias)
+    d.act_fn = _ACT_IDX[act]; d.alpha = float(alpha); d.gain = float(gain); d.clamp = float(clamp)
+    d.out = out.data_ptr(); d.out_dtype = custom_ops.dtype_code(out.dtype)
+    d.out_h, d.out_w = out_h, out_w
+    d.out_stride = (ctypes.c_int64 * 4)(*out.stride())
+    d.accumulate = int(bool(accumulate))
+    _plugin.conv2d_igemm(d, x.device)
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# public API
+
+def conv2d(input, weight, bias=None, stride=1, padding=0, dilation=1, groups=1):
+    if _should_use_custom_op(input):
+        return _conv2d_gradfix(transpose=False, weight_shape=weight.shape, stride=stride, padding=padding, output_padding=0,
+                               dilation=dilation, groups=groups).apply(input, weight, bias)
+    return torch.nn.functional.conv2d(input=input, weight=weight, bias=bias, stride=stride, padding=padding,
+                                      dilation=dilation, groups=groups)
+
+
+def conv_transpose2d(input, weight, bias=None, stride=1, padding=0, output_padding=0, groups=1, dilation=1):
+    if _should_use_custom_op(input):
+        return _conv2d_gradfix(transpose=True, weight_shape=weight.shape, stride=stride, padding=padding,
+                               output_padding=output_padding, groups=groups, dilation=dilation).apply(input, weight, bias)
+    return torch.nn.functional.conv_transpose2d(input=input, weight=weight, bias=bias, stride=stride, padding=padding,
+                                                output_padding=output_padding, groups=groups, dilation=dilation)
+
+
+def _forward_conv(x, weight, bias, stride, padding):
+    """F.conv2d(x, weight, bias, stride, padding) on the tensor cores."""
+    _, parts = _PRODUCTS[precision_for(x.dtype)]
+    pw = packed_plain(weight, True, parts, padding[0], padding[1])
+    return igemm_conv(x, pw, stride=stride[0], bias=bias)
+
+
+def _forward_conv_transpose(x, weight, bias, stride, padding, output_padding):
+    """F.conv_transpose2d(x, weight[I, O, kh, kw], ...) as zero insertion + a stride-1 convolution with the
+    flipped, transposed kernel (the data-gradient form; the fused up=2 layer does NOT come through here)."""
+    from . import upfirdn2d as _up
+    ic, oc, kh, kw = weight.shape
+    sy, sx = stride
+    if sy > 1 or sx > 1:
+        # insert zeros between samples; crop the trailing (s-1) zeros the insertion appends
+        x = _up.upfirdn2d(x, None, up=[sx, sy], padding=[0, -(sx - 1), 0, -(sy - 1)])
+    py, px = kh - 1 - padding[0], kw - 1 - padding[1]
+    assert py >= 0 and px >= 0, 'conv_transpose2d padding larger than kernel_size-1 is not supported'
+    _, parts = _PRODUCTS[precision_for(x.dtype)]
+    pw = packed_plain(weight, False, parts, py, px, transpose_io=True)    # flipped + transposed = equivalent correlation kernel
+    n, _, h, w = x.shape
+    out_h = h + 2 * py - kh + 1 + output_padding[0]
+    out_w = w + 2 * px - kw + 1 + output_padding[1]
+    return igemm_conv(x, pw, stride=1, bias=bias, out_hw=(out_h, out_w))
+
+
+_conv2d_gradfix_cache = dict()
+
+
+def _conv2d_gradfix(transpose, weight_shape, stride, padding, output_padding, dilation, groups):
+    ndim = 2
+    weight_shape = tuple(weight_shape)
+    stride = _tuple_of_ints(stride, ndim)
+    padding = _tuple_of_ints(padding, ndim)
+    output_padding = _tuple_of_ints(output_padding, ndim)
+    dilation = _tuple_of_ints(dilation, ndim)
+    key = (transpose, weight_shape, stride, padding, output_padding, dilation, groups)
+    if key in _conv2d_gradfix_cache:
+        return _conv2d_gradfix_cache[key]
+
+    assert groups >= 1
+    assert len(weight_shape) == ndim + 2
+    assert all(s >= 1 for s in stride)
+    assert all(p >= 0 for p in padding)
+    assert all(d >= 0 for d in dilation)
+    if not transpose:
+        assert all(p == 0 for p in output_padding)
+    else:
+        assert all(0 <= output_padding[i] < max(stride[i], dilation[i]) for i in range(ndim))
+    if groups != 1 or any(d != 1 for d in dilation) or stride[0] != stride[1] or stride[0] > 2:
+        raise NotImplementedError('the sm_100a convolution supports groups=1, dilation=1, stride 1 or 2; '
+                                  'set conv2d_gradfix.enabled = False to route this call to the PyTorch library op')
+
+    common_kwargs = dict(stride=stride, padding=padding, dilation=dilation, groups=groups)
+
+    def calc_output_padding(input_shape, output_shape):
+        if transpose:
+            return [0, 0]
+        return [input_shape[i + 2] - (output_shape[i + 2] - 1) * stride[i] - (1 - 2 * padding[i])
+                - dilation[i] * (weight_shape[i + 2] - 1) for i in range(ndim)]
+
+    class Conv2d(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, input, weight, bias):
+            assert weight.shape == weight_shape
+            if not transpose:
+                output = _forward_conv(input, weight, bias, stride, padding)
+            else:
+                output = _forward_conv_transpose(input, weight, bias, stride, padding, output_padding)
+            ctx.save_for_backward(input, weight)
+            return output
+
+        @staticmethod
+        def backward(ctx, grad_output):
+            input, weight = ctx.saved_tensors
+            grad_input = grad_weight = grad_bias = None
+            if ctx.needs_input_grad[0]:
+                p = calc_output_padding(input_shape=input.shape, output_shape=grad_output.shape)
+                grad_input = _conv2d_gradfix(transpose=(not transpose), weight_shape=weight_shape, output_padding=p,
+                                             **common_kwargs).apply(grad_output, weight, None)
+                assert grad_input.shape == input.shape
+            if ctx.needs_input_grad[1] and not weight_gradients_disabled:
+                grad_weight = Conv2dGradWeight.apply(grad_output, input)
+                assert grad_weight.shape == weight_shape
+            if ctx.needs_input_grad[2]:
+                grad_bias = grad_output.sum([0, 2, 3])
+            return grad_input, grad_weight, grad_bias
+
+    class Conv2dGradWeight(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, grad_output, input):
+            # Library call (round-1 gap, see module docstring): weight gradient of the (transposed) convolution.
+            if not transpose:
+                gw = torch.ops.aten.convolution_backward(grad_output, input, torch.empty(weight_shape, device=input.device, dtype=input.dtype),
+                                                         None, stride, padding, dilation, False, [0, 0], groups, [False, True, False])[1]
+            else:
+                gw = torch.ops.aten.convolution_backward(grad_output, input, torch.empty(weight_shape, device=input.device, dtype=input.dtype),
+                                                         None, stride, padding, dilation, True, output_padding, groups, [False, True, False])[1]
+            assert gw.shape == weight_shape
+            ctx.save_for_backward(grad_output, input)
+            return gw
+
+        @staticmethod
+        def backward(ctx, grad2_grad_weight):
+            grad_output, input = ctx.saved_tensors
+            grad2_grad_output = grad2_input = None
+            if ctx.needs_input_grad[0]:
+                grad2_grad_output = Conv2d.apply(input, grad2_grad_weight, None)
+                assert grad2_grad_output.shape == grad_output.shape
+            if ctx.needs_input_grad[1]:
+                p = calc_output_padding(input_shape=input.shape, output_shape=grad_output.shape)
+                grad2_input = _conv2d_gradfix(transpose=(not transpose), weight_shape=weight_shape, output_padding=p,
+                                              **common_kwargs).apply(grad_output, grad2_grad_weight, None)
+                assert grad2_input.shape == input.shape
+            return grad2_grad_output, grad2_input
+
+    _conv2d_gradfix_cache[key] = Conv2d
+    return Conv2d

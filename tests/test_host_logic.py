@@ -1,0 +1,189 @@
+"""CPU tests (-m "not gpu"): the drop-in modules' PyTorch ('ref') paths and host-side logic against the
+golden fixtures minted from the reference, the operand packing against the oracle, and the C-ABI surface."""
+import ctypes
+import importlib
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN, ROOT, load_pkg
+from helpers import emulate_igemm, rel_l2, t
+from oracle import ref_ops
+from oracle.make_golden import CONV_CASES, MODCONV_CASES, UPFIRDN_CASES
+
+pkg = load_pkg()
+ops = lambda name: importlib.import_module(f'pgpp_b200.torch_utils.ops.{name}')
+bias_act = ops('bias_act'); upfirdn2d = ops('upfirdn2d'); conv2d_resample = ops('conv2d_resample')
+conv2d_gradfix = ops('conv2d_gradfix'); fma = ops('fma')
+networks = importlib.import_module('pgpp_b200.training.networks')
+custom_ops = importlib.import_module('pgpp_b200.torch_utils.custom_ops')
+
+
+def _opt(v):
+    return None if v == 'None' else float(v)
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, 'include', 'pgpp.h')).read()
+    declared = set(re.findall(r'PGPP_API\s+[\w\s\*]+?\b(pgpp_\w+)\s*\(', header))
+    assert declared == set(custom_ops.EXPORTED_SYMBOLS), declared ^ set(custom_ops.EXPORTED_SYMBOLS)
+    lib = ctypes.CDLL(custom_ops.library_path())
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert custom_ops.load_library().pgpp_version() >= 100
+    # struct mirror has the size the C compiler gives pgpp_conv_desc (checked against a tiny C program's sizeof)
+    assert ctypes.sizeof(custom_ops.ConvDesc) % 8 == 0
+
+
+def test_cuda_impl_never_falls_back_on_cpu_tensors():
+    x = torch.randn(2, 3, 4, 4)
+    with pytest.raises(RuntimeError):
+        bias_act.bias_act(x, torch.randn(3))
+    with pytest.raises(RuntimeError):
+        upfirdn2d.upfirdn2d(x, upfirdn2d.setup_filter([1, 3, 3, 1]))
+    with pytest.raises(AssertionError):
+        bias_act.bias_act(x, impl='fast')
+    assert not conv2d_gradfix._should_use_custom_op(x)
+
+
+def test_get_plugin_contract():
+    p = custom_ops.get_plugin('bias_act_plugin', sources=['ignored.cu'], extra_cuda_cflags=['--use_fast_math'])
+    assert p is custom_ops.get_plugin('bias_act_plugin')
+    assert hasattr(p, 'bias_act') and hasattr(custom_ops.get_plugin('upfirdn2d_plugin'), 'upfirdn2d')
+    with pytest.raises(RuntimeError):
+        custom_ops.get_plugin('nope_plugin')
+    assert custom_ops.verbosity in ('none', 'brief', 'full')
+
+
+def test_bias_act_ref_path_matches_reference_golden():
+    g = np.load(os.path.join(GOLDEN, 'bias_act.npz'))
+    x, b = t(g['x']), t(g['b'])
+    assert list(bias_act.activation_funcs) == list(ref_ops.ACTIVATIONS)
+    for name, spec in bias_act.activation_funcs.items():
+        da, dg, idx, ref, has2 = ref_ops.ACTIVATIONS[name]
+        assert (spec.def_alpha, float(spec.def_gain), spec.cuda_idx, spec.ref, spec.has_2nd_grad) == (da, float(dg), idx, ref, has2)
+    n = len([k for k in g.files if k.endswith('_meta')])
+    for i in range(n):
+        act, alpha, gain, clamp = g[f'case{i}_meta']
+        y = bias_act.bias_act(x, b, act=str(act), alpha=_opt(alpha), gain=_opt(gain), clamp=_opt(clamp), impl='ref')
+        np.testing.assert_allclose(y.numpy(), g[f'case{i}_y'], rtol=1e-6, atol=1e-6)
+
+
+@pytest.mark.parametrize('case', UPFIRDN_CASES, ids=[c[0] for c in UPFIRDN_CASES])
+def test_upfirdn2d_ref_path_matches_reference_golden(case):
+    name, shape, taps, sep, up, down, pad, flip, gain = case
+    g = np.load(os.path.join(GOLDEN, 'upfirdn2d.npz'))
+    x = t(g[f'{name}_x'])
+    f = t(g[f'{name}_f']) if g[f'{name}_f'].size else None
+    y = upfirdn2d.upfirdn2d(x, f, up=up, down=down, padding=pad, flip_filter=flip, gain=gain, impl='ref')
+    np.testing.assert_allclose(y.numpy(), g[f'{name}_y'], rtol=1e-5, atol=2e-6)
+
+
+def test_upfirdn2d_helpers_match_reference_golden():
+    g = np.load(os.path.join(GOLDEN, 'upfirdn2d.npz'))
+    x, f = t(g['wrap_x']), t(g['wrap_f'])
+    np.testing.assert_allclose(upfirdn2d.filter2d(x, f, impl='ref').numpy(), g['wrap_filter2d'], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(upfirdn2d.upsample2d(x, f, impl='ref').numpy(), g['wrap_upsample2d'], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(upfirdn2d.downsample2d(x, f, impl='ref').numpy(), g['wrap_downsample2d'], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(upfirdn2d.setup_filter([1, 3, 3, 1]).numpy(), g['setup_1331'], rtol=1e-7)
+    np.testing.assert_allclose(upfirdn2d.setup_filter([1, 2, 3], flip_filter=True, gain=3.0).numpy(), g['setup_flip_gain'], rtol=1e-6)
+    assert upfirdn2d._parse_padding([1, 2]) == (1, 1, 2, 2) and upfirdn2d._parse_scaling(3) == (3, 3)
+    assert upfirdn2d._get_filter_size(None) == (1, 1) and upfirdn2d._get_filter_size(torch.ones(3, 5)) == (5, 3)
+
+
+@pytest.mark.parametrize('case', CONV_CASES, ids=[c[0] for c in CONV_CASES])
+def test_conv2d_resample_cpu_path_matches_reference_golden(case):
+    # on CPU tensors conv2d_gradfix routes to torch.nn.functional like the reference does (conv2d_gradfix.py:51-52),
+    # but upfirdn2d has no CPU kernel by design -> exercise the decomposition with impl='ref' patched in
+    name, xs, ws, up, down, pad, groups, flipw, usef = case
+    g = np.load(os.path.join(GOLDEN, 'conv2d_resample.npz'))
+    x, w, f = t(g[f'{name}_x']), t(g[f'{name}_w']), t(g['f'])
+    orig = upfirdn2d.upfirdn2d
+    upfirdn2d.upfirdn2d = lambda *a, **k: orig(*a, **{**k, 'impl': 'ref'})
+    try:
+        y = conv2d_resample.conv2d_resample(x, w, f=(f if usef else None), up=up, down=down, padding=pad, groups=groups,
+                                            flip_weight=flipw)
+    finally:
+        upfirdn2d.upfirdn2d = orig
+    np.testing.assert_allclose(y.numpy(), g[f'{name}_y'], rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize('case', MODCONV_CASES, ids=[c[0] for c in MODCONV_CASES])
+def test_modulated_conv2d_cpu_path_matches_reference_golden(case):
+    name, n, ic, oc, k, h, up, demod, noise_kind, flipw = case
+    g = np.load(os.path.join(GOLDEN, 'modulated_conv2d.npz'))
+    x, w, s, f = t(g[f'{name}_x']), t(g[f'{name}_w']), t(g[f'{name}_s']), t(g['f'])
+    noise = t(g[f'{name}_noise']) if g[f'{name}_noise'].size else None
+    orig = upfirdn2d.upfirdn2d
+    upfirdn2d.upfirdn2d = lambda *a, **k: orig(*a, **{**k, 'impl': 'ref'})
+    try:
+        for fused, key in ((True, 'y_fused'), (False, 'y_split')):
+            y = networks.modulated_conv2d(x.clone(), w, s, noise=noise, up=up, padding=k // 2, resample_filter=f,
+                                          demodulate=demod, flip_weight=flipw, fused_modconv=fused)
+            assert rel_l2(y, t(g[f'{name}_{key}'])) < 2e-6
+    finally:
+        upfirdn2d.upfirdn2d = orig
+
+
+def test_fma_forward_backward():
+    a = torch.randn(2, 3, 4, 4, dtype=torch.float64, requires_grad=True)
+    b = torch.randn(2, 3, 1, 1, dtype=torch.float64, requires_grad=True)
+    c = torch.randn(4, 4, dtype=torch.float64, requires_grad=True)
+    assert torch.allclose(fma.fma(a, b, c), a * b + c)
+    assert torch.autograd.gradcheck(fma.fma, (a, b, c))
+
+
+@pytest.mark.parametrize('parts,tol', [(1, 8e-3), (2, 4e-5), (3, 3e-7)])
+def test_weight_packing_plain_and_split_precision(parts, tol):
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(2, 20, 9, 11, generator=g)
+    w = torch.randn(24, 20, 3, 3, generator=g)
+    s = torch.randn(2, 20, generator=g) * 0.5 + 1
+    for flip in (True, False):
+        pw = conv2d_gradfix.packed_plain(w, flip, parts, 1, 1)
+        assert pw.c_pad == 32 and pw.o_rows == 32 and pw.data.dtype == torch.bfloat16 and pw.data.shape[0] == parts
+        want = ref_ops.conv2d_resample(x * s.reshape(2, 20, 1, 1), w, padding=1, flip_weight=flip)
+        got = emulate_igemm(x, pw, scale=s)
+        assert rel_l2(got, want) < tol     # bf16 expansion of the WEIGHTS only (activations stay exact here)
+
+
+def test_weight_packing_transposed_layout_and_stride2():
+    g = torch.Generator().manual_seed(4)
+    x = torch.randn(1, 8, 10, 10, generator=g)
+    wt = torch.randn(8, 6, 3, 3, generator=g)       # conv_transpose2d layout [I, O, kh, kw]
+    pw = conv2d_gradfix.packed_plain(wt, False, 3, 2, 2, transpose_io=True)
+    want = ref_ops.conv_transpose2d(x, wt, stride=1, padding=0)
+    assert rel_l2(emulate_igemm(x, pw), want) < 3e-7
+    w = torch.randn(6, 8, 3, 3, generator=g)
+    pw2 = conv2d_gradfix.packed_plain(w, True, 3, 1, 1)
+    assert rel_l2(emulate_igemm(x, pw2, stride=2), ref_ops.conv2d(x, w, stride=2, padding=1)) < 3e-7
+
+
+def test_polyphase_up2_weights_reproduce_transposed_conv_plus_blur():
+    g = torch.Generator().manual_seed(5)
+    f = upfirdn2d.setup_filter([1, 3, 3, 1])
+    x = torch.randn(2, 16, 8, 8, generator=g)
+    w = torch.randn(32, 16, 3, 3, generator=g)
+    for flipw in (False, True):
+        pw = conv2d_gradfix.packed_up2(w, f, flipw, False, 3)
+        assert pw.phases == 4 and pw.o == 32 and pw.o_rows == 128
+        want = ref_ops.conv2d_resample(x, w, f=f, up=2, padding=1, flip_weight=flipw)
+        got = emulate_igemm(x, pw)
+        assert got.shape == want.shape == (2, 32, 16, 16)
+        assert rel_l2(got, want) < 3e-7
+    # asymmetric (non-separable-looking) filter exercises the flip conventions
+    f2 = torch.rand(4, 4, generator=g)
+    pw = conv2d_gradfix.packed_up2(w, f2, False, False, 3)
+    assert rel_l2(emulate_igemm(x, pw), ref_ops.conv2d_resample(x, w, f=f2, up=2, padding=1, flip_weight=False)) < 3e-7
+    pw = conv2d_gradfix.packed_up2(w, f2, False, True, 3)
+    assert rel_l2(emulate_igemm(x, pw), ref_ops.conv2d_resample(x, w, f=f2, up=2, padding=1, flip_weight=False, flip_filter=True)) < 3e-7
+
+
+def test_block_n_choice():
+    assert conv2d_gradfix.choose_block_n(3, 10000) == 16
+    assert conv2d_gradfix.choose_block_n(64, 10000) == 64
+    assert conv2d_gradfix.choose_block_n(512, 10000) == 256
+    assert conv2d_gradfix.choose_block_n(512, 16) <= 64       # few pixel tiles -> more column tiles to fill 148 SMs
