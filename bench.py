@@ -1,0 +1,346 @@
+"""Benchmark of the StyleGAN2 synthesis hot path of the PASTA-GAN++ 512 px generator (BASELINE.json configs[1]).
+
+    python bench.py --gpus 1 --steps 10 --warmup 3                 # this repo's sm_100a kernels
+    python bench.py --impl reference --steps 3 --warmup 1          # the CPU ref path (oracle port) on the host cores
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port P bench.py --gpus 8 ...
+
+One "step" = one batch (default 32 images per GPU) through the synthesis chain of the 512 px generator: the 24
+modulated_conv2d calls of SURVEY Appendix A with their bias_act epilogues, the 5 merge 1x1 convolutions, the 6 image-skip
+upfirdn2d up-samplings and the ToRGB accumulations (pgpp_b200.training.synthesis.SynthesisChain).  The SPADE refinement
+blocks and the encoders of the full generator are outside this round's scope and are NOT in the step; the
+metric is therefore named `synthesis_hot_path_images_per_sec`, not generator images/s.
+
+Prints ONE JSON line (rank 0).  `value` is device-resident throughput over all GPUs; `e2e` goes through the public
+pipeline API with pinned-host inputs and the image read back to the host inside the timed region.
+"""
+import argparse
+import importlib
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+W_DIM = 512
+RES = 512
+
+
+def build_chain(device, resolution=RES):
+    from __graft_entry__ import load_pkg
+    load_pkg()
+    synthesis = importlib.import_module('pgpp_b200.training.synthesis')
+    torch.manual_seed(0)
+    net = synthesis.SynthesisChain(w_dim=W_DIM, img_resolution=resolution).eval()
+    # random init like the reference (weights N(0,1), biases 0, affine bias 1); non-zero noise strength so the
+    # noise path is exercised (the reference initialises it to 0)
+    for name, p in net.named_parameters():
+        if name.endswith('noise_strength'):
+            p.data.fill_(0.1)
+    return net.to(device).requires_grad_(False)
+
+
+def make_inputs(net, batch, seed, device='cpu', pin=False):
+    g = torch.Generator().manual_seed(seed)
+    ws = torch.randn(batch, net.num_ws, W_DIM, generator=g)
+    pose = torch.randn(batch, net.channels[8], 8, 8, generator=g)
+    if pin:
+        ws, pose = ws.pin_memory(), pose.pin_memory()
+    return ws.to(device) if device != 'cpu' else ws, pose.to(device) if device != 'cpu' else pose
+
+
+def make_cat_feats(net, batch, device):
+    # warped garment features: produced on-GPU by the style encoder in the full generator -> device-resident here
+    g = torch.Generator().manual_seed(1)
+    return {str(r): torch.randn(batch, 64, r, r, generator=g).clamp_(-1, 1).to(device) for r in net.block_resolutions if r > 32}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = 'clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
+        'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-lms', '100',
+                                          '-i', str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=lambda: [self.lines.append(l) for l in self.proc.stdout], daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def __exit__(self, *exc):
+        if self.proc is not None:
+            time.sleep(0.15)
+            self.proc.terminate()
+            self.thread.join(timeout=2)
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        for l in self.lines:
+            f = [v.strip() for v in l.split(',')]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), f[3:7]):
+                if v.lower().startswith('active'):
+                    reasons.add(name)
+        if not sm:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': [], 'samples': 0}
+        return {'sm_mhz': statistics.median(sm), 'sm_max_mhz': max(mx), 'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+def peaks():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.isfile(path):
+        p = json.load(open(path))
+        return {'tflops': p['bf16_tflops_sustained'], 'gbs': p['hbm_gbs'], 'source': 'MEASURED_PEAKS.json (bf16 sustained, HBM copy)'}
+    return {'tflops': 1400.0, 'gbs': 6650.0, 'source': 'fallback of B200_PROFILING.md (1.4 PF sustained, 6.65 TB/s)'}
+
+
+def cpu_reference_rate(net_sd, num_ws, c8, batch, reps, threads=None):
+    """images/s of the CPU ref path (oracle port of the reference's impl='ref' ops) on the host cores."""
+    from oracle import ref_chain
+    if threads:
+        torch.set_num_threads(threads)
+    g = torch.Generator().manual_seed(7)
+    ws = torch.randn(batch, num_ws, W_DIM, generator=g)
+    pose = torch.randn(batch, c8, 8, 8, generator=g)
+    cat = {str(r): torch.randn(batch, 64, r, r, generator=g).clamp_(-1, 1) for r in (64, 128, 256, 512)}
+    times = []
+    with torch.no_grad():
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            ref_chain.synthesis_chain(net_sd, ws, pose, cat, img_resolution=RES)
+            times.append(time.perf_counter() - t0)
+    return batch / min(times), times
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', 0))
+    if rank != 0:
+        return
+    net = build_chain('cpu')
+    sd = {k: v.detach() for k, v in net.state_dict().items()}
+    cores = torch.get_num_threads()
+    batch = 1
+    for _ in range(args.warmup):
+        cpu_reference_rate(sd, net.num_ws, net.channels[8], batch, 1)
+    t0 = time.perf_counter()
+    rate, times = cpu_reference_rate(sd, net.num_ws, net.channels[8], batch, args.steps)
+    total = time.perf_counter() - t0
+    value = batch * args.steps / sum(times)
+    line = {
+        'impl': 'reference', 'metric': 'synthesis_hot_path_images_per_sec', 'value': value, 'unit': 'images/s', 'n_gpus': args.gpus,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * sum(times) / args.steps, 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': 'PASTA-GAN++ 512px generator synthesis chain (24 modulated_conv2d + bias_act + upfirdn2d + merge convs), '
+                               'CPU ref path, bounded sample of batch 1 per step', 'resolution': RES},
+        'cpu_baseline': {'value': value, 'unit': 'images/s', 'cores': cores, 'kind': 'port',
+                         'sample': f'{args.steps} steps of batch {batch} through oracle/ref_chain.py (torch CPU ops, {cores} threads)'},
+        'e2e': {'value': value, 'unit': 'images/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+class SynthesisPipeline:
+    """The public end-to-end call: pinned host inputs -> device -> synthesis chain -> image back in pinned host memory.
+    Copies run on a side stream so the read-back of batch i overlaps the compute of batch i+1."""
+
+    def __init__(self, net, cat_feats, batch, device):
+        self.net, self.cat, self.device = net, cat_feats, device
+        self.copy_stream = torch.cuda.Stream(device)
+        self.out_host = [torch.empty(batch, 3, RES, RES, dtype=torch.float32).pin_memory() for _ in range(2)]
+        self.slot = 0
+        self.pending = None
+
+    def __call__(self, ws_host, pose_host):
+        cur = torch.cuda.current_stream(self.device)
+        ws = ws_host.to(self.device, non_blocking=True)
+        pose = pose_host.to(self.device, non_blocking=True)
+        with torch.no_grad():
+            img, parsing, tex = self.net(ws, pose, self.cat, noise_mode='const')
+        done = torch.cuda.Event()
+        done.record(cur)
+        self.copy_stream.wait_event(done)
+        with torch.cuda.stream(self.copy_stream):
+            host = self.out_host[self.slot]
+            host.copy_(img, non_blocking=True)
+            img.record_stream(self.copy_stream)
+            ev = torch.cuda.Event()
+            ev.record(self.copy_stream)
+        prev, self.pending = self.pending, (ev, host)
+        self.slot ^= 1
+        if prev is not None:
+            prev[0].synchronize()       # the previous batch is now readable on the host
+        return prev[1] if prev is not None else None
+
+    def flush(self):
+        if self.pending is not None:
+            self.pending[0].synchronize()
+            host, self.pending = self.pending[1], None
+            return host
+        return None
+
+
+def run_ours(args):
+    rank = int(os.environ.get('RANK', 0)); world = int(os.environ.get('WORLD_SIZE', 1)); local = int(os.environ.get('LOCAL_RANK', 0))
+    assert torch.cuda.is_available(), 'bench.py needs a GPU (there is no CPU fallback; use --impl reference for the CPU ref path)'
+    torch.cuda.set_device(local)
+    device = torch.device('cuda', local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group('nccl', device_id=device)
+    from __graft_entry__ import load_pkg
+    load_pkg()
+    custom_ops = importlib.import_module('pgpp_b200.torch_utils.custom_ops')
+    cg = importlib.import_module('pgpp_b200.torch_utils.ops.conv2d_gradfix')
+    custom_ops.load_library()
+    cg.fp32_precision = args.precision
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+
+    net = build_chain(device)
+    batch = args.batch
+    cat = make_cat_feats(net, batch, device)
+    ws_h, pose_h = make_inputs(net, batch, 100 + rank, pin=True)
+    ws_d, pose_d = ws_h.to(device), pose_h.to(device)
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    def step():
+        with torch.no_grad():
+            return net(ws_d, pose_d, cat, noise_mode='const')
+
+    # ---- device-resident throughput ----
+    for _ in range(max(args.warmup, 3)):
+        out = step()
+    barrier()
+    launches0 = custom_ops.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clocks:
+        barrier()
+        e0.record()
+        for _ in range(args.steps):
+            out = step()
+        e1.record()
+        barrier()
+    ms = e0.elapsed_time(e1)
+    launches = custom_ops.launch_count() - launches0
+
+    # ---- end to end through the pipeline API (pinned host in, image back to host) ----
+    pipe = SynthesisPipeline(net, cat, batch, device)
+    for _ in range(3):
+        pipe(ws_h, pose_h)
+    pipe.flush()
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for _ in range(args.steps):
+        host_img = pipe(ws_h, pose_h)
+    host_img = pipe.flush()
+    f1.record()
+    barrier()
+    e2e_ms = f0.elapsed_time(f1)        # device clock; f1 is recorded after the last read-back completed
+    h2d = ws_h.numel() * 4 + pose_h.numel() * 4
+    d2h = batch * 3 * RES * RES * 4
+
+    # ---- max over ranks ----
+    times = torch.tensor([ms, e2e_ms], device=device, dtype=torch.float64)
+    if world > 1:
+        torch.distributed.all_reduce(times, op=torch.distributed.ReduceOp.MAX)
+    ms, e2e_ms = float(times[0]), float(times[1])
+
+    if rank == 0:
+        # ---- roofline of the dominant kernel (igemm): algorithmic FLOPs / CUDA-event time over one instrumented step ----
+        cg.trace = []
+        step(); torch.cuda.synchronize()
+        cg.trace = []
+        step(); torch.cuda.synchronize()
+        tr, cg.trace = cg.trace, None
+        flops = sum(t[1] for t in tr)
+        kms = sum(t[2].elapsed_time(t[3]) for t in tr)
+        pk = peaks()
+        achieved = flops / (kms * 1e-3) / 1e12
+        step_flops_share = kms / (ms / args.steps)
+        top = sorted(tr, key=lambda t: -t[2].elapsed_time(t[3]))[:3]
+        # parity of this very step against the CPU oracle on a bounded sample (batch 1), reported with the number
+        parity = None
+        cpu = None
+        if not args.skip_cpu:
+            from oracle import ref_chain
+            sd = {k: v.detach().cpu() for k, v in net.state_dict().items()}
+            with torch.no_grad():
+                g_img, g_par, g_tex = net(ws_d[:1], pose_d[:1], {k: v[:1] for k, v in cat.items()}, noise_mode='const')
+                r_img, r_par, r_tex = ref_chain.synthesis_chain(sd, ws_h[:1], pose_h[:1], {k: v[:1].cpu() for k, v in cat.items()}, img_resolution=RES)
+            rel = lambda a, b: float((a.cpu().double() - b.double()).norm() / b.double().norm())
+            parity = {'img_rel_l2': rel(g_img, r_img), 'parsing_rel_l2': rel(g_par, r_par), 'texture_rel_l2': rel(g_tex, r_tex),
+                      'img_max_abs': float((g_img.cpu() - r_img).abs().max()), 'img_abs_scale': float(r_img.abs().max())}
+            cores = torch.get_num_threads()
+            rate, ctimes = cpu_reference_rate(sd, net.num_ws, net.channels[8], 1, 3)
+            cpu = {'value': rate, 'unit': 'images/s', 'cores': cores, 'kind': 'port',
+                   'sample': f'best of 3 x batch 1 through oracle/ref_chain.py (torch CPU ops, {cores} threads; {sum(ctimes):.1f} s total)'}
+        imgs = batch * world * args.steps
+        line = {
+            'metric': 'synthesis_hot_path_images_per_sec', 'value': imgs / (ms * 1e-3), 'unit': 'images/s', 'n_gpus': world,
+            'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': ms / args.steps, 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'f32 in/out; bf16x2-split tcgen05 MMAs with fp32 accumulation' if args.precision != 'bf16' else 'bf16 MMA, fp32 accumulate, f32 in/out',
+            'data': 'synthetic',
+            'config': {'workload': 'PASTA-GAN++ 512px generator synthesis chain: 24 modulated_conv2d (+bias_act, noise, ToRGB accumulate), '
+                                   '5 merge 1x1 convs, 6 image-skip upfirdn2d; SPADE blocks/encoders not included (SURVEY 8f N1)',
+                       'batch_per_gpu': batch, 'global_batch': batch * world, 'resolution': RES, 'precision': args.precision,
+                       'parallelism': f'batch-sharded x{world}, no collective',
+                       'l2': 'per-step working set (several GB of activations) exceeds the 126 MB L2; no flush needed'},
+            'clocks': clocks.summary(),
+            'gpu_launches': launches,
+            'e2e': {'value': imgs / (e2e_ms * 1e-3), 'unit': 'images/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
+                    'note': 'pinned-host ws + pose features in, fp32 image read back (as test.py:162 does); copy of batch i overlaps compute of i+1'},
+            'roofline': {'bound': 'tensor', 'kernel': 'pgpp::igemm_kernel (all launches of one step)', 'achieved': achieved, 'peak': pk['tflops'],
+                         'unit': 'TFLOP/s', 'frac': achieved / pk['tflops'], 'traffic': None, 'peak_source': pk['source'],
+                         'share_of_step': step_flops_share, 'algorithmic_flops_per_step': flops,
+                         'top_launches': [{'launch': t[0], 'ms': t[2].elapsed_time(t[3]), 'tflops': t[1] / t[2].elapsed_time(t[3]) / 1e9} for t in top]},
+            'cpu_baseline': cpu,
+            'parity_vs_cpu_oracle': parity,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--batch', type=int, default=32, help='images per GPU per step')
+    ap.add_argument('--precision', default='bf16x2', choices=['bf16', 'bf16x2', 'bf16x3'])
+    ap.add_argument('--skip-cpu', action='store_true', help='skip the CPU baseline / parity leg')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == '__main__':
+    main()

@@ -105,9 +105,10 @@ typedef struct {
     int32_t stride;                 /* 1 or 2 */
     int32_t conv_h, conv_w;         /* conv output grid (per phase) */
     int32_t o;                      /* logical output channels (per phase) */
-    int32_t phases;                 /* 1, or 4 for the fused up=2 polyphase form: GEMM column g = phase*o + oc,
+    int32_t phases;                 /* 1, or 4 for the fused up=2 polyphase form: GEMM column g = phase*phase_stride + oc,
                                        phase = 2*py + px writes output pixel (2y+py, 2x+px) */
-    int32_t o_rows;                 /* rows per tap in wgt: >= phases*o, multiple of block_n */
+    int32_t phase_stride;           /* columns between phases: >= o, multiple of 16 when phases == 4 (= o when phases == 1) */
+    int32_t o_rows;                 /* rows per tap in wgt: >= phases*phase_stride, multiple of block_n */
     int32_t block_n;                /* GEMM N tile: 16, 32, 64, 128 or 256 */
     int32_t products;               /* 1 (bf16), 3 (2-part split) or 6 (3-part split) */
     /* epilogue: v = acc * dcoef[n,oc] + noise[n?,y,x];  y = clamp(act(v + bias[oc]) * gain) */

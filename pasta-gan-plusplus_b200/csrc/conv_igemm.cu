@@ -35,7 +35,7 @@ struct IgemmParams {
     int kh, kw, pad_y, pad_x, stride;
     int num_cb, kb;
     int products, pa[6], pb[6];
-    int o, phases, o_rows, block_n;
+    int o, phases, phase_stride, o_rows, block_n;
     int tw, th, tn;
     int tiles_x, tiles_y, tiles_n, tiles_col;
     long long total_tiles;
@@ -161,7 +161,7 @@ __device__ __forceinline__ void epilogue_tile(const IgemmParams& p, const TileCo
     const int pn = lane_row / (p.tw * p.th);
     const int x = tc.x0 + px, y = tc.y0 + py, n = tc.n0 + pn;
     const bool pix_ok = x < p.conv_w && y < p.conv_h && n < p.n;
-    const int total_cols = p.phases * p.o;
+    const int total_cols = p.phases * p.phase_stride;
     OT* out = (OT*)p.out;
     const float alpha = p.alpha, gain = p.gain, clamp = p.clamp;
 
@@ -170,8 +170,9 @@ __device__ __forceinline__ void epilogue_tile(const IgemmParams& p, const TileCo
         tmem_ld16(tmem_tile + c0, v);       // warp-collective: executed by all lanes, valid pixel or not
         const int g0 = tc.col0 + c0;
         if (!pix_ok || g0 >= total_cols) continue;
-        const int phase = g0 / p.o;         // a 16-column chunk never straddles phases (o % 16 == 0 when phases > 1)
-        const int oc0 = g0 - phase * p.o;
+        const int phase = g0 / p.phase_stride;      // a 16-column chunk never straddles phases (phase_stride % 16 == 0)
+        const int oc0 = g0 - phase * p.phase_stride;
+        if (oc0 >= p.o) continue;                   // padding columns between phases
         const int oy = y * p.up + (phase >> 1), ox = x * p.up + (phase & 1);
         float nz = 0.f;
         if (p.noise) nz = __ldg(p.noise + n * p.noise_stride_n + (long long)oy * p.out_w + ox);
@@ -381,10 +382,12 @@ extern "C" int pgpp_conv2d_igemm(const pgpp_conv_desc* d, void* stream) {
     PGPP_REQUIRE(d->kh >= 1 && d->kw >= 1, "filter must be at least 1x1");
     PGPP_REQUIRE(d->stride == 1 || d->stride == 2, "stride must be 1 or 2");
     PGPP_REQUIRE(d->phases == 1 || d->phases == 4, "phases must be 1 or 4");
-    PGPP_REQUIRE(d->phases == 1 || d->o % 16 == 0, "polyphase form needs out channels % 16 == 0");
+    PGPP_REQUIRE(d->phase_stride >= d->o && (d->phases == 1 ? d->phase_stride == d->o : d->phase_stride % 16 == 0),
+                 "phase_stride must be o (phases == 1) or a multiple of 16 >= o (phases == 4)");
     PGPP_REQUIRE(d->block_n == 16 || d->block_n == 32 || d->block_n == 64 || d->block_n == 128 || d->block_n == 256,
                  "block_n must be 16, 32, 64, 128 or 256");
-    PGPP_REQUIRE(d->o >= 1 && d->o_rows >= d->phases * d->o && d->o_rows % d->block_n == 0, "o_rows must cover phases*o and be a multiple of block_n");
+    PGPP_REQUIRE(d->o >= 1 && d->o_rows >= d->phases * d->phase_stride && d->o_rows % d->block_n == 0,
+                 "o_rows must cover phases*phase_stride and be a multiple of block_n");
     PGPP_REQUIRE(d->products == 1 || d->products == 3 || d->products == 6, "products must be 1, 3 or 6");
     const int need_parts = d->products == 1 ? 1 : (d->products == 3 ? 2 : 3);
     PGPP_REQUIRE(d->a_parts >= need_parts && d->b_parts >= need_parts, "operand parts do not cover the requested products");
@@ -406,7 +409,7 @@ extern "C" int pgpp_conv2d_igemm(const pgpp_conv_desc* d, void* stream) {
     static const int PA[6] = {0, 0, 1, 1, 0, 2}, PB[6] = {0, 1, 0, 1, 2, 0};
     if (d->products == 3) { p.pa[0] = 0; p.pb[0] = 0; p.pa[1] = 0; p.pb[1] = 1; p.pa[2] = 1; p.pb[2] = 0; }
     else for (int i = 0; i < 6; i++) { p.pa[i] = PA[i]; p.pb[i] = PB[i]; }
-    p.o = d->o; p.phases = d->phases; p.o_rows = d->o_rows; p.block_n = d->block_n; p.up = up;
+    p.o = d->o; p.phases = d->phases; p.phase_stride = d->phase_stride; p.o_rows = d->o_rows; p.block_n = d->block_n; p.up = up;
     // pixel tile: TW x TH x TN = 128
     p.tw = pow2_ceil(d->conv_w); if (p.tw > kTileM) p.tw = kTileM;
     p.th = pow2_ceil(d->conv_h); if (p.th > kTileM / p.tw) p.th = kTileM / p.tw;
@@ -414,7 +417,7 @@ extern "C" int pgpp_conv2d_igemm(const pgpp_conv_desc* d, void* stream) {
     p.tiles_x = (d->conv_w + p.tw - 1) / p.tw;
     p.tiles_y = (d->conv_h + p.th - 1) / p.th;
     p.tiles_n = (d->n + p.tn - 1) / p.tn;
-    p.tiles_col = (d->phases * d->o + d->block_n - 1) / d->block_n;
+    p.tiles_col = (d->phases * d->phase_stride + d->block_n - 1) / d->block_n;
     p.total_tiles = (long long)p.tiles_x * p.tiles_y * p.tiles_n * p.tiles_col;
     const unsigned row_bytes = (unsigned)p.kb * 2;
     p.a_bytes = kTileM * row_bytes;

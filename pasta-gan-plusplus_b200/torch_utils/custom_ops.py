@@ -32,7 +32,7 @@ class ConvDesc(ctypes.Structure):
         ('pad_y', ctypes.c_int32), ('pad_x', ctypes.c_int32),
         ('stride', ctypes.c_int32),
         ('conv_h', ctypes.c_int32), ('conv_w', ctypes.c_int32),
-        ('o', ctypes.c_int32), ('phases', ctypes.c_int32), ('o_rows', ctypes.c_int32), ('block_n', ctypes.c_int32),
+        ('o', ctypes.c_int32), ('phases', ctypes.c_int32), ('phase_stride', ctypes.c_int32), ('o_rows', ctypes.c_int32), ('block_n', ctypes.c_int32),
         ('products', ctypes.c_int32),
         ('dcoef', ctypes.c_void_p), ('noise', ctypes.c_void_p), ('noise_stride_n', ctypes.c_int64), ('bias', ctypes.c_void_p),
         ('act_fn', ctypes.c_int32), ('alpha', ctypes.c_float), ('gain', ctypes.c_float), ('clamp', ctypes.c_float),
@@ -106,6 +106,17 @@ def _same_layout(a, b):
     return all(sa == sb and (sa < 2 or ta == tb) for sa, sb, ta, tb in zip(a.shape, b.shape, a.stride(), b.stride()))
 
 
+def _is_dense(t):
+    """non-overlapping and dense (any dimension order), like at::Tensor::is_non_overlapping_and_dense"""
+    dims = sorted(((st, sz) for sz, st in zip(t.shape, t.stride()) if sz > 1))
+    expect = 1
+    for st, sz in dims:
+        if st != expect:
+            return False
+        expect *= sz
+    return True
+
+
 def dtype_code(dtype):
     _torch_check(dtype in _DTYPES, f'unsupported dtype {dtype}')
     return _DTYPES[dtype]
@@ -128,7 +139,7 @@ class _BiasActPlugin:
         _torch_check(b.numel() == 0 or (0 <= dim < x.dim()), 'dim is out of bounds')
         _torch_check(b.numel() == 0 or b.numel() == x.shape[dim], 'b has wrong number of elements')
         _torch_check(grad >= 0, 'grad must be non-negative')
-        _torch_check(x.is_non_overlapping_and_dense(), 'x must be non-overlapping and dense')
+        _torch_check(_is_dense(x), 'x must be non-overlapping and dense')
         _torch_check(b.is_contiguous(), 'b must be contiguous')
         for t, name in ((xref, 'xref'), (yref, 'yref'), (dy, 'dy')):
             _torch_check(t.numel() == 0 or _same_layout(t, x), f'{name} must have the same layout as x')

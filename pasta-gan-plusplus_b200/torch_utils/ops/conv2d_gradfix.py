@@ -33,6 +33,7 @@ fp32_precision = 'bf16x2'
 _PRODUCTS = {'bf16': (1, 1), 'bf16x2': (3, 2), 'bf16x3': (6, 3)}    # name -> (products, parts)
 _ACT_IDX = {'linear': 1, 'relu': 2, 'lrelu': 3, 'tanh': 4, 'sigmoid': 5, 'elu': 6, 'selu': 7, 'softplus': 8, 'swish': 9}
 _plugin = None
+trace = None        # set to a list to record (label, algorithmic FLOPs, start event, end event) per igemm launch (bench.py roofline)
 
 
 @contextlib.contextmanager
@@ -87,7 +88,7 @@ def _split_bf16(t, parts):
 
 class PackedWeights:
     """[parts, taps, o_rows, c_pad] bf16, K-major rows, ready for the TMA weight map."""
-    __slots__ = ('data', 'kh', 'kw', 'o', 'phases', 'o_rows', 'c_pad', 'parts', 'pad_y', 'pad_x')
+    __slots__ = ('data', 'kh', 'kw', 'o', 'phases', 'phase_stride', 'o_rows', 'c_pad', 'parts', 'pad_y', 'pad_x')
 
 
 def choose_block_n(cols, m_tiles, sms=148):
@@ -100,16 +101,20 @@ def choose_block_n(cols, m_tiles, sms=148):
 
 
 def pack_weights(w_taps, o, phases, kh, kw, parts, pad_y, pad_x):
-    """w_taps: float32 [taps, phases*o, I] -> PackedWeights (rows padded to a multiple of 256 or of the
-    power-of-two >= cols, channels to a multiple of 16)."""
-    taps, cols, ic = w_taps.shape
+    """w_taps: float32 [taps, phases*o, I] -> PackedWeights.  GEMM column of (phase, oc) is phase*phase_stride + oc
+    (phase_stride = o rounded up to 16 when phases == 4); rows are padded to a multiple of 256 or to the
+    power-of-two >= cols, channels to a multiple of 16."""
+    taps, _, ic = w_taps.shape
+    phase_stride = _round_up(o, 16) if phases > 1 else o
+    cols = phases * phase_stride
     c_pad = _round_up(ic, 16)
     o_rows = _round_up(cols, 256) if cols > 128 else max(16, 1 << (cols - 1).bit_length())
     buf = torch.zeros([taps, o_rows, c_pad], dtype=torch.float32, device=w_taps.device)
-    buf[:, :cols, :ic] = w_taps
+    buf[:, :cols].reshape(taps, phases, phase_stride, c_pad)[:, :, :o, :ic] = w_taps.reshape(taps, phases, o, ic)
     pw = PackedWeights()
     pw.data = _split_bf16(buf, parts).contiguous()
     pw.kh, pw.kw, pw.o, pw.phases, pw.o_rows, pw.c_pad, pw.parts = kh, kw, o, phases, o_rows, c_pad, parts
+    pw.phase_stride = phase_stride
     pw.pad_y, pw.pad_x = pad_y, pad_x
     return pw
 
@@ -130,11 +135,12 @@ def _cached(key_tensor, tag, builder):
     return hit[0]
 
 
-def packed_plain(weight, flip_weight, parts, pad_y, pad_x, transpose_io=False):
+def packed_plain(weight, flip_weight, parts, pad_y, pad_x, transpose_io=False, scale=1.0):
     """weight [O, I, kh, kw] used as a correlation kernel (flip_weight=True, F.conv2d semantics) or a true
-    convolution kernel (flip_weight=False).  transpose_io: weight is [I, O, kh, kw] (conv_transpose2d layout)."""
+    convolution kernel (flip_weight=False).  transpose_io: weight is [I, O, kh, kw] (conv_transpose2d layout).
+    scale: constant folded into the packed copy (the layers' runtime weight_gain, networks.py:155,169)."""
     def build():
-        w = weight.detach().to(torch.float32)
+        w = weight.detach().to(torch.float32) * float(scale)
         if transpose_io:
             w = w.transpose(0, 1)
         if not flip_weight:
@@ -142,7 +148,7 @@ def packed_plain(weight, flip_weight, parts, pad_y, pad_x, transpose_io=False):
         o, ic, kh, kw = w.shape
         taps = w.permute(2, 3, 0, 1).reshape(kh * kw, o, ic)
         return pack_weights(taps, o, 1, kh, kw, parts, pad_y, pad_x)
-    return _cached(weight, ('plain', bool(flip_weight), parts, pad_y, pad_x, bool(transpose_io)), build)
+    return _cached(weight, ('plain', bool(flip_weight), parts, pad_y, pad_x, bool(transpose_io), float(scale)), build)
 
 
 def packed_up2(weight, f, flip_weight, flip_filter, parts):
@@ -217,7 +223,7 @@ def igemm_conv(x, pw, *, scale=None, stride=1, out_hw=None, dcoef=None, noise=No
     th = min(128 // tw, 1 << (conv_h - 1).bit_length())
     tn = 128 // (tw * th)
     m_tiles = -(-conv_w // tw) * -(-conv_h // th) * -(-n // tn)
-    block_n = choose_block_n(pw.phases * pw.o, m_tiles)
+    block_n = choose_block_n(pw.phases * pw.phase_stride, m_tiles)
     while pw.o_rows % block_n:
         block_n //= 2
 
@@ -227,7 +233,7 @@ def igemm_conv(x, pw, *, scale=None, stride=1, out_hw=None, dcoef=None, noise=No
     d.n, d.h, d.w, d.c_pad = n, h, w, pw.c_pad
     d.kh, d.kw, d.pad_y, d.pad_x, d.stride = pw.kh, pw.kw, pw.pad_y, pw.pad_x, stride
     d.conv_h, d.conv_w = conv_h, conv_w
-    d.o, d.phases, d.o_rows, d.block_n, d.products = pw.o, pw.phases, pw.o_rows, block_n, products
+    d.o, d.phases, d.phase_stride, d.o_rows, d.block_n, d.products = pw.o, pw.phases, pw.phase_stride, pw.o_rows, block_n, products
     keep = []
     def fptr(t):
         if t is None:
@@ -252,7 +258,16 @@ def igemm_conv(x, pw, *, scale=None, stride=1, out_hw=None, dcoef=None, noise=No
     d.out_h, d.out_w = out_h, out_w
     d.out_stride = (ctypes.c_int64 * 4)(*out.stride())
     d.accumulate = int(bool(accumulate))
-    _plugin.conv2d_igemm(d, x.device)
+    if trace is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        _plugin.conv2d_igemm(d, x.device)
+        e1.record()
+        # algorithmic FLOPs: 2*N*O*I*kh*kw*P; for the polyphase up=2 form the transposed conv's 9 taps per INPUT pixel
+        flops = 2.0 * n * pw.o * ic * (9 if pw.phases == 4 else pw.kh * pw.kw) * conv_h * conv_w
+        trace.append((f'igemm {ic}->{pw.o} k{pw.kh} {h}x{w}->{out_h}x{out_w} n{n} {precision}', flops, e0, e1))
+    else:
+        _plugin.conv2d_igemm(d, x.device)
     return out
 
 

@@ -27,7 +27,8 @@ def emulate_igemm(x, pw, scale=None, stride=1, parts=None):
     if scale is not None:
         xs = xs * scale.double().cpu().reshape(n, c, 1, 1)
     cols = pw.phases * pw.o
-    wk = w[:, :cols, :c].reshape(pw.kh, pw.kw, cols, c).permute(2, 3, 0, 1)      # [cols, c, kh, kw]
+    wsel = w[:, :pw.phases * pw.phase_stride].reshape(w.shape[0], pw.phases, pw.phase_stride, -1)[:, :, :pw.o, :c]
+    wk = wsel.reshape(pw.kh, pw.kw, cols, c).permute(2, 3, 0, 1)      # [cols, c, kh, kw]
     xp = F.pad(xs, [pw.pad_x, pw.kw, pw.pad_y, pw.kh])      # generous bottom/right zero padding
     y = F.conv2d(xp, wk, stride=stride)
     conv_h = (h + 2 * pw.pad_y - pw.kh) // stride + 1
@@ -36,3 +37,18 @@ def emulate_igemm(x, pw, scale=None, stride=1, parts=None):
     if pw.phases == 4:
         y = y.reshape(n, 2, 2, pw.o, conv_h, conv_w).permute(0, 3, 4, 1, 5, 2).reshape(n, pw.o, conv_h * 2, conv_w * 2)
     return y
+
+
+import contextlib
+
+
+@contextlib.contextmanager
+def upfirdn2d_ref_on_cpu(upfirdn2d_module):
+    """CPU tests of the callers: conv2d_resample reaches upfirdn2d with the default impl='cuda', which by design
+    refuses CPU tensors; route those calls to the module's own PyTorch path for the duration of the test."""
+    orig = upfirdn2d_module.upfirdn2d
+    upfirdn2d_module.upfirdn2d = lambda *a, **k: orig(*a, **{**k, 'impl': 'ref'})
+    try:
+        yield
+    finally:
+        upfirdn2d_module.upfirdn2d = orig

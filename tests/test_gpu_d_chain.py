@@ -1,0 +1,67 @@
+"""GPU parity of the synthesis chain (the callers of the hot path) against the CPU oracle chain."""
+import importlib
+
+import pytest
+import torch
+
+from conftest import load_pkg
+from helpers import max_abs, rel_l2
+from oracle import ref_chain
+
+pytestmark = pytest.mark.gpu
+load_pkg()
+synthesis = importlib.import_module('pgpp_b200.training.synthesis')
+cg = importlib.import_module('pgpp_b200.torch_utils.ops.conv2d_gradfix')
+custom_ops = importlib.import_module('pgpp_b200.torch_utils.custom_ops')
+DEV = 'cuda:0'
+
+
+def _net(**kw):
+    torch.manual_seed(0)
+    net = synthesis.SynthesisChain(**kw).eval()
+    for name, p in net.named_parameters():
+        if name.endswith('noise_strength'):
+            p.data.fill_(0.25)
+        if name.endswith('bias') and 'affine' not in name:
+            p.data.normal_(0, 0.5)
+    return net
+
+
+@pytest.mark.parametrize('prec,tol', [('bf16x3', 5e-5), ('bf16x2', 1e-4), ('bf16', 3e-2)])
+def test_small_chain_fused_and_composition_routes(prec, tol):
+    old = cg.fp32_precision
+    cg.fp32_precision = prec
+    try:
+        net = _net(w_dim=64, img_resolution=64, channel_base=2048, channel_max=48, merge_channels=16)
+        n = 3
+        ws = torch.randn(n, net.num_ws, 64); pose = torch.randn(n, net.channels[8], 8, 8)
+        cat = {'64': torch.randn(n, 16, 64, 64)}
+        sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
+        want = ref_chain.synthesis_chain(sd, ws, pose, cat, img_resolution=64)
+        net = net.to(DEV)
+        catd = {k: v.to(DEV) for k, v in cat.items()}
+        with torch.no_grad():
+            for fused in (True, False):
+                got = net(ws.to(DEV), pose.to(DEV), catd, fused=fused, noise_mode='const')
+                for g, w, name in zip(got, want, ('img', 'parsing', 'texture')):
+                    assert rel_l2(g, w) < tol, (prec, fused, name, rel_l2(g, w))
+    finally:
+        cg.fp32_precision = old
+
+
+def test_full_size_512_chain_batch1_against_cpu_oracle():
+    """the bench workload itself at batch 1: north-star tolerance, abs error relative to the output scale"""
+    net = _net(w_dim=512, img_resolution=512)
+    ws = torch.randn(1, net.num_ws, 512); pose = torch.randn(1, 512, 8, 8)
+    cat = {str(r): torch.randn(1, 64, r, r).clamp_(-1, 1) for r in (64, 128, 256, 512)}
+    sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    want = ref_chain.synthesis_chain(sd, ws, pose, cat, img_resolution=512)
+    net = net.to(DEV)
+    before = custom_ops.launch_count()
+    with torch.no_grad():
+        got = net(ws.to(DEV), pose.to(DEV), {k: v.to(DEV) for k, v in cat.items()}, noise_mode='const')
+    assert custom_ops.launch_count() - before >= 24 * 3      # demod + pack + igemm per modulated conv
+    for g, w, name in zip(got, want, ('img', 'parsing', 'texture')):
+        assert tuple(g.shape) == tuple(w.shape)
+        assert rel_l2(g, w) < 1e-4, (name, rel_l2(g, w))
+        assert max_abs(g, w) <= 1e-3 * max(1.0, float(w.abs().max())), (name, max_abs(g, w), float(w.abs().max()))

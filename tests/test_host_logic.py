@@ -10,7 +10,7 @@ import pytest
 import torch
 
 from conftest import GOLDEN, ROOT, load_pkg
-from helpers import emulate_igemm, rel_l2, t
+from helpers import emulate_igemm, rel_l2, t, upfirdn2d_ref_on_cpu
 from oracle import ref_ops
 from oracle.make_golden import CONV_CASES, MODCONV_CASES, UPFIRDN_CASES
 
@@ -187,3 +187,50 @@ def test_block_n_choice():
     assert conv2d_gradfix.choose_block_n(64, 10000) == 64
     assert conv2d_gradfix.choose_block_n(512, 10000) == 256
     assert conv2d_gradfix.choose_block_n(512, 16) <= 64       # few pixel tiles -> more column tiles to fill 148 SMs
+
+
+def test_polyphase_weights_with_out_channels_not_multiple_of_16():
+    g = torch.Generator().manual_seed(6)
+    f = upfirdn2d.setup_filter([1, 3, 3, 1])
+    x = torch.randn(1, 8, 6, 6, generator=g)
+    w = torch.randn(24, 8, 3, 3, generator=g)
+    pw = conv2d_gradfix.packed_up2(w, f, False, False, 3)
+    assert pw.phase_stride == 32 and pw.o == 24 and pw.o_rows == 128
+    assert rel_l2(emulate_igemm(x, pw), ref_ops.conv2d_resample(x, w, f=f, up=2, padding=1, flip_weight=False)) < 3e-7
+
+
+def test_conv_desc_mirror_matches_c_struct_layout(tmp_path):
+    import subprocess
+    src = tmp_path / 'sz.c'
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "pgpp.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu\\n",'
+                   'sizeof(pgpp_conv_desc),offsetof(pgpp_conv_desc,phase_stride),offsetof(pgpp_conv_desc,dcoef),'
+                   'offsetof(pgpp_conv_desc,out),offsetof(pgpp_conv_desc,out_stride),offsetof(pgpp_conv_desc,accumulate));return 0;}\n')
+    exe = tmp_path / 'sz'
+    subprocess.run(['gcc', '-I', os.path.join(ROOT, 'include'), str(src), '-o', str(exe)], check=True)
+    c = [int(v) for v in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()]
+    D = custom_ops.ConvDesc
+    assert c == [ctypes.sizeof(D), D.phase_stride.offset, D.dcoef.offset, D.out.offset, D.out_stride.offset, D.accumulate.offset]
+
+
+def test_synthesis_chain_composition_path_matches_oracle_chain_on_cpu():
+    """host logic of the callers (layer wiring, ws bookkeeping, gains, clamps) with impl='ref' on the CPU"""
+    from oracle import ref_chain
+    synthesis = importlib.import_module('pgpp_b200.training.synthesis')
+    torch.manual_seed(0)
+    net = synthesis.SynthesisChain(w_dim=32, img_resolution=64, channel_base=1024, channel_max=32, merge_channels=8).eval()
+    for name, p in net.named_parameters():
+        if name.endswith('noise_strength'):
+            p.data.fill_(0.3)
+        if name.endswith('bias') and 'affine' not in name:
+            p.data.normal_()
+    n = 2
+    ws = torch.randn(n, net.num_ws, 32)
+    pose = torch.randn(n, net.channels[8], 8, 8)
+    cat = {'64': torch.randn(n, 8, 64, 64)}
+    with torch.no_grad(), upfirdn2d_ref_on_cpu(upfirdn2d):
+        img, parsing, tex = net(ws, pose, cat, fused=False, impl='ref', noise_mode='const')
+    sd = {k: v.detach() for k, v in net.state_dict().items()}
+    rimg, rpars, rtex = ref_chain.synthesis_chain(sd, ws, pose, cat, img_resolution=64)
+    assert img.shape == (n, 3, 64, 64) and parsing.shape == (n, 7, 64, 64) and tex.shape == (n, 3, 64, 64)
+    assert rel_l2(img, rimg) < 1e-5 and rel_l2(parsing, rpars) < 1e-5 and rel_l2(tex, rtex) < 1e-5
+    assert net.num_ws == 1 + 1 + 3 * 3 + 3
