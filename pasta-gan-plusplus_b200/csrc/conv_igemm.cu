@@ -12,36 +12,53 @@
 // The split-precision ("fp32 parity") mode runs the same loop over products (a_part, b_part) of
 // the bf16 expansions of both operands, all accumulated in the same fp32 TMEM tile.
 //
-// Warp roles (192 threads, 1 CTA per SM):
+// Operand traffic (the C<=128 layers are bounded by L2->SM bandwidth, not by the tensor pipe, unless tiles are reused):
+//   * ky reuse: for stride-1 convs the producer loads one activation slab of (TH + kh - 1) image rows per (kx, channel
+//     block) and the kh vertical taps are issued from row-shifted views of it (descriptor start + ky*TW rows; the
+//     shift is a multiple of the 8-row swizzle atom, so no re-swizzling is involved);
+//   * product sharing: all bf16 parts of A (slabs) and B (tiles) are loaded once per K group and every product
+//     (a_part, b_part) of the split-precision mode is issued from them;
+//   * resident weights: when all weight tiles of a column tile fit next to the activation ring (64->64 3x3, ToRGB)
+//     they are loaded once per CTA and stay in shared memory for every pixel tile the CTA processes.
+//
+// Warp roles (320 threads, 1 CTA per SM):
 //   warp 0      TMA producer        (one elected lane)
 //   warp 1      TMEM owner + tcgen05.mma issuer (one elected lane)
-//   warps 2-5   epilogue: tcgen05.ld -> demod / noise / bias / activation / clamp -> global store
+//   warps 2-9   epilogue (two warps per TMEM lane quarter, each half of the columns): tcgen05.ld -> demod / noise /
+//               bias / activation / clamp -> global store
 // Accumulators are double-buffered in TMEM so the epilogue of tile i overlaps the MMAs of tile i+1.
 //
 // Replaces the cuDNN calls of torch_utils/ops/conv2d_gradfix.py:38,43,112-114 and the grouped-conv
 // formulation of training/networks.py:85-93 (algebraically the non-fused form, networks.py:73-82).
 #include <cuda.h>
+#include <stdlib.h>
 #include "act.cuh"
 
 namespace pgpp {
 
-constexpr int kThreads = 192;
+constexpr int kThreads = 320;      // 2 control warps + 8 epilogue warps
+
 constexpr int kTileM = 128;
-constexpr int kMaxStages = 8;
 
 struct IgemmParams {
     int n, h, w;
     int conv_h, conv_w;
     int kh, kw, pad_y, pad_x, stride;
     int num_cb, kb;
-    int products, pa[6], pb[6];
+    int parts;                          // bf16 parts used of each operand (1, 2, 3)
+    unsigned pa_mask[3];                // pa_mask[pb]: which A parts multiply B part pb
+    int n_groups, inner;                // K groups per channel block (kw with ky reuse, kh*kw without) and taps per group (kh or 1)
+    int reuse;                          // 1: one activation slab per (kx, cb), vertical taps are row-shifted views
     int o, phases, phase_stride, o_rows, block_n;
     int tw, th, tn;
     int tiles_x, tiles_y, tiles_n, tiles_col;
     long long total_tiles;
-    int num_stages;
-    unsigned a_bytes, b_bytes;          // bytes one TMA box delivers (armed on the full barrier)
-    unsigned b_off, stage_bytes;        // B offset inside a stage, stage pitch (1024-byte multiples)
+    int a_stages, b_stages, b_resident;
+    unsigned slab_bytes;                // one A part of one stage (= bytes of one activation TMA box)
+    unsigned a_stage_bytes;             // stage pitch: parts * slab_bytes rounded up to 1024
+    unsigned a_tx_bytes;                // parts * slab_bytes: bytes the activation TMA boxes of one stage deliver
+    unsigned b_bytes, b_pitch;          // bytes of one weight TMA box, slot pitch (1024-byte multiple)
+    unsigned ky_step_bytes;             // TW * row_bytes: shift of the slab view per vertical tap
     unsigned layout_type, sbo_bytes;
     unsigned idesc;
     unsigned tmem_cols;
@@ -152,20 +169,23 @@ template <> __device__ __forceinline__ float cvt_in<float>(float v) { return v; 
 template <> __device__ __forceinline__ float cvt_in<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
 template <> __device__ __forceinline__ float cvt_in<__half>(__half v) { return __half2float(v); }
 
-// Epilogue of one 128 x block_n accumulator tile for the calling warp's 32 TMEM lanes.
+// Epilogue of one accumulator tile for the calling warp: its 32 TMEM lanes (pixels) x columns [col_begin, col_end).
+// Per-column demodulation scale and bias come from shared memory (staged once per tile) when the tile holds a single
+// sample; tiny-image tiles that span several samples read them through the read-only path instead.
 template <int A, class OT>
-__device__ __forceinline__ void epilogue_tile(const IgemmParams& p, const TileCoord tc, uint32_t tmem_tile, int lane_row) {
-    // this thread's pixel
+__device__ __forceinline__ void epilogue_tile(const IgemmParams& p, const TileCoord tc, uint32_t tmem_tile, int lane_row,
+                                              int col_begin, int col_end, const float* s_scale, const float* s_shift, bool staged) {
     const int px = lane_row % p.tw;
     const int py = (lane_row / p.tw) % p.th;
     const int pn = lane_row / (p.tw * p.th);
     const int x = tc.x0 + px, y = tc.y0 + py, n = tc.n0 + pn;
     const bool pix_ok = x < p.conv_w && y < p.conv_h && n < p.n;
     const int total_cols = p.phases * p.phase_stride;
-    OT* out = (OT*)p.out;
+    OT* const out = (OT*)p.out;
     const float alpha = p.alpha, gain = p.gain, clamp = p.clamp;
+    const long long cs = p.os_c;
 
-    for (int c0 = 0; c0 < p.block_n; c0 += 16) {
+    for (int c0 = col_begin; c0 < col_end; c0 += 16) {
         float v[16];
         tmem_ld16(tmem_tile + c0, v);       // warp-collective: executed by all lanes, valid pixel or not
         const int g0 = tc.col0 + c0;
@@ -178,20 +198,30 @@ __device__ __forceinline__ void epilogue_tile(const IgemmParams& p, const TileCo
         if (p.noise) nz = __ldg(p.noise + n * p.noise_stride_n + (long long)oy * p.out_w + ox);
         const long long base = n * p.os_n + oy * p.os_h + ox * p.os_w;
         const int valid = min(16, p.o - oc0);
-        #pragma unroll
-        for (int j = 0; j < 16; j++) {
-            if (j < valid) {
-                const int oc = oc0 + j;
-                float r = v[j];
-                if (p.dcoef) r *= __ldg(p.dcoef + (long long)n * p.o + oc);
-                r += nz;
-                if (p.bias) r += __ldg(p.bias + oc);
+        if (staged) {
+            #pragma unroll
+            for (int j = 0; j < 16; j++) {
+                float r = fmaf(v[j], s_scale[c0 + j], nz) + s_shift[c0 + j];
                 r = act_forward<A, float>(r, alpha) * gain;
                 if (clamp >= 0.f) r = fminf(fmaxf(r, -clamp), clamp);
                 v[j] = r;
             }
+        } else {
+            #pragma unroll
+            for (int j = 0; j < 16; j++) {
+                if (j < valid) {
+                    const int oc = oc0 + j;
+                    float r = v[j];
+                    if (p.dcoef) r *= __ldg(p.dcoef + (long long)n * p.o + oc);
+                    r += nz;
+                    if (p.bias) r += __ldg(p.bias + oc);
+                    r = act_forward<A, float>(r, alpha) * gain;
+                    if (clamp >= 0.f) r = fminf(fmaxf(r, -clamp), clamp);
+                    v[j] = r;
+                }
+            }
         }
-        if (p.os_c == 1 && valid == 16 && !p.accumulate && ((base + oc0) * sizeof(OT)) % 16 == 0 && ((uintptr_t)out & 15) == 0) {
+        if (cs == 1 && valid == 16 && !p.accumulate && ((base + oc0) * sizeof(OT)) % 16 == 0 && ((uintptr_t)out & 15) == 0) {
             // channels-innermost output: 16 consecutive channels of one pixel, 128-bit stores
             __align__(16) OT tmp[16];
             #pragma unroll
@@ -200,50 +230,62 @@ __device__ __forceinline__ void epilogue_tile(const IgemmParams& p, const TileCo
             const int4* src = reinterpret_cast<const int4*>(tmp);
             #pragma unroll
             for (int q = 0; q < (int)(16 * sizeof(OT) / 16); q++) dst[q] = src[q];
-        } else {
+        } else if (valid == 16 && !p.accumulate) {
             // NCHW-like output: for a fixed channel the warp's lanes are consecutive pixels of a row
+            OT* dst = out + base + (long long)oc0 * cs;
+            #pragma unroll
+            for (int j = 0; j < 16; j++) { *dst = cvt_out<OT>(v[j]); dst += cs; }
+        } else {
+            OT* dst = out + base + (long long)oc0 * cs;
             #pragma unroll
             for (int j = 0; j < 16; j++) {
                 if (j < valid) {
-                    OT* dst = out + base + (long long)(oc0 + j) * p.os_c;
                     float r = v[j];
                     if (p.accumulate) r += cvt_in<OT>(*dst);
                     *dst = cvt_out<OT>(r);
                 }
+                dst += cs;
             }
         }
     }
 }
 
 template <class OT>
-__device__ __forceinline__ void epilogue_dispatch(const IgemmParams& p, const TileCoord tc, uint32_t tmem_tile, int lane_row) {
+__device__ __forceinline__ void epilogue_dispatch(const IgemmParams& p, const TileCoord tc, uint32_t tmem_tile, int lane_row,
+                                                  int col_begin, int col_end, const float* s_scale, const float* s_shift, bool staged) {
+#define PGPP_EPI(ACT) epilogue_tile<ACT, OT>(p, tc, tmem_tile, lane_row, col_begin, col_end, s_scale, s_shift, staged)
     switch (p.act_fn) {
-        case PGPP_ACT_LINEAR:   epilogue_tile<PGPP_ACT_LINEAR, OT>(p, tc, tmem_tile, lane_row); break;
-        case PGPP_ACT_RELU:     epilogue_tile<PGPP_ACT_RELU, OT>(p, tc, tmem_tile, lane_row); break;
-        case PGPP_ACT_LRELU:    epilogue_tile<PGPP_ACT_LRELU, OT>(p, tc, tmem_tile, lane_row); break;
-        case PGPP_ACT_TANH:     epilogue_tile<PGPP_ACT_TANH, OT>(p, tc, tmem_tile, lane_row); break;
-        case PGPP_ACT_SIGMOID:  epilogue_tile<PGPP_ACT_SIGMOID, OT>(p, tc, tmem_tile, lane_row); break;
-        case PGPP_ACT_ELU:      epilogue_tile<PGPP_ACT_ELU, OT>(p, tc, tmem_tile, lane_row); break;
-        case PGPP_ACT_SELU:     epilogue_tile<PGPP_ACT_SELU, OT>(p, tc, tmem_tile, lane_row); break;
-        case PGPP_ACT_SOFTPLUS: epilogue_tile<PGPP_ACT_SOFTPLUS, OT>(p, tc, tmem_tile, lane_row); break;
-        default:                epilogue_tile<PGPP_ACT_SWISH, OT>(p, tc, tmem_tile, lane_row); break;
+        case PGPP_ACT_LINEAR: PGPP_EPI(PGPP_ACT_LINEAR); break;
+        case PGPP_ACT_RELU: PGPP_EPI(PGPP_ACT_RELU); break;
+        case PGPP_ACT_LRELU: PGPP_EPI(PGPP_ACT_LRELU); break;
+        case PGPP_ACT_TANH: PGPP_EPI(PGPP_ACT_TANH); break;
+        case PGPP_ACT_SIGMOID: PGPP_EPI(PGPP_ACT_SIGMOID); break;
+        case PGPP_ACT_ELU: PGPP_EPI(PGPP_ACT_ELU); break;
+        case PGPP_ACT_SELU: PGPP_EPI(PGPP_ACT_SELU); break;
+        case PGPP_ACT_SOFTPLUS: PGPP_EPI(PGPP_ACT_SOFTPLUS); break;
+        default: PGPP_EPI(PGPP_ACT_SWISH); break;
     }
+#undef PGPP_EPI
 }
 
 __global__ void __launch_bounds__(kThreads, 1)
 igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const IgemmParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    // carve: [stage][A | B] (1024-byte aligned), then barriers
+    // carve: [A ring: a_stages x parts slabs][B slots: b_stages x b_pitch] (1024-byte aligned), then barriers
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const uint32_t stage_bytes = p.stage_bytes;
-    const uint32_t bar_base = smem_base + p.num_stages * stage_bytes;
-    // barrier i at bar_base + 8*i : full[0..S), empty[S..2S), tmem_full[2S, 2S+2), tmem_empty[2S+2, 2S+4); then tmem ptr
-    const int S = p.num_stages;
-    auto full_bar = [&](int s) { return bar_base + 8u * s; };
-    auto empty_bar = [&](int s) { return bar_base + 8u * (S + s); };
-    auto tfull_bar = [&](int b) { return bar_base + 8u * (2 * S + b); };
-    auto tempty_bar = [&](int b) { return bar_base + 8u * (2 * S + 2 + b); };
-    const uint32_t tmem_slot = bar_base + 8u * (2 * S + 4);
+    const uint32_t b_base = smem_base + p.a_stages * p.a_stage_bytes;
+    const uint32_t bar_base = b_base + p.b_stages * p.b_pitch;
+    const int SA = p.a_stages, SB = p.b_stages;
+    // barrier i at bar_base + 8*i
+    auto afull_bar = [&](int s) { return bar_base + 8u * s; };
+    auto aempty_bar = [&](int s) { return bar_base + 8u * (SA + s); };
+    auto bfull_bar = [&](int s) { return bar_base + 8u * (2 * SA + s); };
+    auto bempty_bar = [&](int s) { return bar_base + 8u * (2 * SA + SB + s); };
+    auto tfull_bar = [&](int b) { return bar_base + 8u * (2 * SA + 2 * SB + b); };
+    auto tempty_bar = [&](int b) { return bar_base + 8u * (2 * SA + 2 * SB + 2 + b); };
+    const uint32_t tmem_slot = bar_base + 8u * (2 * SA + 2 * SB + 4);
+    // per-column epilogue parameters, double-buffered with the accumulator: [2][256] scale, [2][256] shift
+    float* const s_params = reinterpret_cast<float*>(smem_raw + (tmem_slot + 16u - smem_u32(smem_raw)));
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -251,8 +293,9 @@ igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
     if (warp == 0 && elect_one()) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
-        for (int s = 0; s < S; s++) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-        for (int b = 0; b < 2; b++) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), 4); }   // 4 epilogue warps arrive
+        for (int s = 0; s < SA; s++) { mbar_init(afull_bar(s), 1); mbar_init(aempty_bar(s), 1); }
+        for (int s = 0; s < SB; s++) { mbar_init(bfull_bar(s), 1); mbar_init(bempty_bar(s), 1); }
+        for (int b = 0; b < 2; b++) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), 8); }   // 8 epilogue warps arrive
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -266,74 +309,141 @@ igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
     uint32_t tmem_base;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
-    const int taps = p.kh * p.kw;
-    const int k_iters = taps * p.num_cb * p.products;
-
     if (warp == 0) {
         // ===================== TMA producer =====================
         if (elect_one()) {
-            int stage = 0; uint32_t phase = 0;
+            int sa = 0; uint32_t pha = 0;
+            int sb = 0; uint32_t phb = 0;
+            bool first_tile = true;
             for (long long t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
                 const TileCoord tc = decode_tile(p, t);
-                for (int tap = 0; tap < taps; tap++) {
-                    const int ky = tap / p.kw, kx = tap - ky * p.kw;
+                int b_slot = 0;
+                for (int g = 0; g < p.n_groups; g++) {
+                    // reuse: group = kx, the slab spans all ky;  no reuse: group = tap
+                    const int ky0 = p.reuse ? 0 : g / p.kw;
+                    const int kx = p.reuse ? g : g - ky0 * p.kw;
                     const int ix = tc.x0 * p.stride + kx - p.pad_x;
-                    const int iy = tc.y0 * p.stride + ky - p.pad_y;
+                    const int iy = tc.y0 * p.stride + ky0 - p.pad_y;
                     for (int cb = 0; cb < p.num_cb; cb++) {
-                        for (int pr = 0; pr < p.products; pr++) {
-                            mbar_wait(empty_bar(stage), phase ^ 1);
-                            const uint32_t a_dst = smem_base + stage * stage_bytes;
-                            const uint32_t b_dst = a_dst + p.b_off;
-                            mbar_expect_tx(full_bar(stage), p.a_bytes + p.b_bytes);
-                            tma_load_5d(a_dst, &map_a, full_bar(stage), cb * p.kb, ix, iy, tc.n0, p.pa[pr]);
-                            tma_load_3d(b_dst, &map_b, full_bar(stage), cb * p.kb, tap * p.o_rows + tc.col0, p.pb[pr]);
-                            if (++stage == S) { stage = 0; phase ^= 1; }
+                        mbar_wait(aempty_bar(sa), pha ^ 1);
+                        mbar_expect_tx(afull_bar(sa), p.a_tx_bytes);
+                        for (int pa = 0; pa < p.parts; pa++)
+                            tma_load_5d(smem_base + sa * p.a_stage_bytes + pa * p.slab_bytes, &map_a, afull_bar(sa), cb * p.kb, ix, iy, tc.n0, pa);
+                        if (++sa == SA) { sa = 0; pha ^= 1; }
+                        for (int j = 0; j < p.inner; j++) {
+                            const int tap = (ky0 + j) * p.kw + kx;
+                            for (int pb = 0; pb < p.parts; pb++) {
+                                if (p.b_resident) {
+                                    if (first_tile) {
+                                        mbar_expect_tx(bfull_bar(b_slot), p.b_bytes);
+                                        tma_load_3d(b_base + b_slot * p.b_pitch, &map_b, bfull_bar(b_slot), cb * p.kb, tap * p.o_rows + tc.col0, pb);
+                                    }
+                                    b_slot++;
+                                } else {
+                                    mbar_wait(bempty_bar(sb), phb ^ 1);
+                                    mbar_expect_tx(bfull_bar(sb), p.b_bytes);
+                                    tma_load_3d(b_base + sb * p.b_pitch, &map_b, bfull_bar(sb), cb * p.kb, tap * p.o_rows + tc.col0, pb);
+                                    if (++sb == SB) { sb = 0; phb ^= 1; }
+                                }
+                            }
                         }
                     }
                 }
+                first_tile = false;
             }
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
         if (elect_one()) {
-            int stage = 0; uint32_t phase = 0;
+            int sa = 0; uint32_t pha = 0;
+            int sb = 0; uint32_t phb = 0;
             int buf = 0; uint32_t buf_phase = 0;
             const int k_steps = p.kb / 16;                  // tcgen05.mma kind::f16 has K = 16
             for (long long t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
                 mbar_wait(tempty_bar(buf), buf_phase ^ 1);  // epilogue has drained this accumulator
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + (uint32_t)(buf * p.block_n);
-                for (int it = 0; it < k_iters; it++) {
-                    mbar_wait(full_bar(stage), phase);
-                    tc_fence_after();
-                    const uint32_t a_addr = smem_base + stage * stage_bytes;
-                    const uint32_t b_addr = a_addr + p.b_off;
-                    const uint64_t da = make_smem_desc(a_addr, p.layout_type, p.sbo_bytes);
-                    const uint64_t db = make_smem_desc(b_addr, p.layout_type, p.sbo_bytes);
-                    for (int k = 0; k < k_steps; k++) {
-                        // advance 16 elements (32 bytes) along K inside the swizzle row: +2 in the >>4 address field
-                        umma_bf16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), p.idesc, (it | k) != 0);
+                uint32_t acc = 0;
+                int b_slot = 0;
+                for (int g = 0; g < p.n_groups; g++) {
+                    for (int cb = 0; cb < p.num_cb; cb++) {
+                        mbar_wait(afull_bar(sa), pha);
+                        tc_fence_after();
+                        const uint32_t a_addr = smem_base + sa * p.a_stage_bytes;
+                        for (int j = 0; j < p.inner; j++) {
+                            for (int pb = 0; pb < p.parts; pb++) {
+                                uint32_t b_addr;
+                                if (p.b_resident) {
+                                    mbar_wait(bfull_bar(b_slot), 0);        // completes once; stays complete afterwards
+                                    b_addr = b_base + b_slot * p.b_pitch;
+                                    b_slot++;
+                                } else {
+                                    mbar_wait(bfull_bar(sb), phb);
+                                    b_addr = b_base + sb * p.b_pitch;
+                                }
+                                tc_fence_after();
+                                const uint64_t db = make_smem_desc(b_addr, p.layout_type, p.sbo_bytes);
+                                const unsigned mask = p.pa_mask[pb];
+                                for (int pa = 0; pa < p.parts; pa++) {
+                                    if (!((mask >> pa) & 1u)) continue;
+                                    const uint64_t da = make_smem_desc(a_addr + pa * p.slab_bytes + j * p.ky_step_bytes, p.layout_type, p.sbo_bytes);
+                                    for (int k = 0; k < k_steps; k++) {
+                                        // advance 16 elements (32 bytes) along K inside the swizzle row: +2 in the >>4 address field
+                                        umma_bf16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), p.idesc, acc);
+                                        acc = 1;
+                                    }
+                                }
+                                if (!p.b_resident) {
+                                    umma_commit(bempty_bar(sb));    // weight slot reusable once these MMAs retire
+                                    if (++sb == SB) { sb = 0; phb ^= 1; }
+                                }
+                            }
+                        }
+                        umma_commit(aempty_bar(sa));                // activation slab reusable
+                        if (++sa == SA) { sa = 0; pha ^= 1; }
                     }
-                    umma_commit(empty_bar(stage));          // smem slot reusable once these MMAs retire
-                    if (++stage == S) { stage = 0; phase ^= 1; }
                 }
-                umma_commit(tfull_bar(buf));                // accumulator complete -> epilogue
+                umma_commit(tfull_bar(buf));                        // accumulator complete -> epilogue
                 if (++buf == 2) { buf = 0; buf_phase ^= 1; }
             }
         }
     } else {
         // ===================== epilogue warps =====================
         const int quarter = warp & 3;                       // TMEM lane quarter this warp may access
+        const int half = (warp - 2) >> 2;                   // which half of the columns
         const int lane_row = quarter * 32 + lane;
+        const int etid = threadIdx.x - 64;                  // 0..255 among the epilogue threads
+        const int cols_per = p.block_n >= 32 ? p.block_n / 2 : p.block_n;
+        const int col_begin = half * cols_per;
+        const int col_end = (p.block_n >= 32 || half == 0) ? col_begin + cols_per : col_begin;
+        const bool staged = p.tn == 1;
         int buf = 0; uint32_t buf_phase = 0;
         for (long long t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
             const TileCoord tc = decode_tile(p, t);
+            float* s_scale = s_params + buf * 512;
+            float* s_shift = s_scale + 256;
+            if (staged) {
+                // stage scale/shift of this tile's columns (safe: the previous user of this buffer pair, tile t-2, finished
+                // before its accumulator was released, and every warp passed the barrier below for tile t-1 after that)
+                if (etid < p.block_n) {
+                    const int g = tc.col0 + etid;
+                    const int phase = g / p.phase_stride;
+                    const int oc = g - phase * p.phase_stride;
+                    float sc = 1.f, sh = 0.f;
+                    if (oc < p.o && phase < p.phases) {
+                        if (p.dcoef) sc = __ldg(p.dcoef + (long long)tc.n0 * p.o + oc);
+                        if (p.bias) sh = __ldg(p.bias + oc);
+                    }
+                    s_scale[etid] = sc; s_shift[etid] = sh;
+                }
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+            }
             mbar_wait(tfull_bar(buf), buf_phase);
             tc_fence_after();
             const uint32_t tmem_tile = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * p.block_n);
-            if (p.out_dtype == PGPP_F32) epilogue_dispatch<float>(p, tc, tmem_tile, lane_row);
-            else if (p.out_dtype == PGPP_BF16) epilogue_dispatch<__nv_bfloat16>(p, tc, tmem_tile, lane_row);
-            else epilogue_dispatch<__half>(p, tc, tmem_tile, lane_row);
+            if (p.out_dtype == PGPP_F32) epilogue_dispatch<float>(p, tc, tmem_tile, lane_row, col_begin, col_end, s_scale, s_shift, staged);
+            else if (p.out_dtype == PGPP_BF16) epilogue_dispatch<__nv_bfloat16>(p, tc, tmem_tile, lane_row, col_begin, col_end, s_scale, s_shift, staged);
+            else epilogue_dispatch<__half>(p, tc, tmem_tile, lane_row, col_begin, col_end, s_scale, s_shift, staged);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty_bar(buf));
@@ -405,47 +515,70 @@ extern "C" int pgpp_conv2d_igemm(const pgpp_conv_desc* d, void* stream) {
     p.kh = d->kh; p.kw = d->kw; p.pad_y = d->pad_y; p.pad_x = d->pad_x; p.stride = d->stride;
     p.kb = (d->c_pad % 64 == 0) ? 64 : ((d->c_pad % 32 == 0) ? 32 : 16);
     p.num_cb = d->c_pad / p.kb;
-    p.products = d->products;
-    static const int PA[6] = {0, 0, 1, 1, 0, 2}, PB[6] = {0, 1, 0, 1, 2, 0};
-    if (d->products == 3) { p.pa[0] = 0; p.pb[0] = 0; p.pa[1] = 0; p.pb[1] = 1; p.pa[2] = 1; p.pb[2] = 0; }
-    else for (int i = 0; i < 6; i++) { p.pa[i] = PA[i]; p.pb[i] = PB[i]; }
+    p.parts = need_parts;
+    // products of the bf16 expansions: parts 1 -> a0b0; 2 -> a0b0 + a1b0 + a0b1; 3 -> + a2b0 + a1b1 + a0b2
+    p.pa_mask[0] = (1u << need_parts) - 1u;
+    p.pa_mask[1] = need_parts == 3 ? 3u : 1u;
+    p.pa_mask[2] = 1u;
     p.o = d->o; p.phases = d->phases; p.phase_stride = d->phase_stride; p.o_rows = d->o_rows; p.block_n = d->block_n; p.up = up;
-    // pixel tile: TW x TH x TN = 128
-    p.tw = pow2_ceil(d->conv_w); if (p.tw > kTileM) p.tw = kTileM;
-    p.th = pow2_ceil(d->conv_h); if (p.th > kTileM / p.tw) p.th = kTileM / p.tw;
-    p.tn = kTileM / (p.tw * p.th);
+    // pixel tile TW x TH x TN = 128.  Stride-1 convs with kh > 1 on images of at least 16 x 8 use a 16 x 8 tile so that
+    // one slab of TH + kh - 1 rows serves all vertical taps (ky reuse); everything else takes the widest tile.
+    p.reuse = (d->stride == 1 && d->kh > 1 && d->conv_w >= 16 && d->conv_h >= 8 && d->kh <= 7) ? 1 : 0;
+    if (getenv("PGPP_IGEMM_NO_REUSE")) p.reuse = 0;
+    if (p.reuse) { p.tw = 16; p.th = 8; p.tn = 1; }
+    else {
+        p.tw = pow2_ceil(d->conv_w); if (p.tw > kTileM) p.tw = kTileM;
+        p.th = pow2_ceil(d->conv_h); if (p.th > kTileM / p.tw) p.th = kTileM / p.tw;
+        p.tn = kTileM / (p.tw * p.th);
+    }
+    p.n_groups = p.reuse ? d->kw : d->kh * d->kw;
+    p.inner = p.reuse ? d->kh : 1;
     p.tiles_x = (d->conv_w + p.tw - 1) / p.tw;
     p.tiles_y = (d->conv_h + p.th - 1) / p.th;
     p.tiles_n = (d->n + p.tn - 1) / p.tn;
     p.tiles_col = (d->phases * d->phase_stride + d->block_n - 1) / d->block_n;
     p.total_tiles = (long long)p.tiles_x * p.tiles_y * p.tiles_n * p.tiles_col;
     const unsigned row_bytes = (unsigned)p.kb * 2;
-    p.a_bytes = kTileM * row_bytes;
+    const int slab_rows = p.tn * (p.th + p.inner - 1) * p.tw;        // multiple of 8 (TW % 8 == 0 with reuse, 128 without)
+    p.slab_bytes = (unsigned)slab_rows * row_bytes;
+    p.a_tx_bytes = p.parts * p.slab_bytes;
+    p.a_stage_bytes = (p.a_tx_bytes + 1023u) & ~1023u;
+    p.ky_step_bytes = (unsigned)p.tw * row_bytes;
     p.b_bytes = (unsigned)d->block_n * row_bytes;
-    // keep every operand buffer 1024-byte aligned (swizzle atom alignment)
-    const unsigned a_al = (p.a_bytes + 1023u) & ~1023u, b_al = (p.b_bytes + 1023u) & ~1023u;
-    p.b_off = a_al;
-    p.stage_bytes = a_al + b_al;
+    p.b_pitch = (p.b_bytes + 1023u) & ~1023u;
     p.layout_type = row_bytes == 128 ? 2u : (row_bytes == 64 ? 4u : 6u);   // SWIZZLE_128B / 64B / 32B
     p.sbo_bytes = 8 * row_bytes;
     // instruction descriptor (cute/arch/mma_sm100_desc.hpp InstrDescriptor): fp32 accum, bf16 A/B, K-major, M = 128
     p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((unsigned)(d->block_n >> 3) << 17) | ((unsigned)(kTileM >> 4) << 24);
     unsigned cols = (unsigned)pow2_ceil(2 * d->block_n); if (cols < 32) cols = 32;
     p.tmem_cols = cols;
+    // shared-memory plan (227 KB per CTA): weights resident if every tile of a column tile fits beside a 2-deep
+    // activation ring, otherwise a weight ring of up to 8 slots and 2..4 activation stages
+    auto smem_need = [&](long long a_st, long long b_st) -> long long {
+        return 1024 + a_st * p.a_stage_bytes + b_st * p.b_pitch + 8 * (2 * a_st + 2 * b_st + 4) + 16 + 16 + 4096;
+    };
+    const long long smem_max = 227 * 1024;
+    const long long n_btiles = (long long)p.n_groups * p.num_cb * p.inner * p.parts;
+    p.b_resident = 0;
+    if (p.tiles_col == 1 && n_btiles <= 64 && !getenv("PGPP_IGEMM_NO_RESIDENT") && smem_need(2, n_btiles) <= smem_max &&
+        p.total_tiles > sm_count()) {
+        p.b_resident = 1;
+        p.b_stages = (int)n_btiles;
+        p.a_stages = 2;
+        while (p.a_stages < 6 && smem_need(p.a_stages + 1, n_btiles) <= smem_max) p.a_stages++;
+    } else {
+        p.a_stages = 2;
+        p.b_stages = 2;
+        if (smem_need(2, 2) > smem_max) { set_error("tile does not fit shared memory"); return PGPP_ERR_UNSUPPORTED; }
+        while (p.b_stages < 8 && smem_need(p.a_stages, p.b_stages + 1) <= smem_max) p.b_stages++;
+        while (p.a_stages < 4 && smem_need(p.a_stages + 1, p.b_stages) <= smem_max) p.a_stages++;
+    }
+    const size_t smem_bytes = (size_t)smem_need(p.a_stages, p.b_stages);
     p.dcoef = d->dcoef; p.noise = d->noise; p.noise_stride_n = d->noise_stride_n; p.bias = d->bias;
     p.act_fn = d->act_fn; p.alpha = d->alpha; p.gain = d->gain; p.clamp = d->clamp;
     p.out = d->out; p.out_dtype = d->out_dtype; p.out_h = d->out_h; p.out_w = d->out_w;
     p.os_n = d->out_stride[0]; p.os_c = d->out_stride[1]; p.os_h = d->out_stride[2]; p.os_w = d->out_stride[3];
     p.accumulate = d->accumulate;
-
-    // stage count from the shared-memory budget
-    const unsigned stage_bytes = p.stage_bytes;
-    const unsigned budget = 200 * 1024;
-    int stages = (int)(budget / stage_bytes);
-    if (stages > kMaxStages) stages = kMaxStages;
-    if (stages < 2) { set_error("tile does not fit shared memory"); return PGPP_ERR_UNSUPPORTED; }
-    p.num_stages = stages;
-    const size_t smem_bytes = 1024 + (size_t)stages * stage_bytes + 8 * (2 * stages + 4) + 16;
 
     // tensor maps
     CUtensorMap map_a, map_b;
@@ -453,7 +586,7 @@ extern "C" int pgpp_conv2d_igemm(const pgpp_conv_desc* d, void* stream) {
         const cuuint64_t dims[5] = {(cuuint64_t)d->c_pad, (cuuint64_t)d->w, (cuuint64_t)d->h, (cuuint64_t)d->n, (cuuint64_t)d->a_parts};
         const cuuint64_t strides[4] = {(cuuint64_t)d->c_pad * 2, (cuuint64_t)d->c_pad * 2 * d->w, (cuuint64_t)d->c_pad * 2 * d->w * d->h,
                                        (cuuint64_t)d->c_pad * 2 * d->w * d->h * d->n};
-        const cuuint32_t box[5] = {(cuuint32_t)p.kb, (cuuint32_t)(p.tw * d->stride), (cuuint32_t)(p.th * d->stride), (cuuint32_t)p.tn, 1};
+        const cuuint32_t box[5] = {(cuuint32_t)p.kb, (cuuint32_t)(p.tw * d->stride), (cuuint32_t)((p.th + p.inner - 1) * d->stride), (cuuint32_t)p.tn, 1};
         const cuuint32_t estr[5] = {1, (cuuint32_t)d->stride, (cuuint32_t)d->stride, 1, 1};
         const CUtensorMapSwizzle sw = row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
         CUresult r = encode(&map_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(d->act), dims, strides, box, estr,

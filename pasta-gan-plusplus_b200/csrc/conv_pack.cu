@@ -47,16 +47,23 @@ __global__ void __launch_bounds__(256) pack_nchw_kernel(PackArgs p, int w_tiles,
         tile[warp * 8 + i][lane] = v;
     }
     __syncthreads();
-    // each warp writes 4 pixels; a lane covers channels 2*lane, 2*lane+1 of the 64-channel slab
+    // write phase: a warp covers 4 pixels x 8 groups of 8 channels, so every pixel's 128-byte channel row is written
+    // by 8 consecutive lanes with one 128-bit store per part
     #pragma unroll
-    for (int i = 0; i < 4; i++) {
-        const int px = warp * 4 + i;
-        if (x0 + px >= p.w) continue;
-        __nv_bfloat16* dst = p.out + (((long long)n * p.h + y) * p.w + (x0 + px)) * p.c_pad + c0;
-        #pragma unroll
-        for (int j = 0; j < 2; j++) {
-            const int cc = 2 * lane + j;
-            if (c0 + cc < p.c_pad) split_store(tile[cc][px], dst + cc, p.part_stride, p.parts);
+    for (int it = 0; it < 1; it++) {
+        const int px = warp * 4 + (lane >> 3);
+        const int cg = lane & 7;
+        if (x0 + px < p.w && c0 + cg * 8 < p.c_pad) {
+            float v[8];
+            #pragma unroll
+            for (int j = 0; j < 8; j++) v[j] = tile[cg * 8 + j][px];
+            __nv_bfloat16* dst = p.out + (((long long)n * p.h + y) * p.w + (x0 + px)) * p.c_pad + c0 + cg * 8;
+            for (int part = 0; part < p.parts; part++) {
+                __align__(16) __nv_bfloat16 q[8];
+                #pragma unroll
+                for (int j = 0; j < 8; j++) { q[j] = __float2bfloat16_rn(v[j]); v[j] -= __bfloat162float(q[j]); }
+                *reinterpret_cast<int4*>(dst + part * p.part_stride) = *reinterpret_cast<const int4*>(q);
+            }
         }
     }
 }

@@ -34,6 +34,14 @@ CASES = [
     ('epilogue_full',     2, 64, 16, 16, 64, 3, 1, 1, 1, 6, {'epi': True}),
     ('bf16_nhwc_out',     2, 64, 16, 16, 64, 3, 1, 1, 1, 1, {'nhwc_bf16': True}),
     ('wide_128px_rows',   1, 64, 8, 256, 64, 3, 1, 1, 1, 1, {}),
+    ('resident_64_bf16x2', 4, 64, 128, 128, 64, 3, 1, 1, 1, 3, {}),
+    ('resident_64_bf16',  4, 64, 128, 128, 64, 3, 1, 1, 1, 1, {}),
+    ('ring_128_bf16x2',   2, 128, 128, 128, 128, 3, 1, 1, 1, 3, {}),
+    ('ragged_reuse',      3, 48, 37, 53, 40, 3, 1, 1, 1, 6, {}),
+    ('k5_reuse',          2, 32, 24, 40, 32, 5, 2, 1, 1, 3, {}),
+    ('k7_c3_big',         2, 3, 96, 64, 64, 7, 3, 1, 1, 3, {}),
+    ('up2_many_tiles',    4, 128, 64, 64, 64, 3, 1, 1, 2, 3, {}),
+    ('torgb_resident',    4, 64, 128, 128, 3, 1, 0, 1, 1, 3, {}),
 ]
 
 
