@@ -67,6 +67,8 @@ struct IgemmParams {
     void* out; int out_dtype; int out_h, out_w; long long os_n, os_c, os_h, os_w;
     int accumulate;
     int up;     // 1, or 2 when phases == 4
+    int fold_gain;                      // activation is positively homogeneous and gain > 0: gain is folded into scale/shift/noise
+    unsigned div_col_m, div_col_s, div_x_m, div_x_s, div_y_m, div_y_s;   // magic numbers for t / tiles_col, / tiles_x, / tiles_y
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -97,10 +99,9 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
 }
 // Bounded wait: a broken pipeline traps (the launch fails with an error) instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    if (mbar_try_wait(bar, parity)) return;
-    const long long t0 = clock64();
+    unsigned polls = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if (clock64() - t0 > 4000000000LL) { printf("pgpp igemm: mbarrier timeout (block %d thread %d)\n", blockIdx.x, threadIdx.x); __trap(); }
+        if (++polls > (1u << 24)) { printf("pgpp igemm: mbarrier timeout (block %d thread %d)\n", blockIdx.x, threadIdx.x); __trap(); }
     }
 }
 
@@ -123,6 +124,21 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint
 // arrives on the mbarrier once every previously issued tcgen05.mma of this thread has completed
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+// asynchronous TMEM load of 16 columns; the registers are valid only after tmem_ld_wait16 on the same array
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t addr, uint32_t* r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(addr) : "memory");
+}
+// tcgen05.wait::ld with the loaded registers as in/out operands so that no consumer can be scheduled above the wait
+__device__ __forceinline__ void tmem_ld_wait16(uint32_t* r) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                   "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+                 :: "memory");
 }
 
 __device__ __forceinline__ void tmem_ld16(uint32_t addr, float* v) {
@@ -151,14 +167,22 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t 
 
 struct TileCoord { int n0, y0, x0, col0; };
 
-__device__ __forceinline__ TileCoord decode_tile(const IgemmParams& p, long long t) {
+// n / d for n < 2^31 with host-computed m = ceil(2^(31+s) / d), s = ceil(log2 d)
+__device__ __forceinline__ unsigned fast_div(unsigned n, unsigned m, unsigned s) {
+    return (unsigned)(((unsigned long long)n * m) >> (31 + s));
+}
+
+__device__ __forceinline__ TileCoord decode_tile(const IgemmParams& p, long long tt) {
     TileCoord c;
-    c.col0 = (int)(t % p.tiles_col) * p.block_n; t /= p.tiles_col;       // column tiles fastest: neighbours share A in L2
-    c.x0 = (int)(t % p.tiles_x) * p.tw; t /= p.tiles_x;
-    c.y0 = (int)(t % p.tiles_y) * p.th; t /= p.tiles_y;
+    unsigned t = (unsigned)tt, q;
+    q = fast_div(t, p.div_col_m, p.div_col_s); c.col0 = (int)(t - q * p.tiles_col) * p.block_n; t = q;   // column tiles fastest: neighbours share A in L2
+    q = fast_div(t, p.div_x_m, p.div_x_s);     c.x0 = (int)(t - q * p.tiles_x) * p.tw; t = q;
+    q = fast_div(t, p.div_y_m, p.div_y_s);     c.y0 = (int)(t - q * p.tiles_y) * p.th; t = q;
     c.n0 = (int)t * p.tn;
     return c;
 }
+
+struct PixelCoord { int px, py, pn; };
 
 template <class OT> __device__ __forceinline__ OT cvt_out(float v);
 template <> __device__ __forceinline__ float cvt_out<float>(float v) { return v; }
@@ -169,16 +193,12 @@ template <> __device__ __forceinline__ float cvt_in<float>(float v) { return v; 
 template <> __device__ __forceinline__ float cvt_in<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
 template <> __device__ __forceinline__ float cvt_in<__half>(__half v) { return __half2float(v); }
 
-// Epilogue of one accumulator tile for the calling warp: its 32 TMEM lanes (pixels) x columns [col_begin, col_end).
-// Per-column demodulation scale and bias come from shared memory (staged once per tile) when the tile holds a single
-// sample; tiny-image tiles that span several samples read them through the read-only path instead.
+// General epilogue of one accumulator tile for the calling warp: its 32 TMEM lanes (pixels) x columns
+// [col_begin, col_end).  Handles every option (several samples per tile, accumulate, partial chunks, any activation).
 template <int A, class OT>
-__device__ __forceinline__ void epilogue_tile(const IgemmParams& p, const TileCoord tc, uint32_t tmem_tile, int lane_row,
-                                              int col_begin, int col_end, const float* s_scale, const float* s_shift, bool staged) {
-    const int px = lane_row % p.tw;
-    const int py = (lane_row / p.tw) % p.th;
-    const int pn = lane_row / (p.tw * p.th);
-    const int x = tc.x0 + px, y = tc.y0 + py, n = tc.n0 + pn;
+__device__ __forceinline__ void epilogue_general(const IgemmParams& p, const TileCoord tc, uint32_t tmem_tile, const PixelCoord pc,
+                                                 int col_begin, int col_end) {
+    const int x = tc.x0 + pc.px, y = tc.y0 + pc.py, n = tc.n0 + pc.pn;
     const bool pix_ok = x < p.conv_w && y < p.conv_h && n < p.n;
     const int total_cols = p.phases * p.phase_stride;
     OT* const out = (OT*)p.out;
@@ -190,39 +210,28 @@ __device__ __forceinline__ void epilogue_tile(const IgemmParams& p, const TileCo
         tmem_ld16(tmem_tile + c0, v);       // warp-collective: executed by all lanes, valid pixel or not
         const int g0 = tc.col0 + c0;
         if (!pix_ok || g0 >= total_cols) continue;
-        const int phase = g0 / p.phase_stride;      // a 16-column chunk never straddles phases (phase_stride % 16 == 0)
-        const int oc0 = g0 - phase * p.phase_stride;
-        if (oc0 >= p.o) continue;                   // padding columns between phases
+        const int phase = (g0 >= p.phase_stride) + (g0 >= 2 * p.phase_stride) + (g0 >= 3 * p.phase_stride);
+        const int oc0 = g0 - phase * p.phase_stride;        // a 16-column chunk never straddles phases (phase_stride % 16 == 0)
+        if (oc0 >= p.o) continue;                           // padding columns between phases
         const int oy = y * p.up + (phase >> 1), ox = x * p.up + (phase & 1);
         float nz = 0.f;
         if (p.noise) nz = __ldg(p.noise + n * p.noise_stride_n + (long long)oy * p.out_w + ox);
         const long long base = n * p.os_n + oy * p.os_h + ox * p.os_w;
         const int valid = min(16, p.o - oc0);
-        if (staged) {
-            #pragma unroll
-            for (int j = 0; j < 16; j++) {
-                float r = fmaf(v[j], s_scale[c0 + j], nz) + s_shift[c0 + j];
+        #pragma unroll
+        for (int j = 0; j < 16; j++) {
+            if (j < valid) {
+                const int oc = oc0 + j;
+                float r = v[j];
+                if (p.dcoef) r *= __ldg(p.dcoef + (long long)n * p.o + oc);
+                r += nz;
+                if (p.bias) r += __ldg(p.bias + oc);
                 r = act_forward<A, float>(r, alpha) * gain;
                 if (clamp >= 0.f) r = fminf(fmaxf(r, -clamp), clamp);
                 v[j] = r;
             }
-        } else {
-            #pragma unroll
-            for (int j = 0; j < 16; j++) {
-                if (j < valid) {
-                    const int oc = oc0 + j;
-                    float r = v[j];
-                    if (p.dcoef) r *= __ldg(p.dcoef + (long long)n * p.o + oc);
-                    r += nz;
-                    if (p.bias) r += __ldg(p.bias + oc);
-                    r = act_forward<A, float>(r, alpha) * gain;
-                    if (clamp >= 0.f) r = fminf(fmaxf(r, -clamp), clamp);
-                    v[j] = r;
-                }
-            }
         }
         if (cs == 1 && valid == 16 && !p.accumulate && ((base + oc0) * sizeof(OT)) % 16 == 0 && ((uintptr_t)out & 15) == 0) {
-            // channels-innermost output: 16 consecutive channels of one pixel, 128-bit stores
             __align__(16) OT tmp[16];
             #pragma unroll
             for (int j = 0; j < 16; j++) tmp[j] = cvt_out<OT>(v[j]);
@@ -230,11 +239,6 @@ __device__ __forceinline__ void epilogue_tile(const IgemmParams& p, const TileCo
             const int4* src = reinterpret_cast<const int4*>(tmp);
             #pragma unroll
             for (int q = 0; q < (int)(16 * sizeof(OT) / 16); q++) dst[q] = src[q];
-        } else if (valid == 16 && !p.accumulate) {
-            // NCHW-like output: for a fixed channel the warp's lanes are consecutive pixels of a row
-            OT* dst = out + base + (long long)oc0 * cs;
-            #pragma unroll
-            for (int j = 0; j < 16; j++) { *dst = cvt_out<OT>(v[j]); dst += cs; }
         } else {
             OT* dst = out + base + (long long)oc0 * cs;
             #pragma unroll
@@ -250,10 +254,83 @@ __device__ __forceinline__ void epilogue_tile(const IgemmParams& p, const TileCo
     }
 }
 
+// Fast epilogue: one sample per tile, per-column (scale, shift) staged in shared memory with the gain already folded in
+// (linear / relu / lrelu are positively homogeneous), no accumulate.
+template <int A, class OT, bool CLAMP>
+__device__ __forceinline__ void epilogue_fast(const IgemmParams& p, const TileCoord tc, uint32_t tmem_tile, const PixelCoord pc,
+                                              int col_begin, int col_end, const float2* s_cs) {
+    const int x = tc.x0 + pc.px, y = tc.y0 + pc.py, n = tc.n0;
+    const bool pix_ok = x < p.conv_w && y < p.conv_h;
+    OT* const out = (OT*)p.out;
+    const float alpha = p.alpha, clamp = p.clamp, gain = p.gain;
+    const unsigned cs = (unsigned)p.os_c;
+    const bool nhwc = p.os_c == 1;
+    const int nchunks = (col_end - col_begin) >> 4;
+    auto process = [&](const uint32_t (&acc)[16], int c0) {
+        const int g0 = tc.col0 + c0;
+        const int phase = (g0 >= p.phase_stride) + (g0 >= 2 * p.phase_stride) + (g0 >= 3 * p.phase_stride);
+        const int oc0 = g0 - phase * p.phase_stride;
+        if (!pix_ok || oc0 >= p.o || phase >= p.phases) return;
+        const int oy = y * p.up + (phase >> 1), ox = x * p.up + (phase & 1);
+        float nz = 0.f;
+        if (p.noise) nz = __ldg(p.noise + n * p.noise_stride_n + (long long)oy * p.out_w + ox) * gain;
+        const long long base = n * p.os_n + oy * p.os_h + ox * p.os_w;
+        const int valid = min(16, p.o - oc0);
+        float v[16];
+        #pragma unroll
+        for (int j = 0; j < 16; j++) {
+            const float2 q = s_cs[c0 + j];
+            float r = fmaf(__uint_as_float(acc[j]), q.x, nz) + q.y;
+            if (A == PGPP_ACT_RELU) r = fmaxf(r, 0.f);
+            if (A == PGPP_ACT_LRELU) r = fmaxf(r, r * alpha);       // 0 <= alpha <= 1 (checked on the host)
+            if (CLAMP) r = fminf(fmaxf(r, -clamp), clamp);
+            v[j] = r;
+        }
+        if (nhwc && valid == 16 && ((base + oc0) * sizeof(OT)) % 16 == 0 && ((uintptr_t)out & 15) == 0) {
+            __align__(16) OT tmp[16];
+            #pragma unroll
+            for (int j = 0; j < 16; j++) tmp[j] = cvt_out<OT>(v[j]);
+            int4* dst = reinterpret_cast<int4*>(out + base + oc0);
+            const int4* src = reinterpret_cast<const int4*>(tmp);
+            #pragma unroll
+            for (int q = 0; q < (int)(16 * sizeof(OT) / 16); q++) dst[q] = src[q];
+        } else {
+            OT* dst = out + base + (long long)oc0 * p.os_c;
+            if (valid == 16) {
+                #pragma unroll
+                for (int j = 0; j < 16; j++) dst[(unsigned)j * cs] = cvt_out<OT>(v[j]);
+            } else {
+                #pragma unroll
+                for (int j = 0; j < 16; j++) if (j < valid) dst[(unsigned)j * cs] = cvt_out<OT>(v[j]);
+            }
+        }
+    };
+    // (the second epilogue warp on the same scheduler covers the TMEM-load latency of this one)
+    for (int ch = 0; ch < nchunks; ch++) {
+        const int c0 = col_begin + ch * 16;
+        uint32_t ra[16];
+        tmem_ld16_issue(tmem_tile + c0, ra);
+        tmem_ld_wait16(ra);
+        process(ra, c0);
+    }
+}
+
 template <class OT>
-__device__ __forceinline__ void epilogue_dispatch(const IgemmParams& p, const TileCoord tc, uint32_t tmem_tile, int lane_row,
-                                                  int col_begin, int col_end, const float* s_scale, const float* s_shift, bool staged) {
-#define PGPP_EPI(ACT) epilogue_tile<ACT, OT>(p, tc, tmem_tile, lane_row, col_begin, col_end, s_scale, s_shift, staged)
+__device__ __forceinline__ void epilogue_dispatch(const IgemmParams& p, const TileCoord tc, uint32_t tmem_tile, const PixelCoord pc,
+                                                  int col_begin, int col_end, const float2* s_cs, bool fast) {
+    if (fast) {
+        const bool cl = p.clamp >= 0.f;
+        switch (p.act_fn) {
+            case PGPP_ACT_LINEAR: if (cl) epilogue_fast<PGPP_ACT_LINEAR, OT, true>(p, tc, tmem_tile, pc, col_begin, col_end, s_cs);
+                                  else    epilogue_fast<PGPP_ACT_LINEAR, OT, false>(p, tc, tmem_tile, pc, col_begin, col_end, s_cs); break;
+            case PGPP_ACT_RELU:   if (cl) epilogue_fast<PGPP_ACT_RELU, OT, true>(p, tc, tmem_tile, pc, col_begin, col_end, s_cs);
+                                  else    epilogue_fast<PGPP_ACT_RELU, OT, false>(p, tc, tmem_tile, pc, col_begin, col_end, s_cs); break;
+            default:              if (cl) epilogue_fast<PGPP_ACT_LRELU, OT, true>(p, tc, tmem_tile, pc, col_begin, col_end, s_cs);
+                                  else    epilogue_fast<PGPP_ACT_LRELU, OT, false>(p, tc, tmem_tile, pc, col_begin, col_end, s_cs); break;
+        }
+        return;
+    }
+#define PGPP_EPI(ACT) epilogue_general<ACT, OT>(p, tc, tmem_tile, pc, col_begin, col_end)
     switch (p.act_fn) {
         case PGPP_ACT_LINEAR: PGPP_EPI(PGPP_ACT_LINEAR); break;
         case PGPP_ACT_RELU: PGPP_EPI(PGPP_ACT_RELU); break;
@@ -284,8 +361,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
     auto tfull_bar = [&](int b) { return bar_base + 8u * (2 * SA + 2 * SB + b); };
     auto tempty_bar = [&](int b) { return bar_base + 8u * (2 * SA + 2 * SB + 2 + b); };
     const uint32_t tmem_slot = bar_base + 8u * (2 * SA + 2 * SB + 4);
-    // per-column epilogue parameters, double-buffered with the accumulator: [2][256] scale, [2][256] shift
-    float* const s_params = reinterpret_cast<float*>(smem_raw + (tmem_slot + 16u - smem_u32(smem_raw)));
+    // per-column epilogue parameters (scale, shift), double-buffered with the accumulator: float2 [2][256]
+    float2* const s_params = reinterpret_cast<float2*>(smem_raw + (tmem_slot + 16u - smem_u32(smem_raw)));
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -354,96 +431,115 @@ igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        if (elect_one()) {
-            int sa = 0; uint32_t pha = 0;
-            int sb = 0; uint32_t phb = 0;
-            int buf = 0; uint32_t buf_phase = 0;
-            const int k_steps = p.kb / 16;                  // tcgen05.mma kind::f16 has K = 16
-            for (long long t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
-                mbar_wait(tempty_bar(buf), buf_phase ^ 1);  // epilogue has drained this accumulator
-                tc_fence_after();
-                const uint32_t tmem_d = tmem_base + (uint32_t)(buf * p.block_n);
-                uint32_t acc = 0;
-                int b_slot = 0;
-                for (int g = 0; g < p.n_groups; g++) {
-                    for (int cb = 0; cb < p.num_cb; cb++) {
-                        mbar_wait(afull_bar(sa), pha);
-                        tc_fence_after();
-                        const uint32_t a_addr = smem_base + sa * p.a_stage_bytes;
-                        for (int j = 0; j < p.inner; j++) {
-                            for (int pb = 0; pb < p.parts; pb++) {
-                                uint32_t b_addr;
-                                if (p.b_resident) {
-                                    mbar_wait(bfull_bar(b_slot), 0);        // completes once; stays complete afterwards
-                                    b_addr = b_base + b_slot * p.b_pitch;
-                                    b_slot++;
-                                } else {
-                                    mbar_wait(bfull_bar(sb), phb);
-                                    b_addr = b_base + sb * p.b_pitch;
-                                }
+        // the whole warp walks the (uniform) loop so that descriptors live in uniform registers; one elected lane issues
+        const bool leader = elect_one();
+        int sa = 0; uint32_t pha = 0;
+        int sb = 0; uint32_t phb = 0;
+        int buf = 0; uint32_t buf_phase = 0;
+        const int k_steps = p.kb / 16;                  // tcgen05.mma kind::f16 has K = 16
+        bool first_tile = true;
+        for (long long t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+            mbar_wait(tempty_bar(buf), buf_phase ^ 1);  // epilogue has drained this accumulator
+            tc_fence_after();
+            const uint32_t tmem_d = tmem_base + (uint32_t)(buf * p.block_n);
+            uint32_t acc = 0;
+            int b_slot = 0;
+            for (int g = 0; g < p.n_groups; g++) {
+                for (int cb = 0; cb < p.num_cb; cb++) {
+                    mbar_wait(afull_bar(sa), pha);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_base + sa * p.a_stage_bytes;
+                    for (int j = 0; j < p.inner; j++) {
+                        for (int pb = 0; pb < p.parts; pb++) {
+                            uint32_t b_addr;
+                            if (p.b_resident) {
+                                if (first_tile) { mbar_wait(bfull_bar(b_slot), 0); tc_fence_after(); }  // loaded once, stays valid
+                                b_addr = b_base + b_slot * p.b_pitch;
+                                b_slot++;
+                            } else {
+                                mbar_wait(bfull_bar(sb), phb);
                                 tc_fence_after();
-                                const uint64_t db = make_smem_desc(b_addr, p.layout_type, p.sbo_bytes);
-                                const unsigned mask = p.pa_mask[pb];
-                                for (int pa = 0; pa < p.parts; pa++) {
-                                    if (!((mask >> pa) & 1u)) continue;
-                                    const uint64_t da = make_smem_desc(a_addr + pa * p.slab_bytes + j * p.ky_step_bytes, p.layout_type, p.sbo_bytes);
-                                    for (int k = 0; k < k_steps; k++) {
+                                b_addr = b_base + sb * p.b_pitch;
+                            }
+                            const uint64_t db = make_smem_desc(b_addr, p.layout_type, p.sbo_bytes);
+                            const unsigned mask = p.pa_mask[pb];
+                            for (int pa = 0; pa < p.parts; pa++) {
+                                if (!((mask >> pa) & 1u)) continue;
+                                const uint64_t da = make_smem_desc(a_addr + pa * p.slab_bytes + j * p.ky_step_bytes, p.layout_type, p.sbo_bytes);
+                                if (leader) {
+                                    if (k_steps == 4) {
                                         // advance 16 elements (32 bytes) along K inside the swizzle row: +2 in the >>4 address field
-                                        umma_bf16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), p.idesc, acc);
-                                        acc = 1;
+                                        umma_bf16(tmem_d, da, db, p.idesc, acc);
+                                        umma_bf16(tmem_d, da + 2, db + 2, p.idesc, 1);
+                                        umma_bf16(tmem_d, da + 4, db + 4, p.idesc, 1);
+                                        umma_bf16(tmem_d, da + 6, db + 6, p.idesc, 1);
+                                    } else {
+                                        for (int k = 0; k < k_steps; k++)
+                                            umma_bf16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), p.idesc, acc | (uint32_t)k);
                                     }
                                 }
-                                if (!p.b_resident) {
-                                    umma_commit(bempty_bar(sb));    // weight slot reusable once these MMAs retire
-                                    if (++sb == SB) { sb = 0; phb ^= 1; }
-                                }
+                                acc = 1;
+                            }
+                            if (!p.b_resident) {
+                                if (leader) umma_commit(bempty_bar(sb));    // weight slot reusable once these MMAs retire
+                                if (++sb == SB) { sb = 0; phb ^= 1; }
                             }
                         }
-                        umma_commit(aempty_bar(sa));                // activation slab reusable
-                        if (++sa == SA) { sa = 0; pha ^= 1; }
                     }
+                    if (leader) umma_commit(aempty_bar(sa));                // activation slab reusable
+                    if (++sa == SA) { sa = 0; pha ^= 1; }
                 }
-                umma_commit(tfull_bar(buf));                        // accumulator complete -> epilogue
-                if (++buf == 2) { buf = 0; buf_phase ^= 1; }
             }
+            if (leader) umma_commit(tfull_bar(buf));                        // accumulator complete -> epilogue
+            if (++buf == 2) { buf = 0; buf_phase ^= 1; }
+            first_tile = false;
         }
+        __syncwarp();
     } else {
         // ===================== epilogue warps =====================
         const int quarter = warp & 3;                       // TMEM lane quarter this warp may access
         const int half = (warp - 2) >> 2;                   // which half of the columns
         const int lane_row = quarter * 32 + lane;
+        PixelCoord pc;
+        pc.px = lane_row % p.tw;
+        pc.py = (lane_row / p.tw) % p.th;
+        pc.pn = lane_row / (p.tw * p.th);
         const int etid = threadIdx.x - 64;                  // 0..255 among the epilogue threads
         const int cols_per = p.block_n >= 32 ? p.block_n / 2 : p.block_n;
         const int col_begin = half * cols_per;
         const int col_end = (p.block_n >= 32 || half == 0) ? col_begin + cols_per : col_begin;
-        const bool staged = p.tn == 1;
+        const bool fast = p.tn == 1 && !p.accumulate && p.fold_gain;
         int buf = 0; uint32_t buf_phase = 0;
+        int tag0 = -1, tag1 = -1;                           // (sample, column tile) whose parameters each staging buffer holds
         for (long long t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
             const TileCoord tc = decode_tile(p, t);
-            float* s_scale = s_params + buf * 512;
-            float* s_shift = s_scale + 256;
-            if (staged) {
-                // stage scale/shift of this tile's columns (safe: the previous user of this buffer pair, tile t-2, finished
-                // before its accumulator was released, and every warp passed the barrier below for tile t-1 after that)
-                if (etid < p.block_n) {
-                    const int g = tc.col0 + etid;
-                    const int phase = g / p.phase_stride;
-                    const int oc = g - phase * p.phase_stride;
-                    float sc = 1.f, sh = 0.f;
-                    if (oc < p.o && phase < p.phases) {
-                        if (p.dcoef) sc = __ldg(p.dcoef + (long long)tc.n0 * p.o + oc);
-                        if (p.bias) sh = __ldg(p.bias + oc);
+            float2* s_cs = s_params + buf * 256;
+            if (fast) {
+                const int tag = tc.n0 * p.tiles_col + tc.col0 / p.block_n;
+                if ((buf ? tag1 : tag0) != tag) {
+                    // every epilogue warp must be done with the tile that last used this buffer before it is rewritten
+                    asm volatile("bar.sync 1, 256;" ::: "memory");
+                    if (etid < p.block_n) {
+                        const int g = tc.col0 + etid;
+                        const int phase = (g >= p.phase_stride) + (g >= 2 * p.phase_stride) + (g >= 3 * p.phase_stride);
+                        const int oc = g - phase * p.phase_stride;
+                        float sc = 1.f, sh = 0.f;
+                        if (oc < p.o && phase < p.phases) {
+                            if (p.dcoef) sc = __ldg(p.dcoef + (long long)tc.n0 * p.o + oc);
+                            if (p.bias) sh = __ldg(p.bias + oc);
+                        }
+                        s_cs[etid] = make_float2(sc * p.gain, sh * p.gain);
                     }
-                    s_scale[etid] = sc; s_shift[etid] = sh;
+                    asm volatile("bar.sync 1, 256;" ::: "memory");
+                    if (buf) tag1 = tag; else tag0 = tag;
                 }
-                asm volatile("bar.sync 1, 256;" ::: "memory");
             }
             mbar_wait(tfull_bar(buf), buf_phase);
             tc_fence_after();
             const uint32_t tmem_tile = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * p.block_n);
-            if (p.out_dtype == PGPP_F32) epilogue_dispatch<float>(p, tc, tmem_tile, lane_row, col_begin, col_end, s_scale, s_shift, staged);
-            else if (p.out_dtype == PGPP_BF16) epilogue_dispatch<__nv_bfloat16>(p, tc, tmem_tile, lane_row, col_begin, col_end, s_scale, s_shift, staged);
-            else epilogue_dispatch<__half>(p, tc, tmem_tile, lane_row, col_begin, col_end, s_scale, s_shift, staged);
+            if (p.out_dtype == PGPP_F32) epilogue_dispatch<float>(p, tc, tmem_tile, pc, col_begin, col_end, s_cs, fast);
+            else if (p.out_dtype == PGPP_BF16) epilogue_dispatch<__nv_bfloat16>(p, tc, tmem_tile, pc, col_begin, col_end, s_cs, fast);
+            else epilogue_dispatch<__half>(p, tc, tmem_tile, pc, col_begin, col_end, s_cs, fast);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty_bar(buf));
@@ -579,6 +675,16 @@ extern "C" int pgpp_conv2d_igemm(const pgpp_conv_desc* d, void* stream) {
     p.out = d->out; p.out_dtype = d->out_dtype; p.out_h = d->out_h; p.out_w = d->out_w;
     p.os_n = d->out_stride[0]; p.os_c = d->out_stride[1]; p.os_h = d->out_stride[2]; p.os_w = d->out_stride[3];
     p.accumulate = d->accumulate;
+    p.fold_gain = (d->gain > 0.f && (d->act_fn == PGPP_ACT_LINEAR || d->act_fn == PGPP_ACT_RELU ||
+                                     (d->act_fn == PGPP_ACT_LRELU && d->alpha >= 0.f && d->alpha <= 1.f))) ? 1 : 0;
+    auto magic = [](unsigned dv, unsigned& m, unsigned& sft) {
+        sft = 0; while ((1ull << sft) < dv) sft++;
+        m = (unsigned)(((1ull << (31 + sft)) + dv - 1) / dv);
+    };
+    magic((unsigned)p.tiles_col, p.div_col_m, p.div_col_s);
+    magic((unsigned)p.tiles_x, p.div_x_m, p.div_x_s);
+    magic((unsigned)p.tiles_y, p.div_y_m, p.div_y_s);
+    PGPP_REQUIRE(p.total_tiles < (1ll << 31), "too many tiles");
 
     // tensor maps
     CUtensorMap map_a, map_b;
