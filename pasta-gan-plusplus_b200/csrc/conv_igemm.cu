@@ -345,6 +345,95 @@ __device__ __forceinline__ void epilogue_dispatch(const IgemmParams& p, const Ti
 #undef PGPP_EPI
 }
 
+struct MmaCtx { uint32_t smem_base, b_base, bar_base, tmem_base; };
+
+// MMA issuer role (warp 1).  The whole warp walks the warp-uniform loop so that descriptors live in uniform registers;
+// one elected lane issues tcgen05.mma / tcgen05.commit.  PARTS / INNER / KS > 0 are compile-time copies of p.parts /
+// p.inner / (kb / 16) for the common configurations (fully unrolled product / tap / K-step loops, a handful of
+// instructions per MMA); <0, 0, 0> is the generic runtime-bounds version.
+template <int PARTS, int INNER, int KS>
+__device__ __forceinline__ void mma_role(const IgemmParams& p, const MmaCtx mc) {
+    const int SA = p.a_stages, SB = p.b_stages;
+    auto afull_bar = [&](int s) { return mc.bar_base + 8u * s; };
+    auto aempty_bar = [&](int s) { return mc.bar_base + 8u * (SA + s); };
+    auto bfull_bar = [&](int s) { return mc.bar_base + 8u * (2 * SA + s); };
+    auto bempty_bar = [&](int s) { return mc.bar_base + 8u * (2 * SA + SB + s); };
+    auto tfull_bar = [&](int b) { return mc.bar_base + 8u * (2 * SA + 2 * SB + b); };
+    auto tempty_bar = [&](int b) { return mc.bar_base + 8u * (2 * SA + 2 * SB + 2 + b); };
+    const int parts = PARTS ? PARTS : p.parts;
+    const int inner = INNER ? INNER : p.inner;
+    const int k_steps = KS ? KS : p.kb / 16;            // tcgen05.mma kind::f16 has K = 16
+    const bool leader = elect_one();
+    const uint64_t desc_hi = make_smem_desc(0, p.layout_type, p.sbo_bytes);     // everything but the start address
+    const uint32_t slab16 = p.slab_bytes >> 4, ky16 = p.ky_step_bytes >> 4, bpitch16 = p.b_pitch >> 4;
+    const uint32_t idesc = p.idesc;
+    int sa = 0; uint32_t pha = 0;
+    int sb = 0; uint32_t phb = 0;
+    int buf = 0; uint32_t buf_phase = 0;
+    bool first_tile = true;
+    for (long long t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+        mbar_wait(tempty_bar(buf), buf_phase ^ 1);      // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t tmem_d = mc.tmem_base + (uint32_t)(buf * p.block_n);
+        uint32_t acc = 0;
+        uint32_t b_res16 = mc.b_base >> 4;              // resident weights: next tile in consumption order
+        for (int g = 0; g < p.n_groups; g++) {
+            for (int cb = 0; cb < p.num_cb; cb++) {
+                mbar_wait(afull_bar(sa), pha);
+                tc_fence_after();
+                const uint32_t a16 = (mc.smem_base + sa * p.a_stage_bytes) >> 4;
+                #pragma unroll
+                for (int j = 0; j < (INNER ? INNER : 8); j++) {
+                    if (j >= inner) break;
+                    #pragma unroll
+                    for (int pb = 0; pb < (PARTS ? PARTS : 3); pb++) {
+                        if (pb >= parts) break;
+                        uint32_t b16;
+                        if (p.b_resident) {
+                            if (first_tile) { mbar_wait(bfull_bar((int)((b_res16 - (mc.b_base >> 4)) / bpitch16)), 0); tc_fence_after(); }
+                            b16 = b_res16;
+                            b_res16 += bpitch16;
+                        } else {
+                            mbar_wait(bfull_bar(sb), phb);
+                            tc_fence_after();
+                            b16 = (mc.b_base + sb * p.b_pitch) >> 4;
+                        }
+                        const uint64_t db = desc_hi | (uint64_t)(b16 & 0x3FFF);
+                        #pragma unroll
+                        for (int pa = 0; pa < (PARTS ? PARTS : 3); pa++) {
+                            if (pa + pb >= parts) break;                    // products a_pa * b_pb with pa + pb < parts
+                            const uint64_t da = desc_hi | (uint64_t)((a16 + pa * slab16 + j * ky16) & 0x3FFF);
+                            if (leader) {
+                                if (KS == 4) {
+                                    // advance 16 elements (32 bytes) along K inside the swizzle row: +2 in the >>4 address field
+                                    umma_bf16(tmem_d, da, db, idesc, acc);
+                                    umma_bf16(tmem_d, da + 2, db + 2, idesc, 1);
+                                    umma_bf16(tmem_d, da + 4, db + 4, idesc, 1);
+                                    umma_bf16(tmem_d, da + 6, db + 6, idesc, 1);
+                                } else {
+                                    for (int k = 0; k < k_steps; k++)
+                                        umma_bf16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, acc | (uint32_t)k);
+                                }
+                            }
+                            acc = 1;
+                        }
+                        if (!p.b_resident) {
+                            if (leader) umma_commit(bempty_bar(sb));        // weight slot reusable once these MMAs retire
+                            if (++sb == SB) { sb = 0; phb ^= 1; }
+                        }
+                    }
+                }
+                if (leader) umma_commit(aempty_bar(sa));                    // activation slab reusable
+                if (++sa == SA) { sa = 0; pha ^= 1; }
+            }
+        }
+        if (leader) umma_commit(tfull_bar(buf));                            // accumulator complete -> epilogue
+        if (++buf == 2) { buf = 0; buf_phase ^= 1; }
+        first_tile = false;
+    }
+    __syncwarp();
+}
+
 __global__ void __launch_bounds__(kThreads, 1)
 igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const IgemmParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -431,70 +520,14 @@ igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        // the whole warp walks the (uniform) loop so that descriptors live in uniform registers; one elected lane issues
-        const bool leader = elect_one();
-        int sa = 0; uint32_t pha = 0;
-        int sb = 0; uint32_t phb = 0;
-        int buf = 0; uint32_t buf_phase = 0;
-        const int k_steps = p.kb / 16;                  // tcgen05.mma kind::f16 has K = 16
-        bool first_tile = true;
-        for (long long t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
-            mbar_wait(tempty_bar(buf), buf_phase ^ 1);  // epilogue has drained this accumulator
-            tc_fence_after();
-            const uint32_t tmem_d = tmem_base + (uint32_t)(buf * p.block_n);
-            uint32_t acc = 0;
-            int b_slot = 0;
-            for (int g = 0; g < p.n_groups; g++) {
-                for (int cb = 0; cb < p.num_cb; cb++) {
-                    mbar_wait(afull_bar(sa), pha);
-                    tc_fence_after();
-                    const uint32_t a_addr = smem_base + sa * p.a_stage_bytes;
-                    for (int j = 0; j < p.inner; j++) {
-                        for (int pb = 0; pb < p.parts; pb++) {
-                            uint32_t b_addr;
-                            if (p.b_resident) {
-                                if (first_tile) { mbar_wait(bfull_bar(b_slot), 0); tc_fence_after(); }  // loaded once, stays valid
-                                b_addr = b_base + b_slot * p.b_pitch;
-                                b_slot++;
-                            } else {
-                                mbar_wait(bfull_bar(sb), phb);
-                                tc_fence_after();
-                                b_addr = b_base + sb * p.b_pitch;
-                            }
-                            const uint64_t db = make_smem_desc(b_addr, p.layout_type, p.sbo_bytes);
-                            const unsigned mask = p.pa_mask[pb];
-                            for (int pa = 0; pa < p.parts; pa++) {
-                                if (!((mask >> pa) & 1u)) continue;
-                                const uint64_t da = make_smem_desc(a_addr + pa * p.slab_bytes + j * p.ky_step_bytes, p.layout_type, p.sbo_bytes);
-                                if (leader) {
-                                    if (k_steps == 4) {
-                                        // advance 16 elements (32 bytes) along K inside the swizzle row: +2 in the >>4 address field
-                                        umma_bf16(tmem_d, da, db, p.idesc, acc);
-                                        umma_bf16(tmem_d, da + 2, db + 2, p.idesc, 1);
-                                        umma_bf16(tmem_d, da + 4, db + 4, p.idesc, 1);
-                                        umma_bf16(tmem_d, da + 6, db + 6, p.idesc, 1);
-                                    } else {
-                                        for (int k = 0; k < k_steps; k++)
-                                            umma_bf16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), p.idesc, acc | (uint32_t)k);
-                                    }
-                                }
-                                acc = 1;
-                            }
-                            if (!p.b_resident) {
-                                if (leader) umma_commit(bempty_bar(sb));    // weight slot reusable once these MMAs retire
-                                if (++sb == SB) { sb = 0; phb ^= 1; }
-                            }
-                        }
-                    }
-                    if (leader) umma_commit(aempty_bar(sa));                // activation slab reusable
-                    if (++sa == SA) { sa = 0; pha ^= 1; }
-                }
-            }
-            if (leader) umma_commit(tfull_bar(buf));                        // accumulator complete -> epilogue
-            if (++buf == 2) { buf = 0; buf_phase ^= 1; }
-            first_tile = false;
-        }
-        __syncwarp();
+        const MmaCtx mc{smem_base, b_base, bar_base, tmem_base};
+        const int ks = p.kb == 64 ? 4 : 0;
+        if (ks == 4 && p.inner == 3 && p.parts == 1) mma_role<1, 3, 4>(p, mc);
+        else if (ks == 4 && p.inner == 3 && p.parts == 2) mma_role<2, 3, 4>(p, mc);
+        else if (ks == 4 && p.inner == 3 && p.parts == 3) mma_role<3, 3, 4>(p, mc);
+        else if (ks == 4 && p.inner == 1 && p.parts == 1) mma_role<1, 1, 4>(p, mc);
+        else if (ks == 4 && p.inner == 1 && p.parts == 2) mma_role<2, 1, 4>(p, mc);
+        else mma_role<0, 0, 0>(p, mc);
     } else {
         // ===================== epilogue warps =====================
         const int quarter = warp & 3;                       // TMEM lane quarter this warp may access
