@@ -36,6 +36,21 @@ inline int sm_count() {
     return cached[dev];
 }
 
+// resident CTAs per SM of a kernel (cached): persistent grids are sized to exactly one full wave
+template <class K>
+inline int occupancy_of(K kernel, int threads, size_t smem) {
+    struct Entry { const void* fn; int threads; size_t smem; int occ; };
+    static thread_local Entry cache[64];
+    static thread_local int used = 0;
+    const void* fn = (const void*)kernel;
+    for (int i = 0; i < used; i++)
+        if (cache[i].fn == fn && cache[i].threads == threads && cache[i].smem == smem) return cache[i].occ;
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, threads, smem) != cudaSuccess || occ < 1) occ = 1;
+    if (used < 64) cache[used++] = Entry{fn, threads, smem, occ};
+    return occ;
+}
+
 // scalar <-> storage conversions; math runs in float (double for f64), like the reference's
 // InternalType (bias_act.cu:15-18, upfirdn2d.cu:15-18)
 template <class T> struct Acc { typedef float type; };

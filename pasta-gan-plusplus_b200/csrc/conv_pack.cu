@@ -96,7 +96,7 @@ static int launch_pack(const PackArgs& p, cudaStream_t stream) {
     } else {
         const long long total = (long long)p.n * p.h * p.w * p.c_pad;
         long long blocks = (total + 255) / 256;
-        const long long cap = (long long)sm_count() * 16;
+        const long long cap = (long long)sm_count() * occupancy_of(pack_generic_kernel<T>, 256, 0);
         if (blocks > cap) blocks = cap;
         pack_generic_kernel<T><<<(unsigned)blocks, 256, 0, stream>>>(p, total);
     }

@@ -44,11 +44,13 @@ __global__ void __launch_bounds__(256) generic_kernel(UpfirdnArgs p, long long t
     const T* x = (const T*)p.x;
     T* y = (T*)p.y;
     for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < total_quads; q += (long long)gridDim.x * blockDim.x) {
-        const int qx = (int)(q % quads_per_row);
-        long long r = q / quads_per_row;
-        const int oy = (int)(r % p.oh); r /= p.oh;
-        const int c = (int)(r % p.c);
-        const int n = (int)(r / p.c);
+        const unsigned q32 = (unsigned)q;               // total_quads <= output numel <= INT_MAX
+        unsigned r = q32 / (unsigned)quads_per_row;
+        const int qx = (int)(q32 - r * (unsigned)quads_per_row);
+        unsigned r2 = r / (unsigned)p.oh;
+        const int oy = (int)(r - r2 * (unsigned)p.oh);
+        const int n = (int)(r2 / (unsigned)p.c);
+        const int c = (int)(r2 - (unsigned)n * (unsigned)p.c);
         const T* xp = x + n * p.xs_n + c * p.xs_c;
         T* yp = y + n * p.ys_n + c * p.ys_c + oy * p.ys_h;
         // rows: taps jy with (base_y + jy) % upy == 0
@@ -115,12 +117,34 @@ __global__ void __launch_bounds__(256) fir_tile_kernel(UpfirdnArgs p, int tiles_
         const int ix0 = ox0 - p.padx0, iy0 = oy0 - p.pady0;
         const T* xp = x + n * p.xs_n + c * p.xs_c;
         __syncthreads();        // previous tile fully consumed
-        for (int e = threadIdx.x; e < SM_H * SM_W; e += 256) {
-            const int ry = e / SM_W, rx = e - ry * SM_W;
-            const int iy = iy0 + ry, ix = ix0 + rx;
-            S v = 0;
-            if (iy >= 0 && iy < p.ih && ix >= 0 && ix < p.iw) v = to_acc<T>(__ldg(xp + iy * p.xs_h + ix));
-            sx[ry][rx] = v;
+        // halo load: a warp walks one tile row at a time (coalesced 128-byte requests), 8 warps interleave rows.
+        // All of a thread's loads are issued before the first shared-memory store so ~25 requests per thread are in flight.
+        {
+            const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+            constexpr int ROWS = (SM_H + 7) / 8, COLS = (SM_W + 31) / 32;
+            S v[ROWS][COLS];
+            #pragma unroll
+            for (int r = 0; r < ROWS; r++) {
+                const int ry = warp + 8 * r;
+                const int iy = iy0 + ry;
+                const bool row_ok = ry < SM_H && iy >= 0 && iy < p.ih;
+                const T* row = xp + (long long)iy * p.xs_h + ix0;
+                #pragma unroll
+                for (int k = 0; k < COLS; k++) {
+                    const int rx = lane + 32 * k;
+                    const int ix = ix0 + rx;
+                    v[r][k] = (row_ok && ix >= 0 && ix < p.iw) ? to_acc<T>(__ldg(row + rx)) : (S)0;
+                }
+            }
+            #pragma unroll
+            for (int r = 0; r < ROWS; r++) {
+                const int ry = warp + 8 * r;
+                #pragma unroll
+                for (int k = 0; k < COLS; k++) {
+                    const int rx = lane + 32 * k;
+                    if (ry < SM_H && rx < SM_W) sx[ry][rx] = v[r][k];
+                }
+            }
         }
         __syncthreads();
         S acc[4][4];
@@ -169,14 +193,14 @@ static int launch_upfirdn(const UpfirdnArgs& p, cudaStream_t stream) {
         const int tiles_x = (p.ow + TILE_W - 1) / TILE_W, tiles_y = (p.oh + TILE_H - 1) / TILE_H;
         const long long total = (long long)tiles_x * tiles_y * p.c * p.n;
         long long blocks = total;
-        const long long cap = (long long)sm_count() * 6;
+        const long long cap = (long long)sm_count() * occupancy_of(fir_tile_kernel<T>, 256, 0);
         if (blocks > cap) blocks = cap;
         fir_tile_kernel<T><<<(unsigned)blocks, 256, 0, stream>>>(p, tiles_x, tiles_y, total);
     } else {
         const int quads_per_row = (p.ow + 3) / 4;
         const long long total = (long long)quads_per_row * p.oh * p.c * p.n;
         long long blocks = (total + 255) / 256;
-        const long long cap = (long long)sm_count() * 8;
+        const long long cap = (long long)sm_count() * occupancy_of(generic_kernel<T>, 256, 0);
         if (blocks > cap) blocks = cap;
         generic_kernel<T><<<(unsigned)blocks, 256, 0, stream>>>(p, total, quads_per_row);
     }
@@ -190,7 +214,7 @@ int launch_upfirdn<double>(const UpfirdnArgs& p, cudaStream_t stream) {
     const int quads_per_row = (p.ow + 3) / 4;
     const long long total = (long long)quads_per_row * p.oh * p.c * p.n;
     long long blocks = (total + 255) / 256;
-    const long long cap = (long long)sm_count() * 8;
+    const long long cap = (long long)sm_count() * occupancy_of(generic_kernel<double>, 256, 0);
     if (blocks > cap) blocks = cap;
     generic_kernel<double><<<(unsigned)blocks, 256, 0, stream>>>(p, total, quads_per_row);
     count_launch();

@@ -244,3 +244,18 @@ class SynthesisChain(torch.nn.Module):
         n = self.texture.num_conv + self.texture.num_torgb
         _, tex, _ = self.texture(x_prev, None, ws.narrow(1, w_idx, n), cat_feat=cat_feats, fused=fused, impl=impl, **layer_kwargs)
         return img, pred_parsing, tex
+
+
+def shard_range(total, rank, world_size):
+    """Contiguous batch shard of rank `rank`: samples are independent in eval mode, so inference shards
+    by batch with no data-path collective.  Remainders go to the lowest ranks."""
+    base, rem = divmod(int(total), int(world_size))
+    start = rank * base + min(rank, rem)
+    return start, start + base + (1 if rank < rem else 0)
+
+
+def run_sharded(net, ws, pose_feature, cat_feats=None, rank=0, world_size=1, **kwargs):
+    """Run this rank's shard of a global batch; returns ((start, stop), outputs)."""
+    a, b = shard_range(ws.shape[0], rank, world_size)
+    cf = None if cat_feats is None else {k: v[a:b] for k, v in cat_feats.items()}
+    return (a, b), net(ws[a:b], pose_feature[a:b], cf, **kwargs)
