@@ -112,11 +112,18 @@ def peaks():
     return {'tflops': 1400.0, 'gbs': 6650.0, 'source': 'fallback of B200_PROFILING.md (1.4 PF sustained, 6.65 TB/s)'}
 
 
+def host_threads():
+    """all host threads this process may use (torchrun exports OMP_NUM_THREADS=1; the CPU arm must not inherit that)"""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_reference_rate(net_sd, num_ws, c8, batch, reps, threads=None):
     """images/s of the CPU ref path (oracle port of the reference's impl='ref' ops) on the host cores."""
     from oracle import ref_chain
-    if threads:
-        torch.set_num_threads(threads)
+    torch.set_num_threads(threads or host_threads())
     g = torch.Generator().manual_seed(7)
     ws = torch.randn(batch, num_ws, W_DIM, generator=g)
     pose = torch.randn(batch, c8, 8, 8, generator=g)
@@ -136,6 +143,7 @@ def run_reference(args):
         return
     net = build_chain('cpu')
     sd = {k: v.detach() for k, v in net.state_dict().items()}
+    torch.set_num_threads(host_threads())
     cores = torch.get_num_threads()
     batch = 1
     for _ in range(args.warmup):
@@ -293,8 +301,8 @@ def run_ours(args):
             rel = lambda a, b: float((a.cpu().double() - b.double()).norm() / b.double().norm())
             parity = {'img_rel_l2': rel(g_img, r_img), 'parsing_rel_l2': rel(g_par, r_par), 'texture_rel_l2': rel(g_tex, r_tex),
                       'img_max_abs': float((g_img.cpu() - r_img).abs().max()), 'img_abs_scale': float(r_img.abs().max())}
-            cores = torch.get_num_threads()
-            rate, ctimes = cpu_reference_rate(sd, net.num_ws, net.channels[8], 1, 3)
+            cores = host_threads()
+            rate, ctimes = cpu_reference_rate(sd, net.num_ws, net.channels[8], 1, 3, threads=cores)
             cpu = {'value': rate, 'unit': 'images/s', 'cores': cores, 'kind': 'port',
                    'sample': f'best of 3 x batch 1 through oracle/ref_chain.py (torch CPU ops, {cores} threads; {sum(ctimes):.1f} s total)'}
         imgs = batch * world * args.steps

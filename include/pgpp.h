@@ -93,13 +93,29 @@ PGPP_API int pgpp_modconv_demod_coefs(const float* w, const float* s, float* d, 
 PGPP_API int pgpp_pack_activations(const void* x, const int64_t size[4], const int64_t stride[4], int dtype,
                           const float* scale, void* out, int c_pad, int parts, void* stream);
 
+/* Same, but writes channels [c_off, c_off + c_pad) of a wider channels-innermost buffer [parts][N][H][W][c_total]
+ * (used to place the warped garment features next to a conv output so that `torch.cat` + 1x1 merge conv,
+ * training/networks.py:2179-2181, needs no concatenation pass). */
+PGPP_API int pgpp_pack_activations_slice(const void* x, const int64_t size[4], const int64_t stride[4], int dtype,
+                          const float* scale, void* out, int c_pad, int c_total, int c_off, int parts, void* stream);
+
+/* Per-sample modulated weights: out[n][p][row][c] = part p of bf16-split(master[row][c] * s[n][c]) for c < c_in,
+ * zero for c_in <= c < c_pad (training/networks.py:65-66, w * styles).  master float32 [rows][c_pad], s float32 [N][c_in]. */
+PGPP_API int pgpp_modulate_weights(const float* master, const float* s, void* out, int n, int64_t rows, int c_pad, int c_in,
+                          int parts, void* stream);
+
 /* Epilogue + geometry of one implicit-GEMM convolution launch. */
 typedef struct {
     /* packed activations [a_parts][N][H][W][c_pad] bf16 and packed weights [b_parts][taps][o_rows][c_pad] bf16 */
     const void* act;
     const void* wgt;
     int32_t a_parts, b_parts;
-    int32_t n, h, w, c_pad;         /* input geometry */
+    int32_t n, h, w, c_pad;         /* input geometry; c_pad = channels consumed (multiple of 16) */
+    int32_t act_pixel_stride;       /* elements between consecutive pixels of act (>= c_pad; 0 means c_pad): lets a conv read a
+                                       channel slice of a wider channels-innermost buffer */
+    int32_t wgt_per_sample;         /* 0: wgt is [b_parts][taps][o_rows][c_pad] shared by all samples;
+                                       1: wgt is [N][b_parts][taps][o_rows][c_pad], sample n uses its own weights (the style
+                                          modulation w * s[n] of training/networks.py:65-66 folded into the weights) */
     int32_t kh, kw;                 /* filter taps */
     int32_t pad_y, pad_x;           /* zero padding (top / left); bottom / right implied by out size */
     int32_t stride;                 /* 1 or 2 */
@@ -124,6 +140,9 @@ typedef struct {
     int32_t out_h, out_w;
     int64_t out_stride[4];
     int32_t accumulate;             /* nonzero: out += result (used for `img = img + y`, networks.py:2190) */
+    int32_t out_parts;              /* 1, or 2 / 3 with out_dtype BF16 and out_stride[1] == 1: write the bf16 expansion of the result
+                                       (part p at out + p * out_part_stride), i.e. the packed activation format of the next conv */
+    int64_t out_part_stride;
 } pgpp_conv_desc;
 
 /* Implicit-GEMM convolution on the 5th-gen tensor cores (tcgen05.mma, TMEM accumulators, TMA operand

@@ -67,6 +67,8 @@ struct IgemmParams {
     void* out; int out_dtype; int out_h, out_w; long long os_n, os_c, os_h, os_w;
     int accumulate;
     int up;     // 1, or 2 when phases == 4
+    int wgt_per_sample;                 // weights carry a leading sample dimension
+    int out_parts; long long out_part_stride;
     int fold_gain;                      // activation is positively homogeneous and gain > 0: gain is folded into scale/shift/noise
     unsigned div_col_m, div_col_s, div_x_m, div_x_s, div_y_m, div_y_s;   // magic numbers for t / tiles_col, / tiles_x, / tiles_y
 };
@@ -109,9 +111,9 @@ __device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map
     asm volatile("cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
                  ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
 }
-__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
-    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-                 ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                 ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
 }
 
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -232,13 +234,15 @@ __device__ __forceinline__ void epilogue_general(const IgemmParams& p, const Til
             }
         }
         if (cs == 1 && valid == 16 && !p.accumulate && ((base + oc0) * sizeof(OT)) % 16 == 0 && ((uintptr_t)out & 15) == 0) {
-            __align__(16) OT tmp[16];
-            #pragma unroll
-            for (int j = 0; j < 16; j++) tmp[j] = cvt_out<OT>(v[j]);
-            int4* dst = reinterpret_cast<int4*>(out + base + oc0);
-            const int4* src = reinterpret_cast<const int4*>(tmp);
-            #pragma unroll
-            for (int q = 0; q < (int)(16 * sizeof(OT) / 16); q++) dst[q] = src[q];
+            for (int part = 0; part < p.out_parts; part++) {
+                __align__(16) OT tmp[16];
+                #pragma unroll
+                for (int j = 0; j < 16; j++) { tmp[j] = cvt_out<OT>(v[j]); v[j] -= cvt_in<OT>(tmp[j]); }
+                int4* dst = reinterpret_cast<int4*>(out + part * p.out_part_stride + base + oc0);
+                const int4* src = reinterpret_cast<const int4*>(tmp);
+                #pragma unroll
+                for (int q = 0; q < (int)(16 * sizeof(OT) / 16); q++) dst[q] = src[q];
+            }
         } else {
             OT* dst = out + base + (long long)oc0 * cs;
             #pragma unroll
@@ -287,13 +291,17 @@ __device__ __forceinline__ void epilogue_fast(const IgemmParams& p, const TileCo
             v[j] = r;
         }
         if (nhwc && valid == 16 && ((base + oc0) * sizeof(OT)) % 16 == 0 && ((uintptr_t)out & 15) == 0) {
-            __align__(16) OT tmp[16];
-            #pragma unroll
-            for (int j = 0; j < 16; j++) tmp[j] = cvt_out<OT>(v[j]);
-            int4* dst = reinterpret_cast<int4*>(out + base + oc0);
-            const int4* src = reinterpret_cast<const int4*>(tmp);
-            #pragma unroll
-            for (int q = 0; q < (int)(16 * sizeof(OT) / 16); q++) dst[q] = src[q];
+            // channels-innermost output: 16 consecutive channels of one pixel, 128-bit stores; with out_parts > 1 the
+            // bf16 expansion of the value is written (part q = bf16(v - earlier parts)): the next conv's operand format
+            for (int part = 0; part < p.out_parts; part++) {
+                __align__(16) OT tmp[16];
+                #pragma unroll
+                for (int j = 0; j < 16; j++) { tmp[j] = cvt_out<OT>(v[j]); v[j] -= cvt_in<OT>(tmp[j]); }
+                int4* dst = reinterpret_cast<int4*>(out + part * p.out_part_stride + base + oc0);
+                const int4* src = reinterpret_cast<const int4*>(tmp);
+                #pragma unroll
+                for (int q = 0; q < (int)(16 * sizeof(OT) / 16); q++) dst[q] = src[q];
+            }
         } else {
             OT* dst = out + base + (long long)oc0 * p.os_c;
             if (valid == 16) {
@@ -371,7 +379,16 @@ __device__ __forceinline__ void mma_role(const IgemmParams& p, const MmaCtx mc) 
     int sb = 0; uint32_t phb = 0;
     int buf = 0; uint32_t buf_phase = 0;
     bool first_tile = true;
+    int last_n = -1; uint32_t res_phase = 0;
     for (long long t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+        // resident weights: wait for the (re)load on the first tile and whenever the sample changed (per-sample weights)
+        bool res_wait = false;
+        if (p.b_resident) {
+            const int n0 = p.wgt_per_sample ? decode_tile(p, t).n0 : 0;
+            res_wait = first_tile || n0 != last_n;
+            if (res_wait && !first_tile) res_phase ^= 1;
+            last_n = n0;
+        }
         mbar_wait(tempty_bar(buf), buf_phase ^ 1);      // epilogue has drained this accumulator
         tc_fence_after();
         const uint32_t tmem_d = mc.tmem_base + (uint32_t)(buf * p.block_n);
@@ -390,7 +407,7 @@ __device__ __forceinline__ void mma_role(const IgemmParams& p, const MmaCtx mc) 
                         if (pb >= parts) break;
                         uint32_t b16;
                         if (p.b_resident) {
-                            if (first_tile) { mbar_wait(bfull_bar((int)((b_res16 - (mc.b_base >> 4)) / bpitch16)), 0); tc_fence_after(); }
+                            if (res_wait) { mbar_wait(bfull_bar((int)((b_res16 - (mc.b_base >> 4)) / bpitch16)), res_phase); tc_fence_after(); }
                             b16 = b_res16;
                             b_res16 += bpitch16;
                         } else {
@@ -480,9 +497,15 @@ igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
         if (elect_one()) {
             int sa = 0; uint32_t pha = 0;
             int sb = 0; uint32_t phb = 0;
-            bool first_tile = true;
-            for (long long t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+            int k_tile = 0, last_n = -1;
+            for (long long t = blockIdx.x; t < p.total_tiles; t += gridDim.x, k_tile++) {
                 const TileCoord tc = decode_tile(p, t);
+                const int wn = p.wgt_per_sample ? tc.n0 : 0;
+                // resident weights are (re)loaded on the first tile and whenever the sample changes (per-sample weights)
+                const bool load_res = p.b_resident && (k_tile == 0 || (p.wgt_per_sample && tc.n0 != last_n));
+                if (load_res && k_tile > 0)     // every MMA of the previous tile must have read the old weights
+                    mbar_wait(tfull_bar((k_tile - 1) & 1), (uint32_t)((k_tile - 1) >> 1) & 1u);
+                last_n = tc.n0;
                 int b_slot = 0;
                 for (int g = 0; g < p.n_groups; g++) {
                     // reuse: group = kx, the slab spans all ky;  no reuse: group = tap
@@ -500,22 +523,21 @@ igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
                             const int tap = (ky0 + j) * p.kw + kx;
                             for (int pb = 0; pb < p.parts; pb++) {
                                 if (p.b_resident) {
-                                    if (first_tile) {
+                                    if (load_res) {
                                         mbar_expect_tx(bfull_bar(b_slot), p.b_bytes);
-                                        tma_load_3d(b_base + b_slot * p.b_pitch, &map_b, bfull_bar(b_slot), cb * p.kb, tap * p.o_rows + tc.col0, pb);
+                                        tma_load_4d(b_base + b_slot * p.b_pitch, &map_b, bfull_bar(b_slot), cb * p.kb, tap * p.o_rows + tc.col0, pb, wn);
                                     }
                                     b_slot++;
                                 } else {
                                     mbar_wait(bempty_bar(sb), phb ^ 1);
                                     mbar_expect_tx(bfull_bar(sb), p.b_bytes);
-                                    tma_load_3d(b_base + sb * p.b_pitch, &map_b, bfull_bar(sb), cb * p.kb, tap * p.o_rows + tc.col0, pb);
+                                    tma_load_4d(b_base + sb * p.b_pitch, &map_b, bfull_bar(sb), cb * p.kb, tap * p.o_rows + tc.col0, pb, wn);
                                     if (++sb == SB) { sb = 0; phb ^= 1; }
                                 }
                             }
                         }
                     }
                 }
-                first_tile = false;
             }
         }
     } else if (warp == 1) {
@@ -633,6 +655,13 @@ extern "C" int pgpp_conv2d_igemm(const pgpp_conv_desc* d, void* stream) {
     PGPP_REQUIRE(d->out_dtype == PGPP_F32 || d->out_dtype == PGPP_BF16 || d->out_dtype == PGPP_F16, "unsupported output dtype");
     PGPP_REQUIRE(d->act_fn >= 1 && d->act_fn <= 9, "no CUDA kernel found for the specified activation func");
     PGPP_REQUIRE(((uintptr_t)d->act & 15) == 0 && ((uintptr_t)d->wgt & 15) == 0, "packed operands must be 16-byte aligned");
+    const int out_parts = d->out_parts <= 0 ? 1 : d->out_parts;
+    PGPP_REQUIRE(out_parts <= 3, "out_parts must be 1, 2 or 3");
+    PGPP_REQUIRE(out_parts == 1 || (d->out_dtype == PGPP_BF16 && d->out_stride[1] == 1 && !d->accumulate && d->o % 16 == 0 &&
+                                    d->out_stride[3] % 8 == 0 && d->out_part_stride % 8 == 0 && ((uintptr_t)d->out & 15) == 0),
+                 "split output needs bf16, channels-innermost, 16-byte aligned pixels, out channels % 16 == 0, no accumulate");
+    const int pix_stride = d->act_pixel_stride > 0 ? d->act_pixel_stride : d->c_pad;
+    PGPP_REQUIRE(pix_stride >= d->c_pad && pix_stride % 8 == 0, "act_pixel_stride must be >= c_pad and a multiple of 8");
     const int up = d->phases == 4 ? 2 : 1;
     PGPP_REQUIRE(d->out_h == d->conv_h * up && d->out_w == d->conv_w * up, "output size does not match the conv grid");
 
@@ -708,6 +737,9 @@ extern "C" int pgpp_conv2d_igemm(const pgpp_conv_desc* d, void* stream) {
     p.out = d->out; p.out_dtype = d->out_dtype; p.out_h = d->out_h; p.out_w = d->out_w;
     p.os_n = d->out_stride[0]; p.os_c = d->out_stride[1]; p.os_h = d->out_stride[2]; p.os_w = d->out_stride[3];
     p.accumulate = d->accumulate;
+    p.wgt_per_sample = d->wgt_per_sample ? 1 : 0;
+    p.out_parts = out_parts; p.out_part_stride = d->out_part_stride;
+    PGPP_REQUIRE(!p.wgt_per_sample || p.tn == 1, "per-sample weights need images of at least 128 pixels (one sample per tile)");
     p.fold_gain = (d->gain > 0.f && (d->act_fn == PGPP_ACT_LINEAR || d->act_fn == PGPP_ACT_RELU ||
                                      (d->act_fn == PGPP_ACT_LRELU && d->alpha >= 0.f && d->alpha <= 1.f))) ? 1 : 0;
     auto magic = [](unsigned dv, unsigned& m, unsigned& sft) {
@@ -723,19 +755,20 @@ extern "C" int pgpp_conv2d_igemm(const pgpp_conv_desc* d, void* stream) {
     CUtensorMap map_a, map_b;
     {
         const cuuint64_t dims[5] = {(cuuint64_t)d->c_pad, (cuuint64_t)d->w, (cuuint64_t)d->h, (cuuint64_t)d->n, (cuuint64_t)d->a_parts};
-        const cuuint64_t strides[4] = {(cuuint64_t)d->c_pad * 2, (cuuint64_t)d->c_pad * 2 * d->w, (cuuint64_t)d->c_pad * 2 * d->w * d->h,
-                                       (cuuint64_t)d->c_pad * 2 * d->w * d->h * d->n};
+        const cuuint64_t strides[4] = {(cuuint64_t)pix_stride * 2, (cuuint64_t)pix_stride * 2 * d->w, (cuuint64_t)pix_stride * 2 * d->w * d->h,
+                                       (cuuint64_t)pix_stride * 2 * d->w * d->h * d->n};
         const cuuint32_t box[5] = {(cuuint32_t)p.kb, (cuuint32_t)(p.tw * d->stride), (cuuint32_t)((p.th + p.inner - 1) * d->stride), (cuuint32_t)p.tn, 1};
         const cuuint32_t estr[5] = {1, (cuuint32_t)d->stride, (cuuint32_t)d->stride, 1, 1};
         const CUtensorMapSwizzle sw = row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
         CUresult r = encode(&map_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(d->act), dims, strides, box, estr,
                             CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(activations) failed with CUresult %d", (int)r); return PGPP_ERR_CUDA; }
-        const cuuint64_t wdims[3] = {(cuuint64_t)d->c_pad, (cuuint64_t)d->o_rows * d->kh * d->kw, (cuuint64_t)d->b_parts};
-        const cuuint64_t wstrides[2] = {(cuuint64_t)d->c_pad * 2, (cuuint64_t)d->c_pad * 2 * d->o_rows * d->kh * d->kw};
-        const cuuint32_t wbox[3] = {(cuuint32_t)p.kb, (cuuint32_t)d->block_n, 1};
-        const cuuint32_t westr[3] = {1, 1, 1};
-        r = encode(&map_b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(d->wgt), wdims, wstrides, wbox, westr,
+        const cuuint64_t wrows = (cuuint64_t)d->o_rows * d->kh * d->kw;
+        const cuuint64_t wdims[4] = {(cuuint64_t)d->c_pad, wrows, (cuuint64_t)d->b_parts, (cuuint64_t)(d->wgt_per_sample ? d->n : 1)};
+        const cuuint64_t wstrides[3] = {(cuuint64_t)d->c_pad * 2, (cuuint64_t)d->c_pad * 2 * wrows, (cuuint64_t)d->c_pad * 2 * wrows * d->b_parts};
+        const cuuint32_t wbox[4] = {(cuuint32_t)p.kb, (cuuint32_t)d->block_n, 1, 1};
+        const cuuint32_t westr[4] = {1, 1, 1, 1};
+        r = encode(&map_b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(d->wgt), wdims, wstrides, wbox, westr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(weights) failed with CUresult %d", (int)r); return PGPP_ERR_CUDA; }
     }

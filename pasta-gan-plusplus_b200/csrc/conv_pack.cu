@@ -9,6 +9,7 @@ namespace pgpp {
 struct PackArgs {
     const void* x; const float* scale; __nv_bfloat16* out;
     int n, c, h, w, c_pad, parts;
+    int c_total, c_off;         // destination pixel stride and first channel
     long long s_n, s_c, s_h, s_w;
     long long part_stride;      // elements between parts = n*h*w*c_pad
 };
@@ -57,7 +58,7 @@ __global__ void __launch_bounds__(256) pack_nchw_kernel(PackArgs p, int w_tiles,
             float v[8];
             #pragma unroll
             for (int j = 0; j < 8; j++) v[j] = tile[cg * 8 + j][px];
-            __nv_bfloat16* dst = p.out + (((long long)n * p.h + y) * p.w + (x0 + px)) * p.c_pad + c0 + cg * 8;
+            __nv_bfloat16* dst = p.out + (((long long)n * p.h + y) * p.w + (x0 + px)) * p.c_total + p.c_off + c0 + cg * 8;
             for (int part = 0; part < p.parts; part++) {
                 __align__(16) __nv_bfloat16 q[8];
                 #pragma unroll
@@ -82,7 +83,7 @@ __global__ void __launch_bounds__(256) pack_generic_kernel(PackArgs p, long long
             v = (float)to_acc<T>(((const T*)p.x)[n * p.s_n + c * p.s_c + y * p.s_h + x * p.s_w]);
             if (p.scale) v *= p.scale[n * p.c + c];
         }
-        split_store(v, p.out + e, p.part_stride, p.parts);
+        split_store(v, p.out + (e / p.c_pad) * p.c_total + p.c_off + c, p.part_stride, p.parts);
     }
 }
 
@@ -131,16 +132,66 @@ __global__ void __launch_bounds__(256) demod_kernel(const float* __restrict__ w,
 
 extern "C" int pgpp_pack_activations(const void* x, const int64_t size[4], const int64_t stride[4], int dtype,
                                      const float* scale, void* out, int c_pad, int parts, void* stream) {
+    return pgpp_pack_activations_slice(x, size, stride, dtype, scale, out, c_pad, c_pad, 0, parts, stream);
+}
+
+namespace pgpp {
+__global__ void __launch_bounds__(256) modulate_weights_kernel(const float* __restrict__ master, const float* __restrict__ s,
+                                                               __nv_bfloat16* __restrict__ out, long long rows, int c_pad, int c_in,
+                                                               int parts, long long per_sample_part) {
+    // one thread per 8 consecutive channels of one (sample, row): 128-bit stores per part
+    const int groups = c_pad / 8;
+    const long long total = rows * groups;
+    const int n = blockIdx.y;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const long long row = e / groups;
+        const int c0 = (int)(e - row * groups) * 8;
+        float v[8];
+        #pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const int c = c0 + j;
+            v[j] = c < c_in ? master[row * c_pad + c] * s[(long long)n * c_in + c] : 0.f;
+        }
+        __nv_bfloat16* dst = out + (long long)n * parts * per_sample_part + row * c_pad + c0;
+        for (int part = 0; part < parts; part++) {
+            __align__(16) __nv_bfloat16 q[8];
+            #pragma unroll
+            for (int j = 0; j < 8; j++) { q[j] = __float2bfloat16_rn(v[j]); v[j] -= __bfloat162float(q[j]); }
+            *reinterpret_cast<int4*>(dst + part * per_sample_part) = *reinterpret_cast<const int4*>(q);
+        }
+    }
+}
+} // namespace pgpp
+
+extern "C" int pgpp_modulate_weights(const float* master, const float* s, void* out, int n, int64_t rows, int c_pad, int c_in,
+                                     int parts, void* stream) {
+    using namespace pgpp;
+    PGPP_REQUIRE(master && s && out, "master, s and out must be device pointers");
+    PGPP_REQUIRE(n >= 1 && n <= 65535 && rows >= 1 && c_pad % 16 == 0 && c_in >= 1 && c_in <= c_pad && parts >= 1 && parts <= 3, "bad modulate_weights arguments");
+    const long long total = rows * (c_pad / 8);
+    long long blocks = (total + 255) / 256;
+    if (blocks > 4096) blocks = 4096;
+    modulate_weights_kernel<<<dim3((unsigned)blocks, (unsigned)n), 256, 0, (cudaStream_t)stream>>>(master, s, (__nv_bfloat16*)out, rows, c_pad, c_in,
+                                                                                                  parts, rows * c_pad);
+    count_launch();
+    PGPP_CUDA_OK(cudaGetLastError());
+    return PGPP_OK;
+}
+
+extern "C" int pgpp_pack_activations_slice(const void* x, const int64_t size[4], const int64_t stride[4], int dtype,
+                                           const float* scale, void* out, int c_pad, int c_total, int c_off, int parts, void* stream) {
     using namespace pgpp;
     PGPP_REQUIRE(x && out, "x and out must be device pointers");
     PGPP_REQUIRE(parts >= 1 && parts <= 3, "parts must be 1, 2 or 3");
     PGPP_REQUIRE(c_pad >= size[1] && c_pad % 16 == 0, "c_pad must be a multiple of 16 and >= C");
+    PGPP_REQUIRE(c_total >= c_off + c_pad && c_total % 8 == 0 && c_off % 8 == 0 && c_off >= 0, "bad destination channel slice");
     PackArgs p;
+    p.c_total = c_total; p.c_off = c_off;
     p.x = x; p.scale = scale; p.out = (__nv_bfloat16*)out;
     p.n = (int)size[0]; p.c = (int)size[1]; p.h = (int)size[2]; p.w = (int)size[3];
     p.c_pad = c_pad; p.parts = parts;
     p.s_n = stride[0]; p.s_c = stride[1]; p.s_h = stride[2]; p.s_w = stride[3];
-    p.part_stride = (long long)p.n * p.h * p.w * c_pad;
+    p.part_stride = (long long)p.n * p.h * p.w * c_total;
     if (p.part_stride == 0) return PGPP_OK;
     cudaStream_t s = (cudaStream_t)stream;
     switch (dtype) {

@@ -28,6 +28,7 @@ class ConvDesc(ctypes.Structure):
         ('act', ctypes.c_void_p), ('wgt', ctypes.c_void_p),
         ('a_parts', ctypes.c_int32), ('b_parts', ctypes.c_int32),
         ('n', ctypes.c_int32), ('h', ctypes.c_int32), ('w', ctypes.c_int32), ('c_pad', ctypes.c_int32),
+        ('act_pixel_stride', ctypes.c_int32), ('wgt_per_sample', ctypes.c_int32),
         ('kh', ctypes.c_int32), ('kw', ctypes.c_int32),
         ('pad_y', ctypes.c_int32), ('pad_x', ctypes.c_int32),
         ('stride', ctypes.c_int32),
@@ -38,7 +39,7 @@ class ConvDesc(ctypes.Structure):
         ('act_fn', ctypes.c_int32), ('alpha', ctypes.c_float), ('gain', ctypes.c_float), ('clamp', ctypes.c_float),
         ('out', ctypes.c_void_p), ('out_dtype', ctypes.c_int32), ('out_h', ctypes.c_int32), ('out_w', ctypes.c_int32),
         ('out_stride', ctypes.c_int64 * 4),
-        ('accumulate', ctypes.c_int32),
+        ('accumulate', ctypes.c_int32), ('out_parts', ctypes.c_int32), ('out_part_stride', ctypes.c_int64),
     ]
 
 
@@ -68,6 +69,10 @@ def load_library():
     lib.pgpp_modconv_demod_coefs.argtypes = [vp, vp, vp, i32, i32, i32, i32, f32, vp]
     lib.pgpp_pack_activations.restype = i32
     lib.pgpp_pack_activations.argtypes = [vp, c_i64x4, c_i64x4, i32, vp, vp, i32, i32, vp]
+    lib.pgpp_pack_activations_slice.restype = i32
+    lib.pgpp_pack_activations_slice.argtypes = [vp, c_i64x4, c_i64x4, i32, vp, vp, i32, i32, i32, i32, vp]
+    lib.pgpp_modulate_weights.restype = i32
+    lib.pgpp_modulate_weights.argtypes = [vp, vp, vp, i32, i64, i32, i32, i32, vp]
     lib.pgpp_conv2d_igemm.restype = i32
     lib.pgpp_conv2d_igemm.argtypes = [ctypes.POINTER(ConvDesc), vp]
     _lib = lib
@@ -75,7 +80,8 @@ def load_library():
 
 
 EXPORTED_SYMBOLS = ('pgpp_version', 'pgpp_last_error', 'pgpp_launch_count', 'pgpp_bias_act', 'pgpp_upfirdn2d',
-                    'pgpp_modconv_demod_coefs', 'pgpp_pack_activations', 'pgpp_conv2d_igemm')
+                    'pgpp_modconv_demod_coefs', 'pgpp_pack_activations', 'pgpp_pack_activations_slice', 'pgpp_modulate_weights',
+                    'pgpp_conv2d_igemm')
 
 
 def launch_count():
@@ -210,6 +216,31 @@ class _ConvPlugin:
         with torch.cuda.device(x.device):
             _check(lib.pgpp_pack_activations(_ptr(x), c_i64x4(*x.shape), c_i64x4(*x.stride()), dtype_code(x.dtype),
                                              _ptr(scale), _ptr(out), int(c_pad), int(parts), _stream(x)))
+        return out
+
+    @staticmethod
+    def pack_activations_into(x, scale, dst, c_pad, c_off):
+        """pack x (optionally * scale[n,c]) into channels [c_off, c_off + c_pad) of dst [parts, N, H, W, c_total]"""
+        lib = load_library()
+        n, c, h, w = x.shape
+        parts, c_total = dst.shape[0], dst.shape[4]
+        _torch_check(tuple(dst.shape[1:4]) == (n, h, w) and dst.dtype == torch.bfloat16 and dst.is_contiguous(), 'bad packed destination')
+        if scale is not None:
+            scale = scale.detach().to(torch.float32).contiguous()
+        with torch.cuda.device(x.device):
+            _check(lib.pgpp_pack_activations_slice(_ptr(x), c_i64x4(*x.shape), c_i64x4(*x.stride()), dtype_code(x.dtype), _ptr(scale),
+                                                   _ptr(dst), int(c_pad), int(c_total), int(c_off), int(parts), _stream(x)))
+        return dst
+
+    @staticmethod
+    def modulate_weights(master, styles, parts):
+        """master float32 [rows, c_pad], styles [N, c_in] -> bf16 [N, parts, rows, c_pad]"""
+        lib = load_library()
+        rows, c_pad = master.shape
+        s = styles.detach().to(torch.float32).contiguous()
+        out = torch.empty([s.shape[0], parts, rows, c_pad], dtype=torch.bfloat16, device=master.device)
+        with torch.cuda.device(master.device):
+            _check(lib.pgpp_modulate_weights(_ptr(master), _ptr(s), _ptr(out), s.shape[0], rows, c_pad, s.shape[1], int(parts), _stream(master)))
         return out
 
     @staticmethod

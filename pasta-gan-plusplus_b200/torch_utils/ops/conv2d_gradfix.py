@@ -88,7 +88,37 @@ def _split_bf16(t, parts):
 
 class PackedWeights:
     """[parts, taps, o_rows, c_pad] bf16, K-major rows, ready for the TMA weight map."""
-    __slots__ = ('data', 'kh', 'kw', 'o', 'phases', 'phase_stride', 'o_rows', 'c_pad', 'parts', 'pad_y', 'pad_x')
+    __slots__ = ('data', 'master', 'kh', 'kw', 'o', 'phases', 'phase_stride', 'o_rows', 'c_pad', 'c_in', 'parts', 'pad_y', 'pad_x')
+
+
+class PackedAct:
+    """Activations in the tensor-core operand format: data [parts, N, H, W, c_total] bf16, channels innermost; the
+    logical tensor is channels [c_off, c_off + c) of every pixel.  Convolutions can write this format directly from
+    their epilogue (`out_packed=`) and read it without a packing pass."""
+    __slots__ = ('data', 'c', 'c_off')
+
+    def __init__(self, data, c, c_off=0):
+        self.data, self.c, self.c_off = data, c, c_off
+
+    @staticmethod
+    def empty(n, h, w, c_total, parts, device):
+        return torch.empty([parts, n, h, w, c_total], dtype=torch.bfloat16, device=device)
+
+    @property
+    def shape(self):
+        return (self.data.shape[1], self.c, self.data.shape[2], self.data.shape[3])
+
+    @property
+    def device(self):
+        return self.data.device
+
+    def view(self, c, c_off):
+        return PackedAct(self.data, c, c_off)
+
+    def to_nchw(self, dtype=torch.float32):
+        """debug / test helper: sum of the parts as a [N, C, H, W] tensor"""
+        v = self.data[:, :, :, :, self.c_off:self.c_off + self.c].to(torch.float32).sum(0)
+        return v.permute(0, 3, 1, 2).contiguous().to(dtype)
 
 
 def choose_block_n(cols, m_tiles, sms=148):
@@ -113,6 +143,8 @@ def pack_weights(w_taps, o, phases, kh, kw, parts, pad_y, pad_x):
     buf[:, :cols].reshape(taps, phases, phase_stride, c_pad)[:, :, :o, :ic] = w_taps.reshape(taps, phases, o, ic)
     pw = PackedWeights()
     pw.data = _split_bf16(buf, parts).contiguous()
+    pw.master = buf.reshape(taps * o_rows, c_pad)       # fp32 rows for the per-sample (style-modulated) weight route
+    pw.c_in = ic
     pw.kh, pw.kw, pw.o, pw.phases, pw.o_rows, pw.c_pad, pw.parts = kh, kw, o, phases, o_rows, c_pad, parts
     pw.phase_stride = phase_stride
     pw.pad_y, pw.pad_x = pad_y, pad_x
@@ -195,16 +227,39 @@ def packed_up2(weight, f, flip_weight, flip_filter, parts):
 
 def igemm_conv(x, pw, *, scale=None, stride=1, out_hw=None, dcoef=None, noise=None, bias=None, act='linear',
                alpha=0.0, gain=1.0, clamp=-1.0, out=None, out_dtype=None, accumulate=False, precision=None,
-               memory_format=None, x_packed=None):
-    """Run one fused convolution.  x: [N, I, H, W] (any float dtype / layout) or pre-packed activations.
-    Returns [N, O, out_h, out_w]."""
+               memory_format=None, out_packed=None):
+    """Run one fused convolution.
+    x          [N, I, H, W] tensor (any float dtype / layout; packed here, `scale` [N, I] = style modulation folded into the
+               packing pass) or a PackedAct (no packing pass; `scale` is then folded into per-sample weights).
+    out_packed None -> returns a [N, O, out_h, out_w] tensor (`out` / `out_dtype` / `memory_format` as given);
+               PackedAct view -> the epilogue writes the bf16 operand format of the next conv into that channel slice."""
     _init()
     n, ic, h, w = x.shape
-    precision = precision or precision_for(x.dtype)
+    src_dtype = torch.float32 if isinstance(x, PackedAct) else x.dtype
+    precision = precision or precision_for(src_dtype)
     products, parts = _PRODUCTS[precision]
     assert pw.parts >= parts, 'weights were packed with fewer parts than the requested precision needs'
-    if x_packed is None:
+    d = custom_ops.ConvDesc()
+    keep = []
+    if isinstance(x, PackedAct):
+        assert x.data.shape[0] >= parts and x.c_off % 8 == 0
+        assert pw.c_pad <= x.data.shape[4] - x.c_off, 'packed activations have fewer channels than the weights expect'
+        d.act = x.data.data_ptr() + 2 * x.c_off
+        d.a_parts = x.data.shape[0]
+        d.act_pixel_stride = x.data.shape[4]
+        device = x.data.device
+        if scale is not None:       # style modulation folded into per-sample weights (needs >= 128 pixels per sample)
+            wdata = _plugin.modulate_weights(pw.master, scale, parts)
+            keep.append(wdata)
+            d.wgt = wdata.data_ptr(); d.b_parts = parts; d.wgt_per_sample = 1
+        else:
+            d.wgt = pw.data.data_ptr(); d.b_parts = pw.data.shape[0]
+    else:
         x_packed = _plugin.pack_activations(x, scale, pw.c_pad, parts)
+        keep.append(x_packed)
+        d.act = x_packed.data_ptr(); d.a_parts = parts
+        d.wgt = pw.data.data_ptr(); d.b_parts = pw.data.shape[0]
+        device = x.device
     up = 2 if pw.phases == 4 else 1
     if out_hw is None:
         conv_h = (h + 2 * pw.pad_y - pw.kh) // stride + 1
@@ -212,12 +267,28 @@ def igemm_conv(x, pw, *, scale=None, stride=1, out_hw=None, dcoef=None, noise=No
     else:
         conv_h, conv_w = out_hw
     out_h, out_w = conv_h * up, conv_w * up
-    if out is None:
-        out_dtype = out_dtype or (x.dtype if x.dtype != torch.float64 else torch.float32)
-        if memory_format is None:
-            memory_format = torch.channels_last if (x.stride(1) == 1 and ic > 1) else torch.contiguous_format
-        out = torch.empty([n, pw.o, out_h, out_w], dtype=out_dtype, device=x.device, memory_format=memory_format)
-    assert tuple(out.shape) == (n, pw.o, out_h, out_w)
+    if out_packed is not None:
+        assert tuple(out_packed.data.shape[1:4]) == (n, out_h, out_w) and out_packed.c == pw.o
+        assert pw.o % 16 == 0 and out_packed.c_off % 8 == 0 and not accumulate
+        c_total = out_packed.data.shape[4]
+        d.out = out_packed.data.data_ptr() + 2 * out_packed.c_off
+        d.out_dtype = custom_ops.dtype_code(torch.bfloat16)
+        d.out_stride = (ctypes.c_int64 * 4)(out_h * out_w * c_total, 1, out_w * c_total, c_total)
+        d.out_parts = out_packed.data.shape[0]
+        d.out_part_stride = out_packed.data[0].numel()
+        result = out_packed
+    else:
+        if out is None:
+            out_dtype = out_dtype or (src_dtype if src_dtype != torch.float64 else torch.float32)
+            if memory_format is None:
+                cl = (not isinstance(x, PackedAct)) and x.stride(1) == 1 and ic > 1
+                memory_format = torch.channels_last if cl else torch.contiguous_format
+            out = torch.empty([n, pw.o, out_h, out_w], dtype=out_dtype, device=device, memory_format=memory_format)
+        assert tuple(out.shape) == (n, pw.o, out_h, out_w)
+        d.out = out.data_ptr(); d.out_dtype = custom_ops.dtype_code(out.dtype)
+        d.out_stride = (ctypes.c_int64 * 4)(*out.stride())
+        d.out_parts = 1
+        result = out
 
     tw = min(128, 1 << (conv_w - 1).bit_length())
     th = min(128 // tw, 1 << (conv_h - 1).bit_length())
@@ -227,14 +298,10 @@ def igemm_conv(x, pw, *, scale=None, stride=1, out_hw=None, dcoef=None, noise=No
     while pw.o_rows % block_n:
         block_n //= 2
 
-    d = custom_ops.ConvDesc()
-    d.act = x_packed.data_ptr(); d.wgt = pw.data.data_ptr()
-    d.a_parts = x_packed.shape[0]; d.b_parts = pw.data.shape[0]
     d.n, d.h, d.w, d.c_pad = n, h, w, pw.c_pad
     d.kh, d.kw, d.pad_y, d.pad_x, d.stride = pw.kh, pw.kw, pw.pad_y, pw.pad_x, stride
     d.conv_h, d.conv_w = conv_h, conv_w
     d.o, d.phases, d.phase_stride, d.o_rows, d.block_n, d.products = pw.o, pw.phases, pw.phase_stride, pw.o_rows, block_n, products
-    keep = []
     def fptr(t):
         if t is None:
             return None
@@ -254,21 +321,19 @@ def igemm_conv(x, pw, *, scale=None, stride=1, out_hw=None, dcoef=None, noise=No
         d.noise = nz.data_ptr()
     d.bias = fptr(bias)
     d.act_fn = _ACT_IDX[act]; d.alpha = float(alpha); d.gain = float(gain); d.clamp = float(clamp)
-    d.out = out.data_ptr(); d.out_dtype = custom_ops.dtype_code(out.dtype)
     d.out_h, d.out_w = out_h, out_w
-    d.out_stride = (ctypes.c_int64 * 4)(*out.stride())
     d.accumulate = int(bool(accumulate))
     if trace is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        _plugin.conv2d_igemm(d, x.device)
+        _plugin.conv2d_igemm(d, device)
         e1.record()
         # algorithmic FLOPs: 2*N*O*I*kh*kw*P; for the polyphase up=2 form the transposed conv's 9 taps per INPUT pixel
         flops = 2.0 * n * pw.o * ic * (9 if pw.phases == 4 else pw.kh * pw.kw) * conv_h * conv_w
         trace.append((f'igemm {ic}->{pw.o} k{pw.kh} {h}x{w}->{out_h}x{out_w} n{n} {precision}', flops, e0, e1))
     else:
-        _plugin.conv2d_igemm(d, x.device)
-    return out
+        _plugin.conv2d_igemm(d, device)
+    return result
 
 
 # ------------------------------------------------------------------------------------------------

@@ -42,15 +42,18 @@ def _kernel_path_ok(x, weight, styles, noise, up, down, padding, resample_filter
 
 def modulated_conv2d_fused_act(x, weight, styles, noise=None, up=1, padding=0, resample_filter=None, demodulate=True,
                                flip_weight=True, bias=None, act='linear', alpha=None, gain=None, clamp=None,
-                               out=None, out_dtype=None, accumulate=False, memory_format=None):
+                               out=None, out_dtype=None, accumulate=False, memory_format=None, out_packed=None):
     """Kernel path of modulated_conv2d with bias_act fused into the same launch (what SynthesisLayer / ToRGB
     compose, networks.py:1925-1935 and SURVEY Appendix E): returns
-    clamp(act(modconv(x) + bias) * gain).  Inference only (no autograd)."""
+    clamp(act(modconv(x) + bias) * gain).  Inference only (no autograd).
+    x may be a conv2d_gradfix.PackedAct (then the style scale is folded into per-sample weights instead of the packing
+    pass) and out_packed a PackedAct view to receive the result in operand format."""
     spec = bias_act.activation_funcs[act]
     alpha = float(spec.def_alpha if alpha is None else alpha)
     gain = float(spec.def_gain if gain is None else gain)
     clamp = float(-1 if clamp is None else clamp)
-    _, parts = conv2d_gradfix._PRODUCTS[conv2d_gradfix.precision_for(x.dtype)]
+    src_dtype = torch.float32 if isinstance(x, conv2d_gradfix.PackedAct) else x.dtype
+    _, parts = conv2d_gradfix._PRODUCTS[conv2d_gradfix.precision_for(src_dtype)]
     dcoef = None
     if demodulate:
         conv2d_gradfix._init()
@@ -61,7 +64,7 @@ def modulated_conv2d_fused_act(x, weight, styles, noise=None, up=1, padding=0, r
         pw = conv2d_gradfix.packed_plain(weight, flip_weight, parts, padding, padding)
     return conv2d_gradfix.igemm_conv(x, pw, scale=styles, dcoef=dcoef, noise=noise, bias=bias, act=act, alpha=alpha,
                                      gain=gain, clamp=clamp, out=out, out_dtype=out_dtype, accumulate=accumulate,
-                                     memory_format=memory_format)
+                                     memory_format=memory_format, out_packed=out_packed)
 
 
 @misc.profiled_function

@@ -29,10 +29,20 @@ from ..torch_utils.ops import upfirdn2d
 from .networks import modulated_conv2d, modulated_conv2d_fused_act
 
 
+PackedAct = conv2d_gradfix.PackedAct
+PACKED_MIN_RES = 128    # blocks at this resolution and above hand activations over in operand format (no packing passes)
+
+
 def _can_fuse(x, *params):
+    if isinstance(x, PackedAct):
+        return True
     if not conv2d_gradfix._should_use_custom_op(x):
         return False
     return not (torch.is_grad_enabled() and any(p is not None and p.requires_grad for p in (x,) + params))
+
+
+def _parts():
+    return conv2d_gradfix._PRODUCTS[conv2d_gradfix.fp32_precision][1]
 
 
 class FullyConnectedLayer(torch.nn.Module):
@@ -70,15 +80,16 @@ class Conv2dLayer(torch.nn.Module):
         self.weight = torch.nn.Parameter(torch.randn([out_channels, in_channels, kernel_size, kernel_size]))
         self.bias = torch.nn.Parameter(torch.zeros([out_channels])) if bias else None
 
-    def forward(self, x, gain=1, fused=True, impl='cuda'):
+    def forward(self, x, gain=1, fused=True, impl='cuda', out_packed=None):
         act_gain = self.act_gain * gain
         act_clamp = self.conv_clamp * gain if self.conv_clamp is not None else None
         if fused and self.up == 1 and self.down == 1 and _can_fuse(x, self.weight, self.bias):
-            _, parts = conv2d_gradfix._PRODUCTS[conv2d_gradfix.precision_for(x.dtype)]
+            parts = _parts() if isinstance(x, PackedAct) else conv2d_gradfix._PRODUCTS[conv2d_gradfix.precision_for(x.dtype)][1]
             pw = conv2d_gradfix.packed_plain(self.weight, True, parts, self.padding, self.padding, scale=self.weight_gain)
             return conv2d_gradfix.igemm_conv(x, pw, bias=self.bias, act=self.activation,
                                              alpha=bias_act.activation_funcs[self.activation].def_alpha, gain=act_gain,
-                                             clamp=-1 if act_clamp is None else act_clamp)
+                                             clamp=-1 if act_clamp is None else act_clamp, out_packed=out_packed)
+        assert out_packed is None and not isinstance(x, PackedAct)
         w = self.weight * self.weight_gain
         b = self.bias.to(x.dtype) if self.bias is not None else None
         x = conv2d_resample.conv2d_resample(x=x, w=w.to(x.dtype), f=self.resample_filter, up=self.up, down=self.down,
@@ -105,7 +116,7 @@ class SynthesisLayer(torch.nn.Module):
             self.noise_strength = torch.nn.Parameter(torch.zeros([]))
         self.bias = torch.nn.Parameter(torch.zeros([out_channels]))
 
-    def forward(self, x, w, noise_mode='random', fused_modconv=True, gain=1, fused=True, impl='cuda'):
+    def forward(self, x, w, noise_mode='random', fused_modconv=True, gain=1, fused=True, impl='cuda', out_packed=None):
         assert noise_mode in ['random', 'const', 'none']
         styles = self.affine(w)
         noise = None
@@ -119,7 +130,8 @@ class SynthesisLayer(torch.nn.Module):
         if fused and _can_fuse(x, self.weight, self.bias, styles, noise):
             return modulated_conv2d_fused_act(x, self.weight, styles, noise=noise, up=self.up, padding=self.padding,
                                               resample_filter=self.resample_filter, flip_weight=flip_weight, bias=self.bias,
-                                              act=self.activation, gain=act_gain, clamp=act_clamp)
+                                              act=self.activation, gain=act_gain, clamp=act_clamp, out_packed=out_packed)
+        assert out_packed is None and not isinstance(x, PackedAct)
         x = modulated_conv2d(x=x, weight=self.weight, styles=styles, noise=noise, up=self.up, padding=self.padding,
                              resample_filter=self.resample_filter, flip_weight=flip_weight, fused_modconv=fused_modconv)
         return bias_act.bias_act(x, self.bias.to(x.dtype), act=self.activation, gain=act_gain, clamp=act_clamp, impl=impl)
@@ -156,6 +168,7 @@ class ToRGBLayer(torch.nn.Module):
                                            out=img, accumulate=img is not None, out_dtype=torch.float32,
                                            memory_format=torch.contiguous_format)
             return y, pred_parsing
+        assert not isinstance(x, PackedAct)
         y = modulated_conv2d(x=x, weight=self.weight, styles=styles, demodulate=False, fused_modconv=fused_modconv)
         y = bias_act.bias_act(y, self.bias.to(x.dtype), clamp=self.conv_clamp, impl=impl)
         y = y.to(dtype=torch.float32, memory_format=torch.contiguous_format)
@@ -187,13 +200,36 @@ class SynthesisBlock(torch.nn.Module):
             self.merge_conv = Conv2dLayer(out_channels + merge_channels, out_channels, kernel_size=1, resample_filter=resample_filter)
 
     def forward(self, x, img, ws, pose_feature=None, cat_feat=None, fused=True, impl='cuda', **layer_kwargs):
+        """x: previous block's feature map as a tensor or (from blocks >= PACKED_MIN_RES on the fused route) a PackedAct.
+        Returns (x, img, pred_parsing); x is a PackedAct when this block ran in operand-format hand-over mode."""
         w_iter = iter(ws.unbind(dim=1))
+        merge = hasattr(self, 'merge_conv') and cat_feat is not None
         if self.in_channels == 0:
             x = self.conv1(pose_feature.to(torch.float32), next(w_iter), fused=fused, impl=impl, **layer_kwargs)
+        elif fused and self.resolution >= PACKED_MIN_RES and _can_fuse(x, self.conv0.weight, self.conv1.weight) and \
+                self.conv1.weight.shape[0] % 16 == 0:
+            # operand-format hand-over: conv epilogues write bf16 (split) channels-innermost buffers that the next conv's
+            # TMA reads directly; the garment features are packed next to conv1's output so the concat disappears
+            n, res, oc, parts = ws.shape[0], self.resolution, self.conv1.weight.shape[0], _parts()
+            dev = ws.device
+            xa = PackedAct(PackedAct.empty(n, res, res, oc, parts, dev), oc)
+            self.conv0(x, next(w_iter), fused=True, out_packed=xa, **layer_kwargs)
+            if merge:
+                cf = cat_feat[str(res)]
+                mc = cf.shape[1]
+                buf = PackedAct.empty(n, res, res, oc + mc, parts, dev)
+                conv2d_gradfix._init()
+                conv2d_gradfix._plugin.pack_activations_into(cf, None, buf, mc, oc)
+                self.conv1(xa, next(w_iter), fused=True, out_packed=PackedAct(buf, oc, 0), **layer_kwargs)
+                x = PackedAct(PackedAct.empty(n, res, res, oc, parts, dev), oc)
+                self.merge_conv(PackedAct(buf, oc + mc, 0), fused=True, out_packed=x)
+            else:
+                x = PackedAct(PackedAct.empty(n, res, res, oc, parts, dev), oc)
+                self.conv1(xa, next(w_iter), fused=True, out_packed=x, **layer_kwargs)
         else:
             x = self.conv0(x, next(w_iter), fused=fused, impl=impl, **layer_kwargs)
             x = self.conv1(x, next(w_iter), fused=fused, impl=impl, **layer_kwargs)
-            if hasattr(self, 'merge_conv') and cat_feat is not None:
+            if merge:
                 x = torch.cat([x, cat_feat[str(x.shape[2])].to(x.dtype)], dim=1)
                 x = self.merge_conv(x, fused=fused, impl=impl)
         if img is not None:

@@ -66,3 +66,50 @@ def test_full_size_512_chain_batch1_against_cpu_oracle():
         # end-to-end over ~15 chained layers (each <= 1e-4 per layer, tests/test_gpu_c_conv.py); measured ~7e-5..1e-4
         assert rel_l2(g, w) < 3e-4, (name, rel_l2(g, w))
         assert max_abs(g, w) <= 1e-3 * max(1.0, float(w.abs().max())), (name, max_abs(g, w), float(w.abs().max()))
+
+
+@pytest.mark.parametrize('prec,tol', [('bf16x3', 5e-5), ('bf16x2', 1e-4), ('bf16', 3e-2)])
+def test_operand_format_handover_route_small(prec, tol):
+    """blocks >= PACKED_MIN_RES exchange bf16-split channels-innermost buffers (no packing pass, no concat, per-sample
+    modulated weights); forced on at 32 px here so the small oracle-checkable net exercises it"""
+    old, old_min = cg.fp32_precision, synthesis.PACKED_MIN_RES
+    cg.fp32_precision = prec
+    synthesis.PACKED_MIN_RES = 32
+    try:
+        net = _net(w_dim=64, img_resolution=128, channel_base=4096, channel_max=48, merge_channels=16)
+        n = 3
+        ws = torch.randn(n, net.num_ws, 64); pose = torch.randn(n, net.channels[8], 8, 8)
+        cat = {'64': torch.randn(n, 16, 64, 64), '128': torch.randn(n, 16, 128, 128)}
+        sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
+        want = ref_chain.synthesis_chain(sd, ws, pose, cat, img_resolution=128)
+        net = net.to(DEV)
+        with torch.no_grad():
+            got = net(ws.to(DEV), pose.to(DEV), {k: v.to(DEV) for k, v in cat.items()}, fused=True, noise_mode='const')
+        for g, w, name in zip(got, want, ('img', 'parsing', 'texture')):
+            assert rel_l2(g, w) < tol, (prec, name, rel_l2(g, w))
+    finally:
+        cg.fp32_precision, synthesis.PACKED_MIN_RES = old, old_min
+
+
+def test_packed_activation_roundtrip_and_per_sample_weights():
+    """one conv writing the operand format, a second one consuming it with style-modulated per-sample weights"""
+    nets = importlib.import_module('pgpp_b200.training.networks')
+    from oracle import ref_ops
+    old = cg.fp32_precision
+    cg.fp32_precision = 'bf16x3'
+    try:
+        g = torch.Generator().manual_seed(41)
+        x = torch.randn(3, 32, 24, 20, generator=g); w1 = torch.randn(48, 32, 3, 3, generator=g) / 17
+        w2 = torch.randn(32, 48, 3, 3, generator=g); s1 = torch.rand(3, 32, generator=g) + 0.5; s2 = torch.rand(3, 48, generator=g) + 0.5
+        b1 = torch.randn(48, generator=g)
+        y1 = ref_ops.synthesis_layer(x, s1, w1, b1, None, 1, None)
+        y2 = ref_ops.modulated_conv2d(y1, w2, s2, padding=1)
+        buf = cg.PackedAct(cg.PackedAct.empty(3, 24, 20, 64, 3, DEV), 48, 16)       # channels [16, 64) of a wider buffer
+        with torch.no_grad():
+            nets.modulated_conv2d_fused_act(x.to(DEV), w1.to(DEV), s1.to(DEV), padding=1, bias=b1.to(DEV), act='lrelu', clamp=256.0,
+                                            out_packed=buf)
+            assert rel_l2(buf.to_nchw(), y1) < 2e-5
+            got = nets.modulated_conv2d_fused_act(buf, w2.to(DEV), s2.to(DEV), padding=1)
+        assert got.dtype == torch.float32 and rel_l2(got, y2) < 4e-5
+    finally:
+        cg.fp32_precision = old
