@@ -259,7 +259,7 @@ __device__ __forceinline__ void epilogue_general(const IgemmParams& p, const Til
 }
 
 // Fast epilogue: one sample per tile, per-column (scale, shift) staged in shared memory with the gain already folded in
-// (linear / relu / lrelu are positively homogeneous), no accumulate.
+// (linear / relu / lrelu are positively homogeneous).
 template <int A, class OT, bool CLAMP>
 __device__ __forceinline__ void epilogue_fast(const IgemmParams& p, const TileCoord tc, uint32_t tmem_tile, const PixelCoord pc,
                                               int col_begin, int col_end, const float2* s_cs) {
@@ -290,7 +290,13 @@ __device__ __forceinline__ void epilogue_fast(const IgemmParams& p, const TileCo
             if (CLAMP) r = fminf(fmaxf(r, -clamp), clamp);
             v[j] = r;
         }
-        if (nhwc && valid == 16 && ((base + oc0) * sizeof(OT)) % 16 == 0 && ((uintptr_t)out & 15) == 0) {
+        if (p.accumulate) {
+            // out += result (ToRGB adding into the up-sampled skip image): read-modify-write, lanes are consecutive pixels
+            OT* dst = out + base + (long long)oc0 * p.os_c;
+            #pragma unroll
+            for (int j = 0; j < 16; j++)
+                if (j < valid) dst[(unsigned)j * cs] = cvt_out<OT>(v[j] + cvt_in<OT>(dst[(unsigned)j * cs]));
+        } else if (nhwc && valid == 16 && ((base + oc0) * sizeof(OT)) % 16 == 0 && ((uintptr_t)out & 15) == 0) {
             // channels-innermost output: 16 consecutive channels of one pixel, 128-bit stores; with out_parts > 1 the
             // bf16 expansion of the value is written (part q = bf16(v - earlier parts)): the next conv's operand format
             for (int part = 0; part < p.out_parts; part++) {
@@ -563,7 +569,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
         const int cols_per = p.block_n >= 32 ? p.block_n / 2 : p.block_n;
         const int col_begin = half * cols_per;
         const int col_end = (p.block_n >= 32 || half == 0) ? col_begin + cols_per : col_begin;
-        const bool fast = p.tn == 1 && !p.accumulate && p.fold_gain;
+        const bool fast = p.tn == 1 && p.fold_gain;
         int buf = 0; uint32_t buf_phase = 0;
         int tag0 = -1, tag1 = -1;                           // (sample, column tile) whose parameters each staging buffer holds
         for (long long t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
