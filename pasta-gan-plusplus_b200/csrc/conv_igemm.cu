@@ -365,7 +365,7 @@ struct MmaCtx { uint32_t smem_base, b_base, bar_base, tmem_base; };
 // one elected lane issues tcgen05.mma / tcgen05.commit.  PARTS / INNER / KS > 0 are compile-time copies of p.parts /
 // p.inner / (kb / 16) for the common configurations (fully unrolled product / tap / K-step loops, a handful of
 // instructions per MMA); <0, 0, 0> is the generic runtime-bounds version.
-template <int PARTS, int INNER, int KS>
+template <int PARTS, int INNER, int KS, bool RES>
 __device__ __forceinline__ void mma_role(const IgemmParams& p, const MmaCtx mc) {
     const int SA = p.a_stages, SB = p.b_stages;
     auto afull_bar = [&](int s) { return mc.bar_base + 8u * s; };
@@ -388,11 +388,12 @@ __device__ __forceinline__ void mma_role(const IgemmParams& p, const MmaCtx mc) 
     int last_n = -1; uint32_t res_phase = 0;
     for (long long t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
         // resident weights: wait for the (re)load on the first tile and whenever the sample changed (per-sample weights)
-        bool res_wait = false;
-        if (p.b_resident) {
+        if (RES) {
             const int n0 = p.wgt_per_sample ? decode_tile(p, t).n0 : 0;
-            res_wait = first_tile || n0 != last_n;
-            if (res_wait && !first_tile) res_phase ^= 1;
+            if (first_tile || n0 != last_n) {
+                if (!first_tile) res_phase ^= 1;
+                for (int sl = 0; sl < SB; sl++) mbar_wait(bfull_bar(sl), res_phase);    // all resident weight tiles have landed
+            }
             last_n = n0;
         }
         mbar_wait(tempty_bar(buf), buf_phase ^ 1);      // epilogue has drained this accumulator
@@ -412,8 +413,7 @@ __device__ __forceinline__ void mma_role(const IgemmParams& p, const MmaCtx mc) 
                     for (int pb = 0; pb < (PARTS ? PARTS : 3); pb++) {
                         if (pb >= parts) break;
                         uint32_t b16;
-                        if (p.b_resident) {
-                            if (res_wait) { mbar_wait(bfull_bar((int)((b_res16 - (mc.b_base >> 4)) / bpitch16)), res_phase); tc_fence_after(); }
+                        if (RES) {
                             b16 = b_res16;
                             b_res16 += bpitch16;
                         } else {
@@ -440,7 +440,7 @@ __device__ __forceinline__ void mma_role(const IgemmParams& p, const MmaCtx mc) 
                             }
                             acc = 1;
                         }
-                        if (!p.b_resident) {
+                        if (!RES) {
                             if (leader) umma_commit(bempty_bar(sb));        // weight slot reusable once these MMAs retire
                             if (++sb == SB) { sb = 0; phb ^= 1; }
                         }
@@ -473,7 +473,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
     auto tfull_bar = [&](int b) { return bar_base + 8u * (2 * SA + 2 * SB + b); };
     auto tempty_bar = [&](int b) { return bar_base + 8u * (2 * SA + 2 * SB + 2 + b); };
     const uint32_t tmem_slot = bar_base + 8u * (2 * SA + 2 * SB + 4);
-    // per-column epilogue parameters (scale, shift), double-buffered with the accumulator: float2 [2][256]
+    // per-column epilogue parameters (scale, shift), double-buffered with the accumulator: float2 [2][block_n]
     float2* const s_params = reinterpret_cast<float2*>(smem_raw + (tmem_slot + 16u - smem_u32(smem_raw)));
 
     const int warp = threadIdx.x >> 5;
@@ -512,7 +512,22 @@ igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
                 if (load_res && k_tile > 0)     // every MMA of the previous tile must have read the old weights
                     mbar_wait(tfull_bar((k_tile - 1) & 1), (uint32_t)((k_tile - 1) >> 1) & 1u);
                 last_n = tc.n0;
-                int b_slot = 0;
+                if (load_res) {
+                    // all resident weight tiles first (the MMA warp waits for the whole set before touching the activation
+                    // ring, so they must not be queued behind activation stages it has not released yet)
+                    int b_slot = 0;
+                    for (int g = 0; g < p.n_groups; g++) {
+                        const int ky0 = p.reuse ? 0 : g / p.kw;
+                        const int kx = p.reuse ? g : g - ky0 * p.kw;
+                        for (int cb = 0; cb < p.num_cb; cb++)
+                            for (int j = 0; j < p.inner; j++)
+                                for (int pb = 0; pb < p.parts; pb++, b_slot++) {
+                                    mbar_expect_tx(bfull_bar(b_slot), p.b_bytes);
+                                    tma_load_4d(b_base + b_slot * p.b_pitch, &map_b, bfull_bar(b_slot), cb * p.kb,
+                                                ((ky0 + j) * p.kw + kx) * p.o_rows + tc.col0, pb, wn);
+                                }
+                    }
+                }
                 for (int g = 0; g < p.n_groups; g++) {
                     // reuse: group = kx, the slab spans all ky;  no reuse: group = tap
                     const int ky0 = p.reuse ? 0 : g / p.kw;
@@ -525,21 +540,14 @@ igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
                         for (int pa = 0; pa < p.parts; pa++)
                             tma_load_5d(smem_base + sa * p.a_stage_bytes + pa * p.slab_bytes, &map_a, afull_bar(sa), cb * p.kb, ix, iy, tc.n0, pa);
                         if (++sa == SA) { sa = 0; pha ^= 1; }
+                        if (p.b_resident) continue;
                         for (int j = 0; j < p.inner; j++) {
                             const int tap = (ky0 + j) * p.kw + kx;
                             for (int pb = 0; pb < p.parts; pb++) {
-                                if (p.b_resident) {
-                                    if (load_res) {
-                                        mbar_expect_tx(bfull_bar(b_slot), p.b_bytes);
-                                        tma_load_4d(b_base + b_slot * p.b_pitch, &map_b, bfull_bar(b_slot), cb * p.kb, tap * p.o_rows + tc.col0, pb, wn);
-                                    }
-                                    b_slot++;
-                                } else {
-                                    mbar_wait(bempty_bar(sb), phb ^ 1);
-                                    mbar_expect_tx(bfull_bar(sb), p.b_bytes);
-                                    tma_load_4d(b_base + sb * p.b_pitch, &map_b, bfull_bar(sb), cb * p.kb, tap * p.o_rows + tc.col0, pb, wn);
-                                    if (++sb == SB) { sb = 0; phb ^= 1; }
-                                }
+                                mbar_wait(bempty_bar(sb), phb ^ 1);
+                                mbar_expect_tx(bfull_bar(sb), p.b_bytes);
+                                tma_load_4d(b_base + sb * p.b_pitch, &map_b, bfull_bar(sb), cb * p.kb, tap * p.o_rows + tc.col0, pb, wn);
+                                if (++sb == SB) { sb = 0; phb ^= 1; }
                             }
                         }
                     }
@@ -550,12 +558,14 @@ igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
         // ===================== MMA issuer =====================
         const MmaCtx mc{smem_base, b_base, bar_base, tmem_base};
         const int ks = p.kb == 64 ? 4 : 0;
-        if (ks == 4 && p.inner == 3 && p.parts == 1) mma_role<1, 3, 4>(p, mc);
-        else if (ks == 4 && p.inner == 3 && p.parts == 2) mma_role<2, 3, 4>(p, mc);
-        else if (ks == 4 && p.inner == 3 && p.parts == 3) mma_role<3, 3, 4>(p, mc);
-        else if (ks == 4 && p.inner == 1 && p.parts == 1) mma_role<1, 1, 4>(p, mc);
-        else if (ks == 4 && p.inner == 1 && p.parts == 2) mma_role<2, 1, 4>(p, mc);
-        else mma_role<0, 0, 0>(p, mc);
+        const bool res = p.b_resident != 0;
+        if (ks == 4 && p.inner == 3 && p.parts == 1) { if (res) mma_role<1, 3, 4, true>(p, mc); else mma_role<1, 3, 4, false>(p, mc); }
+        else if (ks == 4 && p.inner == 3 && p.parts == 2) { if (res) mma_role<2, 3, 4, true>(p, mc); else mma_role<2, 3, 4, false>(p, mc); }
+        else if (ks == 4 && p.inner == 3 && p.parts == 3) mma_role<3, 3, 4, false>(p, mc);
+        else if (ks == 4 && p.inner == 1 && p.parts == 1) { if (res) mma_role<1, 1, 4, true>(p, mc); else mma_role<1, 1, 4, false>(p, mc); }
+        else if (ks == 4 && p.inner == 1 && p.parts == 2) { if (res) mma_role<2, 1, 4, true>(p, mc); else mma_role<2, 1, 4, false>(p, mc); }
+        else if (res) mma_role<0, 0, 0, true>(p, mc);
+        else mma_role<0, 0, 0, false>(p, mc);
     } else {
         // ===================== epilogue warps =====================
         const int quarter = warp & 3;                       // TMEM lane quarter this warp may access
@@ -574,7 +584,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
         int tag0 = -1, tag1 = -1;                           // (sample, column tile) whose parameters each staging buffer holds
         for (long long t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
             const TileCoord tc = decode_tile(p, t);
-            float2* s_cs = s_params + buf * 256;
+            float2* s_cs = s_params + buf * p.block_n;
             if (fast) {
                 const int tag = tc.n0 * p.tiles_col + tc.col0 / p.block_n;
                 if ((buf ? tag1 : tag0) != tag) {
@@ -719,7 +729,7 @@ extern "C" int pgpp_conv2d_igemm(const pgpp_conv_desc* d, void* stream) {
     // shared-memory plan (227 KB per CTA): weights resident if every tile of a column tile fits beside a 2-deep
     // activation ring, otherwise a weight ring of up to 8 slots and 2..4 activation stages
     auto smem_need = [&](long long a_st, long long b_st) -> long long {
-        return 1024 + a_st * p.a_stage_bytes + b_st * p.b_pitch + 8 * (2 * a_st + 2 * b_st + 4) + 16 + 16 + 4096;
+        return 1024 + a_st * p.a_stage_bytes + b_st * p.b_pitch + 8 * (2 * a_st + 2 * b_st + 4) + 16 + 16 + 16ll * p.block_n;
     };
     const long long smem_max = 227 * 1024;
     const long long n_btiles = (long long)p.n_groups * p.num_cb * p.inner * p.parts;
