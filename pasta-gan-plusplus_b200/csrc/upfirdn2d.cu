@@ -185,11 +185,110 @@ __global__ void __launch_bounds__(256) fir_tile_kernel(UpfirdnArgs p, int tiles_
     }
 }
 
+// up = 1, down = 2 in both axes, fw, fh <= 4, unit stride along W: 64 x 16 output tile from a 132 x 35 input halo tile
+// (the FIR-downsampling of the 1x1-skip and encoder paths, conv2d_resample.py:107-110).  Each thread produces 4
+// consecutive outputs of one row: 10 inputs per filter row through two 128-bit and one 64-bit shared load.
+constexpr int D2_TILE_W = 64, D2_TILE_H = 16;
+constexpr int D2_SM_W = 2 * D2_TILE_W + 4, D2_SM_H = 2 * D2_TILE_H + 3;
+
+template <class T>
+__global__ void __launch_bounds__(256) fir_down2_kernel(UpfirdnArgs p, int tiles_x, int tiles_y, long long total_tiles) {
+    typedef float S;
+    __shared__ __align__(16) S sx[D2_SM_H][D2_SM_W];
+    S k[4][4];
+    #pragma unroll
+    for (int jy = 0; jy < 4; jy++)
+        #pragma unroll
+        for (int jx = 0; jx < 4; jx++) {
+            S v = 0;
+            if (jy < p.fh && jx < p.fw) {
+                const int sy = p.flip ? jy : p.fh - 1 - jy, sxx = p.flip ? jx : p.fw - 1 - jx;
+                v = p.f[sy * p.fs_y + sxx * p.fs_x] * p.gain;
+            }
+            k[jy][jx] = v;
+        }
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;      // 16 x 16 threads, 4 x 1 outputs each
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const T* x = (const T*)p.x;
+    T* y = (T*)p.y;
+    const bool vec_store = (sizeof(T) == 4) && ((p.ys_h & 3) == 0) && ((p.ys_c & 3) == 0) && ((p.ys_n & 3) == 0) &&
+                           (((uintptr_t)p.y & 15) == 0);
+    for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const int bx = (int)(t % tiles_x);
+        long long r = t / tiles_x;
+        const int by = (int)(r % tiles_y); r /= tiles_y;
+        const int c = (int)(r % p.c);
+        const int n = (int)(r / p.c);
+        const int ox0 = bx * D2_TILE_W, oy0 = by * D2_TILE_H;
+        const int ix0 = ox0 * 2 - p.padx0, iy0 = oy0 * 2 - p.pady0;
+        const T* xp = x + n * p.xs_n + c * p.xs_c;
+        __syncthreads();
+        {
+            constexpr int ROWS = (D2_SM_H + 7) / 8, COLS = (D2_SM_W + 31) / 32;
+            S v[ROWS][COLS];
+            #pragma unroll
+            for (int rr = 0; rr < ROWS; rr++) {
+                const int ry = warp + 8 * rr;
+                const int iy = iy0 + ry;
+                const bool row_ok = ry < D2_SM_H && iy >= 0 && iy < p.ih;
+                const T* row = xp + (long long)iy * p.xs_h + ix0;
+                #pragma unroll
+                for (int kk = 0; kk < COLS; kk++) {
+                    const int rx = lane + 32 * kk;
+                    const int ix = ix0 + rx;
+                    v[rr][kk] = (row_ok && ix >= 0 && ix < p.iw) ? to_acc<T>(__ldg(row + rx)) : (S)0;
+                }
+            }
+            #pragma unroll
+            for (int rr = 0; rr < ROWS; rr++) {
+                const int ry = warp + 8 * rr;
+                #pragma unroll
+                for (int kk = 0; kk < COLS; kk++) {
+                    const int rx = lane + 32 * kk;
+                    if (ry < D2_SM_H && rx < D2_SM_W) sx[ry][rx] = v[rr][kk];
+                }
+            }
+        }
+        __syncthreads();
+        S acc[4] = {0, 0, 0, 0};
+        #pragma unroll
+        for (int jy = 0; jy < 4; jy++) {
+            const S* rowp = &sx[2 * ty + jy][8 * tx];
+            const float4 a = *reinterpret_cast<const float4*>(rowp);
+            const float4 b = *reinterpret_cast<const float4*>(rowp + 4);
+            const float2 cc = *reinterpret_cast<const float2*>(rowp + 8);
+            const S in[10] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, cc.x, cc.y};
+            #pragma unroll
+            for (int o = 0; o < 4; o++)
+                #pragma unroll
+                for (int jx = 0; jx < 4; jx++) acc[o] = fmaf(in[2 * o + jx], k[jy][jx], acc[o]);
+        }
+        const int oy = oy0 + ty, ox = ox0 + 4 * tx;
+        if (oy < p.oh && ox < p.ow) {
+            T* dst = y + n * p.ys_n + c * p.ys_c + (long long)oy * p.ys_h + ox;
+            if (vec_store && ox + 3 < p.ow) __stcs(reinterpret_cast<float4*>(dst), make_float4(acc[0], acc[1], acc[2], acc[3]));
+            else {
+                #pragma unroll
+                for (int o = 0; o < 4; o++) if (ox + o < p.ow) dst[o] = from_acc<T>(acc[o]);
+            }
+        }
+    }
+}
+
 template <class T>
 static int launch_upfirdn(const UpfirdnArgs& p, cudaStream_t stream) {
     const bool tile_ok = p.upx == 1 && p.upy == 1 && p.downx == 1 && p.downy == 1 && p.fw <= 4 && p.fh <= 4 &&
                          p.xs_w == 1 && p.ys_w == 1 && sizeof(T) <= 4;
-    if (tile_ok) {
+    const bool down2_ok = p.upx == 1 && p.upy == 1 && p.downx == 2 && p.downy == 2 && p.fw <= 4 && p.fh <= 4 &&
+                          p.xs_w == 1 && p.ys_w == 1 && sizeof(T) <= 4;
+    if (down2_ok) {
+        const int tiles_x = (p.ow + D2_TILE_W - 1) / D2_TILE_W, tiles_y = (p.oh + D2_TILE_H - 1) / D2_TILE_H;
+        const long long total = (long long)tiles_x * tiles_y * p.c * p.n;
+        long long blocks = total;
+        const long long cap = (long long)sm_count() * occupancy_of(fir_down2_kernel<T>, 256, 0);
+        if (blocks > cap) blocks = cap;
+        fir_down2_kernel<T><<<(unsigned)blocks, 256, 0, stream>>>(p, tiles_x, tiles_y, total);
+    } else if (tile_ok) {
         const int tiles_x = (p.ow + TILE_W - 1) / TILE_W, tiles_y = (p.oh + TILE_H - 1) / TILE_H;
         const long long total = (long long)tiles_x * tiles_y * p.c * p.n;
         long long blocks = total;
