@@ -1,17 +1,18 @@
-"""Benchmark of the StyleGAN2 synthesis hot path of the PASTA-GAN++ 512 px generator (BASELINE.json configs[1]).
+"""Benchmark of the PASTA-GAN++ 512 px generator on this repo's sm_100a kernels (BASELINE.json configs[1]).
 
-    python bench.py --gpus 1 --steps 10 --warmup 3                 # this repo's sm_100a kernels
+    python bench.py --gpus 1 --steps 10 --warmup 3                 # this repo's kernels, full generator, batch 32 per GPU
     python bench.py --impl reference --steps 3 --warmup 1          # the CPU ref path (oracle port) on the host cores
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port P bench.py --gpus 8 ...
+    python bench.py --workload chain                               # only the modulated-conv synthesis chain (round-1 early workload)
 
-One "step" = one batch (default 32 images per GPU) through the synthesis chain of the 512 px generator: the 24
-modulated_conv2d calls of SURVEY Appendix A with their bias_act epilogues, the 5 merge 1x1 convolutions, the 6 image-skip
-upfirdn2d up-samplings and the ToRGB accumulations (pgpp_b200.training.synthesis.SynthesisChain).  The SPADE refinement
-blocks and the encoders of the full generator are outside this round's scope and are NOT in the step; the
-metric is therefore named `synthesis_hot_path_images_per_sec`, not generator images/s.
+One "step" = one batch (default 32 images per GPU) through `GeneratorFull_v20.forward` (pgpp_b200.training.generator, same
+state-dict as the reference): const / style encoders, mapping, synthesis blocks b8..b512, SPADE blocks and the texture branch --
+per image 24 modulated_conv2d + 76 plain convolutions (all on the tcgen05 implicit-GEMM kernel), the FIR resamplers and the
+bias_act calls; instance norm / nearest resize / masks / per-pixel Linear stay PyTorch library ops as in the reference.
 
-Prints ONE JSON line (rank 0).  `value` is device-resident throughput over all GPUs; `e2e` goes through the public
-pipeline API with pinned-host inputs and the image read back to the host inside the timed region.
+Prints ONE JSON line (rank 0).  `value` is device-resident throughput over all GPUs in the fp32-parity mode (bf16x2 split
+MMAs); `e2e` goes through the pipeline API with uint8 pinned-host inputs and the try-on image read back to the host inside the
+timed region; `bf16_mode` reports the single-product bf16 mode separately; `roofline` describes the dominant kernel launch.
 """
 import argparse
 import importlib
@@ -45,6 +46,63 @@ def build_chain(device, resolution=RES):
         if name.endswith('noise_strength'):
             p.data.fill_(0.1)
     return net.to(device).requires_grad_(False)
+
+
+def build_generator(device):
+    """GeneratorFull_v20 with the reference's configuration, name-seeded random weights (same recipe as the golden fixture)"""
+    from __graft_entry__ import load_pkg
+    load_pkg()
+    gen = importlib.import_module('pgpp_b200.training.generator')
+    G = gen.build_generator().eval()
+    import zlib
+    with torch.no_grad():
+        for name, t in list(G.named_parameters()) + list(G.named_buffers()):
+            if not torch.is_floating_point(t) or name.endswith('resample_filter') or name.endswith('w_avg'):
+                continue
+            g = torch.Generator().manual_seed(zlib.crc32(name.encode()) & 0x7FFFFFFF)
+            v = torch.randn(t.shape, generator=g)
+            if name.endswith('noise_strength'):
+                v = torch.full(t.shape, 0.1)
+            elif name.endswith('affine.bias'):
+                v = 1.0 + 0.1 * v
+            elif name.endswith('bias') or name.endswith('m_bias1'):
+                v = 0.1 * v
+            elif name.endswith('linear.weight'):
+                v = v / (t.shape[1] ** 0.5)
+            elif name.startswith('mapping.fc'):
+                v = v * 100.0
+            t.copy_(v)
+    return G.to(device).requires_grad_(False)
+
+
+def make_generator_inputs_u8(batch, seed):
+    """synthetic 512x320 try-on inputs as the dataset delivers them: uint8 host tensors (test.py:126-147 converts on the GPU).
+    Signal in columns 96..415, constant side bands."""
+    g = torch.Generator().manual_seed(seed)
+    band = torch.zeros(1, 1, 1, 512, dtype=torch.bool); band[..., 96:416] = True
+
+    def img(ch, fill):
+        t = torch.randint(0, 256, (batch, ch, 512, 512), generator=g, dtype=torch.uint8)
+        return torch.where(band, t, torch.full_like(t, fill))
+    return dict(c=torch.randint(0, 256, (batch, 45, 128, 128), generator=g, dtype=torch.uint8),
+                retain=img(6, 255), pose=img(5, 0), denorm_upper=img(3, 255), denorm_lower=img(3, 255),
+                denorm_upper_mask=(torch.rand(batch, 1, 512, 512, generator=g) > 0.5).to(torch.uint8) * band,
+                denorm_lower_mask=(torch.rand(batch, 1, 512, 512, generator=g) > 0.5).to(torch.uint8) * band)
+
+
+def to_device_f32(u8, device):
+    """H2D of the uint8 batch + the /127.5 - 1 conversion of test.py:126-147 on the device"""
+    out = {}
+    for k, v in u8.items():
+        d = v.to(device, non_blocking=True)
+        out[k] = d.to(torch.float32) if k.endswith('mask') else d.to(torch.float32).div_(127.5).sub_(1.0)
+    return out
+
+
+def run_generator(G, x, gt_parsing=None):
+    with torch.no_grad():
+        return G(torch.zeros(x['c'].shape[0], 0, device=x['c'].device), x['c'], x['retain'], x['pose'], x['denorm_upper'], x['denorm_lower'],
+                 x['denorm_upper_mask'], x['denorm_lower_mask'], gt_parsing=gt_parsing, noise_mode='const')
 
 
 def make_inputs(net, batch, seed, device='cpu', pin=False):
@@ -137,29 +195,56 @@ def cpu_reference_rate(net_sd, num_ws, c8, batch, reps, threads=None):
     return batch / min(times), times
 
 
+GEN_DESC = ('PASTA-GAN++ GeneratorFull_v20 512px inference (train.py:191-202 config, 43.1 M params, random weights): encoders + mapping + '
+            'synthesis b8..b512 + SPADE blocks + texture branch = 24 modulated_conv2d + 76 plain convs + upfirdn2d + bias_act per image')
+CHAIN_DESC = ('PASTA-GAN++ 512px generator synthesis chain only: 24 modulated_conv2d (+bias_act, noise, ToRGB accumulate), 5 merge 1x1 convs, '
+              '6 image-skip upfirdn2d; SPADE blocks/encoders not included')
+
+
+def generator_cpu_rate(reps, threads):
+    """images/s of the full generator on the CPU ref path (oracle/ref_generator.py over torch CPU ops), batch 1 per rep"""
+    from oracle import ref_generator
+    torch.set_num_threads(threads)
+    G = build_generator('cpu')
+    sd = {k: v.detach() for k, v in G.state_dict().items()}
+    inp = ref_generator.synthetic_inputs(1, seed=3)
+    times = []
+    with torch.no_grad():
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            ref_generator.generator(sd, inp['c'], inp['retain'], inp['pose'], inp['denorm_upper'], inp['denorm_lower'],
+                                    inp['denorm_upper_mask'], inp['denorm_lower_mask'], None)
+            times.append(time.perf_counter() - t0)
+    return times
+
+
 def run_reference(args):
     rank = int(os.environ.get('RANK', 0))
     if rank != 0:
         return
-    net = build_chain('cpu')
-    sd = {k: v.detach() for k, v in net.state_dict().items()}
-    torch.set_num_threads(host_threads())
-    cores = torch.get_num_threads()
+    cores = host_threads()
+    torch.set_num_threads(cores)
     batch = 1
-    for _ in range(args.warmup):
-        cpu_reference_rate(sd, net.num_ws, net.channels[8], batch, 1)
-    t0 = time.perf_counter()
-    rate, times = cpu_reference_rate(sd, net.num_ws, net.channels[8], batch, args.steps)
-    total = time.perf_counter() - t0
+    if args.workload == 'generator':
+        if args.warmup:
+            generator_cpu_rate(1, cores)
+        times = generator_cpu_rate(args.steps, cores)
+        metric, desc, src = 'generator_512px_images_per_sec', GEN_DESC, 'oracle/ref_generator.py'
+    else:
+        net = build_chain('cpu')
+        sd = {k: v.detach() for k, v in net.state_dict().items()}
+        for _ in range(args.warmup):
+            cpu_reference_rate(sd, net.num_ws, net.channels[8], batch, 1)
+        _, times = cpu_reference_rate(sd, net.num_ws, net.channels[8], batch, args.steps)
+        metric, desc, src = 'synthesis_hot_path_images_per_sec', CHAIN_DESC, 'oracle/ref_chain.py'
     value = batch * args.steps / sum(times)
     line = {
-        'impl': 'reference', 'metric': 'synthesis_hot_path_images_per_sec', 'value': value, 'unit': 'images/s', 'n_gpus': args.gpus,
+        'impl': 'reference', 'metric': metric, 'value': value, 'unit': 'images/s', 'n_gpus': args.gpus,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * sum(times) / args.steps, 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': 'PASTA-GAN++ 512px generator synthesis chain (24 modulated_conv2d + bias_act + upfirdn2d + merge convs), '
-                               'CPU ref path, bounded sample of batch 1 per step', 'resolution': RES},
+        'config': {'workload': desc + '; CPU ref path, bounded sample of batch 1 per step', 'resolution': RES},
         'cpu_baseline': {'value': value, 'unit': 'images/s', 'cores': cores, 'kind': 'port',
-                         'sample': f'{args.steps} steps of batch {batch} through oracle/ref_chain.py (torch CPU ops, {cores} threads)'},
+                         'sample': f'{args.steps} steps of batch {batch} through {src} (torch CPU ops, {cores} threads)'},
         'e2e': {'value': value, 'unit': 'images/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
     }
     print(json.dumps(line), flush=True)
@@ -205,6 +290,41 @@ class SynthesisPipeline:
         return None
 
 
+class GeneratorPipeline:
+    """End-to-end call for the full generator: uint8 pinned-host try-on inputs -> device (+ /127.5-1 conversion, test.py:126-147)
+    -> GeneratorFull_v20 -> fp32 try-on image back in pinned host memory (test.py:162).  Read-back of batch i overlaps compute of i+1."""
+
+    def __init__(self, G, batch, device):
+        self.G, self.device = G, device
+        self.copy_stream = torch.cuda.Stream(device)
+        self.out_host = [torch.empty(batch, 3, RES, RES, dtype=torch.float32).pin_memory() for _ in range(2)]
+        self.slot, self.pending = 0, None
+
+    def __call__(self, host_u8):
+        cur = torch.cuda.current_stream(self.device)
+        x = to_device_f32(host_u8, self.device)
+        _, finetune, _ = run_generator(self.G, x)
+        done = torch.cuda.Event(); done.record(cur)
+        self.copy_stream.wait_event(done)
+        with torch.cuda.stream(self.copy_stream):
+            host = self.out_host[self.slot]
+            host.copy_(finetune, non_blocking=True)
+            finetune.record_stream(self.copy_stream)
+            ev = torch.cuda.Event(); ev.record(self.copy_stream)
+        prev, self.pending = self.pending, (ev, host)
+        self.slot ^= 1
+        if prev is not None:
+            prev[0].synchronize()
+        return prev[1] if prev is not None else None
+
+    def flush(self):
+        if self.pending is not None:
+            self.pending[0].synchronize()
+            host, self.pending = self.pending[1], None
+            return host
+        return None
+
+
 def run_ours(args):
     rank = int(os.environ.get('RANK', 0)); world = int(os.environ.get('WORLD_SIZE', 1)); local = int(os.environ.get('LOCAL_RANK', 0))
     assert torch.cuda.is_available(), 'bench.py needs a GPU (there is no CPU fallback; use --impl reference for the CPU ref path)'
@@ -222,20 +342,29 @@ def run_ours(args):
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
 
-    net = build_chain(device)
     batch = args.batch
-    cat = make_cat_feats(net, batch, device)
-    ws_h, pose_h = make_inputs(net, batch, 100 + rank, pin=True)
-    ws_d, pose_d = ws_h.to(device), pose_h.to(device)
+    gen_mode = args.workload == 'generator'
+    if gen_mode:
+        net = build_generator(device)
+        host_u8 = {k: v.pin_memory() for k, v in make_generator_inputs_u8(batch, 100 + rank).items()}
+        dev_in = to_device_f32(host_u8, device)
+
+        def step():
+            return run_generator(net, dev_in)
+    else:
+        net = build_chain(device)
+        cat = make_cat_feats(net, batch, device)
+        ws_h, pose_h = make_inputs(net, batch, 100 + rank, pin=True)
+        ws_d, pose_d = ws_h.to(device), pose_h.to(device)
+
+        def step():
+            with torch.no_grad():
+                return net(ws_d, pose_d, cat, noise_mode='const')
 
     def barrier():
         if world > 1:
             torch.distributed.barrier()
         torch.cuda.synchronize()
-
-    def step():
-        with torch.no_grad():
-            return net(ws_d, pose_d, cat, noise_mode='const')
 
     # ---- device-resident throughput ----
     for _ in range(max(args.warmup, 3)):
@@ -254,20 +383,26 @@ def run_ours(args):
     launches = custom_ops.launch_count() - launches0
 
     # ---- end to end through the pipeline API (pinned host in, image back to host) ----
-    pipe = SynthesisPipeline(net, cat, batch, device)
+    if gen_mode:
+        pipe = GeneratorPipeline(net, batch, device)
+        call = lambda: pipe(host_u8)
+        h2d = sum(v.numel() for v in host_u8.values())
+    else:
+        pipe = SynthesisPipeline(net, cat, batch, device)
+        call = lambda: pipe(ws_h, pose_h)
+        h2d = ws_h.numel() * 4 + pose_h.numel() * 4
     for _ in range(3):
-        pipe(ws_h, pose_h)
+        call()
     pipe.flush()
     barrier()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0.record()
     for _ in range(args.steps):
-        host_img = pipe(ws_h, pose_h)
+        host_img = call()
     host_img = pipe.flush()
     f1.record()
     barrier()
     e2e_ms = f0.elapsed_time(f1)        # device clock; f1 is recorded after the last read-back completed
-    h2d = ws_h.numel() * 4 + pose_h.numel() * 4
     d2h = batch * 3 * RES * RES * 4
 
     # ---- max over ranks ----
@@ -331,7 +466,38 @@ def run_ours(args):
         # parity of this very step against the CPU oracle on a bounded sample (batch 1), reported with the number
         parity = parity_bf16 = None
         cpu = None
-        if not args.skip_cpu:
+        if not args.skip_cpu and gen_mode:
+            from oracle import ref_generator
+            sd = {k: v.detach().cpu() for k, v in net.state_dict().items()}
+            one = {k: v[:1] for k, v in dev_in.items()}
+            cpu_in = {k: v.cpu() for k, v in one.items()}
+            rel = lambda a, b: float((a.cpu().double() - b.double()).norm() / b.double().norm())
+            gt = torch.randint(0, 7, (1, 1, RES, RES), generator=torch.Generator().manual_seed(5)).float()
+            cores = host_threads()
+            torch.set_num_threads(cores)
+            with torch.no_grad():
+                # parity with gt_parsing fixed (no discrete decision depends on rounding)
+                t0 = time.perf_counter()
+                r_img, r_fin, r_par = ref_generator.generator(sd, cpu_in['c'], cpu_in['retain'], cpu_in['pose'], cpu_in['denorm_upper'],
+                                                              cpu_in['denorm_lower'], cpu_in['denorm_upper_mask'], cpu_in['denorm_lower_mask'], gt)
+                t_first = time.perf_counter() - t0
+                g_img, g_fin, g_par = run_generator(net, one, gt_parsing=gt.to(device))
+                parity = {'img_rel_l2': rel(g_img, r_img), 'finetune_rel_l2': rel(g_fin, r_fin), 'parsing_rel_l2': rel(g_par, r_par),
+                          'finetune_max_abs': float((g_fin.cpu() - r_fin).abs().max()), 'finetune_abs_scale': float(r_fin.abs().max())}
+                cg.fp32_precision = 'bf16'
+                b_img, b_fin, b_par = run_generator(net, one, gt_parsing=gt.to(device))
+                cg.fp32_precision = args.precision
+                parity_bf16 = {'img_rel_l2': rel(b_img, r_img), 'finetune_rel_l2': rel(b_fin, r_fin), 'parsing_rel_l2': rel(b_par, r_par),
+                               'finetune_max_abs': float((b_fin.cpu() - r_fin).abs().max())}
+                ctimes = [t_first]
+                for _ in range(2):
+                    t0 = time.perf_counter()
+                    ref_generator.generator(sd, cpu_in['c'], cpu_in['retain'], cpu_in['pose'], cpu_in['denorm_upper'], cpu_in['denorm_lower'],
+                                            cpu_in['denorm_upper_mask'], cpu_in['denorm_lower_mask'], None)
+                    ctimes.append(time.perf_counter() - t0)
+            cpu = {'value': 1.0 / min(ctimes), 'unit': 'images/s', 'cores': cores, 'kind': 'port',
+                   'sample': f'best of 3 x batch 1 through oracle/ref_generator.py (torch CPU ops, {cores} threads; {sum(ctimes):.1f} s total)'}
+        elif not args.skip_cpu:
             from oracle import ref_chain
             sd = {k: v.detach().cpu() for k, v in net.state_dict().items()}
             cat1 = {k: v[:1] for k, v in cat.items()}
@@ -352,21 +518,23 @@ def run_ours(args):
                    'sample': f'best of 3 x batch 1 through oracle/ref_chain.py (torch CPU ops, {cores} threads; {sum(ctimes):.1f} s total)'}
         imgs = batch * world * args.steps
         line = {
-            'metric': 'synthesis_hot_path_images_per_sec', 'value': imgs / (ms * 1e-3), 'unit': 'images/s', 'n_gpus': world,
+            'metric': 'generator_512px_images_per_sec' if gen_mode else 'synthesis_hot_path_images_per_sec',
+            'value': imgs / (ms * 1e-3), 'unit': 'images/s', 'n_gpus': world,
             'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': ms / args.steps, 'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None,
             'dtype': 'f32 tensors; bf16x2-split tcgen05 MMAs (3 bf16 products per multiply), fp32 accumulation' if args.precision != 'bf16'
                      else 'bf16 MMA, fp32 accumulate, f32 tensors',
             'data': 'synthetic',
-            'config': {'workload': 'PASTA-GAN++ 512px generator synthesis chain: 24 modulated_conv2d (+bias_act, noise, ToRGB accumulate), '
-                                   '5 merge 1x1 convs, 6 image-skip upfirdn2d; SPADE blocks/encoders not included (SURVEY 8f N1)',
+            'config': {'workload': GEN_DESC if gen_mode else CHAIN_DESC,
                        'batch_per_gpu': batch, 'global_batch': batch * world, 'resolution': RES, 'precision': args.precision,
                        'parallelism': f'batch-sharded x{world}, no collective',
                        'l2': 'per-step working set (several GB of activations) exceeds the 126 MB L2; no flush needed'},
             'clocks': clocks.summary(),
             'gpu_launches': launches,
             'e2e': {'value': imgs / (e2e_ms * 1e-3), 'unit': 'images/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
-                    'note': 'pinned-host ws + pose features in, fp32 image read back (as test.py:162 does); copy of batch i overlaps compute of i+1'},
+                    'note': ('uint8 pinned-host try-on inputs in (+ on-device /127.5-1, test.py:126-147), fp32 try-on image read back (test.py:162); '
+                             'copy of batch i overlaps compute of i+1') if gen_mode else
+                            'pinned-host ws + pose features in, fp32 image read back; copy of batch i overlaps compute of i+1'},
             'roofline': roof,
             'cpu_baseline': cpu,
             'parity_vs_cpu_oracle': parity,
@@ -388,6 +556,8 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--batch', type=int, default=32, help='images per GPU per step')
     ap.add_argument('--precision', default='bf16x2', choices=['bf16', 'bf16x2', 'bf16x3'])
+    ap.add_argument('--workload', default='generator', choices=['generator', 'chain'],
+                    help='generator: the full GeneratorFull_v20 forward (BASELINE configs[1]); chain: the modulated-conv synthesis chain only')
     ap.add_argument('--skip-cpu', action='store_true', help='skip the CPU baseline / parity leg')
     args = ap.parse_args()
     if args.impl == 'reference':

@@ -1,0 +1,380 @@
+"""The PASTA-GAN++ 512 px generator (`GeneratorFull_v20`, training/networks.py:2330-2366) as a caller of this package's
+ops -- the "next" row N1 of SURVEY section 8f.  Module, parameter and buffer names follow the reference one-to-one, so a
+reference `state_dict()` loads unchanged (43,076,462 parameters with the kwargs of train.py:191-202).
+
+    FullyConnectedLayer / Conv2dLayer / SynthesisLayer / ToRGBLayer     synthesis.py (networks.py:99-179, 1910-1967)
+    MappingNetwork                  networks.py:184-258
+    ResBlock                        networks.py:287-316
+    ConstEncoderNetwork             networks.py:357-376
+    Dense                           networks.py:391-405
+    Spade_Conv2dLayer / Spade_Norm_Block / Spade_ResBlockV4_512       networks.py:1586-1635, 1702-1723, 1859-1904
+    StyleEncoderNetworkV18          networks.py:1727-1776
+    SynthesisBlockFull              networks.py:1971-2082 (v1_v4, with SPADE) and 2086-2194 (v1_v6)
+    SynthesisNetworkFull_v18        networks.py:2198-2327
+    GeneratorFull_v20               networks.py:2330-2366
+
+Every convolution (modulated or plain, 100 calls per image) runs on the tcgen05 implicit-GEMM kernel with its bias /
+activation fused when `fused=True` on CUDA; FIR resampling and the SPADE pre-activations run on the upfirdn2d / bias_act
+kernels.  Instance norm, nearest-neighbour resizing, masks and the per-pixel `Dense` linear layers are not part of the
+hot path and stay PyTorch library ops, as in the reference.  `fused=False, impl='ref'` is the plain-PyTorch composition
+(any device), which the CPU tests compare against the reference-minted golden fixture.
+"""
+import numpy as np
+import torch
+
+from ..torch_utils.ops import bias_act
+from ..torch_utils.ops import conv2d_gradfix
+from ..torch_utils.ops import conv2d_resample
+from ..torch_utils.ops import upfirdn2d
+from . import synthesis as S
+from .synthesis import Conv2dLayer, FullyConnectedLayer, PackedAct, SynthesisLayer, ToRGBLayer
+
+SQRT_HALF = float(np.sqrt(0.5))
+
+
+def normalize_2nd_moment(x, dim=1, eps=1e-8):
+    return x * (x.square().mean(dim=dim, keepdim=True) + eps).rsqrt()
+
+
+class MappingNetwork(torch.nn.Module):
+    def __init__(self, z_dim, c_dim, w_dim, num_ws, num_layers=8, embed_features=None, layer_features=None, activation='lrelu',
+                 lr_multiplier=0.01, w_avg_beta=0.995):
+        super().__init__()
+        self.z_dim, self.c_dim, self.w_dim, self.num_ws, self.num_layers, self.w_avg_beta = z_dim, c_dim, w_dim, num_ws, num_layers, w_avg_beta
+        if embed_features is None:
+            embed_features = w_dim
+        if c_dim == 0:
+            embed_features = 0
+        if layer_features is None:
+            layer_features = w_dim
+        features = [z_dim + embed_features] + [layer_features] * (num_layers - 1) + [w_dim]
+        if c_dim > 0:
+            self.embed = FullyConnectedLayer(c_dim, embed_features)
+        for idx in range(num_layers):
+            setattr(self, f'fc{idx}', FullyConnectedLayer(features[idx], features[idx + 1], activation=activation, lr_multiplier=lr_multiplier))
+        if num_ws is not None and w_avg_beta is not None:
+            self.register_buffer('w_avg', torch.zeros([w_dim]))
+
+    def forward(self, z, c, truncation_psi=1, truncation_cutoff=None, skip_w_avg_update=False, impl='cuda'):
+        x = None
+        if self.z_dim > 0:
+            x = normalize_2nd_moment(z.to(torch.float32))
+        if self.c_dim > 0:
+            y = normalize_2nd_moment(self.embed(c.to(torch.float32), impl=impl))
+            x = torch.cat([x, y], dim=1) if x is not None else y
+        for idx in range(self.num_layers):
+            x = getattr(self, f'fc{idx}')(x, impl=impl)
+        if self.w_avg_beta is not None and self.training and not skip_w_avg_update:
+            self.w_avg.copy_(x.detach().mean(dim=0).lerp(self.w_avg, self.w_avg_beta))
+        if self.num_ws is not None:
+            x = x.unsqueeze(1).repeat([1, self.num_ws, 1])
+        if truncation_psi != 1:
+            if self.num_ws is None or truncation_cutoff is None:
+                x = self.w_avg.lerp(x, truncation_psi)
+            else:
+                x[:, :truncation_cutoff] = self.w_avg.lerp(x[:, :truncation_cutoff], truncation_psi)
+        return x
+
+
+class ResBlock(torch.nn.Module):
+    def __init__(self, in_channels, out_channels, kernel_size, bias=True, activation='linear', up=1, down=1,
+                 resample_filter=[1, 3, 3, 1], conv_clamp=None):
+        super().__init__()
+        self.register_buffer('resample_filter', upfirdn2d.setup_filter(resample_filter))
+        kw = dict(resample_filter=resample_filter, conv_clamp=conv_clamp)
+        self.conv0 = Conv2dLayer(in_channels, out_channels, kernel_size=3, activation=activation, up=up, down=down, bias=bias, **kw)
+        self.conv1 = Conv2dLayer(out_channels, out_channels, kernel_size=3, activation=activation, bias=bias, **kw)
+        self.skip = Conv2dLayer(in_channels, out_channels, kernel_size=1, bias=False, up=up, down=down, **kw)
+
+    def forward(self, x, fused=True, impl='cuda'):
+        y = self.skip(x, gain=SQRT_HALF, fused=fused, impl=impl)
+        x = self.conv0(x, fused=fused, impl=impl)
+        x = self.conv1(x, gain=SQRT_HALF, fused=fused, impl=impl)
+        return y.add_(x)
+
+
+class ConstEncoderNetwork(torch.nn.Module):
+    def __init__(self, input_nc, output_nc, ngf=64, n_downsampling=4):
+        super().__init__()
+        layers = [Conv2dLayer(input_nc, ngf, kernel_size=1)]
+        mult_ins, mult_outs = [1, 2, 4, 4, 4, 8], [2, 4, 4, 4, 8, 8]
+        for i in range(n_downsampling):
+            layers.append(Conv2dLayer(ngf * mult_ins[i], ngf * mult_outs[i], kernel_size=3, down=2))
+        self.model = torch.nn.ModuleList(layers)
+
+    def forward(self, x, fused=True, impl='cuda'):
+        for layer in self.model:
+            x = layer(x, fused=fused, impl=impl)
+        return x
+
+
+class Dense(torch.nn.Module):
+    """per-pixel Linear + InstanceNorm2d + LeakyReLU(0.01): library ops, not on the hot path"""
+
+    def __init__(self, in_channels, out_channels):
+        super().__init__()
+        self.bn = torch.nn.InstanceNorm2d(out_channels)
+        self.activation = torch.nn.LeakyReLU()
+        self.linear = torch.nn.Linear(in_channels, out_channels)
+
+    def forward(self, x):
+        out = self.linear(x.permute(0, 2, 3, 1)).permute(0, 3, 1, 2)
+        return self.activation(self.bn(out))
+
+
+class StyleEncoderNetworkV18(torch.nn.Module):
+    def __init__(self, input_nc, output_nc, ngf=64, n_downsampling=4):
+        super().__init__()
+        layers = [Conv2dLayer(input_nc, ngf, kernel_size=1)]
+        for mi, mo in zip([1, 2, 4], [2, 4, 8]):
+            layers += [Dense(ngf * mi, ngf * mi), Conv2dLayer(ngf * mi, ngf * mo, kernel_size=3, down=2)]
+        for _ in range(3):
+            layers += [Dense(ngf * 8, ngf * 8), Conv2dLayer(ngf * 8, ngf * 8, kernel_size=3)]
+        layers.append(torch.nn.AdaptiveAvgPool2d(1))
+        self.model = torch.nn.ModuleList(layers)
+        self.fc = FullyConnectedLayer(output_nc, output_nc)
+        feat = [Conv2dLayer(6, ngf, kernel_size=3)] + [Conv2dLayer(ngf, ngf, kernel_size=3, down=2) for _ in range(3)]
+        self.feat_enc = torch.nn.ModuleList(feat)
+
+    def forward(self, x, const_input, fused=True, impl='cuda'):
+        const_feats = []
+        for layer in self.feat_enc:
+            const_input = layer(const_input, fused=fused, impl=impl)
+            const_feats.append(const_input)
+        for layer in self.model:
+            x = layer(x, fused=fused, impl=impl) if isinstance(layer, Conv2dLayer) else layer(x)
+        return self.fc(x.view(x.size(0), -1), impl=impl), const_feats
+
+
+class Spade_Conv2dLayer(torch.nn.Module):
+    """pre-activation (bias_act relu, gain) followed by a plain convolution (networks.py:1627-1633)"""
+
+    def __init__(self, in_channels, out_channels, kernel_size, bias=True, activation='relu', resample_filter=[1, 3, 3, 1], conv_clamp=None):
+        super().__init__()
+        self.activation, self.conv_clamp = activation, conv_clamp
+        self.register_buffer('resample_filter', upfirdn2d.setup_filter(resample_filter))
+        self.padding = kernel_size // 2
+        self.weight_gain = 1 / np.sqrt(in_channels * (kernel_size ** 2))
+        self.act_gain = bias_act.activation_funcs[activation].def_gain
+        self.weight = torch.nn.Parameter(torch.randn([out_channels, in_channels, kernel_size, kernel_size]))
+        self.bias = torch.nn.Parameter(torch.zeros([out_channels])) if bias else None
+
+    def forward(self, x, gain=1, no_act=False, fused=True, impl='cuda'):
+        b = self.bias.to(x.dtype) if self.bias is not None else None
+        if not no_act:
+            act_clamp = self.conv_clamp * gain if self.conv_clamp is not None else None
+            x = bias_act.bias_act(x, b, act=self.activation, gain=self.act_gain * gain, clamp=act_clamp, impl=impl)
+        if fused and S._can_fuse(x, self.weight):
+            parts = conv2d_gradfix._PRODUCTS[conv2d_gradfix.precision_for(x.dtype)][1]
+            pw = conv2d_gradfix.packed_plain(self.weight, True, parts, self.padding, self.padding, scale=self.weight_gain)
+            return conv2d_gradfix.igemm_conv(x, pw)
+        w = self.weight * self.weight_gain
+        return conv2d_resample.conv2d_resample(x=x, w=w.to(x.dtype), f=self.resample_filter, padding=self.padding, flip_weight=True)
+
+
+class Spade_Norm_Block(torch.nn.Module):
+    def __init__(self, in_channels, norm_channels):
+        super().__init__()
+        self.conv_mlp = Spade_Conv2dLayer(in_channels, norm_channels, kernel_size=3, bias=False)
+        self.conv_mlp_act = torch.nn.ReLU()
+        self.conv_gamma = Spade_Conv2dLayer(norm_channels, norm_channels, kernel_size=3, bias=False)
+        self.conv_beta = Spade_Conv2dLayer(norm_channels, norm_channels, kernel_size=3, bias=False)
+        self.param_free_norm = torch.nn.InstanceNorm2d(norm_channels, affine=False)
+
+    def forward(self, x, denorm_feats, fused=True, impl='cuda'):
+        normalized = self.param_free_norm(x)
+        actv = self.conv_mlp_act(self.conv_mlp(denorm_feats, no_act=True, fused=fused, impl=impl))
+        gamma = self.conv_gamma(actv, no_act=True, fused=fused, impl=impl)
+        beta = self.conv_beta(actv, no_act=True, fused=fused, impl=impl)
+        return torch.addcmul(beta, normalized, 1 + gamma)
+
+
+class Spade_ResBlockV4_512(torch.nn.Module):
+    def __init__(self, in_channels, out_channels, spade_channels, resample_filter=[1, 3, 3, 1], conv_clamp=None):
+        super().__init__()
+        self.register_buffer('resample_filter', upfirdn2d.setup_filter(resample_filter))
+        kw = dict(bias=False, resample_filter=resample_filter, conv_clamp=conv_clamp)
+        self.conv = Spade_Conv2dLayer(in_channels, in_channels, kernel_size=3, **kw)
+        self.conv0 = Spade_Conv2dLayer(in_channels, out_channels, kernel_size=3, **kw)
+        self.conv1 = Spade_Conv2dLayer(out_channels, out_channels, kernel_size=3, **kw)
+        self.skip = Spade_Conv2dLayer(in_channels, out_channels, kernel_size=1, **kw)
+        self.spade_skip = Spade_Norm_Block(spade_channels, in_channels)
+        self.spade0 = Spade_Norm_Block(spade_channels, in_channels)
+        self.spade1 = Spade_Norm_Block(spade_channels, out_channels)
+
+    def forward(self, x, denorm_feat, fused=True, impl='cuda'):
+        kw = dict(fused=fused, impl=impl)
+        x = self.conv(x, no_act=True, **kw)
+        y = self.skip(self.spade_skip(x, denorm_feat, **kw), gain=SQRT_HALF, **kw)
+        x = self.conv0(self.spade0(x, denorm_feat, **kw), **kw)
+        x = self.conv1(self.spade1(x, denorm_feat, **kw), gain=SQRT_HALF, **kw)
+        return y.add_(x)
+
+
+class SynthesisBlockFull(torch.nn.Module):
+    """SynthesisBlockFull_v1_v6 ('skip' architecture); with `spade=True` the v1_v4 variant of the texture branch."""
+
+    def __init__(self, in_channels, out_channels, w_dim, resolution, img_channels, is_last, is_style=False, spade=False,
+                 resample_filter=[1, 3, 3, 1], conv_clamp=None, use_noise=True, **_unused):
+        super().__init__()
+        self.in_channels, self.resolution, self.img_channels, self.is_last = in_channels, resolution, img_channels, is_last
+        self.register_buffer('resample_filter', upfirdn2d.setup_filter(resample_filter))
+        self.num_conv = 0
+        self.num_torgb = 1
+        if in_channels == 0:
+            self.const = torch.nn.Parameter(torch.randn([out_channels, resolution, resolution]))      # unused by forward, as in the reference
+        else:
+            self.conv0 = SynthesisLayer(in_channels, out_channels, w_dim=w_dim, resolution=resolution, up=2,
+                                        resample_filter=resample_filter, conv_clamp=conv_clamp, use_noise=use_noise)
+            self.num_conv += 1
+        self.conv1 = SynthesisLayer(out_channels, out_channels, w_dim=w_dim, resolution=resolution, conv_clamp=conv_clamp, use_noise=use_noise)
+        self.num_conv += 1
+        self.torgb = ToRGBLayer(out_channels, img_channels, w_dim=w_dim, conv_clamp=conv_clamp,
+                                parsing_channels=(7 if (is_last and is_style) else 0))
+        if resolution > 32:
+            self.merge_conv = Conv2dLayer(out_channels + 64, out_channels, kernel_size=1, resample_filter=resample_filter)
+        if spade:
+            self.spade_b512 = Spade_ResBlockV4_512(out_channels, out_channels, spade_channels=1)
+
+    def forward(self, x, img, ws, pose_feature, cat_feat, parsing=None, fused=True, impl='cuda', export_tensor=False, **layer_kwargs):
+        """x: tensor or PackedAct.  Returns (x, img, pred_parsing); x is a PackedAct when the block ran in operand-format
+        hand-over mode and `export_tensor` is False (a consumer outside the conv chain needs the fp32 tensor)."""
+        w_iter = iter(ws.unbind(dim=1))
+        has_spade = hasattr(self, 'spade_b512')
+        want_tensor = export_tensor or has_spade
+        if self.in_channels == 0:
+            x = self.conv1(pose_feature.to(torch.float32), next(w_iter), fused=fused, impl=impl, **layer_kwargs)
+        elif fused and self.resolution >= S.PACKED_MIN_RES and S._can_fuse(x, self.conv0.weight, self.conv1.weight) and \
+                self.conv1.weight.shape[0] % 16 == 0:
+            n, res, oc, parts, dev = ws.shape[0], self.resolution, self.conv1.weight.shape[0], S._parts(), ws.device
+            xa = PackedAct(PackedAct.empty(n, res, res, oc, parts, dev), oc)
+            self.conv0(x, next(w_iter), fused=True, out_packed=xa, **layer_kwargs)
+            cf = cat_feat[str(res)]
+            mc = cf.shape[1]
+            buf = PackedAct.empty(n, res, res, oc + mc, parts, dev)
+            conv2d_gradfix._init()
+            conv2d_gradfix._plugin.pack_activations_into(cf, None, buf, mc, oc)
+            self.conv1(xa, next(w_iter), fused=True, out_packed=PackedAct(buf, oc, 0), **layer_kwargs)
+            if want_tensor:
+                x = self.merge_conv(PackedAct(buf, oc + mc, 0), fused=True)
+            else:
+                x = PackedAct(PackedAct.empty(n, res, res, oc, parts, dev), oc)
+                self.merge_conv(PackedAct(buf, oc + mc, 0), fused=True, out_packed=x)
+        else:
+            x = self.conv0(x, next(w_iter), fused=fused, impl=impl, **layer_kwargs)
+            x = self.conv1(x, next(w_iter), fused=fused, impl=impl, **layer_kwargs)
+            if x.shape[2] > 32:
+                x = torch.cat([x, cat_feat[str(x.shape[2])].to(x.dtype)], dim=1)
+                x = self.merge_conv(x, fused=fused, impl=impl)
+        if has_spade:
+            x = self.spade_b512(x, parsing, fused=fused, impl=impl)
+        if img is not None:
+            img = upfirdn2d.upsample2d(img, self.resample_filter, impl=impl)
+        img, pred_parsing = self.torgb(x, next(w_iter), img=img, fused=fused, impl=impl)
+        return x, img, pred_parsing
+
+
+class SynthesisNetworkFull_v18(torch.nn.Module):
+    def __init__(self, w_dim, img_resolution, img_channels, channel_base=32768, channel_max=512, num_fp16_res=0, **block_kwargs):
+        assert img_resolution >= 8 and img_resolution & (img_resolution - 1) == 0
+        super().__init__()
+        self.w_dim, self.img_resolution, self.img_channels = w_dim, img_resolution, img_channels
+        self.img_resolution_log2 = int(np.log2(img_resolution))
+        self.block_resolutions = [2 ** i for i in range(3, self.img_resolution_log2 + 1)]
+        ch = {res: min(channel_base // res, channel_max) for res in self.block_resolutions}
+        self.num_ws = 0
+        for res in self.block_resolutions:
+            block = SynthesisBlockFull(ch[res // 2] if res > 8 else 0, ch[res], w_dim=w_dim, resolution=res, img_channels=img_channels,
+                                       is_last=(res == img_resolution), is_style=True, **block_kwargs)
+            self.num_ws += block.num_conv
+            if res == img_resolution:
+                self.num_ws += block.num_torgb
+            setattr(self, f'b{res}', block)
+        res = self.block_resolutions[-2]
+        self.spade_b256_1 = Spade_ResBlockV4_512(ch[res], ch[res], spade_channels=128)
+        self.spade_b256_2 = Spade_ResBlockV4_512(ch[res], ch[res], spade_channels=128)
+        res = self.block_resolutions[-1]
+        self.texture_b512 = SynthesisBlockFull(ch[res // 2], ch[res], w_dim=w_dim, resolution=res, img_channels=img_channels, is_last=True,
+                                               is_style=False, spade=True, **block_kwargs)
+        ngf = 64
+        self.spade_encoder = torch.nn.ModuleList([Conv2dLayer(3, ngf, kernel_size=7, activation='relu'),
+                                                  ResBlock(ngf, ngf, kernel_size=4, activation='relu'),
+                                                  ResBlock(ngf, ngf * 2, kernel_size=4, activation='relu', down=2)])
+
+    def get_spade_feat(self, mask_512, denorm_mask, denorm_input, fused=True, impl='cuda'):
+        half = lambda t: torch.nn.functional.interpolate(t, scale_factor=0.5)
+        mask_512 = (mask_512 > 0.9).to(mask_512.dtype)
+        mask_256 = (half(mask_512) > 0.9).to(mask_512.dtype)
+        denorm_mask_256 = (half(denorm_mask) > 0.9).to(mask_512.dtype)
+        valid_mask = ((mask_256 + denorm_mask_256) == 2.0).to(mask_512.dtype)
+        res_mask = mask_256 - valid_mask
+        x = denorm_input * mask_512 - (1 - mask_512)
+        for layer in self.spade_encoder:
+            x = layer(x, fused=fused, impl=impl)
+        valid_feat_sum = torch.sum(x * valid_mask, dim=(2, 3), keepdim=True)
+        valid_mask_sum = torch.sum(valid_mask, dim=(2, 3), keepdim=True)
+        valid_index = (valid_mask_sum > 10).to(mask_512.dtype)
+        valid_mask_sum = valid_mask_sum * valid_index + (256 * 256) * (1 - valid_index)
+        return x * (1 - res_mask) + (valid_feat_sum / valid_mask_sum) * res_mask
+
+    def forward(self, ws, pose_feat, cat_feat, denorm_upper_input, denorm_lower_input, denorm_upper_mask, denorm_lower_mask, gt_parsing,
+                fused=True, impl='cuda', **block_kwargs):
+        ws = ws.to(torch.float32)
+        block_ws, w_idx = [], 0
+        for res in self.block_resolutions:
+            block = getattr(self, f'b{res}')
+            block_ws.append(ws.narrow(1, w_idx, block.num_conv + block.num_torgb))
+            w_idx += block.num_conv
+        x = img = pred_parsing = None
+        second_last = self.block_resolutions[-2]
+        for res, cur_ws in zip(self.block_resolutions, block_ws):
+            x, img, pp = getattr(self, f'b{res}')(x, img, cur_ws, pose_feat, cat_feat, fused=fused, impl=impl,
+                                                  export_tensor=(res == second_last), **block_kwargs)
+            pred_parsing = pp if pp is not None else pred_parsing
+            if res == second_last:
+                x_256, img_256 = x, img.clone()
+        if gt_parsing is not None:
+            parsing_index = gt_parsing
+        else:
+            parsing_index = torch.argmax(torch.softmax(pred_parsing.detach(), dim=1), dim=1)[:, None, ...].float()
+        upper_mask = (parsing_index == 1).float() + (parsing_index == 4).float()
+        lower_mask = (parsing_index == 2).float() + (parsing_index == 3).float()
+        kw = dict(fused=fused, impl=impl)
+        spade_upper = self.get_spade_feat(upper_mask, denorm_upper_mask, denorm_upper_input, **kw)
+        spade_lower = self.get_spade_feat(lower_mask, denorm_lower_mask, denorm_lower_input, **kw)
+        half = lambda t: torch.nn.functional.interpolate(t, scale_factor=0.5)
+        upper_256 = (half(upper_mask) > 0.9).to(upper_mask.dtype)
+        lower_256 = (half(lower_mask) > 0.9).to(upper_mask.dtype)
+        spade_feat = spade_upper * upper_256 + spade_lower * lower_256
+        xs = self.spade_b256_1(x_256, spade_feat, **kw)
+        xs = self.spade_b256_2(xs, spade_feat, **kw)
+        _, finetune_img, _ = self.texture_b512(xs, img_256, block_ws[-1], pose_feat, cat_feat, parsing=parsing_index, **kw, **block_kwargs)
+        return img, finetune_img, pred_parsing
+
+
+class GeneratorFull_v20(torch.nn.Module):
+    def __init__(self, z_dim, c_dim, w_dim, img_resolution, img_channels, mapping_kwargs={}, synthesis_kwargs={}):
+        super().__init__()
+        self.z_dim, self.c_dim, self.w_dim, self.img_resolution, self.img_channels = z_dim, c_dim, w_dim, img_resolution, img_channels
+        self.synthesis = SynthesisNetworkFull_v18(w_dim=w_dim, img_resolution=img_resolution, img_channels=img_channels, **synthesis_kwargs)
+        self.num_ws = self.synthesis.num_ws
+        self.mapping = MappingNetwork(z_dim=z_dim, c_dim=c_dim, w_dim=w_dim, num_ws=self.num_ws, **mapping_kwargs)
+        self.const_encoding = ConstEncoderNetwork(input_nc=3 + 2, output_nc=512, ngf=64, n_downsampling=6)
+        self.style_encoding = StyleEncoderNetworkV18(input_nc=(10 * 3 + 5 * 3), output_nc=512, ngf=64, n_downsampling=6)
+
+    def forward(self, z, c, retain, pose, denorm_upper_input, denorm_lower_input, denorm_upper_mask, denorm_lower_mask, gt_parsing=None,
+                truncation_psi=1, truncation_cutoff=None, fused=True, impl='cuda', **synthesis_kwargs):
+        pose_feat = self.const_encoding(pose, fused=fused, impl=impl)
+        stylecode, feats = self.style_encoding(c, retain, fused=fused, impl=impl)
+        ws = self.mapping(z, stylecode, truncation_psi=truncation_psi, truncation_cutoff=truncation_cutoff, impl=impl)
+        cat_feats = {str(f.shape[2]): f for f in feats}
+        return self.synthesis(ws, pose_feat, cat_feats, denorm_upper_input, denorm_lower_input, denorm_upper_mask, denorm_lower_mask,
+                              gt_parsing, fused=fused, impl=impl, **synthesis_kwargs)
+
+
+def build_generator(**overrides):
+    """GeneratorFull_v20 with the reference's training configuration (train.py:191-202, training_loop_fullbody.py:405)."""
+    kw = dict(z_dim=0, c_dim=512, w_dim=512, img_resolution=512, img_channels=3, mapping_kwargs=dict(num_layers=1),
+              synthesis_kwargs=dict(channel_base=32768, channel_max=512, num_fp16_res=3, conv_clamp=256, use_noise=True))
+    kw.update(overrides)
+    return GeneratorFull_v20(**kw)

@@ -89,6 +89,23 @@ class Conv2dLayer(torch.nn.Module):
             return conv2d_gradfix.igemm_conv(x, pw, bias=self.bias, act=self.activation,
                                              alpha=bias_act.activation_funcs[self.activation].def_alpha, gain=act_gain,
                                              clamp=-1 if act_clamp is None else act_clamp, out_packed=out_packed)
+        if fused and self.up == 1 and self.down == 2 and out_packed is None and _can_fuse(x, self.weight, self.bias) and \
+                not isinstance(x, PackedAct):
+            # FIR blur (or FIR decimation for 1x1 kernels) on the upfirdn2d kernel, then ONE strided implicit-GEMM launch with the
+            # bias / activation fused (conv2d_resample.py:107-110, 119-122)
+            k = self.weight.shape[-1]
+            fw = self.resample_filter.shape[-1]
+            p0 = self.padding + (fw - 2 + 1) // 2
+            p1 = self.padding + (fw - 2) // 2
+            parts = conv2d_gradfix._PRODUCTS[conv2d_gradfix.precision_for(x.dtype)][1]
+            pw = conv2d_gradfix.packed_plain(self.weight, True, parts, 0, 0, scale=self.weight_gain)
+            epi = dict(bias=self.bias, act=self.activation, alpha=bias_act.activation_funcs[self.activation].def_alpha, gain=act_gain,
+                       clamp=-1 if act_clamp is None else act_clamp)
+            if k == 1:
+                x = upfirdn2d.upfirdn2d(x, self.resample_filter, down=2, padding=[p0, p1, p0, p1])
+                return conv2d_gradfix.igemm_conv(x, pw, **epi)
+            x = upfirdn2d.upfirdn2d(x, self.resample_filter, padding=[p0, p1, p0, p1])
+            return conv2d_gradfix.igemm_conv(x, pw, stride=2, **epi)
         assert out_packed is None and not isinstance(x, PackedAct)
         w = self.weight * self.weight_gain
         b = self.bias.to(x.dtype) if self.bias is not None else None

@@ -46,3 +46,28 @@ def test_oracle_generator_matches_reference_golden():
             if tag == 'gt':
                 np.testing.assert_allclose(img[:, :, 200:232, 240:272].numpy(), g[f'{tag}_img_crop'], rtol=2e-3, atol=2e-4)
                 np.testing.assert_allclose(fin[:, :, 200:232, 240:272].numpy(), g[f'{tag}_finetune_crop'], rtol=2e-3, atol=5e-4)
+
+
+def test_product_generator_composition_route_matches_reference_golden():
+    """the package's GeneratorFull_v20 (same state-dict names as the reference) on the CPU through its plain-PyTorch
+    composition route; gt_parsing given so no discrete decision depends on rounding"""
+    import importlib
+    from conftest import load_pkg
+    from helpers import upfirdn2d_ref_on_cpu
+    load_pkg()
+    gen = importlib.import_module('pgpp_b200.training.generator')
+    up = importlib.import_module('pgpp_b200.torch_utils.ops.upfirdn2d')
+    torch.set_num_threads(max(1, min(8, os.cpu_count() or 1)))
+    g = np.load(GOLDEN)
+    G = gen.build_generator().eval()
+    assert sorted(f'{k}:{tuple(v.shape)}' for k, v in G.state_dict().items()) == sorted(str(x) for x in g['state_dict_names'])
+    ref_generator.name_seeded_init(list(G.named_parameters()) + list(G.named_buffers()))
+    inp = ref_generator.synthetic_inputs(1, seed=0)
+    with torch.no_grad(), upfirdn2d_ref_on_cpu(up):
+        img, fin, pred = G(torch.zeros(1, 0), inp['c'], inp['retain'], inp['pose'], inp['denorm_upper'], inp['denorm_lower'],
+                           inp['denorm_upper_mask'], inp['denorm_lower_mask'], gt_parsing=inp['gt_parsing'], fused=False, impl='ref',
+                           noise_mode='const')
+    for name, t in (('img', img), ('finetune', fin), ('parsing', pred)):
+        want = torch.from_numpy(g[f'gt_{name}_pooled'])
+        err = float((pooled(t) - want).norm() / want.norm())
+        assert err < 2e-5, (name, err)
