@@ -374,6 +374,7 @@ __device__ __forceinline__ void mma_role(const IgemmParams& p, const MmaCtx mc) 
     auto bempty_bar = [&](int s) { return mc.bar_base + 8u * (2 * SA + SB + s); };
     auto tfull_bar = [&](int b) { return mc.bar_base + 8u * (2 * SA + 2 * SB + b); };
     auto tempty_bar = [&](int b) { return mc.bar_base + 8u * (2 * SA + 2 * SB + 2 + b); };
+    const uint32_t bres_free_bar = mc.bar_base + 8u * (2 * SA + 2 * SB + 4);
     const int parts = PARTS ? PARTS : p.parts;
     const int inner = INNER ? INNER : p.inner;
     const int k_steps = KS ? KS : p.kb / 16;            // tcgen05.mma kind::f16 has K = 16
@@ -451,6 +452,11 @@ __device__ __forceinline__ void mma_role(const IgemmParams& p, const MmaCtx mc) 
             }
         }
         if (leader) umma_commit(tfull_bar(buf));                            // accumulator complete -> epilogue
+        if (RES && p.wgt_per_sample) {
+            // last tile of this sample on this CTA: once its MMAs retire the producer may overwrite the resident weights
+            const long long tn = t + gridDim.x;
+            if (tn < p.total_tiles && decode_tile(p, tn).n0 != last_n && leader) umma_commit(bres_free_bar);
+        }
         if (++buf == 2) { buf = 0; buf_phase ^= 1; }
         first_tile = false;
     }
@@ -472,7 +478,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
     auto bempty_bar = [&](int s) { return bar_base + 8u * (2 * SA + SB + s); };
     auto tfull_bar = [&](int b) { return bar_base + 8u * (2 * SA + 2 * SB + b); };
     auto tempty_bar = [&](int b) { return bar_base + 8u * (2 * SA + 2 * SB + 2 + b); };
-    const uint32_t tmem_slot = bar_base + 8u * (2 * SA + 2 * SB + 4);
+    const uint32_t bres_free_bar = bar_base + 8u * (2 * SA + 2 * SB + 4);     // resident weights may be overwritten (one completion per reload)
+    const uint32_t tmem_slot = bar_base + 8u * (2 * SA + 2 * SB + 5);
     // per-column epilogue parameters (scale, shift), double-buffered with the accumulator: float2 [2][block_n]
     float2* const s_params = reinterpret_cast<float2*>(smem_raw + (tmem_slot + 16u - smem_u32(smem_raw)));
 
@@ -485,6 +492,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
         for (int s = 0; s < SA; s++) { mbar_init(afull_bar(s), 1); mbar_init(aempty_bar(s), 1); }
         for (int s = 0; s < SB; s++) { mbar_init(bfull_bar(s), 1); mbar_init(bempty_bar(s), 1); }
         for (int b = 0; b < 2; b++) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), 8); }   // 8 epilogue warps arrive
+        mbar_init(bres_free_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -504,13 +512,16 @@ igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
             int sa = 0; uint32_t pha = 0;
             int sb = 0; uint32_t phb = 0;
             int k_tile = 0, last_n = -1;
+            uint32_t reload_phase = 0;
             for (long long t = blockIdx.x; t < p.total_tiles; t += gridDim.x, k_tile++) {
                 const TileCoord tc = decode_tile(p, t);
                 const int wn = p.wgt_per_sample ? tc.n0 : 0;
                 // resident weights are (re)loaded on the first tile and whenever the sample changes (per-sample weights)
                 const bool load_res = p.b_resident && (k_tile == 0 || (p.wgt_per_sample && tc.n0 != last_n));
-                if (load_res && k_tile > 0)     // every MMA of the previous tile must have read the old weights
-                    mbar_wait(tfull_bar((k_tile - 1) & 1), (uint32_t)((k_tile - 1) >> 1) & 1u);
+                if (load_res && k_tile > 0) {   // every MMA that reads the old weights must have retired: the MMA warp commits to
+                    mbar_wait(bres_free_bar, reload_phase);     // this barrier after the last tile of each sample (waited in order,
+                    reload_phase ^= 1;                          // one phase per reload, so the parity is never ambiguous)
+                }
                 last_n = tc.n0;
                 if (load_res) {
                     // all resident weight tiles first (the MMA warp waits for the whole set before touching the activation
@@ -729,7 +740,7 @@ extern "C" int pgpp_conv2d_igemm(const pgpp_conv_desc* d, void* stream) {
     // shared-memory plan (227 KB per CTA): weights resident if every tile of a column tile fits beside a 2-deep
     // activation ring, otherwise a weight ring of up to 8 slots and 2..4 activation stages
     auto smem_need = [&](long long a_st, long long b_st) -> long long {
-        return 1024 + a_st * p.a_stage_bytes + b_st * p.b_pitch + 8 * (2 * a_st + 2 * b_st + 4) + 16 + 16 + 16ll * p.block_n;
+        return 1024 + a_st * p.a_stage_bytes + b_st * p.b_pitch + 8 * (2 * a_st + 2 * b_st + 5) + 16 + 16 + 16ll * p.block_n;
     };
     const long long smem_max = 227 * 1024;
     const long long n_btiles = (long long)p.n_groups * p.num_cb * p.inner * p.parts;

@@ -73,4 +73,6 @@ def test_composition_route_on_gpu_and_batch_independence(generator_and_inputs):
     inp2 = {k: torch.cat([v, v.flip(-1)]) for k, v in inp.items()}
     c = _run(G, inp2, fused=True)
     for x, y in zip(c, a):
-        assert float((x[:1] - y).norm() / y.norm()) < 1e-5
+        # not bit-identical: library reductions (instance norm, sums) pick batch-size dependent algorithms; a kernel-level
+        # cross-sample leak (e.g. resident weights reloaded too early) shows up as >= 1e-3
+        assert float((x[:1] - y).norm() / y.norm()) < 2e-4
