@@ -104,6 +104,16 @@ PGPP_API int pgpp_pack_activations_slice(const void* x, const int64_t size[4], c
 PGPP_API int pgpp_modulate_weights(const float* master, const float* s, void* out, int n, int64_t rows, int c_pad, int c_in,
                           int parts, void* stream);
 
+/* SPADE modulation fused with the operand packing (training/networks.py:1713-1723 + the pre-activation of the consuming
+ * Spade_Conv2dLayer, :1627-1630):
+ *     v = (x - mean[n,c]) * rstd[n,c] * (1 + gamma) + beta;   if (pre_gain > 0) v = max(v, 0) * pre_gain;
+ *     out[part][n][y][x][c] = bf16 split of v                  (channels c >= C zero-filled)
+ * x float32 NCHW contiguous; gamma / beta float32 with NCHW-contiguous planes and a batch stride of gb_stride_n elements (so
+ * they may be the two channel halves of one [N, 2C, H, W] tensor); mean / rstd float32 [N, C].  Replaces five element-wise
+ * passes (instance-norm apply, 1 + gamma, multiply-add, bias_act, pack) with one. */
+PGPP_API int pgpp_spade_modulate_pack(const float* x, const float* mean, const float* rstd, const float* gamma, const float* beta,
+                          int64_t gb_stride_n, void* out, int n, int c, int h, int w, int c_pad, int parts, float pre_gain, void* stream);
+
 /* Epilogue + geometry of one implicit-GEMM convolution launch. */
 typedef struct {
     /* packed activations [a_parts][N][H][W][c_pad] bf16 and packed weights [b_parts][taps][o_rows][c_pad] bf16 */

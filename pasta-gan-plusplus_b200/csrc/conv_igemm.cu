@@ -573,6 +573,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
         if (ks == 4 && p.inner == 3 && p.parts == 1) { if (res) mma_role<1, 3, 4, true>(p, mc); else mma_role<1, 3, 4, false>(p, mc); }
         else if (ks == 4 && p.inner == 3 && p.parts == 2) { if (res) mma_role<2, 3, 4, true>(p, mc); else mma_role<2, 3, 4, false>(p, mc); }
         else if (ks == 4 && p.inner == 3 && p.parts == 3) mma_role<3, 3, 4, false>(p, mc);
+        else if (ks == 4 && p.inner == 7 && p.parts == 1) mma_role<1, 7, 4, false>(p, mc);
+        else if (ks == 4 && p.inner == 7 && p.parts == 2) mma_role<2, 7, 4, false>(p, mc);
         else if (ks == 4 && p.inner == 1 && p.parts == 1) { if (res) mma_role<1, 1, 4, true>(p, mc); else mma_role<1, 1, 4, false>(p, mc); }
         else if (ks == 4 && p.inner == 1 && p.parts == 2) { if (res) mma_role<2, 1, 4, true>(p, mc); else mma_role<2, 1, 4, false>(p, mc); }
         else if (res) mma_role<0, 0, 0, true>(p, mc);
@@ -799,7 +801,16 @@ extern "C" int pgpp_conv2d_igemm(const pgpp_conv_desc* d, void* stream) {
                    CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(weights) failed with CUresult %d", (int)r); return PGPP_ERR_CUDA; }
     }
-    PGPP_CUDA_OK(cudaFuncSetAttribute(igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    {
+        // once per device (the attribute is per function per context)
+        static bool done[64] = {false};
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (dev < 0 || dev >= 64 || !done[dev]) {
+            PGPP_CUDA_OK(cudaFuncSetAttribute(igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            if (dev >= 0 && dev < 64) done[dev] = true;
+        }
+    }
     long long grid = p.total_tiles;
     const int sms = sm_count();
     if (grid > sms) grid = sms;

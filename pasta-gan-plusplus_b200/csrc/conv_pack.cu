@@ -106,6 +106,53 @@ static int launch_pack(const PackArgs& p, cudaStream_t stream) {
     return PGPP_OK;
 }
 
+struct SpadeArgs {
+    const float* x; const float* mean; const float* rstd; const float* gamma; const float* beta; __nv_bfloat16* out;
+    int n, c, h, w, c_pad, parts; long long gb_stride_n, part_stride; float pre_gain;
+};
+
+// same 64-channel x 32-pixel transpose tile as pack_nchw_kernel, with the SPADE arithmetic applied on the way in
+__global__ void __launch_bounds__(256) spade_pack_kernel(SpadeArgs p, int w_tiles, int c_tiles) {
+    __shared__ float tile[64][33];
+    long long b = blockIdx.x;
+    const int wt = (int)(b % w_tiles); b /= w_tiles;
+    const int ct = (int)(b % c_tiles); b /= c_tiles;
+    const int y = (int)(b % p.h);
+    const int n = (int)(b / p.h);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int x0 = wt * 32, c0 = ct * 64;
+    const long long plane = (long long)p.h * p.w;
+    #pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const int c = c0 + warp * 8 + i;
+        float v = 0.f;
+        if (c < p.c && x0 + lane < p.w) {
+            const long long off = (long long)c * plane + (long long)y * p.w + (x0 + lane);
+            const float xv = p.x[(long long)n * p.c * plane + off];
+            const float g = p.gamma[n * p.gb_stride_n + off], bt = p.beta[n * p.gb_stride_n + off];
+            const float nv = (xv - p.mean[n * p.c + c]) * p.rstd[n * p.c + c];
+            v = fmaf(nv, 1.f + g, bt);
+            if (p.pre_gain > 0.f) v = fmaxf(v, 0.f) * p.pre_gain;
+        }
+        tile[warp * 8 + i][lane] = v;
+    }
+    __syncthreads();
+    const int px = warp * 4 + (lane >> 3);
+    const int cg = lane & 7;
+    if (x0 + px < p.w && c0 + cg * 8 < p.c_pad) {
+        float v[8];
+        #pragma unroll
+        for (int j = 0; j < 8; j++) v[j] = tile[cg * 8 + j][px];
+        __nv_bfloat16* dst = p.out + (((long long)n * p.h + y) * p.w + (x0 + px)) * p.c_pad + c0 + cg * 8;
+        for (int part = 0; part < p.parts; part++) {
+            __align__(16) __nv_bfloat16 q[8];
+            #pragma unroll
+            for (int j = 0; j < 8; j++) { q[j] = __float2bfloat16_rn(v[j]); v[j] -= __bfloat162float(q[j]); }
+            *reinterpret_cast<int4*>(dst + part * p.part_stride) = *reinterpret_cast<const int4*>(q);
+        }
+    }
+}
+
 // one CTA per output channel: W2[i] = sum_t w[o,i,t]^2 in shared memory, then one warp per sample
 __global__ void __launch_bounds__(256) demod_kernel(const float* __restrict__ w, const float* __restrict__ s,
                                                     float* __restrict__ d, int n, int o, int ic, int taps, float eps) {
@@ -202,6 +249,24 @@ extern "C" int pgpp_pack_activations_slice(const void* x, const int64_t size[4],
     }
     set_error("unsupported dtype %d", dtype);
     return PGPP_ERR_UNSUPPORTED;
+}
+
+extern "C" int pgpp_spade_modulate_pack(const float* x, const float* mean, const float* rstd, const float* gamma, const float* beta,
+                                        int64_t gb_stride_n, void* out, int n, int c, int h, int w, int c_pad, int parts, float pre_gain, void* stream) {
+    using namespace pgpp;
+    PGPP_REQUIRE(x && mean && rstd && gamma && beta && out, "null pointer");
+    PGPP_REQUIRE(n >= 1 && c >= 1 && h >= 1 && w >= 1 && c_pad >= c && c_pad % 16 == 0 && parts >= 1 && parts <= 3, "bad spade_modulate_pack arguments");
+    SpadeArgs p;
+    p.x = x; p.mean = mean; p.rstd = rstd; p.gamma = gamma; p.beta = beta; p.out = (__nv_bfloat16*)out;
+    p.n = n; p.c = c; p.h = h; p.w = w; p.c_pad = c_pad; p.parts = parts; p.gb_stride_n = gb_stride_n;
+    p.part_stride = (long long)n * h * w * c_pad; p.pre_gain = pre_gain;
+    const int w_tiles = (w + 31) / 32, c_tiles = (c_pad + 63) / 64;
+    const long long blocks = (long long)w_tiles * c_tiles * h * n;
+    PGPP_REQUIRE(blocks <= 2147483647LL, "tensor too large");
+    spade_pack_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(p, w_tiles, c_tiles);
+    count_launch();
+    PGPP_CUDA_OK(cudaGetLastError());
+    return PGPP_OK;
 }
 
 extern "C" int pgpp_modconv_demod_coefs(const float* w, const float* s, float* d, int n, int o, int i, int taps,

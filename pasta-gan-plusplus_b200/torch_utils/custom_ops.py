@@ -73,6 +73,8 @@ def load_library():
     lib.pgpp_pack_activations_slice.argtypes = [vp, c_i64x4, c_i64x4, i32, vp, vp, i32, i32, i32, i32, vp]
     lib.pgpp_modulate_weights.restype = i32
     lib.pgpp_modulate_weights.argtypes = [vp, vp, vp, i32, i64, i32, i32, i32, vp]
+    lib.pgpp_spade_modulate_pack.restype = i32
+    lib.pgpp_spade_modulate_pack.argtypes = [vp, vp, vp, vp, vp, i64, vp, i32, i32, i32, i32, i32, i32, f32, vp]
     lib.pgpp_conv2d_igemm.restype = i32
     lib.pgpp_conv2d_igemm.argtypes = [ctypes.POINTER(ConvDesc), vp]
     _lib = lib
@@ -81,7 +83,7 @@ def load_library():
 
 EXPORTED_SYMBOLS = ('pgpp_version', 'pgpp_last_error', 'pgpp_launch_count', 'pgpp_bias_act', 'pgpp_upfirdn2d',
                     'pgpp_modconv_demod_coefs', 'pgpp_pack_activations', 'pgpp_pack_activations_slice', 'pgpp_modulate_weights',
-                    'pgpp_conv2d_igemm')
+                    'pgpp_spade_modulate_pack', 'pgpp_conv2d_igemm')
 
 
 def launch_count():
@@ -241,6 +243,26 @@ class _ConvPlugin:
         out = torch.empty([s.shape[0], parts, rows, c_pad], dtype=torch.bfloat16, device=master.device)
         with torch.cuda.device(master.device):
             _check(lib.pgpp_modulate_weights(_ptr(master), _ptr(s), _ptr(out), s.shape[0], rows, c_pad, s.shape[1], int(parts), _stream(master)))
+        return out
+
+    @staticmethod
+    def spade_modulate_pack(x, mean, rstd, gamma_beta, c_pad, parts, pre_gain):
+        """x [N,C,H,W] f32 contiguous, gamma_beta [N,2C,H,W] f32 contiguous (gamma | beta), mean / rstd [N,C] ->
+        bf16 [parts, N, H, W, c_pad] = split(pre_act((x-mean)*rstd*(1+gamma)+beta))"""
+        lib = load_library()
+        n, c, h, w = x.shape
+        _torch_check(x.dtype == torch.float32 and x.is_contiguous() and gamma_beta.is_contiguous() and
+                     tuple(gamma_beta.shape) == (n, 2 * c, h, w), 'spade_modulate_pack: bad operands')
+        mean = mean.to(torch.float32).contiguous(); rstd = rstd.to(torch.float32).contiguous()
+        if c_pad == c:
+            out = torch.empty([parts, n, h, w, c_pad], dtype=torch.bfloat16, device=x.device)
+        else:
+            out = torch.zeros([parts, n, h, w, c_pad], dtype=torch.bfloat16, device=x.device)
+        gamma_ptr = gamma_beta.data_ptr()
+        beta_ptr = gamma_ptr + 4 * c * h * w
+        with torch.cuda.device(x.device):
+            _check(lib.pgpp_spade_modulate_pack(_ptr(x), _ptr(mean), _ptr(rstd), ctypes.c_void_p(gamma_ptr), ctypes.c_void_p(beta_ptr),
+                                                2 * c * h * w, _ptr(out), n, c, h, w, int(c_pad), int(parts), float(pre_gain), _stream(x)))
         return out
 
     @staticmethod

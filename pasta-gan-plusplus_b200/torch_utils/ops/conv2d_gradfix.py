@@ -102,7 +102,12 @@ class PackedAct:
 
     @staticmethod
     def empty(n, h, w, c_total, parts, device):
-        return torch.empty([parts, n, h, w, c_total], dtype=torch.bfloat16, device=device)
+        """buffer with c_total rounded up to whole 64-channel swizzle rows; padding channels are zeroed (they meet zero weights,
+        but must not hold NaN/Inf bit patterns)"""
+        c_alloc = _round_up(c_total, 64)
+        if c_alloc == c_total:
+            return torch.empty([parts, n, h, w, c_alloc], dtype=torch.bfloat16, device=device)
+        return torch.zeros([parts, n, h, w, c_alloc], dtype=torch.bfloat16, device=device)
 
     @property
     def shape(self):
@@ -133,11 +138,11 @@ def choose_block_n(cols, m_tiles, sms=148):
 def pack_weights(w_taps, o, phases, kh, kw, parts, pad_y, pad_x):
     """w_taps: float32 [taps, phases*o, I] -> PackedWeights.  GEMM column of (phase, oc) is phase*phase_stride + oc
     (phase_stride = o rounded up to 16 when phases == 4); rows are padded to a multiple of 256 or to the
-    power-of-two >= cols, channels to a multiple of 16."""
+    power-of-two >= cols, channels to a multiple of 64."""
     taps, _, ic = w_taps.shape
     phase_stride = _round_up(o, 16) if phases > 1 else o
     cols = phases * phase_stride
-    c_pad = _round_up(ic, 16)
+    c_pad = _round_up(ic, 64)      # whole 128-byte swizzle rows: every conv takes the kb = 64 path with the unrolled MMA issue loop
     o_rows = _round_up(cols, 256) if cols > 128 else max(16, 1 << (cols - 1).bit_length())
     buf = torch.zeros([taps, o_rows, c_pad], dtype=torch.float32, device=w_taps.device)
     buf[:, :cols].reshape(taps, phases, phase_stride, c_pad)[:, :, :o, :ic] = w_taps.reshape(taps, phases, o, ic)

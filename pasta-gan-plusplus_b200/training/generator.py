@@ -159,6 +159,11 @@ class Spade_Conv2dLayer(torch.nn.Module):
         self.weight = torch.nn.Parameter(torch.randn([out_channels, in_channels, kernel_size, kernel_size]))
         self.bias = torch.nn.Parameter(torch.zeros([out_channels])) if bias else None
 
+    def conv_packed(self, xp, act='linear', gain=1.0, out_packed=None, out=None, accumulate=False):
+        """the convolution alone on an operand-format input (pre-activation already applied by the producer of `xp`)"""
+        pw = conv2d_gradfix.packed_plain(self.weight, True, S._parts(), self.padding, self.padding, scale=self.weight_gain)
+        return conv2d_gradfix.igemm_conv(xp, pw, act=act, gain=gain, out_packed=out_packed, out=out, accumulate=accumulate)
+
     def forward(self, x, gain=1, no_act=False, fused=True, impl='cuda'):
         b = self.bias.to(x.dtype) if self.bias is not None else None
         if not no_act:
@@ -181,6 +186,31 @@ class Spade_Norm_Block(torch.nn.Module):
         self.conv_beta = Spade_Conv2dLayer(norm_channels, norm_channels, kernel_size=3, bias=False)
         self.param_free_norm = torch.nn.InstanceNorm2d(norm_channels, affine=False)
 
+    def _gamma_beta_weights(self):
+        """conv_gamma and conv_beta read the same input: one GEMM with 2C output columns"""
+        wg, wb = self.conv_gamma.weight, self.conv_beta.weight
+        def build():
+            w = torch.cat([wg.detach(), wb.detach()], dim=0).to(torch.float32) * float(self.conv_gamma.weight_gain)
+            o, ic, kh, kw = w.shape
+            taps = w.permute(2, 3, 0, 1).reshape(kh * kw, o, ic)
+            return conv2d_gradfix.pack_weights(taps, o, 1, kh, kw, S._parts(), self.conv_gamma.padding, self.conv_gamma.padding)
+        return conv2d_gradfix._cached(wg, ('spade_gb', wb.data_ptr(), wb._version, S._parts()), build)
+
+    def fused_packed(self, x, mean, rstd, feats_packed, pre_gain):
+        """operand-format result of pre_act(IN(x) * (1 + gamma) + beta) for the consuming conv: conv_mlp (+ReLU in its epilogue)
+        hands its output over in operand format, gamma|beta come from one GEMM, and one element-wise kernel applies the
+        normalisation, the modulation, the consumer's relu*gain and the packing."""
+        n, c, h, w = x.shape
+        parts = S._parts()
+        nc = self.conv_mlp.weight.shape[0]
+        actv = PackedAct(PackedAct.empty(n, h, w, nc, parts, x.device), nc)
+        self.conv_mlp.conv_packed(feats_packed, act='relu', gain=1.0, out_packed=actv)
+        gb = conv2d_gradfix.igemm_conv(actv, self._gamma_beta_weights())
+        conv2d_gradfix._init()
+        c_pad = -(-c // 64) * 64
+        data = conv2d_gradfix._plugin.spade_modulate_pack(x, mean, rstd, gb, c_pad, parts, pre_gain)
+        return PackedAct(data, c)
+
     def forward(self, x, denorm_feats, fused=True, impl='cuda'):
         normalized = self.param_free_norm(x)
         actv = self.conv_mlp_act(self.conv_mlp(denorm_feats, no_act=True, fused=fused, impl=impl))
@@ -202,7 +232,26 @@ class Spade_ResBlockV4_512(torch.nn.Module):
         self.spade0 = Spade_Norm_Block(spade_channels, in_channels)
         self.spade1 = Spade_Norm_Block(spade_channels, out_channels)
 
-    def forward(self, x, denorm_feat, fused=True, impl='cuda'):
+    @staticmethod
+    def _stats(x):
+        var, mean = torch.var_mean(x, dim=(2, 3), unbiased=False)
+        return mean, (var + 1e-5).rsqrt()
+
+    def forward(self, x, denorm_feat, fused=True, impl='cuda', feats_packed=None):
+        if fused and torch.is_tensor(x) and x.dtype == torch.float32 and S._can_fuse(x, self.conv.weight):
+            # fused SPADE route: 13 GEMM launches + 3 modulate/pack passes + 2 statistics reductions per block
+            relu_gain = float(bias_act.activation_funcs['relu'].def_gain)
+            if feats_packed is None:
+                conv2d_gradfix._init()
+                fc = denorm_feat.shape[1]
+                feats_packed = PackedAct(conv2d_gradfix._plugin.pack_activations(denorm_feat, None, -(-fc // 64) * 64, S._parts()), fc)
+            x = self.conv(x, no_act=True, fused=True).contiguous()
+            mean, rstd = self._stats(x)
+            y = self.skip.conv_packed(self.spade_skip.fused_packed(x, mean, rstd, feats_packed, relu_gain * SQRT_HALF))
+            x = self.conv0.conv_packed(self.spade0.fused_packed(x, mean, rstd, feats_packed, relu_gain)).contiguous()
+            mean, rstd = self._stats(x)
+            self.conv1.conv_packed(self.spade1.fused_packed(x, mean, rstd, feats_packed, relu_gain * SQRT_HALF), out=y, accumulate=True)
+            return y
         kw = dict(fused=fused, impl=impl)
         x = self.conv(x, no_act=True, **kw)
         y = self.skip(self.spade_skip(x, denorm_feat, **kw), gain=SQRT_HALF, **kw)
@@ -346,8 +395,13 @@ class SynthesisNetworkFull_v18(torch.nn.Module):
         upper_256 = (half(upper_mask) > 0.9).to(upper_mask.dtype)
         lower_256 = (half(lower_mask) > 0.9).to(upper_mask.dtype)
         spade_feat = spade_upper * upper_256 + spade_lower * lower_256
-        xs = self.spade_b256_1(x_256, spade_feat, **kw)
-        xs = self.spade_b256_2(xs, spade_feat, **kw)
+        feats_packed = None
+        if fused and S._can_fuse(spade_feat):       # both SPADE blocks read the same features: pack them once
+            conv2d_gradfix._init()
+            fc = spade_feat.shape[1]
+            feats_packed = PackedAct(conv2d_gradfix._plugin.pack_activations(spade_feat, None, -(-fc // 64) * 64, S._parts()), fc)
+        xs = self.spade_b256_1(x_256, spade_feat, feats_packed=feats_packed, **kw)
+        xs = self.spade_b256_2(xs, spade_feat, feats_packed=feats_packed, **kw)
         _, finetune_img, _ = self.texture_b512(xs, img_256, block_ws[-1], pose_feat, cat_feat, parsing=parsing_index, **kw, **block_kwargs)
         return img, finetune_img, pred_parsing
 

@@ -104,7 +104,7 @@ def test_packed_activation_roundtrip_and_per_sample_weights():
         b1 = torch.randn(48, generator=g)
         y1 = ref_ops.synthesis_layer(x, s1, w1, b1, None, 1, None)
         y2 = ref_ops.modulated_conv2d(y1, w2, s2, padding=1)
-        buf = cg.PackedAct(cg.PackedAct.empty(3, 24, 20, 64, 3, DEV), 48, 16)       # channels [16, 64) of a wider buffer
+        buf = cg.PackedAct(torch.zeros(3, 3, 24, 20, 128, dtype=torch.bfloat16, device=DEV), 48, 64)    # channels [64, 112) of a wider buffer
         with torch.no_grad():
             nets.modulated_conv2d_fused_act(x.to(DEV), w1.to(DEV), s1.to(DEV), padding=1, bias=b1.to(DEV), act='lrelu', clamp=256.0,
                                             out_packed=buf)

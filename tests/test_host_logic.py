@@ -144,7 +144,7 @@ def test_weight_packing_plain_and_split_precision(parts, tol):
     s = torch.randn(2, 20, generator=g) * 0.5 + 1
     for flip in (True, False):
         pw = conv2d_gradfix.packed_plain(w, flip, parts, 1, 1)
-        assert pw.c_pad == 32 and pw.o_rows == 32 and pw.data.dtype == torch.bfloat16 and pw.data.shape[0] == parts
+        assert pw.c_pad == 64 and pw.o_rows == 32 and pw.data.dtype == torch.bfloat16 and pw.data.shape[0] == parts
         want = ref_ops.conv2d_resample(x * s.reshape(2, 20, 1, 1), w, padding=1, flip_weight=flip)
         got = emulate_igemm(x, pw, scale=s)
         assert rel_l2(got, want) < tol     # bf16 expansion of the WEIGHTS only (activations stay exact here)
