@@ -104,6 +104,14 @@ PGPP_API int pgpp_pack_activations_slice(const void* x, const int64_t size[4], c
 PGPP_API int pgpp_modulate_weights(const float* master, const float* s, void* out, int n, int64_t rows, int c_pad, int c_in,
                           int parts, void* stream);
 
+/* Row-group im2col packing for convolutions with very few input channels (the 7x7 RGB stem, 3x3 convs on 1..6 channels):
+ *     out[part][n][yy][x][(ry*kw + kx)*C + c] = split(x[n, c, yy - pad_y + ry, x + kx - pad_x] * scale[n,c])   (0 outside)
+ * for yy in [0, H + pad_y), ry in [0, r), channels >= r*kw*C zero-filled up to 64.  The convolution then runs as a kh' =
+ * ceil(kh / r), kw' = 1 implicit GEMM with vertical tap spacing r (pgpp_conv_desc.dil_y) and 64-channel operand rows, i.e.
+ * r*kw times fewer MMAs and weight tiles than padding C to 64 per tap. */
+PGPP_API int pgpp_pack_im2col(const void* x, const int64_t size[4], const int64_t stride[4], int dtype, const float* scale,
+                          void* out, int kw, int r, int pad_x, int pad_y, int parts, void* stream);
+
 /* SPADE modulation fused with the operand packing (training/networks.py:1713-1723 + the pre-activation of the consuming
  * Spade_Conv2dLayer, :1627-1630):
  *     v = (x - mean[n,c]) * rstd[n,c] * (1 + gamma) + beta;   if (pre_gain > 0) v = max(v, 0) * pre_gain;
@@ -129,6 +137,7 @@ typedef struct {
     int32_t kh, kw;                 /* filter taps */
     int32_t pad_y, pad_x;           /* zero padding (top / left); bottom / right implied by out size */
     int32_t stride;                 /* 1 or 2 */
+    int32_t dil_y;                  /* vertical tap spacing (0 or 1 = dense); > 1 only with stride 1 (row-group im2col operands) */
     int32_t conv_h, conv_w;         /* conv output grid (per phase) */
     int32_t o;                      /* logical output channels (per phase) */
     int32_t phases;                 /* 1, or 4 for the fused up=2 polyphase form: GEMM column g = phase*phase_stride + oc,

@@ -710,7 +710,10 @@ extern "C" int pgpp_conv2d_igemm(const pgpp_conv_desc* d, void* stream) {
     p.o = d->o; p.phases = d->phases; p.phase_stride = d->phase_stride; p.o_rows = d->o_rows; p.block_n = d->block_n; p.up = up;
     // pixel tile TW x TH x TN = 128.  Stride-1 convs with kh > 1 on images of at least 16 x 8 use a 16 x 8 tile so that
     // one slab of TH + kh - 1 rows serves all vertical taps (ky reuse); everything else takes the widest tile.
-    p.reuse = (d->stride == 1 && d->kh > 1 && d->conv_w >= 16 && d->conv_h >= 8 && d->kh <= 7) ? 1 : 0;
+    const int dil_y = d->dil_y > 1 ? d->dil_y : 1;
+    PGPP_REQUIRE(dil_y == 1 || d->stride == 1, "dil_y > 1 needs stride 1");
+    p.reuse = (d->stride == 1 && d->kh > 1 && d->conv_w >= 16 && d->conv_h >= 8 && (d->kh - 1) * dil_y <= 6) ? 1 : 0;
+    PGPP_REQUIRE(dil_y == 1 || p.reuse, "dil_y > 1 is only supported on the slab-reuse path (images of at least 16 x 8, (kh-1)*dil_y <= 6)");
     if (getenv("PGPP_IGEMM_NO_REUSE")) p.reuse = 0;
     if (p.reuse) { p.tw = 16; p.th = 8; p.tn = 1; }
     else {
@@ -726,11 +729,11 @@ extern "C" int pgpp_conv2d_igemm(const pgpp_conv_desc* d, void* stream) {
     p.tiles_col = (d->phases * d->phase_stride + d->block_n - 1) / d->block_n;
     p.total_tiles = (long long)p.tiles_x * p.tiles_y * p.tiles_n * p.tiles_col;
     const unsigned row_bytes = (unsigned)p.kb * 2;
-    const int slab_rows = p.tn * (p.th + p.inner - 1) * p.tw;        // multiple of 8 (TW % 8 == 0 with reuse, 128 without)
+    const int slab_rows = p.tn * (p.th + (p.inner - 1) * dil_y) * p.tw;        // multiple of 8 (TW % 8 == 0 with reuse, 128 without)
     p.slab_bytes = (unsigned)slab_rows * row_bytes;
     p.a_tx_bytes = p.parts * p.slab_bytes;
     p.a_stage_bytes = (p.a_tx_bytes + 1023u) & ~1023u;
-    p.ky_step_bytes = (unsigned)p.tw * row_bytes;
+    p.ky_step_bytes = (unsigned)(p.tw * dil_y) * row_bytes;
     p.b_bytes = (unsigned)d->block_n * row_bytes;
     p.b_pitch = (p.b_bytes + 1023u) & ~1023u;
     p.layout_type = row_bytes == 128 ? 2u : (row_bytes == 64 ? 4u : 6u);   // SWIZZLE_128B / 64B / 32B
@@ -786,7 +789,7 @@ extern "C" int pgpp_conv2d_igemm(const pgpp_conv_desc* d, void* stream) {
         const cuuint64_t dims[5] = {(cuuint64_t)d->c_pad, (cuuint64_t)d->w, (cuuint64_t)d->h, (cuuint64_t)d->n, (cuuint64_t)d->a_parts};
         const cuuint64_t strides[4] = {(cuuint64_t)pix_stride * 2, (cuuint64_t)pix_stride * 2 * d->w, (cuuint64_t)pix_stride * 2 * d->w * d->h,
                                        (cuuint64_t)pix_stride * 2 * d->w * d->h * d->n};
-        const cuuint32_t box[5] = {(cuuint32_t)p.kb, (cuuint32_t)(p.tw * d->stride), (cuuint32_t)((p.th + p.inner - 1) * d->stride), (cuuint32_t)p.tn, 1};
+        const cuuint32_t box[5] = {(cuuint32_t)p.kb, (cuuint32_t)(p.tw * d->stride), (cuuint32_t)((p.th + (p.inner - 1) * dil_y) * d->stride), (cuuint32_t)p.tn, 1};
         const cuuint32_t estr[5] = {1, (cuuint32_t)d->stride, (cuuint32_t)d->stride, 1, 1};
         const CUtensorMapSwizzle sw = row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
         CUresult r = encode(&map_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(d->act), dims, strides, box, estr,

@@ -106,6 +106,50 @@ static int launch_pack(const PackArgs& p, cudaStream_t stream) {
     return PGPP_OK;
 }
 
+struct Im2colArgs {
+    const void* x; const float* scale; __nv_bfloat16* out;
+    int n, c, h, w, hp, kw, r, pad_x, pad_y, parts;
+    long long s_n, s_c, s_h, s_w, part_stride;
+};
+
+// one thread per (packed pixel, group of 8 channels): gathers up to 8 shifted input samples (L1/L2-cached reads of a tiny
+// tensor) and writes one 128-bit store per part; 8 consecutive threads cover the 128-byte channel row of a pixel
+template <class T>
+__global__ void __launch_bounds__(256) im2col_kernel(Im2colArgs p, long long total) {
+    const int used = p.r * p.kw * p.c;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const int cg = (int)(e & 7);
+        long long q = e >> 3;
+        const int x = (int)(q % p.w); q /= p.w;
+        const int yy = (int)(q % p.hp);
+        const int n = (int)(q / p.hp);
+        float v[8];
+        #pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const int ch = cg * 8 + j;
+            float val = 0.f;
+            if (ch < used) {
+                const int c = ch % p.c;
+                const int t = ch / p.c;
+                const int kx = t % p.kw, ry = t / p.kw;
+                const int iy = yy - p.pad_y + ry, ix = x + kx - p.pad_x;
+                if (iy >= 0 && iy < p.h && ix >= 0 && ix < p.w) {
+                    val = (float)to_acc<T>(((const T*)p.x)[n * p.s_n + c * p.s_c + iy * p.s_h + ix * p.s_w]);
+                    if (p.scale) val *= p.scale[n * p.c + c];
+                }
+            }
+            v[j] = val;
+        }
+        __nv_bfloat16* dst = p.out + (((long long)n * p.hp + yy) * p.w + x) * 64 + cg * 8;
+        for (int part = 0; part < p.parts; part++) {
+            __align__(16) __nv_bfloat16 qv[8];
+            #pragma unroll
+            for (int j = 0; j < 8; j++) { qv[j] = __float2bfloat16_rn(v[j]); v[j] -= __bfloat162float(qv[j]); }
+            *reinterpret_cast<int4*>(dst + part * p.part_stride) = *reinterpret_cast<const int4*>(qv);
+        }
+    }
+}
+
 struct SpadeArgs {
     const float* x; const float* mean; const float* rstd; const float* gamma; const float* beta; __nv_bfloat16* out;
     int n, c, h, w, c_pad, parts; long long gb_stride_n, part_stride; float pre_gain;
@@ -249,6 +293,37 @@ extern "C" int pgpp_pack_activations_slice(const void* x, const int64_t size[4],
     }
     set_error("unsupported dtype %d", dtype);
     return PGPP_ERR_UNSUPPORTED;
+}
+
+extern "C" int pgpp_pack_im2col(const void* x, const int64_t size[4], const int64_t stride[4], int dtype, const float* scale,
+                                void* out, int kw, int r, int pad_x, int pad_y, int parts, void* stream) {
+    using namespace pgpp;
+    PGPP_REQUIRE(x && out, "x and out must be device pointers");
+    PGPP_REQUIRE(parts >= 1 && parts <= 3 && kw >= 1 && r >= 1 && pad_x >= 0 && pad_y >= 0, "bad im2col arguments");
+    PGPP_REQUIRE((long long)r * kw * size[1] <= 64, "im2col packing needs r*kw*C <= 64");
+    Im2colArgs p;
+    p.x = x; p.scale = scale; p.out = (__nv_bfloat16*)out;
+    p.n = (int)size[0]; p.c = (int)size[1]; p.h = (int)size[2]; p.w = (int)size[3]; p.hp = p.h + pad_y;
+    p.kw = kw; p.r = r; p.pad_x = pad_x; p.pad_y = pad_y; p.parts = parts;
+    p.s_n = stride[0]; p.s_c = stride[1]; p.s_h = stride[2]; p.s_w = stride[3];
+    p.part_stride = (long long)p.n * p.hp * p.w * 64;
+    const long long total = (long long)p.n * p.hp * p.w * 8;
+    if (total == 0) return PGPP_OK;
+    long long blocks = (total + 255) / 256;
+    cudaStream_t s = (cudaStream_t)stream;
+#define PGPP_IM2COL(T) { const long long cap = (long long)sm_count() * occupancy_of(im2col_kernel<T>, 256, 0); \
+                         if (blocks > cap) blocks = cap; im2col_kernel<T><<<(unsigned)blocks, 256, 0, s>>>(p, total); }
+    switch (dtype) {
+        case PGPP_F32:  PGPP_IM2COL(float) break;
+        case PGPP_F16:  PGPP_IM2COL(__half) break;
+        case PGPP_BF16: PGPP_IM2COL(__nv_bfloat16) break;
+        case PGPP_F64:  PGPP_IM2COL(double) break;
+        default: set_error("unsupported dtype %d", dtype); return PGPP_ERR_UNSUPPORTED;
+    }
+#undef PGPP_IM2COL
+    count_launch();
+    PGPP_CUDA_OK(cudaGetLastError());
+    return PGPP_OK;
 }
 
 extern "C" int pgpp_spade_modulate_pack(const float* x, const float* mean, const float* rstd, const float* gamma, const float* beta,

@@ -31,7 +31,7 @@ class ConvDesc(ctypes.Structure):
         ('act_pixel_stride', ctypes.c_int32), ('wgt_per_sample', ctypes.c_int32),
         ('kh', ctypes.c_int32), ('kw', ctypes.c_int32),
         ('pad_y', ctypes.c_int32), ('pad_x', ctypes.c_int32),
-        ('stride', ctypes.c_int32),
+        ('stride', ctypes.c_int32), ('dil_y', ctypes.c_int32),
         ('conv_h', ctypes.c_int32), ('conv_w', ctypes.c_int32),
         ('o', ctypes.c_int32), ('phases', ctypes.c_int32), ('phase_stride', ctypes.c_int32), ('o_rows', ctypes.c_int32), ('block_n', ctypes.c_int32),
         ('products', ctypes.c_int32),
@@ -73,6 +73,8 @@ def load_library():
     lib.pgpp_pack_activations_slice.argtypes = [vp, c_i64x4, c_i64x4, i32, vp, vp, i32, i32, i32, i32, vp]
     lib.pgpp_modulate_weights.restype = i32
     lib.pgpp_modulate_weights.argtypes = [vp, vp, vp, i32, i64, i32, i32, i32, vp]
+    lib.pgpp_pack_im2col.restype = i32
+    lib.pgpp_pack_im2col.argtypes = [vp, c_i64x4, c_i64x4, i32, vp, vp, i32, i32, i32, i32, i32, vp]
     lib.pgpp_spade_modulate_pack.restype = i32
     lib.pgpp_spade_modulate_pack.argtypes = [vp, vp, vp, vp, vp, i64, vp, i32, i32, i32, i32, i32, i32, f32, vp]
     lib.pgpp_conv2d_igemm.restype = i32
@@ -83,7 +85,7 @@ def load_library():
 
 EXPORTED_SYMBOLS = ('pgpp_version', 'pgpp_last_error', 'pgpp_launch_count', 'pgpp_bias_act', 'pgpp_upfirdn2d',
                     'pgpp_modconv_demod_coefs', 'pgpp_pack_activations', 'pgpp_pack_activations_slice', 'pgpp_modulate_weights',
-                    'pgpp_spade_modulate_pack', 'pgpp_conv2d_igemm')
+                    'pgpp_spade_modulate_pack', 'pgpp_pack_im2col', 'pgpp_conv2d_igemm')
 
 
 def launch_count():
@@ -233,6 +235,20 @@ class _ConvPlugin:
             _check(lib.pgpp_pack_activations_slice(_ptr(x), c_i64x4(*x.shape), c_i64x4(*x.stride()), dtype_code(x.dtype), _ptr(scale),
                                                    _ptr(dst), int(c_pad), int(c_total), int(c_off), int(parts), _stream(x)))
         return dst
+
+    @staticmethod
+    def pack_im2col(x, scale, kw, r, pad_x, pad_y, parts):
+        """row-group im2col operand [parts, N, H + pad_y, W, 64] (see pgpp_pack_im2col)"""
+        lib = load_library()
+        n, c, h, w = x.shape
+        _torch_check(r * kw * c <= 64, 'im2col packing needs r*kw*C <= 64')
+        out = torch.empty([parts, n, h + pad_y, w, 64], dtype=torch.bfloat16, device=x.device)
+        if scale is not None:
+            scale = scale.detach().to(torch.float32).contiguous()
+        with torch.cuda.device(x.device):
+            _check(lib.pgpp_pack_im2col(_ptr(x), c_i64x4(*x.shape), c_i64x4(*x.stride()), dtype_code(x.dtype), _ptr(scale), _ptr(out),
+                                        int(kw), int(r), int(pad_x), int(pad_y), int(parts), _stream(x)))
+        return out
 
     @staticmethod
     def modulate_weights(master, styles, parts):

@@ -88,17 +88,18 @@ def _split_bf16(t, parts):
 
 class PackedWeights:
     """[parts, taps, o_rows, c_pad] bf16, K-major rows, ready for the TMA weight map."""
-    __slots__ = ('data', 'master', 'kh', 'kw', 'o', 'phases', 'phase_stride', 'o_rows', 'c_pad', 'c_in', 'parts', 'pad_y', 'pad_x')
+    __slots__ = ('data', 'master', 'kh', 'kw', 'o', 'phases', 'phase_stride', 'o_rows', 'c_pad', 'c_in', 'parts', 'pad_y', 'pad_x', 'im2col')
 
 
 class PackedAct:
     """Activations in the tensor-core operand format: data [parts, N, H, W, c_total] bf16, channels innermost; the
     logical tensor is channels [c_off, c_off + c) of every pixel.  Convolutions can write this format directly from
     their epilogue (`out_packed=`) and read it without a packing pass."""
-    __slots__ = ('data', 'c', 'c_off')
+    __slots__ = ('data', 'c', 'c_off', 'logical_hw')
 
-    def __init__(self, data, c, c_off=0):
+    def __init__(self, data, c, c_off=0, logical_hw=None):
         self.data, self.c, self.c_off = data, c, c_off
+        self.logical_hw = logical_hw        # (H, W) of the source image for row-group im2col operands (data has H + pad_y rows)
 
     @staticmethod
     def empty(n, h, w, c_total, parts, device):
@@ -153,6 +154,7 @@ def pack_weights(w_taps, o, phases, kh, kw, parts, pad_y, pad_x):
     pw.kh, pw.kw, pw.o, pw.phases, pw.o_rows, pw.c_pad, pw.parts = kh, kw, o, phases, o_rows, c_pad, parts
     pw.phase_stride = phase_stride
     pw.pad_y, pw.pad_x = pad_y, pad_x
+    pw.im2col = None
     return pw
 
 
@@ -172,7 +174,15 @@ def _cached(key_tensor, tag, builder):
     return hit[0]
 
 
-def packed_plain(weight, flip_weight, parts, pad_y, pad_x, transpose_io=False, scale=1.0):
+def im2col_rows(ic, kh, kw):
+    """rows per im2col group (0 = not worthwhile): r*kw*ic <= 64 with r >= min(kh, 3)"""
+    if kh * kw == 1 or ic * kw > 21:
+        return 0
+    r = min(kh, 64 // (ic * kw))
+    return r if (kh - 1) // r * r <= 6 else 0
+
+
+def packed_plain(weight, flip_weight, parts, pad_y, pad_x, transpose_io=False, scale=1.0, allow_im2col=False):
     """weight [O, I, kh, kw] used as a correlation kernel (flip_weight=True, F.conv2d semantics) or a true
     convolution kernel (flip_weight=False).  transpose_io: weight is [I, O, kh, kw] (conv_transpose2d layout).
     scale: constant folded into the packed copy (the layers' runtime weight_gain, networks.py:155,169)."""
@@ -183,9 +193,20 @@ def packed_plain(weight, flip_weight, parts, pad_y, pad_x, transpose_io=False, s
         if not flip_weight:
             w = w.flip([2, 3])
         o, ic, kh, kw = w.shape
+        r = im2col_rows(ic, kh, kw) if allow_im2col else 0
+        if r:
+            # row-group im2col operand (pgpp_pack_im2col): channel (ry*kw + kx)*ic + c of vertical tap group t holds w[o, c, t*r + ry, kx]
+            groups = -(-kh // r)
+            wp = torch.zeros([groups, o, r, kw, ic], dtype=torch.float32, device=w.device)
+            for t in range(groups):
+                rows = min(r, kh - t * r)
+                wp[t, :, :rows] = w[:, :, t * r:t * r + rows, :].permute(0, 2, 3, 1)
+            pw = pack_weights(wp.reshape(groups, o, r * kw * ic), o, 1, groups, 1, parts, 0, 0)
+            pw.im2col = dict(r=r, kw=kw, kh=kh, pad_x=pad_x, pad_y=pad_y)
+            return pw
         taps = w.permute(2, 3, 0, 1).reshape(kh * kw, o, ic)
         return pack_weights(taps, o, 1, kh, kw, parts, pad_y, pad_x)
-    return _cached(weight, ('plain', bool(flip_weight), parts, pad_y, pad_x, bool(transpose_io), float(scale)), build)
+    return _cached(weight, ('plain', bool(flip_weight), parts, pad_y, pad_x, bool(transpose_io), float(scale), bool(allow_im2col)), build)
 
 
 def packed_up2(weight, f, flip_weight, flip_filter, parts):
@@ -240,6 +261,14 @@ def igemm_conv(x, pw, *, scale=None, stride=1, out_hw=None, dcoef=None, noise=No
                PackedAct view -> the epilogue writes the bf16 operand format of the next conv into that channel slice."""
     _init()
     n, ic, h, w = x.shape
+    im = pw.im2col
+    if im is not None:
+        assert stride == 1 and out_hw is None
+        if isinstance(x, PackedAct):
+            src_h, src_w = x.logical_hw
+        else:
+            src_h, src_w = h, w
+        out_hw = (src_h + 2 * im['pad_y'] - im['kh'] + 1, src_w + 2 * im['pad_x'] - im['kw'] + 1)
     src_dtype = torch.float32 if isinstance(x, PackedAct) else x.dtype
     precision = precision or precision_for(src_dtype)
     products, parts = _PRODUCTS[precision]
@@ -260,7 +289,11 @@ def igemm_conv(x, pw, *, scale=None, stride=1, out_hw=None, dcoef=None, noise=No
         else:
             d.wgt = pw.data.data_ptr(); d.b_parts = pw.data.shape[0]
     else:
-        x_packed = _plugin.pack_activations(x, scale, pw.c_pad, parts)
+        if im is not None:
+            x_packed = _plugin.pack_im2col(x, scale, im['kw'], im['r'], im['pad_x'], im['pad_y'], parts)
+            h = x_packed.shape[2]
+        else:
+            x_packed = _plugin.pack_activations(x, scale, pw.c_pad, parts)
         keep.append(x_packed)
         d.act = x_packed.data_ptr(); d.a_parts = parts
         d.wgt = pw.data.data_ptr(); d.b_parts = pw.data.shape[0]
@@ -305,6 +338,7 @@ def igemm_conv(x, pw, *, scale=None, stride=1, out_hw=None, dcoef=None, noise=No
 
     d.n, d.h, d.w, d.c_pad = n, h, w, pw.c_pad
     d.kh, d.kw, d.pad_y, d.pad_x, d.stride = pw.kh, pw.kw, pw.pad_y, pw.pad_x, stride
+    d.dil_y = im['r'] if im is not None else 1
     d.conv_h, d.conv_w = conv_h, conv_w
     d.o, d.phases, d.phase_stride, d.o_rows, d.block_n, d.products = pw.o, pw.phases, pw.phase_stride, pw.o_rows, block_n, products
     def fptr(t):
@@ -334,8 +368,10 @@ def igemm_conv(x, pw, *, scale=None, stride=1, out_hw=None, dcoef=None, noise=No
         _plugin.conv2d_igemm(d, device)
         e1.record()
         # algorithmic FLOPs: 2*N*O*I*kh*kw*P; for the polyphase up=2 form the transposed conv's 9 taps per INPUT pixel
-        flops = 2.0 * n * pw.o * ic * (9 if pw.phases == 4 else pw.kh * pw.kw) * conv_h * conv_w
-        trace.append((f'igemm {ic}->{pw.o} k{pw.kh} {h}x{w}->{out_h}x{out_w} n{n} {precision}', flops, e0, e1))
+        real_ic, real_taps = (ic, 9 if pw.phases == 4 else pw.kh * pw.kw) if im is None else (pw.c_in // (im['r'] * im['kw']), im['kh'] * im['kw'])
+        flops = 2.0 * n * pw.o * real_ic * real_taps * conv_h * conv_w
+        kname = f'k{pw.kh}' if im is None else f"k{im['kh']}(im2col r{im['r']})"
+        trace.append((f'igemm {real_ic}->{pw.o} {kname} {h}x{w}->{out_h}x{out_w} n{n} {precision}', flops, e0, e1))
     else:
         _plugin.conv2d_igemm(d, device)
     return result

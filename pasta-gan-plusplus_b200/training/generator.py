@@ -161,7 +161,8 @@ class Spade_Conv2dLayer(torch.nn.Module):
 
     def conv_packed(self, xp, act='linear', gain=1.0, out_packed=None, out=None, accumulate=False):
         """the convolution alone on an operand-format input (pre-activation already applied by the producer of `xp`)"""
-        pw = conv2d_gradfix.packed_plain(self.weight, True, S._parts(), self.padding, self.padding, scale=self.weight_gain)
+        pw = conv2d_gradfix.packed_plain(self.weight, True, S._parts(), self.padding, self.padding, scale=self.weight_gain,
+                                         allow_im2col=xp.logical_hw is not None)
         return conv2d_gradfix.igemm_conv(xp, pw, act=act, gain=gain, out_packed=out_packed, out=out, accumulate=accumulate)
 
     def forward(self, x, gain=1, no_act=False, fused=True, impl='cuda'):
@@ -243,8 +244,13 @@ class Spade_ResBlockV4_512(torch.nn.Module):
             relu_gain = float(bias_act.activation_funcs['relu'].def_gain)
             if feats_packed is None:
                 conv2d_gradfix._init()
-                fc = denorm_feat.shape[1]
-                feats_packed = PackedAct(conv2d_gradfix._plugin.pack_activations(denorm_feat, None, -(-fc // 64) * 64, S._parts()), fc)
+                fc, fh, fw = denorm_feat.shape[1:]
+                r = conv2d_gradfix.im2col_rows(fc, 3, 3) if (fh >= 8 and fw >= 16) else 0
+                if r:       # 1-channel parsing map: all 9 taps of the three conv_mlp layers go into the channel dimension
+                    data = conv2d_gradfix._plugin.pack_im2col(denorm_feat, None, 3, r, 1, 1, S._parts())
+                    feats_packed = PackedAct(data, r * 3 * fc, 0, logical_hw=(fh, fw))
+                else:
+                    feats_packed = PackedAct(conv2d_gradfix._plugin.pack_activations(denorm_feat, None, -(-fc // 64) * 64, S._parts()), fc)
             x = self.conv(x, no_act=True, fused=True).contiguous()
             mean, rstd = self._stats(x)
             y = self.skip.conv_packed(self.spade_skip.fused_packed(x, mean, rstd, feats_packed, relu_gain * SQRT_HALF))

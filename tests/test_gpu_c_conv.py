@@ -217,3 +217,22 @@ def test_full_size_layers_against_library_conv_and_linearity():
                 assert rel_l2(y2, 2.5 * got) < 1e-5
     finally:
         torch.backends.cudnn.allow_tf32 = old
+
+
+@pytest.mark.parametrize('ic,k,pad,h,w', [(3, 7, 3, 40, 24), (1, 3, 1, 33, 47), (6, 3, 1, 16, 64), (3, 7, 3, 128, 128)])
+def test_few_channel_convs_through_row_group_im2col(ic, k, pad, h, w):
+    """7x7 RGB stem and 3x3 convs on 1..6 channels: pgpp_pack_im2col + dilated kh' x 1 GEMM (Conv2dLayer fused route)"""
+    synthesis = importlib.import_module('pgpp_b200.training.synthesis')
+    cg.fp32_precision = 'bf16x3'
+    torch.manual_seed(0)
+    layer = synthesis.Conv2dLayer(ic, 64, kernel_size=k, activation='relu').to(DEV)
+    layer.bias.data.normal_()
+    x = torch.randn(3, ic, h, w, device=DEV)
+    before = custom_ops.launch_count()
+    with torch.no_grad():
+        got = layer(x, fused=True)
+        want = layer(x.cpu().double(), fused=False, impl='ref') if False else None
+    assert custom_ops.launch_count() - before == 2          # one im2col pack + one GEMM
+    wgt = layer.weight.detach().cpu().double() * layer.weight_gain
+    want = ref_ops.bias_act(ref_ops.conv2d(x.cpu().double(), wgt, padding=pad), layer.bias.detach().cpu().double(), act='relu')
+    assert rel_l2(got, want) < TOL['bf16x3'], rel_l2(got, want)

@@ -234,3 +234,29 @@ def test_synthesis_chain_composition_path_matches_oracle_chain_on_cpu():
     assert img.shape == (n, 3, 64, 64) and parsing.shape == (n, 7, 64, 64) and tex.shape == (n, 3, 64, 64)
     assert rel_l2(img, rimg) < 1e-5 and rel_l2(parsing, rpars) < 1e-5 and rel_l2(tex, rtex) < 1e-5
     assert net.num_ws == 1 + 1 + 3 * 3 + 3
+
+
+@pytest.mark.parametrize('ic,k,pad', [(3, 7, 3), (1, 3, 1), (6, 3, 1)])
+def test_row_group_im2col_weights_reproduce_the_convolution(ic, k, pad):
+    """host logic of the few-channel route: torch emulation of pgpp_pack_im2col + the dilated kh' x 1 GEMM over the packed weights"""
+    g = torch.Generator().manual_seed(8)
+    x = torch.randn(2, ic, 10, 18, generator=g, dtype=torch.float64)
+    w = torch.randn(5, ic, k, k, generator=g)
+    pw = conv2d_gradfix.packed_plain(w, True, 3, pad, pad, allow_im2col=True)
+    im = pw.im2col
+    assert im is not None and im['r'] * k * ic <= 64 and pw.c_pad == 64 and pw.kw == 1
+    r, H, W = im['r'], 10, 18
+    xp = torch.nn.functional.pad(x, [pad, k, pad + pad, k + r])            # generous zero border; row index yy = y' + pad
+    packed = torch.zeros(2, H + pad, W, 64, dtype=torch.float64)
+    for yy in range(H + pad):
+        for ry in range(r):
+            for kx in range(k):
+                # x[n, c, yy - pad + ry, xx + kx - pad]
+                packed[:, yy, :, (ry * k + kx) * ic:(ry * k + kx + 1) * ic] = xp[:, :, yy + ry + pad, kx:kx + W].permute(0, 2, 1)
+    wt = pw.data.double().sum(0)[:, :5, :]                                  # [groups, o, 64]
+    out = torch.zeros(2, 5, H, W, dtype=torch.float64)
+    pk = torch.nn.functional.pad(packed, [0, 0, 0, 0, 0, 8])                # rows past H + pad read as zero (TMA OOB fill)
+    for t_ in range(pw.kh):
+        out += torch.einsum('nyxc,oc->noyx', pk[:, t_ * r:t_ * r + H], wt[t_])
+    want = torch.nn.functional.conv2d(x, w.double(), padding=pad)
+    assert rel_l2(out, want) < 3e-7
