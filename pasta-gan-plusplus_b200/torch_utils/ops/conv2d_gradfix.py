@@ -338,7 +338,7 @@ def igemm_conv(x, pw, *, scale=None, stride=1, out_hw=None, dcoef=None, noise=No
 
     d.n, d.h, d.w, d.c_pad = n, h, w, pw.c_pad
     d.kh, d.kw, d.pad_y, d.pad_x, d.stride = pw.kh, pw.kw, pw.pad_y, pw.pad_x, stride
-    d.dil_y = im['r'] if im is not None else 1
+    d.dil_y = im['r'] if (im is not None and pw.kh > 1) else 1
     d.conv_h, d.conv_w = conv_h, conv_w
     d.o, d.phases, d.phase_stride, d.o_rows, d.block_n, d.products = pw.o, pw.phases, pw.phase_stride, pw.o_rows, block_n, products
     def fptr(t):
