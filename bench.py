@@ -516,6 +516,28 @@ def run_ours(args):
             rate, ctimes = cpu_reference_rate(sd, net.num_ws, net.channels[8], 1, 3, threads=cores)
             cpu = {'value': rate, 'unit': 'images/s', 'cores': cores, 'kind': 'port',
                    'sample': f'best of 3 x batch 1 through oracle/ref_chain.py (torch CPU ops, {cores} threads; {sum(ctimes):.1f} s total)'}
+        batch1 = None
+        if gen_mode:
+            # BASELINE configs[0] shape (batch 1): eager launches vs CUDA-graph replay of the same forward
+            try:
+                gen = importlib.import_module('pgpp_b200.training.generator')
+                one = {k: v[:1].contiguous() for k, v in dev_in.items()}
+                for _ in range(3):
+                    run_generator(net, one)
+                def lat(fn, iters=20):
+                    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    torch.cuda.synchronize(); a.record()
+                    for _ in range(iters):
+                        fn()
+                    b.record(); torch.cuda.synchronize()
+                    return a.elapsed_time(b) / iters
+                eager_ms = lat(lambda: run_generator(net, one))
+                gg = gen.GraphedGenerator(net, one)
+                graph_ms = lat(lambda: gg(one))
+                batch1 = {'eager_ms': eager_ms, 'cuda_graph_ms': graph_ms, 'images_per_sec_cuda_graph': 1e3 / graph_ms,
+                          'note': 'batch-1 latency of the full generator (fp32-parity mode); graph replay is bit-identical to eager'}
+            except Exception as e:      # noqa: BLE001 - the extra measurement must never break the contract line
+                batch1 = {'error': f'{type(e).__name__}: {str(e)[:200]}'}
         imgs = batch * world * args.steps
         line = {
             'metric': 'generator_512px_images_per_sec' if gen_mode else 'synthesis_hot_path_images_per_sec',
@@ -538,6 +560,7 @@ def run_ours(args):
             'roofline': roof,
             'cpu_baseline': cpu,
             'parity_vs_cpu_oracle': parity,
+            'batch1': batch1,
             'bf16_mode': {'value': imgs / (bf16_ms * 1e-3), 'unit': 'images/s', 'ms_per_step': bf16_ms / args.steps, 'roofline': roof_bf16,
                           'parity_vs_cpu_oracle': parity_bf16,
                           'note': 'same step with single-product bf16 MMAs (per-layer rel error ~3e-3); reported separately, not the headline'},

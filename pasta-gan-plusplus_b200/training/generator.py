@@ -438,3 +438,38 @@ def build_generator(**overrides):
               synthesis_kwargs=dict(channel_base=32768, channel_max=512, num_fp16_res=3, conv_clamp=256, use_noise=True))
     kw.update(overrides)
     return GeneratorFull_v20(**kw)
+
+
+class GraphedGenerator:
+    """CUDA-graph replay of `GeneratorFull_v20.forward` for fixed input shapes (inference).  Every kernel of this package is
+    launched on the current stream with host-encoded TMA descriptors, so the whole forward (about 460 launches) captures into
+    one graph; replay removes the ~35 us/launch Python + ctypes overhead that bounds small batches (batch 1: BASELINE
+    configs[0])."""
+
+    def __init__(self, G, example_inputs, gt_parsing=None, warmup=3, **forward_kwargs):
+        self.G = G
+        self.static_in = {k: v.clone() for k, v in example_inputs.items()}
+        self.static_gt = None if gt_parsing is None else gt_parsing.clone()
+        self.kwargs = dict(noise_mode='const', **forward_kwargs)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side), torch.no_grad():
+            for _ in range(warmup):         # packs weights, fills caches, sizes the allocator pool
+                self._run()
+        torch.cuda.current_stream().wait_stream(side)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph), torch.no_grad():
+            self.static_out = self._run()
+
+    def _run(self):
+        x = self.static_in
+        z = torch.zeros(x['c'].shape[0], 0, device=x['c'].device)
+        return self.G(z, x['c'], x['retain'], x['pose'], x['denorm_upper'], x['denorm_lower'], x['denorm_upper_mask'],
+                      x['denorm_lower_mask'], gt_parsing=self.static_gt, **self.kwargs)
+
+    def __call__(self, inputs):
+        for k, v in inputs.items():
+            if k in self.static_in:
+                self.static_in[k].copy_(v, non_blocking=True)
+        self.graph.replay()
+        return self.static_out

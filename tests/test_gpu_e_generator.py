@@ -76,3 +76,15 @@ def test_composition_route_on_gpu_and_batch_independence(generator_and_inputs):
         # not bit-identical: library reductions (instance norm, sums) pick batch-size dependent algorithms; a kernel-level
         # cross-sample leak (e.g. resident weights reloaded too early) shows up as >= 1e-3
         assert float((x[:1] - y).norm() / y.norm()) < 2e-4
+
+
+def test_cuda_graph_replay_is_bit_identical(generator_and_inputs):
+    G, inp = generator_and_inputs
+    x = {k: v for k, v in inp.items() if k != 'gt_parsing'}
+    eager = _run(G, inp, gt=False)
+    gg = gen.GraphedGenerator(G, x)
+    for _ in range(2):
+        out = gg(x)
+    torch.cuda.synchronize()
+    for a, b in zip(out, eager):
+        assert torch.equal(a, b)
