@@ -168,6 +168,35 @@ typedef struct {
  * loads), persistent over the SMs, with the epilogue above fused. */
 PGPP_API int pgpp_conv2d_igemm(const pgpp_conv_desc* desc, void* stream);
 
+/* ---- weight gradient (conv2d_gradfix.py:135-142, Conv2dGradWeight.forward: replaces
+ * aten::cudnn_convolution_backward_weight / cudnn_convolution_transpose_backward_weight) ----
+ *
+ *   G[a, b, ky, kx] = sum_{n, y, x} S[n, a, y, x] * L[n, b, y*stride + ky - pad_y, x*stride + kx - pad_x]
+ *
+ * conv2d:           S = grad_output, L = input        -> G = dW[O, I, kh, kw]
+ * conv_transpose2d: S = input,       L = grad_output  -> G = dW[I, O, kh, kw]
+ * Both operands are channels-innermost packed activations (pgpp_pack_activations: bf16 [parts][N][H][W][c_pad],
+ * channels beyond C zero), the same format the forward kernel consumes. */
+
+typedef struct pgpp_wgrad_desc {
+    const void* small;              /* S: bf16 [s_parts][N][hs][ws][s_pixel_stride] */
+    const void* large;              /* L: bf16 [l_parts][N][hl][wl][l_pixel_stride] */
+    int32_t s_parts, l_parts;
+    int32_t n;
+    int32_t ca, ca_pad, s_pixel_stride;     /* channels of S, padded count (multiple of 64), elements between pixels (0: ca_pad) */
+    int32_t hs, ws;
+    int32_t cb, cb_pad, l_pixel_stride;
+    int32_t hl, wl;
+    int32_t kh, kw, pad_y, pad_x;
+    int32_t stride;                 /* 1 or 2 */
+    int32_t products;               /* 1 (bf16), 3 (2-part split) or 6 (3-part split) */
+    float* out;                     /* G: float32 [ca][cb][kh][kw], overwritten */
+    float* workspace;               /* float32 [kh*kw][ca][cb_pad] scratch (split-K partial sums land here), 16-byte aligned */
+} pgpp_wgrad_desc;
+
+/* Split-K GEMM over the pixels on the 5th-gen tensor cores (tcgen05.mma, TMEM accumulators, TMA operand loads). */
+PGPP_API int pgpp_conv2d_wgrad(const pgpp_wgrad_desc* desc, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

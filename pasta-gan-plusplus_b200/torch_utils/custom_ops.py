@@ -79,13 +79,31 @@ def load_library():
     lib.pgpp_spade_modulate_pack.argtypes = [vp, vp, vp, vp, vp, i64, vp, i32, i32, i32, i32, i32, i32, f32, vp]
     lib.pgpp_conv2d_igemm.restype = i32
     lib.pgpp_conv2d_igemm.argtypes = [ctypes.POINTER(ConvDesc), vp]
+    lib.pgpp_conv2d_wgrad.restype = i32
+    lib.pgpp_conv2d_wgrad.argtypes = [ctypes.POINTER(WgradDesc), vp]
     _lib = lib
     return lib
 
 
 EXPORTED_SYMBOLS = ('pgpp_version', 'pgpp_last_error', 'pgpp_launch_count', 'pgpp_bias_act', 'pgpp_upfirdn2d',
                     'pgpp_modconv_demod_coefs', 'pgpp_pack_activations', 'pgpp_pack_activations_slice', 'pgpp_modulate_weights',
-                    'pgpp_spade_modulate_pack', 'pgpp_pack_im2col', 'pgpp_conv2d_igemm')
+                    'pgpp_spade_modulate_pack', 'pgpp_pack_im2col', 'pgpp_conv2d_igemm', 'pgpp_conv2d_wgrad')
+
+
+class WgradDesc(ctypes.Structure):
+    """mirror of pgpp_wgrad_desc (include/pgpp.h)"""
+    _fields_ = [
+        ('small', ctypes.c_void_p), ('large', ctypes.c_void_p),
+        ('s_parts', ctypes.c_int32), ('l_parts', ctypes.c_int32),
+        ('n', ctypes.c_int32),
+        ('ca', ctypes.c_int32), ('ca_pad', ctypes.c_int32), ('s_pixel_stride', ctypes.c_int32),
+        ('hs', ctypes.c_int32), ('ws', ctypes.c_int32),
+        ('cb', ctypes.c_int32), ('cb_pad', ctypes.c_int32), ('l_pixel_stride', ctypes.c_int32),
+        ('hl', ctypes.c_int32), ('wl', ctypes.c_int32),
+        ('kh', ctypes.c_int32), ('kw', ctypes.c_int32), ('pad_y', ctypes.c_int32), ('pad_x', ctypes.c_int32),
+        ('stride', ctypes.c_int32), ('products', ctypes.c_int32),
+        ('out', ctypes.c_void_p), ('workspace', ctypes.c_void_p),
+    ]
 
 
 def launch_count():
@@ -287,6 +305,13 @@ class _ConvPlugin:
         with torch.cuda.device(device):
             stream = ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
             _check(lib.pgpp_conv2d_igemm(ctypes.byref(desc), stream))
+
+    @staticmethod
+    def conv2d_wgrad(desc, device):
+        lib = load_library()
+        with torch.cuda.device(device):
+            stream = ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+            _check(lib.pgpp_conv2d_wgrad(ctypes.byref(desc), stream))
 
 
 _PLUGINS = {'bias_act_plugin': _BiasActPlugin, 'upfirdn2d_plugin': _Upfirdn2dPlugin, 'conv2d_plugin': _ConvPlugin}

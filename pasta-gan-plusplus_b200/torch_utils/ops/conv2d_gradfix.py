@@ -16,8 +16,8 @@ Switches
                              'bf16x2' 3 products of 2-term splits (rel ~1e-5; default, within the 1e-4 bar)
                              'bf16'   1 product (rel ~3e-3; what bf16/fp16 tensors always use)
 
-Round-1 gap: the weight gradient still calls the library (`aten::convolution_backward`); everything
-else on the path is this repo's kernels.
+The weight gradient (conv2d_gradfix.py:135-142) is the split-K tcgen05 GEMM over the pixels of
+csrc/conv_wgrad.cu (`pgpp_conv2d_wgrad`); no library convolution is called anywhere on the path.
 """
 import contextlib
 import ctypes
@@ -422,6 +422,43 @@ def _forward_conv_transpose(x, weight, bias, stride, padding, output_padding):
     return igemm_conv(x, pw, stride=1, bias=bias, out_hw=(out_h, out_w))
 
 
+def weight_gradient(grad_output, input, weight_shape, stride, padding, transpose, precision=None):
+    """dW of conv2d (transpose=False, weight [O, I, kh, kw]) or conv_transpose2d (transpose=True, weight [I, O, kh, kw]):
+    what Conv2dGradWeight.forward (conv2d_gradfix.py:135-142) gets from cuDNN, computed by pgpp_conv2d_wgrad as
+    G[a, b, ky, kx] = sum S[n, a, y, x] * L[n, b, y*s + ky - p, x*s + kx - p] with (S, L) = (grad_output, input) for the
+    convolution and (input, grad_output) for the transposed convolution."""
+    _init()
+    precision = precision or precision_for(input.dtype)
+    products, parts = _PRODUCTS[precision]
+    small, large = (input, grad_output) if transpose else (grad_output, input)
+    ca, cb, kh, kw = (int(v) for v in weight_shape)
+    n = int(small.shape[0])
+    assert small.shape[1] == ca and large.shape[1] == cb and large.shape[0] == n
+    ca_pad, cb_pad = _round_up(ca, 64), _round_up(cb, 64)
+    s_op = _plugin.pack_activations(small, None, ca_pad, parts)
+    l_op = _plugin.pack_activations(large, None, cb_pad, parts)
+    out = torch.empty([ca, cb, kh, kw], dtype=torch.float32, device=input.device)
+    d = custom_ops.WgradDesc()
+    d.small = s_op.data_ptr(); d.large = l_op.data_ptr()
+    d.s_parts = parts; d.l_parts = parts
+    d.n = n
+    d.ca = ca; d.ca_pad = ca_pad; d.s_pixel_stride = ca_pad; d.hs = int(small.shape[2]); d.ws = int(small.shape[3])
+    d.cb = cb; d.cb_pad = cb_pad; d.l_pixel_stride = cb_pad; d.hl = int(large.shape[2]); d.wl = int(large.shape[3])
+    d.kh = kh; d.kw = kw; d.pad_y = int(padding[0]); d.pad_x = int(padding[1])
+    d.stride = int(stride); d.products = products
+    workspace = torch.empty([kh * kw, ca, cb_pad], dtype=torch.float32, device=input.device)
+    d.out = out.data_ptr(); d.workspace = workspace.data_ptr()
+    if trace is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+    _plugin.conv2d_wgrad(d, input.device)
+    if trace is not None:
+        e1.record()
+        flops = 2.0 * n * small.shape[2] * small.shape[3] * ca * cb * kh * kw
+        trace.append((f'wgrad {ca}x{cb} k{kh} {small.shape[2]}x{small.shape[3]} s{stride} n{n} {precision}', flops, e0, e1))
+    return out if input.dtype == torch.float32 else out.to(input.dtype)
+
+
 _conv2d_gradfix_cache = dict()
 
 
@@ -487,13 +524,7 @@ def _conv2d_gradfix(transpose, weight_shape, stride, padding, output_padding, di
     class Conv2dGradWeight(torch.autograd.Function):
         @staticmethod
         def forward(ctx, grad_output, input):
-            # Library call (round-1 gap, see module docstring): weight gradient of the (transposed) convolution.
-            if not transpose:
-                gw = torch.ops.aten.convolution_backward(grad_output, input, torch.empty(weight_shape, device=input.device, dtype=input.dtype),
-                                                         None, stride, padding, dilation, False, [0, 0], groups, [False, True, False])[1]
-            else:
-                gw = torch.ops.aten.convolution_backward(grad_output, input, torch.empty(weight_shape, device=input.device, dtype=input.dtype),
-                                                         None, stride, padding, dilation, True, output_padding, groups, [False, True, False])[1]
+            gw = weight_gradient(grad_output, input, weight_shape, stride[0], padding, transpose)
             assert gw.shape == weight_shape
             ctx.save_for_backward(grad_output, input)
             return gw
