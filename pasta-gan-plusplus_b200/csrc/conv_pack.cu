@@ -24,49 +24,104 @@ __device__ __forceinline__ void split_store(float v, __nv_bfloat16* dst, long lo
     }
 }
 
-// x has unit stride along W (NCHW-like): transpose 64 channels x 32 pixels through shared memory so
-// that both the read (along W) and the write (along C) are coalesced.
-template <class T>
-__global__ void __launch_bounds__(256) pack_nchw_kernel(PackArgs p, int w_tiles, int c_tiles) {
-    __shared__ float tile[64][33];
-    long long b = blockIdx.x;
-    const int wt = (int)(b % w_tiles); b /= w_tiles;
-    const int ct = (int)(b % c_tiles); b /= c_tiles;
-    const int y = (int)(b % p.h);
-    const int n = (int)(b / p.h);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int x0 = wt * 32, c0 = ct * 64;
-    const T* src = (const T*)p.x + n * p.s_n + y * p.s_h;
+// ---- 64-channel x 128-pixel transposing tile shared by pack_nchw_kernel and spade_pack_kernel -------------------------
+// The source is pixel-contiguous (NCHW-like), the destination channel-contiguous.  A CTA of 256 threads owns 64 channels of
+// 128 pixels (tw x rows block of one image, tw a power of two).  Thread (warp w, lane l) loads channels 8w..8w+7 of pixels
+// 4l..4l+3 (one 128-bit load per channel: a warp reads 512 contiguous bytes of one channel row), converts them to the bf16
+// expansion in registers - 8 consecutive channels of one pixel are one 16-byte packet of the destination - and parks the
+// packets in shared memory (XOR-swizzled by the lane so both sides are bank-conflict free); after one barrier 8 consecutive
+// threads write the 128-byte channel row of a pixel with one 128-bit store each.
+struct TileGeom { int log_tw, x_tiles, y_tiles, c_tiles; };
+
+__device__ __forceinline__ uint4 split_packet(float (&v)[8][4], int k) {
+    __align__(16) __nv_bfloat16 q[8];
     #pragma unroll
-    for (int i = 0; i < 8; i++) {
-        const int c = c0 + warp * 8 + i;
-        float v = 0.f;
-        if (c < p.c && x0 + lane < p.w) {
-            v = (float)to_acc<T>(src[c * p.s_c + (x0 + lane)]);
-            if (p.scale) v *= p.scale[n * p.c + c];
-        }
-        tile[warp * 8 + i][lane] = v;
+    for (int j = 0; j < 8; j++) { q[j] = __float2bfloat16_rn(v[j][k]); v[j][k] -= __bfloat162float(q[j]); }
+    return *reinterpret_cast<const uint4*>(q);
+}
+
+// writes the tile held in v (see above) to out[part][n][y][x][c_off + c0 ...]; sm = parts * 128 * 8 packets
+__device__ __forceinline__ void emit_tile(float (&v)[8][4], uint4* sm, int parts, __nv_bfloat16* out, long long part_stride,
+                                          int n, int h, int w, int y0, int x0, int log_tw, int c0, int c_lim, int c_total, int c_off) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int part = 0; part < parts; part++) {
+        #pragma unroll
+        for (int k = 0; k < 4; k++)
+            sm[(part * 128 + 4 * lane + k) * 8 + (warp ^ (lane & 7))] = split_packet(v, k);
     }
     __syncthreads();
-    // write phase: a warp covers 4 pixels x 8 groups of 8 channels, so every pixel's 128-byte channel row is written
-    // by 8 consecutive lanes with one 128-bit store per part
-    #pragma unroll
-    for (int it = 0; it < 1; it++) {
-        const int px = warp * 4 + (lane >> 3);
-        const int cg = lane & 7;
-        if (x0 + px < p.w && c0 + cg * 8 < p.c_pad) {
-            float v[8];
-            #pragma unroll
-            for (int j = 0; j < 8; j++) v[j] = tile[cg * 8 + j][px];
-            __nv_bfloat16* dst = p.out + (((long long)n * p.h + y) * p.w + (x0 + px)) * p.c_total + p.c_off + c0 + cg * 8;
-            for (int part = 0; part < p.parts; part++) {
-                __align__(16) __nv_bfloat16 q[8];
-                #pragma unroll
-                for (int j = 0; j < 8; j++) { q[j] = __float2bfloat16_rn(v[j]); v[j] -= __bfloat162float(q[j]); }
-                *reinterpret_cast<int4*>(dst + part * p.part_stride) = *reinterpret_cast<const int4*>(q);
+    const int tw_mask = (1 << log_tw) - 1;
+    for (int part = 0; part < parts; part++) {
+        #pragma unroll
+        for (int it = 0; it < 4; it++) {
+            const int item = it * 256 + threadIdx.x;
+            const int px = item >> 3, ch = item & 7;
+            const int y = y0 + (px >> log_tw), x = x0 + (px & tw_mask);
+            if (y < h && x < w && c0 + ch * 8 < c_lim) {
+                __nv_bfloat16* dst = out + part * part_stride + (((long long)n * h + y) * w + x) * c_total + c_off + c0 + ch * 8;
+                *reinterpret_cast<uint4*>(dst) = sm[(part * 128 + px) * 8 + (ch ^ ((px >> 2) & 7))];
             }
         }
     }
+}
+
+__device__ __forceinline__ void decode_tile_block(const TileGeom& g, int& xt, int& yt, int& ct, int& n) {
+    long long b = blockIdx.x;
+    xt = (int)(b % g.x_tiles); b /= g.x_tiles;
+    ct = (int)(b % g.c_tiles); b /= g.c_tiles;
+    yt = (int)(b % g.y_tiles);
+    n = (int)(b / g.y_tiles);
+}
+
+static TileGeom tile_geometry(int h, int w, int c_pad) {
+    int tw;
+    if (w % 128 == 0) tw = 128; else if (w % 64 == 0) tw = 64; else if (w % 32 == 0) tw = 32; else if (w % 16 == 0) tw = 16;
+    else { tw = 16; while (tw < w && tw < 128) tw <<= 1; }
+    TileGeom g;
+    g.log_tw = 0; while ((1 << g.log_tw) < tw) g.log_tw++;
+    const int rows = 128 / tw;
+    g.x_tiles = (w + tw - 1) / tw;
+    g.y_tiles = (h + rows - 1) / rows;
+    g.c_tiles = (c_pad + 63) / 64;
+    return g;
+}
+
+// VEC: float source, W % 4 == 0, all strides and the base pointer 16-byte aligned -> one 128-bit load per channel
+template <class T, bool VEC>
+__global__ void __launch_bounds__(256) pack_nchw_kernel(PackArgs p, TileGeom g) {
+    extern __shared__ uint4 sm_packets[];
+    int xt, yt, ct, n;
+    decode_tile_block(g, xt, yt, ct, n);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int tw_mask = (1 << g.log_tw) - 1;
+    const int x0 = xt << g.log_tw, y0 = yt * (128 >> g.log_tw), c0 = ct * 64;
+    const int y = y0 + ((4 * lane) >> g.log_tw), x = x0 + ((4 * lane) & tw_mask);
+    const T* src = (const T*)p.x + n * p.s_n + y * p.s_h + x;
+    float v[8][4];
+    #pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const int c = c0 + warp * 8 + i;
+        #pragma unroll
+        for (int k = 0; k < 4; k++) v[i][k] = 0.f;
+        if (c < p.c && y < p.h) {
+            if (VEC) {
+                if (x < p.w) {
+                    const float4 q = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(src) + c * p.s_c);
+                    v[i][0] = q.x; v[i][1] = q.y; v[i][2] = q.z; v[i][3] = q.w;
+                }
+            } else {
+                #pragma unroll
+                for (int k = 0; k < 4; k++)
+                    if (x + k < p.w) v[i][k] = (float)to_acc<T>(src[c * p.s_c + k]);
+            }
+            if (p.scale) {
+                const float sc = p.scale[n * p.c + c];
+                #pragma unroll
+                for (int k = 0; k < 4; k++) v[i][k] *= sc;
+            }
+        }
+    }
+    emit_tile(v, sm_packets, p.parts, p.out, p.part_stride, n, p.h, p.w, y0, x0, g.log_tw, c0, p.c_pad, p.c_total, p.c_off);
 }
 
 // any strides (channels_last inputs are coalesced here): one thread per (pixel, channel)
@@ -90,10 +145,13 @@ __global__ void __launch_bounds__(256) pack_generic_kernel(PackArgs p, long long
 template <class T>
 static int launch_pack(const PackArgs& p, cudaStream_t stream) {
     if (p.s_w == 1 && p.s_c != 1) {
-        const int w_tiles = (p.w + 31) / 32, c_tiles = (p.c_pad + 63) / 64;
-        const long long blocks = (long long)w_tiles * c_tiles * p.h * p.n;
+        const TileGeom g = tile_geometry(p.h, p.w, p.c_pad);
+        const long long blocks = (long long)g.x_tiles * g.y_tiles * g.c_tiles * p.n;
         PGPP_REQUIRE(blocks <= 2147483647LL, "activation tensor too large to pack");
-        pack_nchw_kernel<T><<<(unsigned)blocks, 256, 0, stream>>>(p, w_tiles, c_tiles);
+        const size_t smem = (size_t)p.parts * 128 * 8 * sizeof(uint4);
+        const bool vec = sizeof(T) == 4 && p.w % 4 == 0 && p.s_c % 4 == 0 && p.s_h % 4 == 0 && p.s_n % 4 == 0 && ((uintptr_t)p.x & 15) == 0;
+        if (vec) pack_nchw_kernel<float, true><<<(unsigned)blocks, 256, smem, stream>>>(p, g);
+        else pack_nchw_kernel<T, false><<<(unsigned)blocks, 256, smem, stream>>>(p, g);
     } else {
         const long long total = (long long)p.n * p.h * p.w * p.c_pad;
         long long blocks = (total + 255) / 256;
@@ -112,35 +170,56 @@ struct Im2colArgs {
     long long s_n, s_c, s_h, s_w, part_stride;
 };
 
-// one thread per (packed pixel, group of 8 channels): gathers up to 8 shifted input samples (L1/L2-cached reads of a tiny
-// tensor) and writes one 128-bit store per part; 8 consecutive threads cover the 128-byte channel row of a pixel
+// One CTA per 128-pixel segment of one packed row: the r * C source rows it needs (with the kw - 1 halo) are staged in
+// shared memory with coalesced reads, then 8 consecutive threads assemble the 128-byte channel row of a pixel through a
+// channel -> (row, column offset) table and write one 128-bit store per part.
+constexpr int kIm2colTile = 128;
+
 template <class T>
-__global__ void __launch_bounds__(256) im2col_kernel(Im2colArgs p, long long total) {
-    const int used = p.r * p.kw * p.c;
-    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
-        const int cg = (int)(e & 7);
-        long long q = e >> 3;
-        const int x = (int)(q % p.w); q /= p.w;
-        const int yy = (int)(q % p.hp);
-        const int n = (int)(q / p.hp);
+__global__ void __launch_bounds__(256) im2col_kernel(Im2colArgs p, int x_tiles) {
+    extern __shared__ float sm_rows[];                       // [r * c][kIm2colTile + kw - 1], then the table
+    const int pitch = kIm2colTile + p.kw - 1;
+    const int n_rows = p.r * p.c;
+    int* lut = reinterpret_cast<int*>(sm_rows + n_rows * pitch);
+    long long b = blockIdx.x;
+    const int xt = (int)(b % x_tiles); b /= x_tiles;
+    const int yy = (int)(b % p.hp);
+    const int n = (int)(b / p.hp);
+    const int x0 = xt * kIm2colTile;
+    if (threadIdx.x < 64) {
+        const int ch = threadIdx.x;
+        int off = -1;
+        if (ch < p.r * p.kw * p.c) {
+            const int c = ch % p.c, t = ch / p.c;
+            const int kx = t % p.kw, ry = t / p.kw;
+            off = (ry * p.c + c) * pitch + kx;
+        }
+        lut[ch] = off;
+    }
+    for (int idx = threadIdx.x; idx < n_rows * pitch; idx += 256) {
+        const int row = idx / pitch, col = idx - row * pitch;
+        const int ry = row / p.c, c = row - ry * p.c;
+        const int iy = yy - p.pad_y + ry, ix = x0 + col - p.pad_x;
+        float val = 0.f;
+        if (iy >= 0 && iy < p.h && ix >= 0 && ix < p.w) {
+            val = (float)to_acc<T>(((const T*)p.x)[n * p.s_n + c * p.s_c + iy * p.s_h + ix * p.s_w]);
+            if (p.scale) val *= p.scale[n * p.c + c];
+        }
+        sm_rows[idx] = val;
+    }
+    __syncthreads();
+    #pragma unroll
+    for (int it = 0; it < kIm2colTile * 8 / 256; it++) {
+        const int item = it * 256 + threadIdx.x;
+        const int px = item >> 3, cg = item & 7;
+        if (x0 + px >= p.w) continue;
         float v[8];
         #pragma unroll
         for (int j = 0; j < 8; j++) {
-            const int ch = cg * 8 + j;
-            float val = 0.f;
-            if (ch < used) {
-                const int c = ch % p.c;
-                const int t = ch / p.c;
-                const int kx = t % p.kw, ry = t / p.kw;
-                const int iy = yy - p.pad_y + ry, ix = x + kx - p.pad_x;
-                if (iy >= 0 && iy < p.h && ix >= 0 && ix < p.w) {
-                    val = (float)to_acc<T>(((const T*)p.x)[n * p.s_n + c * p.s_c + iy * p.s_h + ix * p.s_w]);
-                    if (p.scale) val *= p.scale[n * p.c + c];
-                }
-            }
-            v[j] = val;
+            const int off = lut[cg * 8 + j];
+            v[j] = off >= 0 ? sm_rows[off + px] : 0.f;
         }
-        __nv_bfloat16* dst = p.out + (((long long)n * p.hp + yy) * p.w + x) * 64 + cg * 8;
+        __nv_bfloat16* dst = p.out + (((long long)n * p.hp + yy) * p.w + x0 + px) * 64 + cg * 8;
         for (int part = 0; part < p.parts; part++) {
             __align__(16) __nv_bfloat16 qv[8];
             #pragma unroll
@@ -155,46 +234,49 @@ struct SpadeArgs {
     int n, c, h, w, c_pad, parts; long long gb_stride_n, part_stride; float pre_gain;
 };
 
-// same 64-channel x 32-pixel transpose tile as pack_nchw_kernel, with the SPADE arithmetic applied on the way in
-__global__ void __launch_bounds__(256) spade_pack_kernel(SpadeArgs p, int w_tiles, int c_tiles) {
-    __shared__ float tile[64][33];
-    long long b = blockIdx.x;
-    const int wt = (int)(b % w_tiles); b /= w_tiles;
-    const int ct = (int)(b % c_tiles); b /= c_tiles;
-    const int y = (int)(b % p.h);
-    const int n = (int)(b / p.h);
+// same 64-channel x 128-pixel transposing tile as pack_nchw_kernel, with the SPADE arithmetic applied on the way in
+template <bool VEC>
+__global__ void __launch_bounds__(256) spade_pack_kernel(SpadeArgs p, TileGeom g) {
+    extern __shared__ uint4 sm_packets[];
+    int xt, yt, ct, n;
+    decode_tile_block(g, xt, yt, ct, n);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int x0 = wt * 32, c0 = ct * 64;
+    const int tw_mask = (1 << g.log_tw) - 1;
+    const int x0 = xt << g.log_tw, y0 = yt * (128 >> g.log_tw), c0 = ct * 64;
+    const int y = y0 + ((4 * lane) >> g.log_tw), x = x0 + ((4 * lane) & tw_mask);
     const long long plane = (long long)p.h * p.w;
+    float v[8][4];
     #pragma unroll
     for (int i = 0; i < 8; i++) {
         const int c = c0 + warp * 8 + i;
-        float v = 0.f;
-        if (c < p.c && x0 + lane < p.w) {
-            const long long off = (long long)c * plane + (long long)y * p.w + (x0 + lane);
-            const float xv = p.x[(long long)n * p.c * plane + off];
-            const float g = p.gamma[n * p.gb_stride_n + off], bt = p.beta[n * p.gb_stride_n + off];
-            const float nv = (xv - p.mean[n * p.c + c]) * p.rstd[n * p.c + c];
-            v = fmaf(nv, 1.f + g, bt);
-            if (p.pre_gain > 0.f) v = fmaxf(v, 0.f) * p.pre_gain;
-        }
-        tile[warp * 8 + i][lane] = v;
-    }
-    __syncthreads();
-    const int px = warp * 4 + (lane >> 3);
-    const int cg = lane & 7;
-    if (x0 + px < p.w && c0 + cg * 8 < p.c_pad) {
-        float v[8];
         #pragma unroll
-        for (int j = 0; j < 8; j++) v[j] = tile[cg * 8 + j][px];
-        __nv_bfloat16* dst = p.out + (((long long)n * p.h + y) * p.w + (x0 + px)) * p.c_pad + c0 + cg * 8;
-        for (int part = 0; part < p.parts; part++) {
-            __align__(16) __nv_bfloat16 q[8];
+        for (int k = 0; k < 4; k++) v[i][k] = 0.f;
+        if (c < p.c && y < p.h && x < p.w) {
+            const long long off = (long long)c * plane + (long long)y * p.w + x;
+            const float* xp = p.x + (long long)n * p.c * plane + off;
+            const float* gp = p.gamma + n * p.gb_stride_n + off;
+            const float* bp = p.beta + n * p.gb_stride_n + off;
+            float xv[4] = {0.f, 0.f, 0.f, 0.f}, gv[4] = {0.f, 0.f, 0.f, 0.f}, bv[4] = {0.f, 0.f, 0.f, 0.f};
+            if (VEC) {
+                const float4 a = *reinterpret_cast<const float4*>(xp), b = *reinterpret_cast<const float4*>(gp), d = *reinterpret_cast<const float4*>(bp);
+                xv[0] = a.x; xv[1] = a.y; xv[2] = a.z; xv[3] = a.w;
+                gv[0] = b.x; gv[1] = b.y; gv[2] = b.z; gv[3] = b.w;
+                bv[0] = d.x; bv[1] = d.y; bv[2] = d.z; bv[3] = d.w;
+            } else {
+                #pragma unroll
+                for (int k = 0; k < 4; k++)
+                    if (x + k < p.w) { xv[k] = xp[k]; gv[k] = gp[k]; bv[k] = bp[k]; }
+            }
+            const float mu = p.mean[n * p.c + c], rs = p.rstd[n * p.c + c];
             #pragma unroll
-            for (int j = 0; j < 8; j++) { q[j] = __float2bfloat16_rn(v[j]); v[j] -= __bfloat162float(q[j]); }
-            *reinterpret_cast<int4*>(dst + part * p.part_stride) = *reinterpret_cast<const int4*>(q);
+            for (int k = 0; k < 4; k++) {
+                float r = fmaf((xv[k] - mu) * rs, 1.f + gv[k], bv[k]);
+                if (p.pre_gain > 0.f) r = fmaxf(r, 0.f) * p.pre_gain;
+                v[i][k] = (VEC || x + k < p.w) ? r : 0.f;
+            }
         }
     }
+    emit_tile(v, sm_packets, p.parts, p.out, p.part_stride, n, p.h, p.w, y0, x0, g.log_tw, c0, p.c_pad, p.c_pad, 0);
 }
 
 // one CTA per output channel: W2[i] = sum_t w[o,i,t]^2 in shared memory, then one warp per sample
@@ -307,12 +389,14 @@ extern "C" int pgpp_pack_im2col(const void* x, const int64_t size[4], const int6
     p.kw = kw; p.r = r; p.pad_x = pad_x; p.pad_y = pad_y; p.parts = parts;
     p.s_n = stride[0]; p.s_c = stride[1]; p.s_h = stride[2]; p.s_w = stride[3];
     p.part_stride = (long long)p.n * p.hp * p.w * 64;
-    const long long total = (long long)p.n * p.hp * p.w * 8;
-    if (total == 0) return PGPP_OK;
-    long long blocks = (total + 255) / 256;
+    if ((long long)p.n * p.hp * p.w == 0) return PGPP_OK;
+    const int x_tiles = (p.w + kIm2colTile - 1) / kIm2colTile;
+    const long long blocks = (long long)x_tiles * p.hp * p.n;
+    PGPP_REQUIRE(blocks <= 2147483647LL, "tensor too large");
+    const size_t smem = sizeof(float) * (size_t)(r * p.c) * (kIm2colTile + kw - 1) + 64 * sizeof(int);
+    PGPP_REQUIRE(smem <= 48 * 1024, "im2col row staging does not fit shared memory");
     cudaStream_t s = (cudaStream_t)stream;
-#define PGPP_IM2COL(T) { const long long cap = (long long)sm_count() * occupancy_of(im2col_kernel<T>, 256, 0); \
-                         if (blocks > cap) blocks = cap; im2col_kernel<T><<<(unsigned)blocks, 256, 0, s>>>(p, total); }
+#define PGPP_IM2COL(T) im2col_kernel<T><<<(unsigned)blocks, 256, smem, s>>>(p, x_tiles);
     switch (dtype) {
         case PGPP_F32:  PGPP_IM2COL(float) break;
         case PGPP_F16:  PGPP_IM2COL(__half) break;
@@ -335,10 +419,13 @@ extern "C" int pgpp_spade_modulate_pack(const float* x, const float* mean, const
     p.x = x; p.mean = mean; p.rstd = rstd; p.gamma = gamma; p.beta = beta; p.out = (__nv_bfloat16*)out;
     p.n = n; p.c = c; p.h = h; p.w = w; p.c_pad = c_pad; p.parts = parts; p.gb_stride_n = gb_stride_n;
     p.part_stride = (long long)n * h * w * c_pad; p.pre_gain = pre_gain;
-    const int w_tiles = (w + 31) / 32, c_tiles = (c_pad + 63) / 64;
-    const long long blocks = (long long)w_tiles * c_tiles * h * n;
+    const TileGeom g = tile_geometry(h, w, c_pad);
+    const long long blocks = (long long)g.x_tiles * g.y_tiles * g.c_tiles * n;
     PGPP_REQUIRE(blocks <= 2147483647LL, "tensor too large");
-    spade_pack_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(p, w_tiles, c_tiles);
+    const size_t smem = (size_t)parts * 128 * 8 * sizeof(uint4);
+    const bool vec = w % 4 == 0 && gb_stride_n % 4 == 0 && (((uintptr_t)x | (uintptr_t)gamma | (uintptr_t)beta) & 15) == 0;
+    if (vec) spade_pack_kernel<true><<<(unsigned)blocks, 256, smem, (cudaStream_t)stream>>>(p, g);
+    else spade_pack_kernel<false><<<(unsigned)blocks, 256, smem, (cudaStream_t)stream>>>(p, g);
     count_launch();
     PGPP_CUDA_OK(cudaGetLastError());
     return PGPP_OK;
