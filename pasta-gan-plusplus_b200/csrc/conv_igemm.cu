@@ -170,7 +170,7 @@ __device__ __forceinline__ void epilogue_general(const IgemmParams& p, const Til
 
 // Fast epilogue: one sample per tile, per-column (scale, shift) staged in shared memory with the gain already folded in
 // (linear / relu / lrelu are positively homogeneous).
-template <int A, class OT, bool CLAMP>
+template <int A, class OT, bool CLAMP, bool ACC>
 __device__ __forceinline__ void epilogue_fast(const IgemmParams& p, const TileCoord tc, uint32_t tmem_tile, const PixelCoord pc,
                                               int col_begin, int col_end, const float2* s_cs) {
     const int x = tc.x0 + pc.px, y = tc.y0 + pc.py, n = tc.n0;
@@ -190,6 +190,14 @@ __device__ __forceinline__ void epilogue_fast(const IgemmParams& p, const TileCo
         if (p.noise) nz = __ldg(p.noise + n * p.noise_stride_n + (long long)oy * p.out_w + ox) * gain;
         const long long base = n * p.os_n + oy * p.os_h + ox * p.os_w;
         const int valid = min(16, p.o - oc0);
+        // out += result (ToRGB adding into the up-sampled skip image, the residual add of the SPADE block): all 16 loads
+        // of the read-modify-write are issued before the arithmetic so that one memory round trip covers the chunk
+        float prev[ACC ? 16 : 1];
+        if (ACC) {
+            const OT* src = out + base + (long long)oc0 * p.os_c;
+            #pragma unroll
+            for (int j = 0; j < 16; j++) prev[j] = j < valid ? cvt_in<OT>(src[(unsigned)j * cs]) : 0.f;
+        }
         float v[16];
         #pragma unroll
         for (int j = 0; j < 16; j++) {
@@ -200,12 +208,12 @@ __device__ __forceinline__ void epilogue_fast(const IgemmParams& p, const TileCo
             if (CLAMP) r = fminf(fmaxf(r, -clamp), clamp);
             v[j] = r;
         }
-        if (p.accumulate) {
-            // out += result (ToRGB adding into the up-sampled skip image): read-modify-write, lanes are consecutive pixels
+        if (ACC) {
+            // lanes are consecutive pixels: coalesced along W for NCHW tensors
             OT* dst = out + base + (long long)oc0 * p.os_c;
             #pragma unroll
             for (int j = 0; j < 16; j++)
-                if (j < valid) dst[(unsigned)j * cs] = cvt_out<OT>(v[j] + cvt_in<OT>(dst[(unsigned)j * cs]));
+                if (j < valid) dst[(unsigned)j * cs] = cvt_out<OT>(v[j] + prev[j]);
         } else if (nhwc && valid == 16 && ((base + oc0) * sizeof(OT)) % 16 == 0 && ((uintptr_t)out & 15) == 0) {
             // channels-innermost output: 16 consecutive channels of one pixel, 128-bit stores; with out_parts > 1 the
             // bf16 expansion of the value is written (part q = bf16(v - earlier parts)): the next conv's operand format
@@ -242,15 +250,22 @@ __device__ __forceinline__ void epilogue_fast(const IgemmParams& p, const TileCo
 template <class OT>
 __device__ __forceinline__ void epilogue_dispatch(const IgemmParams& p, const TileCoord tc, uint32_t tmem_tile, const PixelCoord pc,
                                                   int col_begin, int col_end, const float2* s_cs, bool fast) {
-    if (fast) {
+    if (fast && p.accumulate) {
+        // read-modify-write output (ToRGB into the skip image, residual adds): linear activation only on the fast path
+        if (p.act_fn == PGPP_ACT_LINEAR) {
+            if (p.clamp >= 0.f) epilogue_fast<PGPP_ACT_LINEAR, OT, true, true>(p, tc, tmem_tile, pc, col_begin, col_end, s_cs);
+            else                epilogue_fast<PGPP_ACT_LINEAR, OT, false, true>(p, tc, tmem_tile, pc, col_begin, col_end, s_cs);
+            return;
+        }
+    } else if (fast) {
         const bool cl = p.clamp >= 0.f;
         switch (p.act_fn) {
-            case PGPP_ACT_LINEAR: if (cl) epilogue_fast<PGPP_ACT_LINEAR, OT, true>(p, tc, tmem_tile, pc, col_begin, col_end, s_cs);
-                                  else    epilogue_fast<PGPP_ACT_LINEAR, OT, false>(p, tc, tmem_tile, pc, col_begin, col_end, s_cs); break;
-            case PGPP_ACT_RELU:   if (cl) epilogue_fast<PGPP_ACT_RELU, OT, true>(p, tc, tmem_tile, pc, col_begin, col_end, s_cs);
-                                  else    epilogue_fast<PGPP_ACT_RELU, OT, false>(p, tc, tmem_tile, pc, col_begin, col_end, s_cs); break;
-            default:              if (cl) epilogue_fast<PGPP_ACT_LRELU, OT, true>(p, tc, tmem_tile, pc, col_begin, col_end, s_cs);
-                                  else    epilogue_fast<PGPP_ACT_LRELU, OT, false>(p, tc, tmem_tile, pc, col_begin, col_end, s_cs); break;
+            case PGPP_ACT_LINEAR: if (cl) epilogue_fast<PGPP_ACT_LINEAR, OT, true, false>(p, tc, tmem_tile, pc, col_begin, col_end, s_cs);
+                                  else    epilogue_fast<PGPP_ACT_LINEAR, OT, false, false>(p, tc, tmem_tile, pc, col_begin, col_end, s_cs); break;
+            case PGPP_ACT_RELU:   if (cl) epilogue_fast<PGPP_ACT_RELU, OT, true, false>(p, tc, tmem_tile, pc, col_begin, col_end, s_cs);
+                                  else    epilogue_fast<PGPP_ACT_RELU, OT, false, false>(p, tc, tmem_tile, pc, col_begin, col_end, s_cs); break;
+            default:              if (cl) epilogue_fast<PGPP_ACT_LRELU, OT, true, false>(p, tc, tmem_tile, pc, col_begin, col_end, s_cs);
+                                  else    epilogue_fast<PGPP_ACT_LRELU, OT, false, false>(p, tc, tmem_tile, pc, col_begin, col_end, s_cs); break;
         }
         return;
     }
