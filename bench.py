@@ -91,11 +91,12 @@ def make_generator_inputs_u8(batch, seed):
 
 
 def to_device_f32(u8, device):
-    """H2D of the uint8 batch + the /127.5 - 1 conversion of test.py:126-147 on the device"""
+    """H2D of the uint8 batch + the /127.5 - 1 conversion of test.py:126-147 on the device (pgpp_u8_to_f32; masks: plain cast)"""
+    io = importlib.import_module('pgpp_b200.torch_utils.custom_ops').get_plugin('io_edge_plugin')
     out = {}
     for k, v in u8.items():
         d = v.to(device, non_blocking=True)
-        out[k] = d.to(torch.float32) if k.endswith('mask') else d.to(torch.float32).div_(127.5).sub_(1.0)
+        out[k] = io.u8_to_f32(d, torch.empty(d.shape, dtype=torch.float32, device=device), normalize=not k.endswith('mask'))
     return out
 
 
@@ -257,7 +258,8 @@ class SynthesisPipeline:
     def __init__(self, net, cat_feats, batch, device):
         self.net, self.cat, self.device = net, cat_feats, device
         self.copy_stream = torch.cuda.Stream(device)
-        self.out_host = [torch.empty(batch, 3, RES, RES, dtype=torch.float32).pin_memory() for _ in range(2)]
+        self.out_host = [torch.empty(batch, RES, RES, 3, dtype=torch.uint8).pin_memory() for _ in range(2)]
+        self.io = importlib.import_module('pgpp_b200.torch_utils.custom_ops').get_plugin('io_edge_plugin')
         self.slot = 0
         self.pending = None
 
@@ -292,18 +294,21 @@ class SynthesisPipeline:
 
 class GeneratorPipeline:
     """End-to-end call for the full generator: uint8 pinned-host try-on inputs -> device (+ /127.5-1 conversion, test.py:126-147)
-    -> GeneratorFull_v20 -> fp32 try-on image back in pinned host memory (test.py:162).  Read-back of batch i overlaps compute of i+1."""
+    -> GeneratorFull_v20 -> uint8 BGR HWC try-on image (pgpp_image_to_u8, test.py:162-166) back in pinned host memory.  Read-back
+    of batch i overlaps compute of i+1."""
 
     def __init__(self, G, batch, device):
         self.G, self.device = G, device
         self.copy_stream = torch.cuda.Stream(device)
-        self.out_host = [torch.empty(batch, 3, RES, RES, dtype=torch.float32).pin_memory() for _ in range(2)]
+        self.out_host = [torch.empty(batch, RES, RES, 3, dtype=torch.uint8).pin_memory() for _ in range(2)]
+        self.io = importlib.import_module('pgpp_b200.torch_utils.custom_ops').get_plugin('io_edge_plugin')
         self.slot, self.pending = 0, None
 
     def __call__(self, host_u8):
         cur = torch.cuda.current_stream(self.device)
         x = to_device_f32(host_u8, self.device)
         _, finetune, _ = run_generator(self.G, x)
+        finetune = self.io.image_to_u8(finetune.contiguous(), reverse_channels=True)
         done = torch.cuda.Event(); done.record(cur)
         self.copy_stream.wait_event(done)
         with torch.cuda.stream(self.copy_stream):
@@ -403,7 +408,7 @@ def run_ours(args):
     f1.record()
     barrier()
     e2e_ms = f0.elapsed_time(f1)        # device clock; f1 is recorded after the last read-back completed
-    d2h = batch * 3 * RES * RES * 4
+    d2h = batch * 3 * RES * RES * (1 if gen_mode else 4)
 
     # ---- max over ranks ----
     times = torch.tensor([ms, e2e_ms], device=device, dtype=torch.float64)
@@ -554,7 +559,7 @@ def run_ours(args):
             'clocks': clocks.summary(),
             'gpu_launches': launches,
             'e2e': {'value': imgs / (e2e_ms * 1e-3), 'unit': 'images/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
-                    'note': ('uint8 pinned-host try-on inputs in (+ on-device /127.5-1, test.py:126-147), fp32 try-on image read back (test.py:162); '
+                    'note': ('uint8 pinned-host try-on inputs in (+ on-device /127.5-1, test.py:126-147), uint8 BGR try-on image read back (test.py:162-166); '
                              'copy of batch i overlaps compute of i+1') if gen_mode else
                             'pinned-host ws + pose features in, fp32 image read back; copy of batch i overlaps compute of i+1'},
             'roofline': roof,

@@ -197,6 +197,19 @@ typedef struct pgpp_wgrad_desc {
 /* Split-K GEMM over the pixels on the 5th-gen tensor cores (tcgen05.mma, TMEM accumulators, TMA operand loads). */
 PGPP_API int pgpp_conv2d_wgrad(const pgpp_wgrad_desc* desc, void* stream);
 
+/* ---- input / output edge of the try-on inference loop (test.py:126-147, :162-166) ----
+ *
+ * src uint8 [N, C, H*W] contiguous -> channels [c_off, c_off + C) of dst float32 [N, dst_c_total, H*W]:
+ *   normalize != 0: x / 127.5 - 1 (test.py:126-140), else a plain cast (masks, test.py:139,142);
+ *   mask (float32 [N, 1, H*W] or NULL): then x * mask - (1 - mask), the retain composition of test.py:144.
+ * Separately rounded IEEE operations: bit-identical to the reference's torch expressions. */
+PGPP_API int pgpp_u8_to_f32(const void* src, int64_t n, int64_t c, int64_t hw, void* dst, int64_t dst_c_total, int64_t c_off,
+                   int normalize, const float* mask, void* stream);
+
+/* img float32 [N, C, H*W] -> out uint8 [N, H*W, C] = trunc(clip((x + 1) * 127.5, 0, 255)), channel order reversed when
+ * reverse_channels != 0 (RGB -> BGR, test.py:162-166). */
+PGPP_API int pgpp_image_to_u8(const float* img, int64_t n, int64_t c, int64_t hw, void* out, int reverse_channels, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

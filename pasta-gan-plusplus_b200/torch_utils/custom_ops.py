@@ -81,13 +81,18 @@ def load_library():
     lib.pgpp_conv2d_igemm.argtypes = [ctypes.POINTER(ConvDesc), vp]
     lib.pgpp_conv2d_wgrad.restype = i32
     lib.pgpp_conv2d_wgrad.argtypes = [ctypes.POINTER(WgradDesc), vp]
+    lib.pgpp_u8_to_f32.restype = i32
+    lib.pgpp_u8_to_f32.argtypes = [vp, i64, i64, i64, vp, i64, i64, i32, vp, vp]
+    lib.pgpp_image_to_u8.restype = i32
+    lib.pgpp_image_to_u8.argtypes = [vp, i64, i64, i64, vp, i32, vp]
     _lib = lib
     return lib
 
 
 EXPORTED_SYMBOLS = ('pgpp_version', 'pgpp_last_error', 'pgpp_launch_count', 'pgpp_bias_act', 'pgpp_upfirdn2d',
                     'pgpp_modconv_demod_coefs', 'pgpp_pack_activations', 'pgpp_pack_activations_slice', 'pgpp_modulate_weights',
-                    'pgpp_spade_modulate_pack', 'pgpp_pack_im2col', 'pgpp_conv2d_igemm', 'pgpp_conv2d_wgrad')
+                    'pgpp_spade_modulate_pack', 'pgpp_pack_im2col', 'pgpp_conv2d_igemm', 'pgpp_conv2d_wgrad', 'pgpp_u8_to_f32',
+                    'pgpp_image_to_u8')
 
 
 class WgradDesc(ctypes.Structure):
@@ -314,7 +319,43 @@ class _ConvPlugin:
             _check(lib.pgpp_conv2d_wgrad(ctypes.byref(desc), stream))
 
 
-_PLUGINS = {'bias_act_plugin': _BiasActPlugin, 'upfirdn2d_plugin': _Upfirdn2dPlugin, 'conv2d_plugin': _ConvPlugin}
+class _IoEdgePlugin:
+    """input / output edge of the inference loop (test.py:126-147, :162-166)"""
+
+    @staticmethod
+    def u8_to_f32(src, dst, c_off=0, normalize=True, mask=None):
+        """src uint8 [N,C,H,W] -> channels [c_off, c_off+C) of dst float32 [N,Ct,H,W]; see pgpp_u8_to_f32"""
+        _torch_check(src.is_cuda and src.dtype == torch.uint8 and src.dim() == 4 and src.is_contiguous(), 'src must be a contiguous uint8 CUDA tensor [N,C,H,W]')
+        _torch_check(dst.is_cuda and dst.dtype == torch.float32 and dst.dim() == 4 and dst.is_contiguous() and dst.device == src.device,
+                     'dst must be a contiguous float32 CUDA tensor on the same device')
+        n, c, h, w = src.shape
+        _torch_check(dst.shape[0] == n and tuple(dst.shape[2:]) == (h, w) and 0 <= c_off and c_off + c <= dst.shape[1], 'dst does not hold the channel slice')
+        if mask is not None:
+            _torch_check(mask.is_cuda and mask.dtype == torch.float32 and mask.is_contiguous() and tuple(mask.shape) == (n, 1, h, w),
+                         'mask must be a contiguous float32 tensor [N,1,H,W]')
+        lib = load_library()
+        if src.numel() == 0:
+            return dst
+        with torch.cuda.device(src.device):
+            _check(lib.pgpp_u8_to_f32(_ptr(src), n, c, h * w, _ptr(dst), dst.shape[1], int(c_off), int(bool(normalize)), _ptr(mask), _stream(src)))
+        return dst
+
+    @staticmethod
+    def image_to_u8(img, reverse_channels=True):
+        """img float32 [N,C,H,W] -> uint8 [N,H,W,C]; see pgpp_image_to_u8"""
+        _torch_check(img.is_cuda and img.dtype == torch.float32 and img.dim() == 4 and img.is_contiguous(), 'img must be a contiguous float32 CUDA tensor [N,C,H,W]')
+        n, c, h, w = img.shape
+        out = torch.empty([n, h, w, c], dtype=torch.uint8, device=img.device)
+        lib = load_library()
+        if img.numel() == 0:
+            return out
+        with torch.cuda.device(img.device):
+            _check(lib.pgpp_image_to_u8(_ptr(img), n, c, h * w, _ptr(out), int(bool(reverse_channels)), _stream(img)))
+        return out
+
+
+_PLUGINS = {'bias_act_plugin': _BiasActPlugin, 'upfirdn2d_plugin': _Upfirdn2dPlugin, 'conv2d_plugin': _ConvPlugin,
+            'io_edge_plugin': _IoEdgePlugin}
 
 
 def get_plugin(module_name, sources=None, **build_kwargs):
