@@ -250,23 +250,20 @@ __device__ __forceinline__ void epilogue_fast(const IgemmParams& p, const TileCo
 template <class OT>
 __device__ __forceinline__ void epilogue_dispatch(const IgemmParams& p, const TileCoord tc, uint32_t tmem_tile, const PixelCoord pc,
                                                   int col_begin, int col_end, const float2* s_cs, bool fast) {
-    if (fast && p.accumulate) {
-        // read-modify-write output (ToRGB into the skip image, residual adds): linear activation only on the fast path
-        if (p.act_fn == PGPP_ACT_LINEAR) {
-            if (p.clamp >= 0.f) epilogue_fast<PGPP_ACT_LINEAR, OT, true, true>(p, tc, tmem_tile, pc, col_begin, col_end, s_cs);
-            else                epilogue_fast<PGPP_ACT_LINEAR, OT, false, true>(p, tc, tmem_tile, pc, col_begin, col_end, s_cs);
-            return;
-        }
-    } else if (fast) {
+    if (fast) {
+        // ACC: read-modify-write output (ToRGB into the skip image, residual adds)
+#define PGPP_FAST(ACT) \
+        if (p.accumulate) { if (cl) epilogue_fast<ACT, OT, true, true>(p, tc, tmem_tile, pc, col_begin, col_end, s_cs);   \
+                            else    epilogue_fast<ACT, OT, false, true>(p, tc, tmem_tile, pc, col_begin, col_end, s_cs); } \
+        else               { if (cl) epilogue_fast<ACT, OT, true, false>(p, tc, tmem_tile, pc, col_begin, col_end, s_cs);  \
+                            else    epilogue_fast<ACT, OT, false, false>(p, tc, tmem_tile, pc, col_begin, col_end, s_cs); }
         const bool cl = p.clamp >= 0.f;
         switch (p.act_fn) {
-            case PGPP_ACT_LINEAR: if (cl) epilogue_fast<PGPP_ACT_LINEAR, OT, true, false>(p, tc, tmem_tile, pc, col_begin, col_end, s_cs);
-                                  else    epilogue_fast<PGPP_ACT_LINEAR, OT, false, false>(p, tc, tmem_tile, pc, col_begin, col_end, s_cs); break;
-            case PGPP_ACT_RELU:   if (cl) epilogue_fast<PGPP_ACT_RELU, OT, true, false>(p, tc, tmem_tile, pc, col_begin, col_end, s_cs);
-                                  else    epilogue_fast<PGPP_ACT_RELU, OT, false, false>(p, tc, tmem_tile, pc, col_begin, col_end, s_cs); break;
-            default:              if (cl) epilogue_fast<PGPP_ACT_LRELU, OT, true, false>(p, tc, tmem_tile, pc, col_begin, col_end, s_cs);
-                                  else    epilogue_fast<PGPP_ACT_LRELU, OT, false, false>(p, tc, tmem_tile, pc, col_begin, col_end, s_cs); break;
+            case PGPP_ACT_LINEAR: PGPP_FAST(PGPP_ACT_LINEAR) break;
+            case PGPP_ACT_RELU:   PGPP_FAST(PGPP_ACT_RELU) break;
+            default:              PGPP_FAST(PGPP_ACT_LRELU) break;
         }
+#undef PGPP_FAST
         return;
     }
 #define PGPP_EPI(ACT) epilogue_general<ACT, OT>(p, tc, tmem_tile, pc, col_begin, col_end)

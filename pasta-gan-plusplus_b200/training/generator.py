@@ -87,6 +87,20 @@ class ResBlock(torch.nn.Module):
         self.skip = Conv2dLayer(in_channels, out_channels, kernel_size=1, bias=False, up=up, down=down, **kw)
 
     def forward(self, x, fused=True, impl='cuda'):
+        if fused and self.conv0.up == 1 and S._can_fuse(x, self.conv0.weight, self.conv1.weight, self.skip.weight) and \
+                (isinstance(x, PackedAct) or x.dtype == torch.float32) and self.conv0.weight.shape[0] % 16 == 0:
+            # hand-over route: x is packed once for skip and conv0, conv0 writes conv1's operand format, conv1 adds into y
+            parts = S._parts()
+            if self.conv0.down == 1 and not isinstance(x, PackedAct):
+                conv2d_gradfix._init()
+                c = x.shape[1]
+                x = PackedAct(conv2d_gradfix._plugin.pack_activations(x, None, -(-c // 64) * 64, parts), c)
+            y = self.skip(x, gain=SQRT_HALF, fused=True)
+            n, oc, h, w = y.shape
+            hp = PackedAct(PackedAct.empty(n, h, w, oc, parts, y.device), oc)
+            self.conv0(x, fused=True, out_packed=hp)
+            self.conv1(hp, gain=SQRT_HALF, fused=True, out=y, accumulate=True)
+            return y
         y = self.skip(x, gain=SQRT_HALF, fused=fused, impl=impl)
         x = self.conv0(x, fused=fused, impl=impl)
         x = self.conv1(x, gain=SQRT_HALF, fused=fused, impl=impl)
@@ -364,8 +378,19 @@ class SynthesisNetworkFull_v18(torch.nn.Module):
         valid_mask = ((mask_256 + denorm_mask_256) == 2.0).to(mask_512.dtype)
         res_mask = mask_256 - valid_mask
         x = denorm_input * mask_512 - (1 - mask_512)
-        for layer in self.spade_encoder:
-            x = layer(x, fused=fused, impl=impl)
+        stem = self.spade_encoder[0]
+        if fused and S._can_fuse(x, stem.weight, stem.bias) and x.dtype == torch.float32:
+            # the 7x7 stem writes the operand format of the first residual block
+            n, _, h, w = x.shape
+            oc = stem.weight.shape[0]
+            xp = PackedAct(PackedAct.empty(n, h, w, oc, S._parts(), x.device), oc)
+            stem(x, fused=True, out_packed=xp)
+            x = xp
+            for layer in self.spade_encoder[1:]:
+                x = layer(x, fused=True, impl=impl)
+        else:
+            for layer in self.spade_encoder:
+                x = layer(x, fused=fused, impl=impl)
         valid_feat_sum = torch.sum(x * valid_mask, dim=(2, 3), keepdim=True)
         valid_mask_sum = torch.sum(valid_mask, dim=(2, 3), keepdim=True)
         valid_index = (valid_mask_sum > 10).to(mask_512.dtype)

@@ -80,7 +80,9 @@ class Conv2dLayer(torch.nn.Module):
         self.weight = torch.nn.Parameter(torch.randn([out_channels, in_channels, kernel_size, kernel_size]))
         self.bias = torch.nn.Parameter(torch.zeros([out_channels])) if bias else None
 
-    def forward(self, x, gain=1, fused=True, impl='cuda', out_packed=None):
+    def forward(self, x, gain=1, fused=True, impl='cuda', out_packed=None, out=None, accumulate=False):
+        """`out_packed=`: write the operand format of the next convolution instead of an NCHW tensor; `out=` / `accumulate=`: write
+        (or add, `y = skip + conv1(...)` of the residual blocks) into an existing NCHW float32 tensor.  Fused route only."""
         act_gain = self.act_gain * gain
         act_clamp = self.conv_clamp * gain if self.conv_clamp is not None else None
         if fused and self.up == 1 and self.down == 1 and _can_fuse(x, self.weight, self.bias):
@@ -89,9 +91,10 @@ class Conv2dLayer(torch.nn.Module):
             pw = conv2d_gradfix.packed_plain(self.weight, True, parts, self.padding, self.padding, scale=self.weight_gain, allow_im2col=im2col)
             return conv2d_gradfix.igemm_conv(x, pw, bias=self.bias, act=self.activation,
                                              alpha=bias_act.activation_funcs[self.activation].def_alpha, gain=act_gain,
-                                             clamp=-1 if act_clamp is None else act_clamp, out_packed=out_packed)
-        if fused and self.up == 1 and self.down == 2 and out_packed is None and _can_fuse(x, self.weight, self.bias) and \
-                not isinstance(x, PackedAct):
+                                             clamp=-1 if act_clamp is None else act_clamp, out_packed=out_packed, out=out,
+                                             accumulate=accumulate)
+        assert out is None and not accumulate, 'out= / accumulate= need the fused stride-1 route'
+        if fused and self.up == 1 and self.down == 2 and _can_fuse(x, self.weight, self.bias) and not isinstance(x, PackedAct):
             # FIR blur (or FIR decimation for 1x1 kernels) on the upfirdn2d kernel, then ONE strided implicit-GEMM launch with the
             # bias / activation fused (conv2d_resample.py:107-110, 119-122)
             k = self.weight.shape[-1]
@@ -104,9 +107,9 @@ class Conv2dLayer(torch.nn.Module):
                        clamp=-1 if act_clamp is None else act_clamp)
             if k == 1:
                 x = upfirdn2d.upfirdn2d(x, self.resample_filter, down=2, padding=[p0, p1, p0, p1])
-                return conv2d_gradfix.igemm_conv(x, pw, **epi)
+                return conv2d_gradfix.igemm_conv(x, pw, out_packed=out_packed, **epi)
             x = upfirdn2d.upfirdn2d(x, self.resample_filter, padding=[p0, p1, p0, p1])
-            return conv2d_gradfix.igemm_conv(x, pw, stride=2, **epi)
+            return conv2d_gradfix.igemm_conv(x, pw, stride=2, out_packed=out_packed, **epi)
         assert out_packed is None and not isinstance(x, PackedAct)
         w = self.weight * self.weight_gain
         b = self.bias.to(x.dtype) if self.bias is not None else None

@@ -88,3 +88,34 @@ def test_cuda_graph_replay_is_bit_identical(generator_and_inputs):
     torch.cuda.synchronize()
     for a, b in zip(out, eager):
         assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize('down', [1, 2])
+@pytest.mark.parametrize('packed_input', [False, True])
+def test_resblock_hand_over_route_matches_composition(down, packed_input):
+    """ResBlock (networks.py:287-316): x packed once for skip + conv0, conv0 -> conv1 in operand format, conv1's epilogue adds
+    into y (relu, then += skip) - against the op-by-op composition on the CPU oracle path"""
+    if packed_input and down == 2:
+        pytest.skip('the down=2 block starts with a FIR pass on the NCHW tensor')
+    torch.manual_seed(3)
+    blk = gen.ResBlock(64, 128 if down == 2 else 64, 3, activation='relu', down=down).eval().requires_grad_(False)
+    for p in blk.parameters():
+        p.copy_(torch.randn_like(p))
+    x = torch.randn(2, 64, 48, 80)
+    with torch.no_grad():
+        from helpers import upfirdn2d_ref_on_cpu
+        upf = importlib.import_module('pgpp_b200.torch_utils.ops.upfirdn2d')
+        with upfirdn2d_ref_on_cpu(upf):
+            want = blk(x.double(), fused=False, impl='ref') if False else blk(x, fused=False, impl='ref')
+        blk = blk.to(DEV)
+        xin = x.to(DEV)
+        if packed_input:
+            data = cg._plugin.pack_activations(xin, None, 64, 2) if cg._init() else None
+            xin = cg.PackedAct(data, 64)
+        launches = custom_ops.launch_count()
+        got = blk(xin, fused=True)
+        n_launch = custom_ops.launch_count() - launches
+    rel = ((got.cpu() - want).norm() / want.norm()).item()
+    assert rel < 1e-4, rel
+    # down=1: [pack] + skip + conv0 + conv1;  down=2: 2 FIR + 2 packs + 3 convs
+    assert n_launch == ((3 if packed_input else 4) if down == 1 else 7), n_launch
