@@ -149,7 +149,9 @@ static int launch_pack(const PackArgs& p, cudaStream_t stream) {
         const long long blocks = (long long)g.x_tiles * g.y_tiles * g.c_tiles * p.n;
         PGPP_REQUIRE(blocks <= 2147483647LL, "activation tensor too large to pack");
         const size_t smem = (size_t)p.parts * 128 * 8 * sizeof(uint4);
-        const bool vec = sizeof(T) == 4 && p.w % 4 == 0 && p.s_c % 4 == 0 && p.s_h % 4 == 0 && p.s_n % 4 == 0 && ((uintptr_t)p.x & 15) == 0;
+        // 128-bit loads: rows 16-byte aligned and either W % 4 == 0 or a row pitch that covers the last (partial) group of 4
+        const bool vec = sizeof(T) == 4 && (p.w % 4 == 0 || p.s_h >= (p.w + 3) / 4 * 4) && p.s_c % 4 == 0 && p.s_h % 4 == 0 && p.s_n % 4 == 0 &&
+                         ((uintptr_t)p.x & 15) == 0;
         if (vec) pack_nchw_kernel<float, true><<<(unsigned)blocks, 256, smem, stream>>>(p, g);
         else pack_nchw_kernel<T, false><<<(unsigned)blocks, 256, smem, stream>>>(p, g);
     } else {

@@ -191,7 +191,10 @@ class _Upfirdn2dPlugin:
     and output size follow torch_utils/ops/upfirdn2d.cpp:19-36."""
 
     @staticmethod
-    def upfirdn2d(x, f, upx, upy, downx, downy, padx0, padx1, pady0, pady1, flip, gain):
+    def upfirdn2d(x, f, upx, upy, downx, downy, padx0, padx1, pady0, pady1, flip, gain, row_align=1):
+        """`row_align` > 1 (not in the reference): rows of the (NCHW) result start at multiples of `row_align` elements - the
+        returned tensor is a [..., :out_w] view of a wider allocation - so that odd-width blur outputs (513 = 512 + 1 before
+        a strided conv) keep 16-byte aligned rows for the kernels that follow."""
         lib = load_library()
         _torch_check(x.is_cuda, 'x must reside on CUDA device')
         _torch_check(f.device == x.device, 'f must reside on the same device as x')
@@ -207,7 +210,10 @@ class _Upfirdn2dPlugin:
         out_h = (h * upy + pady0 + pady1 - f.shape[0] + downy) // downy
         _torch_check(out_w >= 1 and out_h >= 1, 'output must be at least 1x1')
         mf = torch.channels_last if (x.stride(1) == 1 and c > 1) else torch.contiguous_format
-        y = torch.empty([n, c, out_h, out_w], dtype=x.dtype, device=x.device, memory_format=mf)
+        if row_align > 1 and mf == torch.contiguous_format and out_w % row_align:
+            y = torch.empty([n, c, out_h, -(-out_w // row_align) * row_align], dtype=x.dtype, device=x.device)[..., :out_w]
+        else:
+            y = torch.empty([n, c, out_h, out_w], dtype=x.dtype, device=x.device, memory_format=mf)
         _torch_check(y.numel() <= 2 ** 31 - 1, 'output is too large')
         with torch.cuda.device(x.device):
             _check(lib.pgpp_upfirdn2d(_ptr(x), _ptr(f), _ptr(y), c_i64x4(*x.shape), c_i64x4(*x.stride()),

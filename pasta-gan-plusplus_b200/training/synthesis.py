@@ -108,7 +108,9 @@ class Conv2dLayer(torch.nn.Module):
             if k == 1:
                 x = upfirdn2d.upfirdn2d(x, self.resample_filter, down=2, padding=[p0, p1, p0, p1])
                 return conv2d_gradfix.igemm_conv(x, pw, out_packed=out_packed, **epi)
-            x = upfirdn2d.upfirdn2d(x, self.resample_filter, padding=[p0, p1, p0, p1])
+            # blurred image of odd width (2W' + 1): rows padded to 16 bytes so the FIR stores and the packing loads stay 128-bit
+            upfirdn2d._init()
+            x = upfirdn2d._plugin.upfirdn2d(x, self.resample_filter, 1, 1, 1, 1, p0, p1, p0, p1, False, 1.0, row_align=4)
             return conv2d_gradfix.igemm_conv(x, pw, stride=2, out_packed=out_packed, **epi)
         assert out_packed is None and not isinstance(x, PackedAct)
         w = self.weight * self.weight_gain

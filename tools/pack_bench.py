@@ -36,6 +36,15 @@ for (n, c, h, w, parts) in [(32, 64, 512, 320, 2), (32, 128, 256, 160, 2), (32, 
     x = torch.randn(n, c, h, w, device=dev)
     ms = timeit(lambda: plugin.pack_activations(x, None, (c + 63) // 64 * 64, parts))
     report(f'pack_nchw {n}x{c}x{h}x{w} f32 -> {parts} part(s)', ms, x.numel() * (4 + 2 * parts))
+xpad = torch.randn(32, 64, 513, 516, device=dev)[..., :513]
+ms = timeit(lambda: plugin.pack_activations(xpad, None, 64, 2))
+report('pack_nchw 32x64x513x513 (row pitch 516) f32 -> 2 parts', ms, xpad.numel() * 8)
+up = custom_ops.get_plugin('upfirdn2d_plugin')
+f = torch.tensor([1., 3., 3., 1.], device=dev); f = torch.outer(f, f); f = f / f.sum()
+xin = torch.randn(32, 64, 512, 512, device=dev)
+for align in (1, 4):
+    ms = timeit(lambda: up.upfirdn2d(xin, f, 1, 1, 1, 1, 2, 2, 2, 2, False, 1.0, row_align=align))
+    report(f'fir blur 32x64x512x512 -> 513x513 row_align={align}', ms, xin.numel() * 4 + 32 * 64 * 513 * 513 * 4)
 for (n, c, h, w) in [(32, 128, 256, 160), (32, 64, 512, 320)]:
     x = torch.randn(n, c, h, w, device=dev)
     gb = torch.randn(n, 2 * c, h, w, device=dev)
