@@ -168,6 +168,12 @@ typedef struct {
  * loads), persistent over the SMs, with the epilogue above fused. */
 PGPP_API int pgpp_conv2d_igemm(const pgpp_conv_desc* desc, void* stream);
 
+/* Masked feature composition + packing (networks.py:2256-2266, 2315-2317: the warped-garment features fed to the SPADE blocks):
+ *   v[n,c,p] = x1[n,c,p]*a1[n,p] + m1[n,c]*b1[n,p]  (+ x2[n,c,p]*a2[n,p] + m2[n,c]*b2[n,p] when x2 != NULL)
+ * x float32 [N,C,H,W] contiguous, m float32 [N,C], a / b float32 [N,H,W]; out = bf16 [parts][N][H][W][c_pad] (the operand format). */
+PGPP_API int pgpp_mix_pack(const float* x1, const float* m1, const float* a1, const float* b1, const float* x2, const float* m2,
+                  const float* a2, const float* b2, void* out, int n, int c, int h, int w, int c_pad, int parts, void* stream);
+
 /* ---- weight gradient (conv2d_gradfix.py:135-142, Conv2dGradWeight.forward: replaces
  * aten::cudnn_convolution_backward_weight / cudnn_convolution_transpose_backward_weight) ----
  *

@@ -281,6 +281,65 @@ __global__ void __launch_bounds__(256) spade_pack_kernel(SpadeArgs p, TileGeom g
     emit_tile(v, sm_packets, p.parts, p.out, p.part_stride, n, p.h, p.w, y0, x0, g.log_tw, c0, p.c_pad, p.c_pad, 0);
 }
 
+struct MixArgs {
+    const float* x[2]; const float* m[2]; const float* a[2]; const float* b[2]; __nv_bfloat16* out;
+    int n, c, h, w, c_pad, parts, terms; long long part_stride;
+};
+
+// v[n,c,p] = sum_t x_t[n,c,p] * a_t[n,p] + m_t[n,c] * b_t[n,p]  ->  packed operand (same transposing tile as pack_nchw_kernel).
+// The masked feature composition of SynthesisNetworkFull_v18 (networks.py:2256-2266, 2315-2317): per branch
+// x * (1 - res_mask) + mean * res_mask, times the branch's 256 x 256 mask, summed over the upper / lower branches.
+template <bool VEC>
+__global__ void __launch_bounds__(256) mix_pack_kernel(MixArgs p, TileGeom g) {
+    extern __shared__ uint4 sm_packets[];
+    int xt, yt, ct, n;
+    decode_tile_block(g, xt, yt, ct, n);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int tw_mask = (1 << g.log_tw) - 1;
+    const int x0 = xt << g.log_tw, y0 = yt * (128 >> g.log_tw), c0 = ct * 64;
+    const int y = y0 + ((4 * lane) >> g.log_tw), x = x0 + ((4 * lane) & tw_mask);
+    const long long plane = (long long)p.h * p.w;
+    const long long pix = (long long)y * p.w + x;
+    float v[8][4];
+    #pragma unroll
+    for (int i = 0; i < 8; i++)
+        #pragma unroll
+        for (int k = 0; k < 4; k++) v[i][k] = 0.f;
+    if (y < p.h && x < p.w) {
+        for (int t = 0; t < p.terms; t++) {
+            float av[4] = {0.f, 0.f, 0.f, 0.f}, bv[4] = {0.f, 0.f, 0.f, 0.f};
+            const float* ap = p.a[t] + n * plane + pix;
+            const float* bp = p.b[t] + n * plane + pix;
+            if (VEC) {
+                const float4 qa = *reinterpret_cast<const float4*>(ap), qb = *reinterpret_cast<const float4*>(bp);
+                av[0] = qa.x; av[1] = qa.y; av[2] = qa.z; av[3] = qa.w;
+                bv[0] = qb.x; bv[1] = qb.y; bv[2] = qb.z; bv[3] = qb.w;
+            } else {
+                #pragma unroll
+                for (int k = 0; k < 4; k++) if (x + k < p.w) { av[k] = ap[k]; bv[k] = bp[k]; }
+            }
+            #pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const int c = c0 + warp * 8 + i;
+                if (c >= p.c) continue;
+                const float* xp = p.x[t] + ((long long)n * p.c + c) * plane + pix;
+                float xv[4] = {0.f, 0.f, 0.f, 0.f};
+                if (VEC) {
+                    const float4 q = *reinterpret_cast<const float4*>(xp);
+                    xv[0] = q.x; xv[1] = q.y; xv[2] = q.z; xv[3] = q.w;
+                } else {
+                    #pragma unroll
+                    for (int k = 0; k < 4; k++) if (x + k < p.w) xv[k] = xp[k];
+                }
+                const float mv = p.m[t][n * p.c + c];
+                #pragma unroll
+                for (int k = 0; k < 4; k++) v[i][k] += __fadd_rn(__fmul_rn(xv[k], av[k]), __fmul_rn(mv, bv[k]));
+            }
+        }
+    }
+    emit_tile(v, sm_packets, p.parts, p.out, p.part_stride, n, p.h, p.w, y0, x0, g.log_tw, c0, p.c_pad, p.c_pad, 0);
+}
+
 // one CTA per output channel: W2[i] = sum_t w[o,i,t]^2 in shared memory, then one warp per sample
 __global__ void __launch_bounds__(256) demod_kernel(const float* __restrict__ w, const float* __restrict__ s,
                                                     float* __restrict__ d, int n, int o, int ic, int taps, float eps) {
@@ -443,6 +502,31 @@ extern "C" int pgpp_modconv_demod_coefs(const float* w, const float* s, float* d
     if (smem > 48 * 1024)
         PGPP_CUDA_OK(cudaFuncSetAttribute(demod_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     demod_kernel<<<o, 256, smem, (cudaStream_t)stream>>>(w, s, d, n, o, i, taps, eps);
+    count_launch();
+    PGPP_CUDA_OK(cudaGetLastError());
+    return PGPP_OK;
+}
+
+extern "C" int pgpp_mix_pack(const float* x1, const float* m1, const float* a1, const float* b1, const float* x2, const float* m2,
+                             const float* a2, const float* b2, void* out, int n, int c, int h, int w, int c_pad, int parts, void* stream) {
+    using namespace pgpp;
+    PGPP_REQUIRE(x1 && m1 && a1 && b1 && out, "null pointer");
+    PGPP_REQUIRE((x2 == nullptr) == (m2 == nullptr) && (x2 == nullptr) == (a2 == nullptr) && (x2 == nullptr) == (b2 == nullptr),
+                 "the second term needs all of x2, m2, a2, b2");
+    PGPP_REQUIRE(n >= 1 && c >= 1 && h >= 1 && w >= 1 && c_pad >= c && c_pad % 16 == 0 && parts >= 1 && parts <= 3, "bad mix_pack arguments");
+    MixArgs p;
+    p.x[0] = x1; p.m[0] = m1; p.a[0] = a1; p.b[0] = b1; p.x[1] = x2; p.m[1] = m2; p.a[1] = a2; p.b[1] = b2;
+    p.terms = x2 ? 2 : 1;
+    p.out = (__nv_bfloat16*)out; p.n = n; p.c = c; p.h = h; p.w = w; p.c_pad = c_pad; p.parts = parts;
+    p.part_stride = (long long)n * h * w * c_pad;
+    const TileGeom g = tile_geometry(h, w, c_pad);
+    const long long blocks = (long long)g.x_tiles * g.y_tiles * g.c_tiles * n;
+    PGPP_REQUIRE(blocks <= 2147483647LL, "tensor too large");
+    const size_t smem = (size_t)parts * 128 * 8 * sizeof(uint4);
+    const uintptr_t al = (uintptr_t)x1 | (uintptr_t)a1 | (uintptr_t)b1 | (uintptr_t)x2 | (uintptr_t)a2 | (uintptr_t)b2;
+    const bool vec = w % 4 == 0 && (al & 15) == 0;
+    if (vec) mix_pack_kernel<true><<<(unsigned)blocks, 256, smem, (cudaStream_t)stream>>>(p, g);
+    else mix_pack_kernel<false><<<(unsigned)blocks, 256, smem, (cudaStream_t)stream>>>(p, g);
     count_launch();
     PGPP_CUDA_OK(cudaGetLastError());
     return PGPP_OK;

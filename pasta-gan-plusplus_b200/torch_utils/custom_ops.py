@@ -77,6 +77,8 @@ def load_library():
     lib.pgpp_pack_im2col.argtypes = [vp, c_i64x4, c_i64x4, i32, vp, vp, i32, i32, i32, i32, i32, vp]
     lib.pgpp_spade_modulate_pack.restype = i32
     lib.pgpp_spade_modulate_pack.argtypes = [vp, vp, vp, vp, vp, i64, vp, i32, i32, i32, i32, i32, i32, f32, vp]
+    lib.pgpp_mix_pack.restype = i32
+    lib.pgpp_mix_pack.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp]
     lib.pgpp_conv2d_igemm.restype = i32
     lib.pgpp_conv2d_igemm.argtypes = [ctypes.POINTER(ConvDesc), vp]
     lib.pgpp_conv2d_wgrad.restype = i32
@@ -91,7 +93,7 @@ def load_library():
 
 EXPORTED_SYMBOLS = ('pgpp_version', 'pgpp_last_error', 'pgpp_launch_count', 'pgpp_bias_act', 'pgpp_upfirdn2d',
                     'pgpp_modconv_demod_coefs', 'pgpp_pack_activations', 'pgpp_pack_activations_slice', 'pgpp_modulate_weights',
-                    'pgpp_spade_modulate_pack', 'pgpp_pack_im2col', 'pgpp_conv2d_igemm', 'pgpp_conv2d_wgrad', 'pgpp_u8_to_f32',
+                    'pgpp_spade_modulate_pack', 'pgpp_mix_pack', 'pgpp_pack_im2col', 'pgpp_conv2d_igemm', 'pgpp_conv2d_wgrad', 'pgpp_u8_to_f32',
                     'pgpp_image_to_u8')
 
 
@@ -308,6 +310,25 @@ class _ConvPlugin:
         with torch.cuda.device(x.device):
             _check(lib.pgpp_spade_modulate_pack(_ptr(x), _ptr(mean), _ptr(rstd), ctypes.c_void_p(gamma_ptr), ctypes.c_void_p(beta_ptr),
                                                 2 * c * h * w, _ptr(out), n, c, h, w, int(c_pad), int(parts), float(pre_gain), _stream(x)))
+        return out
+
+    @staticmethod
+    def mix_pack(terms, c_pad, parts):
+        """terms: one or two (x [N,C,H,W], m [N,C], a [N,H,W], b [N,H,W]) float32 tuples -> bf16 [parts, N, H, W, c_pad] =
+        split(sum_t x_t * a_t + m_t * b_t); see pgpp_mix_pack"""
+        lib = load_library()
+        _torch_check(len(terms) in (1, 2), 'mix_pack takes one or two terms')
+        x0 = terms[0][0]
+        n, c, h, w = x0.shape
+        flat = []
+        for x, m, a, b in terms:
+            _torch_check(x.is_cuda and x.dtype == torch.float32 and tuple(x.shape) == (n, c, h, w), 'mix_pack: x must be float32 [N,C,H,W]')
+            flat += [x.contiguous(), m.to(torch.float32).reshape(n, c).contiguous(), a.to(torch.float32).reshape(n, h, w).contiguous(),
+                     b.to(torch.float32).reshape(n, h, w).contiguous()]
+        ptrs = [_ptr(t) for t in flat] + [None] * (8 - len(flat))
+        out = torch.empty([parts, n, h, w, c_pad], dtype=torch.bfloat16, device=x0.device)
+        with torch.cuda.device(x0.device):
+            _check(lib.pgpp_mix_pack(*ptrs, _ptr(out), n, c, h, w, int(c_pad), int(parts), _stream(x0)))
         return out
 
     @staticmethod

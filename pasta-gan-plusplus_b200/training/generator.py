@@ -370,7 +370,9 @@ class SynthesisNetworkFull_v18(torch.nn.Module):
                                                   ResBlock(ngf, ngf, kernel_size=4, activation='relu'),
                                                   ResBlock(ngf, ngf * 2, kernel_size=4, activation='relu', down=2)])
 
-    def get_spade_feat(self, mask_512, denorm_mask, denorm_input, fused=True, impl='cuda'):
+    def get_spade_feat(self, mask_512, denorm_mask, denorm_input, fused=True, impl='cuda', as_terms=False):
+        """networks.py:2249-2266.  `as_terms`: return (x, mean, 1 - res_mask, res_mask) for the fused composition kernel
+        (pgpp_mix_pack) instead of the composed NCHW feature tensor."""
         half = lambda t: torch.nn.functional.interpolate(t, scale_factor=0.5)
         mask_512 = (mask_512 > 0.9).to(mask_512.dtype)
         mask_256 = (half(mask_512) > 0.9).to(mask_512.dtype)
@@ -391,10 +393,15 @@ class SynthesisNetworkFull_v18(torch.nn.Module):
         else:
             for layer in self.spade_encoder:
                 x = layer(x, fused=fused, impl=impl)
-        valid_feat_sum = torch.sum(x * valid_mask, dim=(2, 3), keepdim=True)
         valid_mask_sum = torch.sum(valid_mask, dim=(2, 3), keepdim=True)
         valid_index = (valid_mask_sum > 10).to(mask_512.dtype)
         valid_mask_sum = valid_mask_sum * valid_index + (256 * 256) * (1 - valid_index)
+        if as_terms:
+            n, c = x.shape[:2]
+            # masked spatial sum as one batched matrix-vector product (reads x once, no x * mask temporary)
+            valid_feat_sum = torch.bmm(x.reshape(n, c, -1), valid_mask.reshape(n, -1, 1)).reshape(n, c, 1, 1)
+            return x, valid_feat_sum / valid_mask_sum, 1 - res_mask, res_mask
+        valid_feat_sum = torch.sum(x * valid_mask, dim=(2, 3), keepdim=True)
         return x * (1 - res_mask) + (valid_feat_sum / valid_mask_sum) * res_mask
 
     def forward(self, ws, pose_feat, cat_feat, denorm_upper_input, denorm_lower_input, denorm_upper_mask, denorm_lower_mask, gt_parsing,
@@ -420,17 +427,24 @@ class SynthesisNetworkFull_v18(torch.nn.Module):
         upper_mask = (parsing_index == 1).float() + (parsing_index == 4).float()
         lower_mask = (parsing_index == 2).float() + (parsing_index == 3).float()
         kw = dict(fused=fused, impl=impl)
-        spade_upper = self.get_spade_feat(upper_mask, denorm_upper_mask, denorm_upper_input, **kw)
-        spade_lower = self.get_spade_feat(lower_mask, denorm_lower_mask, denorm_lower_input, **kw)
         half = lambda t: torch.nn.functional.interpolate(t, scale_factor=0.5)
         upper_256 = (half(upper_mask) > 0.9).to(upper_mask.dtype)
         lower_256 = (half(lower_mask) > 0.9).to(upper_mask.dtype)
-        spade_feat = spade_upper * upper_256 + spade_lower * lower_256
-        feats_packed = None
-        if fused and S._can_fuse(spade_feat):       # both SPADE blocks read the same features: pack them once
+        feats_packed = spade_feat = None
+        if fused and S._can_fuse(denorm_upper_input) and denorm_upper_input.dtype == torch.float32:
+            # the masked composition of both branches goes straight into the operand format both SPADE blocks read:
+            # feat = (x_u*(1-res_u) + mean_u*res_u)*upper_256 + (x_l*(1-res_l) + mean_l*res_l)*lower_256   (all masks are 0/1)
             conv2d_gradfix._init()
-            fc = spade_feat.shape[1]
-            feats_packed = PackedAct(conv2d_gradfix._plugin.pack_activations(spade_feat, None, -(-fc // 64) * 64, S._parts()), fc)
+            xu, mu, keep_u, res_u = self.get_spade_feat(upper_mask, denorm_upper_mask, denorm_upper_input, as_terms=True, **kw)
+            xl, ml, keep_l, res_l = self.get_spade_feat(lower_mask, denorm_lower_mask, denorm_lower_input, as_terms=True, **kw)
+            fc = xu.shape[1]
+            data = conv2d_gradfix._plugin.mix_pack([(xu, mu, keep_u * upper_256, res_u * upper_256),
+                                                    (xl, ml, keep_l * lower_256, res_l * lower_256)], -(-fc // 64) * 64, S._parts())
+            feats_packed = PackedAct(data, fc)
+        else:
+            spade_upper = self.get_spade_feat(upper_mask, denorm_upper_mask, denorm_upper_input, **kw)
+            spade_lower = self.get_spade_feat(lower_mask, denorm_lower_mask, denorm_lower_input, **kw)
+            spade_feat = spade_upper * upper_256 + spade_lower * lower_256
         xs = self.spade_b256_1(x_256, spade_feat, feats_packed=feats_packed, **kw)
         xs = self.spade_b256_2(xs, spade_feat, feats_packed=feats_packed, **kw)
         _, finetune_img, _ = self.texture_b512(xs, img_256, block_ws[-1], pose_feat, cat_feat, parsing=parsing_index, **kw, **block_kwargs)

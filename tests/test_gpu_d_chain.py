@@ -113,3 +113,31 @@ def test_packed_activation_roundtrip_and_per_sample_weights():
         assert got.dtype == torch.float32 and rel_l2(got, y2) < 4e-5
     finally:
         cg.fp32_precision = old
+
+
+@pytest.mark.parametrize('shape', [(2, 128, 64, 48), (1, 70, 9, 13), (3, 64, 16, 128)], ids=str)
+@pytest.mark.parametrize('terms', [1, 2])
+def test_mix_pack_matches_the_masked_feature_composition(shape, terms):
+    """pgpp_mix_pack = (x*(1-res) + mean*res) * mask, summed over branches (networks.py:2256-2266, 2315-2317), written in the
+    operand format; with 0/1 masks every product is exact, so the packed sum equals the fp32 composition up to the bf16 split"""
+    import importlib
+    custom_ops = importlib.import_module('pgpp_b200.torch_utils.custom_ops')
+    plugin = custom_ops.get_plugin('conv2d_plugin')
+    n, c, h, w = shape
+    g = torch.Generator().manual_seed(17)
+    want = torch.zeros(n, c, h, w)
+    args = []
+    for t in range(terms):
+        x = torch.randn(n, c, h, w, generator=g)
+        m = torch.randn(n, c, 1, 1, generator=g)
+        res = (torch.rand(n, 1, h, w, generator=g) > 0.7).float()
+        mask = (torch.rand(n, 1, h, w, generator=g) > 0.4).float() if t == 0 else 1 - args[0][4]
+        want += (x * (1 - res) + m * res) * mask
+        args.append((x, m, (1 - res) * mask, res * mask, mask))
+    c_pad = -(-c // 64) * 64
+    for parts, tol in ((3, 1e-6), (2, 2e-5), (1, 4e-3)):
+        data = plugin.mix_pack([tuple(v.to(DEV) for v in a[:4]) for a in args], c_pad, parts)
+        assert tuple(data.shape) == (parts, n, h, w, c_pad)
+        got = data.float().sum(0).permute(0, 3, 1, 2).cpu()
+        assert torch.all(got[:, c:] == 0)
+        assert (got[:, :c] - want).abs().max().item() <= tol * want.abs().max().item(), (parts, (got[:, :c] - want).abs().max().item())
