@@ -162,6 +162,14 @@ typedef struct {
     int32_t out_parts;              /* 1, or 2 / 3 with out_dtype BF16 and out_stride[1] == 1: write the bf16 expansion of the result
                                        (part p at out + p * out_part_stride), i.e. the packed activation format of the next conv */
     int64_t out_part_stride;
+    /* SPADE epilogue (optional, spade_x != NULL; training/networks.py:1702-1723): the GEMM's o = 2C columns are gamma | beta of a
+     * Spade_Norm_Block; the epilogue writes  pre_act((spade_x - mean) * rstd * (1 + gamma) + beta)  for the C channels of spade_x
+     * (float32 [N, C, out_h, out_w] contiguous; mean / rstd float32 [N, C]; pre_act = relu * spade_pre_gain when spade_pre_gain > 0)
+     * as channels-innermost bf16 parts (out_stride[1] == 1, out_parts 1..3).  Needs block_n == o, linear act, gain 1. */
+    const float* spade_x;
+    const float* spade_mean;
+    const float* spade_rstd;
+    float spade_pre_gain;
 } pgpp_conv_desc;
 
 /* Implicit-GEMM convolution on the 5th-gen tensor cores (tcgen05.mma, TMEM accumulators, TMA operand

@@ -70,6 +70,7 @@ struct IgemmParams {
     int up;     // 1, or 2 when phases == 4
     int wgt_per_sample;                 // weights carry a leading sample dimension
     int out_parts; long long out_part_stride;
+    const float* spade_x; const float* spade_mean; const float* spade_rstd; float spade_pre_gain;   // SPADE epilogue (see epilogue_spade)
     int fold_gain;                      // activation is positively homogeneous and gain > 0: gain is folded into scale/shift/noise
     unsigned div_col_m, div_col_s, div_x_m, div_x_s, div_y_m, div_y_s;   // magic numbers for t / tiles_col, / tiles_x, / tiles_y
 };
@@ -244,6 +245,55 @@ __device__ __forceinline__ void epilogue_fast(const IgemmParams& p, const TileCo
         tmem_ld16_issue(tmem_tile + c0, ra);
         tmem_ld_wait16(ra);
         process(ra, c0);
+    }
+}
+
+// SPADE epilogue (networks.py:1702-1723 fused into the gamma|beta GEMM): the accumulator tile holds gamma in columns [0, C)
+// and beta in columns [C, 2C) of one pixel row per lane; the lane reads x[n, c, y, x] (float32 NCHW, coalesced across the
+// lanes of a warp), applies the instance normalisation with the staged per-(sample, channel) statistics,
+//   v = (x - mean) * rstd * (1 + gamma) + beta,   then the consumer's pre-activation relu(v) * pre_gain,
+// and writes the bf16 expansion of v channels-innermost: the operand format of the next convolution.
+// s_cs[c] = (rstd[n, c], bias_gamma[c]), s_cs[C + c] = (mean[n, c], bias_beta[c]).
+__device__ __forceinline__ void epilogue_spade(const IgemmParams& p, const TileCoord tc, uint32_t tmem_tile, const PixelCoord pc,
+                                               int half, const float2* s_cs) {
+    const int C = p.o >> 1;
+    const int chunks = C >> 4;
+    const int ch_begin = (half * chunks) >> 1, ch_end = ((half + 1) * chunks) >> 1;
+    const int x = tc.x0 + pc.px, y = tc.y0 + pc.py, n = tc.n0;
+    const bool pix_ok = x < p.conv_w && y < p.conv_h;
+    const long long plane = (long long)p.conv_h * p.conv_w;
+    const float* xin = p.spade_x + (long long)n * C * plane + (long long)y * p.conv_w + x;
+    __nv_bfloat16* const out = (__nv_bfloat16*)p.out + n * p.os_n + y * p.os_h + x * p.os_w;
+    const float pre_gain = p.spade_pre_gain;
+    for (int ch = ch_begin; ch < ch_end; ch++) {
+        const int c0 = ch << 4;
+        float xv[16];
+        #pragma unroll
+        for (int j = 0; j < 16; j++) xv[j] = pix_ok ? __ldg(xin + (long long)(c0 + j) * plane) : 0.f;
+        uint32_t rg[16], rb[16];
+        tmem_ld16_issue(tmem_tile + c0, rg);
+        tmem_ld16_issue(tmem_tile + C + c0, rb);
+        tmem_ld_wait16(rg);
+        tmem_ld_wait16(rb);
+        if (!pix_ok) continue;
+        float v[16];
+        #pragma unroll
+        for (int j = 0; j < 16; j++) {
+            const float2 qg = s_cs[c0 + j], qb = s_cs[C + c0 + j];
+            const float g = __uint_as_float(rg[j]) + qg.y, b = __uint_as_float(rb[j]) + qb.y;
+            float r = fmaf((xv[j] - qb.x) * qg.x, 1.f + g, b);
+            if (pre_gain > 0.f) r = fmaxf(r, 0.f) * pre_gain;
+            v[j] = r;
+        }
+        for (int part = 0; part < p.out_parts; part++) {
+            __align__(16) __nv_bfloat16 tmp[16];
+            #pragma unroll
+            for (int j = 0; j < 16; j++) { tmp[j] = __float2bfloat16_rn(v[j]); v[j] -= __bfloat162float(tmp[j]); }
+            int4* dst = reinterpret_cast<int4*>(out + part * p.out_part_stride + c0);
+            const int4* src = reinterpret_cast<const int4*>(tmp);
+            dst[0] = src[0];
+            dst[1] = src[1];
+        }
     }
 }
 
@@ -534,6 +584,12 @@ igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
                             if (p.dcoef) sc = __ldg(p.dcoef + (long long)tc.n0 * p.o + oc);
                             if (p.bias) sh = __ldg(p.bias + oc);
                         }
+                        if (p.spade_x) {        // (rstd | mean of the normalised tensor, bias of gamma | beta)
+                            const int C = p.o >> 1;
+                            const float st = etid < C ? __ldg(p.spade_rstd + (long long)tc.n0 * C + etid)
+                                                      : (etid < p.o ? __ldg(p.spade_mean + (long long)tc.n0 * C + (etid - C)) : 0.f);
+                            s_cs[etid] = make_float2(st, sh);
+                        } else
                         s_cs[etid] = make_float2(sc * p.gain, sh * p.gain);
                     }
                     asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -543,7 +599,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
             mbar_wait(tfull_bar(buf), buf_phase);
             tc_fence_after();
             const uint32_t tmem_tile = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * p.block_n);
-            if (p.out_dtype == PGPP_F32) epilogue_dispatch<float>(p, tc, tmem_tile, pc, col_begin, col_end, s_cs, fast);
+            if (p.spade_x) epilogue_spade(p, tc, tmem_tile, pc, half, s_cs);
+            else if (p.out_dtype == PGPP_F32) epilogue_dispatch<float>(p, tc, tmem_tile, pc, col_begin, col_end, s_cs, fast);
             else if (p.out_dtype == PGPP_BF16) epilogue_dispatch<__nv_bfloat16>(p, tc, tmem_tile, pc, col_begin, col_end, s_cs, fast);
             else epilogue_dispatch<__half>(p, tc, tmem_tile, pc, col_begin, col_end, s_cs, fast);
             tc_fence_before();
@@ -676,6 +733,17 @@ extern "C" int pgpp_conv2d_igemm(const pgpp_conv_desc* d, void* stream) {
     p.wgt_per_sample = d->wgt_per_sample ? 1 : 0;
     p.out_parts = out_parts; p.out_part_stride = d->out_part_stride;
     PGPP_REQUIRE(!p.wgt_per_sample || p.tn == 1, "per-sample weights need images of at least 128 pixels (one sample per tile)");
+    p.spade_x = d->spade_x; p.spade_mean = d->spade_mean; p.spade_rstd = d->spade_rstd; p.spade_pre_gain = d->spade_pre_gain;
+    if (d->spade_x) {
+        PGPP_REQUIRE(d->spade_mean && d->spade_rstd, "SPADE epilogue needs mean and rstd");
+        PGPP_REQUIRE(d->phases == 1 && d->o % 32 == 0 && d->block_n == d->o && d->stride == 1 && p.tn == 1,
+                     "SPADE epilogue: o = 2C (gamma | beta) with C % 16 == 0 in ONE column tile (block_n == o), stride 1, images of at least 128 pixels");
+        PGPP_REQUIRE(d->out_dtype == PGPP_BF16 && d->out_stride[1] == 1 && !d->accumulate && d->out_stride[3] % 8 == 0 &&
+                     d->out_part_stride % 8 == 0 && ((uintptr_t)d->out & 15) == 0,
+                     "SPADE epilogue writes the channels-innermost bf16 operand format (16-byte aligned pixels)");
+        PGPP_REQUIRE(d->act_fn == PGPP_ACT_LINEAR && d->gain == 1.f && d->clamp < 0.f && !d->noise && !d->dcoef,
+                     "SPADE epilogue: the GEMM itself must be linear (no noise, demodulation, gain or clamp)");
+    }
     p.fold_gain = (d->gain > 0.f && (d->act_fn == PGPP_ACT_LINEAR || d->act_fn == PGPP_ACT_RELU ||
                                      (d->act_fn == PGPP_ACT_LRELU && d->alpha >= 0.f && d->alpha <= 1.f))) ? 1 : 0;
     auto magic = [](unsigned dv, unsigned& m, unsigned& sft) {

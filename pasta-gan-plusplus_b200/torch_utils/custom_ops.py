@@ -40,6 +40,7 @@ class ConvDesc(ctypes.Structure):
         ('out', ctypes.c_void_p), ('out_dtype', ctypes.c_int32), ('out_h', ctypes.c_int32), ('out_w', ctypes.c_int32),
         ('out_stride', ctypes.c_int64 * 4),
         ('accumulate', ctypes.c_int32), ('out_parts', ctypes.c_int32), ('out_part_stride', ctypes.c_int64),
+        ('spade_x', ctypes.c_void_p), ('spade_mean', ctypes.c_void_p), ('spade_rstd', ctypes.c_void_p), ('spade_pre_gain', ctypes.c_float),
     ]
 
 

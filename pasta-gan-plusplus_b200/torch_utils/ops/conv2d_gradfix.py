@@ -253,12 +253,14 @@ def packed_up2(weight, f, flip_weight, flip_filter, parts):
 
 def igemm_conv(x, pw, *, scale=None, stride=1, out_hw=None, dcoef=None, noise=None, bias=None, act='linear',
                alpha=0.0, gain=1.0, clamp=-1.0, out=None, out_dtype=None, accumulate=False, precision=None,
-               memory_format=None, out_packed=None):
+               memory_format=None, out_packed=None, spade=None):
     """Run one fused convolution.
     x          [N, I, H, W] tensor (any float dtype / layout; packed here, `scale` [N, I] = style modulation folded into the
                packing pass) or a PackedAct (no packing pass; `scale` is then folded into per-sample weights).
     out_packed None -> returns a [N, O, out_h, out_w] tensor (`out` / `out_dtype` / `memory_format` as given);
-               PackedAct view -> the epilogue writes the bf16 operand format of the next conv into that channel slice."""
+               PackedAct view -> the epilogue writes the bf16 operand format of the next conv into that channel slice.
+    spade      (x_norm [N, C, H, W] float32, mean [N, C], rstd [N, C], pre_gain): the GEMM's O = 2C columns are gamma | beta and the
+               epilogue writes pre_act((x_norm - mean) * rstd * (1 + gamma) + beta) into `out_packed` (C channels)."""
     _init()
     n, ic, h, w = x.shape
     im = pw.im2col
@@ -306,7 +308,7 @@ def igemm_conv(x, pw, *, scale=None, stride=1, out_hw=None, dcoef=None, noise=No
         conv_h, conv_w = out_hw
     out_h, out_w = conv_h * up, conv_w * up
     if out_packed is not None:
-        assert tuple(out_packed.data.shape[1:4]) == (n, out_h, out_w) and out_packed.c == pw.o
+        assert tuple(out_packed.data.shape[1:4]) == (n, out_h, out_w) and out_packed.c == (pw.o // 2 if spade is not None else pw.o)
         assert pw.o % 16 == 0 and out_packed.c_off % 8 == 0 and not accumulate
         c_total = out_packed.data.shape[4]
         d.out = out_packed.data.data_ptr() + 2 * out_packed.c_off
@@ -335,6 +337,15 @@ def igemm_conv(x, pw, *, scale=None, stride=1, out_hw=None, dcoef=None, noise=No
     block_n = choose_block_n(pw.phases * pw.phase_stride, m_tiles)
     while pw.o_rows % block_n:
         block_n //= 2
+    if spade is not None:
+        sx, smean, srstd, spre = spade
+        assert out_packed is not None and pw.phases == 1 and pw.o % 32 == 0 and pw.o in (32, 64, 128, 256) and pw.o_rows % pw.o == 0
+        assert sx.dtype == torch.float32 and sx.is_contiguous() and tuple(sx.shape) == (n, pw.o // 2, out_h, out_w)
+        smean = smean.detach().to(torch.float32).reshape(n, pw.o // 2).contiguous()
+        srstd = srstd.detach().to(torch.float32).reshape(n, pw.o // 2).contiguous()
+        keep += [smean, srstd]
+        block_n = pw.o          # gamma and beta of a channel must sit in the same accumulator tile
+        d.spade_x = sx.data_ptr(); d.spade_mean = smean.data_ptr(); d.spade_rstd = srstd.data_ptr(); d.spade_pre_gain = float(spre)
 
     d.n, d.h, d.w, d.c_pad = n, h, w, pw.c_pad
     d.kh, d.kw, d.pad_y, d.pad_x, d.stride = pw.kh, pw.kw, pw.pad_y, pw.pad_x, stride

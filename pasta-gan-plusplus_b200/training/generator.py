@@ -192,6 +192,9 @@ class Spade_Conv2dLayer(torch.nn.Module):
         return conv2d_resample.conv2d_resample(x=x, w=w.to(x.dtype), f=self.resample_filter, padding=self.padding, flip_weight=True)
 
 
+FUSE_SPADE_EPILOGUE = True      # False: gamma|beta GEMM -> float32 NCHW, then pgpp_spade_modulate_pack (kept for comparison / tests)
+
+
 class Spade_Norm_Block(torch.nn.Module):
     def __init__(self, in_channels, norm_channels):
         super().__init__()
@@ -220,7 +223,13 @@ class Spade_Norm_Block(torch.nn.Module):
         nc = self.conv_mlp.weight.shape[0]
         actv = PackedAct(PackedAct.empty(n, h, w, nc, parts, x.device), nc)
         self.conv_mlp.conv_packed(feats_packed, act='relu', gain=1.0, out_packed=actv)
-        gb = conv2d_gradfix.igemm_conv(actv, self._gamma_beta_weights())
+        pw = self._gamma_beta_weights()
+        if FUSE_SPADE_EPILOGUE and pw.o in (64, 128, 256) and pw.o_rows % pw.o == 0 and h * w >= 128:
+            # gamma | beta never leave the SM: the GEMM's epilogue normalises x, modulates it and writes the consumer's operand
+            xn = PackedAct(PackedAct.empty(n, h, w, c, parts, x.device), c)
+            conv2d_gradfix.igemm_conv(actv, pw, out_packed=xn, spade=(x, mean, rstd, pre_gain))
+            return xn
+        gb = conv2d_gradfix.igemm_conv(actv, pw)
         conv2d_gradfix._init()
         c_pad = -(-c // 64) * 64
         data = conv2d_gradfix._plugin.spade_modulate_pack(x, mean, rstd, gb, c_pad, parts, pre_gain)

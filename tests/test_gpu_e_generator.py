@@ -119,3 +119,32 @@ def test_resblock_hand_over_route_matches_composition(down, packed_input):
     assert rel < 1e-4, rel
     # down=1: [pack] + skip + conv0 + conv1;  down=2: 2 FIR + 2 packs + 3 convs
     assert n_launch == ((3 if packed_input else 4) if down == 1 else 7), n_launch
+
+
+@pytest.mark.parametrize('c,hw', [(128, (32, 48)), (64, (24, 40))])
+def test_spade_epilogue_equals_the_two_pass_route(c, hw):
+    """Spade_Norm_Block fused into the gamma|beta GEMM's epilogue (pgpp_conv_desc.spade_*) against the GEMM -> float32 ->
+    pgpp_spade_modulate_pack route: same arithmetic on the same accumulators, so the operands must be bit-identical; and both
+    against the module's op-by-op forward."""
+    torch.manual_seed(5)
+    blk = gen.Spade_Norm_Block(128, c).to(DEV).eval().requires_grad_(False)
+    for p in blk.parameters():
+        p.copy_(torch.randn_like(p))
+    h, w = hw
+    x = torch.randn(2, c, h, w, device=DEV) * 2 + 0.5
+    feats = torch.randn(2, 128, h, w, device=DEV)
+    var, mean = torch.var_mean(x, dim=(2, 3), unbiased=False)
+    rstd = (var + 1e-5).rsqrt()
+    fp = cg.PackedAct(cg._plugin.pack_activations(feats, None, 128, 2), 128) if cg._init() else None
+    outs = []
+    for flag in (True, False):
+        gen.FUSE_SPADE_EPILOGUE = flag
+        try:
+            outs.append(blk.fused_packed(x, mean, rstd, fp, pre_gain=1.25))
+        finally:
+            gen.FUSE_SPADE_EPILOGUE = True
+    assert torch.equal(outs[0].data[..., :c], outs[1].data[..., :c])
+    with torch.no_grad():
+        want = torch.relu(blk(x, feats, fused=False)) * 1.25
+    got = outs[0].to_nchw()
+    assert ((got - want).norm() / want.norm()).item() < 1e-4
