@@ -224,6 +224,16 @@ PGPP_API int pgpp_u8_to_f32(const void* src, int64_t n, int64_t c, int64_t hw, v
  * reverse_channels != 0 (RGB -> BGR, test.py:162-166). */
 PGPP_API int pgpp_image_to_u8(const float* img, int64_t n, int64_t c, int64_t hw, void* out, int reverse_channels, void* stream);
 
+/* ---- grid_sample (torch_utils/ops/grid_sample_gradfix.py:27-83): 2-D, bilinear, zeros padding, align_corners = False ----
+ * input float32 [N,C,H,W] contiguous, grid float32 [N,Ho,Wo,2] contiguous (x, y in [-1, 1]), out float32 [N,C,Ho,Wo].
+ * Replaces aten::grid_sampler_2d (grid_sample_gradfix.py:47). */
+PGPP_API int pgpp_grid_sample_2d(const float* input, const float* grid, float* out, int n, int c, int h, int w, int ho, int wo, void* stream);
+
+/* Replaces aten::grid_sampler_2d_backward (grid_sample_gradfix.py:64-65).  grad_input [N,C,H,W] (zeroed here, scatter-add) and / or
+ * grad_grid [N,Ho,Wo,2]; pass NULL for the one that is not needed. */
+PGPP_API int pgpp_grid_sample_2d_backward(const float* grad_out, const float* input, const float* grid, float* grad_input, float* grad_grid,
+                                 int n, int c, int h, int w, int ho, int wo, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

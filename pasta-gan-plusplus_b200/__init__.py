@@ -2,7 +2,7 @@
 
 Package layout mirrors the reference's import paths for the hot path only:
     torch_utils/custom_ops.py            prebuilt C-ABI library loader (replaces the ninja JIT)
-    torch_utils/ops/{bias_act,upfirdn2d,conv2d_gradfix,conv2d_resample,fma}.py
+    torch_utils/ops/{bias_act,upfirdn2d,conv2d_gradfix,conv2d_resample,fma,grid_sample_gradfix}.py
     training/networks.py                 modulated_conv2d (+ the layer classes that call it)
     csrc/                                CUDA sources of lib/libpgpp_sm100a.so (C ABI: include/pgpp.h)
 
@@ -15,7 +15,7 @@ import sys
 
 __version__ = '0.1.0'
 
-OP_MODULES = ('bias_act', 'upfirdn2d', 'conv2d_gradfix', 'conv2d_resample', 'fma')
+OP_MODULES = ('bias_act', 'upfirdn2d', 'conv2d_gradfix', 'conv2d_resample', 'fma', 'grid_sample_gradfix')
 
 
 def install(patch_networks=True):

@@ -88,6 +88,10 @@ def load_library():
     lib.pgpp_u8_to_f32.argtypes = [vp, i64, i64, i64, vp, i64, i64, i32, vp, vp]
     lib.pgpp_image_to_u8.restype = i32
     lib.pgpp_image_to_u8.argtypes = [vp, i64, i64, i64, vp, i32, vp]
+    lib.pgpp_grid_sample_2d.restype = i32
+    lib.pgpp_grid_sample_2d.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, i32, vp]
+    lib.pgpp_grid_sample_2d_backward.restype = i32
+    lib.pgpp_grid_sample_2d_backward.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp]
     _lib = lib
     return lib
 
@@ -95,7 +99,7 @@ def load_library():
 EXPORTED_SYMBOLS = ('pgpp_version', 'pgpp_last_error', 'pgpp_launch_count', 'pgpp_bias_act', 'pgpp_upfirdn2d',
                     'pgpp_modconv_demod_coefs', 'pgpp_pack_activations', 'pgpp_pack_activations_slice', 'pgpp_modulate_weights',
                     'pgpp_spade_modulate_pack', 'pgpp_mix_pack', 'pgpp_pack_im2col', 'pgpp_conv2d_igemm', 'pgpp_conv2d_wgrad', 'pgpp_u8_to_f32',
-                    'pgpp_image_to_u8')
+                    'pgpp_image_to_u8', 'pgpp_grid_sample_2d', 'pgpp_grid_sample_2d_backward')
 
 
 class WgradDesc(ctypes.Structure):
@@ -382,8 +386,49 @@ class _IoEdgePlugin:
         return out
 
 
+class _GridSamplePlugin:
+    """aten::grid_sampler_2d / grid_sampler_2d_backward with (bilinear, zeros, align_corners=False), the only mode the reference
+    uses (grid_sample_gradfix.py:47,64-65)"""
+
+    @staticmethod
+    def _check_operands(input, grid):
+        _torch_check(input.is_cuda and grid.is_cuda and input.device == grid.device, 'input and grid must reside on the same CUDA device')
+        _torch_check(input.dtype == torch.float32 and grid.dtype == torch.float32, 'grid_sample: float32 tensors only')
+        _torch_check(input.dim() == 4 and grid.dim() == 4 and grid.shape[3] == 2 and grid.shape[0] == input.shape[0],
+                     'grid_sample: input [N,C,H,W], grid [N,Ho,Wo,2]')
+        _torch_check(input.shape[2] >= 1 and input.shape[3] >= 1, 'grid_sample: input must be at least 1x1')
+
+    @staticmethod
+    def forward(input, grid):
+        _GridSamplePlugin._check_operands(input, grid)
+        lib = load_library()
+        input, grid = input.contiguous(), grid.contiguous()
+        n, c, h, w = input.shape
+        ho, wo = grid.shape[1], grid.shape[2]
+        out = torch.empty([n, c, ho, wo], dtype=torch.float32, device=input.device)
+        with torch.cuda.device(input.device):
+            _check(lib.pgpp_grid_sample_2d(_ptr(input), _ptr(grid), _ptr(out), n, c, h, w, ho, wo, _stream(input)))
+        return out
+
+    @staticmethod
+    def backward(grad_output, input, grid, need_input=True, need_grid=True):
+        _GridSamplePlugin._check_operands(input, grid)
+        lib = load_library()
+        grad_output, input, grid = grad_output.to(torch.float32).contiguous(), input.contiguous(), grid.contiguous()
+        n, c, h, w = input.shape
+        ho, wo = grid.shape[1], grid.shape[2]
+        _torch_check(tuple(grad_output.shape) == (n, c, ho, wo), 'grid_sample backward: grad_output has the wrong shape')
+        gi = torch.empty_like(input) if need_input else None
+        gg = torch.empty_like(grid) if need_grid else None
+        if need_input or need_grid:
+            with torch.cuda.device(input.device):
+                _check(lib.pgpp_grid_sample_2d_backward(_ptr(grad_output), _ptr(input), _ptr(grid), _ptr(gi), _ptr(gg), n, c, h, w, ho, wo,
+                                                        _stream(input)))
+        return gi, gg
+
+
 _PLUGINS = {'bias_act_plugin': _BiasActPlugin, 'upfirdn2d_plugin': _Upfirdn2dPlugin, 'conv2d_plugin': _ConvPlugin,
-            'io_edge_plugin': _IoEdgePlugin}
+            'io_edge_plugin': _IoEdgePlugin, 'grid_sample_plugin': _GridSamplePlugin}
 
 
 def get_plugin(module_name, sources=None, **build_kwargs):
