@@ -182,6 +182,15 @@ PGPP_API int pgpp_conv2d_igemm(const pgpp_conv_desc* desc, void* stream);
 PGPP_API int pgpp_mix_pack(const float* x1, const float* m1, const float* a1, const float* b1, const float* x2, const float* m2,
                   const float* a2, const float* b2, void* out, int n, int c, int h, int w, int c_pad, int parts, void* stream);
 
+/* Direct (CUDA-core, exact float32) convolution for few-tap inputs, C * kh * kw <= 16, kw = 1 or 3, 'same' padding, stride 1 (the 3x3 conv on the
+ * 1-channel parsing map of the SPADE blocks, networks.py:1702-1723; the 1x1 stem on the 5-channel pose map, :357-371):
+ *   y = clamp(act(conv(x, w * wscale) + bias) * gain)
+ * x float32 [N,C,H,W] contiguous, w float32 [O,C,kh,kw] contiguous; the result goes EITHER to out_nchw (float32 [N,O,H,W]) OR to
+ * out_packed (bf16 operand format [parts][N][H][W][c_total], channels [c_off, c_off + O)). */
+PGPP_API int pgpp_conv2d_direct(const float* x, const float* w, const float* bias, int n, int c, int h, int wd, int o, int kh, int kw,
+                       int pad_y, int pad_x, float wscale, int act_fn, float alpha, float gain, float clamp,
+                       float* out_nchw, void* out_packed, int c_total, int c_off, int parts, void* stream);
+
 /* ---- weight gradient (conv2d_gradfix.py:135-142, Conv2dGradWeight.forward: replaces
  * aten::cudnn_convolution_backward_weight / cudnn_convolution_transpose_backward_weight) ----
  *

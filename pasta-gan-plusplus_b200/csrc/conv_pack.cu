@@ -281,6 +281,111 @@ __global__ void __launch_bounds__(256) spade_pack_kernel(SpadeArgs p, TileGeom g
     emit_tile(v, sm_packets, p.parts, p.out, p.part_stride, n, p.h, p.w, y0, x0, g.log_tw, c0, p.c_pad, p.c_pad, 0);
 }
 
+struct DirectArgs {
+    const float* x; const float* w; const float* bias; float* out_nchw; __nv_bfloat16* out_packed;
+    int n, c, h, wd, o, kh, kw, pad_y, pad_x, taps;
+    int act; float alpha, gain, clamp, wscale;
+    int c_pad, c_total, c_off, parts; long long part_stride;
+};
+
+// Direct (CUDA-core, exact fp32) convolution for inputs with very few taps per output (C * kh * kw <= 16: the 3x3 conv_mlp on the
+// 1-channel parsing map, the 1x1 stem on the 5-channel pose map).  Such layers are bound by writing their 64..128-channel output;
+// expanding the input to 64-channel operand rows for the tensor-core path costs 3-4x their roofline time.  Same 64-channel x
+// 128-pixel tile and thread mapping as pack_nchw_kernel: a thread accumulates 8 output channels x 4 pixels from a sliding window
+// of the input rows, weights are broadcast from shared memory, and the result leaves either as NCHW float32 (128-bit stores) or
+// through emit_tile as the bf16 operand format of the next convolution, with bias / activation / gain / clamp applied.
+constexpr int kDirectMaxTaps = 16;
+
+template <int KW>
+__global__ void __launch_bounds__(256) conv_direct_kernel(DirectArgs p, TileGeom g, long long total_tiles) {
+    extern __shared__ uint4 sm_packets[];
+    __shared__ float sw[64 * kDirectMaxTaps];
+    __shared__ float sb[64];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int tw_mask = (1 << g.log_tw) - 1;
+    const long long plane = (long long)p.h * p.wd;
+    int loaded_ct = -1;
+    // persistent over the tiles: the weights of a 64-channel tile are staged once (the channel tile is the slowest tile index)
+    for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        long long b = tile;
+        const int xt = (int)(b % g.x_tiles); b /= g.x_tiles;
+        const int yt = (int)(b % g.y_tiles); b /= g.y_tiles;
+        const int n = (int)(b % p.n);
+        const int ct = (int)(b / p.n);
+        const int x0 = xt << g.log_tw, y0 = yt * (128 >> g.log_tw), c0 = ct * 64;
+        __syncthreads();                        // previous tile's packets fully written out; weights no longer in use
+        if (ct != loaded_ct) {
+            for (int i = threadIdx.x; i < 64 * p.taps; i += 256) {
+                const int oc = c0 + i / p.taps;
+                sw[i] = oc < p.o ? p.w[(long long)oc * p.taps + i % p.taps] * p.wscale : 0.f;
+            }
+            if (threadIdx.x < 64) sb[threadIdx.x] = (p.bias && c0 + threadIdx.x < p.o) ? p.bias[c0 + threadIdx.x] : 0.f;
+            loaded_ct = ct;
+            __syncthreads();
+        }
+        const int y = y0 + ((4 * lane) >> g.log_tw), x = x0 + ((4 * lane) & tw_mask);
+        float v[8][4];
+        #pragma unroll
+        for (int i = 0; i < 8; i++)
+            #pragma unroll
+            for (int k = 0; k < 4; k++) v[i][k] = 0.f;
+        if (y < p.h && x < p.wd) {
+            const float* src = p.x + (long long)n * p.c * plane;
+            const float* wrow = sw + warp * 8 * p.taps;
+            for (int ci = 0; ci < p.c; ci++, src += plane) {
+                for (int ky = 0; ky < p.kh; ky++) {
+                    const int iy = y + ky - p.pad_y;
+                    const bool row_ok = iy >= 0 && iy < p.h;
+                    const float* row = src + (long long)iy * p.wd;
+                    float in[4 + KW - 1];
+                    #pragma unroll
+                    for (int j = 0; j < 4 + KW - 1; j++) {
+                        const int ix = x + j - KW / 2;
+                        in[j] = (row_ok && ix >= 0 && ix < p.wd) ? __ldg(row + ix) : 0.f;
+                    }
+                    const float* wt = wrow + (ci * p.kh + ky) * KW;
+                    #pragma unroll
+                    for (int kx = 0; kx < KW; kx++)
+                        #pragma unroll
+                        for (int i = 0; i < 8; i++) {
+                            const float wv = wt[i * p.taps + kx];
+                            #pragma unroll
+                            for (int k = 0; k < 4; k++) v[i][k] = fmaf(wv, in[kx + k], v[i][k]);
+                        }
+                }
+            }
+        }
+        #pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const float bb = sb[warp * 8 + i];
+            #pragma unroll
+            for (int k = 0; k < 4; k++) {
+                float r = v[i][k] + bb;
+                if (p.act == PGPP_ACT_RELU) r = fmaxf(r, 0.f);
+                else if (p.act == PGPP_ACT_LRELU) r = r > 0.f ? r : r * p.alpha;
+                r *= p.gain;
+                if (p.clamp >= 0.f) r = fminf(fmaxf(r, -p.clamp), p.clamp);
+                v[i][k] = r;
+            }
+        }
+        if (p.out_packed) {
+            emit_tile(v, sm_packets, p.parts, p.out_packed, p.part_stride, n, p.h, p.wd, y0, x0, g.log_tw, c0, p.c_pad, p.c_total, p.c_off);
+        } else if (y < p.h && x < p.wd) {
+            #pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const int oc = c0 + warp * 8 + i;
+                if (oc >= p.o) continue;
+                float* dst = p.out_nchw + ((long long)n * p.o + oc) * plane + (long long)y * p.wd + x;
+                if (x + 3 < p.wd && (p.wd & 3) == 0) __stcs(reinterpret_cast<float4*>(dst), make_float4(v[i][0], v[i][1], v[i][2], v[i][3]));
+                else {
+                    #pragma unroll
+                    for (int k = 0; k < 4; k++) if (x + k < p.wd) dst[k] = v[i][k];
+                }
+            }
+        }
+    }
+}
+
 struct MixArgs {
     const float* x[2]; const float* m[2]; const float* a[2]; const float* b[2]; __nv_bfloat16* out;
     int n, c, h, w, c_pad, parts, terms; long long part_stride;
@@ -527,6 +632,44 @@ extern "C" int pgpp_mix_pack(const float* x1, const float* m1, const float* a1, 
     const bool vec = w % 4 == 0 && (al & 15) == 0;
     if (vec) mix_pack_kernel<true><<<(unsigned)blocks, 256, smem, (cudaStream_t)stream>>>(p, g);
     else mix_pack_kernel<false><<<(unsigned)blocks, 256, smem, (cudaStream_t)stream>>>(p, g);
+    count_launch();
+    PGPP_CUDA_OK(cudaGetLastError());
+    return PGPP_OK;
+}
+
+extern "C" int pgpp_conv2d_direct(const float* x, const float* w, const float* bias, int n, int c, int h, int wd, int o, int kh, int kw,
+                                  int pad_y, int pad_x, float wscale, int act_fn, float alpha, float gain, float clamp,
+                                  float* out_nchw, void* out_packed, int c_total, int c_off, int parts, void* stream) {
+    using namespace pgpp;
+    PGPP_REQUIRE(x && w && (out_nchw != nullptr) != (out_packed != nullptr), "x, w and exactly one of out_nchw / out_packed are required");
+    PGPP_REQUIRE(n >= 1 && c >= 1 && h >= 1 && wd >= 1 && o >= 1, "empty problem");
+    PGPP_REQUIRE(kh >= 1 && (kw == 1 || kw == 3) && c * kh * kw <= kDirectMaxTaps, "direct convolution: C * kh * kw <= 16 and kw = 1 or 3");
+    PGPP_REQUIRE(2 * pad_y == kh - 1 && 2 * pad_x == kw - 1, "direct convolution: 'same' padding only");
+    PGPP_REQUIRE(act_fn == PGPP_ACT_LINEAR || act_fn == PGPP_ACT_RELU || act_fn == PGPP_ACT_LRELU, "direct convolution: linear, relu or lrelu");
+    DirectArgs p;
+    p.x = x; p.w = w; p.bias = bias; p.out_nchw = out_nchw; p.out_packed = (__nv_bfloat16*)out_packed;
+    p.n = n; p.c = c; p.h = h; p.wd = wd; p.o = o; p.kh = kh; p.kw = kw; p.pad_y = pad_y; p.pad_x = pad_x; p.taps = c * kh * kw;
+    p.act = act_fn; p.alpha = alpha; p.gain = gain; p.clamp = clamp; p.wscale = wscale;
+    p.parts = parts; p.c_total = c_total; p.c_off = c_off; p.c_pad = (o + 7) / 8 * 8;
+    p.part_stride = (long long)n * h * wd * c_total;
+    size_t smem = 0;
+    if (out_packed) {
+        PGPP_REQUIRE(parts >= 1 && parts <= 3 && o % 8 == 0 && c_off % 8 == 0 && c_total % 8 == 0 && c_total >= c_off + o &&
+                     ((uintptr_t)out_packed & 15) == 0, "bad packed destination");
+        smem = (size_t)parts * 128 * 8 * sizeof(uint4);
+    }
+    TileGeom g = tile_geometry(h, wd, (o + 63) / 64 * 64);
+    const long long total = (long long)g.x_tiles * g.y_tiles * g.c_tiles * n;
+    auto launch = [&](auto kernel) -> int {
+        if (smem > 40 * 1024) PGPP_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        long long blocks = total;
+        const long long cap = (long long)sm_count() * occupancy_of(kernel, 256, smem);
+        if (blocks > cap) blocks = cap;
+        kernel<<<(unsigned)blocks, 256, smem, (cudaStream_t)stream>>>(p, g, total);
+        return PGPP_OK;
+    };
+    const int rc = kw == 1 ? launch(conv_direct_kernel<1>) : launch(conv_direct_kernel<3>);
+    if (rc != PGPP_OK) return rc;
     count_launch();
     PGPP_CUDA_OK(cudaGetLastError());
     return PGPP_OK;

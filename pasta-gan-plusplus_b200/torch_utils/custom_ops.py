@@ -80,6 +80,8 @@ def load_library():
     lib.pgpp_spade_modulate_pack.argtypes = [vp, vp, vp, vp, vp, i64, vp, i32, i32, i32, i32, i32, i32, f32, vp]
     lib.pgpp_mix_pack.restype = i32
     lib.pgpp_mix_pack.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp]
+    lib.pgpp_conv2d_direct.restype = i32
+    lib.pgpp_conv2d_direct.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, f32, i32, f32, f32, f32, vp, vp, i32, i32, i32, vp]
     lib.pgpp_conv2d_igemm.restype = i32
     lib.pgpp_conv2d_igemm.argtypes = [ctypes.POINTER(ConvDesc), vp]
     lib.pgpp_conv2d_wgrad.restype = i32
@@ -98,7 +100,7 @@ def load_library():
 
 EXPORTED_SYMBOLS = ('pgpp_version', 'pgpp_last_error', 'pgpp_launch_count', 'pgpp_bias_act', 'pgpp_upfirdn2d',
                     'pgpp_modconv_demod_coefs', 'pgpp_pack_activations', 'pgpp_pack_activations_slice', 'pgpp_modulate_weights',
-                    'pgpp_spade_modulate_pack', 'pgpp_mix_pack', 'pgpp_pack_im2col', 'pgpp_conv2d_igemm', 'pgpp_conv2d_wgrad', 'pgpp_u8_to_f32',
+                    'pgpp_spade_modulate_pack', 'pgpp_mix_pack', 'pgpp_conv2d_direct', 'pgpp_pack_im2col', 'pgpp_conv2d_igemm', 'pgpp_conv2d_wgrad', 'pgpp_u8_to_f32',
                     'pgpp_image_to_u8', 'pgpp_grid_sample_2d', 'pgpp_grid_sample_2d_backward')
 
 
@@ -315,6 +317,31 @@ class _ConvPlugin:
         with torch.cuda.device(x.device):
             _check(lib.pgpp_spade_modulate_pack(_ptr(x), _ptr(mean), _ptr(rstd), ctypes.c_void_p(gamma_ptr), ctypes.c_void_p(beta_ptr),
                                                 2 * c * h * w, _ptr(out), n, c, h, w, int(c_pad), int(parts), float(pre_gain), _stream(x)))
+        return out
+
+    @staticmethod
+    def conv2d_direct(x, weight, bias, wscale, act_idx, alpha, gain, clamp, out_packed_data=None, c_off=0):
+        """exact-fp32 direct convolution for C*kh*kw <= 16 ('same' padding): returns float32 [N,O,H,W], or writes channels
+        [c_off, c_off+O) of the operand-format buffer `out_packed_data` [parts,N,H,W,c_total]; see pgpp_conv2d_direct"""
+        lib = load_library()
+        _torch_check(x.is_cuda and x.dtype == torch.float32 and x.dim() == 4, 'conv2d_direct: x must be a float32 CUDA tensor [N,C,H,W]')
+        x = x.contiguous()
+        w = weight.detach().to(torch.float32).contiguous()
+        n, c, h, wd = x.shape
+        o, ic, kh, kw = w.shape
+        _torch_check(ic == c, 'conv2d_direct: channel mismatch')
+        b = bias.detach().to(torch.float32).contiguous() if bias is not None else None
+        out = None
+        if out_packed_data is None:
+            out = torch.empty([n, o, h, wd], dtype=torch.float32, device=x.device)
+            parts, c_total = 0, 0
+        else:
+            _torch_check(out_packed_data.dtype == torch.bfloat16 and tuple(out_packed_data.shape[1:4]) == (n, h, wd), 'conv2d_direct: bad packed destination')
+            parts, c_total = out_packed_data.shape[0], out_packed_data.shape[4]
+        with torch.cuda.device(x.device):
+            _check(lib.pgpp_conv2d_direct(_ptr(x), _ptr(w), _ptr(b), n, c, h, wd, o, kh, kw, kh // 2, kw // 2, float(wscale), int(act_idx),
+                                          float(alpha), float(gain), float(clamp), _ptr(out), _ptr(out_packed_data), int(c_total), int(c_off),
+                                          int(parts), _stream(x)))
         return out
 
     @staticmethod

@@ -21,6 +21,7 @@ csrc/conv_wgrad.cu (`pgpp_conv2d_wgrad`); no library convolution is called anywh
 """
 import contextlib
 import ctypes
+import os
 
 import torch
 
@@ -29,6 +30,7 @@ from .. import custom_ops
 enabled = True                      # the reference defaults to False and train.py flips it; here the kernel IS the path
 weight_gradients_disabled = False
 fp32_precision = 'bf16x2'
+direct_few_tap_convs = os.environ.get('PGPP_NO_DIRECT_CONV') is None    # C*kh*kw <= 16 convs on the exact-fp32 direct kernel
 
 _PRODUCTS = {'bf16': (1, 1), 'bf16x2': (3, 2), 'bf16x3': (6, 3)}    # name -> (products, parts)
 _ACT_IDX = {'linear': 1, 'relu': 2, 'lrelu': 3, 'tanh': 4, 'sigmoid': 5, 'elu': 6, 'selu': 7, 'softplus': 8, 'swish': 9}
@@ -125,6 +127,26 @@ class PackedAct:
         """debug / test helper: sum of the parts as a [N, C, H, W] tensor"""
         v = self.data[:, :, :, :, self.c_off:self.c_off + self.c].to(torch.float32).sum(0)
         return v.permute(0, 3, 1, 2).contiguous().to(dtype)
+
+
+def direct_conv_ok(weight, act='linear'):
+    """few-tap convolutions (C*kh*kw <= 16, odd filter, 'same' padding) take the exact-fp32 direct kernel instead of being
+    expanded to 64-channel tensor-core operands"""
+    o, ic, kh, kw = weight.shape
+    if not direct_few_tap_convs:
+        return False
+    return ic * kh * kw <= 16 and kh % 2 == 1 and kw in (1, 3) and act in ('linear', 'relu', 'lrelu')
+
+
+def direct_conv(x, weight, bias=None, *, wscale=1.0, act='linear', alpha=0.0, gain=1.0, clamp=-1.0, out_packed=None):
+    """y = clamp(act(conv2d(x, weight * wscale, padding='same') + bias) * gain) on pgpp_conv2d_direct; `out_packed`: PackedAct view
+    to receive the operand format instead of returning an NCHW tensor"""
+    _init()
+    if out_packed is not None:
+        assert out_packed.c == weight.shape[0]
+        _plugin.conv2d_direct(x, weight, bias, wscale, _ACT_IDX[act], alpha, gain, clamp, out_packed.data, out_packed.c_off)
+        return out_packed
+    return _plugin.conv2d_direct(x, weight, bias, wscale, _ACT_IDX[act], alpha, gain, clamp)
 
 
 def choose_block_n(cols, m_tiles, sms=148):

@@ -160,6 +160,14 @@ class StyleEncoderNetworkV18(torch.nn.Module):
         return self.fc(x.view(x.size(0), -1), impl=impl), const_feats
 
 
+class RawFeat:
+    """few-channel NCHW float32 feature map handed to `Spade_Conv2dLayer.conv_packed` as is (no operand-format expansion)"""
+    __slots__ = ('x',)
+
+    def __init__(self, x):
+        self.x = x
+
+
 class Spade_Conv2dLayer(torch.nn.Module):
     """pre-activation (bias_act relu, gain) followed by a plain convolution (networks.py:1627-1633)"""
 
@@ -174,7 +182,11 @@ class Spade_Conv2dLayer(torch.nn.Module):
         self.bias = torch.nn.Parameter(torch.zeros([out_channels])) if bias else None
 
     def conv_packed(self, xp, act='linear', gain=1.0, out_packed=None, out=None, accumulate=False):
-        """the convolution alone on an operand-format input (pre-activation already applied by the producer of `xp`)"""
+        """the convolution alone on an operand-format input (pre-activation already applied by the producer of `xp`); a
+        `RawFeat` input (few-channel NCHW map) goes through the exact-fp32 direct kernel instead"""
+        if isinstance(xp, RawFeat):
+            assert out is None and not accumulate
+            return conv2d_gradfix.direct_conv(xp.x, self.weight, None, wscale=self.weight_gain, act=act, gain=gain, out_packed=out_packed)
         pw = conv2d_gradfix.packed_plain(self.weight, True, S._parts(), self.padding, self.padding, scale=self.weight_gain,
                                          allow_im2col=xp.logical_hw is not None)
         return conv2d_gradfix.igemm_conv(xp, pw, act=act, gain=gain, out_packed=out_packed, out=out, accumulate=accumulate)
@@ -269,7 +281,10 @@ class Spade_ResBlockV4_512(torch.nn.Module):
                 conv2d_gradfix._init()
                 fc, fh, fw = denorm_feat.shape[1:]
                 r = conv2d_gradfix.im2col_rows(fc, 3, 3) if (fh >= 8 and fw >= 16) else 0
-                if r:       # 1-channel parsing map: all 9 taps of the three conv_mlp layers go into the channel dimension
+                if denorm_feat.dtype == torch.float32 and conv2d_gradfix.direct_conv_ok(self.spade0.conv_mlp.weight, 'relu') and \
+                        self.spade0.conv_mlp.bias is None:
+                    feats_packed = RawFeat(denorm_feat)     # 1-channel parsing map: exact-fp32 direct conv, no 64-channel expansion
+                elif r:     # few-channel map: all taps of the three conv_mlp layers go into the channel dimension
                     data = conv2d_gradfix._plugin.pack_im2col(denorm_feat, None, 3, r, 1, 1, S._parts())
                     feats_packed = PackedAct(data, r * 3 * fc, 0, logical_hw=(fh, fw))
                 else:

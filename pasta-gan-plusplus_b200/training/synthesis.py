@@ -85,6 +85,13 @@ class Conv2dLayer(torch.nn.Module):
         (or add, `y = skip + conv1(...)` of the residual blocks) into an existing NCHW float32 tensor.  Fused route only."""
         act_gain = self.act_gain * gain
         act_clamp = self.conv_clamp * gain if self.conv_clamp is not None else None
+        if fused and self.up == 1 and self.down == 1 and _can_fuse(x, self.weight, self.bias) and not isinstance(x, PackedAct) and \
+                x.dtype == torch.float32 and out is None and self.padding * 2 == self.weight.shape[-1] - 1 and \
+                conv2d_gradfix.direct_conv_ok(self.weight, self.activation):
+            # few-tap stem (e.g. 1x1 on the 5-channel pose map): exact-fp32 direct kernel, bound by writing its output
+            return conv2d_gradfix.direct_conv(x, self.weight, self.bias, wscale=self.weight_gain, act=self.activation,
+                                              alpha=bias_act.activation_funcs[self.activation].def_alpha, gain=act_gain,
+                                              clamp=-1 if act_clamp is None else act_clamp, out_packed=out_packed)
         if fused and self.up == 1 and self.down == 1 and _can_fuse(x, self.weight, self.bias):
             parts = _parts() if isinstance(x, PackedAct) else conv2d_gradfix._PRODUCTS[conv2d_gradfix.precision_for(x.dtype)][1]
             im2col = (not isinstance(x, PackedAct)) and x.shape[2] >= 8 and x.shape[3] >= 16      # few-channel stems (7x7 RGB, 3x3 on 6 ch)

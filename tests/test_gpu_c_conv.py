@@ -232,7 +232,43 @@ def test_few_channel_convs_through_row_group_im2col(ic, k, pad, h, w):
     with torch.no_grad():
         got = layer(x, fused=True)
         want = layer(x.cpu().double(), fused=False, impl='ref') if False else None
-    assert custom_ops.launch_count() - before == 2          # one im2col pack + one GEMM
+    # one im2col pack + one GEMM; the 9-tap case (1 channel, 3x3) takes the direct fp32 kernel instead: one launch
+    assert custom_ops.launch_count() - before == (1 if ic * k * k <= 16 else 2)
     wgt = layer.weight.detach().cpu().double() * layer.weight_gain
     want = ref_ops.bias_act(ref_ops.conv2d(x.cpu().double(), wgt, padding=pad), layer.bias.detach().cpu().double(), act='relu')
     assert rel_l2(got, want) < TOL['bf16x3'], rel_l2(got, want)
+
+
+@pytest.mark.parametrize('ic,oc,k,h,w', [(1, 64, 3, 64, 128), (5, 64, 1, 40, 56), (1, 128, 3, 17, 23), (4, 72, 1, 9, 130), (2, 64, 1, 4, 4),
+                                          (1, 8, 3, 33, 7)])
+@pytest.mark.parametrize('act', ['linear', 'relu', 'lrelu'])
+def test_direct_few_tap_convolution(ic, oc, k, h, w, act):
+    """pgpp_conv2d_direct (C*kh*kw <= 16, exact fp32) against float64 F.conv2d: NCHW result and operand-format result"""
+    g = torch.Generator().manual_seed(51)
+    x = torch.randn(2, ic, h, w, generator=g)
+    wt = torch.randn(oc, ic, k, k, generator=g)
+    b = torch.randn(oc, generator=g)
+    assert cg.direct_conv_ok(wt, act)
+    y = torch.nn.functional.conv2d(x.double(), wt.double() * 0.37, b.double(), padding=k // 2)
+    want = {'linear': y, 'relu': y.clamp(min=0), 'lrelu': torch.where(y > 0, y, y * 0.2)}[act] * 1.3
+    want = want.clamp(-2.5, 2.5)
+    kw = dict(wscale=0.37, act=act, alpha=0.2, gain=1.3, clamp=2.5)
+    got = cg.direct_conv(x.to(DEV), wt.to(DEV), b.to(DEV), **kw)
+    assert got.dtype == torch.float32 and tuple(got.shape) == tuple(want.shape)
+    assert max_abs(got, want) <= 2e-6 * max(1.0, want.abs().max().item())
+    if oc % 8 == 0:
+        for parts, tol in ((3, 2e-6), (2, 2e-5), (1, 4e-3)):
+            buf = cg.PackedAct.empty(2, h, w, oc + 64, parts, DEV)
+            buf.fill_(7.0)
+            out = cg.direct_conv(x.to(DEV), wt.to(DEV), b.to(DEV), out_packed=cg.PackedAct(buf, oc, 64), **kw)
+            assert max_abs(out.to_nchw(), want) <= tol * 2.5
+            assert torch.all(buf[..., :64] == 7.0)                      # the neighbouring channel slice is untouched
+
+
+def test_direct_convolution_rejects_what_it_does_not_cover():
+    x = torch.randn(1, 2, 8, 8, device=DEV)
+    assert not cg.direct_conv_ok(torch.empty(8, 2, 3, 3)) and not cg.direct_conv_ok(torch.empty(8, 1, 3, 3), 'tanh')
+    with pytest.raises(RuntimeError, match='C \\* kh \\* kw <= 16'):
+        cg.direct_conv(x, torch.randn(8, 2, 3, 3, device=DEV))
+    with pytest.raises(RuntimeError, match='channel mismatch'):
+        cg.direct_conv(x, torch.randn(8, 1, 3, 3, device=DEV))

@@ -54,3 +54,11 @@ for (n, c, h, w) in [(32, 128, 256, 160), (32, 64, 512, 320)]:
 x = torch.randn(32, 3, 512, 320, device=dev)
 ms = timeit(lambda: plugin.pack_im2col(x, None, 7, 3, 3, 3, 2))
 report('im2col 32x3x512x320 k7 r3 -> 2 parts', ms, x.numel() * 4 + 32 * 515 * 320 * 64 * 2 * 2)
+
+cg = __import__('importlib').import_module('pgpp_b200.torch_utils.ops.conv2d_gradfix')
+for (ic, oc, k, h, w, packed) in [(1, 64, 3, 512, 512, True), (1, 64, 3, 512, 512, False), (5, 64, 1, 512, 512, False), (1, 128, 3, 256, 256, True)]:
+    x = torch.randn(32, ic, h, w, device=dev)
+    wt = torch.randn(oc, ic, k, k, device=dev)
+    op = cg.PackedAct(cg.PackedAct.empty(32, h, w, oc, 2, dev), oc) if packed else None
+    ms = timeit(lambda: cg.direct_conv(x, wt, None, act='relu', out_packed=op))
+    report(f'direct conv {ic}->{oc} k{k} 32x{h}x{w} -> {"2 bf16 parts" if packed else "f32 NCHW"}', ms, x.numel() * 4 + 32 * oc * h * w * 4)
