@@ -191,6 +191,12 @@ PGPP_API int pgpp_conv2d_direct(const float* x, const float* w, const float* bia
                        int pad_y, int pad_x, float wscale, int act_fn, float alpha, float gain, float clamp,
                        float* out_nchw, void* out_packed, int c_total, int c_off, int parts, void* stream);
 
+/* FIR blur written straight into the operand format (conv2d_resample.py:119-122, "blur, then strided convolution", without the
+ * float32 intermediate): upfirdn2d with up = down = 1 and a filter of at most 4 x 4 on x (float32 [N,C,H,W], unit stride along W,
+ * element strides given) -> bf16 [parts][N][H'][W'][c_pad], H' = H + pady0 + pady1 - fh + 1.  f is a HOST array of fh * fw taps. */
+PGPP_API int pgpp_fir_pack(const float* x, const int64_t size[4], const int64_t stride[4], const float* f_host, int fw, int fh,
+                  int padx0, int padx1, int pady0, int pady1, int flip, float gain, void* out, int c_pad, int parts, void* stream);
+
 /* ---- weight gradient (conv2d_gradfix.py:135-142, Conv2dGradWeight.forward: replaces
  * aten::cudnn_convolution_backward_weight / cudnn_convolution_transpose_backward_weight) ----
  *

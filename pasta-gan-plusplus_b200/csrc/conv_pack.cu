@@ -386,6 +386,80 @@ __global__ void __launch_bounds__(256) conv_direct_kernel(DirectArgs p, TileGeom
     }
 }
 
+struct FirPackArgs {
+    const float* x; __nv_bfloat16* out;
+    int n, c, ih, iw, oh, ow, padx0, pady0, c_pad, parts;
+    long long xs_n, xs_c, xs_h, part_stride;
+    float k[4][4];              // taps, flipped / zero-padded to 4 x 4 and scaled by gain on the host
+};
+
+// FIR blur (up = down = 1, filter up to 4 x 4) of an NCHW float32 tensor written directly in the operand format: the
+// "blur, then strided convolution" pair of conv2d_resample.py:119-122 without the float32 intermediate.  A CTA owns 64 channels
+// of a 32 x 4 block of output pixels: the 35 x 7 input halo of every channel is staged in shared memory with coalesced loads,
+// thread (warp w, lane l) filters channels 8w..8w+7 of 4 consecutive pixels from it, and the packets leave through emit_tile
+// (which reuses the staging buffer).
+constexpr int kFirTw = 32, kFirTh = 4, kFirPitch = 36, kFirRows = kFirTh + 3;
+
+__global__ void __launch_bounds__(256) fir_pack_kernel(FirPackArgs p, int x_tiles, int y_tiles, int c_tiles) {
+    extern __shared__ uint4 sm_packets[];
+    float* stage = reinterpret_cast<float*>(sm_packets);                 // [64][kFirRows][kFirPitch]
+    long long b = blockIdx.x;
+    const int xt = (int)(b % x_tiles); b /= x_tiles;
+    const int ct = (int)(b % c_tiles); b /= c_tiles;
+    const int yt = (int)(b % y_tiles);
+    const int n = (int)(b / y_tiles);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int x0 = xt * kFirTw, y0 = yt * kFirTh, c0 = ct * 64;
+    const int ix0 = x0 - p.padx0, iy0 = y0 - p.pady0;
+    // stage: one (channel, row) of 35 floats per warp and step, lanes along x; 8 steps are issued back to back so that 8..16 loads
+    // per lane are in flight before the first shared-memory store
+    for (int i0 = 0; i0 < 64 * kFirRows / 8; i0 += 8) {
+        float va[8], vb[8];
+        #pragma unroll
+        for (int u = 0; u < 8; u++) {
+            const int cr = warp + 8 * (i0 + u);
+            const int ch = cr / kFirRows, r = cr - ch * kFirRows;
+            const int c = c0 + ch, iy = iy0 + r;
+            const bool ok = c < p.c && iy >= 0 && iy < p.ih;
+            const float* row = p.x + n * p.xs_n + (long long)c * p.xs_c + (long long)iy * p.xs_h;
+            const int ixa = ix0 + lane, ixb = ix0 + lane + 32;
+            va[u] = (ok && ixa >= 0 && ixa < p.iw) ? __ldg(row + ixa) : 0.f;
+            vb[u] = (ok && lane < kFirTw + 3 - 32 && ixb >= 0 && ixb < p.iw) ? __ldg(row + ixb) : 0.f;
+        }
+        #pragma unroll
+        for (int u = 0; u < 8; u++) {
+            const int cr = warp + 8 * (i0 + u);
+            float* dst = stage + cr * kFirPitch;
+            dst[lane] = va[u];
+            if (lane < kFirPitch - 32) dst[lane + 32] = vb[u];
+        }
+    }
+    __syncthreads();
+    const int r = lane >> 3, cx = (lane & 7) * 4;                   // pixel row of the tile, first of the 4 columns
+    float v[8][4];
+    #pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const float* src = stage + ((warp * 8 + i) * kFirRows + r) * kFirPitch + cx;
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        #pragma unroll
+        for (int jy = 0; jy < 4; jy++) {
+            // 8 consecutive staged floats as two 128-bit loads (cx and the row pitch are multiples of 4): a quarter warp reads
+            // 128 contiguous bytes, no bank conflicts
+            const float4 lo = *reinterpret_cast<const float4*>(src + jy * kFirPitch);
+            const float4 hi = *reinterpret_cast<const float4*>(src + jy * kFirPitch + 4);
+            const float in[7] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z};
+            #pragma unroll
+            for (int jx = 0; jx < 4; jx++)
+                #pragma unroll
+                for (int k = 0; k < 4; k++) acc[k] = fmaf(in[k + jx], p.k[jy][jx], acc[k]);
+        }
+        #pragma unroll
+        for (int k = 0; k < 4; k++) v[i][k] = acc[k];
+    }
+    __syncthreads();                                                // staging buffer becomes the packet buffer
+    emit_tile(v, sm_packets, p.parts, p.out, p.part_stride, n, p.oh, p.ow, y0, x0, 5, c0, p.c_pad, p.c_pad, 0);
+}
+
 struct MixArgs {
     const float* x[2]; const float* m[2]; const float* a[2]; const float* b[2]; __nv_bfloat16* out;
     int n, c, h, w, c_pad, parts, terms; long long part_stride;
@@ -670,6 +744,45 @@ extern "C" int pgpp_conv2d_direct(const float* x, const float* w, const float* b
     };
     const int rc = kw == 1 ? launch(conv_direct_kernel<1>) : launch(conv_direct_kernel<3>);
     if (rc != PGPP_OK) return rc;
+    count_launch();
+    PGPP_CUDA_OK(cudaGetLastError());
+    return PGPP_OK;
+}
+
+extern "C" int pgpp_fir_pack(const float* x, const int64_t size[4], const int64_t stride[4], const float* f_host, int fw, int fh,
+                             int padx0, int padx1, int pady0, int pady1, int flip, float gain, void* out, int c_pad, int parts, void* stream) {
+    using namespace pgpp;
+    PGPP_REQUIRE(x && f_host && out, "x, f and out must be given (f is a HOST array of fh * fw taps)");
+    PGPP_REQUIRE(fw >= 1 && fw <= 4 && fh >= 1 && fh <= 4, "fir_pack: filter up to 4 x 4");
+    PGPP_REQUIRE(stride[3] == 1, "fir_pack: x must have unit stride along W");
+    PGPP_REQUIRE(parts >= 1 && parts <= 3 && c_pad >= size[1] && c_pad % 8 == 0, "bad fir_pack destination");
+    FirPackArgs p;
+    p.x = x; p.out = (__nv_bfloat16*)out;
+    p.n = (int)size[0]; p.c = (int)size[1]; p.ih = (int)size[2]; p.iw = (int)size[3];
+    p.ow = p.iw + padx0 + padx1 - fw + 1; p.oh = p.ih + pady0 + pady1 - fh + 1;
+    PGPP_REQUIRE(p.ow >= 1 && p.oh >= 1, "output must be at least 1x1");
+    p.padx0 = padx0; p.pady0 = pady0; p.c_pad = c_pad; p.parts = parts;
+    p.xs_n = stride[0]; p.xs_c = stride[1]; p.xs_h = stride[2];
+    p.part_stride = (long long)p.n * p.oh * p.ow * c_pad;
+    for (int jy = 0; jy < 4; jy++)
+        for (int jx = 0; jx < 4; jx++) {
+            float v = 0.f;
+            if (jy < fh && jx < fw) {
+                const int sy = flip ? jy : fh - 1 - jy, sx = flip ? jx : fw - 1 - jx;     // upfirdn2d correlates with the flipped filter
+                v = f_host[sy * fw + sx] * gain;
+            }
+            p.k[jy][jx] = v;
+        }
+    if (p.n == 0 || p.c == 0) return PGPP_OK;
+    const int x_tiles = (p.ow + kFirTw - 1) / kFirTw, y_tiles = (p.oh + kFirTh - 1) / kFirTh, c_tiles = (c_pad + 63) / 64;
+    const long long blocks = (long long)x_tiles * y_tiles * c_tiles * p.n;
+    PGPP_REQUIRE(blocks <= 2147483647LL, "tensor too large");
+    size_t smem = sizeof(float) * 64 * kFirRows * kFirPitch;
+    const size_t packets = (size_t)parts * 128 * 8 * sizeof(uint4);
+    if (packets > smem) smem = packets;
+    static bool attr_done = false;
+    if (!attr_done) { PGPP_CUDA_OK(cudaFuncSetAttribute(fir_pack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024)); attr_done = true; }
+    fir_pack_kernel<<<(unsigned)blocks, 256, smem, (cudaStream_t)stream>>>(p, x_tiles, y_tiles, c_tiles);
     count_launch();
     PGPP_CUDA_OK(cudaGetLastError());
     return PGPP_OK;

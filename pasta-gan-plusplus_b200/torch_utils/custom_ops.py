@@ -80,6 +80,8 @@ def load_library():
     lib.pgpp_spade_modulate_pack.argtypes = [vp, vp, vp, vp, vp, i64, vp, i32, i32, i32, i32, i32, i32, f32, vp]
     lib.pgpp_mix_pack.restype = i32
     lib.pgpp_mix_pack.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp]
+    lib.pgpp_fir_pack.restype = i32
+    lib.pgpp_fir_pack.argtypes = [vp, c_i64x4, c_i64x4, ctypes.POINTER(ctypes.c_float), i32, i32, i32, i32, i32, i32, i32, f32, vp, i32, i32, vp]
     lib.pgpp_conv2d_direct.restype = i32
     lib.pgpp_conv2d_direct.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, f32, i32, f32, f32, f32, vp, vp, i32, i32, i32, vp]
     lib.pgpp_conv2d_igemm.restype = i32
@@ -100,7 +102,7 @@ def load_library():
 
 EXPORTED_SYMBOLS = ('pgpp_version', 'pgpp_last_error', 'pgpp_launch_count', 'pgpp_bias_act', 'pgpp_upfirdn2d',
                     'pgpp_modconv_demod_coefs', 'pgpp_pack_activations', 'pgpp_pack_activations_slice', 'pgpp_modulate_weights',
-                    'pgpp_spade_modulate_pack', 'pgpp_mix_pack', 'pgpp_conv2d_direct', 'pgpp_pack_im2col', 'pgpp_conv2d_igemm', 'pgpp_conv2d_wgrad', 'pgpp_u8_to_f32',
+                    'pgpp_spade_modulate_pack', 'pgpp_mix_pack', 'pgpp_conv2d_direct', 'pgpp_fir_pack', 'pgpp_pack_im2col', 'pgpp_conv2d_igemm', 'pgpp_conv2d_wgrad', 'pgpp_u8_to_f32',
                     'pgpp_image_to_u8', 'pgpp_grid_sample_2d', 'pgpp_grid_sample_2d_backward')
 
 
@@ -342,6 +344,22 @@ class _ConvPlugin:
             _check(lib.pgpp_conv2d_direct(_ptr(x), _ptr(w), _ptr(b), n, c, h, wd, o, kh, kw, kh // 2, kw // 2, float(wscale), int(act_idx),
                                           float(alpha), float(gain), float(clamp), _ptr(out), _ptr(out_packed_data), int(c_total), int(c_off),
                                           int(parts), _stream(x)))
+        return out
+
+    @staticmethod
+    def fir_pack(x, taps, fw, fh, padx0, padx1, pady0, pady1, flip, gain, c_pad, parts):
+        """FIR blur (up = down = 1, `taps` = host list of fh * fw filter values) of x float32 [N,C,H,W] written as the operand
+        format bf16 [parts, N, H', W', c_pad]; see pgpp_fir_pack"""
+        lib = load_library()
+        _torch_check(x.is_cuda and x.dtype == torch.float32 and x.dim() == 4 and x.stride(3) == 1, 'fir_pack: x must be float32 [N,C,H,W] with unit W stride')
+        n, c, h, w = x.shape
+        oh, ow = h + pady0 + pady1 - fh + 1, w + padx0 + padx1 - fw + 1
+        _torch_check(oh >= 1 and ow >= 1 and len(taps) == fw * fh, 'fir_pack: bad filter / padding')
+        out = torch.empty([parts, n, oh, ow, c_pad], dtype=torch.bfloat16, device=x.device)
+        f = (ctypes.c_float * (fw * fh))(*[float(t) for t in taps])
+        with torch.cuda.device(x.device):
+            _check(lib.pgpp_fir_pack(_ptr(x), c_i64x4(*x.shape), c_i64x4(*x.stride()), f, fw, fh, int(padx0), int(padx1), int(pady0), int(pady1),
+                                     int(bool(flip)), float(gain), _ptr(out), int(c_pad), int(parts), _stream(x)))
         return out
 
     @staticmethod

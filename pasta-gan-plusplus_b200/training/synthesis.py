@@ -33,6 +33,12 @@ PackedAct = conv2d_gradfix.PackedAct
 PACKED_MIN_RES = 128    # blocks at this resolution and above hand activations over in operand format (no packing passes)
 
 
+# pgpp_fir_pack (one pass: blur -> operand format) measured 2.57 ms for 32x64x512x512 against 1.18 + 0.75 ms for the blur kernel
+# followed by the packing kernel (profiles/r01_pack_bench_v15.txt): its 64-channel x 128-pixel tile pays a 1.9x halo and a long
+# staging loop.  Kept for comparison, off by default.
+FUSE_BLUR_PACK = False
+
+
 def _can_fuse(x, *params):
     if isinstance(x, PackedAct):
         return True
@@ -115,6 +121,14 @@ class Conv2dLayer(torch.nn.Module):
             if k == 1:
                 x = upfirdn2d.upfirdn2d(x, self.resample_filter, down=2, padding=[p0, p1, p0, p1])
                 return conv2d_gradfix.igemm_conv(x, pw, out_packed=out_packed, **epi)
+            if FUSE_BLUR_PACK and x.dtype == torch.float32 and x.stride(3) == 1 and self.resample_filter.ndim == 2 and fw <= 4:
+                # blur written straight into the operand format of the strided GEMM (no float32 intermediate, no packing pass)
+                if getattr(self, '_filter_host', None) is None:
+                    self._filter_host = [float(v) for v in self.resample_filter.detach().cpu().reshape(-1)]     # one sync, first call only
+                conv2d_gradfix._init()
+                ic = x.shape[1]
+                data = conv2d_gradfix._plugin.fir_pack(x, self._filter_host, fw, fw, p0, p1, p0, p1, False, 1.0, pw.c_pad, parts)
+                return conv2d_gradfix.igemm_conv(PackedAct(data, ic), pw, stride=2, out_packed=out_packed, **epi)
             # blurred image of odd width (2W' + 1): rows padded to 16 bytes so the FIR stores and the packing loads stay 128-bit
             upfirdn2d._init()
             x = upfirdn2d._plugin.upfirdn2d(x, self.resample_filter, 1, 1, 1, 1, p0, p1, p0, p1, False, 1.0, row_align=4)

@@ -101,3 +101,27 @@ def test_full_size_blur_properties():
     lhs = upfirdn2d.upfirdn2d(a + 3 * b, f, padding=[1, 1, 1, 1])
     rhs = upfirdn2d.upfirdn2d(a, f, padding=[1, 1, 1, 1]) + 3 * upfirdn2d.upfirdn2d(b, f, padding=[1, 1, 1, 1])
     assert float((lhs - rhs).abs().max()) < 2e-5
+
+
+@pytest.mark.parametrize('shape', [(2, 64, 32, 64), (1, 70, 17, 23), (3, 8, 5, 3), (2, 128, 64, 36)], ids=str)
+@pytest.mark.parametrize('pad', [(2, 1, 2, 1), (1, 1, 1, 1), (2, 2, 2, 2)], ids=str)
+def test_fir_pack_equals_blur_then_pack(shape, pad):
+    """pgpp_fir_pack (blur written straight into the operand format, conv2d_resample.py:119-122) against the oracle's upfirdn2d
+    on the CPU; with 3 bf16 parts the result carries 24 significand bits"""
+    custom_ops = importlib.import_module('pgpp_b200.torch_utils.custom_ops')
+    plugin = custom_ops.get_plugin('conv2d_plugin')
+    n, c, h, w = shape
+    g = torch.Generator().manual_seed(61)
+    x = torch.randn(n, c, h, w, generator=g)
+    f = upfirdn2d.setup_filter([1, 3, 3, 1])
+    f_asym = torch.randn(3, 4, generator=g)                    # a non-symmetric, non-square filter checks the flip convention
+    for filt, flip in ((f, False), (f_asym, False), (f_asym, True)):
+        fh, fw = filt.shape
+        want = ref_ops.upfirdn2d(x.double(), filt, padding=list(pad), flip_filter=flip, gain=1.7)
+        c_pad = -(-c // 64) * 64
+        for parts, tol in ((3, 2e-6), (2, 2e-5)):
+            data = plugin.fir_pack(x.to(DEV), [float(v) for v in filt.reshape(-1)], fw, fh, *pad, flip, 1.7, c_pad, parts)
+            assert tuple(data.shape) == (parts, n, want.shape[2], want.shape[3], c_pad)
+            got = data.float().sum(0).permute(0, 3, 1, 2).cpu()
+            assert torch.all(got[:, c:] == 0)
+            assert max_abs(got[:, :c], want) <= tol * max(1.0, want.abs().max().item()), (fh, fw, flip, parts)

@@ -117,7 +117,7 @@ def test_resblock_hand_over_route_matches_composition(down, packed_input):
         n_launch = custom_ops.launch_count() - launches
     rel = ((got.cpu() - want).norm() / want.norm()).item()
     assert rel < 1e-4, rel
-    # down=1: [pack] + skip + conv0 + conv1;  down=2: 2 FIR + 2 packs + 3 convs
+    # down=1: [pack] + skip + conv0 + conv1;  down=2: FIR decimation + pack + skip, blur + pack + conv0, conv1
     assert n_launch == ((3 if packed_input else 4) if down == 1 else 7), n_launch
 
 

@@ -62,3 +62,9 @@ for (ic, oc, k, h, w, packed) in [(1, 64, 3, 512, 512, True), (1, 64, 3, 512, 51
     op = cg.PackedAct(cg.PackedAct.empty(32, h, w, oc, 2, dev), oc) if packed else None
     ms = timeit(lambda: cg.direct_conv(x, wt, None, act='relu', out_packed=op))
     report(f'direct conv {ic}->{oc} k{k} 32x{h}x{w} -> {"2 bf16 parts" if packed else "f32 NCHW"}', ms, x.numel() * 4 + 32 * oc * h * w * 4)
+
+f16 = [1., 3., 3., 1.]; taps = [a * b / 64. for a in f16 for b in f16]
+for (n, c, h, w) in [(32, 64, 512, 512), (32, 128, 256, 256)]:
+    x = torch.randn(n, c, h, w, device=dev)
+    ms = timeit(lambda: plugin.fir_pack(x, taps, 4, 4, 2, 2, 2, 2, False, 1.0, c, 2))
+    report(f'fir_pack {n}x{c}x{h}x{w} -> {h + 1}x{w + 1}, 2 parts', ms, x.numel() * 4 + n * c * (h + 1) * (w + 1) * 4)
