@@ -71,6 +71,9 @@ struct IgemmParams {
     int wgt_per_sample;                 // weights carry a leading sample dimension
     int out_parts; long long out_part_stride;
     const float* spade_x; const float* spade_mean; const float* spade_rstd; float spade_pre_gain;   // SPADE epilogue (see epilogue_spade)
+    int stack;                          // 1: split-precision products a0 x [b0; b1] issued as ONE N = 2 * block_n MMA (see mma_role)
+    int acc_cols;                       // TMEM columns per accumulator buffer (block_n, or 2 * block_n when stack)
+    unsigned idesc_stack;               // instruction descriptor with N = 2 * block_n
     int fold_gain;                      // activation is positively homogeneous and gain > 0: gain is folded into scale/shift/noise
     unsigned div_col_m, div_col_s, div_x_m, div_x_s, div_y_m, div_y_s;   // magic numbers for t / tiles_col, / tiles_x, / tiles_y
 };
@@ -243,7 +246,17 @@ __device__ __forceinline__ void epilogue_fast(const IgemmParams& p, const TileCo
         const int c0 = col_begin + ch * 16;
         uint32_t ra[16];
         tmem_ld16_issue(tmem_tile + c0, ra);
-        tmem_ld_wait16(ra);
+        if (p.stack) {
+            // stacked split-precision products: columns [block_n, 2 * block_n) hold a0 x b1, to be added to a0 x b0 + a1 x b0
+            uint32_t rb[16];
+            tmem_ld16_issue(tmem_tile + p.block_n + c0, rb);
+            tmem_ld_wait16(ra);
+            tmem_ld_wait16(rb);
+            #pragma unroll
+            for (int j = 0; j < 16; j++) ra[j] = __float_as_uint(__uint_as_float(ra[j]) + __uint_as_float(rb[j]));
+        } else {
+            tmem_ld_wait16(ra);
+        }
         process(ra, c0);
     }
 }
@@ -337,7 +350,7 @@ struct MmaCtx { uint32_t smem_base, b_base, bar_base, tmem_base; };
 // one elected lane issues tcgen05.mma / tcgen05.commit.  PARTS / INNER / KS > 0 are compile-time copies of p.parts /
 // p.inner / (kb / 16) for the common configurations (fully unrolled product / tap / K-step loops, a handful of
 // instructions per MMA); <0, 0, 0> is the generic runtime-bounds version.
-template <int PARTS, int INNER, int KS, bool RES>
+template <int PARTS, int INNER, int KS, bool RES, bool STK = false>
 __device__ __forceinline__ void mma_role(const IgemmParams& p, const MmaCtx mc) {
     const int SA = p.a_stages, SB = p.b_stages;
     auto afull_bar = [&](int s) { return mc.bar_base + 8u * s; };
@@ -371,7 +384,7 @@ __device__ __forceinline__ void mma_role(const IgemmParams& p, const MmaCtx mc) 
         }
         mbar_wait(tempty_bar(buf), buf_phase ^ 1);      // epilogue has drained this accumulator
         tc_fence_after();
-        const uint32_t tmem_d = mc.tmem_base + (uint32_t)(buf * p.block_n);
+        const uint32_t tmem_d = mc.tmem_base + (uint32_t)(buf * p.acc_cols);
         uint32_t acc = 0;
         uint32_t b_res16 = mc.b_base >> 4;              // resident weights: next tile in consumption order
         for (int g = 0; g < p.n_groups; g++) {
@@ -382,6 +395,28 @@ __device__ __forceinline__ void mma_role(const IgemmParams& p, const MmaCtx mc) 
                 #pragma unroll
                 for (int j = 0; j < (INNER ? INNER : 8); j++) {
                     if (j >= inner) break;
+                    if (STK) {
+                        // parts = 2, resident weights, block_n = 64: the tiles of b0 and b1 of a tap are adjacent in shared memory, so
+                        // a0 x [b0; b1] is ONE MMA with N = 128 (a0 x b0 in columns [0, 64), a0 x b1 in [64, 128), summed by the
+                        // epilogue) and a1 x b0 a second one with N = 64: two reads of the A tile per K step instead of three
+                        const uint32_t b16 = b_res16;
+                        b_res16 += 2 * bpitch16;
+                        const uint64_t db = desc_hi | (uint64_t)(b16 & 0x3FFF);
+                        const uint64_t da0 = desc_hi | (uint64_t)((a16 + j * ky16) & 0x3FFF);
+                        const uint64_t da1 = desc_hi | (uint64_t)((a16 + slab16 + j * ky16) & 0x3FFF);
+                        if (leader) {
+                            umma_bf16(tmem_d, da0, db, p.idesc_stack, acc);
+                            umma_bf16(tmem_d, da0 + 2, db + 2, p.idesc_stack, 1);
+                            umma_bf16(tmem_d, da0 + 4, db + 4, p.idesc_stack, 1);
+                            umma_bf16(tmem_d, da0 + 6, db + 6, p.idesc_stack, 1);
+                            umma_bf16(tmem_d, da1, db, idesc, 1);
+                            umma_bf16(tmem_d, da1 + 2, db + 2, idesc, 1);
+                            umma_bf16(tmem_d, da1 + 4, db + 4, idesc, 1);
+                            umma_bf16(tmem_d, da1 + 6, db + 6, idesc, 1);
+                        }
+                        acc = 1;
+                    }
+                    if (!STK)
                     #pragma unroll
                     for (int pb = 0; pb < (PARTS ? PARTS : 3); pb++) {
                         if (pb >= parts) break;
@@ -543,6 +578,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
         const int ks = p.kb == 64 ? 4 : 0;
         const bool res = p.b_resident != 0;
         if (ks == 4 && p.inner == 3 && p.parts == 1) { if (res) mma_role<1, 3, 4, true>(p, mc); else mma_role<1, 3, 4, false>(p, mc); }
+        else if (ks == 4 && p.inner == 3 && p.parts == 2 && p.stack) mma_role<2, 3, 4, true, true>(p, mc);
+        else if (ks == 4 && p.inner == 1 && p.parts == 2 && p.stack) mma_role<2, 1, 4, true, true>(p, mc);
         else if (ks == 4 && p.inner == 3 && p.parts == 2) { if (res) mma_role<2, 3, 4, true>(p, mc); else mma_role<2, 3, 4, false>(p, mc); }
         else if (ks == 4 && p.inner == 3 && p.parts == 3) mma_role<3, 3, 4, false>(p, mc);
         else if (ks == 4 && p.inner == 7 && p.parts == 1) mma_role<1, 7, 4, false>(p, mc);
@@ -598,7 +635,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
             }
             mbar_wait(tfull_bar(buf), buf_phase);
             tc_fence_after();
-            const uint32_t tmem_tile = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * p.block_n);
+            const uint32_t tmem_tile = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * p.acc_cols);
             if (p.spade_x) epilogue_spade(p, tc, tmem_tile, pc, half, s_cs);
             else if (p.out_dtype == PGPP_F32) epilogue_dispatch<float>(p, tc, tmem_tile, pc, col_begin, col_end, s_cs, fast);
             else if (p.out_dtype == PGPP_BF16) epilogue_dispatch<__nv_bfloat16>(p, tc, tmem_tile, pc, col_begin, col_end, s_cs, fast);
@@ -746,6 +783,12 @@ extern "C" int pgpp_conv2d_igemm(const pgpp_conv_desc* d, void* stream) {
     }
     p.fold_gain = (d->gain > 0.f && (d->act_fn == PGPP_ACT_LINEAR || d->act_fn == PGPP_ACT_RELU ||
                                      (d->act_fn == PGPP_ACT_LRELU && d->alpha >= 0.f && d->alpha <= 1.f))) ? 1 : 0;
+    // stacked products (see mma_role): fp32-parity mode with 2 parts, resident 64-column weight tiles, fast epilogue
+    p.stack = (need_parts == 2 && d->block_n == 64 && p.b_resident && p.kb == 64 && (p.inner == 3 || p.inner == 1) && p.tn == 1 && p.fold_gain &&
+               !d->spade_x && !getenv("PGPP_IGEMM_NO_STACK")) ? 1 : 0;
+    p.acc_cols = p.stack ? 2 * d->block_n : d->block_n;
+    p.idesc_stack = (1u << 4) | (1u << 7) | (1u << 10) | ((unsigned)((2 * d->block_n) >> 3) << 17) | ((unsigned)(kTileM >> 4) << 24);
+    if (p.stack) p.tmem_cols = 256;
     auto magic = [](unsigned dv, unsigned& m, unsigned& sft) {
         sft = 0; while ((1ull << sft) < dv) sft++;
         m = (unsigned)(((1ull << (31 + sft)) + dv - 1) / dv);
