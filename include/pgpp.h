@@ -176,7 +176,7 @@ typedef struct {
  * loads), persistent over the SMs, with the epilogue above fused. */
 PGPP_API int pgpp_conv2d_igemm(const pgpp_conv_desc* desc, void* stream);
 
-/* Masked feature composition + packing (networks.py:2256-2266, 2315-2317: the warped-garment features fed to the SPADE blocks):
+/* Masked feature composition + packing (networks.py:2253-2276, 2307-2315: the warped-garment features fed to the SPADE blocks):
  *   v[n,c,p] = x1[n,c,p]*a1[n,p] + m1[n,c]*b1[n,p]  (+ x2[n,c,p]*a2[n,p] + m2[n,c]*b2[n,p] when x2 != NULL)
  * x float32 [N,C,H,W] contiguous, m float32 [N,C], a / b float32 [N,H,W]; out = bf16 [parts][N][H][W][c_pad] (the operand format). */
 PGPP_API int pgpp_mix_pack(const float* x1, const float* m1, const float* a1, const float* b1, const float* x2, const float* m2,
@@ -241,7 +241,7 @@ PGPP_API int pgpp_image_to_u8(const float* img, int64_t n, int64_t c, int64_t hw
 
 /* ---- grid_sample (torch_utils/ops/grid_sample_gradfix.py:27-83): 2-D, bilinear, zeros padding, align_corners = False ----
  * input float32 [N,C,H,W] contiguous, grid float32 [N,Ho,Wo,2] contiguous (x, y in [-1, 1]), out float32 [N,C,Ho,Wo].
- * Replaces aten::grid_sampler_2d (grid_sample_gradfix.py:47). */
+ * Replaces aten::grid_sampler_2d (grid_sample_gradfix.py:49). */
 PGPP_API int pgpp_grid_sample_2d(const float* input, const float* grid, float* out, int n, int c, int h, int w, int ho, int wo, void* stream);
 
 /* Replaces aten::grid_sampler_2d_backward (grid_sample_gradfix.py:64-65).  grad_input [N,C,H,W] (zeroed here, scatter-add) and / or

@@ -466,7 +466,7 @@ struct MixArgs {
 };
 
 // v[n,c,p] = sum_t x_t[n,c,p] * a_t[n,p] + m_t[n,c] * b_t[n,p]  ->  packed operand (same transposing tile as pack_nchw_kernel).
-// The masked feature composition of SynthesisNetworkFull_v18 (networks.py:2256-2266, 2315-2317): per branch
+// The masked feature composition of SynthesisNetworkFull_v18 (networks.py:2253-2276, 2307-2315): per branch
 // x * (1 - res_mask) + mean * res_mask, times the branch's 256 x 256 mask, summed over the upper / lower branches.
 template <bool VEC>
 __global__ void __launch_bounds__(256) mix_pack_kernel(MixArgs p, TileGeom g) {

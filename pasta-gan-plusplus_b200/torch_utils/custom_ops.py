@@ -433,7 +433,7 @@ class _IoEdgePlugin:
 
 class _GridSamplePlugin:
     """aten::grid_sampler_2d / grid_sampler_2d_backward with (bilinear, zeros, align_corners=False), the only mode the reference
-    uses (grid_sample_gradfix.py:47,64-65)"""
+    uses (grid_sample_gradfix.py:49,64-65)"""
 
     @staticmethod
     def _check_operands(input, grid):

@@ -395,7 +395,7 @@ class SynthesisNetworkFull_v18(torch.nn.Module):
                                                   ResBlock(ngf, ngf * 2, kernel_size=4, activation='relu', down=2)])
 
     def get_spade_feat(self, mask_512, denorm_mask, denorm_input, fused=True, impl='cuda', as_terms=False):
-        """networks.py:2249-2266.  `as_terms`: return (x, mean, 1 - res_mask, res_mask) for the fused composition kernel
+        """networks.py:2253-2276.  `as_terms`: return (x, mean, 1 - res_mask, res_mask) for the fused composition kernel
         (pgpp_mix_pack) instead of the composed NCHW feature tensor."""
         half = lambda t: torch.nn.functional.interpolate(t, scale_factor=0.5)
         mask_512 = (mask_512 > 0.9).to(mask_512.dtype)

@@ -118,7 +118,7 @@ def test_packed_activation_roundtrip_and_per_sample_weights():
 @pytest.mark.parametrize('shape', [(2, 128, 64, 48), (1, 70, 9, 13), (3, 64, 16, 128)], ids=str)
 @pytest.mark.parametrize('terms', [1, 2])
 def test_mix_pack_matches_the_masked_feature_composition(shape, terms):
-    """pgpp_mix_pack = (x*(1-res) + mean*res) * mask, summed over branches (networks.py:2256-2266, 2315-2317), written in the
+    """pgpp_mix_pack = (x*(1-res) + mean*res) * mask, summed over branches (networks.py:2253-2276, 2307-2315), written in the
     operand format; with 0/1 masks every product is exact, so the packed sum equals the fp32 composition up to the bf16 split"""
     import importlib
     custom_ops = importlib.import_module('pgpp_b200.torch_utils.custom_ops')
