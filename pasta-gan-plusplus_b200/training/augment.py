@@ -103,11 +103,11 @@ class AugmentPipe(torch.nn.Module):
 
     # -- random parameters ----------------------------------------------------------------------------------------------------
     def _pick(self, value, gate_shape, prob, neutral, forced):
-        """keep `value` where a fresh uniform draw of `gate_shape` falls below prob * p, else `neutral`; `forced` (debug mode)
-        overrides both.  The uniform draw happens AFTER `value` was drawn - the reference's order."""
+        """keep `value` where a fresh uniform draw of `gate_shape` falls below prob * p, else `neutral`; `forced` (debug mode,
+        python scalar or 0-d tensor) overrides both.  The uniform draw happens AFTER `value` was drawn - the reference's order."""
         keep = torch.rand(gate_shape, device=value.device) < prob * self.p
         value = torch.where(keep, value, torch.full_like(value, neutral))
-        return value if forced is None else torch.full_like(value, forced) if not torch.is_tensor(forced) or forced.ndim == 0 else forced
+        return value if forced is None else torch.full_like(value, forced)
 
     def forward(self, images, debug_percentile=None):
         assert isinstance(images, torch.Tensor) and images.ndim == 4

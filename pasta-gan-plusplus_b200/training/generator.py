@@ -275,7 +275,8 @@ class Spade_ResBlockV4_512(torch.nn.Module):
 
     def forward(self, x, denorm_feat, fused=True, impl='cuda', feats_packed=None):
         if fused and torch.is_tensor(x) and x.dtype == torch.float32 and S._can_fuse(x, self.conv.weight):
-            # fused SPADE route: 13 GEMM launches + 3 modulate/pack passes + 2 statistics reductions per block
+            # fused SPADE route: per block 1 + 3 x (conv_mlp, gamma|beta GEMM with the SPADE epilogue, consuming conv) = 10 GEMM launches,
+            # one packing pass for the block input and 2 statistics reductions
             relu_gain = float(bias_act.activation_funcs['relu'].def_gain)
             if feats_packed is None:
                 conv2d_gradfix._init()
