@@ -24,11 +24,8 @@ SYM6 = [0.015404109327027373, 0.0034907120842174702, -0.11799011114819057, -0.04
         0.3379294217276218, -0.07263752278646252, -0.021060292512300564, 0.04472490177066578, 0.0017677118642428036,
         -0.007800708325034148]
 
-_PROBABILITIES = ('xflip', 'rotate90', 'xint', 'scale', 'rotate', 'aniso', 'xfrac', 'brightness', 'contrast', 'lumaflip', 'hue',
-                  'saturation', 'imgfilter', 'noise', 'cutout')
 
-
-def _mat(rows, like=None, device=None):
+def _mat(rows, device=None):
     """[..., R, C] matrix from nested rows of python scalars and / or equally shaped tensors (scalars are broadcast)"""
     tensors = [e for row in rows for e in row if torch.is_tensor(e)]
     if not tensors:
