@@ -49,7 +49,10 @@ struct IgemmParams {
     int parts;                          // bf16 parts used of each operand (1, 2, 3)
     unsigned pa_mask[3];                // pa_mask[pb]: which A parts multiply B part pb
     int n_groups, inner;                // K groups per channel block (kw with ky reuse, kh*kw without) and taps per group (kh or 1)
-    int reuse;                          // 1: one activation slab per (kx, cb), vertical taps are row-shifted views
+    int reuse;                          // 1: one activation slab per (kx, cb), vertical taps are row-shifted views;
+                                        // 2: ONE slab with an x halo per (cb, part), every tap is a row-shifted view (mma_role_slab)
+    unsigned short tap_off16[64];       // reuse == 2: descriptor start offset of tap j inside the slab, in 16-byte units
+    unsigned sbo_a;                     // reuse == 2: 8-row group stride of the A operand = slab row pitch in bytes
     int o, phases, phase_stride, o_rows, block_n;
     int tw, th, tn;
     int tiles_x, tiles_y, tiles_n, tiles_col;
@@ -176,7 +179,7 @@ __device__ __forceinline__ void epilogue_general(const IgemmParams& p, const Til
 // (linear / relu / lrelu are positively homogeneous).
 template <int A, class OT, bool CLAMP, bool ACC>
 __device__ __forceinline__ void epilogue_fast(const IgemmParams& p, const TileCoord tc, uint32_t tmem_tile, const PixelCoord pc,
-                                              int col_begin, int col_end, const float2* s_cs) {
+                                              int col_begin, int col_end, const float2* s_cs, float nz_pre) {
     const int x = tc.x0 + pc.px, y = tc.y0 + pc.py, n = tc.n0;
     const bool pix_ok = x < p.conv_w && y < p.conv_h;
     OT* const out = (OT*)p.out;
@@ -190,8 +193,9 @@ __device__ __forceinline__ void epilogue_fast(const IgemmParams& p, const TileCo
         const int oc0 = g0 - phase * p.phase_stride;
         if (!pix_ok || oc0 >= p.o || phase >= p.phases) return;
         const int oy = y * p.up + (phase >> 1), ox = x * p.up + (phase & 1);
-        float nz = 0.f;
-        if (p.noise) nz = __ldg(p.noise + n * p.noise_stride_n + (long long)oy * p.out_w + ox) * gain;
+        // up = 1: the pixel's noise value was fetched before the accumulator wait (nz_pre); up = 2: it depends on the phase
+        float nz = nz_pre;
+        if (p.noise && p.phases != 1) nz = __ldg(p.noise + n * p.noise_stride_n + (long long)oy * p.out_w + ox) * gain;
         const long long base = n * p.os_n + oy * p.os_h + ox * p.os_w;
         const int valid = min(16, p.o - oc0);
         // out += result (ToRGB adding into the up-sampled skip image, the residual add of the SPADE block): all 16 loads
@@ -241,8 +245,22 @@ __device__ __forceinline__ void epilogue_fast(const IgemmParams& p, const TileCo
             }
         }
     };
-    // (the second epilogue warp on the same scheduler covers the TMEM-load latency of this one)
-    for (int ch = 0; ch < nchunks; ch++) {
+    // two chunks of TMEM loads are kept in flight (one round trip per 32 columns); the second epilogue warp on the same scheduler
+    // covers the rest of the latency
+    int ch = 0;
+    if (!p.stack) {
+        for (; ch + 1 < nchunks; ch += 2) {
+            const int c0 = col_begin + ch * 16;
+            uint32_t ra[16], rb[16];
+            tmem_ld16_issue(tmem_tile + c0, ra);
+            tmem_ld16_issue(tmem_tile + c0 + 16, rb);
+            tmem_ld_wait16(ra);
+            tmem_ld_wait16(rb);
+            process(ra, c0);
+            process(rb, c0 + 16);
+        }
+    }
+    for (; ch < nchunks; ch++) {
         const int c0 = col_begin + ch * 16;
         uint32_t ra[16];
         tmem_ld16_issue(tmem_tile + c0, ra);
@@ -312,14 +330,14 @@ __device__ __forceinline__ void epilogue_spade(const IgemmParams& p, const TileC
 
 template <class OT>
 __device__ __forceinline__ void epilogue_dispatch(const IgemmParams& p, const TileCoord tc, uint32_t tmem_tile, const PixelCoord pc,
-                                                  int col_begin, int col_end, const float2* s_cs, bool fast) {
+                                                  int col_begin, int col_end, const float2* s_cs, bool fast, float nz_pre) {
     if (fast) {
         // ACC: read-modify-write output (ToRGB into the skip image, residual adds)
 #define PGPP_FAST(ACT) \
-        if (p.accumulate) { if (cl) epilogue_fast<ACT, OT, true, true>(p, tc, tmem_tile, pc, col_begin, col_end, s_cs);   \
-                            else    epilogue_fast<ACT, OT, false, true>(p, tc, tmem_tile, pc, col_begin, col_end, s_cs); } \
-        else               { if (cl) epilogue_fast<ACT, OT, true, false>(p, tc, tmem_tile, pc, col_begin, col_end, s_cs);  \
-                            else    epilogue_fast<ACT, OT, false, false>(p, tc, tmem_tile, pc, col_begin, col_end, s_cs); }
+        if (p.accumulate) { if (cl) epilogue_fast<ACT, OT, true, true>(p, tc, tmem_tile, pc, col_begin, col_end, s_cs, nz_pre);   \
+                            else    epilogue_fast<ACT, OT, false, true>(p, tc, tmem_tile, pc, col_begin, col_end, s_cs, nz_pre); } \
+        else               { if (cl) epilogue_fast<ACT, OT, true, false>(p, tc, tmem_tile, pc, col_begin, col_end, s_cs, nz_pre);  \
+                            else    epilogue_fast<ACT, OT, false, false>(p, tc, tmem_tile, pc, col_begin, col_end, s_cs, nz_pre); }
         const bool cl = p.clamp >= 0.f;
         switch (p.act_fn) {
             case PGPP_ACT_LINEAR: PGPP_FAST(PGPP_ACT_LINEAR) break;
@@ -470,6 +488,96 @@ __device__ __forceinline__ void mma_role(const IgemmParams& p, const MmaCtx mc) 
     __syncwarp();
 }
 
+// MMA issuer for the single-slab mode (p.reuse == 2): the activation ring holds one (channel block, part) slab per stage, the
+// weights are resident, and tap j of the filter reads the slab through a descriptor whose start is shifted by whole pixel rows
+// (tap_off16) with an 8-row group stride of one slab row (sbo_a) - the tensor core applies the 128-byte swizzle on the absolute
+// shared-memory address, so such views are exact (tools/umma_probe.cu).  Product order: for every part a_pa of the slab, all taps,
+// all weight parts b_pb with pa + pb < parts.  STK: parts == 2 and block_n == 64 -> a0 x [b0; b1] is one N = 128 MMA.
+template <int PARTS, int TAPS, bool STK>
+__device__ __forceinline__ void mma_role_slab(const IgemmParams& p, const MmaCtx mc) {
+    const int SA = p.a_stages, SB = p.b_stages;
+    auto afull_bar = [&](int s) { return mc.bar_base + 8u * s; };
+    auto aempty_bar = [&](int s) { return mc.bar_base + 8u * (SA + s); };
+    auto bfull_bar = [&](int s) { return mc.bar_base + 8u * (2 * SA + s); };
+    auto tfull_bar = [&](int b) { return mc.bar_base + 8u * (2 * SA + 2 * SB + b); };
+    auto tempty_bar = [&](int b) { return mc.bar_base + 8u * (2 * SA + 2 * SB + 2 + b); };
+    const uint32_t bres_free_bar = mc.bar_base + 8u * (2 * SA + 2 * SB + 4);
+    const int parts = PARTS ? PARTS : p.parts;
+    const int taps = TAPS ? TAPS : p.inner;
+    const bool leader = elect_one();
+    const uint64_t desc_a_hi = make_smem_desc(0, p.layout_type, p.sbo_a);
+    const uint64_t desc_b_hi = make_smem_desc(0, p.layout_type, p.sbo_bytes);
+    const uint32_t bpitch16 = p.b_pitch >> 4;
+    const uint32_t idesc = p.idesc;
+    int sa = 0; uint32_t pha = 0;
+    int buf = 0; uint32_t buf_phase = 0;
+    bool first_tile = true;
+    int last_n = -1; uint32_t res_phase = 0;
+    for (long long t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+        const int n0 = p.wgt_per_sample ? decode_tile(p, t).n0 : 0;
+        if (first_tile || n0 != last_n) {
+            if (!first_tile) res_phase ^= 1;
+            for (int sl = 0; sl < SB; sl++) mbar_wait(bfull_bar(sl), res_phase);
+        }
+        last_n = n0;
+        mbar_wait(tempty_bar(buf), buf_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = mc.tmem_base + (uint32_t)(buf * p.acc_cols);
+        uint32_t acc = 0;
+        for (int cb = 0; cb < p.num_cb; cb++) {
+            #pragma unroll
+            for (int pa = 0; pa < (PARTS ? PARTS : 3); pa++) {
+                if (pa >= parts) break;
+                mbar_wait(afull_bar(sa), pha);
+                tc_fence_after();
+                const uint32_t a16 = (mc.smem_base + sa * p.a_stage_bytes) >> 4;
+                const uint32_t b_cb16 = (mc.b_base >> 4) + (uint32_t)(cb * taps * parts) * bpitch16;
+                #pragma unroll
+                for (int j = 0; j < (TAPS ? TAPS : 64); j++) {
+                    if (j >= taps) break;
+                    const uint64_t da = desc_a_hi | (uint64_t)((a16 + p.tap_off16[j]) & 0x3FFF);
+                    const uint32_t b_tap16 = b_cb16 + (uint32_t)(j * parts) * bpitch16;
+                    if (STK) {
+                        // pa == 0: a0 x [b0; b1] (N = 2 * block_n);  pa == 1: a1 x b0 (N = block_n)
+                        const uint64_t db = desc_b_hi | (uint64_t)(b_tap16 & 0x3FFF);
+                        const uint32_t id = pa == 0 ? p.idesc_stack : idesc;
+                        if (leader) {
+                            umma_bf16(tmem_d, da, db, id, acc);
+                            umma_bf16(tmem_d, da + 2, db + 2, id, 1);
+                            umma_bf16(tmem_d, da + 4, db + 4, id, 1);
+                            umma_bf16(tmem_d, da + 6, db + 6, id, 1);
+                        }
+                        acc = 1;
+                    } else {
+                        #pragma unroll
+                        for (int pb = 0; pb < (PARTS ? PARTS : 3); pb++) {
+                            if (pa + pb >= parts) break;
+                            const uint64_t db = desc_b_hi | (uint64_t)((b_tap16 + pb * bpitch16) & 0x3FFF);
+                            if (leader) {
+                                umma_bf16(tmem_d, da, db, idesc, acc);
+                                umma_bf16(tmem_d, da + 2, db + 2, idesc, 1);
+                                umma_bf16(tmem_d, da + 4, db + 4, idesc, 1);
+                                umma_bf16(tmem_d, da + 6, db + 6, idesc, 1);
+                            }
+                            acc = 1;
+                        }
+                    }
+                }
+                if (leader) umma_commit(aempty_bar(sa));
+                if (++sa == SA) { sa = 0; pha ^= 1; }
+            }
+        }
+        if (leader) umma_commit(tfull_bar(buf));
+        if (p.wgt_per_sample) {
+            const long long tn = t + gridDim.x;
+            if (tn < p.total_tiles && decode_tile(p, tn).n0 != last_n && leader) umma_commit(bres_free_bar);
+        }
+        if (++buf == 2) { buf = 0; buf_phase ^= 1; }
+        first_tile = false;
+    }
+    __syncwarp();
+}
+
 __global__ void __launch_bounds__(kThreads, 1)
 igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const IgemmParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -542,9 +650,20 @@ igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
                                 for (int pb = 0; pb < p.parts; pb++, b_slot++) {
                                     mbar_expect_tx(bfull_bar(b_slot), p.b_bytes);
                                     tma_load_4d(b_base + b_slot * p.b_pitch, &map_b, bfull_bar(b_slot), cb * p.kb,
-                                                ((ky0 + j) * p.kw + kx) * p.o_rows + tc.col0, pb, wn);
+                                                (p.reuse == 2 ? j : (ky0 + j) * p.kw + kx) * p.o_rows + tc.col0, pb, wn);
                                 }
                     }
+                }
+                if (p.reuse == 2) {
+                    // one slab (TW + kw - 1) x (TH + kh - 1) pixels per (channel block, part); stages are single parts
+                    for (int cb = 0; cb < p.num_cb; cb++)
+                        for (int pa = 0; pa < p.parts; pa++) {
+                            mbar_wait(aempty_bar(sa), pha ^ 1);
+                            mbar_expect_tx(afull_bar(sa), p.a_tx_bytes);
+                            tma_load_5d(smem_base + sa * p.a_stage_bytes, &map_a, afull_bar(sa), cb * p.kb, tc.x0 - p.pad_x, tc.y0 - p.pad_y, tc.n0, pa);
+                            if (++sa == SA) { sa = 0; pha ^= 1; }
+                        }
+                    continue;
                 }
                 for (int g = 0; g < p.n_groups; g++) {
                     // reuse: group = kx, the slab spans all ky;  no reuse: group = tap
@@ -577,7 +696,14 @@ igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
         const MmaCtx mc{smem_base, b_base, bar_base, tmem_base};
         const int ks = p.kb == 64 ? 4 : 0;
         const bool res = p.b_resident != 0;
-        if (ks == 4 && p.inner == 3 && p.parts == 1) { if (res) mma_role<1, 3, 4, true>(p, mc); else mma_role<1, 3, 4, false>(p, mc); }
+        if (p.reuse == 2) {
+            if (p.inner == 9 && p.parts == 1) mma_role_slab<1, 9, false>(p, mc);
+            else if (p.inner == 9 && p.parts == 2 && p.stack) mma_role_slab<2, 9, true>(p, mc);
+            else if (p.inner == 9 && p.parts == 2) mma_role_slab<2, 9, false>(p, mc);
+            else if (p.stack) mma_role_slab<2, 0, true>(p, mc);
+            else mma_role_slab<0, 0, false>(p, mc);
+        }
+        else if (ks == 4 && p.inner == 3 && p.parts == 1) { if (res) mma_role<1, 3, 4, true>(p, mc); else mma_role<1, 3, 4, false>(p, mc); }
         else if (ks == 4 && p.inner == 3 && p.parts == 2 && p.stack) mma_role<2, 3, 4, true, true>(p, mc);
         else if (ks == 4 && p.inner == 1 && p.parts == 2 && p.stack) mma_role<2, 1, 4, true, true>(p, mc);
         else if (ks == 4 && p.inner == 3 && p.parts == 2) { if (res) mma_role<2, 3, 4, true>(p, mc); else mma_role<2, 3, 4, false>(p, mc); }
@@ -633,13 +759,19 @@ igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
                     if (buf) tag1 = tag; else tag0 = tag;
                 }
             }
+            // the pixel's noise value does not depend on the accumulators: fetch it while the MMAs of this tile are still running
+            float nz_pre = 0.f;
+            if (fast && p.noise && p.phases == 1) {
+                const int x = tc.x0 + pc.px, y = tc.y0 + pc.py;
+                if (x < p.conv_w && y < p.conv_h) nz_pre = __ldg(p.noise + tc.n0 * p.noise_stride_n + (long long)y * p.out_w + x) * p.gain;
+            }
             mbar_wait(tfull_bar(buf), buf_phase);
             tc_fence_after();
             const uint32_t tmem_tile = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * p.acc_cols);
             if (p.spade_x) epilogue_spade(p, tc, tmem_tile, pc, half, s_cs);
-            else if (p.out_dtype == PGPP_F32) epilogue_dispatch<float>(p, tc, tmem_tile, pc, col_begin, col_end, s_cs, fast);
-            else if (p.out_dtype == PGPP_BF16) epilogue_dispatch<__nv_bfloat16>(p, tc, tmem_tile, pc, col_begin, col_end, s_cs, fast);
-            else epilogue_dispatch<__half>(p, tc, tmem_tile, pc, col_begin, col_end, s_cs, fast);
+            else if (p.out_dtype == PGPP_F32) epilogue_dispatch<float>(p, tc, tmem_tile, pc, col_begin, col_end, s_cs, fast, nz_pre);
+            else if (p.out_dtype == PGPP_BF16) epilogue_dispatch<__nv_bfloat16>(p, tc, tmem_tile, pc, col_begin, col_end, s_cs, fast, nz_pre);
+            else epilogue_dispatch<__half>(p, tc, tmem_tile, pc, col_begin, col_end, s_cs, fast, nz_pre);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty_bar(buf));
@@ -713,14 +845,30 @@ extern "C" int pgpp_conv2d_igemm(const pgpp_conv_desc* d, void* stream) {
     p.reuse = (d->stride == 1 && d->kh > 1 && d->conv_w >= 16 && d->conv_h >= 8 && (d->kh - 1) * dil_y <= 6) ? 1 : 0;
     PGPP_REQUIRE(dil_y == 1 || p.reuse, "dil_y > 1 is only supported on the slab-reuse path (images of at least 16 x 8, (kh-1)*dil_y <= 6)");
     if (getenv("PGPP_IGEMM_NO_REUSE")) p.reuse = 0;
-    if (p.reuse) { p.tw = 16; p.th = 8; p.tn = 1; }
+    // single-slab mode (reuse == 2): layers whose GEMM N is at most 64 are bound by the L2 -> shared-memory traffic of the three
+    // filter-column slabs; an 8 x 16 pixel tile reads ONE (8 + kw - 1) x (16 + kh - 1) slab per (channel block, part) instead and
+    // takes every tap as a row-shifted descriptor view of it (2.7x fewer activation bytes for 3 x 3).  Needs resident weights.
+    const int slab_pitch = 8 + d->kw - 1, slab_rows2 = 16 + d->kh - 1;
+    const bool slab2_shape = d->stride == 1 && d->kh * d->kw > 1 && d->kh * d->kw <= 64 && dil_y == 1 && d->c_pad % 64 == 0 && d->block_n <= 64 &&
+                             d->phases * d->phase_stride <= d->block_n && d->conv_w >= 8 && d->conv_h >= 16 && need_parts <= 2 &&
+                             !getenv("PGPP_IGEMM_NO_SLAB2") && !getenv("PGPP_IGEMM_NO_RESIDENT");
+    if (slab2_shape) {
+        const long long stage = ((long long)slab_pitch * slab_rows2 * 128 + 1023) & ~1023ll;
+        const long long n_bt = (long long)(d->c_pad / 64) * d->kh * d->kw * need_parts;
+        const long long b_pitch2 = ((long long)d->block_n * 128 + 1023) & ~1023ll;
+        const long long need = 1024 + 2 * stage + n_bt * b_pitch2 + 8 * (2 * 2 + 2 * n_bt + 5) + 32 + 16ll * d->block_n;
+        const long long tiles = (long long)((d->conv_w + 7) / 8) * ((d->conv_h + 15) / 16) * d->n;
+        if (n_bt <= 64 && need <= 227 * 1024 && tiles > sm_count()) p.reuse = 2;
+    }
+    if (p.reuse == 2) { p.tw = 8; p.th = 16; p.tn = 1; }
+    else if (p.reuse) { p.tw = 16; p.th = 8; p.tn = 1; }
     else {
         p.tw = pow2_ceil(d->conv_w); if (p.tw > kTileM) p.tw = kTileM;
         p.th = pow2_ceil(d->conv_h); if (p.th > kTileM / p.tw) p.th = kTileM / p.tw;
         p.tn = kTileM / (p.tw * p.th);
     }
-    p.n_groups = p.reuse ? d->kw : d->kh * d->kw;
-    p.inner = p.reuse ? d->kh : 1;
+    p.n_groups = p.reuse == 2 ? 1 : (p.reuse ? d->kw : d->kh * d->kw);
+    p.inner = p.reuse == 2 ? d->kh * d->kw : (p.reuse ? d->kh : 1);
     p.tiles_x = (d->conv_w + p.tw - 1) / p.tw;
     p.tiles_y = (d->conv_h + p.th - 1) / p.th;
     p.tiles_n = (d->n + p.tn - 1) / p.tn;
@@ -731,6 +879,17 @@ extern "C" int pgpp_conv2d_igemm(const pgpp_conv_desc* d, void* stream) {
     p.slab_bytes = (unsigned)slab_rows * row_bytes;
     p.a_tx_bytes = p.parts * p.slab_bytes;
     p.a_stage_bytes = (p.a_tx_bytes + 1023u) & ~1023u;
+    p.sbo_a = 8 * row_bytes;
+    for (int j = 0; j < 64; j++) p.tap_off16[j] = 0;
+    if (p.reuse == 2) {             // one part per stage; tap (ky, kx) starts (ky * pitch + kx) pixel rows into the slab
+        p.slab_bytes = (unsigned)(slab_pitch * slab_rows2) * row_bytes;
+        p.a_tx_bytes = p.slab_bytes;
+        p.a_stage_bytes = (p.slab_bytes + 1023u) & ~1023u;
+        p.sbo_a = (unsigned)slab_pitch * row_bytes;
+        for (int ky = 0; ky < d->kh; ky++)
+            for (int kx = 0; kx < d->kw; kx++)
+                p.tap_off16[ky * d->kw + kx] = (unsigned short)(((ky * slab_pitch + kx) * row_bytes) >> 4);
+    }
     p.ky_step_bytes = (unsigned)(p.tw * dil_y) * row_bytes;
     p.b_bytes = (unsigned)d->block_n * row_bytes;
     p.b_pitch = (p.b_bytes + 1023u) & ~1023u;
@@ -753,8 +912,9 @@ extern "C" int pgpp_conv2d_igemm(const pgpp_conv_desc* d, void* stream) {
         p.b_resident = 1;
         p.b_stages = (int)n_btiles;
         p.a_stages = 2;
-        while (p.a_stages < 6 && smem_need(p.a_stages + 1, n_btiles) <= smem_max) p.a_stages++;
+        while (p.a_stages < (p.reuse == 2 ? 8 : 6) && smem_need(p.a_stages + 1, n_btiles) <= smem_max) p.a_stages++;
     } else {
+        PGPP_REQUIRE(p.reuse != 2, "internal: single-slab mode needs resident weights");
         p.a_stages = 2;
         p.b_stages = 2;
         if (smem_need(2, 2) > smem_max) { set_error("tile does not fit shared memory"); return PGPP_ERR_UNSUPPORTED; }
@@ -784,7 +944,7 @@ extern "C" int pgpp_conv2d_igemm(const pgpp_conv_desc* d, void* stream) {
     p.fold_gain = (d->gain > 0.f && (d->act_fn == PGPP_ACT_LINEAR || d->act_fn == PGPP_ACT_RELU ||
                                      (d->act_fn == PGPP_ACT_LRELU && d->alpha >= 0.f && d->alpha <= 1.f))) ? 1 : 0;
     // stacked products (see mma_role): fp32-parity mode with 2 parts, resident 64-column weight tiles, fast epilogue
-    p.stack = (need_parts == 2 && d->block_n == 64 && p.b_resident && p.kb == 64 && (p.inner == 3 || p.inner == 1) && p.tn == 1 && p.fold_gain &&
+    p.stack = (need_parts == 2 && d->block_n == 64 && p.b_resident && p.kb == 64 && (p.inner == 3 || p.inner == 1 || p.reuse == 2) && p.tn == 1 && p.fold_gain &&
                !d->spade_x && !getenv("PGPP_IGEMM_NO_STACK")) ? 1 : 0;
     p.acc_cols = p.stack ? 2 * d->block_n : d->block_n;
     p.idesc_stack = (1u << 4) | (1u << 7) | (1u << 10) | ((unsigned)((2 * d->block_n) >> 3) << 17) | ((unsigned)(kTileM >> 4) << 24);
@@ -804,7 +964,8 @@ extern "C" int pgpp_conv2d_igemm(const pgpp_conv_desc* d, void* stream) {
         const cuuint64_t dims[5] = {(cuuint64_t)d->c_pad, (cuuint64_t)d->w, (cuuint64_t)d->h, (cuuint64_t)d->n, (cuuint64_t)d->a_parts};
         const cuuint64_t strides[4] = {(cuuint64_t)pix_stride * 2, (cuuint64_t)pix_stride * 2 * d->w, (cuuint64_t)pix_stride * 2 * d->w * d->h,
                                        (cuuint64_t)pix_stride * 2 * d->w * d->h * d->n};
-        const cuuint32_t box[5] = {(cuuint32_t)p.kb, (cuuint32_t)(p.tw * d->stride), (cuuint32_t)((p.th + (p.inner - 1) * dil_y) * d->stride), (cuuint32_t)p.tn, 1};
+        cuuint32_t box[5] = {(cuuint32_t)p.kb, (cuuint32_t)(p.tw * d->stride), (cuuint32_t)((p.th + (p.inner - 1) * dil_y) * d->stride), (cuuint32_t)p.tn, 1};
+        if (p.reuse == 2) { box[1] = (cuuint32_t)slab_pitch; box[2] = (cuuint32_t)slab_rows2; }
         const cuuint32_t estr[5] = {1, (cuuint32_t)d->stride, (cuuint32_t)d->stride, 1, 1};
         const CUtensorMapSwizzle sw = row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
         CUresult r = encode(&map_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(d->act), dims, strides, box, estr,
