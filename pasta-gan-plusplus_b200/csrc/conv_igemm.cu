@@ -103,6 +103,8 @@ __device__ __forceinline__ TileCoord decode_tile(const IgemmParams& p, long long
 
 struct PixelCoord { int px, py, pn; };
 
+template <class OT> struct IsBf16 { static constexpr bool value = false; };
+template <> struct IsBf16<__nv_bfloat16> { static constexpr bool value = true; };
 template <class OT> __device__ __forceinline__ OT cvt_out(float v);
 template <> __device__ __forceinline__ float cvt_out<float>(float v) { return v; }
 template <> __device__ __forceinline__ __nv_bfloat16 cvt_out<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
@@ -207,14 +209,16 @@ __device__ __forceinline__ void epilogue_fast(const IgemmParams& p, const TileCo
             for (int j = 0; j < 16; j++) prev[j] = j < valid ? cvt_in<OT>(src[(unsigned)j * cs]) : 0.f;
         }
         float v[16];
+        const float4* s_cs4 = reinterpret_cast<const float4*>(s_cs + c0);      // (scale, shift) of two columns per 128-bit load
         #pragma unroll
-        for (int j = 0; j < 16; j++) {
-            const float2 q = s_cs[c0 + j];
-            float r = fmaf(__uint_as_float(acc[j]), q.x, nz) + q.y;
-            if (A == PGPP_ACT_RELU) r = fmaxf(r, 0.f);
-            if (A == PGPP_ACT_LRELU) r = fmaxf(r, r * alpha);       // 0 <= alpha <= 1 (checked on the host)
-            if (CLAMP) r = fminf(fmaxf(r, -clamp), clamp);
-            v[j] = r;
+        for (int j = 0; j < 16; j += 2) {
+            const float4 q = s_cs4[j >> 1];
+            float r0 = fmaf(__uint_as_float(acc[j]), q.x, nz) + q.y;
+            float r1 = fmaf(__uint_as_float(acc[j + 1]), q.z, nz) + q.w;
+            if (A == PGPP_ACT_RELU) { r0 = fmaxf(r0, 0.f); r1 = fmaxf(r1, 0.f); }
+            if (A == PGPP_ACT_LRELU) { r0 = fmaxf(r0, r0 * alpha); r1 = fmaxf(r1, r1 * alpha); }    // 0 <= alpha <= 1 (checked on the host)
+            if (CLAMP) { r0 = fminf(fmaxf(r0, -clamp), clamp); r1 = fminf(fmaxf(r1, -clamp), clamp); }
+            v[j] = r0; v[j + 1] = r1;
         }
         if (ACC) {
             // lanes are consecutive pixels: coalesced along W for NCHW tensors
@@ -225,6 +229,25 @@ __device__ __forceinline__ void epilogue_fast(const IgemmParams& p, const TileCo
         } else if (nhwc && valid == 16 && ((base + oc0) * sizeof(OT)) % 16 == 0 && ((uintptr_t)out & 15) == 0) {
             // channels-innermost output: 16 consecutive channels of one pixel, 128-bit stores; with out_parts > 1 the
             // bf16 expansion of the value is written (part q = bf16(v - earlier parts)): the next conv's operand format
+            if (IsBf16<OT>::value) {
+                // packed conversions (two values per cvt.rn.bf16x2.f32); the residual is formed only if another part follows
+                for (int part = 0; part < p.out_parts; part++) {
+                    const bool more = part + 1 < p.out_parts;
+                    uint32_t w[8];
+                    #pragma unroll
+                    for (int j = 0; j < 8; j++) {
+                        const __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+                        w[j] = *reinterpret_cast<const uint32_t*>(&h);
+                        if (more) {
+                            v[2 * j] -= __uint_as_float(w[j] << 16);
+                            v[2 * j + 1] -= __uint_as_float(w[j] & 0xffff0000u);
+                        }
+                    }
+                    int4* dst = reinterpret_cast<int4*>(out + part * p.out_part_stride + base + oc0);
+                    dst[0] = make_int4((int)w[0], (int)w[1], (int)w[2], (int)w[3]);
+                    dst[1] = make_int4((int)w[4], (int)w[5], (int)w[6], (int)w[7]);
+                }
+            } else
             for (int part = 0; part < p.out_parts; part++) {
                 __align__(16) OT tmp[16];
                 #pragma unroll
@@ -596,7 +619,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
     const uint32_t bres_free_bar = bar_base + 8u * (2 * SA + 2 * SB + 4);     // resident weights may be overwritten (one completion per reload)
     const uint32_t tmem_slot = bar_base + 8u * (2 * SA + 2 * SB + 5);
     // per-column epilogue parameters (scale, shift), double-buffered with the accumulator: float2 [2][block_n]
-    float2* const s_params = reinterpret_cast<float2*>(smem_raw + (tmem_slot + 16u - smem_u32(smem_raw)));
+    float2* const s_params = reinterpret_cast<float2*>(smem_raw + (((tmem_slot + 16u + 15u) & ~15u) - smem_u32(smem_raw)));   // 16-byte aligned: read as float4
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
