@@ -273,3 +273,43 @@ def test_row_group_im2col_weights_reproduce_the_convolution(ic, k, pad):
         out += torch.einsum('nyxc,oc->noyx', pk[:, t_ * r:t_ * r + H], wt[t_])
     want = torch.nn.functional.conv2d(x, w.double(), padding=pad)
     assert rel_l2(out, want) < 3e-7
+
+
+def test_c_abi_argument_validation_needs_no_gpu():
+    """every entry point validates its arguments before the first CUDA call: error code + message through pgpp_last_error(),
+    exercised here on the CPU box with dummy (never dereferenced) pointers"""
+    lib = custom_ops.load_library()
+    err = lambda: lib.pgpp_last_error().decode()
+    p = ctypes.c_void_p(0x1000)             # non-NULL, 16-byte aligned, never touched: validation fails first
+    d = custom_ops.ConvDesc()
+    assert lib.pgpp_conv2d_igemm(None, None) != 0 and 'NULL' in err()
+    d.act = d.wgt = d.out = 0x1000
+    d.n = d.h = d.w = d.conv_h = d.conv_w = d.out_h = d.out_w = 8
+    d.c_pad = 64; d.kh = d.kw = 3; d.stride = 1; d.phases = 1; d.o = d.phase_stride = 64; d.o_rows = 64; d.block_n = 48; d.products = 1
+    d.a_parts = d.b_parts = 1; d.act_fn = 1
+    assert lib.pgpp_conv2d_igemm(ctypes.byref(d), None) != 0 and 'block_n' in err()
+    d.block_n = 64; d.products = 2
+    assert lib.pgpp_conv2d_igemm(ctypes.byref(d), None) != 0 and 'products' in err()
+    d.products = 3
+    assert lib.pgpp_conv2d_igemm(ctypes.byref(d), None) != 0 and 'parts' in err()
+    d.products = 1; d.stride = 3
+    assert lib.pgpp_conv2d_igemm(ctypes.byref(d), None) != 0 and 'stride' in err()
+    d.stride = 1; d.act_fn = 12
+    assert lib.pgpp_conv2d_igemm(ctypes.byref(d), None) != 0 and 'no CUDA kernel found' in err()
+    w = custom_ops.WgradDesc()
+    w.small = w.large = w.out = w.workspace = 0x1000
+    w.s_parts = w.l_parts = 1; w.n = 1; w.ca = w.cb = 8; w.ca_pad = w.cb_pad = 64; w.hs = w.ws = w.hl = w.wl = 8
+    w.kh = w.kw = 3; w.pad_y = w.pad_x = 1; w.stride = 4; w.products = 1
+    assert lib.pgpp_conv2d_wgrad(ctypes.byref(w), None) != 0 and 'stride' in err()
+    w.stride = 1; w.cb_pad = 40
+    assert lib.pgpp_conv2d_wgrad(ctypes.byref(w), None) != 0 and 'cb_pad' in err()
+    assert lib.pgpp_u8_to_f32(p, 1, 4, 16, p, 4, 2, 1, None, None) != 0 and 'channel slice' in err()
+    assert lib.pgpp_image_to_u8(p, 1, 0, 16, p, 0, None) != 0 and 'bad tensor size' in err()
+    assert lib.pgpp_grid_sample_2d(p, p, p, 1, 1, 0, 4, 2, 2, None) != 0 and 'bad grid_sample sizes' in err()
+    assert lib.pgpp_grid_sample_2d_backward(p, p, p, None, None, 1, 1, 4, 4, 2, 2, None) != 0 and 'at least one' in err()
+    assert lib.pgpp_conv2d_direct(p, p, None, 1, 2, 8, 8, 8, 3, 3, 1, 1, 1.0, 1, 0.0, 1.0, -1.0, p, None, 0, 0, 0, None) != 0 and 'C * kh * kw <= 16' in err()
+    assert lib.pgpp_conv2d_direct(p, p, None, 1, 1, 8, 8, 8, 3, 3, 1, 1, 1.0, 4, 0.0, 1.0, -1.0, p, None, 0, 0, 0, None) != 0 and 'linear, relu or lrelu' in err()
+    taps = (ctypes.c_float * 25)(*([0.04] * 25))
+    size = custom_ops.c_i64x4(1, 8, 8, 8); stride = custom_ops.c_i64x4(512, 64, 8, 1)
+    assert lib.pgpp_fir_pack(p, size, stride, taps, 5, 5, 2, 2, 2, 2, 0, 1.0, p, 64, 2, None) != 0 and 'filter up to 4 x 4' in err()
+    assert lib.pgpp_mix_pack(p, p, p, p, p, None, None, None, p, 1, 8, 8, 8, 64, 2, None) != 0 and 'second term' in err()
