@@ -34,6 +34,45 @@ def _needs_grad(*tensors):
     return torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors)
 
 
+class _Pad:
+    """(x0, x1, y0, y1) padding of the up-sampled image, with the bookkeeping the FIR stages add (conv2d_resample.py:96-106)"""
+
+    def __init__(self, padding):
+        self.x0, self.x1, self.y0, self.y1 = _parse_padding(padding)
+
+    def widen(self, fw, fh, up, down):
+        for factor, lo, hi in ((up, lambda t: (t + up - 1) // 2, lambda t: (t - up) // 2),
+                               (down, lambda t: (t - down + 1) // 2, lambda t: (t - down) // 2)):
+            if factor > 1:
+                self.x0 += lo(fw); self.x1 += hi(fw)
+                self.y0 += lo(fh); self.y1 += hi(fh)
+        return self
+
+    def shift(self, dx0, dx1, dy0, dy1):
+        self.x0 += dx0; self.x1 += dx1; self.y0 += dy0; self.y1 += dy1
+        return self
+
+    @property
+    def fir(self):              # upfirdn2d order
+        return [self.x0, self.x1, self.y0, self.y1]
+
+    @property
+    def conv(self):             # F.conv2d order, valid only when symmetric
+        return [self.y0, self.x0]
+
+    @property
+    def symmetric(self):
+        return self.x0 == self.x1 and self.y0 == self.y1 and min(self.x0, self.y0) >= 0
+
+
+def _transposed_weight(w, groups):
+    """[O, I/g, kh, kw] -> the [I, O/g, kh, kw] layout conv_transpose2d expects"""
+    o, ig, kh, kw = _get_weight_shape(w)
+    if groups == 1:
+        return w.transpose(0, 1)
+    return w.reshape(groups, o // groups, ig, kh, kw).transpose(1, 2).reshape(groups * ig, o // groups, kh, kw)
+
+
 @misc.profiled_function
 def conv2d_resample(x, w, f=None, up=1, down=1, padding=0, groups=1, flip_weight=True, flip_filter=False):
     """x [N, I, H, W], w [O, I/groups, kh, kw], f from upfirdn2d.setup_filter() or None.  Padding is given
@@ -44,71 +83,40 @@ def conv2d_resample(x, w, f=None, up=1, down=1, padding=0, groups=1, flip_weight
     assert isinstance(up, int) and (up >= 1)
     assert isinstance(down, int) and (down >= 1)
     assert isinstance(groups, int) and (groups >= 1)
-    out_channels, in_channels_per_group, kh, kw = _get_weight_shape(w)
+    _, _, kh, kw = _get_weight_shape(w)
     fw, fh = _get_filter_size(f)
-    px0, px1, py0, py1 = _parse_padding(padding)
+    pad = _Pad(padding)
 
-    # fused polyphase form of the up=2 layer (inference)
-    if (up == 2 and down == 1 and groups == 1 and kh == 3 and kw == 3 and f is not None and f.ndim == 2 and fw == 4 and fh == 4
-            and (px0, px1, py0, py1) == (1, 1, 1, 1) and conv2d_gradfix._should_use_custom_op(x) and not _needs_grad(x, w)):
+    # fused polyphase form of the up=2 layer (inference): one implicit-GEMM launch
+    if (up == 2 and down == 1 and groups == 1 and (kh, kw) == (3, 3) and f is not None and f.ndim == 2 and (fw, fh) == (4, 4)
+            and pad.fir == [1, 1, 1, 1] and conv2d_gradfix._should_use_custom_op(x) and not _needs_grad(x, w)):
         _, parts = conv2d_gradfix._PRODUCTS[conv2d_gradfix.precision_for(x.dtype)]
-        pw = conv2d_gradfix.packed_up2(w, f, flip_weight, flip_filter, parts)
-        return conv2d_gradfix.igemm_conv(x, pw)
+        return conv2d_gradfix.igemm_conv(x, conv2d_gradfix.packed_up2(w, f, flip_weight, flip_filter, parts))
 
-    # padding bookkeeping of conv2d_resample.py:96-106
-    if up > 1:
-        px0 += (fw + up - 1) // 2
-        px1 += (fw - up) // 2
-        py0 += (fh + up - 1) // 2
-        py1 += (fh - up) // 2
-    if down > 1:
-        px0 += (fw - down + 1) // 2
-        px1 += (fw - down) // 2
-        py0 += (fh - down + 1) // 2
-        py1 += (fh - down) // 2
+    pad.widen(fw, fh, up, down)
+    fir = lambda t, **kw_: upfirdn2d.upfirdn2d(x=t, f=f, flip_filter=flip_filter, **kw_)
+    conv = lambda t, **kw_: _conv2d_wrapper(x=t, w=w, groups=groups, flip_weight=flip_weight, **kw_)
+    pointwise = kh == 1 and kw == 1
 
-    # 1x1 kernel + downsampling: filter first, convolve the smaller image
-    if kw == 1 and kh == 1 and (down > 1 and up == 1):
-        x = upfirdn2d.upfirdn2d(x=x, f=f, down=down, padding=[px0, px1, py0, py1], flip_filter=flip_filter)
-        return _conv2d_wrapper(x=x, w=w, groups=groups, flip_weight=flip_weight)
+    if up == 1 and down > 1:
+        if pointwise:                       # decimate first, convolve the smaller image (conv2d_resample.py:107-110)
+            return conv(fir(x, down=down, padding=pad.fir))
+        return conv(fir(x, padding=pad.fir), stride=down)       # blur, then strided convolution (:119-122)
 
-    # 1x1 kernel + upsampling: convolve the smaller image, upsample afterwards
-    if kw == 1 and kh == 1 and (up > 1 and down == 1):
-        x = _conv2d_wrapper(x=x, w=w, groups=groups, flip_weight=flip_weight)
-        return upfirdn2d.upfirdn2d(x=x, f=f, up=up, padding=[px0, px1, py0, py1], gain=up ** 2, flip_filter=flip_filter)
+    if up > 1 and down == 1 and pointwise:  # convolve the smaller image, interpolate afterwards (:113-116)
+        return fir(conv(x), up=up, padding=pad.fir, gain=up ** 2)
 
-    # downsampling only: blur, then strided convolution
-    if down > 1 and up == 1:
-        x = upfirdn2d.upfirdn2d(x=x, f=f, padding=[px0, px1, py0, py1], flip_filter=flip_filter)
-        return _conv2d_wrapper(x=x, w=w, stride=down, groups=groups, flip_weight=flip_weight)
+    if up > 1:                              # transposed strided convolution, then blur (:125-142)
+        pad.shift(-(kw - 1), -(kw - up), -(kh - 1), -(kh - up))
+        pxt = max(min(-pad.x0, -pad.x1), 0)
+        pyt = max(min(-pad.y0, -pad.y1), 0)
+        x = _conv2d_wrapper(x=x, w=_transposed_weight(w, groups), stride=up, padding=[pyt, pxt], groups=groups, transpose=True,
+                            flip_weight=(not flip_weight))
+        x = fir(x, padding=pad.shift(pxt, pxt, pyt, pyt).fir, gain=up ** 2)
+        return fir(x, down=down) if down > 1 else x
 
-    # upsampling (optionally followed by downsampling): transposed strided convolution, then blur
-    if up > 1:
-        if groups == 1:
-            w = w.transpose(0, 1)
-        else:
-            w = w.reshape(groups, out_channels // groups, in_channels_per_group, kh, kw).transpose(1, 2)
-            w = w.reshape(groups * in_channels_per_group, out_channels // groups, kh, kw)
-        px0 -= kw - 1
-        px1 -= kw - up
-        py0 -= kh - 1
-        py1 -= kh - up
-        pxt = max(min(-px0, -px1), 0)
-        pyt = max(min(-py0, -py1), 0)
-        x = _conv2d_wrapper(x=x, w=w, stride=up, padding=[pyt, pxt], groups=groups, transpose=True, flip_weight=(not flip_weight))
-        x = upfirdn2d.upfirdn2d(x=x, f=f, padding=[px0 + pxt, px1 + pxt, py0 + pyt, py1 + pyt], gain=up ** 2, flip_filter=flip_filter)
-        if down > 1:
-            x = upfirdn2d.upfirdn2d(x=x, f=f, down=down, flip_filter=flip_filter)
-        return x
+    if pad.symmetric:                       # no resampling: plain convolution (:145-147)
+        return conv(x, padding=pad.conv)
 
-    # no resampling and symmetric non-negative padding: plain convolution
-    if up == 1 and down == 1:
-        if px0 == px1 and py0 == py1 and px0 >= 0 and py0 >= 0:
-            return _conv2d_wrapper(x=x, w=w, padding=[py0, px0], groups=groups, flip_weight=flip_weight)
-
-    # anything else: pad/upsample with upfirdn2d, convolve without padding, downsample
-    x = upfirdn2d.upfirdn2d(x=x, f=(f if up > 1 else None), up=up, padding=[px0, px1, py0, py1], gain=up ** 2, flip_filter=flip_filter)
-    x = _conv2d_wrapper(x=x, w=w, groups=groups, flip_weight=flip_weight)
-    if down > 1:
-        x = upfirdn2d.upfirdn2d(x=x, f=f, down=down, flip_filter=flip_filter)
-    return x
+    # anything else (:150-154): pad with upfirdn2d, convolve without padding
+    return conv(upfirdn2d.upfirdn2d(x=x, f=None, up=up, padding=pad.fir, gain=up ** 2, flip_filter=flip_filter))

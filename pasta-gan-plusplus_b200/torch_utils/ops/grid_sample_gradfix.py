@@ -25,48 +25,47 @@ def _init():
 
 
 def grid_sample(input, grid):
-    if _should_use_custom_op(input):
-        return _GridSample2dForward.apply(input, grid)
-    return torch.nn.functional.grid_sample(input=input, grid=grid, mode='bilinear', padding_mode='zeros', align_corners=False)
+    """bilinear / zeros / align_corners=False sampling of `input` [N,C,H,W] at `grid` [N,Ho,Wo,2]"""
+    if not _should_use_custom_op(input):
+        return torch.nn.functional.grid_sample(input=input, grid=grid, mode='bilinear', padding_mode='zeros', align_corners=False)
+    return _Sample.apply(input, grid)
 
 
 def _should_use_custom_op(input=None):
     return enabled and (input is None or input.device.type == 'cuda')
 
 
-class _GridSample2dForward(torch.autograd.Function):
+class _Sample(torch.autograd.Function):
+    """out = A(grid) @ input.  Linear in `input`, so its input-gradient is A^T @ grad_out (`_SampleGrad`) and the gradient of THAT
+    with respect to grad_out is A again: a forward sample of the incoming second-order gradient."""
+
     @staticmethod
-    def forward(ctx, input, grid):
-        assert input.ndim == 4
-        assert grid.ndim == 4
+    def forward(ctx, image, grid):
+        assert image.ndim == 4 and grid.ndim == 4
         _init()
-        output = _plugin.forward(input, grid)
-        ctx.save_for_backward(input, grid)
-        return output
+        ctx.save_for_backward(image, grid)
+        return _plugin.forward(image, grid)
 
     @staticmethod
-    def backward(ctx, grad_output):
-        input, grid = ctx.saved_tensors
-        grad_input, grad_grid = _GridSample2dBackward.apply(grad_output, input, grid)
-        return grad_input, grad_grid
+    def backward(ctx, d_out):
+        image, grid = ctx.saved_tensors
+        return _SampleGrad.apply(d_out, image, grid)
 
 
-class _GridSample2dBackward(torch.autograd.Function):
+class _SampleGrad(torch.autograd.Function):
+    """(d_image, d_grid) of `_Sample`; differentiable once more with respect to d_out only (what R1 needs,
+    grid_sample_gradfix.py:67-83) - the grid gradient of the second order is not provided, as in the reference."""
+
     @staticmethod
-    def forward(ctx, grad_output, input, grid):
+    def forward(ctx, d_out, image, grid):
         _init()
-        grad_input, grad_grid = _plugin.backward(grad_output, input, grid)
         ctx.save_for_backward(grid)
-        return grad_input, grad_grid
+        return _plugin.backward(d_out, image, grid)
 
     @staticmethod
-    def backward(ctx, grad2_grad_input, grad2_grad_grid):
-        _ = grad2_grad_grid     # unused, as in the reference (grid_sample_gradfix.py:70)
+    def backward(ctx, dd_image, dd_grid):
+        del dd_grid
         grid, = ctx.saved_tensors
-        grad2_grad_output = None
-        grad2_input = None
-        grad2_grid = None
-        if ctx.needs_input_grad[0]:
-            grad2_grad_output = _GridSample2dForward.apply(grad2_grad_input, grid)
         assert not ctx.needs_input_grad[2]
-        return grad2_grad_output, grad2_input, grad2_grid
+        dd_out = _Sample.apply(dd_image, grid) if ctx.needs_input_grad[0] else None
+        return dd_out, None, None
