@@ -190,8 +190,8 @@ def class_source(record, class_name):
 def build_module(record, registry=None):
     """Instantiate this package's class of the same name with the record's init arguments and load its weights."""
     if registry is None:
-        from .training import augment, generator, synthesis
-        registry = {**vars(synthesis), **vars(generator), 'AugmentPipe': augment.AugmentPipe}
+        from .training import augment, discriminator, generator, synthesis
+        registry = {**vars(synthesis), **vars(generator), **vars(discriminator), 'AugmentPipe': augment.AugmentPipe}
     if record.class_name not in registry:
         raise KeyError(f'this package has no class named {record.class_name}')
     module = registry[record.class_name](*record.init_args, **record.init_kwargs)
