@@ -330,6 +330,136 @@ class GeneratorPipeline:
         return None
 
 
+TRAIN_DESC = ('PASTA-GAN++ 512px training iteration (training_loop_fullbody.py:603-650, loss_fullbody.py:115-330): phases Gboth, Dboth, '
+              'D_parsingboth x2 (the reference lists D_parsing twice) = G forward/backward through D and D_parsing, D and D_parsing steps on '
+              'generated + real batches with the R1 penalty (conv2d_gradfix double backward) EVERY iteration (lazy regularisation off), '
+              'Adam, G_ema; GeneratorFull_v20 43.1 M + 2 x Discriminator (channel_base 32768, c_dim 512, fp16 blocks at >= 128 px as '
+              'train.py:196); l1 10, mask 30, r1_gamma 10, vgg / contextual 0 (checkpoints not shipped), aug=noaug')
+
+
+def make_train_inputs_u8(batch, seed):
+    """what the data loader delivers per iteration (training_loop_fullbody.py:540-590): uint8 host tensors"""
+    d = make_generator_inputs_u8(batch, seed)
+    g = torch.Generator().manual_seed(seed + 7)
+    band = torch.zeros(1, 1, 1, 512, dtype=torch.bool); band[..., 96:416] = True
+    real = torch.randint(0, 256, (batch, 3, 512, 512), generator=g, dtype=torch.uint8)
+    d['real_img'] = torch.where(band, real, torch.full_like(real, 255))
+    d['gt_parsing'] = torch.randint(0, 7, (batch, 1, 512, 512), generator=g, dtype=torch.uint8)
+    return d
+
+
+def train_inputs_to_device(u8, device):
+    x = to_device_f32({k: v for k, v in u8.items() if k != 'gt_parsing'}, device)
+    return dict(real_img=x['real_img'], style_input=x['c'], retain=x['retain'], pose=x['pose'], denorm_upper_input=x['denorm_upper'],
+                denorm_lower_input=x['denorm_lower'], denorm_upper_mask=x['denorm_upper_mask'], denorm_lower_mask=x['denorm_lower_mask'],
+                gt_parsing=u8['gt_parsing'].to(device, non_blocking=True).float())
+
+
+def train_leg(steps, warmup, batch, precision, device, rank, world, fp16_res=3):
+    """BASELINE configs[4]: the G + D + D_parsing training iteration with R1, data-parallel (DDP gradient all-reduce over NCCL when
+    world > 1).  Returns the per-rank measurement dict (times already max-reduced over ranks)."""
+    import torch.distributed as dist
+    ts = importlib.import_module('pgpp_b200.training.training_step')
+    cg = importlib.import_module('pgpp_b200.torch_utils.ops.conv2d_gradfix')
+    custom_ops = importlib.import_module('pgpp_b200.torch_utils.custom_ops')
+    cg.fp32_precision = precision
+    torch.manual_seed(0)
+    G, D, DP = ts.build_networks(device, num_fp16_res=fp16_res)
+    step = ts.TrainingStep(G, D, DP, device, batch_size=batch * world)
+    host = {k: v.pin_memory() for k, v in make_train_inputs_u8(batch, 200 + rank).items()}
+    data = train_inputs_to_device(host, device)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, n):
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(n):
+            fn()
+        b.record()
+        barrier()
+        t = torch.tensor([a.elapsed_time(b)], device=device, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0]) / n
+
+    for _ in range(max(warmup, 3)):
+        step(data)
+    torch.cuda.reset_peak_memory_stats(device)
+    l0 = custom_ops.launch_count()
+    ms = timed(lambda: step(data), steps)
+    launches = (custom_ops.launch_count() - l0) // steps
+    # per-phase split on rank 0 (CUDA events around each phase of one more iteration)
+    phase_ms = {}
+    for ph in dict.fromkeys(p['name'] for p in step.phases):
+        phase_ms[ph] = timed(lambda: step(data, phases=[ph]), 2)
+    # the exchange step alone: the same iteration with the gradient all-reduce suppressed (DDP no_sync) -> exposed all-reduce time
+    nosync_ms = None
+    if world > 1:
+        orig = step.loss.accumulate_gradients
+        step.loss.accumulate_gradients = lambda **kw: orig(**{**kw, 'sync': False})
+        timed(lambda: step(data), 1)
+        nosync_ms = timed(lambda: step(data), steps)
+        step.loss.accumulate_gradients = orig
+
+    # end to end: uint8 pinned-host batch in, loss scalar back, every iteration
+    def e2e_step():
+        d = train_inputs_to_device(host, device)
+        st = step(d)
+        return float(st['Loss/scores/real'].item())
+    e2e_step()
+    e2e_ms = timed(e2e_step, steps)
+    grad_bytes = {n: 4 * sum(p.numel() for p in m.parameters()) for n, m in (('G', G), ('D', D), ('D_parsing', DP))}
+    return {'ms_per_step': ms, 'images_per_sec': batch * world / (ms * 1e-3), 'e2e_ms_per_step': e2e_ms,
+            'e2e_images_per_sec': batch * world / (e2e_ms * 1e-3), 'h2d_bytes_per_step': sum(v.numel() for v in host.values()),
+            'd2h_bytes_per_step': 4, 'gpu_launches_per_step': launches, 'phase_ms': phase_ms,
+            'no_allreduce_ms_per_step': nosync_ms, 'exposed_allreduce_ms': None if nosync_ms is None else ms - nosync_ms,
+            'allreduce_bytes_per_step': grad_bytes['G'] + grad_bytes['D'] + 2 * grad_bytes['D_parsing'], 'grad_bytes': grad_bytes,
+            'collective': f'DDP bucketed gradient all-reduce (NCCL, {world} ranks) per phase' if world > 1 else 'none (1 GPU)',
+            'peak_mem_gb': torch.cuda.max_memory_allocated(device) / 2 ** 30, 'batch_per_gpu': batch, 'global_batch': batch * world,
+            'precision': precision, 'fp16_blocks': fp16_res}
+
+
+def run_train(args):
+    rank = int(os.environ.get('RANK', 0)); world = int(os.environ.get('WORLD_SIZE', 1)); local = int(os.environ.get('LOCAL_RANK', 0))
+    assert torch.cuda.is_available(), 'bench.py needs a GPU'
+    torch.cuda.set_device(local)
+    device = torch.device('cuda', local)
+    if world > 1:
+        torch.distributed.init_process_group('nccl', device_id=device)
+    from __graft_entry__ import load_pkg
+    load_pkg()
+    importlib.import_module('pgpp_b200.torch_utils.custom_ops').load_library()
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    batch = args.batch if args.batch != 32 else 8
+    with ClockSampler(local) as clocks:
+        r = train_leg(args.steps, args.warmup, batch, args.precision, device, rank, world, fp16_res=args.fp16_res)
+    if rank == 0:
+        line = {'metric': 'training_512px_images_per_sec', 'value': r['images_per_sec'], 'unit': 'images/s', 'n_gpus': world,
+                'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': r['ms_per_step'], 'higher_is_better': True,
+                'scaling': 'weak', 'vs_baseline': None,
+                'dtype': f'f32 tensors ({args.precision} split tcgen05 MMAs); D blocks >= 128 px in fp16 (native f16 MMA)' if args.fp16_res else
+                         f'f32 tensors ({args.precision} split tcgen05 MMAs)',
+                'data': 'synthetic',
+                'config': {'workload': TRAIN_DESC, 'batch_per_gpu': batch, 'global_batch': batch * world, 'resolution': RES,
+                           'parallelism': f'data-parallel x{world}, DDP gradient all-reduce over NCCL', 'precision': args.precision,
+                           'l2': 'per-step working set (tens of GB of saved activations) exceeds the 126 MB L2; no flush needed'},
+                'clocks': clocks.summary(), 'gpu_launches': r['gpu_launches_per_step'] * args.steps,
+                'e2e': {'value': r['e2e_images_per_sec'], 'unit': 'images/s', 'h2d_bytes_per_step': r['h2d_bytes_per_step'],
+                        'd2h_bytes_per_step': r['d2h_bytes_per_step'],
+                        'note': 'uint8 pinned-host batch in (+ on-device /127.5-1), one loss scalar read back, every iteration'},
+                'train': r}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
+
+
 def run_ours(args):
     rank = int(os.environ.get('RANK', 0)); world = int(os.environ.get('WORLD_SIZE', 1)); local = int(os.environ.get('LOCAL_RANK', 0))
     assert torch.cuda.is_available(), 'bench.py needs a GPU (there is no CPU fallback; use --impl reference for the CPU ref path)'
@@ -432,6 +562,16 @@ def run_ours(args):
     if world > 1:
         torch.distributed.all_reduce(times, op=torch.distributed.ReduceOp.MAX)
     bf16_ms = float(times[0])
+
+    # ---- BASELINE configs[4] beside the headline: a few training iterations (G + D + D_parsing with R1, DDP all-reduce when world > 1) ----
+    train = None
+    if gen_mode and args.train_steps > 0:
+        try:
+            train = train_leg(args.train_steps, 1, 8, args.precision, device, rank, world, fp16_res=args.fp16_res)
+        except Exception as e:      # noqa: BLE001 - the extra measurement must never break the contract line
+            train = {'error': f'{type(e).__name__}: {str(e)[:300]}'}
+        cg.fp32_precision = args.precision
+        torch.cuda.empty_cache()
 
     if rank == 0:
         pk = peaks()
@@ -566,6 +706,7 @@ def run_ours(args):
             'cpu_baseline': cpu,
             'parity_vs_cpu_oracle': parity,
             'batch1': batch1,
+            'train': train,
             'bf16_mode': {'value': imgs / (bf16_ms * 1e-3), 'unit': 'images/s', 'ms_per_step': bf16_ms / args.steps, 'roofline': roof_bf16,
                           'parity_vs_cpu_oracle': parity_bf16,
                           'note': 'same step with single-product bf16 MMAs (per-layer rel error ~3e-3); reported separately, not the headline'},
@@ -584,12 +725,17 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--batch', type=int, default=32, help='images per GPU per step')
     ap.add_argument('--precision', default='bf16x2', choices=['bf16', 'bf16x2', 'bf16x3'])
-    ap.add_argument('--workload', default='generator', choices=['generator', 'chain'],
-                    help='generator: the full GeneratorFull_v20 forward (BASELINE configs[1]); chain: the modulated-conv synthesis chain only')
+    ap.add_argument('--workload', default='generator', choices=['generator', 'chain', 'train'],
+                    help='generator: the full GeneratorFull_v20 forward (BASELINE configs[1]); chain: the modulated-conv synthesis chain only; '
+                         'train: the G + D training iteration with R1 under DDP (BASELINE configs[4], batch 8 per GPU)')
+    ap.add_argument('--train-steps', type=int, default=3, help='generator workload: also time this many training iterations (0 = skip)')
+    ap.add_argument('--fp16-res', type=int, default=3, help='train workload: number of highest-resolution D blocks in fp16 (train.py:196)')
     ap.add_argument('--skip-cpu', action='store_true', help='skip the CPU baseline / parity leg')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference(args)
+    elif args.workload == 'train':
+        run_train(args)
     else:
         run_ours(args)
 

@@ -18,11 +18,17 @@ __version__ = '0.1.0'
 OP_MODULES = ('bias_act', 'upfirdn2d', 'conv2d_gradfix', 'conv2d_resample', 'fma', 'grid_sample_gradfix')
 
 
-def install(patch_networks=True):
+def install(patch_networks=True, cpu_tensors=None):
     """Drop-in switch: make `torch_utils.ops.<op>` and `torch_utils.custom_ops` resolve to this package
     and replace `training.networks.modulated_conv2d` (if that module is importable / imported).
-    Call before the reference model modules are imported."""
+    Call before the reference model modules are imported.
+    cpu_tensors: 'ref' lets the ops take their PyTorch reference path for non-CUDA tensors, which is the reference's own
+    dispatch rule (bias_act.py:87, upfirdn2d.py:162) and what its model code relies on when run on the CPU; the default
+    ('raise') refuses them.  CUDA tensors always reach the sm_100a kernels."""
     me = sys.modules[__name__]
+    if cpu_tensors is not None:
+        assert cpu_tensors in ('raise', 'ref')
+        importlib.import_module(f'{__name__}.torch_utils.custom_ops').cpu_tensors = cpu_tensors
     ops = importlib.import_module(f'{__name__}.torch_utils.ops')
     for name in OP_MODULES:
         mod = importlib.import_module(f'{__name__}.torch_utils.ops.{name}')

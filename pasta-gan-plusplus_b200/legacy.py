@@ -13,6 +13,7 @@ allow-list raises `pickle.UnpicklingError`.  The records are then turned into th
 """
 import ast
 import collections
+import inspect
 import io
 import pickle
 
@@ -187,14 +188,32 @@ def class_source(record, class_name):
     raise KeyError(f'{class_name} is not defined in the embedded source of {record.class_name}')
 
 
+def default_registry():
+    """explicit allow-list of the network classes a snapshot may name (never helper functions or other module globals)"""
+    from .training import augment, discriminator, generator, synthesis
+    names = {generator: ('GeneratorFull_v20', 'SynthesisNetworkFull_v18', 'SynthesisBlockFull', 'MappingNetwork', 'ResBlock',
+                         'ConstEncoderNetwork', 'StyleEncoderNetworkV18', 'Dense', 'Spade_Conv2dLayer', 'Spade_Norm_Block',
+                         'Spade_ResBlockV4_512'),
+             synthesis: ('FullyConnectedLayer', 'Conv2dLayer', 'SynthesisLayer', 'ToRGBLayer', 'SynthesisBlock', 'SynthesisChain'),
+             discriminator: ('Discriminator', 'DiscriminatorBlock', 'DiscriminatorEpilogue', 'MinibatchStdLayer'),
+             augment: ('AugmentPipe',)}
+    return {n: getattr(mod, n) for mod, ns in names.items() for n in ns}
+
+
 def build_module(record, registry=None):
     """Instantiate this package's class of the same name with the record's init arguments and load its weights."""
     if registry is None:
-        from .training import augment, discriminator, generator, synthesis
-        registry = {**vars(synthesis), **vars(generator), **vars(discriminator), 'AugmentPipe': augment.AugmentPipe}
-    if record.class_name not in registry:
-        raise KeyError(f'this package has no class named {record.class_name}')
-    module = registry[record.class_name](*record.init_args, **record.init_kwargs)
+        registry = default_registry()
+    cls = registry.get(record.class_name)
+    if cls is None or not (isinstance(cls, type) and issubclass(cls, torch.nn.Module)):
+        raise KeyError(f'this package has no network class named {record.class_name}')
+    # class name and arguments come from the (untrusted) file: only torch.nn.Module classes on the allow-list are
+    # instantiated, and only with arguments their constructor declares
+    try:
+        inspect.signature(cls.__init__).bind(None, *record.init_args, **record.init_kwargs)
+    except TypeError as e:
+        raise pickle.UnpicklingError(f'snapshot arguments do not match {record.class_name}.__init__: {e}') from None
+    module = cls(*record.init_args, **record.init_kwargs)
     module.load_state_dict(state_dict(record), strict=True)
     return module.eval().requires_grad_(False)
 

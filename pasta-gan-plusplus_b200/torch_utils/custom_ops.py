@@ -13,6 +13,12 @@ import torch
 
 verbosity = 'brief'     # 'none', 'brief', 'full' -- kept for compatibility (custom_ops.py:23)
 
+# What `impl='cuda'` does with a NON-CUDA tensor.  'raise' (default): RuntimeError -- nothing is ever silently computed off the
+# kernels.  'ref': the reference's own dispatch rule (bias_act.py:87, upfirdn2d.py:162: "cuda iff the tensor is on a CUDA device,
+# else the ref path"), so that reference model code runs unchanged on CPU tensors through `pgpp_b200.install(cpu_tensors='ref')`.
+# CUDA tensors are unaffected by this switch: they reach the sm_100a kernel or raise.
+cpu_tensors = 'raise'
+
 _LIB_PATH = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'lib', 'libpgpp_sm100a.so')
 _lib = None
 _cached_plugins = dict()

@@ -65,6 +65,8 @@ def bias_act(x, b=None, dim=1, act='linear', alpha=None, gain=None, clamp=None, 
     if impl == 'ref':
         return _bias_act_ref(x=x, b=b, dim=dim, act=act, alpha=alpha, gain=gain, clamp=clamp)
     if x.device.type != 'cuda':
+        if custom_ops.cpu_tensors == 'ref':     # explicit opt-in to the reference's dispatch rule (bias_act.py:87)
+            return _bias_act_ref(x=x, b=b, dim=dim, act=act, alpha=alpha, gain=gain, clamp=clamp)
         raise RuntimeError("bias_act(impl='cuda') needs a CUDA tensor; pass impl='ref' for the PyTorch reference path")
     _init()
     return _bias_act_cuda(dim=dim, act=act, alpha=alpha, gain=gain, clamp=clamp).apply(x, b)

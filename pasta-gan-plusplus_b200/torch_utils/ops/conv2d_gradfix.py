@@ -22,6 +22,8 @@ csrc/conv_wgrad.cu (`pgpp_conv2d_wgrad`); no library convolution is called anywh
 import contextlib
 import ctypes
 import os
+import threading
+import weakref
 
 import torch
 
@@ -180,20 +182,35 @@ def pack_weights(w_taps, o, phases, kh, kw, parts, pad_y, pad_x):
     return pw
 
 
-_weight_cache = dict()
+_weight_cache = dict()      # (id(tensor), tag) -> (weakref(tensor), (data_ptr, _version, ...), None, packed); one entry per (parameter, tag)
+_weight_cache_lock = threading.RLock()     # re-entrant: a weakref callback may fire while the lock is held
 
 
-def _cached(key_tensor, tag, builder):
-    """Cache packed weights per (storage, version, tag); parameters bump `_version` on every optimizer step."""
-    key = (key_tensor.data_ptr(), key_tensor._version, tuple(key_tensor.shape), key_tensor.dtype, tag)
-    hit = _weight_cache.get(key)
-    if hit is None:
-        if len(_weight_cache) > 512:
-            _weight_cache.clear()
-        # keep the key tensor alive with the entry so its address cannot be recycled under the same key
-        hit = (builder(), key_tensor)
-        _weight_cache[key] = hit
-    return hit[0]
+def _cached(key_tensor, tag, builder, also=()):
+    """Packed weights per leaf tensor (Parameter / buffer) and `tag`.  An entry is valid while the SAME tensor object still owns
+    the SAME storage address at the SAME `_version` (optimizer steps bump the version; `module.to()` / `param.data = ...` change
+    the address), so a recycled address or a new version rebuilds and REPLACES the entry - nothing stale is returned and nothing
+    piles up.  Temporaries (anything with a grad_fn, e.g. `self.weight * self.weight_gain` on the autograd path) are never
+    cached: the entry could never hit again and would pin the temporary and its packed copies.
+    `also`: further tensors the packed copy is built from (the second weight of a merged GEMM, the FIR filter)."""
+    if key_tensor.grad_fn is not None or any(t.grad_fn is not None for t in also):
+        return builder()
+    key = (id(key_tensor), tag)
+    stamp = (key_tensor.data_ptr(), key_tensor._version) + tuple(v for t in also for v in (id(t), t.data_ptr(), t._version))
+    with _weight_cache_lock:
+        hit = _weight_cache.get(key)
+    if hit is not None and hit[0]() is key_tensor and hit[1] == stamp:
+        return hit[3]
+    value = builder()
+
+    def _drop(_ref, key=key):
+        with _weight_cache_lock:
+            cur = _weight_cache.get(key)
+            if cur is not None and cur[0] is _ref:
+                del _weight_cache[key]
+    with _weight_cache_lock:
+        _weight_cache[key] = (weakref.ref(key_tensor, _drop), stamp, None, value)
+    return value
 
 
 def im2col_rows(ic, kh, kw):
@@ -267,7 +284,7 @@ def packed_up2(weight, f, flip_weight, flip_filter, parts):
                                 wp[py, px, :, :, a, b] += 4.0 * k[fy, fx] * w[:, :, ky, kx]
         taps = wp.permute(4, 5, 0, 1, 2, 3).reshape(9, 4 * o, ic)     # [tap][phase*o + oc][i]
         return pack_weights(taps, o, 4, 3, 3, parts, 1, 1)
-    return _cached(weight, ('up2', bool(flip_weight), bool(flip_filter), parts, f.data_ptr(), f._version), build)
+    return _cached(weight, ('up2', bool(flip_weight), bool(flip_filter), parts), build, also=(f,))
 
 
 # ------------------------------------------------------------------------------------------------
@@ -340,6 +357,7 @@ def igemm_conv(x, pw, *, scale=None, stride=1, out_hw=None, dcoef=None, noise=No
         d.out_part_stride = out_packed.data[0].numel()
         result = out_packed
     else:
+        want_f64 = out is None and out_dtype is None and src_dtype == torch.float64      # computed in the fp32-parity mode, returned as float64
         if out is None:
             out_dtype = out_dtype or (src_dtype if src_dtype != torch.float64 else torch.float32)
             if memory_format is None:
@@ -407,6 +425,8 @@ def igemm_conv(x, pw, *, scale=None, stride=1, out_hw=None, dcoef=None, noise=No
         trace.append((f'igemm {real_ic}->{pw.o} {kname} {h}x{w}->{out_h}x{out_w} n{n} {precision}', flops, e0, e1))
     else:
         _plugin.conv2d_igemm(d, device)
+    if out_packed is None and want_f64:
+        result = result.to(torch.float64)       # the reference returns the input dtype (conv2d_gradfix.py:112-114)
     return result
 
 

@@ -83,6 +83,8 @@ def upfirdn2d(x, f, up=1, down=1, padding=0, flip_filter=False, gain=1, impl='cu
     if impl == 'ref':
         return _upfirdn2d_ref(x, f, up=up, down=down, padding=padding, flip_filter=flip_filter, gain=gain)
     if x.device.type != 'cuda':
+        if custom_ops.cpu_tensors == 'ref':     # explicit opt-in to the reference's dispatch rule (upfirdn2d.py:162)
+            return _upfirdn2d_ref(x, f, up=up, down=down, padding=padding, flip_filter=flip_filter, gain=gain)
         raise RuntimeError("upfirdn2d(impl='cuda') needs a CUDA tensor; pass impl='ref' for the PyTorch reference path")
     _init()
     return _upfirdn2d_cuda(up=up, down=down, padding=padding, flip_filter=flip_filter, gain=gain).apply(x, f)

@@ -17,13 +17,6 @@ from .synthesis import Conv2dLayer, FullyConnectedLayer
 SQRT_HALF = float(np.sqrt(0.5))
 
 
-def _frozen(layer, trainable):
-    """Freeze-D (networks.py:153-162 registers the tensors as buffers): same state-dict names, no gradients"""
-    if not trainable:
-        layer.requires_grad_(False)
-    return layer
-
-
 class DiscriminatorBlock(torch.nn.Module):
     def __init__(self, in_channels, tmp_channels, out_channels, resolution, img_channels, first_layer_idx, architecture='resnet',
                  activation='lrelu', resample_filter=[1, 3, 3, 1], conv_clamp=None, use_fp16=False, fp16_channels_last=False,
@@ -37,18 +30,19 @@ class DiscriminatorBlock(torch.nn.Module):
         self.register_buffer('resample_filter', upfirdn2d.setup_filter(resample_filter))
         self.num_layers = 0
 
-        def add(name, layer):
+        def add(name, *args, **kwargs):
+            # Freeze-D (networks.py:476-481): the first `freeze_layers` layers hold their tensors as buffers
             trainable = self.first_layer_idx + self.num_layers >= freeze_layers
             self.num_layers += 1
-            setattr(self, name, _frozen(layer, trainable))
+            setattr(self, name, Conv2dLayer(*args, trainable=trainable, **kwargs))
 
         kw = dict(activation=activation, conv_clamp=conv_clamp)
         if in_channels == 0 or architecture == 'skip':
-            add('fromrgb', Conv2dLayer(img_channels, tmp_channels, kernel_size=1, **kw))
-        add('conv0', Conv2dLayer(tmp_channels, tmp_channels, kernel_size=3, **kw))
-        add('conv1', Conv2dLayer(tmp_channels, out_channels, kernel_size=3, down=2, resample_filter=resample_filter, **kw))
+            add('fromrgb', img_channels, tmp_channels, kernel_size=1, **kw)
+        add('conv0', tmp_channels, tmp_channels, kernel_size=3, **kw)
+        add('conv1', tmp_channels, out_channels, kernel_size=3, down=2, resample_filter=resample_filter, **kw)
         if architecture == 'resnet':
-            add('skip', Conv2dLayer(tmp_channels, out_channels, kernel_size=1, bias=False, down=2, resample_filter=resample_filter))
+            add('skip', tmp_channels, out_channels, kernel_size=1, bias=False, down=2, resample_filter=resample_filter)
 
     def forward(self, x, img, force_fp32=False, fused=True, impl='cuda'):
         dtype = torch.float16 if self.use_fp16 and not force_fp32 else torch.float32

@@ -224,7 +224,7 @@ class Spade_Norm_Block(torch.nn.Module):
             o, ic, kh, kw = w.shape
             taps = w.permute(2, 3, 0, 1).reshape(kh * kw, o, ic)
             return conv2d_gradfix.pack_weights(taps, o, 1, kh, kw, S._parts(), self.conv_gamma.padding, self.conv_gamma.padding)
-        return conv2d_gradfix._cached(wg, ('spade_gb', wb.data_ptr(), wb._version, S._parts()), build)
+        return conv2d_gradfix._cached(wg, ('spade_gb', S._parts()), build, also=(wb,))
 
     def fused_packed(self, x, mean, rstd, feats_packed, pre_gain):
         """operand-format result of pre_act(IN(x) * (1 + gamma) + beta) for the consuming conv: conv_mlp (+ReLU in its epilogue)
@@ -330,9 +330,12 @@ class SynthesisBlockFull(torch.nn.Module):
         if spade:
             self.spade_b512 = Spade_ResBlockV4_512(out_channels, out_channels, spade_channels=1)
 
-    def forward(self, x, img, ws, pose_feature, cat_feat, parsing=None, fused=True, impl='cuda', export_tensor=False, **layer_kwargs):
+    def forward(self, x, img, ws, pose_feature, cat_feat, parsing=None, fused=True, impl='cuda', export_tensor=False, force_fp32=True,
+                **layer_kwargs):
         """x: tensor or PackedAct.  Returns (x, img, pred_parsing); x is a PackedAct when the block ran in operand-format
-        hand-over mode and `export_tensor` is False (a consumer outside the conv chain needs the fp32 tensor)."""
+        hand-over mode and `export_tensor` is False (a consumer outside the conv chain needs the fp32 tensor).
+        `force_fp32` is accepted for call compatibility (networks.py:2147): the generator blocks always run in float32
+        (`use_fp16=False`, networks.py:2223)."""
         w_iter = iter(ws.unbind(dim=1))
         has_spade = hasattr(self, 'spade_b512')
         want_tensor = export_tensor or has_spade
@@ -514,7 +517,11 @@ class GraphedGenerator:
         self.G = G
         self.static_in = {k: v.clone() for k, v in example_inputs.items()}
         self.static_gt = None if gt_parsing is None else gt_parsing.clone()
-        self.kwargs = dict(noise_mode='const', **forward_kwargs)
+        assert forward_kwargs.get('noise_mode', 'const') != 'random', "noise_mode='random' draws inside the forward: not capturable"
+        self.kwargs = dict(noise_mode='const', **{k: v for k, v in forward_kwargs.items() if k != 'noise_mode'})
+        self.kwargs['noise_mode'] = forward_kwargs.get('noise_mode', 'const')
+        # the captured launches read the packed weight copies made now: remember which parameter versions those were
+        self._versions = [(p, p._version, p.data_ptr()) for p in G.parameters()]
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side), torch.no_grad():
@@ -531,9 +538,21 @@ class GraphedGenerator:
         return self.G(z, x['c'], x['retain'], x['pose'], x['denorm_upper'], x['denorm_lower'], x['denorm_upper_mask'],
                       x['denorm_lower_mask'], gt_parsing=self.static_gt, **self.kwargs)
 
-    def __call__(self, inputs):
+    def __call__(self, inputs, gt_parsing=None):
+        """inputs: dict with exactly the keys of the example batch; gt_parsing: required iff the graph was captured with one (it is
+        a static input like the others, refreshed on every call)."""
+        unknown, missing = set(inputs) - set(self.static_in), set(self.static_in) - set(inputs)
+        if unknown or missing:
+            raise KeyError(f'GraphedGenerator inputs: unknown keys {sorted(unknown)}, missing keys {sorted(missing)}')
+        if (gt_parsing is None) != (self.static_gt is None):
+            raise ValueError('GraphedGenerator was captured ' + ('without' if self.static_gt is None else 'with') +
+                             ' gt_parsing; the call must match (capture a second graph for the other mode)')
+        if any(p._version != v or p.data_ptr() != ptr for p, v, ptr in self._versions):
+            raise RuntimeError('generator weights changed after the graph was captured (the captured launches read the packed copies '
+                               'of the old weights): build a new GraphedGenerator')
         for k, v in inputs.items():
-            if k in self.static_in:
-                self.static_in[k].copy_(v, non_blocking=True)
+            self.static_in[k].copy_(v, non_blocking=True)
+        if gt_parsing is not None:
+            self.static_gt.copy_(gt_parsing, non_blocking=True)
         self.graph.replay()
         return self.static_out

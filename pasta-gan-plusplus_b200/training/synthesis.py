@@ -51,12 +51,23 @@ def _parts():
     return conv2d_gradfix._PRODUCTS[conv2d_gradfix.fp32_precision][1]
 
 
+def _register(module, name, value, trainable):
+    """frozen layers keep their tensors as BUFFERS (networks.py:153-162): same state-dict names, but absent from `parameters()`, so
+    neither `module.requires_grad_(True)` at the start of a phase nor the optimiser or DDP ever touches them"""
+    if value is None:
+        setattr(module, name, None)
+    elif trainable:
+        setattr(module, name, torch.nn.Parameter(value))
+    else:
+        module.register_buffer(name, value)
+
+
 class FullyConnectedLayer(torch.nn.Module):
-    def __init__(self, in_features, out_features, bias=True, activation='linear', lr_multiplier=1, bias_init=0):
+    def __init__(self, in_features, out_features, bias=True, activation='linear', lr_multiplier=1, bias_init=0, trainable=True):
         super().__init__()
         self.activation = activation
-        self.weight = torch.nn.Parameter(torch.randn([out_features, in_features]) / lr_multiplier)
-        self.bias = torch.nn.Parameter(torch.full([out_features], np.float32(bias_init))) if bias else None
+        _register(self, 'weight', torch.randn([out_features, in_features]) / lr_multiplier, trainable)
+        _register(self, 'bias', torch.full([out_features], np.float32(bias_init)) if bias else None, trainable)
         self.weight_gain = lr_multiplier / np.sqrt(in_features)
         self.bias_gain = lr_multiplier
 
@@ -74,7 +85,7 @@ class FullyConnectedLayer(torch.nn.Module):
 
 class Conv2dLayer(torch.nn.Module):
     def __init__(self, in_channels, out_channels, kernel_size, bias=True, activation='linear', up=1, down=1,
-                 resample_filter=[1, 3, 3, 1], conv_clamp=None):
+                 resample_filter=[1, 3, 3, 1], conv_clamp=None, channels_last=False, trainable=True):
         super().__init__()
         self.activation = activation
         self.up, self.down = up, down
@@ -83,8 +94,8 @@ class Conv2dLayer(torch.nn.Module):
         self.padding = kernel_size // 2
         self.weight_gain = 1 / np.sqrt(in_channels * (kernel_size ** 2))
         self.act_gain = bias_act.activation_funcs[activation].def_gain
-        self.weight = torch.nn.Parameter(torch.randn([out_channels, in_channels, kernel_size, kernel_size]))
-        self.bias = torch.nn.Parameter(torch.zeros([out_channels])) if bias else None
+        _register(self, 'weight', torch.randn([out_channels, in_channels, kernel_size, kernel_size]), trainable)
+        _register(self, 'bias', torch.zeros([out_channels]) if bias else None, trainable)
 
     def forward(self, x, gain=1, fused=True, impl='cuda', out_packed=None, out=None, accumulate=False):
         """`out_packed=`: write the operand format of the next convolution instead of an NCHW tensor; `out=` / `accumulate=`: write

@@ -57,8 +57,14 @@ def _step(D, img, c):
 
 def test_freeze_d_and_minibatch_std():
     D = disc.Discriminator(c_dim=0, img_resolution=16, img_channels=3, channel_base=128, channel_max=16, block_kwargs=dict(freeze_layers=2))
-    frozen = [n for n, p in D.named_parameters() if not p.requires_grad]
-    assert frozen and all(n.startswith('b16.fromrgb') or n.startswith('b16.conv0') for n in frozen)
+    # frozen layers keep their tensors as buffers (networks.py:153-162): same state-dict names, not in parameters(), so the
+    # training loop's `module.requires_grad_(True)` (training_loop_fullbody.py:613) cannot un-freeze them
+    names = {n for n, _ in D.named_parameters()}
+    frozen = [n for n, _ in D.named_buffers() if n.endswith('.weight') or n.endswith('.bias')]
+    assert sorted(frozen) == ['b16.conv0.bias', 'b16.conv0.weight', 'b16.fromrgb.bias', 'b16.fromrgb.weight'] and not names & set(frozen)
+    assert all(k in D.state_dict() for k in frozen)
+    D.requires_grad_(True)
+    assert not any(getattr(D.b16.conv0, k).requires_grad for k in ('weight', 'bias'))
     x = torch.randn(8, 4, 4, 4)
     y = disc.MinibatchStdLayer(group_size=4)(x)
     assert y.shape == (8, 5, 4, 4) and torch.equal(y[:, :4], x)

@@ -44,6 +44,11 @@ def test_oracle_generator_matches_reference_golden():
                 tol = 1e-3 if (tag == 'pred' and name == 'finetune') else 2e-5
                 assert err < tol, (tag, name, err)
             if tag == 'gt':
+                # un-pooled samples of the real reference's outputs over the whole image (generator_fullres.npz)
+                gf = np.load(os.path.join(os.path.dirname(GOLDEN), 'generator_fullres.npz'))
+                for t, key, step in ((img, 'gt_img_s3', 3), (fin, 'gt_finetune_s3', 3), (pred, 'gt_parsing_s5', 5)):
+                    want = torch.from_numpy(gf[key])
+                    assert float((t[:, :, ::step, ::step] - want).norm() / want.norm()) < 2e-5, key
                 np.testing.assert_allclose(img[:, :, 200:232, 240:272].numpy(), g[f'{tag}_img_crop'], rtol=2e-3, atol=2e-4)
                 np.testing.assert_allclose(fin[:, :, 200:232, 240:272].numpy(), g[f'{tag}_finetune_crop'], rtol=2e-3, atol=5e-4)
 

@@ -78,10 +78,14 @@ def test_modulated_conv2d_differentiable_path_matches_golden_and_has_grads():
     assert rel_l2(x.grad, xc.grad) < 1e-5 and rel_l2(w.grad, wc.grad) < 1e-4 and rel_l2(s.grad, sc.grad) < 1e-4
 
 
+FP32_MODES = ['bf16x2', 'bf16x3']       # bf16x2 is the mode bench.py runs; both must hold the per-layer bar
+
+
+@pytest.mark.parametrize('prec', FP32_MODES)
 @pytest.mark.parametrize('case', CONV_CASES, ids=[c[0] for c in CONV_CASES])
-def test_conv2d_resample_golden(case):
+def test_conv2d_resample_golden(case, prec):
     name, xs, ws, up, down, pad, groups, flipw, usef = case
-    cg.fp32_precision = 'bf16x3'
+    cg.fp32_precision = prec
     g = np.load(os.path.join(GOLDEN, 'conv2d_resample.npz'))
     x, w, f = t(g[f'{name}_x']).to(DEV), t(g[f'{name}_w']).to(DEV), t(g['f']).to(DEV)
     kw = dict(f=(f if usef else None), up=up, down=down, padding=pad, groups=groups, flip_weight=flipw)
@@ -94,8 +98,8 @@ def test_conv2d_resample_golden(case):
         with torch.no_grad():
             y = cr.conv2d_resample(x, w, **kw)
         yg = cr.conv2d_resample(x.clone().requires_grad_(True), w, **kw)       # decomposed (differentiable) route
-        assert rel_l2(yg, t(g[f'{name}_y'])) < TOL['bf16x3']
-    assert rel_l2(y, t(g[f'{name}_y'])) < TOL['bf16x3'], rel_l2(y, t(g[f'{name}_y']))
+        assert rel_l2(yg, t(g[f'{name}_y'])) < TOL[prec]
+    assert rel_l2(y, t(g[f'{name}_y'])) < TOL[prec], rel_l2(y, t(g[f'{name}_y']))
 
 
 SHAPES = [  # n, ic, oc, k, h, w, stride, pad
@@ -105,10 +109,11 @@ SHAPES = [  # n, ic, oc, k, h, w, stride, pad
 ]
 
 
+@pytest.mark.parametrize('prec', FP32_MODES)
 @pytest.mark.parametrize('shape', SHAPES, ids=[str(s) for s in SHAPES])
-def test_conv2d_vs_oracle(shape):
+def test_conv2d_vs_oracle(shape, prec):
     n, ic, oc, k, h, w, stride, pad = shape
-    cg.fp32_precision = 'bf16x3'
+    cg.fp32_precision = prec
     g = torch.Generator().manual_seed(31)
     x = torch.randn(n, ic, h, w, generator=g)
     wt = torch.randn(oc, ic, k, k, generator=g)
@@ -116,26 +121,28 @@ def test_conv2d_vs_oracle(shape):
     want = ref_ops.conv2d(x.double(), wt.double(), stride=stride, padding=pad) + b.double().reshape(1, -1, 1, 1)
     with torch.no_grad():
         got = cg.conv2d(x.to(DEV), wt.to(DEV), b.to(DEV), stride=stride, padding=pad)
-    assert tuple(got.shape) == tuple(want.shape) and rel_l2(got, want) < TOL['bf16x3'], rel_l2(got, want)
+    assert tuple(got.shape) == tuple(want.shape) and rel_l2(got, want) < TOL[prec], rel_l2(got, want)
 
 
+@pytest.mark.parametrize('prec', FP32_MODES)
 @pytest.mark.parametrize('stride,pad,opad', [(1, 0, 0), (1, 1, 0), (2, 0, 0), (2, 1, 1), (2, 1, 0)])
-def test_conv_transpose2d_vs_oracle(stride, pad, opad):
-    cg.fp32_precision = 'bf16x3'
+def test_conv_transpose2d_vs_oracle(stride, pad, opad, prec):
+    cg.fp32_precision = prec
     g = torch.Generator().manual_seed(32)
     x = torch.randn(2, 24, 9, 11, generator=g)
     wt = torch.randn(24, 20, 3, 3, generator=g)
     want = ref_ops.conv_transpose2d(x.double(), wt.double(), stride=stride, padding=pad, output_padding=opad)
     with torch.no_grad():
         got = cg.conv_transpose2d(x.to(DEV), wt.to(DEV), stride=stride, padding=pad, output_padding=opad)
-    assert tuple(got.shape) == tuple(want.shape) and rel_l2(got, want) < TOL['bf16x3'], rel_l2(got, want)
+    assert tuple(got.shape) == tuple(want.shape) and rel_l2(got, want) < TOL[prec], rel_l2(got, want)
 
 
+@pytest.mark.parametrize('prec', FP32_MODES)
 @pytest.mark.parametrize('stride', [1, 2])
-def test_gradients_and_r1_double_backward(stride):
+def test_gradients_and_r1_double_backward(stride, prec):
     """first-order grads and the R1 pattern (grad of grad-norm w.r.t. weights, loss_fullbody.py:264-274)
     against float64 autograd of the library convolution on the CPU"""
-    cg.fp32_precision = 'bf16x3'
+    cg.fp32_precision = prec
     g = torch.Generator().manual_seed(33)
     x0 = torch.randn(2, 16, 12, 12, generator=g)
     w0 = torch.randn(24, 16, 3, 3, generator=g) * 0.2
@@ -153,7 +160,7 @@ def test_gradients_and_r1_double_backward(stride):
     xg, wg, bg = (v.to(DEV).requires_grad_(True) for v in (x0, w0, b0))
     got = run(cg.conv2d, xg, wg, bg)
     for a, r, name in zip(got, ref, ('y', 'grad_x', 'grad_w(double backward)', 'grad_b')):
-        assert rel_l2(a, r) < 5e-5, (name, rel_l2(a, r))
+        assert rel_l2(a, r) < 1.25 * TOL[prec], (name, rel_l2(a, r))        # two chained convolutions per gradient
     # no_weight_gradients(): weight grads are skipped, data grads still flow (conv2d_gradfix.py:23-31,130)
     xg2, wg2 = x0.to(DEV).requires_grad_(True), w0.to(DEV).requires_grad_(True)
     with cg.no_weight_gradients():
@@ -219,11 +226,12 @@ def test_full_size_layers_against_library_conv_and_linearity():
         torch.backends.cudnn.allow_tf32 = old
 
 
+@pytest.mark.parametrize('prec', FP32_MODES)
 @pytest.mark.parametrize('ic,k,pad,h,w', [(3, 7, 3, 40, 24), (1, 3, 1, 33, 47), (6, 3, 1, 16, 64), (3, 7, 3, 128, 128)])
-def test_few_channel_convs_through_row_group_im2col(ic, k, pad, h, w):
+def test_few_channel_convs_through_row_group_im2col(ic, k, pad, h, w, prec):
     """7x7 RGB stem and 3x3 convs on 1..6 channels: pgpp_pack_im2col + dilated kh' x 1 GEMM (Conv2dLayer fused route)"""
     synthesis = importlib.import_module('pgpp_b200.training.synthesis')
-    cg.fp32_precision = 'bf16x3'
+    cg.fp32_precision = prec
     torch.manual_seed(0)
     layer = synthesis.Conv2dLayer(ic, 64, kernel_size=k, activation='relu').to(DEV)
     layer.bias.data.normal_()
@@ -236,7 +244,7 @@ def test_few_channel_convs_through_row_group_im2col(ic, k, pad, h, w):
     assert custom_ops.launch_count() - before == (1 if ic * k * k <= 16 else 2)
     wgt = layer.weight.detach().cpu().double() * layer.weight_gain
     want = ref_ops.bias_act(ref_ops.conv2d(x.cpu().double(), wgt, padding=pad), layer.bias.detach().cpu().double(), act='relu')
-    assert rel_l2(got, want) < TOL['bf16x3'], rel_l2(got, want)
+    assert rel_l2(got, want) < TOL[prec], rel_l2(got, want)
 
 
 @pytest.mark.parametrize('ic,oc,k,h,w', [(1, 64, 3, 64, 128), (5, 64, 1, 40, 56), (1, 128, 3, 17, 23), (4, 72, 1, 9, 130), (2, 64, 1, 4, 4),

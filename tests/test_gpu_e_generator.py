@@ -63,6 +63,36 @@ def test_fused_generator_matches_reference_golden(generator_and_inputs, prec, to
         assert np.abs(crop - g['gt_finetune_crop']).max() <= 1e-3 * max(1.0, stats[2])
 
 
+FULLRES = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'generator_fullres.npz')
+# end-to-end bars at FULL resolution (no pooling): north star max-abs <= 1e-3 of the output scale; rel-L2 of the whole image
+FULL_TOL = {'bf16x2': 1.2e-4, 'bf16x3': 6e-5}
+
+
+@pytest.mark.parametrize('prec', ['bf16x2', 'bf16x3'])
+def test_fused_generator_full_resolution_against_reference_samples(generator_and_inputs, prec):
+    """un-pooled comparison with the REAL reference's outputs (oracle/make_golden_generator.py -> generator_fullres.npz): every 3rd
+    (parsing: 5th) pixel of all three outputs, per-pixel"""
+    G, inp = generator_and_inputs
+    g = np.load(FULLRES)
+    old = cg.fp32_precision
+    cg.fp32_precision = prec
+    try:
+        img, fin, pred = _run(G, inp)
+    finally:
+        cg.fp32_precision = old
+    report = {}
+    for name, t, key, step in (('img', img, 'gt_img_s3', 3), ('finetune', fin, 'gt_finetune_s3', 3), ('parsing', pred, 'gt_parsing_s5', 5)):
+        want = torch.from_numpy(g[key]).double()
+        got = t[:, :, ::step, ::step].cpu().double()
+        rel = float((got - want).norm() / want.norm())
+        mx = float((got - want).abs().max())
+        scale = float(want.abs().max())
+        report[name] = (rel, mx / scale)
+        assert mx <= 1e-3 * max(1.0, scale), (prec, name, mx, scale)
+        assert rel <= FULL_TOL[prec], (prec, name, rel)
+    print(f'full-resolution parity {prec}: ' + ', '.join(f'{k} rel-L2 {v[0]:.2e} max-abs/scale {v[1]:.2e}' for k, v in report.items()))
+
+
 def test_composition_route_on_gpu_and_batch_independence(generator_and_inputs):
     """drop-in composition (modulated_conv2d + bias_act + conv2d_resample calls) equals the fused route; samples are independent"""
     G, inp = generator_and_inputs
@@ -88,6 +118,25 @@ def test_cuda_graph_replay_is_bit_identical(generator_and_inputs):
     torch.cuda.synchronize()
     for a, b in zip(out, eager):
         assert torch.equal(a, b)
+
+
+def test_cuda_graph_gt_parsing_is_a_refreshed_static_input_and_bad_calls_raise(generator_and_inputs):
+    G, inp = generator_and_inputs
+    x = {k: v for k, v in inp.items() if k != 'gt_parsing'}
+    gt_a = inp['gt_parsing']
+    gt_b = (gt_a + 1) % 7
+    gg = gen.GraphedGenerator(G, x, gt_parsing=gt_a)
+    out_b = [t.clone() for t in gg(x, gt_parsing=gt_b)]
+    torch.cuda.synchronize()
+    want_b = _run(G, dict(x, gt_parsing=gt_b))
+    for a, b in zip(out_b, want_b):
+        assert torch.equal(a, b)                       # the new parsing map was used, not the one baked in at capture
+    with pytest.raises(ValueError):
+        gg(x)                                          # captured with gt_parsing: must be supplied
+    with pytest.raises(KeyError):
+        gg(dict(x, extra=x['c']))
+    with pytest.raises(KeyError):
+        gg({k: v for k, v in x.items() if k != 'pose'})
 
 
 @pytest.mark.parametrize('down', [1, 2])
