@@ -99,10 +99,44 @@ PGPP_API int pgpp_pack_activations(const void* x, const int64_t size[4], const i
 PGPP_API int pgpp_pack_activations_slice(const void* x, const int64_t size[4], const int64_t stride[4], int dtype,
                           const float* scale, void* out, int c_pad, int c_total, int c_off, int parts, void* stream);
 
+/* Same as pgpp_pack_activations_slice with ONE part of IEEE half instead of bfloat16 parts (operand_f16 of the conv descriptors). */
+PGPP_API int pgpp_pack_activations_f16(const void* x, const int64_t size[4], const int64_t stride[4], int dtype,
+                          const float* scale, void* out, int c_pad, int c_total, int c_off, void* stream);
+
 /* Per-sample modulated weights: out[n][p][row][c] = part p of bf16-split(master[row][c] * s[n][c]) for c < c_in,
  * zero for c_in <= c < c_pad (training/networks.py:65-66, w * styles).  master float32 [rows][c_pad], s float32 [N][c_in]. */
 PGPP_API int pgpp_modulate_weights(const float* master, const float* s, void* out, int n, int64_t rows, int c_pad, int c_in,
                           int parts, void* stream);
+
+/* Weight operand packing, one launch (replaces the eager packing the round-1 Python shim did with library ops; there is no
+ * reference counterpart: cuDNN consumes [O, I, kh, kw] directly at conv2d_gradfix.py:112-114):
+ *   out[part][tap][o_off + row][c]  = split part `part` of  scale * W'[row, c, tap]      (zero for row / c beyond the tensor)
+ *   master[tap][o_off + row][c]     = the same value in float32 (optional; start of the per-sample route, pgpp_modulate_weights)
+ * w: [O, I, kh, kw] with element strides w_stride (any float dtype), or [I, O, kh, kw] with transpose_io != 0 (the
+ * conv_transpose2d layout).  flip != 0 uses the spatially flipped kernel (true convolution; F.conv2d correlates).
+ * phases == 1: taps = kh*kw, rows = O.  phases == 4: the StyleGAN2 up=2 layer (conv2d_resample.py:125-139) as ONE 3x3 stencil per
+ * output phase (py, px): taps = 9, rows = 4 * phase_stride (row = phase * phase_stride + o),
+ *   W'[phase][o, i, a, b] = 4 * sum_{fy,ky: py+fy-1-ky = 2(a-1)} sum_{fx,kx: px+fx-1-kx = 2(b-1)} k[fy,fx] * w_f[o, i, ky, kx]
+ * with k the 4x4 FIR `fir` (device, float32, row-major; flipped unless flip_filter, upfirdn2d.py:193-196) and w_f the flipped /
+ * unflipped kernel.  operand_f16 != 0 writes IEEE half instead of bfloat16 (parts must be 1): the fp16 layers of the
+ * discriminator (networks.py:634,647) run native f16 MMAs.  The destination has o_rows rows per tap; rows outside
+ * [o_off, o_off + rows) are left untouched (zero them once, or pack several tensors side by side: gamma | beta). */
+PGPP_API int pgpp_pack_weights(const void* w, int w_dtype, const int64_t w_size[4], const int64_t w_stride[4], int transpose_io, int flip,
+                      float scale, int phases, int phase_stride, const float* fir, int flip_filter,
+                      void* out, float* master, int parts, int operand_f16, int o_rows, int o_off, int c_pad, void* stream);
+
+/* Adjoint of the polyphase construction above: grad_weight[o, i, ky, kx] (float32 [O, I, 3, 3], storage order of the layer's
+ * weight) from grad_polyphase float32 [4][O][I][3][3].  Used by the differentiable fused up=2 layer. */
+PGPP_API int pgpp_up2_weight_adjoint(const float* grad_polyphase, const float* fir, int flip_filter, int flip, int o, int ic,
+                            float* grad_weight, void* stream);
+
+/* Plane reductions of the differentiable fused modulated convolution (networks.py:73-82 differentiated by hand), float32 NCHW:
+ *   r[n,c]        = sum_hw a[n,c,hw] * (b[n,c,hw] - sub[n * sub_stride_n + hw])      (b NULL: 1; sub NULL: 0; r NULL: skipped)
+ *   out_scaled[n,c,hw] = a[n,c,hw] * scale[n,c]                                      (out_scaled NULL: skipped; may alias a)
+ * (a, b, sub) = (grad_y, y, noise): gradient of the demodulation coefficients (times dcoef);
+ * (a, b, scale) = (grad of the modulated input, x, styles): style gradient and grad_x in one pass. */
+PGPP_API int pgpp_mul_reduce_hw(const float* a, const float* b, const float* sub, int64_t sub_stride_n, const float* scale,
+                       float* out_scaled, float* r, int n, int c, int64_t hw, void* stream);
 
 /* Row-group im2col packing for convolutions with very few input channels (the 7x7 RGB stem, 3x3 convs on 1..6 channels):
  *     out[part][n][yy][x][(ry*kw + kx)*C + c] = split(x[n, c, yy - pad_y + ry, x + kx - pad_x] * scale[n,c])   (0 outside)
@@ -170,6 +204,8 @@ typedef struct {
     const float* spade_mean;
     const float* spade_rstd;
     float spade_pre_gain;
+    int32_t operand_f16;            /* nonzero: act and wgt hold IEEE half (one part each, products == 1) instead of bfloat16 parts:
+                                       the fp16 blocks of the discriminator (networks.py:634,647) on native f16 tensor-core MMAs */
 } pgpp_conv_desc;
 
 /* Implicit-GEMM convolution on the 5th-gen tensor cores (tcgen05.mma, TMEM accumulators, TMA operand
@@ -221,6 +257,7 @@ typedef struct pgpp_wgrad_desc {
     int32_t products;               /* 1 (bf16), 3 (2-part split) or 6 (3-part split) */
     float* out;                     /* G: float32 [ca][cb][kh][kw], overwritten */
     float* workspace;               /* float32 [kh*kw][ca][cb_pad] scratch (split-K partial sums land here), 16-byte aligned */
+    int32_t operand_f16;            /* nonzero: S and L hold IEEE half (one part, products == 1) instead of bfloat16 parts */
 } pgpp_wgrad_desc;
 
 /* Split-K GEMM over the pixels on the 5th-gen tensor cores (tcgen05.mma, TMEM accumulators, TMA operand loads). */

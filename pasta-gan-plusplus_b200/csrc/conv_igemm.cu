@@ -919,7 +919,10 @@ extern "C" int pgpp_conv2d_igemm(const pgpp_conv_desc* d, void* stream) {
     p.layout_type = row_bytes == 128 ? 2u : (row_bytes == 64 ? 4u : 6u);   // SWIZZLE_128B / 64B / 32B
     p.sbo_bytes = 8 * row_bytes;
     // instruction descriptor (cute/arch/mma_sm100_desc.hpp InstrDescriptor): fp32 accum, bf16 A/B, K-major, M = 128
-    p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((unsigned)(d->block_n >> 3) << 17) | ((unsigned)(kTileM >> 4) << 24);
+    // a_format / b_format (bits 7-9 / 10-12): 1 = bf16, 0 = f16 (the fp16 layers of the discriminator run native f16 MMAs)
+    const unsigned ab_fmt = d->operand_f16 ? 0u : ((1u << 7) | (1u << 10));
+    PGPP_REQUIRE(!d->operand_f16 || d->products == 1, "fp16 operands are a single part (products must be 1)");
+    p.idesc = (1u << 4) | ab_fmt | ((unsigned)(d->block_n >> 3) << 17) | ((unsigned)(kTileM >> 4) << 24);
     unsigned cols = (unsigned)pow2_ceil(2 * d->block_n); if (cols < 32) cols = 32;
     p.tmem_cols = cols;
     // shared-memory plan (227 KB per CTA): weights resident if every tile of a column tile fits beside a 2-deep
@@ -970,7 +973,7 @@ extern "C" int pgpp_conv2d_igemm(const pgpp_conv_desc* d, void* stream) {
     p.stack = (need_parts == 2 && d->block_n == 64 && p.b_resident && p.kb == 64 && (p.inner == 3 || p.inner == 1 || p.reuse == 2) && p.tn == 1 && p.fold_gain &&
                !d->spade_x && !getenv("PGPP_IGEMM_NO_STACK")) ? 1 : 0;
     p.acc_cols = p.stack ? 2 * d->block_n : d->block_n;
-    p.idesc_stack = (1u << 4) | (1u << 7) | (1u << 10) | ((unsigned)((2 * d->block_n) >> 3) << 17) | ((unsigned)(kTileM >> 4) << 24);
+    p.idesc_stack = (1u << 4) | ab_fmt | ((unsigned)((2 * d->block_n) >> 3) << 17) | ((unsigned)(kTileM >> 4) << 24);
     if (p.stack) p.tmem_cols = 256;
     auto magic = [](unsigned dv, unsigned& m, unsigned& sft) {
         sft = 0; while ((1ull << sft) < dv) sft++;

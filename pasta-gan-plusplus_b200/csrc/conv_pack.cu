@@ -12,9 +12,11 @@ struct PackArgs {
     int c_total, c_off;         // destination pixel stride and first channel
     long long s_n, s_c, s_h, s_w;
     long long part_stride;      // elements between parts = n*h*w*c_pad
+    int f16;                    // 1: the operand is IEEE half (one part) instead of the bf16 expansion (fp16 layers, native f16 MMA)
 };
 
-__device__ __forceinline__ void split_store(float v, __nv_bfloat16* dst, long long part_stride, int parts) {
+__device__ __forceinline__ void split_store(float v, __nv_bfloat16* dst, long long part_stride, int parts, int f16 = 0) {
+    if (f16) { *reinterpret_cast<__half*>(dst) = __float2half_rn(v); return; }
     // part p = bf16(v - sum of earlier parts): 8, 16, 24 significand bits for 1, 2, 3 parts
     #pragma unroll 3
     for (int p = 0; p < parts; p++) {
@@ -33,7 +35,13 @@ __device__ __forceinline__ void split_store(float v, __nv_bfloat16* dst, long lo
 // threads write the 128-byte channel row of a pixel with one 128-bit store each.
 struct TileGeom { int log_tw, x_tiles, y_tiles, c_tiles; };
 
-__device__ __forceinline__ uint4 split_packet(float (&v)[8][4], int k) {
+__device__ __forceinline__ uint4 split_packet(float (&v)[8][4], int k, int f16 = 0) {
+    if (f16) {
+        __align__(16) __half hq[8];
+        #pragma unroll
+        for (int j = 0; j < 8; j++) hq[j] = __float2half_rn(v[j][k]);
+        return *reinterpret_cast<const uint4*>(hq);
+    }
     __align__(16) __nv_bfloat16 q[8];
     #pragma unroll
     for (int j = 0; j < 8; j++) { q[j] = __float2bfloat16_rn(v[j][k]); v[j][k] -= __bfloat162float(q[j]); }
@@ -42,12 +50,13 @@ __device__ __forceinline__ uint4 split_packet(float (&v)[8][4], int k) {
 
 // writes the tile held in v (see above) to out[part][n][y][x][c_off + c0 ...]; sm = parts * 128 * 8 packets
 __device__ __forceinline__ void emit_tile(float (&v)[8][4], uint4* sm, int parts, __nv_bfloat16* out, long long part_stride,
-                                          int n, int h, int w, int y0, int x0, int log_tw, int c0, int c_lim, int c_total, int c_off) {
+                                          int n, int h, int w, int y0, int x0, int log_tw, int c0, int c_lim, int c_total, int c_off,
+                                          int f16 = 0) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int part = 0; part < parts; part++) {
         #pragma unroll
         for (int k = 0; k < 4; k++)
-            sm[(part * 128 + 4 * lane + k) * 8 + (warp ^ (lane & 7))] = split_packet(v, k);
+            sm[(part * 128 + 4 * lane + k) * 8 + (warp ^ (lane & 7))] = split_packet(v, k, f16);
     }
     __syncthreads();
     const int tw_mask = (1 << log_tw) - 1;
@@ -121,7 +130,7 @@ __global__ void __launch_bounds__(256) pack_nchw_kernel(PackArgs p, TileGeom g) 
             }
         }
     }
-    emit_tile(v, sm_packets, p.parts, p.out, p.part_stride, n, p.h, p.w, y0, x0, g.log_tw, c0, p.c_pad, p.c_total, p.c_off);
+    emit_tile(v, sm_packets, p.parts, p.out, p.part_stride, n, p.h, p.w, y0, x0, g.log_tw, c0, p.c_pad, p.c_total, p.c_off, p.f16);
 }
 
 // any strides (channels_last inputs are coalesced here): one thread per (pixel, channel)
@@ -138,7 +147,7 @@ __global__ void __launch_bounds__(256) pack_generic_kernel(PackArgs p, long long
             v = (float)to_acc<T>(((const T*)p.x)[n * p.s_n + c * p.s_c + y * p.s_h + x * p.s_w]);
             if (p.scale) v *= p.scale[n * p.c + c];
         }
-        split_store(v, p.out + (e / p.c_pad) * p.c_total + p.c_off + c, p.part_stride, p.parts);
+        split_store(v, p.out + (e / p.c_pad) * p.c_total + p.c_off + c, p.part_stride, p.parts, p.f16);
     }
 }
 
@@ -591,9 +600,21 @@ extern "C" int pgpp_modulate_weights(const float* master, const float* s, void* 
     return PGPP_OK;
 }
 
+namespace pgpp { static int pack_slice(const void* x, const int64_t size[4], const int64_t stride[4], int dtype, const float* scale, void* out,
+                                       int c_pad, int c_total, int c_off, int parts, int f16, void* stream); }
+
 extern "C" int pgpp_pack_activations_slice(const void* x, const int64_t size[4], const int64_t stride[4], int dtype,
                                            const float* scale, void* out, int c_pad, int c_total, int c_off, int parts, void* stream) {
-    using namespace pgpp;
+    return pgpp::pack_slice(x, size, stride, dtype, scale, out, c_pad, c_total, c_off, parts, 0, stream);
+}
+
+extern "C" int pgpp_pack_activations_f16(const void* x, const int64_t size[4], const int64_t stride[4], int dtype,
+                                         const float* scale, void* out, int c_pad, int c_total, int c_off, void* stream) {
+    return pgpp::pack_slice(x, size, stride, dtype, scale, out, c_pad, c_total, c_off, 1, 1, stream);
+}
+
+int pgpp::pack_slice(const void* x, const int64_t size[4], const int64_t stride[4], int dtype, const float* scale, void* out,
+                     int c_pad, int c_total, int c_off, int parts, int f16, void* stream) {
     PGPP_REQUIRE(x && out, "x and out must be device pointers");
     PGPP_REQUIRE(parts >= 1 && parts <= 3, "parts must be 1, 2 or 3");
     PGPP_REQUIRE(c_pad >= size[1] && c_pad % 16 == 0, "c_pad must be a multiple of 16 and >= C");
@@ -602,7 +623,7 @@ extern "C" int pgpp_pack_activations_slice(const void* x, const int64_t size[4],
     p.c_total = c_total; p.c_off = c_off;
     p.x = x; p.scale = scale; p.out = (__nv_bfloat16*)out;
     p.n = (int)size[0]; p.c = (int)size[1]; p.h = (int)size[2]; p.w = (int)size[3];
-    p.c_pad = c_pad; p.parts = parts;
+    p.c_pad = c_pad; p.parts = parts; p.f16 = f16;
     p.s_n = stride[0]; p.s_c = stride[1]; p.s_h = stride[2]; p.s_w = stride[3];
     p.part_stride = (long long)p.n * p.h * p.w * c_total;
     if (p.part_stride == 0) return PGPP_OK;

@@ -380,7 +380,10 @@ extern "C" int pgpp_conv2d_wgrad(const pgpp_wgrad_desc* d, void* stream) {
     p.a_stage_bytes = (unsigned)parts * p.a_part_bytes;
     p.b_bytes = (unsigned)p.b_chunks * p.b_chunk_bytes;
     // instruction descriptor: fp32 accumulate, bf16 A / B, both MN-major (bits 15, 16), N = block_n, M = 128
-    p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((unsigned)(bn >> 3) << 17) | ((unsigned)(128 >> 4) << 24);
+    // a_format / b_format: 1 = bf16, 0 = f16 (fp16 layers); both operands MN-major (bits 15 / 16)
+    const unsigned ab_fmt = d->operand_f16 ? 0u : ((1u << 7) | (1u << 10));
+    PGPP_REQUIRE(!d->operand_f16 || d->products == 1, "fp16 operands are a single part (products must be 1)");
+    p.idesc = (1u << 4) | ab_fmt | (1u << 15) | (1u << 16) | ((unsigned)(bn >> 3) << 17) | ((unsigned)(128 >> 4) << 24);
     unsigned cols = (unsigned)pow2_ceil(p.t_group * bn); if (cols < 32) cols = 32;
     PGPP_REQUIRE(cols <= 512, "internal: tap group does not fit TMEM");
     p.tmem_cols = cols;

@@ -47,6 +47,7 @@ class ConvDesc(ctypes.Structure):
         ('out_stride', ctypes.c_int64 * 4),
         ('accumulate', ctypes.c_int32), ('out_parts', ctypes.c_int32), ('out_part_stride', ctypes.c_int64),
         ('spade_x', ctypes.c_void_p), ('spade_mean', ctypes.c_void_p), ('spade_rstd', ctypes.c_void_p), ('spade_pre_gain', ctypes.c_float),
+        ('operand_f16', ctypes.c_int32),
     ]
 
 
@@ -78,6 +79,14 @@ def load_library():
     lib.pgpp_pack_activations.argtypes = [vp, c_i64x4, c_i64x4, i32, vp, vp, i32, i32, vp]
     lib.pgpp_pack_activations_slice.restype = i32
     lib.pgpp_pack_activations_slice.argtypes = [vp, c_i64x4, c_i64x4, i32, vp, vp, i32, i32, i32, i32, vp]
+    lib.pgpp_pack_activations_f16.restype = i32
+    lib.pgpp_pack_activations_f16.argtypes = [vp, c_i64x4, c_i64x4, i32, vp, vp, i32, i32, i32, vp]
+    lib.pgpp_pack_weights.restype = i32
+    lib.pgpp_pack_weights.argtypes = [vp, i32, c_i64x4, c_i64x4, i32, i32, f32, i32, i32, vp, i32, vp, vp, i32, i32, i32, i32, i32, vp]
+    lib.pgpp_up2_weight_adjoint.restype = i32
+    lib.pgpp_up2_weight_adjoint.argtypes = [vp, vp, i32, i32, i32, i32, vp, vp]
+    lib.pgpp_mul_reduce_hw.restype = i32
+    lib.pgpp_mul_reduce_hw.argtypes = [vp, vp, vp, i64, vp, vp, vp, i32, i32, i64, vp]
     lib.pgpp_modulate_weights.restype = i32
     lib.pgpp_modulate_weights.argtypes = [vp, vp, vp, i32, i64, i32, i32, i32, vp]
     lib.pgpp_pack_im2col.restype = i32
@@ -107,7 +116,8 @@ def load_library():
 
 
 EXPORTED_SYMBOLS = ('pgpp_version', 'pgpp_last_error', 'pgpp_launch_count', 'pgpp_bias_act', 'pgpp_upfirdn2d',
-                    'pgpp_modconv_demod_coefs', 'pgpp_pack_activations', 'pgpp_pack_activations_slice', 'pgpp_modulate_weights',
+                    'pgpp_modconv_demod_coefs', 'pgpp_pack_activations', 'pgpp_pack_activations_slice', 'pgpp_pack_activations_f16',
+                    'pgpp_pack_weights', 'pgpp_up2_weight_adjoint', 'pgpp_mul_reduce_hw', 'pgpp_modulate_weights',
                     'pgpp_spade_modulate_pack', 'pgpp_mix_pack', 'pgpp_conv2d_direct', 'pgpp_fir_pack', 'pgpp_pack_im2col', 'pgpp_conv2d_igemm', 'pgpp_conv2d_wgrad', 'pgpp_u8_to_f32',
                     'pgpp_image_to_u8', 'pgpp_grid_sample_2d', 'pgpp_grid_sample_2d_backward')
 
@@ -125,6 +135,7 @@ class WgradDesc(ctypes.Structure):
         ('kh', ctypes.c_int32), ('kw', ctypes.c_int32), ('pad_y', ctypes.c_int32), ('pad_x', ctypes.c_int32),
         ('stride', ctypes.c_int32), ('products', ctypes.c_int32),
         ('out', ctypes.c_void_p), ('workspace', ctypes.c_void_p),
+        ('operand_f16', ctypes.c_int32),
     ]
 
 
@@ -255,17 +266,86 @@ class _ConvPlugin:
         return d
 
     @staticmethod
-    def pack_activations(x, scale, c_pad, parts):
+    def pack_activations(x, scale, c_pad, parts, f16=False):
+        """-> [parts, N, H, W, c_pad] bfloat16 parts; with f16=True one part of IEEE half (dtype float16)"""
         lib = load_library()
         _torch_check(x.is_cuda and x.dim() == 4, 'x must be a rank-4 CUDA tensor')
         n, c, h, w = x.shape
-        out = torch.empty([parts, n, h, w, c_pad], dtype=torch.bfloat16, device=x.device)
         if scale is not None:
             scale = scale.detach().to(torch.float32).contiguous()
             _torch_check(tuple(scale.shape) == (n, c), 'scale must be [N, C]')
+        if f16:
+            out = torch.empty([1, n, h, w, c_pad], dtype=torch.float16, device=x.device)
+            with torch.cuda.device(x.device):
+                _check(lib.pgpp_pack_activations_f16(_ptr(x), c_i64x4(*x.shape), c_i64x4(*x.stride()), dtype_code(x.dtype),
+                                                     _ptr(scale), _ptr(out), int(c_pad), int(c_pad), 0, _stream(x)))
+            return out
+        out = torch.empty([parts, n, h, w, c_pad], dtype=torch.bfloat16, device=x.device)
         with torch.cuda.device(x.device):
             _check(lib.pgpp_pack_activations(_ptr(x), c_i64x4(*x.shape), c_i64x4(*x.stride()), dtype_code(x.dtype),
                                              _ptr(scale), _ptr(out), int(c_pad), int(parts), _stream(x)))
+        return out
+
+    @staticmethod
+    def pack_weights(weight, out, master, *, transpose_io=False, flip=False, scale=1.0, phases=1, phase_stride=0, fir=None, flip_filter=False,
+                     parts=1, f16=False, o_off=0):
+        """weight [O, I, kh, kw] (or [I, O, kh, kw] with transpose_io) -> rows [o_off, ...) of out [parts, taps, o_rows, c_pad]
+        (bfloat16 parts or one float16 part) and optionally master float32 [taps, o_rows, c_pad]; see pgpp_pack_weights"""
+        lib = load_library()
+        _torch_check(weight.is_cuda and weight.dim() == 4, 'weight must be a rank-4 CUDA tensor')
+        _torch_check(out.dim() == 4 and out.is_contiguous() and out.dtype in (torch.bfloat16, torch.float16) and out.shape[0] >= parts,
+                     'out must be a contiguous [parts, taps, o_rows, c_pad] 16-bit tensor')
+        _torch_check((out.dtype == torch.float16) == bool(f16), 'fp16 operands need a float16 destination (and only then)')
+        w = weight.detach()
+        if fir is not None:
+            _torch_check(fir.is_cuda and fir.dtype == torch.float32 and tuple(fir.shape) == (4, 4), 'fir must be a float32 CUDA tensor [4, 4]')
+            fir = fir.contiguous()
+        _torch_check(master is None or (master.dtype == torch.float32 and master.is_contiguous() and master.numel() == out[0].numel()),
+                     'master must be a contiguous float32 tensor with taps * o_rows * c_pad elements')
+        with torch.cuda.device(w.device):
+            _check(lib.pgpp_pack_weights(_ptr(w), dtype_code(w.dtype), c_i64x4(*w.shape), c_i64x4(*w.stride()), int(bool(transpose_io)),
+                                         int(bool(flip)), float(scale), int(phases), int(phase_stride), _ptr(fir), int(bool(flip_filter)),
+                                         _ptr(out), _ptr(master), int(parts), int(bool(f16)), int(out.shape[2]), int(o_off), int(out.shape[3]),
+                                         _stream(w)))
+        return out
+
+    @staticmethod
+    def mul_reduce_hw(a, b=None, sub=None, scale=None, out_scaled=False, reduce=True):
+        """a, b float32 [N,C,H,W] contiguous; sub [H,W] or [N,1,H,W]; scale [N,C] ->
+        (r [N,C] = sum_hw a * (b - sub) or None, a * scale[n,c] or None); see pgpp_mul_reduce_hw"""
+        lib = load_library()
+        _torch_check(a.is_cuda and a.dtype == torch.float32 and a.dim() == 4, 'mul_reduce_hw: a must be a float32 CUDA tensor [N,C,H,W]')
+        a = a.contiguous()
+        n, c, h, w = a.shape
+        if b is not None:
+            _torch_check(b.dtype == torch.float32 and tuple(b.shape) == tuple(a.shape), 'mul_reduce_hw: b must match a')
+            b = b.contiguous()
+        sub_stride = 0
+        if sub is not None:
+            sub = sub.detach().to(torch.float32).contiguous()
+            _torch_check(sub.numel() in (h * w, n * h * w), 'mul_reduce_hw: sub must be [H,W] or [N,1,H,W]')
+            sub_stride = h * w if sub.numel() == n * h * w and n > 1 else 0
+        if scale is not None:
+            scale = scale.detach().to(torch.float32).contiguous()
+            _torch_check(scale.numel() == n * c, 'mul_reduce_hw: scale must be [N,C]')
+        r = torch.empty([n, c], dtype=torch.float32, device=a.device) if reduce else None
+        out = torch.empty_like(a) if out_scaled else None
+        if a.numel() == 0:
+            return (r.zero_() if r is not None else None), out
+        with torch.cuda.device(a.device):
+            _check(lib.pgpp_mul_reduce_hw(_ptr(a), _ptr(b), _ptr(sub), int(sub_stride), _ptr(scale), _ptr(out), _ptr(r), n, c, h * w, _stream(a)))
+        return r, out
+
+    @staticmethod
+    def up2_weight_adjoint(grad_polyphase, fir, flip_filter, flip, o, ic):
+        """grad_polyphase float32 [4, O, I, 3, 3] -> grad_weight float32 [O, I, 3, 3]; see pgpp_up2_weight_adjoint"""
+        lib = load_library()
+        g = grad_polyphase.contiguous()
+        _torch_check(g.dtype == torch.float32 and g.numel() == 36 * o * ic, 'grad_polyphase must be float32 [4, O, I, 3, 3]')
+        out = torch.empty([o, ic, 3, 3], dtype=torch.float32, device=g.device)
+        with torch.cuda.device(g.device):
+            _check(lib.pgpp_up2_weight_adjoint(_ptr(g), _ptr(fir.contiguous()), int(bool(flip_filter)), int(bool(flip)), int(o), int(ic),
+                                               _ptr(out), _stream(g)))
         return out
 
     @staticmethod

@@ -33,8 +33,13 @@ enabled = True                      # the reference defaults to False and train.
 weight_gradients_disabled = False
 fp32_precision = 'bf16x2'
 direct_few_tap_convs = os.environ.get('PGPP_NO_DIRECT_CONV') is None    # C*kh*kw <= 16 convs on the exact-fp32 direct kernel
+# Training path: the forward pass keeps the packed (operand-format) copy of its input for the weight-gradient GEMM, and a plain
+# backward pass (no create_graph) packs grad_output ONCE for both the data-gradient and the weight-gradient kernels instead of going
+# through two more autograd Functions that each re-pack from NCHW.  Costs one operand-format copy per saved activation (the same
+# bytes as the fp32 tensor in the bf16x2 mode) - sized for 180 GB of HBM3e.  False: re-pack in backward (round-1 behaviour).
+keep_packed_operands = True
 
-_PRODUCTS = {'bf16': (1, 1), 'bf16x2': (3, 2), 'bf16x3': (6, 3)}    # name -> (products, parts)
+_PRODUCTS = {'bf16': (1, 1), 'bf16x2': (3, 2), 'bf16x3': (6, 3), 'f16': (1, 1)}    # name -> (MMA products, operand parts)
 _ACT_IDX = {'linear': 1, 'relu': 2, 'lrelu': 3, 'tanh': 4, 'sigmoid': 5, 'elu': 6, 'selu': 7, 'softplus': 8, 'swish': 9}
 _plugin = None
 trace = None        # set to a list to record (label, algorithmic FLOPs, start event, end event) per igemm launch (bench.py roofline)
@@ -69,7 +74,12 @@ def _tuple_of_ints(xs, ndim):
 
 
 def precision_for(dtype):
-    return fp32_precision if dtype in (torch.float32, torch.float64) else 'bf16'
+    """float32 / float64 tensors: the error-compensated bf16 split selected by `fp32_precision`; float16 tensors (the mixed-precision
+    blocks of the discriminator, networks.py:634,647): native fp16 operands on the f16 tensor-core path, as cuDNN does for the
+    reference; bfloat16 tensors: native bf16."""
+    if dtype in (torch.float32, torch.float64):
+        return fp32_precision
+    return 'f16' if dtype == torch.float16 else 'bf16'
 
 
 # ------------------------------------------------------------------------------------------------
@@ -92,7 +102,7 @@ def _split_bf16(t, parts):
 
 class PackedWeights:
     """[parts, taps, o_rows, c_pad] bf16, K-major rows, ready for the TMA weight map."""
-    __slots__ = ('data', 'master', 'kh', 'kw', 'o', 'phases', 'phase_stride', 'o_rows', 'c_pad', 'c_in', 'parts', 'pad_y', 'pad_x', 'im2col')
+    __slots__ = ('data', 'master', 'kh', 'kw', 'o', 'phases', 'phase_stride', 'o_rows', 'c_pad', 'c_in', 'parts', 'pad_y', 'pad_x', 'im2col', 'f16')
 
 
 class PackedAct:
@@ -179,6 +189,53 @@ def pack_weights(w_taps, o, phases, kh, kw, parts, pad_y, pad_x):
     pw.phase_stride = phase_stride
     pw.pad_y, pw.pad_x = pad_y, pad_x
     pw.im2col = None
+    pw.f16 = False
+    return pw
+
+
+def weight_layout(o, ic, phases=1):
+    """(phase_stride, cols, o_rows, c_pad) of the packed weight operand: GEMM column of (phase, oc) is phase * phase_stride + oc
+    (phase_stride = o rounded up to 16 for the 4-phase up=2 form); rows are padded to a multiple of 256 or to the power of two
+    >= cols (whole N tiles), channels to whole 128-byte swizzle rows."""
+    phase_stride = _round_up(o, 16) if phases > 1 else o
+    cols = phases * phase_stride
+    o_rows = _round_up(cols, 256) if cols > 128 else max(16, 1 << (cols - 1).bit_length())
+    return phase_stride, cols, o_rows, _round_up(ic, 64)
+
+
+def pack_weights_native(weights, kh, kw, parts, pad_y, pad_x, *, transpose_io=False, flip=False, scale=1.0, up2_filter=None, flip_filter=False,
+                        f16=False):
+    """PackedWeights from one weight tensor - or several stacked along the output channels (gamma | beta of a SPADE block) - in ONE
+    kernel launch per tensor (pgpp_pack_weights): scale, flip, transposition, padding, bf16 split / fp16 copy, and with `up2_filter`
+    the polyphase form of the up=2 layer.  No library op touches the weights."""
+    _init()
+    weights = list(weights) if isinstance(weights, (list, tuple)) else [weights]
+    dims = [(int(w.shape[1]), int(w.shape[0])) if transpose_io else (int(w.shape[0]), int(w.shape[1])) for w in weights]
+    ic = dims[0][1]
+    assert all(d[1] == ic for d in dims)
+    o = sum(d[0] for d in dims)
+    phases = 4 if up2_filter is not None else 1
+    assert phases == 1 or len(weights) == 1
+    phase_stride, cols, o_rows, c_pad = weight_layout(o, ic, phases)
+    taps = 9 if phases > 1 else kh * kw
+    dev = weights[0].device
+    dt = torch.float16 if f16 else torch.bfloat16
+    alloc = torch.zeros if o_rows != cols else torch.empty          # rows beyond the tensor must read as zero weights
+    pw = PackedWeights()
+    pw.data = alloc([parts, taps, o_rows, c_pad], dtype=dt, device=dev)
+    master = None if f16 else alloc([taps, o_rows, c_pad], dtype=torch.float32, device=dev)
+    o_off = 0
+    for w, (wo, _) in zip(weights, dims):
+        _plugin.pack_weights(w, pw.data, master, transpose_io=transpose_io, flip=flip, scale=scale, phases=phases, phase_stride=phase_stride,
+                             fir=up2_filter, flip_filter=flip_filter, parts=parts, f16=f16, o_off=o_off)
+        o_off += wo
+    pw.master = None if master is None else master.reshape(taps * o_rows, c_pad)
+    pw.c_in = ic
+    pw.kh, pw.kw, pw.o, pw.phases, pw.o_rows, pw.c_pad, pw.parts = (3, 3, o, 4, o_rows, c_pad, parts) if phases > 1 else (kh, kw, o, 1, o_rows, c_pad, parts)
+    pw.phase_stride = phase_stride
+    pw.pad_y, pw.pad_x = pad_y, pad_x
+    pw.im2col = None
+    pw.f16 = bool(f16)
     return pw
 
 
@@ -221,19 +278,23 @@ def im2col_rows(ic, kh, kw):
     return r if (kh - 1) // r * r <= 6 else 0
 
 
-def packed_plain(weight, flip_weight, parts, pad_y, pad_x, transpose_io=False, scale=1.0, allow_im2col=False):
+def packed_plain(weight, flip_weight, parts, pad_y, pad_x, transpose_io=False, scale=1.0, allow_im2col=False, f16=False):
     """weight [O, I, kh, kw] used as a correlation kernel (flip_weight=True, F.conv2d semantics) or a true
     convolution kernel (flip_weight=False).  transpose_io: weight is [I, O, kh, kw] (conv_transpose2d layout).
     scale: constant folded into the packed copy (the layers' runtime weight_gain, networks.py:155,169)."""
     def build():
+        o, ic, kh, kw = (weight.shape[1], weight.shape[0], *weight.shape[2:]) if transpose_io else weight.shape
+        r = im2col_rows(ic, kh, kw) if allow_im2col else 0
+        if not r:
+            return pack_weights_native(weight, kh, kw, parts, pad_y, pad_x, transpose_io=transpose_io, flip=not flip_weight, scale=float(scale),
+                                       f16=f16)
+        assert not f16
         w = weight.detach().to(torch.float32) * float(scale)
         if transpose_io:
             w = w.transpose(0, 1)
         if not flip_weight:
             w = w.flip([2, 3])
-        o, ic, kh, kw = w.shape
-        r = im2col_rows(ic, kh, kw) if allow_im2col else 0
-        if r:
+        if True:
             # row-group im2col operand (pgpp_pack_im2col): channel (ry*kw + kx)*ic + c of vertical tap group t holds w[o, c, t*r + ry, kx]
             groups = -(-kh // r)
             wp = torch.zeros([groups, o, r, kw, ic], dtype=torch.float32, device=w.device)
@@ -243,9 +304,7 @@ def packed_plain(weight, flip_weight, parts, pad_y, pad_x, transpose_io=False, s
             pw = pack_weights(wp.reshape(groups, o, r * kw * ic), o, 1, groups, 1, parts, 0, 0)
             pw.im2col = dict(r=r, kw=kw, kh=kh, pad_x=pad_x, pad_y=pad_y)
             return pw
-        taps = w.permute(2, 3, 0, 1).reshape(kh * kw, o, ic)
-        return pack_weights(taps, o, 1, kh, kw, parts, pad_y, pad_x)
-    return _cached(weight, ('plain', bool(flip_weight), parts, pad_y, pad_x, bool(transpose_io), float(scale), bool(allow_im2col)), build)
+    return _cached(weight, ('plain', bool(flip_weight), parts, pad_y, pad_x, bool(transpose_io), float(scale), bool(allow_im2col), bool(f16)), build)
 
 
 def packed_up2(weight, f, flip_weight, flip_filter, parts):
@@ -258,32 +317,8 @@ def packed_up2(weight, f, flip_weight, flip_filter, parts):
     with w' the kernel as conv_transpose2d sees it and k the (flipped) FIR.  One 3x3 GEMM with 4*O columns
     replaces the transposed convolution, its (2H+1)^2 intermediate and the blur pass."""
     def build():
-        w = weight.detach().to(torch.float32)
-        o, ic, kh, kw = w.shape
-        assert kh == 3 and kw == 3 and tuple(f.shape) == (4, 4)
-        if flip_weight:
-            w = w.flip([2, 3])
-        k = f.to(device=w.device, dtype=torch.float32)
-        if not flip_filter:
-            k = k.flip([0, 1])
-        wp = torch.zeros([2, 2, o, ic, 3, 3], dtype=torch.float32, device=w.device)
-        for py in range(2):
-            for fy in range(4):
-                for ky in range(3):
-                    num_y = py + fy - 1 - ky
-                    if num_y % 2:
-                        continue
-                    a = num_y // 2 + 1
-                    for px in range(2):
-                        for fx in range(4):
-                            for kx in range(3):
-                                num_x = px + fx - 1 - kx
-                                if num_x % 2:
-                                    continue
-                                b = num_x // 2 + 1
-                                wp[py, px, :, :, a, b] += 4.0 * k[fy, fx] * w[:, :, ky, kx]
-        taps = wp.permute(4, 5, 0, 1, 2, 3).reshape(9, 4 * o, ic)     # [tap][phase*o + oc][i]
-        return pack_weights(taps, o, 4, 3, 3, parts, 1, 1)
+        assert tuple(weight.shape[2:]) == (3, 3) and tuple(f.shape) == (4, 4) and f.dtype == torch.float32
+        return pack_weights_native(weight, 3, 3, parts, 1, 1, flip=bool(flip_weight), up2_filter=f, flip_filter=bool(flip_filter))
     return _cached(weight, ('up2', bool(flip_weight), bool(flip_filter), parts), build, also=(f,))
 
 
@@ -313,7 +348,9 @@ def igemm_conv(x, pw, *, scale=None, stride=1, out_hw=None, dcoef=None, noise=No
     src_dtype = torch.float32 if isinstance(x, PackedAct) else x.dtype
     precision = precision or precision_for(src_dtype)
     products, parts = _PRODUCTS[precision]
+    f16 = precision == 'f16'
     assert pw.parts >= parts, 'weights were packed with fewer parts than the requested precision needs'
+    assert bool(pw.f16) == f16, 'fp16 operands need fp16-packed weights (and only they)'
     d = custom_ops.ConvDesc()
     keep = []
     if isinstance(x, PackedAct):
@@ -334,7 +371,7 @@ def igemm_conv(x, pw, *, scale=None, stride=1, out_hw=None, dcoef=None, noise=No
             x_packed = _plugin.pack_im2col(x, scale, im['kw'], im['r'], im['pad_x'], im['pad_y'], parts)
             h = x_packed.shape[2]
         else:
-            x_packed = _plugin.pack_activations(x, scale, pw.c_pad, parts)
+            x_packed = _plugin.pack_activations(x, scale, pw.c_pad, parts, f16=f16)
         keep.append(x_packed)
         d.act = x_packed.data_ptr(); d.a_parts = parts
         d.wgt = pw.data.data_ptr(); d.b_parts = pw.data.shape[0]
@@ -413,6 +450,7 @@ def igemm_conv(x, pw, *, scale=None, stride=1, out_hw=None, dcoef=None, noise=No
     d.act_fn = _ACT_IDX[act]; d.alpha = float(alpha); d.gain = float(gain); d.clamp = float(clamp)
     d.out_h, d.out_w = out_h, out_w
     d.accumulate = int(bool(accumulate))
+    d.operand_f16 = int(f16)
     if trace is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -449,67 +487,106 @@ def conv_transpose2d(input, weight, bias=None, stride=1, padding=0, output_paddi
                                                 output_padding=output_padding, groups=groups, dilation=dilation)
 
 
-def _forward_conv(x, weight, bias, stride, padding):
-    """F.conv2d(x, weight, bias, stride, padding) on the tensor cores."""
-    _, parts = _PRODUCTS[precision_for(x.dtype)]
-    pw = packed_plain(weight, True, parts, padding[0], padding[1])
-    return igemm_conv(x, pw, stride=stride[0], bias=bias)
+def pack_operand(x, prec=None):
+    """NCHW (or any-strided) tensor -> PackedAct in the operand format of `prec` (channels padded to whole 64-channel rows)"""
+    _init()
+    prec = prec or precision_for(x.dtype)
+    data = _plugin.pack_activations(x, None, _round_up(x.shape[1], 64), _PRODUCTS[prec][1], f16=prec == 'f16')
+    return PackedAct(data, x.shape[1])
 
 
-def _forward_conv_transpose(x, weight, bias, stride, padding, output_padding):
+def _forward_conv(x, weight, bias, stride, padding, keep=False):
+    """F.conv2d(x, weight, bias, stride, padding) on the tensor cores.  x: tensor or PackedAct (then `keep` is moot).
+    keep=True also returns the packed copy of x (for the weight gradient)."""
+    src_dtype = weight.dtype if isinstance(x, PackedAct) else x.dtype
+    prec = precision_for(src_dtype)
+    pw = packed_plain(weight, True, _PRODUCTS[prec][1], padding[0], padding[1], f16=prec == 'f16')
+    xp, mf = x, None
+    if keep and not isinstance(x, PackedAct):
+        mf = torch.channels_last if (x.stride(1) == 1 and x.shape[1] > 1) else torch.contiguous_format     # the output follows the input's layout
+        xp = pack_operand(x, prec)
+    y = igemm_conv(xp, pw, stride=stride[0], bias=bias, precision=prec, out_dtype=src_dtype if src_dtype != torch.float64 else None,
+                   memory_format=mf)
+    if src_dtype == torch.float64 and y.dtype != torch.float64:
+        y = y.to(torch.float64)
+    return (y, xp) if keep else y
+
+
+def _forward_conv_transpose(x, weight, bias, stride, padding, output_padding, keep=False):
     """F.conv_transpose2d(x, weight[I, O, kh, kw], ...) as zero insertion + a stride-1 convolution with the
-    flipped, transposed kernel (the data-gradient form; the fused up=2 layer does NOT come through here)."""
+    flipped, transposed kernel (the data-gradient form; the fused up=2 layer does NOT come through here).
+    x: tensor, or for stride 1 a PackedAct.  keep=True also returns the packed copy of x when the kernel consumed x itself
+    (stride 1), else None."""
     from . import upfirdn2d as _up
     ic, oc, kh, kw = weight.shape
     sy, sx = stride
-    if sy > 1 or sx > 1:
+    src_dtype = weight.dtype if isinstance(x, PackedAct) else x.dtype
+    strided = sy > 1 or sx > 1
+    if strided:
+        assert not isinstance(x, PackedAct)
         # insert zeros between samples; crop the trailing (s-1) zeros the insertion appends
         x = _up.upfirdn2d(x, None, up=[sx, sy], padding=[0, -(sx - 1), 0, -(sy - 1)])
     py, px = kh - 1 - padding[0], kw - 1 - padding[1]
     assert py >= 0 and px >= 0, 'conv_transpose2d padding larger than kernel_size-1 is not supported'
-    _, parts = _PRODUCTS[precision_for(x.dtype)]
-    pw = packed_plain(weight, False, parts, py, px, transpose_io=True)    # flipped + transposed = equivalent correlation kernel
+    prec = precision_for(src_dtype)
+    pw = packed_plain(weight, False, _PRODUCTS[prec][1], py, px, transpose_io=True, f16=prec == 'f16')    # flipped + transposed = equivalent correlation kernel
     n, _, h, w = x.shape
     out_h = h + 2 * py - kh + 1 + output_padding[0]
     out_w = w + 2 * px - kw + 1 + output_padding[1]
-    return igemm_conv(x, pw, stride=1, bias=bias, out_hw=(out_h, out_w))
+    xp, mf = x, None
+    if keep and not strided and not isinstance(x, PackedAct):
+        mf = torch.channels_last if (x.stride(1) == 1 and x.shape[1] > 1) else torch.contiguous_format
+        xp = pack_operand(x, prec)
+    y = igemm_conv(xp, pw, stride=1, bias=bias, out_hw=(out_h, out_w), precision=prec, out_dtype=src_dtype if src_dtype != torch.float64 else None,
+                   memory_format=mf)
+    if src_dtype == torch.float64 and y.dtype != torch.float64:
+        y = y.to(torch.float64)
+    if keep:
+        return y, (xp if isinstance(xp, PackedAct) else None)
+    return y
 
 
-def weight_gradient(grad_output, input, weight_shape, stride, padding, transpose, precision=None):
+def weight_gradient(grad_output, input, weight_shape, stride, padding, transpose, precision=None, out_dtype=None):
     """dW of conv2d (transpose=False, weight [O, I, kh, kw]) or conv_transpose2d (transpose=True, weight [I, O, kh, kw]):
     what Conv2dGradWeight.forward (conv2d_gradfix.py:135-142) gets from cuDNN, computed by pgpp_conv2d_wgrad as
     G[a, b, ky, kx] = sum S[n, a, y, x] * L[n, b, y*s + ky - p, x*s + kx - p] with (S, L) = (grad_output, input) for the
     convolution and (input, grad_output) for the transposed convolution."""
     _init()
-    precision = precision or precision_for(input.dtype)
+    if out_dtype is None:
+        out_dtype = next(t.dtype for t in (input, grad_output) if not isinstance(t, PackedAct))
+    precision = precision or precision_for(out_dtype)
     products, parts = _PRODUCTS[precision]
     small, large = (input, grad_output) if transpose else (grad_output, input)
     ca, cb, kh, kw = (int(v) for v in weight_shape)
     n = int(small.shape[0])
     assert small.shape[1] == ca and large.shape[1] == cb and large.shape[0] == n
     ca_pad, cb_pad = _round_up(ca, 64), _round_up(cb, 64)
-    s_op = _plugin.pack_activations(small, None, ca_pad, parts)
-    l_op = _plugin.pack_activations(large, None, cb_pad, parts)
-    out = torch.empty([ca, cb, kh, kw], dtype=torch.float32, device=input.device)
+    f16 = precision == 'f16'
+    s_op = small if isinstance(small, PackedAct) else pack_operand(small, precision)      # operands the forward / data-gradient kernels
+    l_op = large if isinstance(large, PackedAct) else pack_operand(large, precision)      # already packed are used as they are
+    for op, cpad in ((s_op, ca_pad), (l_op, cb_pad)):
+        assert op.data.shape[0] >= parts and op.data.shape[4] - op.c_off >= cpad and (op.data.dtype == torch.float16) == f16
+    device = s_op.data.device
+    out = torch.empty([ca, cb, kh, kw], dtype=torch.float32, device=device)
     d = custom_ops.WgradDesc()
-    d.small = s_op.data_ptr(); d.large = l_op.data_ptr()
-    d.s_parts = parts; d.l_parts = parts
+    d.small = s_op.data.data_ptr() + 2 * s_op.c_off; d.large = l_op.data.data_ptr() + 2 * l_op.c_off
+    d.s_parts = s_op.data.shape[0]; d.l_parts = l_op.data.shape[0]
     d.n = n
-    d.ca = ca; d.ca_pad = ca_pad; d.s_pixel_stride = ca_pad; d.hs = int(small.shape[2]); d.ws = int(small.shape[3])
-    d.cb = cb; d.cb_pad = cb_pad; d.l_pixel_stride = cb_pad; d.hl = int(large.shape[2]); d.wl = int(large.shape[3])
+    d.ca = ca; d.ca_pad = ca_pad; d.s_pixel_stride = s_op.data.shape[4]; d.hs = int(small.shape[2]); d.ws = int(small.shape[3])
+    d.cb = cb; d.cb_pad = cb_pad; d.l_pixel_stride = l_op.data.shape[4]; d.hl = int(large.shape[2]); d.wl = int(large.shape[3])
     d.kh = kh; d.kw = kw; d.pad_y = int(padding[0]); d.pad_x = int(padding[1])
-    d.stride = int(stride); d.products = products
-    workspace = torch.empty([kh * kw, ca, cb_pad], dtype=torch.float32, device=input.device)
+    d.stride = int(stride); d.products = products; d.operand_f16 = int(f16)
+    workspace = torch.empty([kh * kw, ca, cb_pad], dtype=torch.float32, device=device)
     d.out = out.data_ptr(); d.workspace = workspace.data_ptr()
     if trace is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-    _plugin.conv2d_wgrad(d, input.device)
+    _plugin.conv2d_wgrad(d, device)
     if trace is not None:
         e1.record()
         flops = 2.0 * n * small.shape[2] * small.shape[3] * ca * cb * kh * kw
         trace.append((f'wgrad {ca}x{cb} k{kh} {small.shape[2]}x{small.shape[3]} s{stride} n{n} {precision}', flops, e0, e1))
-    return out if input.dtype == torch.float32 else out.to(input.dtype)
+    return out if out_dtype == torch.float32 else out.to(out_dtype)
 
 
 _conv2d_gradfix_cache = dict()
@@ -551,10 +628,14 @@ def _conv2d_gradfix(transpose, weight_shape, stride, padding, output_padding, di
         @staticmethod
         def forward(ctx, input, weight, bias):
             assert weight.shape == weight_shape
+            keep = keep_packed_operands and ctx.needs_input_grad[1]
+            ctx.input_packed = None
             if not transpose:
-                output = _forward_conv(input, weight, bias, stride, padding)
+                output = _forward_conv(input, weight, bias, stride, padding, keep=keep)
             else:
-                output = _forward_conv_transpose(input, weight, bias, stride, padding, output_padding)
+                output = _forward_conv_transpose(input, weight, bias, stride, padding, output_padding, keep=keep)
+            if keep:
+                output, ctx.input_packed = output
             ctx.save_for_backward(input, weight)
             return output
 
@@ -562,14 +643,35 @@ def _conv2d_gradfix(transpose, weight_shape, stride, padding, output_padding, di
         def backward(ctx, grad_output):
             input, weight = ctx.saved_tensors
             grad_input = grad_weight = grad_bias = None
-            if ctx.needs_input_grad[0]:
-                p = calc_output_padding(input_shape=input.shape, output_shape=grad_output.shape)
-                grad_input = _conv2d_gradfix(transpose=(not transpose), weight_shape=weight_shape, output_padding=p,
-                                             **common_kwargs).apply(grad_output, weight, None)
-                assert grad_input.shape == input.shape
-            if ctx.needs_input_grad[1] and not weight_gradients_disabled:
-                grad_weight = Conv2dGradWeight.apply(grad_output, input)
-                assert grad_weight.shape == weight_shape
+            want_w = ctx.needs_input_grad[1] and not weight_gradients_disabled
+            if not torch.is_grad_enabled() and keep_packed_operands:
+                # plain backward pass (no graph is being recorded): grad_output is packed once and feeds both the data-gradient and
+                # the weight-gradient kernel; the weight gradient reads the input operand the forward pass kept
+                prec = precision_for(grad_output.dtype)
+                go = None
+                if want_w or (ctx.needs_input_grad[0] and (transpose or stride[0] == 1)):
+                    go = pack_operand(grad_output, prec)
+                if ctx.needs_input_grad[0]:
+                    p = calc_output_padding(input_shape=input.shape, output_shape=grad_output.shape)
+                    if transpose:       # gradient of conv_transpose2d = conv2d of grad_output with the same weight
+                        grad_input = _forward_conv(go, weight, None, stride, padding)
+                    else:               # gradient of conv2d = conv_transpose2d (zero insertion first when strided)
+                        grad_input = _forward_conv_transpose(go if stride[0] == 1 else grad_output, weight, None, stride, padding, p)
+                    assert grad_input.shape == input.shape
+                if want_w:
+                    xin = ctx.input_packed if ctx.input_packed is not None else input
+                    grad_weight = weight_gradient(go, xin, weight_shape, stride[0], padding, transpose, precision=prec, out_dtype=weight.dtype)
+                    assert grad_weight.shape == weight_shape
+                ctx.input_packed = None
+            else:
+                if ctx.needs_input_grad[0]:
+                    p = calc_output_padding(input_shape=input.shape, output_shape=grad_output.shape)
+                    grad_input = _conv2d_gradfix(transpose=(not transpose), weight_shape=weight_shape, output_padding=p,
+                                                 **common_kwargs).apply(grad_output, weight, None)
+                    assert grad_input.shape == input.shape
+                if want_w:
+                    grad_weight = Conv2dGradWeight.apply(grad_output, input)
+                    assert grad_weight.shape == weight_shape
             if ctx.needs_input_grad[2]:
                 grad_bias = grad_output.sum([0, 2, 3])
             return grad_input, grad_weight, grad_bias

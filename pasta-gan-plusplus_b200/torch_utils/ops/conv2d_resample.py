@@ -89,7 +89,7 @@ def conv2d_resample(x, w, f=None, up=1, down=1, padding=0, groups=1, flip_weight
 
     # fused polyphase form of the up=2 layer (inference): one implicit-GEMM launch
     if (up == 2 and down == 1 and groups == 1 and (kh, kw) == (3, 3) and f is not None and f.ndim == 2 and (fw, fh) == (4, 4)
-            and pad.fir == [1, 1, 1, 1] and conv2d_gradfix._should_use_custom_op(x) and not _needs_grad(x, w)):
+            and pad.fir == [1, 1, 1, 1] and conv2d_gradfix._should_use_custom_op(x) and not _needs_grad(x, w) and x.dtype != torch.float16):
         _, parts = conv2d_gradfix._PRODUCTS[conv2d_gradfix.precision_for(x.dtype)]
         return conv2d_gradfix.igemm_conv(x, conv2d_gradfix.packed_up2(w, f, flip_weight, flip_filter, parts))
 

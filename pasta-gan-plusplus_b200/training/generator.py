@@ -220,10 +220,8 @@ class Spade_Norm_Block(torch.nn.Module):
         """conv_gamma and conv_beta read the same input: one GEMM with 2C output columns"""
         wg, wb = self.conv_gamma.weight, self.conv_beta.weight
         def build():
-            w = torch.cat([wg.detach(), wb.detach()], dim=0).to(torch.float32) * float(self.conv_gamma.weight_gain)
-            o, ic, kh, kw = w.shape
-            taps = w.permute(2, 3, 0, 1).reshape(kh * kw, o, ic)
-            return conv2d_gradfix.pack_weights(taps, o, 1, kh, kw, S._parts(), self.conv_gamma.padding, self.conv_gamma.padding)
+            return conv2d_gradfix.pack_weights_native([wg, wb], wg.shape[2], wg.shape[3], S._parts(), self.conv_gamma.padding, self.conv_gamma.padding,
+                                                      scale=float(self.conv_gamma.weight_gain))
         return conv2d_gradfix._cached(wg, ('spade_gb', S._parts()), build, also=(wb,))
 
     def fused_packed(self, x, mean, rstd, feats_packed, pre_gain):

@@ -23,6 +23,8 @@ from ..torch_utils.ops import conv2d_resample
 from ..torch_utils.ops import fma
 from ..torch_utils.ops import upfirdn2d
 
+fused_training = True       # False: the grad-enabled CUDA path composes x * s -> conv2d_resample -> fma from separate ops (round 1)
+
 
 def _kernel_path_ok(x, weight, styles, noise, up, down, padding, resample_filter):
     if not conv2d_gradfix._should_use_custom_op(x):
@@ -30,7 +32,7 @@ def _kernel_path_ok(x, weight, styles, noise, up, down, padding, resample_filter
     if torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in (x, weight, styles, noise)):
         return False
     kh, kw = weight.shape[2:]
-    if down != 1 or kh != kw:
+    if down != 1 or kh != kw or x.dtype == torch.float16:      # fp16 tensors: composition over conv2d_gradfix (native f16 MMAs)
         return False
     if up == 1:
         return isinstance(padding, int) and 0 <= padding <= kh - 1
@@ -58,13 +60,93 @@ def modulated_conv2d_fused_act(x, weight, styles, noise=None, up=1, padding=0, r
     if demodulate:
         conv2d_gradfix._init()
         dcoef = conv2d_gradfix._plugin.demod_coefs(weight, styles)
+    f16 = src_dtype == torch.float16
     if up == 2:
+        if f16:
+            raise NotImplementedError('the fused up=2 layer takes float32 / bfloat16 tensors; call modulated_conv2d for float16')
         pw = conv2d_gradfix.packed_up2(weight, resample_filter, flip_weight, False, parts)
     else:
-        pw = conv2d_gradfix.packed_plain(weight, flip_weight, parts, padding, padding)
+        pw = conv2d_gradfix.packed_plain(weight, flip_weight, parts, padding, padding, f16=f16)
     return conv2d_gradfix.igemm_conv(x, pw, scale=styles, dcoef=dcoef, noise=noise, bias=bias, act=act, alpha=alpha,
                                      gain=gain, clamp=clamp, out=out, out_dtype=out_dtype, accumulate=accumulate,
                                      memory_format=memory_format, out_packed=out_packed)
+
+
+class _FusedModulatedConv2d(torch.autograd.Function):
+    """Differentiable form of the kernel path for up = down = 1 (the training-mode SynthesisLayer / ToRGB of the generator phases):
+
+        y[n,o] = d[n,o] * conv(x[n] * s[n], W)[o] + noise            (networks.py:73-82, the reference's non-fused formulation)
+
+    forward : ONE packing pass (x * s folded in) + ONE implicit-GEMM launch with d and the noise in its epilogue
+    backward: gz = pack(gy * d);  g_xs = dgrad(gz) on the tensor cores;  (g_x, g_s) = (g_xs * s, sum_hw g_xs * x) in one reduction pass;
+              g_W = wgrad(gz, packed x*s kept from the forward);  g_d = sum_hw gy * (y - noise) / d;  g_noise = sum over channels of gy.
+    d itself is computed by the caller with a few tiny differentiable library ops on [N, I] x [O, I], so its dependence on W and s
+    is handled by autograd.  First-order only (the reference has path-length regularisation - the only double backward through G -
+    commented out, loss_fullbody.py:213-232)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, styles, dcoefs, noise, padding, flip_weight):
+        cg = conv2d_gradfix
+        cg._init()
+        prec = cg.precision_for(x.dtype)
+        parts = cg._PRODUCTS[prec][1]
+        o, ic, kh, kw = weight.shape
+        xs = cg.PackedAct(cg._plugin.pack_activations(x, styles, cg._round_up(ic, 64), parts), ic)
+        pw = cg.packed_plain(weight, flip_weight, parts, padding, padding)
+        y = cg.igemm_conv(xs, pw, dcoef=dcoefs, noise=noise, precision=prec, out_dtype=x.dtype)
+        need_y = dcoefs is not None and ctx.needs_input_grad[3]
+        ctx.save_for_backward(x, weight, styles, dcoefs, noise, y if need_y else None)
+        ctx.xs = xs if ctx.needs_input_grad[1] else None
+        ctx.cfg = (padding, flip_weight, prec, parts)
+        return y
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, gy):
+        cg = conv2d_gradfix
+        x, weight, styles, dcoefs, noise, y = ctx.saved_tensors
+        padding, flip_weight, prec, parts = ctx.cfg
+        o, ic, kh, kw = weight.shape
+        gy = gy.contiguous()
+        g_x = g_w = g_s = g_d = g_noise = None
+        gz = cg.PackedAct(cg._plugin.pack_activations(gy, dcoefs, cg._round_up(o, 64), parts), o)      # gy * d in operand format
+        if ctx.needs_input_grad[0] or ctx.needs_input_grad[2]:
+            pw_t = cg.packed_plain(weight, not flip_weight, parts, kh - 1 - padding, kw - 1 - padding, transpose_io=True)
+            g_xs = cg.igemm_conv(gz, pw_t, precision=prec, out_dtype=torch.float32, out_hw=tuple(x.shape[2:]))
+            xf = x if x.dtype == torch.float32 else x.float()
+            g_s, g_x = cg._plugin.mul_reduce_hw(g_xs, xf, scale=styles, out_scaled=ctx.needs_input_grad[0], reduce=ctx.needs_input_grad[2])
+            if g_x is not None and g_x.dtype != x.dtype:
+                g_x = g_x.to(x.dtype)
+            if g_s is not None:
+                g_s = g_s.to(styles.dtype)
+        if ctx.needs_input_grad[1] and not cg.weight_gradients_disabled:
+            xs = ctx.xs if ctx.xs is not None else cg.PackedAct(cg._plugin.pack_activations(x, styles, cg._round_up(ic, 64), parts), ic)
+            g_w = cg.weight_gradient(gz, xs, (o, ic, kh, kw), 1, (padding, padding), False, precision=prec, out_dtype=weight.dtype)
+            if not flip_weight:
+                g_w = g_w.flip([2, 3])
+        ctx.xs = None
+        if dcoefs is not None and ctx.needs_input_grad[3]:
+            gyf = gy if gy.dtype == torch.float32 else gy.float()
+            yf = y if y.dtype == torch.float32 else y.float()
+            r, _ = cg._plugin.mul_reduce_hw(gyf, yf, sub=noise)
+            g_d = (r / dcoefs.to(torch.float32)).to(dcoefs.dtype)
+        if noise is not None and ctx.needs_input_grad[4]:
+            g_noise = gy.sum(dim=(0, 1)) if noise.dim() == 2 else gy.sum(dim=1, keepdim=True)
+            if noise.dim() == 4 and noise.shape[0] == 1 and gy.shape[0] > 1:
+                g_noise = g_noise.sum(dim=0, keepdim=True)
+            g_noise = g_noise.to(noise.dtype)
+        return g_x, g_w, g_s, g_d, g_noise, None, None
+
+
+def _fused_training_path_ok(x, weight, styles, noise, up, down, padding):
+    """CUDA float32 / bfloat16 tensors, gradients required, stride-1 modulated convolution: the fused differentiable Function"""
+    if not conv2d_gradfix._should_use_custom_op(x) or not torch.is_grad_enabled():
+        return False
+    if not any(t is not None and t.requires_grad for t in (x, weight, styles, noise)):
+        return False
+    kh, kw = weight.shape[2:]
+    return (up == 1 and down == 1 and kh == kw and isinstance(padding, int) and 0 <= padding <= kh - 1 and
+            x.dtype in (torch.float32, torch.bfloat16) and x.shape[2] * x.shape[3] >= 1)
 
 
 @misc.profiled_function
@@ -91,6 +173,14 @@ def modulated_conv2d(
     if _kernel_path_ok(x, weight, styles, noise, up, down, padding, resample_filter):
         return modulated_conv2d_fused_act(x, weight, styles, noise=noise, up=up, padding=padding,
                                           resample_filter=resample_filter, demodulate=demodulate, flip_weight=flip_weight)
+
+    # ---- sm_100a training path (gradients required, up = 1): the same fused launch as a differentiable Function ----
+    if fused_training and _fused_training_path_ok(x, weight, styles, noise, up, down, padding):
+        dcoefs = None
+        if demodulate:      # d[n,o] = rsqrt(sum_i s[n,i]^2 * sum_k w[o,i,k]^2 + 1e-8): tiny differentiable library ops
+            w2 = weight.to(torch.float32).square().sum(dim=[2, 3])
+            dcoefs = (styles.to(torch.float32).square() @ w2.t() + 1e-8).rsqrt()
+        return _FusedModulatedConv2d.apply(x, weight, styles.to(torch.float32), dcoefs, noise, padding, bool(flip_weight))
 
     # ---- composition path (differentiable; any device): the reference's two formulations ----
     if x.dtype == torch.float16 and demodulate:     # pre-normalise to avoid fp16 overflow

@@ -111,8 +111,10 @@ class Conv2dLayer(torch.nn.Module):
                                               clamp=-1 if act_clamp is None else act_clamp, out_packed=out_packed)
         if fused and self.up == 1 and self.down == 1 and _can_fuse(x, self.weight, self.bias):
             parts = _parts() if isinstance(x, PackedAct) else conv2d_gradfix._PRODUCTS[conv2d_gradfix.precision_for(x.dtype)][1]
-            im2col = (not isinstance(x, PackedAct)) and x.shape[2] >= 8 and x.shape[3] >= 16      # few-channel stems (7x7 RGB, 3x3 on 6 ch)
-            pw = conv2d_gradfix.packed_plain(self.weight, True, parts, self.padding, self.padding, scale=self.weight_gain, allow_im2col=im2col)
+            f16 = (not isinstance(x, PackedAct)) and x.dtype == torch.float16                     # fp16 blocks of the discriminator
+            im2col = (not isinstance(x, PackedAct)) and x.shape[2] >= 8 and x.shape[3] >= 16 and not f16      # few-channel stems (7x7 RGB, 3x3 on 6 ch)
+            pw = conv2d_gradfix.packed_plain(self.weight, True, parts, self.padding, self.padding, scale=self.weight_gain, allow_im2col=im2col,
+                                             f16=f16)
             return conv2d_gradfix.igemm_conv(x, pw, bias=self.bias, act=self.activation,
                                              alpha=bias_act.activation_funcs[self.activation].def_alpha, gain=act_gain,
                                              clamp=-1 if act_clamp is None else act_clamp, out_packed=out_packed, out=out,
@@ -126,7 +128,7 @@ class Conv2dLayer(torch.nn.Module):
             p0 = self.padding + (fw - 2 + 1) // 2
             p1 = self.padding + (fw - 2) // 2
             parts = conv2d_gradfix._PRODUCTS[conv2d_gradfix.precision_for(x.dtype)][1]
-            pw = conv2d_gradfix.packed_plain(self.weight, True, parts, 0, 0, scale=self.weight_gain)
+            pw = conv2d_gradfix.packed_plain(self.weight, True, parts, 0, 0, scale=self.weight_gain, f16=x.dtype == torch.float16)
             epi = dict(bias=self.bias, act=self.activation, alpha=bias_act.activation_funcs[self.activation].def_alpha, gain=act_gain,
                        clamp=-1 if act_clamp is None else act_clamp)
             if k == 1:

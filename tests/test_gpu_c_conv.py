@@ -78,6 +78,102 @@ def test_modulated_conv2d_differentiable_path_matches_golden_and_has_grads():
     assert rel_l2(x.grad, xc.grad) < 1e-5 and rel_l2(w.grad, wc.grad) < 1e-4 and rel_l2(s.grad, sc.grad) < 1e-4
 
 
+TRAIN_CASES = [  # n, ic, oc, k, h, w, demodulate, noise kind, flip_weight
+    (2, 16, 24, 3, 12, 10, True, 'hw', True), (2, 16, 24, 3, 12, 10, True, 'hw', False), (3, 8, 8, 3, 6, 6, True, None, True),
+    (2, 16, 3, 1, 8, 8, False, None, True), (2, 8, 8, 3, 8, 8, True, 'n1hw', True), (1, 70, 40, 3, 20, 36, True, 'hw', True),
+]
+
+
+@pytest.mark.parametrize('prec', ['bf16x2', 'bf16x3'])
+@pytest.mark.parametrize('case', TRAIN_CASES, ids=str)
+def test_fused_differentiable_modulated_conv2d_gradients(case, prec):
+    """training-mode kernel path (_FusedModulatedConv2d): output and the gradients of x, weight, styles and noise against float64
+    autograd of the oracle's formulation; the composition of separate ops (nets.fused_training = False) must agree too"""
+    n, ic, oc, k, h, w, demod, noise_kind, flipw = case
+    cg.fp32_precision = prec
+    g = torch.Generator().manual_seed(61)
+    x0 = torch.randn(n, ic, h, w, generator=g); w0 = torch.randn(oc, ic, k, k, generator=g); s0 = torch.randn(n, ic, generator=g) * 0.5 + 1
+    nz0 = {None: None, 'hw': torch.randn(h, w, generator=g) * 0.1, 'n1hw': torch.randn(n, 1, h, w, generator=g) * 0.1}[noise_kind]
+    probe = torch.randn(n, oc, h, w, generator=g)
+
+    def run(fn, dev, dt):
+        x, wt, s = (v.to(dev, dt).requires_grad_(True) for v in (x0, w0, s0))
+        nz = None if nz0 is None else nz0.to(dev, dt).requires_grad_(True)
+        y = fn(x, wt, s, noise=nz, padding=k // 2, demodulate=demod, flip_weight=flipw, fused_modconv=False)
+        grads = torch.autograd.grad((y * probe.to(dev, dt)).sum() + 0.1 * y.square().sum(), [x, wt, s] + ([nz] if nz is not None else []))
+        return [y] + list(grads)
+
+    want = run(ref_ops.modulated_conv2d, 'cpu', torch.float64)
+    before = custom_ops.launch_count()
+    got = run(nets.modulated_conv2d, DEV, torch.float32)
+    fused_launches = custom_ops.launch_count() - before
+    names = ['y', 'grad_x', 'grad_w', 'grad_s', 'grad_noise']
+    for a, r, name in zip(got, want, names):
+        assert rel_l2(a, r) < 2.5 * TOL[prec], (name, rel_l2(a, r))      # grad_w / grad_s also flow through the demodulation coefficients
+    old = nets.fused_training
+    nets.fused_training = False
+    try:
+        before = custom_ops.launch_count()
+        comp = run(nets.modulated_conv2d, DEV, torch.float32)
+        comp_launches = custom_ops.launch_count() - before
+    finally:
+        nets.fused_training = old
+    for a, b, name in zip(got, comp, names):
+        assert rel_l2(a, b) < 2.5 * TOL[prec], (name, rel_l2(a, b))
+    assert fused_launches <= 12, fused_launches          # pack, GEMM | pack(gy*d), dgrad, reduce, wgrad (+finalize, packs), d-gradient reduce
+
+
+@pytest.mark.parametrize('stride', [1, 2])
+@pytest.mark.parametrize('transpose', [False, True])
+def test_plain_backward_shares_packed_operands_and_matches_the_function_path(stride, transpose):
+    """keep_packed_operands: the forward keeps its packed input for the weight gradient and a plain backward packs grad_output once;
+    identical results to the per-Function path (keep_packed_operands = False), fewer launches"""
+    cg.fp32_precision = 'bf16x2'
+    g = torch.Generator().manual_seed(62)
+    x0 = torch.randn(2, 24, 13, 11, generator=g)
+    w0 = torch.randn(24, 20, 3, 3, generator=g) * 0.2 if transpose else torch.randn(20, 24, 3, 3, generator=g) * 0.2
+    opad = 1 if (transpose and stride == 2) else 0
+    op = (lambda x, w: cg.conv_transpose2d(x, w, stride=stride, padding=1, output_padding=opad)) if transpose else \
+         (lambda x, w: cg.conv2d(x, w, stride=stride, padding=1))
+    res = {}
+    for keep in (True, False):
+        cg.keep_packed_operands = keep
+        try:
+            x, w = x0.to(DEV).requires_grad_(True), w0.to(DEV).requires_grad_(True)
+            y = op(x, w)
+            before = custom_ops.launch_count()
+            gx, gw = torch.autograd.grad(y.square().sum(), [x, w])
+            res[keep] = (gx, gw, custom_ops.launch_count() - before)
+        finally:
+            cg.keep_packed_operands = True
+    assert torch.equal(res[True][0], res[False][0]) and torch.equal(res[True][1], res[False][1])
+    assert res[True][2] < res[False][2], (res[True][2], res[False][2])
+    ref = (torch.nn.functional.conv_transpose2d(x0.double(), w0.double(), stride=stride, padding=1, output_padding=opad) if transpose
+           else torch.nn.functional.conv2d(x0.double(), w0.double(), stride=stride, padding=1))
+    xr, wr = x0.double().requires_grad_(True), w0.double().requires_grad_(True)
+    yr = (torch.nn.functional.conv_transpose2d(xr, wr, stride=stride, padding=1, output_padding=opad) if transpose
+          else torch.nn.functional.conv2d(xr, wr, stride=stride, padding=1))
+    gxr, gwr = torch.autograd.grad(yr.square().sum(), [xr, wr])
+    assert rel_l2(res[True][0], gxr) < 1.25 * TOL['bf16x2'] and rel_l2(res[True][1], gwr) < 1.25 * TOL['bf16x2']
+
+
+@pytest.mark.parametrize('dt', [torch.float16, torch.bfloat16])
+def test_half_precision_layers_run_native_operands(dt):
+    """fp16 tensors (the discriminator's mixed-precision blocks, networks.py:634,647) use IEEE-half operands on the f16 MMA path:
+    forward, data gradient and weight gradient agree with float64 on the SAME rounded inputs to fp16 / bf16 output rounding"""
+    g = torch.Generator().manual_seed(63)
+    x0 = torch.randn(2, 32, 16, 16, generator=g).to(dt); w0 = (torch.randn(48, 32, 3, 3, generator=g) * 0.1).to(dt)
+    x, w = x0.to(DEV).requires_grad_(True), w0.to(DEV).requires_grad_(True)
+    y = cg.conv2d(x, w, padding=1)
+    gx, gw = torch.autograd.grad(y.float().square().sum(), [x, w])
+    xr, wr = x0.double().requires_grad_(True), w0.double().requires_grad_(True)
+    yr = torch.nn.functional.conv2d(xr, wr, padding=1)
+    gxr, gwr = torch.autograd.grad(yr.square().sum(), [xr, wr])
+    eps = 1e-3 if dt == torch.float16 else 8e-3          # one rounding of the output (and of grad_output on the way back)
+    assert y.dtype == dt and gx.dtype == dt and gw.dtype == dt
+    assert rel_l2(y.float(), yr) < eps and rel_l2(gx.float(), gxr) < 2 * eps and rel_l2(gw.float(), gwr) < 2 * eps
+
+
 FP32_MODES = ['bf16x2', 'bf16x3']       # bf16x2 is the mode bench.py runs; both must hold the per-layer bar
 
 

@@ -136,52 +136,6 @@ def test_fma_forward_backward():
     assert torch.autograd.gradcheck(fma.fma, (a, b, c))
 
 
-@pytest.mark.parametrize('parts,tol', [(1, 8e-3), (2, 4e-5), (3, 3e-7)])
-def test_weight_packing_plain_and_split_precision(parts, tol):
-    g = torch.Generator().manual_seed(3)
-    x = torch.randn(2, 20, 9, 11, generator=g)
-    w = torch.randn(24, 20, 3, 3, generator=g)
-    s = torch.randn(2, 20, generator=g) * 0.5 + 1
-    for flip in (True, False):
-        pw = conv2d_gradfix.packed_plain(w, flip, parts, 1, 1)
-        assert pw.c_pad == 64 and pw.o_rows == 32 and pw.data.dtype == torch.bfloat16 and pw.data.shape[0] == parts
-        want = ref_ops.conv2d_resample(x * s.reshape(2, 20, 1, 1), w, padding=1, flip_weight=flip)
-        got = emulate_igemm(x, pw, scale=s)
-        assert rel_l2(got, want) < tol     # bf16 expansion of the WEIGHTS only (activations stay exact here)
-
-
-def test_weight_packing_transposed_layout_and_stride2():
-    g = torch.Generator().manual_seed(4)
-    x = torch.randn(1, 8, 10, 10, generator=g)
-    wt = torch.randn(8, 6, 3, 3, generator=g)       # conv_transpose2d layout [I, O, kh, kw]
-    pw = conv2d_gradfix.packed_plain(wt, False, 3, 2, 2, transpose_io=True)
-    want = ref_ops.conv_transpose2d(x, wt, stride=1, padding=0)
-    assert rel_l2(emulate_igemm(x, pw), want) < 3e-7
-    w = torch.randn(6, 8, 3, 3, generator=g)
-    pw2 = conv2d_gradfix.packed_plain(w, True, 3, 1, 1)
-    assert rel_l2(emulate_igemm(x, pw2, stride=2), ref_ops.conv2d(x, w, stride=2, padding=1)) < 3e-7
-
-
-def test_polyphase_up2_weights_reproduce_transposed_conv_plus_blur():
-    g = torch.Generator().manual_seed(5)
-    f = upfirdn2d.setup_filter([1, 3, 3, 1])
-    x = torch.randn(2, 16, 8, 8, generator=g)
-    w = torch.randn(32, 16, 3, 3, generator=g)
-    for flipw in (False, True):
-        pw = conv2d_gradfix.packed_up2(w, f, flipw, False, 3)
-        assert pw.phases == 4 and pw.o == 32 and pw.o_rows == 128
-        want = ref_ops.conv2d_resample(x, w, f=f, up=2, padding=1, flip_weight=flipw)
-        got = emulate_igemm(x, pw)
-        assert got.shape == want.shape == (2, 32, 16, 16)
-        assert rel_l2(got, want) < 3e-7
-    # asymmetric (non-separable-looking) filter exercises the flip conventions
-    f2 = torch.rand(4, 4, generator=g)
-    pw = conv2d_gradfix.packed_up2(w, f2, False, False, 3)
-    assert rel_l2(emulate_igemm(x, pw), ref_ops.conv2d_resample(x, w, f=f2, up=2, padding=1, flip_weight=False)) < 3e-7
-    pw = conv2d_gradfix.packed_up2(w, f2, False, True, 3)
-    assert rel_l2(emulate_igemm(x, pw), ref_ops.conv2d_resample(x, w, f=f2, up=2, padding=1, flip_weight=False, flip_filter=True)) < 3e-7
-
-
 def test_block_n_choice():
     assert conv2d_gradfix.choose_block_n(3, 10000) == 16
     assert conv2d_gradfix.choose_block_n(64, 10000) == 64
@@ -189,14 +143,16 @@ def test_block_n_choice():
     assert conv2d_gradfix.choose_block_n(512, 16) <= 64       # few pixel tiles -> more column tiles to fill 148 SMs
 
 
-def test_polyphase_weights_with_out_channels_not_multiple_of_16():
-    g = torch.Generator().manual_seed(6)
-    f = upfirdn2d.setup_filter([1, 3, 3, 1])
-    x = torch.randn(1, 8, 6, 6, generator=g)
-    w = torch.randn(24, 8, 3, 3, generator=g)
-    pw = conv2d_gradfix.packed_up2(w, f, False, False, 3)
-    assert pw.phase_stride == 32 and pw.o == 24 and pw.o_rows == 128
-    assert rel_l2(emulate_igemm(x, pw), ref_ops.conv2d_resample(x, w, f=f, up=2, padding=1, flip_weight=False)) < 3e-7
+def test_weight_operand_layout():
+    wl = conv2d_gradfix.weight_layout
+    assert wl(24, 20) == (24, 24, 32, 64)              # rows to the power of two, channels to whole swizzle rows
+    assert wl(512, 513) == (512, 512, 512, 576)
+    assert wl(32, 16, phases=4) == (32, 128, 128, 64)
+    assert wl(24, 8, phases=4) == (32, 128, 128, 64)   # phases start at multiples of 16 columns
+    assert wl(64, 64, phases=4) == (64, 256, 256, 64)
+    assert wl(3, 64) == (3, 3, 16, 64)
+    with pytest.raises(RuntimeError):                   # the packing kernel is the only implementation: CPU tensors are refused
+        conv2d_gradfix.packed_plain(torch.randn(8, 8, 3, 3), True, 2, 1, 1)
 
 
 def test_conv_desc_mirror_matches_c_struct_layout(tmp_path):
