@@ -457,7 +457,8 @@ class SynthesisNetworkFull_v18(torch.nn.Module):
         upper_256 = (half(upper_mask) > 0.9).to(upper_mask.dtype)
         lower_256 = (half(lower_mask) > 0.9).to(upper_mask.dtype)
         feats_packed = spade_feat = None
-        if fused and S._can_fuse(denorm_upper_input) and denorm_upper_input.dtype == torch.float32:
+        if fused and S._can_fuse(denorm_upper_input, self.spade_b256_1.conv.weight, self.spade_encoder[0].weight) and \
+                denorm_upper_input.dtype == torch.float32:     # inference only: in training the SPADE blocks take the differentiable route
             # the masked composition of both branches goes straight into the operand format both SPADE blocks read:
             # feat = (x_u*(1-res_u) + mean_u*res_u)*upper_256 + (x_l*(1-res_l) + mean_l*res_l)*lower_256   (all masks are 0/1)
             conv2d_gradfix._init()

@@ -146,7 +146,8 @@ def test_plain_backward_shares_packed_operands_and_matches_the_function_path(str
             res[keep] = (gx, gw, custom_ops.launch_count() - before)
         finally:
             cg.keep_packed_operands = True
-    assert torch.equal(res[True][0], res[False][0]) and torch.equal(res[True][1], res[False][1])
+    # same kernels on the same operands; the split-K weight gradient accumulates with floating-point atomics (order varies)
+    assert torch.equal(res[True][0], res[False][0]) and rel_l2(res[True][1], res[False][1]) < 1e-6
     assert res[True][2] < res[False][2], (res[True][2], res[False][2])
     ref = (torch.nn.functional.conv_transpose2d(x0.double(), w0.double(), stride=stride, padding=1, output_padding=opad) if transpose
            else torch.nn.functional.conv2d(x0.double(), w0.double(), stride=stride, padding=1))
