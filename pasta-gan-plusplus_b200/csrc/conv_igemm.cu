@@ -32,6 +32,7 @@
 // formulation of training/networks.py:85-93 (algebraically the non-fused form, networks.py:73-82).
 #include <cuda.h>
 #include <stdlib.h>
+#include <atomic>
 #include "act.cuh"
 #include "tc_ptx.cuh"
 
@@ -79,6 +80,9 @@ struct IgemmParams {
     unsigned idesc_stack;               // instruction descriptor with N = 2 * block_n
     int fold_gain;                      // activation is positively homogeneous and gain > 0: gain is folded into scale/shift/noise
     unsigned div_col_m, div_col_s, div_x_m, div_x_s, div_y_m, div_y_s;   // magic numbers for t / tiles_col, / tiles_x, / tiles_y
+    int dbg;                            // PGPP_IGEMM_DEBUG ablation bits (timing experiments only, results are wrong): 1 epilogue without
+                                        // arithmetic / stores, 2 without TMEM loads, 4 no MMAs issued, 8 arithmetic but no stores, 16 stores go to one
+                                        // tile-sized region (no DRAM write traffic), 32 128-bit instead of 256-bit stores of the operand format
 };
 
 
@@ -188,17 +192,20 @@ __device__ __forceinline__ void epilogue_fast(const IgemmParams& p, const TileCo
     const float alpha = p.alpha, clamp = p.clamp, gain = p.gain;
     const unsigned cs = (unsigned)p.os_c;
     const bool nhwc = p.os_c == 1;
-    const int nchunks = (col_end - col_begin) >> 4;
+    const int nchunks = (p.dbg & 2) ? 0 : (col_end - col_begin) >> 4;
+    // 256-bit stores need 32-byte aligned pixels and parts
+    const bool v8_ok = IsBf16<OT>::value && !(p.dbg & 32) && ((uintptr_t)out & 31) == 0 && p.os_w % 16 == 0 && p.os_h % 16 == 0 && p.os_n % 16 == 0 &&
+                       p.out_part_stride % 16 == 0;
     auto process = [&](const uint32_t (&acc)[16], int c0) {
         const int g0 = tc.col0 + c0;
         const int phase = (g0 >= p.phase_stride) + (g0 >= 2 * p.phase_stride) + (g0 >= 3 * p.phase_stride);
         const int oc0 = g0 - phase * p.phase_stride;
-        if (!pix_ok || oc0 >= p.o || phase >= p.phases) return;
+        if (!pix_ok || oc0 >= p.o || phase >= p.phases || (p.dbg & 1)) return;
         const int oy = y * p.up + (phase >> 1), ox = x * p.up + (phase & 1);
         // up = 1: the pixel's noise value was fetched before the accumulator wait (nz_pre); up = 2: it depends on the phase
         float nz = nz_pre;
         if (p.noise && p.phases != 1) nz = __ldg(p.noise + n * p.noise_stride_n + (long long)oy * p.out_w + ox) * gain;
-        const long long base = n * p.os_n + oy * p.os_h + ox * p.os_w;
+        const long long base = (p.dbg & 16) ? pc.py * p.os_h + pc.px * p.os_w : n * p.os_n + oy * p.os_h + ox * p.os_w;
         const int valid = min(16, p.o - oc0);
         // out += result (ToRGB adding into the up-sampled skip image, the residual add of the SPADE block): all 16 loads
         // of the read-modify-write are issued before the arithmetic so that one memory round trip covers the chunk
@@ -219,6 +226,12 @@ __device__ __forceinline__ void epilogue_fast(const IgemmParams& p, const TileCo
             if (A == PGPP_ACT_LRELU) { r0 = fmaxf(r0, r0 * alpha); r1 = fmaxf(r1, r1 * alpha); }    // 0 <= alpha <= 1 (checked on the host)
             if (CLAMP) { r0 = fminf(fmaxf(r0, -clamp), clamp); r1 = fminf(fmaxf(r1, -clamp), clamp); }
             v[j] = r0; v[j + 1] = r1;
+        }
+        if (p.dbg & 8) {
+            float sum = 0.f;
+            #pragma unroll
+            for (int j = 0; j < 16; j++) sum += v[j];
+            if (sum != 1.2345e38f) return;
         }
         if (ACC) {
             // lanes are consecutive pixels: coalesced along W for NCHW tensors
@@ -243,9 +256,16 @@ __device__ __forceinline__ void epilogue_fast(const IgemmParams& p, const TileCo
                             v[2 * j + 1] -= __uint_as_float(w[j] & 0xffff0000u);
                         }
                     }
-                    int4* dst = reinterpret_cast<int4*>(out + part * p.out_part_stride + base + oc0);
-                    dst[0] = make_int4((int)w[0], (int)w[1], (int)w[2], (int)w[3]);
-                    dst[1] = make_int4((int)w[4], (int)w[5], (int)w[6], (int)w[7]);
+                    OT* const dptr = out + part * p.out_part_stride + base + oc0;
+                    if (v8_ok) {
+                        // one 256-bit store: the lane's 16 channels are one full 32-byte sector
+                        asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dptr), "r"(w[0]), "r"(w[1]), "r"(w[2]),
+                                     "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]) : "memory");
+                    } else {
+                        int4* dst = reinterpret_cast<int4*>(dptr);
+                        dst[0] = make_int4((int)w[0], (int)w[1], (int)w[2], (int)w[3]);
+                        dst[1] = make_int4((int)w[4], (int)w[5], (int)w[6], (int)w[7]);
+                    }
                 }
             } else
             for (int part = 0; part < p.out_parts; part++) {
@@ -385,6 +405,138 @@ __device__ __forceinline__ void epilogue_dispatch(const IgemmParams& p, const Ti
 #undef PGPP_EPI
 }
 
+// Lean epilogue for the operand-format hand-over, the configuration almost every large layer of the generator runs in: one sample
+// per tile, gain folded into the staged (scale, shift), bf16 channels-innermost output in 1..3 parts (the next conv's TMA operand),
+// phases == 1, no accumulate, linear / relu / lrelu.  Against the general path: everything tile-invariant is hoisted out of the tile
+// loop, the pixel's noise value of the NEXT tile is fetched before this tile's accumulator wait (its latency was the largest single
+// stall of the general epilogue), 32 columns per TMEM load, one 256-bit store per (16 channels, part).
+// STK: columns [block_n, 2 * block_n) of the accumulator hold a0 x b1 and are added to a0 x b0 + a1 x b0 (see mma_role).
+template <int A, bool STK>
+__device__ __forceinline__ void epilogue_packed_role(const IgemmParams& p, uint32_t bar_base, uint32_t tmem_base, float2* s_params,
+                                                     int warp, int lane) {
+    const uint32_t tfull0 = bar_base + 8u * (2 * p.a_stages + 2 * p.b_stages), tempty0 = tfull0 + 16u;
+    const int quarter = warp & 3, half = (warp - 2) >> 2;
+    const int lane_row = quarter * 32 + lane;
+    const int px = lane_row % p.tw, py = lane_row / p.tw;        // tn == 1
+    const int etid = threadIdx.x - 64;
+    const int block_n = p.block_n, cols_per = block_n >> 1, col_begin = half * cols_per;
+    const float alpha = p.alpha, gain = p.gain;
+    const float cl = p.clamp >= 0.f ? p.clamp : __int_as_float(0x7f800000);      // no clamp: +-inf bounds
+    __nv_bfloat16* const out = (__nv_bfloat16*)p.out;
+    const long long part_stride = p.out_part_stride;
+    const int nparts = p.out_parts;
+    const float* const noise = p.noise;
+    const int conv_w = p.conv_w, conv_h = p.conv_h;
+    const long long total = p.total_tiles;
+    auto noise_at = [&](const TileCoord& c) -> float {
+        const int x = c.x0 + px, y = c.y0 + py;
+        return (noise && x < conv_w && y < conv_h) ? __ldg(noise + c.n0 * p.noise_stride_n + (long long)y * p.out_w + x) : 0.f;
+    };
+    // one 16-column chunk: scale / noise / shift / activation / clamp, bf16 expansion, 256-bit stores
+    auto chunk = [&](const uint32_t* acc, const float2* s_cs, float nz, __nv_bfloat16* dst, bool store) {
+        float v[16];
+        const float4* s_cs4 = reinterpret_cast<const float4*>(s_cs);
+        #pragma unroll
+        for (int j = 0; j < 16; j += 2) {
+            const float4 q = s_cs4[j >> 1];
+            float r0 = fmaf(__uint_as_float(acc[j]), q.x, nz) + q.y;
+            float r1 = fmaf(__uint_as_float(acc[j + 1]), q.z, nz) + q.w;
+            if (A == PGPP_ACT_RELU) { r0 = fmaxf(r0, 0.f); r1 = fmaxf(r1, 0.f); }
+            if (A == PGPP_ACT_LRELU) { r0 = fmaxf(r0, r0 * alpha); r1 = fmaxf(r1, r1 * alpha); }
+            v[j] = fminf(fmaxf(r0, -cl), cl); v[j + 1] = fminf(fmaxf(r1, -cl), cl);
+        }
+        if (p.dbg & 8) {
+            float sum = 0.f;
+            #pragma unroll
+            for (int j = 0; j < 16; j++) sum += v[j];
+            store = store && sum == 1.2345e38f;
+        }
+        if (!store) return;
+        for (int part = 0; part < nparts; part++) {
+            const bool more = part + 1 < nparts;
+            uint32_t w[8];
+            #pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+                w[j] = *reinterpret_cast<const uint32_t*>(&h);
+                if (more) {
+                    v[2 * j] -= __uint_as_float(w[j] << 16);
+                    v[2 * j + 1] -= __uint_as_float(w[j] & 0xffff0000u);
+                }
+            }
+            asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst + part * part_stride), "r"(w[0]), "r"(w[1]),
+                         "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]) : "memory");
+        }
+    };
+    int buf = 0; uint32_t buf_phase = 0;
+    int tag0 = -1, tag1 = -1;
+    long long t = blockIdx.x;
+    TileCoord tc = decode_tile(p, t);
+    float nz_raw = noise_at(tc);
+    while (t < total) {
+        float2* const s_buf = s_params + buf * block_n;
+        const int tag = tc.n0 * p.tiles_col + tc.col0 / block_n;
+        if ((buf ? tag1 : tag0) != tag) {
+            asm volatile("bar.sync 1, 256;" ::: "memory");      // every epilogue warp is done with the tile that last used this buffer
+            if (etid < block_n) {
+                const int oc = tc.col0 + etid;
+                float sc = 1.f, sh = 0.f;
+                if (oc < p.o) {
+                    if (p.dcoef) sc = __ldg(p.dcoef + (long long)tc.n0 * p.o + oc);
+                    if (p.bias) sh = __ldg(p.bias + oc);
+                }
+                s_buf[etid] = make_float2(sc * gain, sh * gain);
+            }
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (buf) tag1 = tag; else tag0 = tag;
+        }
+        // next tile: coordinates and noise value, fetched while this tile's MMAs may still be running
+        const long long t_next = t + gridDim.x;
+        TileCoord tc_next = tc;
+        float nz_next = 0.f;
+        if (t_next < total) { tc_next = decode_tile(p, t_next); nz_next = noise_at(tc_next); }
+        const int x = tc.x0 + px, y = tc.y0 + py;
+        const bool pix_ok = x < conv_w && y < conv_h && !(p.dbg & 1);
+        __nv_bfloat16* const dst = out + tc.n0 * p.os_n + y * p.os_h + x * p.os_w + tc.col0 + col_begin;
+        const float2* const s_cs = s_buf + col_begin;
+        const int o_left = p.o - (tc.col0 + col_begin);                 // valid columns counted from this warp's first column
+        const float nz = nz_raw * gain;
+        mbar_wait(tfull0 + 8u * buf, buf_phase);
+        tc_fence_after();
+        const uint32_t tmem_tile = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * p.acc_cols + col_begin);
+        if (!(p.dbg & 2)) {
+            if (cols_per >= 32) {
+                for (int c0 = 0; c0 < cols_per; c0 += 32) {
+                    uint32_t ra[32];
+                    tmem_ld32_issue(tmem_tile + c0, ra);
+                    if (STK) {
+                        uint32_t rb[32];
+                        tmem_ld32_issue(tmem_tile + block_n + c0, rb);
+                        tmem_ld_wait32(ra);
+                        tmem_ld_wait32(rb);
+                        #pragma unroll
+                        for (int j = 0; j < 32; j++) ra[j] = __float_as_uint(__uint_as_float(ra[j]) + __uint_as_float(rb[j]));
+                    } else {
+                        tmem_ld_wait32(ra);
+                    }
+                    chunk(ra, s_cs + c0, nz, dst + c0, pix_ok && c0 + 16 <= o_left);
+                    chunk(ra + 16, s_cs + c0 + 16, nz, dst + c0 + 16, pix_ok && c0 + 32 <= o_left);
+                }
+            } else {
+                uint32_t ra[16];
+                tmem_ld16_issue(tmem_tile, ra);
+                tmem_ld_wait16(ra);
+                chunk(ra, s_cs, nz, dst, pix_ok && 16 <= o_left);
+            }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty0 + 8u * buf);
+        if (++buf == 2) { buf = 0; buf_phase ^= 1; }
+        t = t_next; tc = tc_next; nz_raw = nz_next;
+    }
+}
+
 struct MmaCtx { uint32_t smem_base, b_base, bar_base, tmem_base; };
 
 // MMA issuer role (warp 1).  The whole warp walks the warp-uniform loop so that descriptors live in uniform registers;
@@ -405,6 +557,7 @@ __device__ __forceinline__ void mma_role(const IgemmParams& p, const MmaCtx mc) 
     const int inner = INNER ? INNER : p.inner;
     const int k_steps = KS ? KS : p.kb / 16;            // tcgen05.mma kind::f16 has K = 16
     const bool leader = elect_one();
+    const bool mma_on = !(p.dbg & 4);
     const uint64_t desc_hi = make_smem_desc(0, p.layout_type, p.sbo_bytes);     // everything but the start address
     const uint32_t slab16 = p.slab_bytes >> 4, ky16 = p.ky_step_bytes >> 4, bpitch16 = p.b_pitch >> 4;
     const uint32_t idesc = p.idesc;
@@ -445,7 +598,7 @@ __device__ __forceinline__ void mma_role(const IgemmParams& p, const MmaCtx mc) 
                         const uint64_t db = desc_hi | (uint64_t)(b16 & 0x3FFF);
                         const uint64_t da0 = desc_hi | (uint64_t)((a16 + j * ky16) & 0x3FFF);
                         const uint64_t da1 = desc_hi | (uint64_t)((a16 + slab16 + j * ky16) & 0x3FFF);
-                        if (leader) {
+                        if (leader && mma_on) {
                             umma_bf16(tmem_d, da0, db, p.idesc_stack, acc);
                             umma_bf16(tmem_d, da0 + 2, db + 2, p.idesc_stack, 1);
                             umma_bf16(tmem_d, da0 + 4, db + 4, p.idesc_stack, 1);
@@ -475,7 +628,7 @@ __device__ __forceinline__ void mma_role(const IgemmParams& p, const MmaCtx mc) 
                         for (int pa = 0; pa < (PARTS ? PARTS : 3); pa++) {
                             if (pa + pb >= parts) break;                    // products a_pa * b_pb with pa + pb < parts
                             const uint64_t da = desc_hi | (uint64_t)((a16 + pa * slab16 + j * ky16) & 0x3FFF);
-                            if (leader) {
+                            if (leader && mma_on) {
                                 if (KS == 4) {
                                     // advance 16 elements (32 bytes) along K inside the swizzle row: +2 in the >>4 address field
                                     umma_bf16(tmem_d, da, db, idesc, acc);
@@ -528,6 +681,7 @@ __device__ __forceinline__ void mma_role_slab(const IgemmParams& p, const MmaCtx
     const int parts = PARTS ? PARTS : p.parts;
     const int taps = TAPS ? TAPS : p.inner;
     const bool leader = elect_one();
+    const bool mma_on = !(p.dbg & 4);
     const uint64_t desc_a_hi = make_smem_desc(0, p.layout_type, p.sbo_a);
     const uint64_t desc_b_hi = make_smem_desc(0, p.layout_type, p.sbo_bytes);
     const uint32_t bpitch16 = p.b_pitch >> 4;
@@ -564,7 +718,7 @@ __device__ __forceinline__ void mma_role_slab(const IgemmParams& p, const MmaCtx
                         // pa == 0: a0 x [b0; b1] (N = 2 * block_n);  pa == 1: a1 x b0 (N = block_n)
                         const uint64_t db = desc_b_hi | (uint64_t)(b_tap16 & 0x3FFF);
                         const uint32_t id = pa == 0 ? p.idesc_stack : idesc;
-                        if (leader) {
+                        if (leader && mma_on) {
                             umma_bf16(tmem_d, da, db, id, acc);
                             umma_bf16(tmem_d, da + 2, db + 2, id, 1);
                             umma_bf16(tmem_d, da + 4, db + 4, id, 1);
@@ -576,7 +730,7 @@ __device__ __forceinline__ void mma_role_slab(const IgemmParams& p, const MmaCtx
                         for (int pb = 0; pb < (PARTS ? PARTS : 3); pb++) {
                             if (pa + pb >= parts) break;
                             const uint64_t db = desc_b_hi | (uint64_t)((b_tap16 + pb * bpitch16) & 0x3FFF);
-                            if (leader) {
+                            if (leader && mma_on) {
                                 umma_bf16(tmem_d, da, db, idesc, acc);
                                 umma_bf16(tmem_d, da + 2, db + 2, idesc, 1);
                                 umma_bf16(tmem_d, da + 4, db + 4, idesc, 1);
@@ -601,6 +755,8 @@ __device__ __forceinline__ void mma_role_slab(const IgemmParams& p, const MmaCtx
     __syncwarp();
 }
 
+// EPI 0: every epilogue option;  EPI 1: the lean operand-format epilogue only (epilogue_packed_role; smaller code and register footprint)
+template <int EPI>
 __global__ void __launch_bounds__(kThreads, 1)
 igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const IgemmParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -737,6 +893,17 @@ igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
         else if (ks == 4 && p.inner == 1 && p.parts == 2) { if (res) mma_role<2, 1, 4, true>(p, mc); else mma_role<2, 1, 4, false>(p, mc); }
         else if (res) mma_role<0, 0, 0, true>(p, mc);
         else mma_role<0, 0, 0, false>(p, mc);
+    } else if (EPI == 1) {
+        // ===================== epilogue warps, operand-format hand-over =====================
+        if (p.stack) {
+            if (p.act_fn == PGPP_ACT_LINEAR) epilogue_packed_role<PGPP_ACT_LINEAR, true>(p, bar_base, tmem_base, s_params, warp, lane);
+            else if (p.act_fn == PGPP_ACT_RELU) epilogue_packed_role<PGPP_ACT_RELU, true>(p, bar_base, tmem_base, s_params, warp, lane);
+            else epilogue_packed_role<PGPP_ACT_LRELU, true>(p, bar_base, tmem_base, s_params, warp, lane);
+        } else {
+            if (p.act_fn == PGPP_ACT_LINEAR) epilogue_packed_role<PGPP_ACT_LINEAR, false>(p, bar_base, tmem_base, s_params, warp, lane);
+            else if (p.act_fn == PGPP_ACT_RELU) epilogue_packed_role<PGPP_ACT_RELU, false>(p, bar_base, tmem_base, s_params, warp, lane);
+            else epilogue_packed_role<PGPP_ACT_LRELU, false>(p, bar_base, tmem_base, s_params, warp, lane);
+        }
     } else {
         // ===================== epilogue warps =====================
         const int quarter = warp & 3;                       // TMEM lane quarter this warp may access
@@ -983,6 +1150,7 @@ extern "C" int pgpp_conv2d_igemm(const pgpp_conv_desc* d, void* stream) {
     magic((unsigned)p.tiles_x, p.div_x_m, p.div_x_s);
     magic((unsigned)p.tiles_y, p.div_y_m, p.div_y_s);
     PGPP_REQUIRE(p.total_tiles < (1ll << 31), "too many tiles");
+    { const char* e = getenv("PGPP_IGEMM_DEBUG"); p.dbg = e ? atoi(e) : 0; }
 
     // tensor maps
     CUtensorMap map_a, map_b;
@@ -1006,20 +1174,26 @@ extern "C" int pgpp_conv2d_igemm(const pgpp_conv_desc* d, void* stream) {
                    CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(weights) failed with CUresult %d", (int)r); return PGPP_ERR_CUDA; }
     }
+    // lean operand-format epilogue (EPI 1) when the launch needs nothing else
+    const bool epi_packed = p.tn == 1 && p.fold_gain && d->out_dtype == PGPP_BF16 && p.os_c == 1 && d->phases == 1 && !d->accumulate && !d->spade_x &&
+                            d->o % 16 == 0 && d->block_n >= 32 && ((uintptr_t)d->out & 31) == 0 && p.os_w % 16 == 0 && p.os_h % 16 == 0 &&
+                            p.os_n % 16 == 0 && p.out_part_stride % 16 == 0 && !getenv("PGPP_IGEMM_NO_LEAN_EPILOGUE");
     {
         // once per device (the attribute is per function per context)
-        static bool done[64] = {false};
+        static std::atomic<bool> done[64];
         int dev = 0;
         cudaGetDevice(&dev);
-        if (dev < 0 || dev >= 64 || !done[dev]) {
-            PGPP_CUDA_OK(cudaFuncSetAttribute(igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-            if (dev >= 0 && dev < 64) done[dev] = true;
+        if (dev < 0 || dev >= 64 || !done[dev].load(std::memory_order_acquire)) {
+            PGPP_CUDA_OK(cudaFuncSetAttribute(igemm_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            PGPP_CUDA_OK(cudaFuncSetAttribute(igemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            if (dev >= 0 && dev < 64) done[dev].store(true, std::memory_order_release);
         }
     }
     long long grid = p.total_tiles;
     const int sms = sm_count();
     if (grid > sms) grid = sms;
-    igemm_kernel<<<(unsigned)grid, kThreads, smem_bytes, (cudaStream_t)stream>>>(map_a, map_b, p);
+    if (epi_packed) igemm_kernel<1><<<(unsigned)grid, kThreads, smem_bytes, (cudaStream_t)stream>>>(map_a, map_b, p);
+    else igemm_kernel<0><<<(unsigned)grid, kThreads, smem_bytes, (cudaStream_t)stream>>>(map_a, map_b, p);
     count_launch();
     PGPP_CUDA_OK(cudaGetLastError());
     return PGPP_OK;
