@@ -233,6 +233,16 @@ PGPP_API int pgpp_conv2d_direct(const float* x, const float* w, const float* bia
 PGPP_API int pgpp_fir_pack(const float* x, const int64_t size[4], const int64_t stride[4], const float* f_host, int fw, int fh,
                   int padx0, int padx1, int pady0, int pady1, int flip, float gain, void* out, int c_pad, int parts, void* stream);
 
+/* upfirdn2d with up = 1 on the operand format, packed -> packed (the blur of "blur, then strided convolution", conv2d_resample.py:119-122,
+ * and the FIR decimation before a 1x1 down-sampling convolution, :107-110, for inputs whose producer already wrote the operand format):
+ *   out = split_bf16( gain * sum_{jy,jx} X[n][oy*down + jy - pady0][ox*down + jx - padx0][c] * k[jy][jx] ),  X = sum of the input parts,
+ * k = f flipped unless `flip` (upfirdn2d.py:193-196).  in: bf16 [in_parts][N][H][W][in_c_total] (pointer at the first of the c channels),
+ * out: bf16 [out_parts][N][H'][W'][out_c_total], H' = (H + pady0 + pady1 - fh) / down + 1.  c % 8 == 0, filter at most 4 x 4 (HOST array
+ * of fh * fw taps, NULL = the identity for fw * fh == 1: a channel-slice copy), down 1 or 2. */
+PGPP_API int pgpp_fir_packed(const void* in, int in_parts, int64_t in_part_stride, int n, int h, int w, int c, int in_c_total,
+                    const float* f_host, int fw, int fh, int down, int padx0, int padx1, int pady0, int pady1, int flip, float gain,
+                    void* out, int out_parts, int64_t out_part_stride, int out_c_total, void* stream);
+
 /* ---- weight gradient (conv2d_gradfix.py:135-142, Conv2dGradWeight.forward: replaces
  * aten::cudnn_convolution_backward_weight / cudnn_convolution_transpose_backward_weight) ----
  *

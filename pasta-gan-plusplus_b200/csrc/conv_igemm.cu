@@ -411,7 +411,9 @@ __device__ __forceinline__ void epilogue_dispatch(const IgemmParams& p, const Ti
 // loop, the pixel's noise value of the NEXT tile is fetched before this tile's accumulator wait (its latency was the largest single
 // stall of the general epilogue), 32 columns per TMEM load, one 256-bit store per (16 channels, part).
 // STK: columns [block_n, 2 * block_n) of the accumulator hold a0 x b1 and are added to a0 x b0 + a1 x b0 (see mma_role).
-template <int A, bool STK>
+// ACC: out += result on the operand format (the residual adds y = skip + conv1(...) of ResBlock / Spade_ResBlockV4_512 without
+// leaving the format): the parts already stored are summed, the result added and the bf16 expansion written back.
+template <int A, bool STK, bool ACC>
 __device__ __forceinline__ void epilogue_packed_role(const IgemmParams& p, uint32_t bar_base, uint32_t tmem_base, float2* s_params,
                                                      int warp, int lane) {
     const uint32_t tfull0 = bar_base + 8u * (2 * p.a_stages + 2 * p.b_stages), tempty0 = tfull0 + 16u;
@@ -452,6 +454,24 @@ __device__ __forceinline__ void epilogue_packed_role(const IgemmParams& p, uint3
             store = store && sum == 1.2345e38f;
         }
         if (!store) return;
+        if (ACC) {
+            uint32_t prev[3][8];
+            #pragma unroll
+            for (int part = 0; part < 3; part++)
+                if (part < nparts)
+                asm volatile("ld.global.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];" : "=r"(prev[part][0]), "=r"(prev[part][1]), "=r"(prev[part][2]),
+                             "=r"(prev[part][3]), "=r"(prev[part][4]), "=r"(prev[part][5]), "=r"(prev[part][6]), "=r"(prev[part][7])
+                             : "l"(dst + part * part_stride) : "memory");
+            #pragma unroll
+            for (int part = 2; part >= 0; part--) {                 // smallest part first
+                if (part >= nparts) continue;
+                #pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    v[2 * j] += __uint_as_float(prev[part][j] << 16);
+                    v[2 * j + 1] += __uint_as_float(prev[part][j] & 0xffff0000u);
+                }
+            }
+        }
         for (int part = 0; part < nparts; part++) {
             const bool more = part + 1 < nparts;
             uint32_t w[8];
@@ -895,15 +915,15 @@ igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
         else mma_role<0, 0, 0, false>(p, mc);
     } else if (EPI == 1) {
         // ===================== epilogue warps, operand-format hand-over =====================
-        if (p.stack) {
-            if (p.act_fn == PGPP_ACT_LINEAR) epilogue_packed_role<PGPP_ACT_LINEAR, true>(p, bar_base, tmem_base, s_params, warp, lane);
-            else if (p.act_fn == PGPP_ACT_RELU) epilogue_packed_role<PGPP_ACT_RELU, true>(p, bar_base, tmem_base, s_params, warp, lane);
-            else epilogue_packed_role<PGPP_ACT_LRELU, true>(p, bar_base, tmem_base, s_params, warp, lane);
-        } else {
-            if (p.act_fn == PGPP_ACT_LINEAR) epilogue_packed_role<PGPP_ACT_LINEAR, false>(p, bar_base, tmem_base, s_params, warp, lane);
-            else if (p.act_fn == PGPP_ACT_RELU) epilogue_packed_role<PGPP_ACT_RELU, false>(p, bar_base, tmem_base, s_params, warp, lane);
-            else epilogue_packed_role<PGPP_ACT_LRELU, false>(p, bar_base, tmem_base, s_params, warp, lane);
-        }
+#define PGPP_PACKED(ACT) \
+        if (p.accumulate) { if (p.stack) epilogue_packed_role<ACT, true, true>(p, bar_base, tmem_base, s_params, warp, lane);   \
+                            else         epilogue_packed_role<ACT, false, true>(p, bar_base, tmem_base, s_params, warp, lane); } \
+        else              { if (p.stack) epilogue_packed_role<ACT, true, false>(p, bar_base, tmem_base, s_params, warp, lane);  \
+                            else         epilogue_packed_role<ACT, false, false>(p, bar_base, tmem_base, s_params, warp, lane); }
+        if (p.act_fn == PGPP_ACT_LINEAR) { PGPP_PACKED(PGPP_ACT_LINEAR) }
+        else if (p.act_fn == PGPP_ACT_RELU) { PGPP_PACKED(PGPP_ACT_RELU) }
+        else { PGPP_PACKED(PGPP_ACT_LRELU) }
+#undef PGPP_PACKED
     } else {
         // ===================== epilogue warps =====================
         const int quarter = warp & 3;                       // TMEM lane quarter this warp may access
@@ -1006,9 +1026,9 @@ extern "C" int pgpp_conv2d_igemm(const pgpp_conv_desc* d, void* stream) {
     PGPP_REQUIRE(((uintptr_t)d->act & 15) == 0 && ((uintptr_t)d->wgt & 15) == 0, "packed operands must be 16-byte aligned");
     const int out_parts = d->out_parts <= 0 ? 1 : d->out_parts;
     PGPP_REQUIRE(out_parts <= 3, "out_parts must be 1, 2 or 3");
-    PGPP_REQUIRE(out_parts == 1 || (d->out_dtype == PGPP_BF16 && d->out_stride[1] == 1 && !d->accumulate && d->o % 16 == 0 &&
+    PGPP_REQUIRE(out_parts == 1 || (d->out_dtype == PGPP_BF16 && d->out_stride[1] == 1 && d->o % 16 == 0 &&
                                     d->out_stride[3] % 8 == 0 && d->out_part_stride % 8 == 0 && ((uintptr_t)d->out & 15) == 0),
-                 "split output needs bf16, channels-innermost, 16-byte aligned pixels, out channels % 16 == 0, no accumulate");
+                 "split output needs bf16, channels-innermost, 16-byte aligned pixels, out channels % 16 == 0");
     const int pix_stride = d->act_pixel_stride > 0 ? d->act_pixel_stride : d->c_pad;
     PGPP_REQUIRE(pix_stride >= d->c_pad && pix_stride % 8 == 0, "act_pixel_stride must be >= c_pad and a multiple of 8");
     const int up = d->phases == 4 ? 2 : 1;
@@ -1175,7 +1195,7 @@ extern "C" int pgpp_conv2d_igemm(const pgpp_conv_desc* d, void* stream) {
         if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(weights) failed with CUresult %d", (int)r); return PGPP_ERR_CUDA; }
     }
     // lean operand-format epilogue (EPI 1) when the launch needs nothing else
-    const bool epi_packed = p.tn == 1 && p.fold_gain && d->out_dtype == PGPP_BF16 && p.os_c == 1 && d->phases == 1 && !d->accumulate && !d->spade_x &&
+    const bool epi_packed = p.tn == 1 && p.fold_gain && d->out_dtype == PGPP_BF16 && p.os_c == 1 && d->phases == 1 && !d->spade_x &&
                             d->o % 16 == 0 && d->block_n >= 32 && ((uintptr_t)d->out & 31) == 0 && p.os_w % 16 == 0 && p.os_h % 16 == 0 &&
                             p.os_n % 16 == 0 && p.out_part_stride % 16 == 0 && !getenv("PGPP_IGEMM_NO_LEAN_EPILOGUE");
     {
@@ -1192,6 +1212,9 @@ extern "C" int pgpp_conv2d_igemm(const pgpp_conv_desc* d, void* stream) {
     long long grid = p.total_tiles;
     const int sms = sm_count();
     if (grid > sms) grid = sms;
+    PGPP_REQUIRE(epi_packed || out_parts == 1 || !d->accumulate,
+                 "accumulating into a split (operand-format) output needs the lean epilogue: one sample per tile, linear / relu / lrelu with gain > 0, "
+                 "32-byte aligned pixels, block_n >= 32, phases == 1");
     if (epi_packed) igemm_kernel<1><<<(unsigned)grid, kThreads, smem_bytes, (cudaStream_t)stream>>>(map_a, map_b, p);
     else igemm_kernel<0><<<(unsigned)grid, kThreads, smem_bytes, (cudaStream_t)stream>>>(map_a, map_b, p);
     count_launch();

@@ -97,6 +97,9 @@ def load_library():
     lib.pgpp_mix_pack.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp]
     lib.pgpp_fir_pack.restype = i32
     lib.pgpp_fir_pack.argtypes = [vp, c_i64x4, c_i64x4, ctypes.POINTER(ctypes.c_float), i32, i32, i32, i32, i32, i32, i32, f32, vp, i32, i32, vp]
+    lib.pgpp_fir_packed.restype = i32
+    lib.pgpp_fir_packed.argtypes = [vp, i32, i64, i32, i32, i32, i32, i32, ctypes.POINTER(ctypes.c_float), i32, i32, i32, i32, i32, i32, i32, i32, f32,
+                                    vp, i32, i64, i32, vp]
     lib.pgpp_conv2d_direct.restype = i32
     lib.pgpp_conv2d_direct.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, f32, i32, f32, f32, f32, vp, vp, i32, i32, i32, vp]
     lib.pgpp_conv2d_igemm.restype = i32
@@ -118,7 +121,7 @@ def load_library():
 EXPORTED_SYMBOLS = ('pgpp_version', 'pgpp_last_error', 'pgpp_launch_count', 'pgpp_bias_act', 'pgpp_upfirdn2d',
                     'pgpp_modconv_demod_coefs', 'pgpp_pack_activations', 'pgpp_pack_activations_slice', 'pgpp_pack_activations_f16',
                     'pgpp_pack_weights', 'pgpp_up2_weight_adjoint', 'pgpp_mul_reduce_hw', 'pgpp_modulate_weights',
-                    'pgpp_spade_modulate_pack', 'pgpp_mix_pack', 'pgpp_conv2d_direct', 'pgpp_fir_pack', 'pgpp_pack_im2col', 'pgpp_conv2d_igemm', 'pgpp_conv2d_wgrad', 'pgpp_u8_to_f32',
+                    'pgpp_spade_modulate_pack', 'pgpp_mix_pack', 'pgpp_conv2d_direct', 'pgpp_fir_pack', 'pgpp_fir_packed', 'pgpp_pack_im2col', 'pgpp_conv2d_igemm', 'pgpp_conv2d_wgrad', 'pgpp_u8_to_f32',
                     'pgpp_image_to_u8', 'pgpp_grid_sample_2d', 'pgpp_grid_sample_2d_backward')
 
 
@@ -447,6 +450,28 @@ class _ConvPlugin:
             _check(lib.pgpp_fir_pack(_ptr(x), c_i64x4(*x.shape), c_i64x4(*x.stride()), f, fw, fh, int(padx0), int(padx1), int(pady0), int(pady1),
                                      int(bool(flip)), float(gain), _ptr(out), int(c_pad), int(parts), _stream(x)))
         return out
+
+    @staticmethod
+    def fir_packed(src, c, c_off, taps, fw, fh, down, padx0, padx1, pady0, pady1, flip, gain, dst=None, dst_c_off=0, parts=None):
+        """upfirdn2d (up = 1, down 1 or 2, filter at most 4 x 4 given as a host list, None = identity) on the operand format: channels
+        [c_off, c_off + c) of `src` (bf16 [parts, N, H, W, c_total]) -> channels [dst_c_off, dst_c_off + c) of `dst` (allocated with
+        c rounded up to whole 64-channel rows when None); see pgpp_fir_packed"""
+        lib = load_library()
+        _torch_check(src.is_cuda and src.dtype == torch.bfloat16 and src.dim() == 5 and src.is_contiguous(), 'fir_packed: src must be a contiguous bf16 [parts,N,H,W,C] tensor')
+        sp, n, h, w, ct = src.shape
+        oh, ow = (h + pady0 + pady1 - fh) // down + 1, (w + padx0 + padx1 - fw) // down + 1
+        _torch_check(oh >= 1 and ow >= 1 and (taps is None or len(taps) == fw * fh), 'fir_packed: bad filter / padding')
+        if dst is None:
+            c_alloc = -(-c // 64) * 64
+            alloc = torch.empty if c_alloc == c else torch.zeros
+            dst = alloc([parts or sp, n, oh, ow, c_alloc], dtype=torch.bfloat16, device=src.device)
+        _torch_check(dst.dtype == torch.bfloat16 and dst.is_contiguous() and tuple(dst.shape[1:4]) == (n, oh, ow), 'fir_packed: dst has the wrong shape')
+        f = None if taps is None else (ctypes.c_float * (fw * fh))(*[float(t) for t in taps])
+        with torch.cuda.device(src.device):
+            _check(lib.pgpp_fir_packed(src.data_ptr() + 2 * c_off, int(sp), int(src[0].numel()), n, h, w, int(c), int(ct), f, int(fw), int(fh), int(down),
+                                       int(padx0), int(padx1), int(pady0), int(pady1), int(bool(flip)), float(gain),
+                                       dst.data_ptr() + 2 * dst_c_off, int(dst.shape[0]), int(dst[0].numel()), int(dst.shape[4]), _stream(src)))
+        return dst
 
     @staticmethod
     def mix_pack(terms, c_pad, parts):

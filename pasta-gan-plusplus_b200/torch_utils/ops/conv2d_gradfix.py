@@ -322,6 +322,40 @@ def packed_up2(weight, f, flip_weight, flip_filter, parts):
     return _cached(weight, ('up2', bool(flip_weight), bool(flip_filter), parts), build, also=(f,))
 
 
+_host_filter_cache = dict()     # id(filter tensor) -> (weakref, (data_ptr, _version), (taps, fw, fh))
+
+
+def host_filter(f):
+    """(taps, fw, fh) of a FIR filter tensor as host floats (one device -> host copy per filter tensor, first use only); a 1-D
+    filter is the separable pair, i.e. its outer product (upfirdn2d.py:103-106)"""
+    key = id(f)
+    hit = _host_filter_cache.get(key)
+    if hit is not None and hit[0]() is f and hit[1] == (f.data_ptr(), f._version):
+        return hit[2]
+    ff = f.detach().to(torch.float32).cpu()
+    if ff.ndim == 1:
+        ff = ff.ger(ff)
+    assert ff.ndim == 2 and ff.shape[0] <= 4 and ff.shape[1] <= 4, 'the operand-format FIR takes filters of at most 4 x 4 taps'
+    val = ([float(v) for v in ff.reshape(-1)], int(ff.shape[1]), int(ff.shape[0]))
+    _host_filter_cache[key] = (weakref.ref(f, lambda _r, key=key: _host_filter_cache.pop(key, None)), (f.data_ptr(), f._version), val)
+    return val
+
+
+def fir_packed(xp, f, down=1, padding=(0, 0, 0, 0), flip_filter=False, gain=1.0, out=None):
+    """`upfirdn2d(x, f, down=down, padding=[padx0, padx1, pady0, pady1], flip_filter=..., gain=...)` on a PackedAct, result as a
+    PackedAct (`out`: PackedAct view to write into, else a new buffer): the blur / decimation in front of a down-sampling convolution
+    (conv2d_resample.py:107-110, 119-122) without leaving the operand format.  f=None copies the channel slice."""
+    _init()
+    taps, fw, fh = (None, 1, 1) if f is None else host_filter(f)
+    px0, px1, py0, py1 = (int(v) for v in padding)
+    if out is None:
+        data = _plugin.fir_packed(xp.data, xp.c, xp.c_off, taps, fw, fh, down, px0, px1, py0, py1, flip_filter, gain)
+        return PackedAct(data, xp.c)
+    assert out.c == xp.c
+    _plugin.fir_packed(xp.data, xp.c, xp.c_off, taps, fw, fh, down, px0, px1, py0, py1, flip_filter, gain, dst=out.data, dst_c_off=out.c_off)
+    return out
+
+
 # ------------------------------------------------------------------------------------------------
 # the kernel launch
 
@@ -385,7 +419,7 @@ def igemm_conv(x, pw, *, scale=None, stride=1, out_hw=None, dcoef=None, noise=No
     out_h, out_w = conv_h * up, conv_w * up
     if out_packed is not None:
         assert tuple(out_packed.data.shape[1:4]) == (n, out_h, out_w) and out_packed.c == (pw.o // 2 if spade is not None else pw.o)
-        assert pw.o % 16 == 0 and out_packed.c_off % 8 == 0 and not accumulate
+        assert pw.o % 16 == 0 and out_packed.c_off % 8 == 0
         c_total = out_packed.data.shape[4]
         d.out = out_packed.data.data_ptr() + 2 * out_packed.c_off
         d.out_dtype = custom_ops.dtype_code(torch.bfloat16)

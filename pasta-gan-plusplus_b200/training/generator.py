@@ -86,7 +86,9 @@ class ResBlock(torch.nn.Module):
         self.conv1 = Conv2dLayer(out_channels, out_channels, kernel_size=3, activation=activation, bias=bias, **kw)
         self.skip = Conv2dLayer(in_channels, out_channels, kernel_size=1, bias=False, up=up, down=down, **kw)
 
-    def forward(self, x, fused=True, impl='cuda'):
+    def forward(self, x, fused=True, impl='cuda', out_packed=False):
+        """`out_packed=True` (fused route): the block's result stays in the operand format (PackedAct) - the skip convolution writes it
+        and conv1 adds into it in place - for a consumer that is another convolution."""
         if fused and self.conv0.up == 1 and S._can_fuse(x, self.conv0.weight, self.conv1.weight, self.skip.weight) and \
                 (isinstance(x, PackedAct) or x.dtype == torch.float32) and self.conv0.weight.shape[0] % 16 == 0:
             # hand-over route: x is packed once for skip and conv0, conv0 writes conv1's operand format, conv1 adds into y
@@ -95,11 +97,22 @@ class ResBlock(torch.nn.Module):
                 conv2d_gradfix._init()
                 c = x.shape[1]
                 x = PackedAct(conv2d_gradfix._plugin.pack_activations(x, None, -(-c // 64) * 64, parts), c)
-            y = self.skip(x, gain=SQRT_HALF, fused=True)
-            n, oc, h, w = y.shape
-            hp = PackedAct(PackedAct.empty(n, h, w, oc, parts, y.device), oc)
+            n, _, h, w = x.shape
+            oc = self.conv0.weight.shape[0]
+            h, w = h // self.conv0.down, w // self.conv0.down
+            dev = x.device
+            if out_packed:
+                y = PackedAct(PackedAct.empty(n, h, w, oc, parts, dev), oc)
+                self.skip(x, gain=SQRT_HALF, fused=True, out_packed=y)
+            else:
+                y = self.skip(x, gain=SQRT_HALF, fused=True)
+                assert tuple(y.shape) == (n, oc, h, w)
+            hp = PackedAct(PackedAct.empty(n, h, w, oc, parts, dev), oc)
             self.conv0(x, fused=True, out_packed=hp)
-            self.conv1(hp, gain=SQRT_HALF, fused=True, out=y, accumulate=True)
+            if out_packed:
+                self.conv1(hp, gain=SQRT_HALF, fused=True, out_packed=y, accumulate=True)
+            else:
+                self.conv1(hp, gain=SQRT_HALF, fused=True, out=y, accumulate=True)
             return y
         y = self.skip(x, gain=SQRT_HALF, fused=fused, impl=impl)
         x = self.conv0(x, fused=fused, impl=impl)
@@ -117,9 +130,35 @@ class ConstEncoderNetwork(torch.nn.Module):
         self.model = torch.nn.ModuleList(layers)
 
     def forward(self, x, fused=True, impl='cuda'):
+        if fused and torch.is_tensor(x) and x.dtype == torch.float32 and x.shape[2] % (1 << (len(self.model) - 1)) == 0 and \
+                x.shape[3] % (1 << (len(self.model) - 1)) == 0 and S._can_fuse(x, *[l.weight for l in self.model]):
+            # operand-format hand-over through the whole chain: every convolution writes the bf16 expansion the next one reads, the
+            # blur in front of each strided convolution runs on that format; only the last (8 x 8) map is an NCHW tensor
+            x = _packed_chain(self.model, x)[-1]
+            return x
         for layer in self.model:
             x = layer(x, fused=fused, impl=impl)
         return x
+
+
+def _packed_chain(layers, x, tensor_last=True):
+    """Run a chain of Conv2dLayers (stride 1 or down=2) in operand-format hand-over mode; returns every layer's output (PackedAct; the
+    last one an NCHW float32 tensor when `tensor_last`)."""
+    outs = []
+    n, _, h, w = x.shape
+    parts = S._parts()
+    for i, layer in enumerate(layers):
+        oc = layer.weight.shape[0]
+        h, w = h // layer.down, w // layer.down
+        if tensor_last and i == len(layers) - 1:
+            x = layer(x, fused=True)
+            assert tuple(x.shape) == (n, oc, h, w)
+        else:
+            out = PackedAct(PackedAct.empty(n, h, w, oc, parts, x.device), oc)
+            layer(x, fused=True, out_packed=out)
+            x = out
+        outs.append(x)
+    return outs
 
 
 class Dense(torch.nn.Module):
@@ -151,10 +190,16 @@ class StyleEncoderNetworkV18(torch.nn.Module):
         self.feat_enc = torch.nn.ModuleList(feat)
 
     def forward(self, x, const_input, fused=True, impl='cuda'):
-        const_feats = []
-        for layer in self.feat_enc:
-            const_input = layer(const_input, fused=fused, impl=impl)
-            const_feats.append(const_input)
+        if fused and torch.is_tensor(const_input) and const_input.dtype == torch.float32 and const_input.shape[2] % 8 == 0 and \
+                const_input.shape[3] % 8 == 0 and S._can_fuse(const_input, *[l.weight for l in self.feat_enc]):
+            # hand-over chain; the 512 / 256 / 128 pixel maps stay in the operand format (the synthesis blocks copy them as channel
+            # slices into their concat buffers), the last (64 pixel) one is consumed as a tensor by the unpacked b64 block
+            const_feats = _packed_chain(self.feat_enc, const_input)
+        else:
+            const_feats = []
+            for layer in self.feat_enc:
+                const_input = layer(const_input, fused=fused, impl=impl)
+                const_feats.append(const_input)
         for layer in self.model:
             x = layer(x, fused=fused, impl=impl) if isinstance(layer, Conv2dLayer) else layer(x)
         return self.fc(x.view(x.size(0), -1), impl=impl), const_feats
@@ -271,8 +316,9 @@ class Spade_ResBlockV4_512(torch.nn.Module):
         var, mean = torch.var_mean(x, dim=(2, 3), unbiased=False)
         return mean, (var + 1e-5).rsqrt()
 
-    def forward(self, x, denorm_feat, fused=True, impl='cuda', feats_packed=None):
-        if fused and torch.is_tensor(x) and x.dtype == torch.float32 and S._can_fuse(x, self.conv.weight):
+    def forward(self, x, denorm_feat, fused=True, impl='cuda', feats_packed=None, out_packed=False):
+        """x: tensor or (fused route) PackedAct; `out_packed=True` (fused route): the result stays in the operand format."""
+        if fused and (isinstance(x, PackedAct) or (torch.is_tensor(x) and x.dtype == torch.float32)) and S._can_fuse(x, self.conv.weight):
             # fused SPADE route: per block 1 + 3 x (conv_mlp, gamma|beta GEMM with the SPADE epilogue, consuming conv) = 10 GEMM launches,
             # one packing pass for the block input and 2 statistics reductions
             relu_gain = float(bias_act.activation_funcs['relu'].def_gain)
@@ -288,12 +334,23 @@ class Spade_ResBlockV4_512(torch.nn.Module):
                     feats_packed = PackedAct(data, r * 3 * fc, 0, logical_hw=(fh, fw))
                 else:
                     feats_packed = PackedAct(conv2d_gradfix._plugin.pack_activations(denorm_feat, None, -(-fc // 64) * 64, S._parts()), fc)
-            x = self.conv(x, no_act=True, fused=True).contiguous()
+            x = (self.conv.conv_packed(x) if isinstance(x, PackedAct) else self.conv(x, no_act=True, fused=True)).contiguous()
             mean, rstd = self._stats(x)
-            y = self.skip.conv_packed(self.spade_skip.fused_packed(x, mean, rstd, feats_packed, relu_gain * SQRT_HALF))
+            xs = self.spade_skip.fused_packed(x, mean, rstd, feats_packed, relu_gain * SQRT_HALF)
+            if out_packed:
+                n, _, h, w = x.shape
+                oc = self.skip.weight.shape[0]
+                y = PackedAct(PackedAct.empty(n, h, w, oc, S._parts(), x.device), oc)
+                self.skip.conv_packed(xs, out_packed=y)
+            else:
+                y = self.skip.conv_packed(xs)
             x = self.conv0.conv_packed(self.spade0.fused_packed(x, mean, rstd, feats_packed, relu_gain)).contiguous()
             mean, rstd = self._stats(x)
-            self.conv1.conv_packed(self.spade1.fused_packed(x, mean, rstd, feats_packed, relu_gain * SQRT_HALF), out=y, accumulate=True)
+            xs = self.spade1.fused_packed(x, mean, rstd, feats_packed, relu_gain * SQRT_HALF)
+            if out_packed:
+                self.conv1.conv_packed(xs, out_packed=y, accumulate=True)
+            else:
+                self.conv1.conv_packed(xs, out=y, accumulate=True)
             return y
         kw = dict(fused=fused, impl=impl)
         x = self.conv(x, no_act=True, **kw)
@@ -336,7 +393,7 @@ class SynthesisBlockFull(torch.nn.Module):
         (`use_fp16=False`, networks.py:2223)."""
         w_iter = iter(ws.unbind(dim=1))
         has_spade = hasattr(self, 'spade_b512')
-        want_tensor = export_tensor or has_spade
+        want_tensor = export_tensor
         if self.in_channels == 0:
             x = self.conv1(pose_feature.to(torch.float32), next(w_iter), fused=fused, impl=impl, **layer_kwargs)
         elif fused and self.resolution >= S.PACKED_MIN_RES and S._can_fuse(x, self.conv0.weight, self.conv1.weight) and \
@@ -348,7 +405,10 @@ class SynthesisBlockFull(torch.nn.Module):
             mc = cf.shape[1]
             buf = PackedAct.empty(n, res, res, oc + mc, parts, dev)
             conv2d_gradfix._init()
-            conv2d_gradfix._plugin.pack_activations_into(cf, None, buf, mc, oc)
+            if isinstance(cf, PackedAct):       # produced in the operand format by the style encoder: channel-slice copy
+                conv2d_gradfix.fir_packed(cf, None, out=PackedAct(buf, mc, oc))
+            else:
+                conv2d_gradfix._plugin.pack_activations_into(cf, None, buf, mc, oc)
             self.conv1(xa, next(w_iter), fused=True, out_packed=PackedAct(buf, oc, 0), **layer_kwargs)
             if want_tensor:
                 x = self.merge_conv(PackedAct(buf, oc + mc, 0), fused=True)
@@ -359,10 +419,11 @@ class SynthesisBlockFull(torch.nn.Module):
             x = self.conv0(x, next(w_iter), fused=fused, impl=impl, **layer_kwargs)
             x = self.conv1(x, next(w_iter), fused=fused, impl=impl, **layer_kwargs)
             if x.shape[2] > 32:
-                x = torch.cat([x, cat_feat[str(x.shape[2])].to(x.dtype)], dim=1)
+                cf = cat_feat[str(x.shape[2])]
+                x = torch.cat([x, (cf.to_nchw() if isinstance(cf, PackedAct) else cf).to(x.dtype)], dim=1)
                 x = self.merge_conv(x, fused=fused, impl=impl)
         if has_spade:
-            x = self.spade_b512(x, parsing, fused=fused, impl=impl)
+            x = self.spade_b512(x, parsing, fused=fused, impl=impl, out_packed=isinstance(x, PackedAct))
         if img is not None:
             img = upfirdn2d.upsample2d(img, self.resample_filter, impl=impl)
         img, pred_parsing = self.torgb(x, next(w_iter), img=img, fused=fused, impl=impl)
@@ -413,9 +474,8 @@ class SynthesisNetworkFull_v18(torch.nn.Module):
             oc = stem.weight.shape[0]
             xp = PackedAct(PackedAct.empty(n, h, w, oc, S._parts(), x.device), oc)
             stem(x, fused=True, out_packed=xp)
-            x = xp
-            for layer in self.spade_encoder[1:]:
-                x = layer(x, fused=True, impl=impl)
+            x = self.spade_encoder[1](xp, fused=True, impl=impl, out_packed=True)     # stays in the operand format for the next block
+            x = self.spade_encoder[2](x, fused=True, impl=impl)
         else:
             for layer in self.spade_encoder:
                 x = layer(x, fused=fused, impl=impl)
@@ -441,8 +501,7 @@ class SynthesisNetworkFull_v18(torch.nn.Module):
         x = img = pred_parsing = None
         second_last = self.block_resolutions[-2]
         for res, cur_ws in zip(self.block_resolutions, block_ws):
-            x, img, pp = getattr(self, f'b{res}')(x, img, cur_ws, pose_feat, cat_feat, fused=fused, impl=impl,
-                                                  export_tensor=(res == second_last), **block_kwargs)
+            x, img, pp = getattr(self, f'b{res}')(x, img, cur_ws, pose_feat, cat_feat, fused=fused, impl=impl, **block_kwargs)
             pred_parsing = pp if pp is not None else pred_parsing
             if res == second_last:
                 x_256, img_256 = x, img.clone()
@@ -472,8 +531,9 @@ class SynthesisNetworkFull_v18(torch.nn.Module):
             spade_upper = self.get_spade_feat(upper_mask, denorm_upper_mask, denorm_upper_input, **kw)
             spade_lower = self.get_spade_feat(lower_mask, denorm_lower_mask, denorm_lower_input, **kw)
             spade_feat = spade_upper * upper_256 + spade_lower * lower_256
-        xs = self.spade_b256_1(x_256, spade_feat, feats_packed=feats_packed, **kw)
-        xs = self.spade_b256_2(xs, spade_feat, feats_packed=feats_packed, **kw)
+        keep_packed = isinstance(x_256, PackedAct)     # operand-format hand-over through both SPADE blocks into the texture branch
+        xs = self.spade_b256_1(x_256, spade_feat, feats_packed=feats_packed, out_packed=keep_packed, **kw)
+        xs = self.spade_b256_2(xs, spade_feat, feats_packed=feats_packed, out_packed=keep_packed, **kw)
         _, finetune_img, _ = self.texture_b512(xs, img_256, block_ws[-1], pose_feat, cat_feat, parsing=parsing_index, **kw, **block_kwargs)
         return img, finetune_img, pred_parsing
 

@@ -120,6 +120,20 @@ class Conv2dLayer(torch.nn.Module):
                                              clamp=-1 if act_clamp is None else act_clamp, out_packed=out_packed, out=out,
                                              accumulate=accumulate)
         assert out is None and not accumulate, 'out= / accumulate= need the fused stride-1 route'
+        if fused and self.up == 1 and self.down == 2 and isinstance(x, PackedAct):
+            # operand-format input: the FIR runs on that format too (pgpp_fir_packed), no float32 intermediate and no packing pass
+            k = self.weight.shape[-1]
+            fw = self.resample_filter.shape[-1]
+            p0 = self.padding + (fw - 2 + 1) // 2
+            p1 = self.padding + (fw - 2) // 2
+            pw = conv2d_gradfix.packed_plain(self.weight, True, _parts(), 0, 0, scale=self.weight_gain)
+            epi = dict(bias=self.bias, act=self.activation, alpha=bias_act.activation_funcs[self.activation].def_alpha, gain=act_gain,
+                       clamp=-1 if act_clamp is None else act_clamp)
+            if k == 1:
+                xd = conv2d_gradfix.fir_packed(x, self.resample_filter, down=2, padding=(p0, p1, p0, p1))
+                return conv2d_gradfix.igemm_conv(xd, pw, out_packed=out_packed, **epi)
+            xb = conv2d_gradfix.fir_packed(x, self.resample_filter, down=1, padding=(p0, p1, p0, p1))
+            return conv2d_gradfix.igemm_conv(xb, pw, stride=2, out_packed=out_packed, **epi)
         if fused and self.up == 1 and self.down == 2 and _can_fuse(x, self.weight, self.bias) and not isinstance(x, PackedAct):
             # FIR blur (or FIR decimation for 1x1 kernels) on the upfirdn2d kernel, then ONE strided implicit-GEMM launch with the
             # bias / activation fused (conv2d_resample.py:107-110, 119-122)

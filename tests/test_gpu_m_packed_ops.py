@@ -1,0 +1,154 @@
+"""GPU parity tests of the operand-format (packed -> packed) companions of the convolution kernel: pgpp_fir_packed (the FIR in
+front of a down-sampling convolution, conv2d_resample.py:107-122, run on the bf16 expansion), the accumulate mode of the lean
+operand-format epilogue (residual adds without leaving the format), and the encoder chains built from them."""
+import importlib
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_pkg
+from helpers import rel_l2
+from oracle import ref_ops
+
+pytestmark = pytest.mark.gpu
+load_pkg()
+cg = importlib.import_module('pgpp_b200.torch_utils.ops.conv2d_gradfix')
+upf = importlib.import_module('pgpp_b200.torch_utils.ops.upfirdn2d')
+syn = importlib.import_module('pgpp_b200.training.synthesis')
+gen = importlib.import_module('pgpp_b200.training.generator')
+DEV = 'cuda:0'
+# the operand format itself carries 8 * parts significand bits: error of one round trip through it
+FMT_TOL = {1: 4e-3, 2: 2e-5, 3: 2e-7}
+
+
+@pytest.fixture(autouse=True)
+def _restore_precision():
+    old = cg.fp32_precision
+    yield
+    cg.fp32_precision = old
+
+
+FIR_CASES = [
+    # name,             n, c,   h,  w,  filter,        down, padding (x0, x1, y0, y1), gain
+    ('blur_even',       2, 64,  32, 48, [1, 3, 3, 1],  1,    (2, 2, 2, 2), 1.0),
+    ('blur_odd_ragged', 3, 24,  17, 29, [1, 3, 3, 1],  1,    (2, 2, 2, 2), 1.0),
+    ('blur_after_up',   1, 128, 33, 33, [1, 3, 3, 1],  1,    (1, 1, 1, 1), 4.0),
+    ('down2_skip',      2, 64,  32, 32, [1, 3, 3, 1],  2,    (1, 1, 1, 1), 1.0),
+    ('down2_odd',       2, 72,  19, 23, [1, 3, 3, 1],  2,    (1, 1, 1, 1), 1.0),
+    ('taps3',           2, 16,  12, 20, [1, 2, 1],     1,    (1, 1, 1, 1), 1.0),
+    ('taps2_asym_pad',  2, 8,   9,  9,  [1, 1],        2,    (1, 0, 0, 1), 2.0),
+    ('one_pixel_out',   1, 8,   2,  2,  [1, 3, 3, 1],  1,    (1, 1, 1, 1), 1.0),
+    ('tall_strips',     1, 8,   67, 5,  [1, 3, 3, 1],  1,    (2, 2, 2, 2), 1.0),
+]
+
+
+@pytest.mark.parametrize('parts', [1, 2, 3])
+@pytest.mark.parametrize('flip', [False, True])
+@pytest.mark.parametrize('case', FIR_CASES, ids=[c[0] for c in FIR_CASES])
+def test_fir_packed_vs_oracle(case, flip, parts):
+    name, n, c, h, w, taps, down, pad, gain = case
+    g = torch.Generator().manual_seed(hash(name) % 1000)
+    x = torch.randn(n, c, h, w, generator=g)
+    f = ref_ops.setup_filter(taps)
+    if len(taps) == 3:
+        f = f * torch.tensor([[1.0, 2.0, 0.5]])      # asymmetric filter: flip_filter must matter
+    prec = {1: 'bf16', 2: 'bf16x2', 3: 'bf16x3'}[parts]
+    xp = cg.pack_operand(x.to(DEV), prec)
+    x_seen = xp.to_nchw().cpu()                      # what the kernel reads: the bf16 expansion of x
+    want = ref_ops.upfirdn2d(x_seen, f, down=down, padding=list(pad), flip_filter=flip, gain=gain)
+    got = cg.fir_packed(xp, f.to(DEV), down=down, padding=pad, flip_filter=flip, gain=gain)
+    assert tuple(got.shape) == tuple(want.shape)
+    assert rel_l2(got.to_nchw(), want) < FMT_TOL[parts], (name, rel_l2(got.to_nchw(), want))
+    # padding channels of a freshly allocated result are zero (they meet zero weights but must not be NaN / Inf patterns)
+    assert torch.isfinite(got.data.float()).all()
+
+
+def test_fir_packed_slice_copy_and_into():
+    """f=None is the channel-slice copy the synthesis blocks use to place the garment features next to conv1's output"""
+    g = torch.Generator().manual_seed(5)
+    a = torch.randn(2, 64, 16, 24, generator=g)
+    src = cg.pack_operand(a.to(DEV), 'bf16x2')
+    buf = cg.PackedAct.empty(2, 16, 24, 128 + 64, 2, DEV)
+    buf.zero_()
+    cg.fir_packed(src, None, out=cg.PackedAct(buf, 64, 128))
+    whole = cg.PackedAct(buf, 192, 0).to_nchw()
+    assert torch.equal(whole[:, 128:], src.to_nchw())
+    assert float(whole[:, :128].abs().max()) == 0.0
+    # blur out of a slice of a wider buffer into a slice of another one
+    f = ref_ops.setup_filter([1, 3, 3, 1])
+    dst = cg.PackedAct.empty(2, 17, 25, 128, 2, DEV)
+    dst.zero_()
+    cg.fir_packed(cg.PackedAct(buf, 64, 128), f.to(DEV), padding=(2, 2, 2, 2), out=cg.PackedAct(dst, 64, 64))
+    want = ref_ops.upfirdn2d(src.to_nchw().cpu(), f, padding=[2, 2, 2, 2])
+    assert rel_l2(cg.PackedAct(dst, 64, 64).to_nchw(), want) < FMT_TOL[2]
+    assert float(cg.PackedAct(dst, 64, 0).to_nchw().abs().max()) == 0.0
+
+
+@pytest.mark.parametrize('prec', ['bf16x2', 'bf16x3', 'bf16'])
+@pytest.mark.parametrize('shape', [(2, 64, 64, 32, 32, 3), (2, 128, 128, 16, 40, 3), (3, 64, 128, 24, 24, 1), (2, 64, 64, 128, 64, 3)],
+                         ids=['64x64', '128x128', '1x1_64_128', 'resident_slab'])
+def test_packed_accumulate(shape, prec):
+    """out_packed + accumulate: y(packed) += act(conv(x) + b) * gain, the residual add of ResBlock / Spade_ResBlockV4_512 on the format"""
+    n, ic, oc, h, w, k = shape
+    cg.fp32_precision = prec
+    parts = cg._PRODUCTS[prec][1]
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(n, ic, h, w, generator=g)
+    wt = torch.randn(oc, ic, k, k, generator=g) / np.sqrt(ic * k * k)
+    b = torch.randn(oc, generator=g)
+    y0 = torch.randn(n, oc, h, w, generator=g)
+    xp = cg.pack_operand(x.to(DEV), prec)
+    yp = cg.pack_operand(y0.to(DEV), prec)
+    y_seen = yp.to_nchw().cpu().double()
+    pw = cg.packed_plain(wt.to(DEV), True, parts, k // 2, k // 2)
+    cg.igemm_conv(xp, pw, bias=b.to(DEV), act='relu', gain=0.75, out_packed=yp, accumulate=True)
+    conv = torch.nn.functional.conv2d(xp.to_nchw().cpu().double(), wt.double(), b.double(), padding=k // 2)
+    want = y_seen + conv.clamp_min(0) * 0.75
+    tol = {'bf16x2': 8e-5, 'bf16x3': 4e-5, 'bf16': 1.5e-2}[prec]
+    assert rel_l2(yp.to_nchw(), want) < tol, rel_l2(yp.to_nchw(), want)
+
+
+@pytest.mark.parametrize('k', [1, 3])
+def test_down_conv_on_packed_input_matches_tensor_route(k):
+    """Conv2dLayer(down=2) fed a PackedAct (FIR on the operand format) against the same layer fed the tensor (float32 FIR, then packing)"""
+    torch.manual_seed(3)
+    layer = syn.Conv2dLayer(64, 128, kernel_size=k, down=2, activation='lrelu').to(DEV).eval()
+    layer.bias.data.normal_()
+    x = torch.randn(2, 64, 64, 48, device=DEV)
+    with torch.no_grad():
+        want = layer(x, fused=True)
+        xp = cg.pack_operand(x, cg.fp32_precision)
+        out = cg.PackedAct(cg.PackedAct.empty(2, 32, 24, 128, syn._parts(), DEV), 128)
+        layer(xp, fused=True, out_packed=out)
+        comp = layer(x, fused=False)         # conv2d_resample composition (reference call sequence)
+    assert rel_l2(out.to_nchw(), want) < 3e-5
+    assert rel_l2(out.to_nchw(), comp) < 8e-5
+
+
+def test_resblock_packed_output_matches_tensor_output():
+    torch.manual_seed(4)
+    blk = gen.ResBlock(64, 64, kernel_size=4, activation='relu').to(DEV).eval()
+    blk2 = gen.ResBlock(64, 128, kernel_size=4, activation='relu', down=2).to(DEV).eval()
+    x = torch.randn(2, 64, 48, 64, device=DEV)
+    with torch.no_grad():
+        want = blk(x, fused=True)
+        got = blk(x, fused=True, out_packed=True)
+        assert isinstance(got, cg.PackedAct)
+        assert rel_l2(got.to_nchw(), want) < 3e-5
+        want2 = blk2(want, fused=True)
+        got2 = blk2(got, fused=True)                # operand-format input into the down-sampling block
+        comp2 = blk2(blk(x, fused=False), fused=False)
+    assert rel_l2(got2, want2) < 5e-5
+    assert rel_l2(got2, comp2) < 1e-4
+
+
+def test_const_encoder_packed_chain_matches_composition():
+    torch.manual_seed(6)
+    enc = gen.ConstEncoderNetwork(input_nc=5, output_nc=512, ngf=64, n_downsampling=6).to(DEV).eval()
+    x = torch.randn(2, 5, 128, 128, device=DEV).clamp(-1, 1)
+    with torch.no_grad():
+        got = enc(x, fused=True)
+        want = enc(x, fused=False)
+    assert torch.is_tensor(got) and tuple(got.shape) == tuple(want.shape) == (2, 512, 2, 2)
+    assert rel_l2(got, want) < 1e-4, rel_l2(got, want)
