@@ -16,6 +16,7 @@ timed region; `bf16_mode` reports the single-product bf16 mode separately; `roof
 """
 import argparse
 import importlib
+import importlib.util
 import json
 import os
 import statistics
@@ -594,9 +595,13 @@ def run_ours(args):
             top_name, (tfl, tms, tcnt) = max(by.items(), key=lambda kv: kv[1][1])
             achieved = tfl / (tms * 1e-3) / 1e12
             traffic = None
-            tpath = os.path.join(ROOT, 'profiles', 'r01_traffic.json')
-            if os.path.isfile(tpath):
-                traffic = json.load(open(tpath)).get(f'{top_name}')
+            # DRAM bytes of that launch shape from a committed ncu --set full capture (newest round first); the key is the
+            # launch label without its operand-format suffix
+            shape_key = ' '.join(top_name.split(' ')[:6])
+            for tfile in ('r02_traffic.json', 'r01_traffic.json'):
+                tpath = os.path.join(ROOT, 'profiles', tfile)
+                if traffic is None and os.path.isfile(tpath):
+                    traffic = json.load(open(tpath)).get(shape_key)
             return {'bound': 'tensor', 'kernel': 'pgpp::igemm_kernel', 'launch': top_name, 'launches_per_step': tcnt,
                     'achieved': achieved, 'peak': pk['tflops'], 'unit': 'TFLOP/s', 'frac': achieved / pk['tflops'], 'traffic': traffic,
                     'peak_source': pk['source'], 'avg_launch_ms': tms / tcnt, 'algorithmic_flops_per_launch': tfl / tcnt,
@@ -683,6 +688,19 @@ def run_ours(args):
                           'note': 'batch-1 latency of the full generator (fp32-parity mode); graph replay is bit-identical to eager'}
             except Exception as e:      # noqa: BLE001 - the extra measurement must never break the contract line
                 batch1 = {'error': f'{type(e).__name__}: {str(e)[:200]}'}
+        # BASELINE configs[3] / the metric's "modconv TFLOPS and upfirdn2d GB/s": the op sweep of this very build (tools/op_bench.py)
+        ops = None
+        if gen_mode and not args.no_ops:
+            try:
+                del net
+                torch.cuda.empty_cache()
+                spec = importlib.util.spec_from_file_location('pgpp_op_bench', os.path.join(ROOT, 'tools', 'op_bench.py'))
+                op_bench = importlib.util.module_from_spec(spec)
+                spec.loader.exec_module(op_bench)
+                ops = op_bench.run_ops(device=device, n=32)
+            except Exception as e:      # noqa: BLE001 - the extra measurement must never break the contract line
+                ops = {'error': f'{type(e).__name__}: {str(e)[:300]}'}
+            cg.fp32_precision = args.precision
         imgs = batch * world * args.steps
         line = {
             'metric': 'generator_512px_images_per_sec' if gen_mode else 'synthesis_hot_path_images_per_sec',
@@ -706,6 +724,7 @@ def run_ours(args):
             'cpu_baseline': cpu,
             'parity_vs_cpu_oracle': parity,
             'batch1': batch1,
+            'ops': ops,
             'train': train,
             'bf16_mode': {'value': imgs / (bf16_ms * 1e-3), 'unit': 'images/s', 'ms_per_step': bf16_ms / args.steps, 'roofline': roof_bf16,
                           'parity_vs_cpu_oracle': parity_bf16,
@@ -731,6 +750,7 @@ def main():
     ap.add_argument('--train-steps', type=int, default=3, help='generator workload: also time this many training iterations (0 = skip)')
     ap.add_argument('--fp16-res', type=int, default=3, help='train workload: number of highest-resolution D blocks in fp16 (train.py:196)')
     ap.add_argument('--skip-cpu', action='store_true', help='skip the CPU baseline / parity leg')
+    ap.add_argument('--no-ops', action='store_true', help='generator workload: skip the op microbench sweep (the `ops` key, BASELINE configs[3])')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference(args)

@@ -233,6 +233,17 @@ PGPP_API int pgpp_conv2d_direct(const float* x, const float* w, const float* bia
 PGPP_API int pgpp_fir_pack(const float* x, const int64_t size[4], const int64_t stride[4], const float* f_host, int fw, int fh,
                   int padx0, int padx1, int pady0, int pady1, int flip, float gain, void* out, int c_pad, int parts, void* stream);
 
+/* 1x1 modulated convolution with at most 8 output channels (o1 + o2) per launch on the operand format (the ToRGB layers, networks.py:1925-1967; with the
+ * 7-channel parsing head of ToRGBLayerFull_v1_v5 as a second head computed in the same pass over x):
+ *   out[n, o, p] (+)= clamp(act(sum_c X[n, p, c] * w[o, c] * styles[n, c] + b[o]) * gain),  X = sum of the x_parts bf16 parts.
+ * x: bf16 [x_parts][N][hw][c_total] (pointer at the first of the c channels); w1 [o1, c], w2 [o2, c] float32; styles [N, c] or NULL;
+ * out1 [N, o1, hw] float32 (accumulate1: added to its previous content), out2 [N, o2, hw] float32 (o2 may be 0).
+ * act_fn linear / relu / lrelu.  Bound by reading x once: runs on the CUDA cores. */
+PGPP_API int pgpp_conv1x1_thin(const void* x, int x_parts, int64_t x_part_stride, int c_total, int n, int c, int64_t hw,
+                      const float* w1, const float* b1, int o1, float* out1, int accumulate1,
+                      const float* w2, const float* b2, int o2, float* out2,
+                      const float* styles, int act_fn, float alpha, float gain, float clamp, void* stream);
+
 /* upfirdn2d with up = 1 on the operand format, packed -> packed (the blur of "blur, then strided convolution", conv2d_resample.py:119-122,
  * and the FIR decimation before a 1x1 down-sampling convolution, :107-110, for inputs whose producer already wrote the operand format):
  *   out = split_bf16( gain * sum_{jy,jx} X[n][oy*down + jy - pady0][ox*down + jx - padx0][c] * k[jy][jx] ),  X = sum of the input parts,

@@ -64,4 +64,14 @@ template <class T> __device__ __forceinline__ T from_acc(typename Acc<T>::type v
 template <> __device__ __forceinline__ __half from_acc<__half>(float v) { return __float2half_rn(v); }
 template <> __device__ __forceinline__ __nv_bfloat16 from_acc<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
 
+// packed float32x2 arithmetic (sm_100a FFMA2 / FADD2): halves the instruction count of the bandwidth-bound kernels that work on the
+// bf16 operand format, where the conversions and sums per byte are what limits them
+typedef unsigned long long f32x2;       // two packed float32 (low word = even channel)
+
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) { return (f32x2)__float_as_uint(lo) | ((f32x2)__float_as_uint(hi) << 32); }
+__device__ __forceinline__ void ffma2(f32x2& d, const f32x2 a, const f32x2 b) { asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(d) : "l"(a), "l"(b)); }
+__device__ __forceinline__ f32x2 fadd2(const f32x2 a, const f32x2 b) { f32x2 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+// bf16 pair (one 32-bit word, low half = even channel) -> packed float32 pair
+__device__ __forceinline__ f32x2 bf2_to_f32x2(uint32_t w) { return (f32x2)(w << 16) | ((f32x2)(w & 0xffff0000u) << 32); }
+
 } // namespace pgpp

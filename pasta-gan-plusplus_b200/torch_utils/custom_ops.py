@@ -100,6 +100,8 @@ def load_library():
     lib.pgpp_fir_packed.restype = i32
     lib.pgpp_fir_packed.argtypes = [vp, i32, i64, i32, i32, i32, i32, i32, ctypes.POINTER(ctypes.c_float), i32, i32, i32, i32, i32, i32, i32, i32, f32,
                                     vp, i32, i64, i32, vp]
+    lib.pgpp_conv1x1_thin.restype = i32
+    lib.pgpp_conv1x1_thin.argtypes = [vp, i32, i64, i32, i32, i32, i64, vp, vp, i32, vp, i32, vp, vp, i32, vp, vp, i32, f32, f32, f32, vp]
     lib.pgpp_conv2d_direct.restype = i32
     lib.pgpp_conv2d_direct.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, f32, i32, f32, f32, f32, vp, vp, i32, i32, i32, vp]
     lib.pgpp_conv2d_igemm.restype = i32
@@ -121,7 +123,7 @@ def load_library():
 EXPORTED_SYMBOLS = ('pgpp_version', 'pgpp_last_error', 'pgpp_launch_count', 'pgpp_bias_act', 'pgpp_upfirdn2d',
                     'pgpp_modconv_demod_coefs', 'pgpp_pack_activations', 'pgpp_pack_activations_slice', 'pgpp_pack_activations_f16',
                     'pgpp_pack_weights', 'pgpp_up2_weight_adjoint', 'pgpp_mul_reduce_hw', 'pgpp_modulate_weights',
-                    'pgpp_spade_modulate_pack', 'pgpp_mix_pack', 'pgpp_conv2d_direct', 'pgpp_fir_pack', 'pgpp_fir_packed', 'pgpp_pack_im2col', 'pgpp_conv2d_igemm', 'pgpp_conv2d_wgrad', 'pgpp_u8_to_f32',
+                    'pgpp_spade_modulate_pack', 'pgpp_mix_pack', 'pgpp_conv2d_direct', 'pgpp_fir_pack', 'pgpp_fir_packed', 'pgpp_conv1x1_thin', 'pgpp_pack_im2col', 'pgpp_conv2d_igemm', 'pgpp_conv2d_wgrad', 'pgpp_u8_to_f32',
                     'pgpp_image_to_u8', 'pgpp_grid_sample_2d', 'pgpp_grid_sample_2d_backward')
 
 
@@ -450,6 +452,27 @@ class _ConvPlugin:
             _check(lib.pgpp_fir_pack(_ptr(x), c_i64x4(*x.shape), c_i64x4(*x.stride()), f, fw, fh, int(padx0), int(padx1), int(pady0), int(pady1),
                                      int(bool(flip)), float(gain), _ptr(out), int(c_pad), int(parts), _stream(x)))
         return out
+
+    @staticmethod
+    def conv1x1_thin(src, c, c_off, w1, b1, out1, accumulate1, w2=None, b2=None, out2=None, styles=None, act_idx=1, alpha=0.0, gain=1.0, clamp=-1.0):
+        """1x1 modulated convolution with few output channels on the operand format (`src` bf16 [parts, N, H, W, c_total], channels
+        [c_off, c_off + c)): out1 [N, o1, H, W] float32 (+= when accumulate1), optional second head out2 from w2 / b2; see pgpp_conv1x1_thin"""
+        lib = load_library()
+        _torch_check(src.is_cuda and src.dtype == torch.bfloat16 and src.dim() == 5 and src.is_contiguous(), 'conv1x1_thin: src must be a contiguous bf16 [parts,N,H,W,C] tensor')
+        parts, n, h, w, ct = src.shape
+        f32 = lambda t: None if t is None else t.detach().to(torch.float32).contiguous()
+        w1, b1, w2, b2, styles = f32(w1), f32(b1), f32(w2), f32(b2), f32(styles)
+        o1, o2 = int(w1.shape[0]), 0 if w2 is None else int(w2.shape[0])
+        _torch_check(out1.dtype == torch.float32 and out1.is_contiguous() and tuple(out1.shape) == (n, o1, h, w), 'conv1x1_thin: out1 must be contiguous float32 [N,o1,H,W]')
+        _torch_check(w1.numel() == o1 * c and (styles is None or tuple(styles.shape) == (n, c)), 'conv1x1_thin: weight / styles shape')
+        if o2:
+            _torch_check(out2 is not None and out2.dtype == torch.float32 and out2.is_contiguous() and tuple(out2.shape) == (n, o2, h, w) and w2.numel() == o2 * c,
+                         'conv1x1_thin: out2 must be contiguous float32 [N,o2,H,W]')
+        with torch.cuda.device(src.device):
+            _check(lib.pgpp_conv1x1_thin(src.data_ptr() + 2 * c_off, int(parts), int(src[0].numel()), int(ct), n, int(c), h * w,
+                                         _ptr(w1), _ptr(b1), o1, _ptr(out1), int(bool(accumulate1)), _ptr(w2), _ptr(b2), o2, _ptr(out2),
+                                         _ptr(styles), int(act_idx), float(alpha), float(gain), float(clamp), _stream(src)))
+        return out1, out2
 
     @staticmethod
     def fir_packed(src, c, c_off, taps, fw, fh, down, padx0, padx1, pady0, pady1, flip, gain, dst=None, dst_c_off=0, parts=None):

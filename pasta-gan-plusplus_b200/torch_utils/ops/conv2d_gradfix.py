@@ -494,7 +494,9 @@ def igemm_conv(x, pw, *, scale=None, stride=1, out_hw=None, dcoef=None, noise=No
         real_ic, real_taps = (ic, 9 if pw.phases == 4 else pw.kh * pw.kw) if im is None else (pw.c_in // (im['r'] * im['kw']), im['kh'] * im['kw'])
         flops = 2.0 * n * pw.o * real_ic * real_taps * conv_h * conv_w
         kname = f'k{pw.kh}' if im is None else f"k{im['kh']}(im2col r{im['r']})"
-        trace.append((f'igemm {real_ic}->{pw.o} {kname} {h}x{w}->{out_h}x{out_w} n{n} {precision}', flops, e0, e1))
+        okind = ('spade' if spade is not None else 'packed' if out_packed is not None else 'nchw') + ('+acc' if accumulate else '')
+        ikind = 'packed' if isinstance(x, PackedAct) else 'tensor'
+        trace.append((f'igemm {real_ic}->{pw.o} {kname} {h}x{w}->{out_h}x{out_w} n{n} {precision} {ikind}->{okind}', flops, e0, e1))
     else:
         _plugin.conv2d_igemm(d, device)
     if out_packed is None and want_f64:

@@ -37,6 +37,7 @@ PACKED_MIN_RES = 128    # blocks at this resolution and above hand activations o
 # followed by the packing kernel (profiles/r01_pack_bench_v15.txt): its 64-channel x 128-pixel tile pays a 1.9x halo and a long
 # staging loop.  Kept for comparison, off by default.
 FUSE_BLUR_PACK = False
+THIN_TORGB = True       # ToRGB (and its parsing head) on operand-format inputs: one pass of the bandwidth-bound pgpp_conv1x1_thin kernel
 
 
 def _can_fuse(x, *params):
@@ -227,6 +228,24 @@ class ToRGBLayer(torch.nn.Module):
         styles = self.affine(w) * self.weight_gain
         pred_parsing = None
         can = fused and _can_fuse(x, self.weight, self.bias, styles)
+        if can and THIN_TORGB and isinstance(x, PackedAct) and tuple(self.weight.shape[2:]) == (1, 1) and x.c % 8 == 0 and x.c <= 512 and \
+                self.weight.shape[0] + self.parsing_channels <= 16 and (img is None or (img.dtype == torch.float32 and img.is_contiguous())):
+            # operand-format input: both heads (RGB and parsing) from ONE pass over x on the bandwidth-bound thin kernel
+            conv2d_gradfix._init()
+            n, ic, h, wd = x.shape
+            oc = self.weight.shape[0]
+            y = img if img is not None else torch.empty([n, oc, h, wd], dtype=torch.float32, device=x.device)
+            clamp = -1.0 if self.conv_clamp is None else float(self.conv_clamp)
+            w2 = b2 = None
+            if self.parsing_channels:
+                pred_parsing = torch.empty([n, self.parsing_channels, h, wd], dtype=torch.float32, device=x.device)
+                w2, b2 = self.m_weight1.reshape(self.parsing_channels, ic), self.m_bias1
+                if oc + self.parsing_channels > 8:      # one launch holds 8 outputs' weights in registers: the parsing head takes its own pass
+                    conv2d_gradfix._plugin.conv1x1_thin(x.data, ic, x.c_off, w2, b2, pred_parsing, False, styles=styles, clamp=clamp)
+                    w2 = b2 = None
+            conv2d_gradfix._plugin.conv1x1_thin(x.data, ic, x.c_off, self.weight.reshape(oc, ic), self.bias, y, img is not None, w2=w2, b2=b2,
+                                                out2=pred_parsing if w2 is not None else None, styles=styles, clamp=clamp)
+            return y, pred_parsing
         if self.parsing_channels:
             if can:
                 pred_parsing = modulated_conv2d_fused_act(x, self.m_weight1, styles, demodulate=False, bias=self.m_bias1,

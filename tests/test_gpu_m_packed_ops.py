@@ -152,3 +152,39 @@ def test_const_encoder_packed_chain_matches_composition():
         want = enc(x, fused=False)
     assert torch.is_tensor(got) and tuple(got.shape) == tuple(want.shape) == (2, 512, 2, 2)
     assert rel_l2(got, want) < 1e-4, rel_l2(got, want)
+
+
+@pytest.mark.parametrize('prec', ['bf16x2', 'bf16x3', 'bf16'])
+@pytest.mark.parametrize('cfg', [(64, 7, True, 40, 56), (128, 0, True, 32, 32), (512, 0, False, 16, 24), (64, 7, False, 17, 19)],
+                         ids=['c64_parsing_acc', 'c128_acc', 'c512_noacc', 'ragged_noacc'])
+def test_torgb_thin_kernel(cfg, prec):
+    """ToRGB (+ parsing head) on an operand-format input: the thin CUDA-core kernel against the tensor-core route and float64"""
+    ic, pc, acc, h, w = cfg
+    cg.fp32_precision = prec
+    torch.manual_seed(9)
+    layer = syn.ToRGBLayer(ic, 3, w_dim=32, conv_clamp=2.0, parsing_channels=pc).to(DEV).eval()
+    layer.bias.data.normal_()
+    if pc:
+        layer.m_bias1.data.normal_()
+    x = torch.randn(3, ic, h, w, device=DEV)
+    ws = torch.randn(3, 32, device=DEV)
+    img0 = torch.randn(3, 3, h, w, device=DEV)
+    xp = cg.pack_operand(x, prec)
+    x_seen = xp.to_nchw().double()
+    with torch.no_grad():
+        got, got_pp = layer(xp, ws, img=img0.clone() if acc else None)
+        syn.THIN_TORGB = False
+        try:
+            ref, ref_pp = layer(xp, ws, img=img0.clone() if acc else None)
+        finally:
+            syn.THIN_TORGB = True
+        styles = (layer.affine(ws) * layer.weight_gain).double()
+        want = torch.einsum('nchw,oc,nc->nohw', x_seen, layer.weight.double().reshape(3, ic), styles) + layer.bias.double().reshape(1, 3, 1, 1)
+        want = want.clamp(-2, 2) + (img0.double() if acc else 0)
+    # the thin kernel multiplies the exact float32 weights: its only error is float32 accumulation
+    assert rel_l2(got, want) < 2e-6, rel_l2(got, want)
+    assert rel_l2(got, ref) < {'bf16x2': 8e-5, 'bf16x3': 4e-5, 'bf16': 1.5e-2}[prec]
+    if pc:
+        want_pp = (torch.einsum('nchw,oc,nc->nohw', x_seen, layer.m_weight1.double().reshape(pc, ic), styles) + layer.m_bias1.double().reshape(1, pc, 1, 1)).clamp(-2, 2)
+        assert rel_l2(got_pp, want_pp) < 2e-6
+        assert rel_l2(got_pp, ref_pp) < {'bf16x2': 8e-5, 'bf16x3': 4e-5, 'bf16': 1.5e-2}[prec]
