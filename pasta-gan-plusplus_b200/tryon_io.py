@@ -39,6 +39,19 @@ def prepare_inputs(data, device):
     def new(c, like):
         return torch.empty([n, c, like.shape[2], like.shape[3]], dtype=torch.float32, device=device)
 
+    class _Edge:
+        """uint8 sources take the pgpp_u8_to_f32 kernel; a field the loader delivered as float (lower_label_map = 127.5 for skirts,
+        dataset.py:2219) takes the same expression on library ops"""
+        @staticmethod
+        def u8_to_f32(src, dst, c_off=0, normalize=True, mask=None):
+            if src.dtype == torch.uint8:
+                return _plugin.u8_to_f32(src, dst, c_off, normalize=normalize, mask=mask)
+            assert mask is None
+            v = src.to(torch.float32)
+            dst[:, c_off:c_off + src.shape[1]] = (v / 127.5 - 1) if normalize else v
+            return dst
+    io = _Edge
+
     out = {}
     out['image'] = io.u8_to_f32(d['image'], new(3, d['image']))                                         # test.py:126
     cu, cl = d['norm_img'].shape[1], d['norm_img_lower'].shape[1]
@@ -63,6 +76,37 @@ def prepare_inputs(data, device):
     for key in ('denorm_upper_mask', 'denorm_lower_mask'):                                              # test.py:138,141
         out[key] = io.u8_to_f32(d[key], new(1, d[key]), normalize=False)
     return out
+
+
+FIXTURE_KEYS = {'denorm_upper_img': 'denorm_upper_clothes', 'denorm_lower_img': 'denorm_lower_clothes'}      # dataset.py:2221 names -> test.py:121 names
+
+
+def load_test_pairs(npz_path, indices=(0,)):
+    """Batch of real try-on pairs in the layout the reference's DataLoader hands to test.py:121-123, read from a fixture written by
+    the reference's own loader (oracle/make_golden_testpair.py: UvitonDatasetFull_512_test_upper over test_datas/, dataset.py:1952-2223).
+    Returns the dict `prepare_inputs` takes (host tensors, uint8 except where the loader itself produced floats)."""
+    import numpy as np
+    z = np.load(npz_path)
+    fields = sorted({k.rsplit('_', 1)[0] for k in z.files if k != 'names'})
+    out = {}
+    for f in fields:
+        arrs = [z[f'{f}_{i}'] for i in indices]
+        if any(a.dtype != np.uint8 for a in arrs):
+            arrs = [a.astype(np.float32) for a in arrs]
+        out[FIXTURE_KEYS.get(f, f)] = torch.from_numpy(np.stack(arrs))
+    out['person_name'] = [str(z['names'][i][0]) for i in indices]
+    out['clothes_name'] = [str(z['names'][i][1]) for i in indices]
+    return out
+
+
+def tryon(G, inputs, gt_parsing=None, **synthesis_kwargs):
+    """test.py:147-160: the generator call of the inference loop on the tensors `prepare_inputs` returns; -> (img, finetune_img,
+    pred_parsing).  `z` has zero width (z_dim = 0, test.py:147)."""
+    n = inputs['parts'].shape[0]
+    z = torch.zeros([n, 0], device=inputs['parts'].device)
+    with torch.no_grad():
+        return G(z, inputs['parts'], inputs['retain'], inputs['pose'], inputs['denorm_upper_clothes'], inputs['denorm_lower_clothes'],
+                 inputs['denorm_upper_mask'], inputs['denorm_lower_mask'], gt_parsing=gt_parsing, **synthesis_kwargs)
 
 
 def images_to_uint8(gen_imgs, bgr=True):
