@@ -3,11 +3,16 @@
 //   out[n,c,oy,ox] = gain * sum_{jy,jx} z[oy*downy + jy - pady0, ox*downx + jx - padx0] * k[jy,jx]
 //   z = x with (up-1) zeros inserted after every sample, zero outside; k = f flipped unless `flip`.
 //
-// Two kernels:
+// Kernels:
 //   * fir_tile_kernel  - the shapes that carry the traffic in the generator (up = down = 1, filter
 //     up to 4x4, unit stride along W): shared-memory halo tile, each thread produces a 4x4 patch of
 //     outputs from a sliding window of 128-bit shared loads with the taps held in registers, and
 //     writes 128-bit rows.  HBM-bound; one read and one write per element.
+//   * fir_down2_kernel - down = 2 from the same kind of halo tile (1x1-skip / encoder downsampling).
+//   * fir_up2_kernel   - up = 2 (image-skip upsampling, and the gradient of every down = 2 call): the
+//     zero-stuffed signal is never formed; output parity selects 2 of the 4 taps per axis at compile time.
+//   Rows whose pitch is not a multiple of 4 elements (the 513-wide blurred images) leave through a
+//   shared-memory transpose so that every store instruction of a warp covers one contiguous row segment.
 //   * generic_kernel   - any up/down/pad/filter size/strides (channels_last included); one thread per
 //     4 consecutive outputs, taps from shared memory, input through the read-only path.
 #include "common.cuh"
@@ -78,6 +83,48 @@ __global__ void __launch_bounds__(256) generic_kernel(UpfirdnArgs p, long long t
     }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// Output helpers shared by the tiled kernels.  A thread owns 4 consecutive outputs of a row.
+template <class T> __device__ __forceinline__ void store4(T* dst, float a, float b, float c, float d);
+template <> __device__ __forceinline__ void store4<float>(float* dst, float a, float b, float c, float d) {
+    __stcs(reinterpret_cast<float4*>(dst), make_float4(a, b, c, d));
+}
+template <> __device__ __forceinline__ void store4<__half>(__half* dst, float a, float b, float c, float d) {
+    const __half2 lo = __floats2half2_rn(a, b), hi = __floats2half2_rn(c, d);
+    uint2 v; v.x = *reinterpret_cast<const uint32_t*>(&lo); v.y = *reinterpret_cast<const uint32_t*>(&hi);
+    __stcs(reinterpret_cast<uint2*>(dst), v);
+}
+template <> __device__ __forceinline__ void store4<__nv_bfloat16>(__nv_bfloat16* dst, float a, float b, float c, float d) {
+    const __nv_bfloat162 lo = __floats2bfloat162_rn(a, b), hi = __floats2bfloat162_rn(c, d);
+    uint2 v; v.x = *reinterpret_cast<const uint32_t*>(&lo); v.y = *reinterpret_cast<const uint32_t*>(&hi);
+    __stcs(reinterpret_cast<uint2*>(dst), v);
+}
+
+// every row of y starts on a 4-element boundary: a thread's 4 outputs go out as one 16-byte (8-byte for 16-bit types) store
+template <class T> __device__ __forceinline__ bool rows_aligned4(const UpfirdnArgs& p) {
+    return ((p.ys_h & 3) == 0) && ((p.ys_c & 3) == 0) && ((p.ys_n & 3) == 0) && (((uintptr_t)p.y & (4 * sizeof(T) - 1)) == 0);
+}
+
+// Unaligned rows: the CTA's TH x TW output tile goes through shared memory (`stage`, rows of PITCH floats, written as float4) and leaves as whole row
+// segments, consecutive lanes writing consecutive elements (a warp store covers 128 contiguous bytes instead of 32 4-byte
+// pieces 16 bytes apart).  Called by all 256 threads; `stage` must not alias live input data (caller syncs before).
+template <class T, int TW, int TH, int PITCH>
+__device__ __forceinline__ void store_tile_staged(const float* stage, T* yp, long long ys_h, int ox0, int oy0, int ow, int oh) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    #pragma unroll 1
+    for (int ry = warp; ry < TH; ry += 8) {
+        const int oy = oy0 + ry;
+        if (oy >= oh) break;
+        T* row = yp + (long long)oy * ys_h + ox0;
+        #pragma unroll
+        for (int k = 0; k < TW / 32; k++) {
+            const int rx = lane + 32 * k;
+            if (ox0 + rx < ow) row[rx] = from_acc<T>(stage[ry * PITCH + rx]);
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // up = down = 1, fw, fh <= 4, x/y unit stride along W.
 constexpr int TILE_W = 128, TILE_H = 32, HALO = 3;
@@ -104,8 +151,7 @@ __global__ void __launch_bounds__(256) fir_tile_kernel(UpfirdnArgs p, int tiles_
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;      // 32 x 8 threads, 4 x 4 outputs each
     const T* x = (const T*)p.x;
     T* y = (T*)p.y;
-    const bool vec_store = (sizeof(T) == 4) && ((p.ys_h & 3) == 0) && ((p.ys_c & 3) == 0) && ((p.ys_n & 3) == 0) &&
-                           (((uintptr_t)p.y & 15) == 0);
+    const bool vec_store = rows_aligned4<T>(p);
 
     for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
         const int bx = (int)(t % tiles_x);
@@ -169,18 +215,25 @@ __global__ void __launch_bounds__(256) fir_tile_kernel(UpfirdnArgs p, int tiles_
             }
         }
         T* yp = y + n * p.ys_n + c * p.ys_c;
-        #pragma unroll
-        for (int a = 0; a < 4; a++) {
-            const int oy = oy0 + cy + a, ox = ox0 + cx;
-            if (oy >= p.oh || ox >= p.ow) continue;
-            T* dst = yp + (long long)oy * p.ys_h + ox;
-            if (vec_store && ox + 3 < p.ow) {
-                float4 o4 = make_float4(acc[a][0], acc[a][1], acc[a][2], acc[a][3]);
-                __stcs(reinterpret_cast<float4*>(dst), o4);
-            } else {
-                #pragma unroll
-                for (int b = 0; b < 4; b++) if (ox + b < p.ow) dst[b] = from_acc<T>(acc[a][b]);
+        if (vec_store) {
+            #pragma unroll
+            for (int a = 0; a < 4; a++) {
+                const int oy = oy0 + cy + a, ox = ox0 + cx;
+                if (oy >= p.oh || ox >= p.ow) continue;
+                T* dst = yp + (long long)oy * p.ys_h + ox;
+                if (ox + 3 < p.ow) store4<T>(dst, acc[a][0], acc[a][1], acc[a][2], acc[a][3]);
+                else {
+                    #pragma unroll
+                    for (int b = 0; b < 4; b++) if (ox + b < p.ow) dst[b] = from_acc<T>(acc[a][b]);
+                }
             }
+        } else {
+            __syncthreads();        // every thread has read its window: the halo tile becomes the output stage
+            #pragma unroll
+            for (int a = 0; a < 4; a++)
+                *reinterpret_cast<float4*>(&sx[cy + a][cx]) = make_float4(acc[a][0], acc[a][1], acc[a][2], acc[a][3]);
+            __syncthreads();
+            store_tile_staged<T, TILE_W, TILE_H, SM_W>(&sx[0][0], yp, p.ys_h, ox0, oy0, p.ow, p.oh);
         }
     }
 }
@@ -211,8 +264,7 @@ __global__ void __launch_bounds__(256) fir_down2_kernel(UpfirdnArgs p, int tiles
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const T* x = (const T*)p.x;
     T* y = (T*)p.y;
-    const bool vec_store = (sizeof(T) == 4) && ((p.ys_h & 3) == 0) && ((p.ys_c & 3) == 0) && ((p.ys_n & 3) == 0) &&
-                           (((uintptr_t)p.y & 15) == 0);
+    const bool vec_store = rows_aligned4<T>(p);
     for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
         const int bx = (int)(t % tiles_x);
         long long r = t / tiles_x;
@@ -264,13 +316,126 @@ __global__ void __launch_bounds__(256) fir_down2_kernel(UpfirdnArgs p, int tiles
                 for (int jx = 0; jx < 4; jx++) acc[o] = fmaf(in[2 * o + jx], k[jy][jx], acc[o]);
         }
         const int oy = oy0 + ty, ox = ox0 + 4 * tx;
-        if (oy < p.oh && ox < p.ow) {
-            T* dst = y + n * p.ys_n + c * p.ys_c + (long long)oy * p.ys_h + ox;
-            if (vec_store && ox + 3 < p.ow) __stcs(reinterpret_cast<float4*>(dst), make_float4(acc[0], acc[1], acc[2], acc[3]));
-            else {
-                #pragma unroll
-                for (int o = 0; o < 4; o++) if (ox + o < p.ow) dst[o] = from_acc<T>(acc[o]);
+        T* yp = y + n * p.ys_n + c * p.ys_c;
+        if (vec_store) {
+            if (oy < p.oh && ox < p.ow) {
+                T* dst = yp + (long long)oy * p.ys_h + ox;
+                if (ox + 3 < p.ow) store4<T>(dst, acc[0], acc[1], acc[2], acc[3]);
+                else {
+                    #pragma unroll
+                    for (int o = 0; o < 4; o++) if (ox + o < p.ow) dst[o] = from_acc<T>(acc[o]);
+                }
             }
+        } else {
+            __syncthreads();
+            *reinterpret_cast<float4*>(&sx[ty][4 * tx]) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+            __syncthreads();
+            store_tile_staged<T, D2_TILE_W, D2_TILE_H, D2_SM_W>(&sx[0][0], yp, p.ys_h, ox0, oy0, p.ow, p.oh);
+        }
+    }
+}
+
+// up = 2 in both axes, down = 1, fw, fh <= 4, unit stride along W (upsample2d of the image skip, networks.py ToRGB path /
+// upfirdn2d.py:326-348, and the gradient of every down = 2 call, upfirdn2d.py:232-247).  out[o] = sum_j z[o + j - pad0] k[j] with
+// z[2i] = x[i], z[odd] = 0: an output of parity q = (o - pad0) & 1 sees taps q and q + 2 on inputs (o - pad0 + q) / 2 and the
+// next one.  PX / PY = parity of padx0 / pady0, so a thread's 4 x 4 outputs (tile origins are even) have compile-time tap
+// sets: 4 FMAs per output from a 4 x 4 input window read as two 64-bit shared loads per row.
+constexpr int U2_TILE_W = 128, U2_TILE_H = 32;
+constexpr int U2_SM_W = 68, U2_SM_H = 18;         // 66 x 18 inputs used
+constexpr int U2_STAGE_W = 132;
+
+template <class T, int PX, int PY>
+__global__ void __launch_bounds__(256) fir_up2_kernel(UpfirdnArgs p, int tiles_x, int tiles_y, long long total_tiles) {
+    typedef float S;
+    __shared__ __align__(16) S sx[U2_SM_H][U2_SM_W];
+    __shared__ __align__(16) S dyn_stage[U2_TILE_H * U2_STAGE_W];     // output stage, used only when rows are unaligned
+    S k[4][4];
+    #pragma unroll
+    for (int jy = 0; jy < 4; jy++)
+        #pragma unroll
+        for (int jx = 0; jx < 4; jx++) {
+            S v = 0;
+            if (jy < p.fh && jx < p.fw) {
+                const int sy = p.flip ? jy : p.fh - 1 - jy, sxx = p.flip ? jx : p.fw - 1 - jx;
+                v = p.f[sy * p.fs_y + sxx * p.fs_x] * p.gain;
+            }
+            k[jy][jx] = v;
+        }
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;      // 32 x 8 threads, 4 x 4 outputs each
+    const T* x = (const T*)p.x;
+    T* y = (T*)p.y;
+    const bool vec_store = rows_aligned4<T>(p);
+    for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const int bx = (int)(t % tiles_x);
+        long long r = t / tiles_x;
+        const int by = (int)(r % tiles_y); r /= tiles_y;
+        const int c = (int)(r % p.c);
+        const int n = (int)(r / p.c);
+        const int ox0 = bx * U2_TILE_W, oy0 = by * U2_TILE_H;
+        // first input column / row any output of the tile can touch: (o0 - pad0 + P) / 2 (exact: the numerator is even)
+        const int ix0 = (ox0 - p.padx0 + PX) >> 1, iy0 = (oy0 - p.pady0 + PY) >> 1;
+        const T* xp = x + n * p.xs_n + c * p.xs_c;
+        __syncthreads();
+        {
+            constexpr int USED_W = 66, PER = (U2_SM_H * USED_W + 255) / 256;
+            S v[PER];
+            #pragma unroll
+            for (int i = 0; i < PER; i++) {
+                const int idx = threadIdx.x + 256 * i;
+                const int ry = idx / USED_W, rx = idx - ry * USED_W;
+                const int iy = iy0 + ry, ix = ix0 + rx;
+                const bool ok = ry < U2_SM_H && iy >= 0 && iy < p.ih && ix >= 0 && ix < p.iw;
+                v[i] = ok ? to_acc<T>(__ldg(xp + (long long)iy * p.xs_h + ix)) : (S)0;
+            }
+            #pragma unroll
+            for (int i = 0; i < PER; i++) {
+                const int idx = threadIdx.x + 256 * i;
+                const int ry = idx / USED_W, rx = idx - ry * USED_W;
+                if (ry < U2_SM_H) sx[ry][rx] = v[i];
+            }
+        }
+        __syncthreads();
+        S in[4][4];
+        #pragma unroll
+        for (int ry = 0; ry < 4; ry++) {
+            const float2 lo = *reinterpret_cast<const float2*>(&sx[2 * ty + ry][2 * tx]);
+            const float2 hi = *reinterpret_cast<const float2*>(&sx[2 * ty + ry][2 * tx + 2]);
+            in[ry][0] = lo.x; in[ry][1] = lo.y; in[ry][2] = hi.x; in[ry][3] = hi.y;
+        }
+        S acc[4][4];
+        #pragma unroll
+        for (int a = 0; a < 4; a++) {
+            const int qy = (PY + a) & 1, ry = (a + qy - PY) / 2;
+            #pragma unroll
+            for (int b = 0; b < 4; b++) {
+                const int qx = (PX + b) & 1, rx = (b + qx - PX) / 2;
+                S s = in[ry][rx] * k[qy][qx];
+                s = fmaf(in[ry][rx + 1], k[qy][qx + 2], s);
+                s = fmaf(in[ry + 1][rx], k[qy + 2][qx], s);
+                s = fmaf(in[ry + 1][rx + 1], k[qy + 2][qx + 2], s);
+                acc[a][b] = s;
+            }
+        }
+        const int cx = tx * 4, cy = ty * 4;
+        T* yp = y + n * p.ys_n + c * p.ys_c;
+        if (vec_store) {
+            #pragma unroll
+            for (int a = 0; a < 4; a++) {
+                const int oy = oy0 + cy + a, ox = ox0 + cx;
+                if (oy >= p.oh || ox >= p.ow) continue;
+                T* dst = yp + (long long)oy * p.ys_h + ox;
+                if (ox + 3 < p.ow) store4<T>(dst, acc[a][0], acc[a][1], acc[a][2], acc[a][3]);
+                else {
+                    #pragma unroll
+                    for (int b = 0; b < 4; b++) if (ox + b < p.ow) dst[b] = from_acc<T>(acc[a][b]);
+                }
+            }
+        } else {
+            #pragma unroll
+            for (int a = 0; a < 4; a++)
+                *reinterpret_cast<float4*>(&dyn_stage[(cy + a) * U2_STAGE_W + cx]) = make_float4(acc[a][0], acc[a][1], acc[a][2], acc[a][3]);
+            __syncthreads();
+            store_tile_staged<T, U2_TILE_W, U2_TILE_H, U2_STAGE_W>(dyn_stage, yp, p.ys_h, ox0, oy0, p.ow, p.oh);
         }
     }
 }
@@ -281,7 +446,19 @@ static int launch_upfirdn(const UpfirdnArgs& p, cudaStream_t stream) {
                          p.xs_w == 1 && p.ys_w == 1 && sizeof(T) <= 4;
     const bool down2_ok = p.upx == 1 && p.upy == 1 && p.downx == 2 && p.downy == 2 && p.fw <= 4 && p.fh <= 4 &&
                           p.xs_w == 1 && p.ys_w == 1 && sizeof(T) <= 4;
-    if (down2_ok) {
+    const bool up2_ok = p.upx == 2 && p.upy == 2 && p.downx == 1 && p.downy == 1 && p.fw <= 4 && p.fh <= 4 &&
+                        p.xs_w == 1 && p.ys_w == 1 && sizeof(T) <= 4;
+    if (up2_ok) {
+        const int tiles_x = (p.ow + U2_TILE_W - 1) / U2_TILE_W, tiles_y = (p.oh + U2_TILE_H - 1) / U2_TILE_H;
+        const long long total = (long long)tiles_x * tiles_y * p.c * p.n;
+        void (*kern)(UpfirdnArgs, int, int, long long) =
+            (p.padx0 & 1) ? ((p.pady0 & 1) ? fir_up2_kernel<T, 1, 1> : fir_up2_kernel<T, 1, 0>)
+                          : ((p.pady0 & 1) ? fir_up2_kernel<T, 0, 1> : fir_up2_kernel<T, 0, 0>);
+        long long blocks = total;
+        const long long cap = (long long)sm_count() * occupancy_of(kern, 256, 0);
+        if (blocks > cap) blocks = cap;
+        kern<<<(unsigned)blocks, 256, 0, stream>>>(p, tiles_x, tiles_y, total);
+    } else if (down2_ok) {
         const int tiles_x = (p.ow + D2_TILE_W - 1) / D2_TILE_W, tiles_y = (p.oh + D2_TILE_H - 1) / D2_TILE_H;
         const long long total = (long long)tiles_x * tiles_y * p.c * p.n;
         long long blocks = total;

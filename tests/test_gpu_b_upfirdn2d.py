@@ -61,6 +61,53 @@ def test_generator_families_vs_oracle(shape, up, down, pad, gain, dtype, tol):
     assert max_abs(got, want) <= tol * 8 * gain, max_abs(got, want)
 
 
+# tiled up = 2 / down = 2 kernels: every parity of the padding (compile-time tap sets of fir_up2_kernel), negative padding (crop),
+# non-square and asymmetric filters in both flip conventions, odd output widths (rows leave through the shared-memory stage)
+@pytest.mark.parametrize('dtype,tol', [(torch.float32, 3e-6), (torch.float16, 2e-3)])
+@pytest.mark.parametrize('pad', [(2, 1, 2, 1), (1, 2, 2, 1), (2, 1, 1, 2), (1, 1, 1, 1), (3, 0, 0, 3), (0, 0, 0, 0), (-1, 2, 1, -2), (5, 4, 4, 5)], ids=str)
+@pytest.mark.parametrize('shape', [(2, 3, 32, 32), (1, 2, 67, 131), (1, 5, 17, 300), (3, 1, 1, 1)], ids=str)
+def test_up2_tiled_kernel_vs_oracle(shape, pad, dtype, tol):
+    g = torch.Generator().manual_seed(23)
+    x = torch.randn(*shape, generator=g, dtype=torch.float64).to(dtype)
+    filters = [(ref_ops.setup_filter([1, 3, 3, 1]), False), (torch.randn(3, 4, generator=g), False), (torch.randn(4, 2, generator=g), True),
+               (torch.randn(1, 1, generator=g), False)]
+    for f, flip in filters:
+        fh, fw = f.shape
+        if shape[3] * 2 + pad[0] + pad[1] - fw + 1 < 1 or shape[2] * 2 + pad[2] + pad[3] - fh + 1 < 1:
+            continue
+        want = ref_ops.upfirdn2d(x.double(), f, up=2, padding=list(pad), flip_filter=flip, gain=4)
+        got = upfirdn2d.upfirdn2d(x.to(DEV), f.to(DEV), up=2, padding=list(pad), flip_filter=flip, gain=4)
+        assert got.dtype == dtype and tuple(got.shape) == tuple(want.shape)
+        assert max_abs(got, want) <= tol * 8 * max(1.0, float(want.abs().max())), (fh, fw, flip, max_abs(got, want))
+
+
+@pytest.mark.parametrize('dtype,tol', [(torch.float32, 3e-6), (torch.float16, 2e-3)])
+@pytest.mark.parametrize('shape,pad', [((2, 3, 66, 70), (1, 1, 1, 1)), ((1, 2, 131, 259), (2, 1, 1, 2)), ((1, 4, 37, 130), (0, 0, 0, 0)), ((1, 1, 9, 520), (1, 1, 1, 1))], ids=str)
+def test_down2_tiled_kernel_ragged_and_odd_widths(shape, pad, dtype, tol):
+    g = torch.Generator().manual_seed(24)
+    x = torch.randn(*shape, generator=g, dtype=torch.float64).to(dtype)
+    for f, flip in [(ref_ops.setup_filter([1, 3, 3, 1]), False), (torch.randn(4, 3, generator=g), True)]:
+        want = ref_ops.upfirdn2d(x.double(), f, down=2, padding=list(pad), flip_filter=flip)
+        got = upfirdn2d.upfirdn2d(x.to(DEV), f.to(DEV), down=2, padding=list(pad), flip_filter=flip)
+        assert tuple(got.shape) == tuple(want.shape)
+        assert max_abs(got, want) <= tol * 8 * max(1.0, float(want.abs().max())), max_abs(got, want)
+
+
+def test_up2_is_the_adjoint_of_down2():
+    """<down2(x), y> == <x, up2'(y)> with the padding list of the reference's backward (upfirdn2d.py:232-247): the property the D / R1
+    backward relies on, at the full 512 px size of BASELINE configs[4]"""
+    torch.manual_seed(3)
+    f = ref_ops.setup_filter([1, 3, 3, 1]).to(DEV)
+    x = torch.randn(2, 8, 512, 512, device=DEV, requires_grad=True)
+    y = upfirdn2d.upfirdn2d(x, f, down=2, padding=[1, 1, 1, 1])
+    dy = torch.randn_like(y)
+    dx, = torch.autograd.grad(y, [x], dy)
+    lhs, rhs = float((y.double() * dy.double()).sum()), float((x.double() * dx.double()).sum())
+    assert abs(lhs - rhs) <= 1e-6 * max(1.0, abs(lhs)) * 50, (lhs, rhs)
+    want = upfirdn2d.upfirdn2d(dy, f, up=2, padding=[2, 1, 2, 1], flip_filter=True, impl='ref')
+    assert float((dx - want).abs().max()) < 2e-5
+
+
 def test_channels_last_and_strided_inputs():
     g = torch.Generator().manual_seed(22)
     x = torch.randn(2, 8, 20, 24, generator=g)
