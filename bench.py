@@ -398,15 +398,6 @@ def train_leg(steps, warmup, batch, precision, device, rank, world, fp16_res=3):
     phase_ms = {}
     for ph in dict.fromkeys(p['name'] for p in step.phases):
         phase_ms[ph] = timed(lambda: step(data, phases=[ph]), 2)
-    # the exchange step alone: the same iteration with the gradient all-reduce suppressed (DDP no_sync) -> exposed all-reduce time
-    nosync_ms = None
-    if world > 1:
-        orig = step.loss.accumulate_gradients
-        step.loss.accumulate_gradients = lambda **kw: orig(**{**kw, 'sync': False})
-        timed(lambda: step(data), 1)
-        nosync_ms = timed(lambda: step(data), steps)
-        step.loss.accumulate_gradients = orig
-
     # end to end: uint8 pinned-host batch in, loss scalar back, every iteration
     def e2e_step():
         d = train_inputs_to_device(host, device)
@@ -414,6 +405,18 @@ def train_leg(steps, warmup, batch, precision, device, rank, world, fp16_res=3):
         return float(st['Loss/scores/real'].item())
     e2e_step()
     e2e_ms = timed(e2e_step, steps)
+    # the exchange step alone: the same iteration on the same networks WITHOUT the DistributedDataParallel wrappers (no bucketing, no
+    # all-reduce) -> compute-only time per rank; ms - compute-only = exposed all-reduce.  (DDP.no_sync cannot be used for this: the loss
+    # runs G_style_encoding under a synchronising forward in phases that never back-propagate into it, as the reference does, and a
+    # no_sync forward after such an unfinished reduction trips the reducer.)  Measured last: the replicas' weights diverge from here on.
+    nosync_ms = None
+    if world > 1:
+        import gc
+        step.loss = step.ddp_modules = None     # drop the DDP wrappers: their reducers take their autograd hooks off the parameters
+        gc.collect()
+        local = ts.TrainingStep(G, D, DP, device, batch_size=batch * world, distributed=False)
+        local(data)
+        nosync_ms = timed(lambda: local(data), steps)
     grad_bytes = {n: 4 * sum(p.numel() for p in m.parameters()) for n, m in (('G', G), ('D', D), ('D_parsing', DP))}
     return {'ms_per_step': ms, 'images_per_sec': batch * world / (ms * 1e-3), 'e2e_ms_per_step': e2e_ms,
             'e2e_images_per_sec': batch * world / (e2e_ms * 1e-3), 'h2d_bytes_per_step': sum(v.numel() for v in host.values()),

@@ -47,6 +47,9 @@ PGPP_API int pgpp_version(void);
 PGPP_API const char* pgpp_last_error(void);
 /* number of kernel launches issued through this library by the calling process (bench.py's gpu_launches) */
 PGPP_API int64_t pgpp_launch_count(void);
+/* The PGPP_* ablation switches are read from the environment once, when the library is loaded; this re-reads
+ * them (timing tools that flip a switch between launches). */
+PGPP_API void pgpp_refresh_env(void);
 
 /* ---------------------------------------------------------------------------------------------
  * bias_act: y = clamp(act(x + b[(i / step_b) % size_b]) * gain), or its 1st / 2nd derivative.

@@ -185,7 +185,7 @@ extern "C" int pgpp_bias_act(const void* x, const void* b, const void* xref, con
     p.size_x = size_x; p.size_b = b ? (int)size_b : 1; p.step_b = b ? step_b : 1;
     p.grad = grad; p.alpha = alpha; p.gain = gain; p.clamp = clamp;
     p.bias_mode = b ? 1 : 0;
-    p.hint = getenv("PGPP_BA_NOSTREAM") ? 0 : 1;
+    p.hint = env_flags().ba_nostream ? 0 : 1;
     auto magic = [](unsigned dv, unsigned& m, unsigned& sft) {
         sft = 0; while ((1ull << sft) < dv) sft++;
         m = (unsigned)(((1ull << (31 + sft)) + dv - 1) / dv);

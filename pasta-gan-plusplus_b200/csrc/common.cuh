@@ -16,6 +16,15 @@ extern std::atomic<long long> g_launches;
 
 inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
+// Ablation switches (PGPP_* environment variables): read once per process, not per launch;
+// pgpp_refresh_env() re-reads them (timing tools that flip a switch between launches call it).
+struct EnvFlags {
+    bool igemm_no_reuse, igemm_no_slab2, igemm_no_resident, igemm_no_stack, igemm_no_lean_epilogue, igemm_no_tma_store;
+    bool wgrad_no_reuse, ba_nostream, fir_packed_no_tile;
+    int igemm_debug;
+};
+const EnvFlags& env_flags();
+
 #define PGPP_REQUIRE(cond, ...)                                  \
     do { if (!(cond)) { ::pgpp::set_error(__VA_ARGS__); return PGPP_ERR_INVALID; } } while (0)
 
@@ -63,6 +72,10 @@ template <> __device__ __forceinline__ float to_acc<__nv_bfloat16>(__nv_bfloat16
 template <class T> __device__ __forceinline__ T from_acc(typename Acc<T>::type v) { return (T)v; }
 template <> __device__ __forceinline__ __half from_acc<__half>(float v) { return __float2half_rn(v); }
 template <> __device__ __forceinline__ __nv_bfloat16 from_acc<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+// tile index -> coordinates in 32-bit arithmetic (callers guarantee fewer than 2^31 tiles): r = t % d, t /= d.  A 64-bit division by a
+// runtime divisor costs ~100 instructions per thread, several times per tile in a persistent kernel.
+__device__ __forceinline__ int divmod_u32(unsigned& t, unsigned d) { const unsigned q = t / d, r = t - q * d; t = q; return (int)r; }
 
 // packed float32x2 arithmetic (sm_100a FFMA2 / FADD2): halves the instruction count of the bandwidth-bound kernels that work on the
 // bf16 operand format, where the conversions and sums per byte are what limits them

@@ -1054,14 +1054,15 @@ extern "C" int pgpp_conv2d_igemm(const pgpp_conv_desc* d, void* stream) {
     PGPP_REQUIRE(dil_y == 1 || d->stride == 1, "dil_y > 1 needs stride 1");
     p.reuse = (d->stride == 1 && d->kh > 1 && d->conv_w >= 16 && d->conv_h >= 8 && (d->kh - 1) * dil_y <= 6) ? 1 : 0;
     PGPP_REQUIRE(dil_y == 1 || p.reuse, "dil_y > 1 is only supported on the slab-reuse path (images of at least 16 x 8, (kh-1)*dil_y <= 6)");
-    if (getenv("PGPP_IGEMM_NO_REUSE")) p.reuse = 0;
+    const EnvFlags& env = env_flags();
+    if (env.igemm_no_reuse) p.reuse = 0;
     // single-slab mode (reuse == 2): layers whose GEMM N is at most 64 are bound by the L2 -> shared-memory traffic of the three
     // filter-column slabs; an 8 x 16 pixel tile reads ONE (8 + kw - 1) x (16 + kh - 1) slab per (channel block, part) instead and
     // takes every tap as a row-shifted descriptor view of it (2.7x fewer activation bytes for 3 x 3).  Needs resident weights.
     const int slab_pitch = 8 + d->kw - 1, slab_rows2 = 16 + d->kh - 1;
     const bool slab2_shape = d->stride == 1 && d->kh * d->kw > 1 && d->kh * d->kw <= 64 && dil_y == 1 && d->c_pad % 64 == 0 && d->block_n <= 64 &&
                              d->phases * d->phase_stride <= d->block_n && d->conv_w >= 8 && d->conv_h >= 16 && need_parts <= 2 &&
-                             !getenv("PGPP_IGEMM_NO_SLAB2") && !getenv("PGPP_IGEMM_NO_RESIDENT");
+                             !env.igemm_no_slab2 && !env.igemm_no_resident;
     if (slab2_shape) {
         const long long stage = ((long long)slab_pitch * slab_rows2 * 128 + 1023) & ~1023ll;
         const long long n_bt = (long long)(d->c_pad / 64) * d->kh * d->kw * need_parts;
@@ -1120,7 +1121,7 @@ extern "C" int pgpp_conv2d_igemm(const pgpp_conv_desc* d, void* stream) {
     const long long smem_max = 227 * 1024;
     const long long n_btiles = (long long)p.n_groups * p.num_cb * p.inner * p.parts;
     p.b_resident = 0;
-    if (p.tiles_col == 1 && n_btiles <= 64 && !getenv("PGPP_IGEMM_NO_RESIDENT") && smem_need(2, n_btiles) <= smem_max &&
+    if (p.tiles_col == 1 && n_btiles <= 64 && !env.igemm_no_resident && smem_need(2, n_btiles) <= smem_max &&
         p.total_tiles > sm_count()) {
         p.b_resident = 1;
         p.b_stages = (int)n_btiles;
@@ -1158,7 +1159,7 @@ extern "C" int pgpp_conv2d_igemm(const pgpp_conv_desc* d, void* stream) {
                                      (d->act_fn == PGPP_ACT_LRELU && d->alpha >= 0.f && d->alpha <= 1.f))) ? 1 : 0;
     // stacked products (see mma_role): fp32-parity mode with 2 parts, resident 64-column weight tiles, fast epilogue
     p.stack = (need_parts == 2 && d->block_n == 64 && p.b_resident && p.kb == 64 && (p.inner == 3 || p.inner == 1 || p.reuse == 2) && p.tn == 1 && p.fold_gain &&
-               !d->spade_x && !getenv("PGPP_IGEMM_NO_STACK")) ? 1 : 0;
+               !d->spade_x && !env.igemm_no_stack) ? 1 : 0;
     p.acc_cols = p.stack ? 2 * d->block_n : d->block_n;
     p.idesc_stack = (1u << 4) | ab_fmt | ((unsigned)((2 * d->block_n) >> 3) << 17) | ((unsigned)(kTileM >> 4) << 24);
     if (p.stack) p.tmem_cols = 256;
@@ -1170,7 +1171,7 @@ extern "C" int pgpp_conv2d_igemm(const pgpp_conv_desc* d, void* stream) {
     magic((unsigned)p.tiles_x, p.div_x_m, p.div_x_s);
     magic((unsigned)p.tiles_y, p.div_y_m, p.div_y_s);
     PGPP_REQUIRE(p.total_tiles < (1ll << 31), "too many tiles");
-    { const char* e = getenv("PGPP_IGEMM_DEBUG"); p.dbg = e ? atoi(e) : 0; }
+    p.dbg = env.igemm_debug;
 
     // tensor maps
     CUtensorMap map_a, map_b;
@@ -1197,7 +1198,7 @@ extern "C" int pgpp_conv2d_igemm(const pgpp_conv_desc* d, void* stream) {
     // lean operand-format epilogue (EPI 1) when the launch needs nothing else
     const bool epi_packed = p.tn == 1 && p.fold_gain && d->out_dtype == PGPP_BF16 && p.os_c == 1 && d->phases == 1 && !d->spade_x &&
                             d->o % 16 == 0 && d->block_n >= 32 && ((uintptr_t)d->out & 31) == 0 && p.os_w % 16 == 0 && p.os_h % 16 == 0 &&
-                            p.os_n % 16 == 0 && p.out_part_stride % 16 == 0 && !getenv("PGPP_IGEMM_NO_LEAN_EPILOGUE");
+                            p.os_n % 16 == 0 && p.out_part_stride % 16 == 0 && !env.igemm_no_lean_epilogue;
     {
         // once per device (the attribute is per function per context)
         static std::atomic<bool> done[64];

@@ -35,17 +35,26 @@ __device__ __forceinline__ void split_store(float v, __nv_bfloat16* dst, long lo
 // threads write the 128-byte channel row of a pixel with one 128-bit store each.
 struct TileGeom { int log_tw, x_tiles, y_tiles, c_tiles; };
 
-__device__ __forceinline__ uint4 split_packet(float (&v)[8][4], int k, int f16 = 0) {
+// 8 consecutive channels of pixel k as one 16-byte packet of the current bf16 part; `more`: another part follows, so the residual
+// v - bf16(v) is left in v (packed conversions: one cvt.rn.bf16x2.f32 per channel pair)
+__device__ __forceinline__ uint4 split_packet(float (&v)[8][4], int k, int f16 = 0, bool more = true) {
     if (f16) {
         __align__(16) __half hq[8];
         #pragma unroll
         for (int j = 0; j < 8; j++) hq[j] = __float2half_rn(v[j][k]);
         return *reinterpret_cast<const uint4*>(hq);
     }
-    __align__(16) __nv_bfloat16 q[8];
+    uint32_t w[4];
     #pragma unroll
-    for (int j = 0; j < 8; j++) { q[j] = __float2bfloat16_rn(v[j][k]); v[j][k] -= __bfloat162float(q[j]); }
-    return *reinterpret_cast<const uint4*>(q);
+    for (int j = 0; j < 4; j++) {
+        const __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * j][k], v[2 * j + 1][k]);
+        w[j] = *reinterpret_cast<const uint32_t*>(&h);
+        if (more) {
+            v[2 * j][k] -= __uint_as_float(w[j] << 16);
+            v[2 * j + 1][k] -= __uint_as_float(w[j] & 0xffff0000u);
+        }
+    }
+    return make_uint4(w[0], w[1], w[2], w[3]);
 }
 
 // writes the tile held in v (see above) to out[part][n][y][x][c_off + c0 ...]; sm = parts * 128 * 8 packets
@@ -56,7 +65,7 @@ __device__ __forceinline__ void emit_tile(float (&v)[8][4], uint4* sm, int parts
     for (int part = 0; part < parts; part++) {
         #pragma unroll
         for (int k = 0; k < 4; k++)
-            sm[(part * 128 + 4 * lane + k) * 8 + (warp ^ (lane & 7))] = split_packet(v, k, f16);
+            sm[(part * 128 + 4 * lane + k) * 8 + (warp ^ (lane & 7))] = split_packet(v, k, f16, part + 1 < parts);
     }
     __syncthreads();
     const int tw_mask = (1 << log_tw) - 1;
@@ -305,65 +314,86 @@ struct DirectArgs {
 // through emit_tile as the bf16 operand format of the next convolution, with bias / activation / gain / clamp applied.
 constexpr int kDirectMaxTaps = 16;
 
-template <int KW>
+// KH, CIN > 0: compile-time filter height / input channels (fully unrolled tap loops); 0: runtime values.
+// The 8 channels of a thread are accumulated as 4 packed float32 pairs (FFMA2): the kernel is bound by instruction issue, not by
+// its 2 GB of output (ncu: profiles/r02_ncu_small_kernels.md).
+template <int KW, int KH, int CIN>
 __global__ void __launch_bounds__(256) conv_direct_kernel(DirectArgs p, TileGeom g, long long total_tiles) {
     extern __shared__ uint4 sm_packets[];
-    __shared__ float sw[64 * kDirectMaxTaps];
+    __shared__ __align__(16) float sw[kDirectMaxTaps * 64];      // [tap][channel of the 64-channel tile]
     __shared__ float sb[64];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int tw_mask = (1 << g.log_tw) - 1;
     const long long plane = (long long)p.h * p.wd;
+    const int kh = KH ? KH : p.kh, cin = CIN ? CIN : p.c;
     int loaded_ct = -1;
     // persistent over the tiles: the weights of a 64-channel tile are staged once (the channel tile is the slowest tile index)
     for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        long long b = tile;
-        const int xt = (int)(b % g.x_tiles); b /= g.x_tiles;
-        const int yt = (int)(b % g.y_tiles); b /= g.y_tiles;
-        const int n = (int)(b % p.n);
-        const int ct = (int)(b / p.n);
+        unsigned b = (unsigned)tile;
+        const int xt = divmod_u32(b, (unsigned)g.x_tiles);
+        const int yt = divmod_u32(b, (unsigned)g.y_tiles);
+        const int n = divmod_u32(b, (unsigned)p.n);
+        const int ct = (int)b;
         const int x0 = xt << g.log_tw, y0 = yt * (128 >> g.log_tw), c0 = ct * 64;
         __syncthreads();                        // previous tile's packets fully written out; weights no longer in use
         if (ct != loaded_ct) {
             for (int i = threadIdx.x; i < 64 * p.taps; i += 256) {
-                const int oc = c0 + i / p.taps;
-                sw[i] = oc < p.o ? p.w[(long long)oc * p.taps + i % p.taps] * p.wscale : 0.f;
+                const int tap = i >> 6, oc = c0 + (i & 63);
+                sw[i] = oc < p.o ? p.w[(long long)oc * p.taps + tap] * p.wscale : 0.f;
             }
             if (threadIdx.x < 64) sb[threadIdx.x] = (p.bias && c0 + threadIdx.x < p.o) ? p.bias[c0 + threadIdx.x] : 0.f;
             loaded_ct = ct;
             __syncthreads();
         }
         const int y = y0 + ((4 * lane) >> g.log_tw), x = x0 + ((4 * lane) & tw_mask);
-        float v[8][4];
+        f32x2 acc[4][4];                        // [channel pair][pixel]
         #pragma unroll
-        for (int i = 0; i < 8; i++)
+        for (int i = 0; i < 4; i++)
             #pragma unroll
-            for (int k = 0; k < 4; k++) v[i][k] = 0.f;
+            for (int k = 0; k < 4; k++) acc[i][k] = 0ull;
         if (y < p.h && x < p.wd) {
             const float* src = p.x + (long long)n * p.c * plane;
-            const float* wrow = sw + warp * 8 * p.taps;
-            for (int ci = 0; ci < p.c; ci++, src += plane) {
-                for (int ky = 0; ky < p.kh; ky++) {
-                    const int iy = y + ky - p.pad_y;
-                    const bool row_ok = iy >= 0 && iy < p.h;
-                    const float* row = src + (long long)iy * p.wd;
-                    float in[4 + KW - 1];
-                    #pragma unroll
-                    for (int j = 0; j < 4 + KW - 1; j++) {
-                        const int ix = x + j - KW / 2;
-                        in[j] = (row_ok && ix >= 0 && ix < p.wd) ? __ldg(row + ix) : 0.f;
-                    }
-                    const float* wt = wrow + (ci * p.kh + ky) * KW;
-                    #pragma unroll
-                    for (int kx = 0; kx < KW; kx++)
+            const float* wrow = sw + warp * 8;
+            #pragma unroll
+            for (int ci = 0; ci < (CIN ? CIN : kDirectMaxTaps); ci++) {
+                if (ci >= cin) break;
+                #pragma unroll
+                for (int ky = 0; ky < (KH ? KH : 1); ky++) {
+                    for (int kyr = ky; kyr < kh; kyr += (KH ? KH : 1)) {           // KH == 0: runtime loop over the filter rows
+                        const int iy = y + kyr - p.pad_y;
+                        const bool row_ok = iy >= 0 && iy < p.h;
+                        const float* row = src + (long long)ci * plane + (long long)iy * p.wd;
+                        f32x2 in2[4 + KW - 1];
                         #pragma unroll
-                        for (int i = 0; i < 8; i++) {
-                            const float wv = wt[i * p.taps + kx];
-                            #pragma unroll
-                            for (int k = 0; k < 4; k++) v[i][k] = fmaf(wv, in[kx + k], v[i][k]);
+                        for (int j = 0; j < 4 + KW - 1; j++) {
+                            const int ix = x + j - KW / 2;
+                            const float v = (row_ok && ix >= 0 && ix < p.wd) ? __ldg(row + ix) : 0.f;
+                            in2[j] = pack2(v, v);
                         }
+                        const float* wt = wrow + ((ci * kh + kyr) * KW) * 64;
+                        #pragma unroll
+                        for (int kx = 0; kx < KW; kx++) {
+                            const float4 wa = *reinterpret_cast<const float4*>(wt + kx * 64);
+                            const float4 wb = *reinterpret_cast<const float4*>(wt + kx * 64 + 4);
+                            const f32x2 w2[4] = {pack2(wa.x, wa.y), pack2(wa.z, wa.w), pack2(wb.x, wb.y), pack2(wb.z, wb.w)};
+                            #pragma unroll
+                            for (int i = 0; i < 4; i++)
+                                #pragma unroll
+                                for (int k = 0; k < 4; k++) ffma2(acc[i][k], w2[i], in2[kx + k]);
+                        }
+                        if (KH) break;
+                    }
                 }
             }
         }
+        float v[8][4];
+        #pragma unroll
+        for (int i = 0; i < 4; i++)
+            #pragma unroll
+            for (int k = 0; k < 4; k++) {
+                v[2 * i][k] = __uint_as_float((uint32_t)acc[i][k]);
+                v[2 * i + 1][k] = __uint_as_float((uint32_t)(acc[i][k] >> 32));
+            }
         #pragma unroll
         for (int i = 0; i < 8; i++) {
             const float bb = sb[warp * 8 + i];
@@ -755,6 +785,7 @@ extern "C" int pgpp_conv2d_direct(const float* x, const float* w, const float* b
     }
     TileGeom g = tile_geometry(h, wd, (o + 63) / 64 * 64);
     const long long total = (long long)g.x_tiles * g.y_tiles * g.c_tiles * n;
+    PGPP_REQUIRE(total < (1ll << 31), "direct convolution: too many tiles");
     auto launch = [&](auto kernel) -> int {
         if (smem > 40 * 1024) PGPP_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
         long long blocks = total;
@@ -763,7 +794,9 @@ extern "C" int pgpp_conv2d_direct(const float* x, const float* w, const float* b
         kernel<<<(unsigned)blocks, 256, smem, (cudaStream_t)stream>>>(p, g, total);
         return PGPP_OK;
     };
-    const int rc = kw == 1 ? launch(conv_direct_kernel<1>) : launch(conv_direct_kernel<3>);
+    const int rc = (kw == 3 && kh == 3 && c == 1) ? launch(conv_direct_kernel<3, 3, 1>)
+                 : (kw == 1 && kh == 1) ? launch(conv_direct_kernel<1, 1, 0>)
+                 : kw == 1 ? launch(conv_direct_kernel<1, 0, 0>) : launch(conv_direct_kernel<3, 0, 0>);
     if (rc != PGPP_OK) return rc;
     count_launch();
     PGPP_CUDA_OK(cudaGetLastError());

@@ -337,7 +337,7 @@ extern "C" int pgpp_conv2d_wgrad(const pgpp_wgrad_desc* d, void* stream) {
     // that one L slab of th + kh - 1 rows serves all vertical taps of a filter column (the ky shift is a whole number of
     // 8-pixel swizzle atoms); everything else takes the widest box that fits the image, then rows, then samples.
     p.reuse = (d->stride == 1 && d->kh > 1 && d->kh * bn <= 512 && d->ws >= 8 && (long long)d->ws * d->hs >= 64) ? 1 : 0;
-    if (getenv("PGPP_WGRAD_NO_REUSE")) p.reuse = 0;
+    if (env_flags().wgrad_no_reuse) p.reuse = 0;
     if (p.reuse) {
         p.tw = d->ws >= 16 ? 16 : 8; p.th = 64 / p.tw; p.tn = 1;
         p.t_group = d->kh; p.n_groups = d->kw;

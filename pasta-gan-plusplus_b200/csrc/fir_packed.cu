@@ -320,7 +320,7 @@ extern "C" int pgpp_fir_packed(const void* in, int in_parts, int64_t in_part_str
         PGPP_CUDA_OK(cudaGetLastError());
         return PGPP_OK;
     }
-    if (down == 1 && !getenv("PGPP_FIR_PACKED_NO_TILE")) {
+    if (down == 1 && !env_flags().fir_packed_no_tile) {
         // separable?  f = outer(ky, kx) with the pivot at the largest tap
         int pj = 0;
         for (int i = 1; i < 16; i++) if (fabsf(a.k[i]) > fabsf(a.k[pj])) pj = i;

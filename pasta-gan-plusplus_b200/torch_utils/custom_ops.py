@@ -68,6 +68,7 @@ def load_library():
     lib.pgpp_version.restype = i32
     lib.pgpp_last_error.restype = ctypes.c_char_p
     lib.pgpp_launch_count.restype = i64
+    lib.pgpp_refresh_env.restype = None
     lib.pgpp_bias_act.restype = i32
     lib.pgpp_bias_act.argtypes = [vp, vp, vp, vp, vp, vp, i64, i64, i64, i32, i32, i32, f32, f32, f32, vp]
     lib.pgpp_upfirdn2d.restype = i32
@@ -120,7 +121,7 @@ def load_library():
     return lib
 
 
-EXPORTED_SYMBOLS = ('pgpp_version', 'pgpp_last_error', 'pgpp_launch_count', 'pgpp_bias_act', 'pgpp_upfirdn2d',
+EXPORTED_SYMBOLS = ('pgpp_version', 'pgpp_last_error', 'pgpp_launch_count', 'pgpp_refresh_env', 'pgpp_bias_act', 'pgpp_upfirdn2d',
                     'pgpp_modconv_demod_coefs', 'pgpp_pack_activations', 'pgpp_pack_activations_slice', 'pgpp_pack_activations_f16',
                     'pgpp_pack_weights', 'pgpp_up2_weight_adjoint', 'pgpp_mul_reduce_hw', 'pgpp_modulate_weights',
                     'pgpp_spade_modulate_pack', 'pgpp_mix_pack', 'pgpp_conv2d_direct', 'pgpp_fir_pack', 'pgpp_fir_packed', 'pgpp_conv1x1_thin', 'pgpp_pack_im2col', 'pgpp_conv2d_igemm', 'pgpp_conv2d_wgrad', 'pgpp_u8_to_f32',
@@ -146,6 +147,11 @@ class WgradDesc(ctypes.Structure):
 
 def launch_count():
     return int(load_library().pgpp_launch_count())
+
+
+def refresh_env():
+    """re-read the PGPP_* ablation switches from os.environ (the library caches them at load time)"""
+    load_library().pgpp_refresh_env()
 
 
 def _check(status):

@@ -141,9 +141,10 @@ class ConstEncoderNetwork(torch.nn.Module):
         return x
 
 
-def _packed_chain(layers, x, tensor_last=True):
+def _packed_chain(layers, x, tensor_last=True, outs_into=None):
     """Run a chain of Conv2dLayers (stride 1 or down=2) in operand-format hand-over mode; returns every layer's output (PackedAct; the
-    last one an NCHW float32 tensor when `tensor_last`)."""
+    last one an NCHW float32 tensor when `tensor_last`).  `outs_into`: {height: PackedAct view} - a layer whose output has that height
+    writes into the given channel slice (the consumer's concat buffer) instead of a buffer of its own."""
     outs = []
     n, _, h, w = x.shape
     parts = S._parts()
@@ -154,7 +155,9 @@ def _packed_chain(layers, x, tensor_last=True):
             x = layer(x, fused=True)
             assert tuple(x.shape) == (n, oc, h, w)
         else:
-            out = PackedAct(PackedAct.empty(n, h, w, oc, parts, x.device), oc)
+            out = outs_into.get(h) if outs_into else None
+            if out is None or tuple(out.shape) != (n, oc, h, w) or out.data.shape[0] != parts:
+                out = PackedAct(PackedAct.empty(n, h, w, oc, parts, x.device), oc)
             layer(x, fused=True, out_packed=out)
             x = out
         outs.append(x)
@@ -189,12 +192,15 @@ class StyleEncoderNetworkV18(torch.nn.Module):
         feat = [Conv2dLayer(6, ngf, kernel_size=3)] + [Conv2dLayer(ngf, ngf, kernel_size=3, down=2) for _ in range(3)]
         self.feat_enc = torch.nn.ModuleList(feat)
 
-    def forward(self, x, const_input, fused=True, impl='cuda'):
+    def forward(self, x, const_input, fused=True, impl='cuda', feat_targets=None):
+        """`feat_targets` (fused route): {resolution: PackedAct view} from `SynthesisNetworkFull_v18.concat_targets` - the garment
+        feature map of that resolution is written straight into the synthesis block's concat buffer."""
         if fused and torch.is_tensor(const_input) and const_input.dtype == torch.float32 and const_input.shape[2] % 8 == 0 and \
                 const_input.shape[3] % 8 == 0 and S._can_fuse(const_input, *[l.weight for l in self.feat_enc]):
-            # hand-over chain; the 512 / 256 / 128 pixel maps stay in the operand format (the synthesis blocks copy them as channel
-            # slices into their concat buffers), the last (64 pixel) one is consumed as a tensor by the unpacked b64 block
-            const_feats = _packed_chain(self.feat_enc, const_input)
+            # hand-over chain; the 512 / 256 / 128 pixel maps stay in the operand format (written into the synthesis blocks' concat
+            # buffers when `feat_targets` is given, else copied there as channel slices by the blocks), the last (64 pixel) one is
+            # consumed as a tensor by the unpacked b64 block
+            const_feats = _packed_chain(self.feat_enc, const_input, outs_into=feat_targets)
         else:
             const_feats = []
             for layer in self.feat_enc:
@@ -403,12 +409,15 @@ class SynthesisBlockFull(torch.nn.Module):
             self.conv0(x, next(w_iter), fused=True, out_packed=xa, **layer_kwargs)
             cf = cat_feat[str(res)]
             mc = cf.shape[1]
-            buf = PackedAct.empty(n, res, res, oc + mc, parts, dev)
             conv2d_gradfix._init()
-            if isinstance(cf, PackedAct):       # produced in the operand format by the style encoder: channel-slice copy
-                conv2d_gradfix.fir_packed(cf, None, out=PackedAct(buf, mc, oc))
+            if isinstance(cf, PackedAct) and cf.c_off == oc and tuple(cf.data.shape) == (parts, n, res, res, oc + mc):
+                buf = cf.data                   # the style encoder wrote the garment features into this block's concat buffer
             else:
-                conv2d_gradfix._plugin.pack_activations_into(cf, None, buf, mc, oc)
+                buf = PackedAct.empty(n, res, res, oc + mc, parts, dev)
+                if isinstance(cf, PackedAct):   # produced in the operand format by the style encoder: channel-slice copy
+                    conv2d_gradfix.fir_packed(cf, None, out=PackedAct(buf, mc, oc))
+                else:
+                    conv2d_gradfix._plugin.pack_activations_into(cf, None, buf, mc, oc)
             self.conv1(xa, next(w_iter), fused=True, out_packed=PackedAct(buf, oc, 0), **layer_kwargs)
             if want_tensor:
                 x = self.merge_conv(PackedAct(buf, oc + mc, 0), fused=True)
@@ -490,6 +499,19 @@ class SynthesisNetworkFull_v18(torch.nn.Module):
         valid_feat_sum = torch.sum(x * valid_mask, dim=(2, 3), keepdim=True)
         return x * (1 - res_mask) + (valid_feat_sum / valid_mask_sum) * res_mask
 
+    def concat_targets(self, n, device, feat_channels=64):
+        """{resolution: PackedAct view}: channels [oc, oc + feat_channels) of the `torch.cat([x, cat_feat])` buffer of every block that
+        runs in operand-format hand-over mode (b512 and texture_b512 share one buffer: the second block's conv1 overwrites channels
+        [0, oc) after the first block's merge convolution has consumed them).  The style encoder writes its feature maps there."""
+        targets, parts = {}, S._parts()
+        for res in self.block_resolutions:
+            block = getattr(self, f'b{res}')
+            if res >= S.PACKED_MIN_RES and hasattr(block, 'merge_conv') and block.in_channels != 0:
+                oc = block.conv1.weight.shape[0]
+                if oc % 16 == 0 and block.merge_conv.weight.shape[1] == oc + feat_channels:
+                    targets[res] = PackedAct(PackedAct.empty(n, res, res, oc + feat_channels, parts, device), feat_channels, oc)
+        return targets
+
     def forward(self, ws, pose_feat, cat_feat, denorm_upper_input, denorm_lower_input, denorm_upper_mask, denorm_lower_mask, gt_parsing,
                 fused=True, impl='cuda', **block_kwargs):
         ws = ws.to(torch.float32)
@@ -551,7 +573,10 @@ class GeneratorFull_v20(torch.nn.Module):
     def forward(self, z, c, retain, pose, denorm_upper_input, denorm_lower_input, denorm_upper_mask, denorm_lower_mask, gt_parsing=None,
                 truncation_psi=1, truncation_cutoff=None, fused=True, impl='cuda', **synthesis_kwargs):
         pose_feat = self.const_encoding(pose, fused=fused, impl=impl)
-        stylecode, feats = self.style_encoding(c, retain, fused=fused, impl=impl)
+        targets = None
+        if fused and torch.is_tensor(retain) and retain.is_cuda and retain.dtype == torch.float32 and not torch.is_grad_enabled():
+            targets = self.synthesis.concat_targets(retain.shape[0], retain.device, self.style_encoding.feat_enc[0].weight.shape[0])
+        stylecode, feats = self.style_encoding(c, retain, fused=fused, impl=impl, feat_targets=targets)
         ws = self.mapping(z, stylecode, truncation_psi=truncation_psi, truncation_cutoff=truncation_cutoff, impl=impl)
         cat_feats = {str(f.shape[2]): f for f in feats}
         return self.synthesis(ws, pose_feat, cat_feats, denorm_upper_input, denorm_lower_input, denorm_upper_mask, denorm_lower_mask,

@@ -9,6 +9,7 @@ from conftest import load_pkg
 load_pkg()
 cg = importlib.import_module('pgpp_b200.torch_utils.ops.conv2d_gradfix')
 nets = importlib.import_module('pgpp_b200.training.networks')
+custom_ops = importlib.import_module('pgpp_b200.torch_utils.custom_ops')
 up = importlib.import_module('pgpp_b200.torch_utils.ops.upfirdn2d')
 ic, oc, res, n, prec = int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4]), sys.argv[5]
 opts = dict(a.split('=') for a in sys.argv[6:])
@@ -34,12 +35,14 @@ def run(reps=5):
     return ts[len(ts) // 2], cg.trace[-1][0], cg.trace[-1][1]
 
 
-for env in ([{}, {'PGPP_IGEMM_NO_LEAN_EPILOGUE': '1'}] if os.environ.get('AB') else [{}]):
-    for k in ('PGPP_IGEMM_NO_STACK', 'PGPP_IGEMM_NO_SLAB2', 'PGPP_IGEMM_NO_LEAN_EPILOGUE'):
+AB = {'lean': 'PGPP_IGEMM_NO_LEAN_EPILOGUE', 'tma': 'PGPP_IGEMM_NO_TMA_STORE', 'stack': 'PGPP_IGEMM_NO_STACK', 'slab2': 'PGPP_IGEMM_NO_SLAB2'}
+for env in ([{}, {AB[os.environ['AB']]: '1'}] if os.environ.get('AB') else [{}]):
+    for k in AB.values():
         os.environ.pop(k, None)
     os.environ.update(env)
     for dbg in [int(v) for v in os.environ.get('DBG_LIST', '0,8,1,2,4,6,5').split(',')]:
         os.environ['PGPP_IGEMM_DEBUG'] = str(dbg)
+        custom_ops.refresh_env()
         ms, name, fl = run()
         print(f'{name} {opts} {env} dbg={dbg}: {ms:.3f} ms  {fl / ms / 1e9:.1f} TF/s', flush=True)
 os.environ['PGPP_IGEMM_DEBUG'] = '0'
