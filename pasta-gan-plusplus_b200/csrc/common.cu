@@ -21,6 +21,7 @@ static EnvFlags read_env() {
     f.igemm_no_stack = getenv("PGPP_IGEMM_NO_STACK") != nullptr;
     f.igemm_no_lean_epilogue = getenv("PGPP_IGEMM_NO_LEAN_EPILOGUE") != nullptr;
     f.igemm_no_tma_store = getenv("PGPP_IGEMM_NO_TMA_STORE") != nullptr;
+    f.igemm_slab9 = getenv("PGPP_IGEMM_SLAB9") != nullptr;
     f.wgrad_no_reuse = getenv("PGPP_WGRAD_NO_REUSE") != nullptr;
     f.ba_nostream = getenv("PGPP_BA_NOSTREAM") != nullptr;
     f.fir_packed_no_tile = getenv("PGPP_FIR_PACKED_NO_TILE") != nullptr;

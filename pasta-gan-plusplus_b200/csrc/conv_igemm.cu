@@ -80,9 +80,11 @@ struct IgemmParams {
     unsigned idesc_stack;               // instruction descriptor with N = 2 * block_n
     int fold_gain;                      // activation is positively homogeneous and gain > 0: gain is folded into scale/shift/noise
     unsigned div_col_m, div_col_s, div_x_m, div_x_s, div_y_m, div_y_s;   // magic numbers for t / tiles_col, / tiles_x, / tiles_y
+    int slab9;                          // reuse == 2 with a 3 x 3 filter, 64-channel rows and 64-column weight tiles: mma_role_slab9 (compile-time descriptor offsets)
     int dbg;                            // PGPP_IGEMM_DEBUG ablation bits (timing experiments only, results are wrong): 1 epilogue without
                                         // arithmetic / stores, 2 without TMEM loads, 4 no MMAs issued, 8 arithmetic but no stores, 16 stores go to one
-                                        // tile-sized region (no DRAM write traffic), 32 128-bit instead of 256-bit stores of the operand format
+                                        // tile-sized region (no DRAM write traffic), 32 128-bit instead of 256-bit stores of the operand format, 64 no activation loads (the MMA warp
+                                        // does not wait for them: MMA issue + tensor time alone)
 };
 
 
@@ -725,7 +727,7 @@ __device__ __forceinline__ void mma_role_slab(const IgemmParams& p, const MmaCtx
             #pragma unroll
             for (int pa = 0; pa < (PARTS ? PARTS : 3); pa++) {
                 if (pa >= parts) break;
-                mbar_wait(afull_bar(sa), pha);
+                if (!(p.dbg & 64)) mbar_wait(afull_bar(sa), pha);
                 tc_fence_after();
                 const uint32_t a16 = (mc.smem_base + sa * p.a_stage_bytes) >> 4;
                 const uint32_t b_cb16 = (mc.b_base >> 4) + (uint32_t)(cb * taps * parts) * bpitch16;
@@ -757,6 +759,92 @@ __device__ __forceinline__ void mma_role_slab(const IgemmParams& p, const MmaCtx
                                 umma_bf16(tmem_d, da + 6, db + 6, idesc, 1);
                             }
                             acc = 1;
+                        }
+                    }
+                }
+                if (leader) umma_commit(aempty_bar(sa));
+                if (++sa == SA) { sa = 0; pha ^= 1; }
+            }
+        }
+        if (leader) umma_commit(tfull_bar(buf));
+        if (p.wgt_per_sample) {
+            const long long tn = t + gridDim.x;
+            if (tn < p.total_tiles && decode_tile(p, tn).n0 != last_n && leader) umma_commit(bres_free_bar);
+        }
+        if (++buf == 2) { buf = 0; buf_phase ^= 1; }
+        first_tile = false;
+    }
+    __syncwarp();
+}
+
+// Experimental single-slab MMA issuer (PGPP_IGEMM_SLAB9=1) for 3 x 3 filters, 64-channel rows, 64-column resident weight tiles, 1 or 2 parts:
+// every shared-memory descriptor of a tile differs from the stage's first one by a compile-time offset (tap (ky, kx) starts (ky * 10 + kx)
+// 128-byte pixel rows into the slab, weight tile t starts t * 8 KB after the first, a K step is 32 bytes), so the elected lane issues the 36
+// MMAs of a stage as straight-line code, ~4 instead of ~9 instructions per MMA.  Measured on 64->64 3x3 @512^2 n32 (profiles/
+// r02_igemm64_issuer_ablation.md): with neither activation loads nor epilogue the fp32-parity tile loop runs in 1.23 ms against 1.40 ms for the
+// generic issuer, but the complete kernel stays at 1.57 ms (bf16 mode: 0.83 vs 0.79 ms, uniform-register spills): the issuing warp is not what
+// bounds these layers - the tensor pipe alone, fed from shared memory at N <= 128, already needs 1.23 ms.  Off by default.
+template <int PARTS, bool STK>
+__device__ __forceinline__ void mma_role_slab9(const IgemmParams& p, const MmaCtx mc) {
+    constexpr int TAPS = 9, PITCH = 10;
+    constexpr uint32_t BP16 = 512;          // 64 rows x 128 bytes per weight tile, in 16-byte units
+    const int SA = p.a_stages, SB = p.b_stages;
+    auto afull_bar = [&](int s) { return mc.bar_base + 8u * s; };
+    auto aempty_bar = [&](int s) { return mc.bar_base + 8u * (SA + s); };
+    auto bfull_bar = [&](int s) { return mc.bar_base + 8u * (2 * SA + s); };
+    auto tfull_bar = [&](int b) { return mc.bar_base + 8u * (2 * SA + 2 * SB + b); };
+    auto tempty_bar = [&](int b) { return mc.bar_base + 8u * (2 * SA + 2 * SB + 2 + b); };
+    const uint32_t bres_free_bar = mc.bar_base + 8u * (2 * SA + 2 * SB + 4);
+    const bool leader = elect_one();
+    const bool mma_on = !(p.dbg & 4), wait_a = !(p.dbg & 64);
+    const uint64_t desc_a = make_smem_desc(0, p.layout_type, p.sbo_a), desc_b = make_smem_desc(0, p.layout_type, p.sbo_bytes);
+    const uint32_t a_hi = (uint32_t)(desc_a >> 32), b_hi = (uint32_t)(desc_b >> 32), lo_flags = (uint32_t)desc_a;     // low word without the address
+    const uint32_t idesc = p.idesc, idesc_stack = p.idesc_stack;
+    const uint32_t a_stage16 = p.a_stage_bytes >> 4;
+    int sa = 0; uint32_t pha = 0;
+    int buf = 0; uint32_t buf_phase = 0;
+    bool first_tile = true;
+    int last_n = -1; uint32_t res_phase = 0;
+    for (long long t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+        const int n0 = p.wgt_per_sample ? decode_tile(p, t).n0 : 0;
+        if (first_tile || n0 != last_n) {
+            if (!first_tile) res_phase ^= 1;
+            for (int sl = 0; sl < SB; sl++) mbar_wait(bfull_bar(sl), res_phase);
+        }
+        last_n = n0;
+        mbar_wait(tempty_bar(buf), buf_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = mc.tmem_base + (uint32_t)(buf * p.acc_cols);
+        for (int cb = 0; cb < p.num_cb; cb++) {
+            const uint32_t b_lo0 = lo_flags | (((mc.b_base >> 4) + (uint32_t)(cb * TAPS * PARTS) * BP16) & 0x3FFFu);
+            #pragma unroll
+            for (int pa = 0; pa < PARTS; pa++) {
+                if (wait_a) mbar_wait(afull_bar(sa), pha);
+                tc_fence_after();
+                const uint32_t a_lo0 = lo_flags | (((mc.smem_base >> 4) + (uint32_t)sa * a_stage16) & 0x3FFFu);
+                const uint32_t first = (cb == 0 && pa == 0) ? 0u : 1u;          // the first MMA of a tile overwrites the accumulator
+                if (leader && mma_on) {
+                    #pragma unroll
+                    for (int j = 0; j < TAPS; j++) {
+                        const uint32_t a_lo = a_lo0 + (uint32_t)(((j / 3) * PITCH + (j % 3)) * 8);
+                        if (STK) {
+                            // pa == 0: a0 x [b0; b1] (N = 128);  pa == 1: a1 x b0 (N = 64)
+                            const uint32_t b_lo = b_lo0 + (uint32_t)(j * PARTS) * BP16;
+                            const uint32_t id = pa == 0 ? idesc_stack : idesc;
+                            umma_bf16_lh(tmem_d, a_lo, a_hi, b_lo, b_hi, id, j == 0 ? first : 1u);
+                            umma_bf16_lh(tmem_d, a_lo + 2, a_hi, b_lo + 2, b_hi, id, 1u);
+                            umma_bf16_lh(tmem_d, a_lo + 4, a_hi, b_lo + 4, b_hi, id, 1u);
+                            umma_bf16_lh(tmem_d, a_lo + 6, a_hi, b_lo + 6, b_hi, id, 1u);
+                        } else {
+                            #pragma unroll
+                            for (int pb = 0; pb < PARTS; pb++) {
+                                if (pa + pb >= PARTS) break;
+                                const uint32_t b_lo = b_lo0 + (uint32_t)(j * PARTS + pb) * BP16;
+                                umma_bf16_lh(tmem_d, a_lo, a_hi, b_lo, b_hi, idesc, (j == 0 && pb == 0) ? first : 1u);
+                                umma_bf16_lh(tmem_d, a_lo + 2, a_hi, b_lo + 2, b_hi, idesc, 1u);
+                                umma_bf16_lh(tmem_d, a_lo + 4, a_hi, b_lo + 4, b_hi, idesc, 1u);
+                                umma_bf16_lh(tmem_d, a_lo + 6, a_hi, b_lo + 6, b_hi, idesc, 1u);
+                            }
                         }
                     }
                 }
@@ -854,6 +942,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
                     }
                 }
                 if (p.reuse == 2) {
+                    if (p.dbg & 64) continue;
                     // one slab (TW + kw - 1) x (TH + kh - 1) pixels per (channel block, part); stages are single parts
                     for (int cb = 0; cb < p.num_cb; cb++)
                         for (int pa = 0; pa < p.parts; pa++) {
@@ -895,7 +984,12 @@ igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
         const MmaCtx mc{smem_base, b_base, bar_base, tmem_base};
         const int ks = p.kb == 64 ? 4 : 0;
         const bool res = p.b_resident != 0;
-        if (p.reuse == 2) {
+        if (p.reuse == 2 && p.slab9) {
+            if (p.parts == 1) mma_role_slab9<1, false>(p, mc);
+            else if (p.stack) mma_role_slab9<2, true>(p, mc);
+            else mma_role_slab9<2, false>(p, mc);
+        }
+        else if (p.reuse == 2) {
             if (p.inner == 9 && p.parts == 1) mma_role_slab<1, 9, false>(p, mc);
             else if (p.inner == 9 && p.parts == 2 && p.stack) mma_role_slab<2, 9, true>(p, mc);
             else if (p.inner == 9 && p.parts == 2) mma_role_slab<2, 9, false>(p, mc);
@@ -1160,6 +1254,8 @@ extern "C" int pgpp_conv2d_igemm(const pgpp_conv_desc* d, void* stream) {
     // stacked products (see mma_role): fp32-parity mode with 2 parts, resident 64-column weight tiles, fast epilogue
     p.stack = (need_parts == 2 && d->block_n == 64 && p.b_resident && p.kb == 64 && (p.inner == 3 || p.inner == 1 || p.reuse == 2) && p.tn == 1 && p.fold_gain &&
                !d->spade_x && !env.igemm_no_stack) ? 1 : 0;
+    p.slab9 = (p.reuse == 2 && d->kh == 3 && d->kw == 3 && p.kb == 64 && d->block_n == 64 && p.b_pitch == 8192 && need_parts <= 2 &&
+               env.igemm_slab9) ? 1 : 0;       // opt-in (PGPP_IGEMM_SLAB9=1): measured neutral in fp32-parity mode, 5 % slower in bf16 mode
     p.acc_cols = p.stack ? 2 * d->block_n : d->block_n;
     p.idesc_stack = (1u << 4) | ab_fmt | ((unsigned)((2 * d->block_n) >> 3) << 17) | ((unsigned)(kTileM >> 4) << 24);
     if (p.stack) p.tmem_cols = 256;

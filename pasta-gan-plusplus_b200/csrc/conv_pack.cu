@@ -124,8 +124,15 @@ __global__ void __launch_bounds__(256) pack_nchw_kernel(PackArgs p, TileGeom g) 
         if (c < p.c && y < p.h) {
             if (VEC) {
                 if (x < p.w) {
-                    const float4 q = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(src) + c * p.s_c);
-                    v[i][0] = q.x; v[i][1] = q.y; v[i][2] = q.z; v[i][3] = q.w;
+                    if constexpr (sizeof(T) == 4) {
+                        const float4 q = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(src) + c * p.s_c);
+                        v[i][0] = q.x; v[i][1] = q.y; v[i][2] = q.z; v[i][3] = q.w;
+                    } else if constexpr (sizeof(T) == 2) {            // 16-bit source: 4 pixels = one 64-bit load
+                        const uint2 q = *reinterpret_cast<const uint2*>(src + c * p.s_c);
+                        const T* h4 = reinterpret_cast<const T*>(&q);
+                        #pragma unroll
+                        for (int k = 0; k < 4; k++) v[i][k] = (float)to_acc<T>(h4[k]);
+                    }
                 }
             } else {
                 #pragma unroll
@@ -168,9 +175,9 @@ static int launch_pack(const PackArgs& p, cudaStream_t stream) {
         PGPP_REQUIRE(blocks <= 2147483647LL, "activation tensor too large to pack");
         const size_t smem = (size_t)p.parts * 128 * 8 * sizeof(uint4);
         // 128-bit loads: rows 16-byte aligned and either W % 4 == 0 or a row pitch that covers the last (partial) group of 4
-        const bool vec = sizeof(T) == 4 && (p.w % 4 == 0 || p.s_h >= (p.w + 3) / 4 * 4) && p.s_c % 4 == 0 && p.s_h % 4 == 0 && p.s_n % 4 == 0 &&
-                         ((uintptr_t)p.x & 15) == 0;
-        if (vec) pack_nchw_kernel<float, true><<<(unsigned)blocks, 256, smem, stream>>>(p, g);
+        const bool vec = sizeof(T) <= 4 && (p.w % 4 == 0 || p.s_h >= (p.w + 3) / 4 * 4) && p.s_c % 4 == 0 && p.s_h % 4 == 0 && p.s_n % 4 == 0 &&
+                         ((uintptr_t)p.x & (4 * sizeof(T) - 1)) == 0;
+        if (vec) pack_nchw_kernel<T, true><<<(unsigned)blocks, 256, smem, stream>>>(p, g);
         else pack_nchw_kernel<T, false><<<(unsigned)blocks, 256, smem, stream>>>(p, g);
     } else {
         const long long total = (long long)p.n * p.h * p.w * p.c_pad;

@@ -188,3 +188,35 @@ def test_torgb_thin_kernel(cfg, prec):
         want_pp = (torch.einsum('nchw,oc,nc->nohw', x_seen, layer.m_weight1.double().reshape(pc, ic), styles) + layer.m_bias1.double().reshape(1, pc, 1, 1)).clamp(-2, 2)
         assert rel_l2(got_pp, want_pp) < 2e-6
         assert rel_l2(got_pp, ref_pp) < {'bf16x2': 8e-5, 'bf16x3': 4e-5, 'bf16': 1.5e-2}[prec]
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.float16, torch.bfloat16])
+@pytest.mark.parametrize('shape', [(2, 64, 16, 32), (1, 70, 9, 20), (2, 24, 7, 13), (1, 128, 4, 130), (3, 8, 33, 6)], ids=str)
+def test_pack_activations_every_source_dtype_and_alignment(shape, dtype):
+    """pgpp_pack_activations (the entry into the operand format): float32 / float16 / bfloat16 NCHW sources, widths that are and are not
+    multiples of 4 (128-bit / 64-bit vector loads vs the scalar path), a row-strided view, with and without the style scale; the sum
+    of the 2 bf16 parts reproduces the source to 16 significand bits, padding channels are zero."""
+    cg._init()
+    n, c, h, w = shape
+    g = torch.Generator().manual_seed(71)
+    x = torch.randn(n, c, h, w, generator=g).to(dtype).to(DEV)
+    s = torch.randn(n, c, generator=g).to(DEV)
+    c_pad = -(-c // 64) * 64
+    views = [x]
+    if w % 4 == 0:
+        big = torch.randn(n, c, h, w + 4, generator=g).to(dtype).to(DEV)
+        views.append(big[..., :w])                                      # row pitch w + 4: still 4-element aligned rows
+    views.append(torch.randn(n, c, h, w + 1, generator=g).to(dtype).to(DEV)[..., 1:])      # misaligned base: scalar path
+    for src in views:
+        for scale in (None, s):
+            data = cg._plugin.pack_activations(src, scale, c_pad, 2)
+            assert tuple(data.shape) == (2, n, h, w, c_pad)
+            got = data.float().sum(0).permute(0, 3, 1, 2)
+            want = src.float() * (1 if scale is None else scale[:, :, None, None])
+            assert torch.all(got[:, c:] == 0)
+            err = float((got[:, :c] - want).abs().max())
+            assert err <= 2e-5 * max(1.0, float(want.abs().max())), (err, tuple(src.stride()))
+    if dtype == torch.float16:                                          # native f16 operand (one part, exact copy)
+        data = cg._plugin.pack_activations(x, None, c_pad, 1, f16=True)
+        got = data.view(torch.float16)[0].permute(0, 3, 1, 2)[:, :c]
+        assert torch.equal(got, x)

@@ -35,7 +35,7 @@ def run(reps=5):
     return ts[len(ts) // 2], cg.trace[-1][0], cg.trace[-1][1]
 
 
-AB = {'lean': 'PGPP_IGEMM_NO_LEAN_EPILOGUE', 'tma': 'PGPP_IGEMM_NO_TMA_STORE', 'stack': 'PGPP_IGEMM_NO_STACK', 'slab2': 'PGPP_IGEMM_NO_SLAB2'}
+AB = {'lean': 'PGPP_IGEMM_NO_LEAN_EPILOGUE', 'tma': 'PGPP_IGEMM_NO_TMA_STORE', 'stack': 'PGPP_IGEMM_NO_STACK', 'slab2': 'PGPP_IGEMM_NO_SLAB2', 'slab9': 'PGPP_IGEMM_SLAB9'}
 for env in ([{}, {AB[os.environ['AB']]: '1'}] if os.environ.get('AB') else [{}]):
     for k in AB.values():
         os.environ.pop(k, None)

@@ -35,6 +35,6 @@ for r in data:
     top = sorted(stalls.items(), key=lambda kv: -kv[1])[:2]
     smem = (gs(r, 'launch__shared_mem_per_block_static') + gs(r, 'launch__shared_mem_per_block_dynamic')) / 1024
     print(f"| `{name}` | {r[H['Grid Size']]} x {r[H['Block Size']]} | {g(r, 'launch__registers_per_thread'):.0f} | {smem:.1f} | "
-          f"{t_us:.1f} | {(rd + wr) / 1e6:.0f} | {gbs:.0f} | {100 * gbs / peak:.0f} | {g(r, 'dram__throughput.avg.pct_of_peak_sustained_elapsed'):.0f} | {g(r, 'lts__t_sector_hit_rate.pct'):.0f} | "
+          f"{t_us:.1f} | {(rd + wr) / 1e6:.0f} | {gbs:.0f} | {100 * gbs / peak:.0f} | {g(r, 'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed'):.0f} | {g(r, 'lts__t_sector_hit_rate.pct'):.0f} | "
           f"{g(r, 'sm__throughput.avg.pct_of_peak_sustained_elapsed'):.0f} | {g(r, 'smsp__issue_active.avg.pct_of_peak_sustained_active'):.0f} | {g(r, 'sm__warps_active.avg.pct_of_peak_sustained_active'):.0f} | "
           + ', '.join(f'{k} {v:.1f}' for k, v in top) + ' |')
