@@ -298,8 +298,8 @@ class GeneratorPipeline:
     -> GeneratorFull_v20 -> uint8 BGR HWC try-on image (pgpp_image_to_u8, test.py:162-166) back in pinned host memory.  Read-back
     of batch i overlaps compute of i+1."""
 
-    def __init__(self, G, batch, device):
-        self.G, self.device = G, device
+    def __init__(self, G, batch, device, graphed=None):
+        self.G, self.device, self.graphed = G, device, graphed
         self.copy_stream = torch.cuda.Stream(device)
         self.out_host = [torch.empty(batch, RES, RES, 3, dtype=torch.uint8).pin_memory() for _ in range(2)]
         self.io = importlib.import_module('pgpp_b200.torch_utils.custom_ops').get_plugin('io_edge_plugin')
@@ -308,7 +308,7 @@ class GeneratorPipeline:
     def __call__(self, host_u8):
         cur = torch.cuda.current_stream(self.device)
         x = to_device_f32(host_u8, self.device)
-        _, finetune, _ = run_generator(self.G, x)
+        _, finetune, _ = self.graphed(x) if self.graphed is not None else run_generator(self.G, x)
         finetune = self.io.image_to_u8(finetune.contiguous(), reverse_channels=True)
         done = torch.cuda.Event(); done.record(cur)
         self.copy_stream.wait_event(done)
@@ -483,22 +483,25 @@ def run_ours(args):
 
     batch = args.batch
     gen_mode = args.workload == 'generator'
+    gen = importlib.import_module('pgpp_b200.training.generator')
     if gen_mode:
         net = build_generator(device)
         host_u8 = {k: v.pin_memory() for k, v in make_generator_inputs_u8(batch, 100 + rank).items()}
         dev_in = to_device_f32(host_u8, device)
 
-        def step():
+        def step_eager():
             return run_generator(net, dev_in)
+        step = step_eager
     else:
         net = build_chain(device)
         cat = make_cat_feats(net, batch, device)
         ws_h, pose_h = make_inputs(net, batch, 100 + rank, pin=True)
         ws_d, pose_d = ws_h.to(device), pose_h.to(device)
 
-        def step():
+        def step_eager():
             with torch.no_grad():
                 return net(ws_d, pose_d, cat, noise_mode='const')
+        step = step_eager
 
     def barrier():
         if world > 1:
@@ -506,6 +509,26 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     # ---- device-resident throughput ----
+    # The public inference entry for fixed shapes is `GraphedGenerator`: the whole forward (about 400 launches) captured once into a CUDA
+    # graph and replayed - same kernels, same order, bit-identical output, no per-launch host work.  `--no-graph` times eager launches.
+    eager_ms = None
+    graphed = None
+    launches_per_step = None
+    if gen_mode and not args.no_graph:
+        for _ in range(3):
+            step_eager()
+        barrier()
+        l0 = custom_ops.launch_count()
+        step_eager()
+        launches_per_step = custom_ops.launch_count() - l0         # graph replays do not pass through the C ABI: count one eager pass
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier(); a0.record()
+        for _ in range(args.steps):
+            step_eager()
+        a1.record(); barrier()
+        eager_ms = a0.elapsed_time(a1) / args.steps
+        graphed = gen.GraphedGenerator(net, dev_in)
+        step = graphed.replay
     for _ in range(max(args.warmup, 3)):
         out = step()
     barrier()
@@ -520,10 +543,12 @@ def run_ours(args):
         barrier()
     ms = e0.elapsed_time(e1)
     launches = custom_ops.launch_count() - launches0
+    if graphed is not None:
+        launches = launches_per_step * args.steps
 
     # ---- end to end through the pipeline API (pinned host in, image back to host) ----
     if gen_mode:
-        pipe = GeneratorPipeline(net, batch, device)
+        pipe = GeneratorPipeline(net, batch, device, graphed=graphed)
         call = lambda: pipe(host_u8)
         h2d = sum(v.numel() for v in host_u8.values())
     else:
@@ -545,13 +570,21 @@ def run_ours(args):
     d2h = batch * 3 * RES * RES * (1 if gen_mode else 4)
 
     # ---- max over ranks ----
-    times = torch.tensor([ms, e2e_ms], device=device, dtype=torch.float64)
+    times = torch.tensor([ms, e2e_ms, eager_ms or 0.0], device=device, dtype=torch.float64)
     if world > 1:
         torch.distributed.all_reduce(times, op=torch.distributed.ReduceOp.MAX)
     ms, e2e_ms = float(times[0]), float(times[1])
+    if eager_ms is not None:
+        eager_ms = float(times[2])
 
     # ---- bf16 mode (reported separately, north star): same step with single-product bf16 MMAs ----
     cg.fp32_precision = 'bf16'
+    if graphed is not None:
+        del pipe
+        graphed = None
+        torch.cuda.empty_cache()
+        graphed_bf16 = gen.GraphedGenerator(net, dev_in)          # the captured launches carry the precision they were captured with
+        step = graphed_bf16.replay
     for _ in range(3):
         step()
     barrier()
@@ -566,6 +599,10 @@ def run_ours(args):
     if world > 1:
         torch.distributed.all_reduce(times, op=torch.distributed.ReduceOp.MAX)
     bf16_ms = float(times[0])
+    if gen_mode and not args.no_graph:
+        step = step_eager
+        graphed_bf16 = None
+        torch.cuda.empty_cache()
 
     # ---- BASELINE configs[4] beside the headline: a few training iterations (G + D + D_parsing with R1, DDP all-reduce when world > 1) ----
     train = None
@@ -716,9 +753,13 @@ def run_ours(args):
             'config': {'workload': GEN_DESC if gen_mode else CHAIN_DESC,
                        'batch_per_gpu': batch, 'global_batch': batch * world, 'resolution': RES, 'precision': args.precision,
                        'parallelism': f'batch-sharded x{world}, no collective',
+                       'launch': ('CUDA-graph replay of the whole forward (GraphedGenerator, the inference entry for fixed shapes; same kernels as the '
+                                  'eager pass, bit-identical output)') if eager_ms is not None else 'eager launches',
                        'l2': 'per-step working set (several GB of activations) exceeds the 126 MB L2; no flush needed'},
             'clocks': clocks.summary(),
             'gpu_launches': launches,
+            'eager': None if eager_ms is None else {'ms_per_step': eager_ms, 'value': imgs / args.steps / (eager_ms * 1e-3), 'unit': 'images/s',
+                                                     'note': 'the same step issued launch by launch through Python / ctypes (device-resident inputs)'},
             'e2e': {'value': imgs / (e2e_ms * 1e-3), 'unit': 'images/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                     'note': ('uint8 pinned-host try-on inputs in (+ on-device /127.5-1, test.py:126-147), uint8 BGR try-on image read back (test.py:162-166); '
                              'copy of batch i overlaps compute of i+1') if gen_mode else
@@ -753,6 +794,7 @@ def main():
     ap.add_argument('--train-steps', type=int, default=3, help='generator workload: also time this many training iterations (0 = skip)')
     ap.add_argument('--fp16-res', type=int, default=3, help='train workload: number of highest-resolution D blocks in fp16 (train.py:196)')
     ap.add_argument('--skip-cpu', action='store_true', help='skip the CPU baseline / parity leg')
+    ap.add_argument('--no-graph', action='store_true', help='generator workload: time eager launches instead of CUDA-graph replay (GraphedGenerator)')
     ap.add_argument('--no-ops', action='store_true', help='generator workload: skip the op microbench sweep (the `ops` key, BASELINE configs[3])')
     args = ap.parse_args()
     if args.impl == 'reference':

@@ -622,6 +622,14 @@ class GraphedGenerator:
         return self.G(z, x['c'], x['retain'], x['pose'], x['denorm_upper'], x['denorm_lower'], x['denorm_upper_mask'],
                       x['denorm_lower_mask'], gt_parsing=self.static_gt, **self.kwargs)
 
+    def replay(self):
+        """replay on whatever the static input buffers (`self.static_in`, `self.static_gt`) hold now - for callers that write their
+        inputs straight into them"""
+        if any(p._version != v or p.data_ptr() != ptr for p, v, ptr in self._versions):
+            raise RuntimeError('generator weights changed after the graph was captured: build a new GraphedGenerator')
+        self.graph.replay()
+        return self.static_out
+
     def __call__(self, inputs, gt_parsing=None):
         """inputs: dict with exactly the keys of the example batch; gt_parsing: required iff the graph was captured with one (it is
         a static input like the others, refreshed on every call)."""
