@@ -511,7 +511,7 @@ def run_ours(args):
     # ---- device-resident throughput ----
     # The public inference entry for fixed shapes is `GraphedGenerator`: the whole forward (about 400 launches) captured once into a CUDA
     # graph and replayed - same kernels, same order, bit-identical output, no per-launch host work.  `--no-graph` times eager launches.
-    eager_ms = None
+    eager_step_ms = None
     graphed = None
     launches_per_step = None
     if gen_mode and not args.no_graph:
@@ -526,7 +526,7 @@ def run_ours(args):
         for _ in range(args.steps):
             step_eager()
         a1.record(); barrier()
-        eager_ms = a0.elapsed_time(a1) / args.steps
+        eager_step_ms = a0.elapsed_time(a1) / args.steps
         graphed = gen.GraphedGenerator(net, dev_in)
         step = graphed.replay
     for _ in range(max(args.warmup, 3)):
@@ -570,12 +570,12 @@ def run_ours(args):
     d2h = batch * 3 * RES * RES * (1 if gen_mode else 4)
 
     # ---- max over ranks ----
-    times = torch.tensor([ms, e2e_ms, eager_ms or 0.0], device=device, dtype=torch.float64)
+    times = torch.tensor([ms, e2e_ms, eager_step_ms or 0.0], device=device, dtype=torch.float64)
     if world > 1:
         torch.distributed.all_reduce(times, op=torch.distributed.ReduceOp.MAX)
     ms, e2e_ms = float(times[0]), float(times[1])
-    if eager_ms is not None:
-        eager_ms = float(times[2])
+    if eager_step_ms is not None:
+        eager_step_ms = float(times[2])
 
     # ---- bf16 mode (reported separately, north star): same step with single-product bf16 MMAs ----
     cg.fp32_precision = 'bf16'
@@ -754,11 +754,11 @@ def run_ours(args):
                        'batch_per_gpu': batch, 'global_batch': batch * world, 'resolution': RES, 'precision': args.precision,
                        'parallelism': f'batch-sharded x{world}, no collective',
                        'launch': ('CUDA-graph replay of the whole forward (GraphedGenerator, the inference entry for fixed shapes; same kernels as the '
-                                  'eager pass, bit-identical output)') if eager_ms is not None else 'eager launches',
+                                  'eager pass, bit-identical output)') if eager_step_ms is not None else 'eager launches',
                        'l2': 'per-step working set (several GB of activations) exceeds the 126 MB L2; no flush needed'},
             'clocks': clocks.summary(),
             'gpu_launches': launches,
-            'eager': None if eager_ms is None else {'ms_per_step': eager_ms, 'value': imgs / args.steps / (eager_ms * 1e-3), 'unit': 'images/s',
+            'eager': None if eager_step_ms is None else {'ms_per_step': eager_step_ms, 'value': imgs / args.steps / (eager_step_ms * 1e-3), 'unit': 'images/s',
                                                      'note': 'the same step issued launch by launch through Python / ctypes (device-resident inputs)'},
             'e2e': {'value': imgs / (e2e_ms * 1e-3), 'unit': 'images/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                     'note': ('uint8 pinned-host try-on inputs in (+ on-device /127.5-1, test.py:126-147), uint8 BGR try-on image read back (test.py:162-166); '

@@ -209,11 +209,25 @@ typedef struct {
     float spade_pre_gain;
     int32_t operand_f16;            /* nonzero: act and wgt hold IEEE half (one part each, products == 1) instead of bfloat16 parts:
                                        the fp16 blocks of the discriminator (networks.py:634,647) on native f16 tensor-core MMAs */
+    /* Instance-norm statistics of the OUTPUT fused into the epilogue (optional, stats_ws != NULL; the `param_free_norm` of
+     * Spade_Norm_Block, networks.py:1702-1723, normalises what this convolution writes): every epilogue warp leaves, for its 32 pixels
+     * and each output channel, a pivot value, the sum of the deviations from it and the sum of their squares:
+     *     stats_ws float32 [3][M][o],  M = tiles * 4 warp partials, sample n owns rows [n * M / N, (n + 1) * M / N)
+     * (no atomics: deterministic).  pgpp_instnorm_finalize turns them into mean / rstd.  Needs float32 NCHW output, one sample per
+     * tile, conv_w and conv_h multiples of the pixel tile (16 x 8, or 8 x 16 in single-slab mode), o % 16 == 0, phases == 1, no
+     * accumulate; pgpp_conv2d_igemm_stats_rows reports M (0 = this launch cannot produce statistics). */
+    float* stats_ws;
 } pgpp_conv_desc;
 
 /* Implicit-GEMM convolution on the 5th-gen tensor cores (tcgen05.mma, TMEM accumulators, TMA operand
  * loads), persistent over the SMs, with the epilogue above fused. */
 PGPP_API int pgpp_conv2d_igemm(const pgpp_conv_desc* desc, void* stream);
+/* rows M of the statistics workspace pgpp_conv2d_igemm would fill for this descriptor (stats_ws itself is ignored), 0 if the launch
+ * cannot produce statistics, negative on an invalid descriptor */
+PGPP_API int64_t pgpp_conv2d_igemm_stats_rows(const pgpp_conv_desc* desc);
+/* mean[n, c] and rstd[n, c] = rsqrt(var + eps) (biased variance, torch.nn.InstanceNorm2d / torch.var_mean(unbiased=False)) from the
+ * warp partials of pgpp_conv2d_igemm: ws float32 [3][rows][c], rows / n partials of 32 pixels per sample, merged in float64. */
+PGPP_API int pgpp_instnorm_finalize(const float* ws, int64_t rows, int n, int c, float eps, float* mean, float* rstd, void* stream);
 
 /* Masked feature composition + packing (networks.py:2253-2276, 2307-2315: the warped-garment features fed to the SPADE blocks):
  *   v[n,c,p] = x1[n,c,p]*a1[n,p] + m1[n,c]*b1[n,p]  (+ x2[n,c,p]*a2[n,p] + m2[n,c]*b2[n,p] when x2 != NULL)

@@ -80,6 +80,7 @@ struct IgemmParams {
     unsigned idesc_stack;               // instruction descriptor with N = 2 * block_n
     int fold_gain;                      // activation is positively homogeneous and gain > 0: gain is folded into scale/shift/noise
     unsigned div_col_m, div_col_s, div_x_m, div_x_s, div_y_m, div_y_s;   // magic numbers for t / tiles_col, / tiles_x, / tiles_y
+    float* stats_ws; long long stats_plane;    // instance-norm partials of the output: [3][stats_plane / o][o] (see pgpp_conv_desc.stats_ws)
     int slab9;                          // reuse == 2 with a 3 x 3 filter, 64-channel rows and 64-column weight tiles: mma_role_slab9 (compile-time descriptor offsets)
     int dbg;                            // PGPP_IGEMM_DEBUG ablation bits (timing experiments only, results are wrong): 1 epilogue without
                                         // arithmetic / stores, 2 without TMEM loads, 4 no MMAs issued, 8 arithmetic but no stores, 16 stores go to one
@@ -183,11 +184,27 @@ __device__ __forceinline__ void epilogue_general(const IgemmParams& p, const Til
     }
 }
 
+// Sum over the 32 lanes of a warp of 16 values per lane in 16 shuffles (butterfly that halves the values per lane at every step):
+// returns, in every lane, the total of value index (lane >> 1).
+__device__ __forceinline__ float warp_sum16(const float (&a)[16], int lane) {
+    const bool h4 = lane & 16, h3 = lane & 8, h2 = lane & 4, h1 = lane & 2;
+    float b[8], c[4], e[2];
+    #pragma unroll
+    for (int i = 0; i < 8; i++) b[i] = (h4 ? a[i + 8] : a[i]) + __shfl_xor_sync(0xffffffffu, h4 ? a[i] : a[i + 8], 16);
+    #pragma unroll
+    for (int i = 0; i < 4; i++) c[i] = (h3 ? b[i + 4] : b[i]) + __shfl_xor_sync(0xffffffffu, h3 ? b[i] : b[i + 4], 8);
+    #pragma unroll
+    for (int i = 0; i < 2; i++) e[i] = (h2 ? c[i + 2] : c[i]) + __shfl_xor_sync(0xffffffffu, h2 ? c[i] : c[i + 2], 4);
+    float r = (h1 ? e[1] : e[0]) + __shfl_xor_sync(0xffffffffu, h1 ? e[0] : e[1], 2);
+    r += __shfl_xor_sync(0xffffffffu, r, 1);
+    return r;
+}
+
 // Fast epilogue: one sample per tile, per-column (scale, shift) staged in shared memory with the gain already folded in
 // (linear / relu / lrelu are positively homogeneous).
 template <int A, class OT, bool CLAMP, bool ACC>
 __device__ __forceinline__ void epilogue_fast(const IgemmParams& p, const TileCoord tc, uint32_t tmem_tile, const PixelCoord pc,
-                                              int col_begin, int col_end, const float2* s_cs, float nz_pre) {
+                                              int col_begin, int col_end, const float2* s_cs, float nz_pre, float* stats_row) {
     const int x = tc.x0 + pc.px, y = tc.y0 + pc.py, n = tc.n0;
     const bool pix_ok = x < p.conv_w && y < p.conv_h;
     OT* const out = (OT*)p.out;
@@ -234,6 +251,28 @@ __device__ __forceinline__ void epilogue_fast(const IgemmParams& p, const TileCo
             #pragma unroll
             for (int j = 0; j < 16; j++) sum += v[j];
             if (sum != 1.2345e38f) return;
+        }
+        if (!ACC && stats_row) {
+            // instance-norm partials of this warp's 32 pixels (host guarantees full tiles, o % 16 == 0: the whole warp is here):
+            // pivot = lane 0's value, so a locally constant channel leaves exactly zero deviations
+            const int lane = threadIdx.x & 31;
+            float pv[16], d1[16], d2[16];
+            #pragma unroll
+            for (int j = 0; j < 16; j++) {
+                pv[j] = __shfl_sync(0xffffffffu, v[j], 0);
+                d1[j] = v[j] - pv[j];
+                d2[j] = d1[j] * d1[j];
+            }
+            const float s1 = warp_sum16(d1, lane), s2 = warp_sum16(d2, lane);
+            float* row = stats_row + oc0;
+            if (lane == 0) {
+                #pragma unroll
+                for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(row + j) = make_float4(pv[j], pv[j + 1], pv[j + 2], pv[j + 3]);
+            }
+            if (!(lane & 1)) {
+                row[p.stats_plane + (lane >> 1)] = s1;
+                row[2 * p.stats_plane + (lane >> 1)] = s2;
+            }
         }
         if (ACC) {
             // lanes are consecutive pixels: coalesced along W for NCHW tensors
@@ -375,14 +414,14 @@ __device__ __forceinline__ void epilogue_spade(const IgemmParams& p, const TileC
 
 template <class OT>
 __device__ __forceinline__ void epilogue_dispatch(const IgemmParams& p, const TileCoord tc, uint32_t tmem_tile, const PixelCoord pc,
-                                                  int col_begin, int col_end, const float2* s_cs, bool fast, float nz_pre) {
+                                                  int col_begin, int col_end, const float2* s_cs, bool fast, float nz_pre, float* stats_row) {
     if (fast) {
         // ACC: read-modify-write output (ToRGB into the skip image, residual adds)
 #define PGPP_FAST(ACT) \
-        if (p.accumulate) { if (cl) epilogue_fast<ACT, OT, true, true>(p, tc, tmem_tile, pc, col_begin, col_end, s_cs, nz_pre);   \
-                            else    epilogue_fast<ACT, OT, false, true>(p, tc, tmem_tile, pc, col_begin, col_end, s_cs, nz_pre); } \
-        else               { if (cl) epilogue_fast<ACT, OT, true, false>(p, tc, tmem_tile, pc, col_begin, col_end, s_cs, nz_pre);  \
-                            else    epilogue_fast<ACT, OT, false, false>(p, tc, tmem_tile, pc, col_begin, col_end, s_cs, nz_pre); }
+        if (p.accumulate) { if (cl) epilogue_fast<ACT, OT, true, true>(p, tc, tmem_tile, pc, col_begin, col_end, s_cs, nz_pre, stats_row);   \
+                            else    epilogue_fast<ACT, OT, false, true>(p, tc, tmem_tile, pc, col_begin, col_end, s_cs, nz_pre, stats_row); } \
+        else               { if (cl) epilogue_fast<ACT, OT, true, false>(p, tc, tmem_tile, pc, col_begin, col_end, s_cs, nz_pre, stats_row);  \
+                            else    epilogue_fast<ACT, OT, false, false>(p, tc, tmem_tile, pc, col_begin, col_end, s_cs, nz_pre, stats_row); }
         const bool cl = p.clamp >= 0.f;
         switch (p.act_fn) {
             case PGPP_ACT_LINEAR: PGPP_FAST(PGPP_ACT_LINEAR) break;
@@ -1072,10 +1111,13 @@ igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
             mbar_wait(tfull_bar(buf), buf_phase);
             tc_fence_after();
             const uint32_t tmem_tile = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * p.acc_cols);
+            // instance-norm partials: row (pixel tile, lane quarter) of the workspace, pixel tiles numbered sample-major
+            float* stats_row = nullptr;
+            if (p.stats_ws) stats_row = p.stats_ws + ((long long)fast_div((unsigned)t, p.div_col_m, p.div_col_s) * 4 + quarter) * p.o;
             if (p.spade_x) epilogue_spade(p, tc, tmem_tile, pc, half, s_cs);
-            else if (p.out_dtype == PGPP_F32) epilogue_dispatch<float>(p, tc, tmem_tile, pc, col_begin, col_end, s_cs, fast, nz_pre);
-            else if (p.out_dtype == PGPP_BF16) epilogue_dispatch<__nv_bfloat16>(p, tc, tmem_tile, pc, col_begin, col_end, s_cs, fast, nz_pre);
-            else epilogue_dispatch<__half>(p, tc, tmem_tile, pc, col_begin, col_end, s_cs, fast, nz_pre);
+            else if (p.out_dtype == PGPP_F32) epilogue_dispatch<float>(p, tc, tmem_tile, pc, col_begin, col_end, s_cs, fast, nz_pre, stats_row);
+            else if (p.out_dtype == PGPP_BF16) epilogue_dispatch<__nv_bfloat16>(p, tc, tmem_tile, pc, col_begin, col_end, s_cs, fast, nz_pre, nullptr);
+            else epilogue_dispatch<__half>(p, tc, tmem_tile, pc, col_begin, col_end, s_cs, fast, nz_pre, nullptr);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty_bar(buf));
@@ -1097,7 +1139,75 @@ igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
 
 } // namespace pgpp
 
-extern "C" int pgpp_conv2d_igemm(const pgpp_conv_desc* d, void* stream) {
+namespace pgpp { static int igemm_launch(const pgpp_conv_desc* d, void* stream, long long* stats_rows_query); }
+
+extern "C" int pgpp_conv2d_igemm(const pgpp_conv_desc* d, void* stream) { return pgpp::igemm_launch(d, stream, nullptr); }
+
+extern "C" int64_t pgpp_conv2d_igemm_stats_rows(const pgpp_conv_desc* d) {
+    long long rows = 0;
+    const int rc = pgpp::igemm_launch(d, nullptr, &rows);
+    return rc == PGPP_OK ? (int64_t)rows : (int64_t)rc;
+}
+
+// mean / rstd from the warp partials (pivot, sum of deviations, sum of squared deviations over 32 pixels each): all partials have the same
+// count, so  mean = avg(mean_w),  M2 = sum M2_w + 32 * sum (mean_w - mean)^2  with  mean_w = pivot + s1 / 32,  M2_w = s2 - s1^2 / 32;
+// accumulated in float64 (the between-partial term is formed from sums of mean_w and mean_w^2).
+namespace pgpp {
+__global__ void __launch_bounds__(1024) instnorm_finalize_kernel(const float* ws, long long rows, long long rows_per_sample, int c, float eps,
+                                                                 float* mean, float* rstd) {
+    __shared__ double sh[3][32][33];
+    const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;        // 32 channels x 32 row slices per CTA, 4 rows in flight per thread
+    const int ch = blockIdx.x * 32 + lane, n = blockIdx.y;
+    const long long plane = rows * c;
+    double a = 0.0, b = 0.0, m2 = 0.0;
+    if (ch < c) {
+        const float* base = ws + (long long)n * rows_per_sample * c + ch;
+        for (long long r0 = slice; r0 < rows_per_sample; r0 += 128) {
+            float pv[4], s1[4], s2[4];
+            #pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const long long r = r0 + 32 * k;
+                const bool ok = r < rows_per_sample;
+                pv[k] = ok ? __ldg(base + r * c) : 0.f;
+                s1[k] = ok ? __ldg(base + plane + r * c) : 0.f;
+                s2[k] = ok ? __ldg(base + 2 * plane + r * c) : 0.f;
+            }
+            #pragma unroll
+            for (int k = 0; k < 4; k++) {
+                if (r0 + 32 * k >= rows_per_sample) break;
+                const double mw = (double)pv[k] + (double)s1[k] * (1.0 / 32.0);
+                a += mw; b += mw * mw;
+                m2 += (double)s2[k] - (double)s1[k] * (double)s1[k] * (1.0 / 32.0);
+            }
+        }
+    }
+    sh[0][slice][lane] = a; sh[1][slice][lane] = b; sh[2][slice][lane] = m2;
+    __syncthreads();
+    if (slice == 0 && ch < c) {
+        #pragma unroll 1
+        for (int k = 1; k < 32; k++) { a += sh[0][k][lane]; b += sh[1][k][lane]; m2 += sh[2][k][lane]; }
+        const double w = (double)rows_per_sample;
+        const double mu = a / w;
+        double var = (m2 + 32.0 * (b - a * a / w)) / (32.0 * w);
+        if (var < 0.0) var = 0.0;
+        mean[(long long)n * c + ch] = (float)mu;
+        rstd[(long long)n * c + ch] = (float)(1.0 / sqrt(var + (double)eps));
+    }
+}
+} // namespace pgpp
+
+extern "C" int pgpp_instnorm_finalize(const float* ws, int64_t rows, int n, int c, float eps, float* mean, float* rstd, void* stream) {
+    using namespace pgpp;
+    PGPP_REQUIRE(ws && mean && rstd, "ws, mean and rstd must be device pointers");
+    PGPP_REQUIRE(n >= 1 && c >= 1 && rows >= n && rows % n == 0, "rows must be a positive multiple of n");
+    dim3 grid((unsigned)((c + 31) / 32), (unsigned)n);
+    instnorm_finalize_kernel<<<grid, 1024, 0, (cudaStream_t)stream>>>(ws, rows, rows / n, c, eps, mean, rstd);
+    count_launch();
+    PGPP_CUDA_OK(cudaGetLastError());
+    return PGPP_OK;
+}
+
+static int pgpp::igemm_launch(const pgpp_conv_desc* d, void* stream, long long* stats_rows_query) {
     using namespace pgpp;
     PGPP_REQUIRE(d != nullptr, "desc is NULL");
     PGPP_REQUIRE(d->act && d->wgt && d->out, "act, wgt and out must be device pointers");
@@ -1268,6 +1378,15 @@ extern "C" int pgpp_conv2d_igemm(const pgpp_conv_desc* d, void* stream) {
     magic((unsigned)p.tiles_y, p.div_y_m, p.div_y_s);
     PGPP_REQUIRE(p.total_tiles < (1ll << 31), "too many tiles");
     p.dbg = env.igemm_debug;
+
+    // instance-norm partials of the output (pgpp_conv_desc.stats_ws): fast float32 NCHW epilogue, full pixel tiles, whole 16-column chunks
+    const bool stats_ok = p.tn == 1 && p.fold_gain && d->out_dtype == PGPP_F32 && d->phases == 1 && !d->accumulate && !d->spade_x && d->o % 16 == 0 &&
+                          d->conv_w % p.tw == 0 && d->conv_h % p.th == 0 && out_parts == 1;
+    const long long stats_rows = stats_ok ? (long long)p.tiles_x * p.tiles_y * p.tiles_n * 4 : 0;
+    if (stats_rows_query) { *stats_rows_query = stats_rows; return PGPP_OK; }
+    PGPP_REQUIRE(!d->stats_ws || stats_ok, "stats_ws: this launch cannot produce instance-norm statistics (see pgpp_conv2d_igemm_stats_rows)");
+    PGPP_REQUIRE(((uintptr_t)d->stats_ws & 15) == 0, "stats_ws must be 16-byte aligned");
+    p.stats_ws = d->stats_ws; p.stats_plane = stats_rows * d->o;
 
     // tensor maps
     CUtensorMap map_a, map_b;

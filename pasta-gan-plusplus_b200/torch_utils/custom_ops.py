@@ -48,6 +48,7 @@ class ConvDesc(ctypes.Structure):
         ('accumulate', ctypes.c_int32), ('out_parts', ctypes.c_int32), ('out_part_stride', ctypes.c_int64),
         ('spade_x', ctypes.c_void_p), ('spade_mean', ctypes.c_void_p), ('spade_rstd', ctypes.c_void_p), ('spade_pre_gain', ctypes.c_float),
         ('operand_f16', ctypes.c_int32),
+        ('stats_ws', ctypes.c_void_p),
     ]
 
 
@@ -107,6 +108,10 @@ def load_library():
     lib.pgpp_conv2d_direct.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, f32, i32, f32, f32, f32, vp, vp, i32, i32, i32, vp]
     lib.pgpp_conv2d_igemm.restype = i32
     lib.pgpp_conv2d_igemm.argtypes = [ctypes.POINTER(ConvDesc), vp]
+    lib.pgpp_conv2d_igemm_stats_rows.restype = i64
+    lib.pgpp_conv2d_igemm_stats_rows.argtypes = [ctypes.POINTER(ConvDesc)]
+    lib.pgpp_instnorm_finalize.restype = i32
+    lib.pgpp_instnorm_finalize.argtypes = [vp, i64, i32, i32, f32, vp, vp, vp]
     lib.pgpp_conv2d_wgrad.restype = i32
     lib.pgpp_conv2d_wgrad.argtypes = [ctypes.POINTER(WgradDesc), vp]
     lib.pgpp_u8_to_f32.restype = i32
@@ -124,7 +129,7 @@ def load_library():
 EXPORTED_SYMBOLS = ('pgpp_version', 'pgpp_last_error', 'pgpp_launch_count', 'pgpp_refresh_env', 'pgpp_bias_act', 'pgpp_upfirdn2d',
                     'pgpp_modconv_demod_coefs', 'pgpp_pack_activations', 'pgpp_pack_activations_slice', 'pgpp_pack_activations_f16',
                     'pgpp_pack_weights', 'pgpp_up2_weight_adjoint', 'pgpp_mul_reduce_hw', 'pgpp_modulate_weights',
-                    'pgpp_spade_modulate_pack', 'pgpp_mix_pack', 'pgpp_conv2d_direct', 'pgpp_fir_pack', 'pgpp_fir_packed', 'pgpp_conv1x1_thin', 'pgpp_pack_im2col', 'pgpp_conv2d_igemm', 'pgpp_conv2d_wgrad', 'pgpp_u8_to_f32',
+                    'pgpp_spade_modulate_pack', 'pgpp_mix_pack', 'pgpp_conv2d_direct', 'pgpp_fir_pack', 'pgpp_fir_packed', 'pgpp_conv1x1_thin', 'pgpp_pack_im2col', 'pgpp_conv2d_igemm', 'pgpp_conv2d_igemm_stats_rows', 'pgpp_instnorm_finalize', 'pgpp_conv2d_wgrad', 'pgpp_u8_to_f32',
                     'pgpp_image_to_u8', 'pgpp_grid_sample_2d', 'pgpp_grid_sample_2d_backward')
 
 
@@ -527,6 +532,27 @@ class _ConvPlugin:
         with torch.cuda.device(device):
             stream = ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
             _check(lib.pgpp_conv2d_igemm(ctypes.byref(desc), stream))
+
+    @staticmethod
+    def conv2d_igemm_stats_rows(desc, device):
+        """rows of the instance-norm partial workspace this launch would fill (0: it cannot produce statistics)"""
+        lib = load_library()
+        with torch.cuda.device(device):
+            rows = int(lib.pgpp_conv2d_igemm_stats_rows(ctypes.byref(desc)))
+        if rows < 0:
+            raise RuntimeError(lib.pgpp_last_error().decode())
+        return rows
+
+    @staticmethod
+    def instnorm_finalize(ws, n, eps):
+        """ws float32 [3, rows, C] (warp partials written by conv2d_igemm) -> (mean [N, C], rstd [N, C]) float32"""
+        lib = load_library()
+        rows, c = int(ws.shape[1]), int(ws.shape[2])
+        mean = torch.empty([n, c], dtype=torch.float32, device=ws.device)
+        rstd = torch.empty([n, c], dtype=torch.float32, device=ws.device)
+        with torch.cuda.device(ws.device):
+            _check(lib.pgpp_instnorm_finalize(_ptr(ws), rows, int(n), c, float(eps), _ptr(mean), _ptr(rstd), _stream(ws)))
+        return mean, rstd
 
     @staticmethod
     def conv2d_wgrad(desc, device):

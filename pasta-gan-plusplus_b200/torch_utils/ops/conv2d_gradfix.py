@@ -361,14 +361,17 @@ def fir_packed(xp, f, down=1, padding=(0, 0, 0, 0), flip_filter=False, gain=1.0,
 
 def igemm_conv(x, pw, *, scale=None, stride=1, out_hw=None, dcoef=None, noise=None, bias=None, act='linear',
                alpha=0.0, gain=1.0, clamp=-1.0, out=None, out_dtype=None, accumulate=False, precision=None,
-               memory_format=None, out_packed=None, spade=None):
+               memory_format=None, out_packed=None, spade=None, instnorm_eps=None):
     """Run one fused convolution.
     x          [N, I, H, W] tensor (any float dtype / layout; packed here, `scale` [N, I] = style modulation folded into the
                packing pass) or a PackedAct (no packing pass; `scale` is then folded into per-sample weights).
     out_packed None -> returns a [N, O, out_h, out_w] tensor (`out` / `out_dtype` / `memory_format` as given);
                PackedAct view -> the epilogue writes the bf16 operand format of the next conv into that channel slice.
     spade      (x_norm [N, C, H, W] float32, mean [N, C], rstd [N, C], pre_gain): the GEMM's O = 2C columns are gamma | beta and the
-               epilogue writes pre_act((x_norm - mean) * rstd * (1 + gamma) + beta) into `out_packed` (C channels)."""
+               epilogue writes pre_act((x_norm - mean) * rstd * (1 + gamma) + beta) into `out_packed` (C channels).
+    instnorm_eps  not None -> returns (y, mean [N, O], rstd [N, O]): the instance-norm statistics of the float32 NCHW result
+               (torch.var_mean(y, (2, 3), unbiased=False), rstd = rsqrt(var + eps)), from partial sums the epilogue leaves per warp and a
+               small float64 merge kernel - no second pass over y.  Launches that cannot produce them fall back to torch.var_mean."""
     _init()
     n, ic, h, w = x.shape
     im = pw.im2col
@@ -485,6 +488,13 @@ def igemm_conv(x, pw, *, scale=None, stride=1, out_hw=None, dcoef=None, noise=No
     d.out_h, d.out_w = out_h, out_w
     d.accumulate = int(bool(accumulate))
     d.operand_f16 = int(f16)
+    stats_ws = None
+    if instnorm_eps is not None:
+        assert out_packed is None and spade is None
+        rows = _plugin.conv2d_igemm_stats_rows(d, device) if (result.dtype == torch.float32 and result.is_contiguous()) else 0
+        if rows > 0:
+            stats_ws = torch.empty([3, rows, pw.o], dtype=torch.float32, device=device)
+            d.stats_ws = stats_ws.data_ptr()
     if trace is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -501,6 +511,13 @@ def igemm_conv(x, pw, *, scale=None, stride=1, out_hw=None, dcoef=None, noise=No
         _plugin.conv2d_igemm(d, device)
     if out_packed is None and want_f64:
         result = result.to(torch.float64)       # the reference returns the input dtype (conv2d_gradfix.py:112-114)
+    if instnorm_eps is not None:
+        if stats_ws is not None:
+            mean, rstd = _plugin.instnorm_finalize(stats_ws, n, instnorm_eps)
+        else:
+            var, mean = torch.var_mean(result.to(torch.float32), dim=(2, 3), unbiased=False)
+            rstd = (var + instnorm_eps).rsqrt()
+        return result, mean, rstd
     return result
 
 

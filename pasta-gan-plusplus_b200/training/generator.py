@@ -173,8 +173,17 @@ class Dense(torch.nn.Module):
         self.activation = torch.nn.LeakyReLU()
         self.linear = torch.nn.Linear(in_channels, out_channels)
 
-    def forward(self, x):
-        out = self.linear(x.permute(0, 2, 3, 1)).permute(0, 3, 1, 2)
+    def forward(self, x, fused=True):
+        w = self.linear.weight
+        if fused and torch.is_tensor(x) and x.dtype == torch.float32 and x.shape[2] * x.shape[3] >= 128 and S._can_fuse(x, w, self.linear.bias):
+            # the per-pixel Linear is a 1x1 convolution: one packing pass + one implicit-GEMM launch instead of a permuted copy, a SIMT
+            # float32 GEMM and a second copy back to NCHW (networks.py:391-408 computes exactly sum_c W[o, c] x[n, c, h, w] + b[o])
+            parts = S._parts()
+            pw = conv2d_gradfix._cached(w, ('dense1x1', parts),
+                                        lambda: conv2d_gradfix.pack_weights_native(w.detach()[:, :, None, None], 1, 1, parts, 0, 0))
+            out = conv2d_gradfix.igemm_conv(x, pw, bias=self.linear.bias)
+        else:
+            out = self.linear(x.permute(0, 2, 3, 1)).permute(0, 3, 1, 2)
         return self.activation(self.bn(out))
 
 
@@ -207,7 +216,7 @@ class StyleEncoderNetworkV18(torch.nn.Module):
                 const_input = layer(const_input, fused=fused, impl=impl)
                 const_feats.append(const_input)
         for layer in self.model:
-            x = layer(x, fused=fused, impl=impl) if isinstance(layer, Conv2dLayer) else layer(x)
+            x = layer(x, fused=fused, impl=impl) if isinstance(layer, Conv2dLayer) else (layer(x, fused=fused) if isinstance(layer, Dense) else layer(x))
         return self.fc(x.view(x.size(0), -1), impl=impl), const_feats
 
 
@@ -232,7 +241,7 @@ class Spade_Conv2dLayer(torch.nn.Module):
         self.weight = torch.nn.Parameter(torch.randn([out_channels, in_channels, kernel_size, kernel_size]))
         self.bias = torch.nn.Parameter(torch.zeros([out_channels])) if bias else None
 
-    def conv_packed(self, xp, act='linear', gain=1.0, out_packed=None, out=None, accumulate=False):
+    def conv_packed(self, xp, act='linear', gain=1.0, out_packed=None, out=None, accumulate=False, instnorm_eps=None):
         """the convolution alone on an operand-format input (pre-activation already applied by the producer of `xp`); a
         `RawFeat` input (few-channel NCHW map) goes through the exact-fp32 direct kernel instead"""
         if isinstance(xp, RawFeat):
@@ -240,7 +249,7 @@ class Spade_Conv2dLayer(torch.nn.Module):
             return conv2d_gradfix.direct_conv(xp.x, self.weight, None, wscale=self.weight_gain, act=act, gain=gain, out_packed=out_packed)
         pw = conv2d_gradfix.packed_plain(self.weight, True, S._parts(), self.padding, self.padding, scale=self.weight_gain,
                                          allow_im2col=xp.logical_hw is not None)
-        return conv2d_gradfix.igemm_conv(xp, pw, act=act, gain=gain, out_packed=out_packed, out=out, accumulate=accumulate)
+        return conv2d_gradfix.igemm_conv(xp, pw, act=act, gain=gain, out_packed=out_packed, out=out, accumulate=accumulate, instnorm_eps=instnorm_eps)
 
     def forward(self, x, gain=1, no_act=False, fused=True, impl='cuda'):
         b = self.bias.to(x.dtype) if self.bias is not None else None
@@ -255,6 +264,7 @@ class Spade_Conv2dLayer(torch.nn.Module):
         return conv2d_resample.conv2d_resample(x=x, w=w.to(x.dtype), f=self.resample_filter, padding=self.padding, flip_weight=True)
 
 
+FUSE_INSTNORM_STATS = True      # False: torch.var_mean over the float32 NCHW tensor (a second pass over it; kept for comparison / tests)
 FUSE_SPADE_EPILOGUE = True      # False: gamma|beta GEMM -> float32 NCHW, then pgpp_spade_modulate_pack (kept for comparison / tests)
 
 
@@ -340,8 +350,13 @@ class Spade_ResBlockV4_512(torch.nn.Module):
                     feats_packed = PackedAct(data, r * 3 * fc, 0, logical_hw=(fh, fw))
                 else:
                     feats_packed = PackedAct(conv2d_gradfix._plugin.pack_activations(denorm_feat, None, -(-fc // 64) * 64, S._parts()), fc)
-            x = (self.conv.conv_packed(x) if isinstance(x, PackedAct) else self.conv(x, no_act=True, fused=True)).contiguous()
-            mean, rstd = self._stats(x)
+            # the instance-norm statistics of x come out of the producing convolution's epilogue (FUSE_INSTNORM_STATS)
+            eps = float(self.spade0.param_free_norm.eps)
+            if isinstance(x, PackedAct) and FUSE_INSTNORM_STATS:
+                x, mean, rstd = self.conv.conv_packed(x, instnorm_eps=eps)
+            else:
+                x = (self.conv.conv_packed(x) if isinstance(x, PackedAct) else self.conv(x, no_act=True, fused=True)).contiguous()
+                mean, rstd = self._stats(x)
             xs = self.spade_skip.fused_packed(x, mean, rstd, feats_packed, relu_gain * SQRT_HALF)
             if out_packed:
                 n, _, h, w = x.shape
@@ -350,8 +365,11 @@ class Spade_ResBlockV4_512(torch.nn.Module):
                 self.skip.conv_packed(xs, out_packed=y)
             else:
                 y = self.skip.conv_packed(xs)
-            x = self.conv0.conv_packed(self.spade0.fused_packed(x, mean, rstd, feats_packed, relu_gain)).contiguous()
-            mean, rstd = self._stats(x)
+            if FUSE_INSTNORM_STATS:
+                x, mean, rstd = self.conv0.conv_packed(self.spade0.fused_packed(x, mean, rstd, feats_packed, relu_gain), instnorm_eps=eps)
+            else:
+                x = self.conv0.conv_packed(self.spade0.fused_packed(x, mean, rstd, feats_packed, relu_gain)).contiguous()
+                mean, rstd = self._stats(x)
             xs = self.spade1.fused_packed(x, mean, rstd, feats_packed, relu_gain * SQRT_HALF)
             if out_packed:
                 self.conv1.conv_packed(xs, out_packed=y, accumulate=True)

@@ -220,3 +220,58 @@ def test_pack_activations_every_source_dtype_and_alignment(shape, dtype):
         data = cg._plugin.pack_activations(x, None, c_pad, 1, f16=True)
         got = data.view(torch.float16)[0].permute(0, 3, 1, 2)[:, :c]
         assert torch.equal(got, x)
+
+
+@pytest.mark.parametrize('prec', ['bf16x2', 'bf16'])
+@pytest.mark.parametrize('n,ic,oc,h,w', [(2, 64, 64, 32, 32), (3, 128, 128, 16, 32), (1, 64, 128, 64, 16), (2, 64, 48, 16, 16), (2, 64, 64, 20, 24)], ids=str)
+def test_instance_norm_statistics_from_the_conv_epilogue(n, ic, oc, h, w, prec):
+    """igemm_conv(instnorm_eps=...) returns the statistics `torch.nn.InstanceNorm2d` / `torch.var_mean(y, (2, 3), unbiased=False)` would
+    compute on the convolution's OWN float32 output (networks.py:1702-1723 normalises what the preceding conv wrote): warp partials
+    around a pivot in the epilogue + a float64 merge.  Checked against float64 statistics of the returned tensor, including a channel
+    with a large mean and a tiny variance (cancellation) and a constant channel; (20, 24) is not a multiple of the pixel tile and takes
+    the torch.var_mean fall-back."""
+    cg._init()
+    cg.fp32_precision = prec
+    g = torch.Generator().manual_seed(81)
+    x = torch.randn(n, ic, h, w, generator=g).to(DEV)
+    wt = torch.randn(oc, ic, 3, 3, generator=g).to(DEV) / (ic * 9) ** 0.5
+    bias = torch.randn(oc, generator=g).to(DEV)
+    wt[1] = 0; bias[1] = 3.0                       # constant channel: variance exactly 0
+    wt[2] *= 1e-4; bias[2] = 50.0                  # mean^2 / var ~ 1e10
+    parts = cg._PRODUCTS[prec][1]
+    xp = cg.PackedAct(cg._plugin.pack_activations(x, None, ic, parts), ic)
+    pw = cg.packed_plain(wt, True, parts, 1, 1)
+    y, mean, rstd = cg.igemm_conv(xp, pw, bias=bias, instnorm_eps=1e-5)
+    assert tuple(y.shape) == (n, oc, h, w) and tuple(mean.shape) == (n, oc) and tuple(rstd.shape) == (n, oc)
+    y_plain = cg.igemm_conv(xp, pw, bias=bias)
+    assert torch.equal(y, y_plain)                                      # the statistics do not change what is written
+    yd = y.double()
+    want_mean = yd.mean(dim=(2, 3))
+    want_var = yd.var(dim=(2, 3), unbiased=False)
+    want_rstd = (want_var + 1e-5).rsqrt()
+    assert float((mean.double() - want_mean).abs().max()) <= 2e-6 * max(1.0, float(want_mean.abs().max()))
+    assert float(((rstd.double() - want_rstd) / want_rstd).abs().max()) <= 2e-5
+    assert float(mean[:, 1].sub(3.0).abs().max()) == 0.0 and float((rstd[:, 1] - 1e-5 ** -0.5).abs().max()) <= 1e-2
+    # and against the library statistics the unfused route uses
+    var_t, mean_t = torch.var_mean(y, dim=(2, 3), unbiased=False)
+    assert float((mean - mean_t).abs().max()) <= 1e-5 * max(1.0, float(mean_t.abs().max()))
+    assert float(((rstd - (var_t + 1e-5).rsqrt()) / want_rstd.float()).abs().max()) <= 1e-3
+
+
+def test_spade_block_with_fused_statistics_equals_the_var_mean_route():
+    cg._init()
+    torch.manual_seed(5)
+    blk = gen.Spade_ResBlockV4_512(64, 64, spade_channels=1).to(DEV).eval()
+    x = torch.randn(2, 64, 64, 64, device=DEV)
+    parsing = torch.randint(0, 7, (2, 1, 64, 64), device=DEV).float()
+    xp = lambda: cg.PackedAct(cg._plugin.pack_activations(x, None, 64, 2), 64)
+    with torch.no_grad():
+        old = gen.FUSE_INSTNORM_STATS
+        try:
+            gen.FUSE_INSTNORM_STATS = True
+            a = blk(xp(), parsing)
+            gen.FUSE_INSTNORM_STATS = False
+            b = blk(xp(), parsing)
+        finally:
+            gen.FUSE_INSTNORM_STATS = old
+    assert rel_l2(a, b) < 2e-6

@@ -158,14 +158,16 @@ def test_weight_operand_layout():
 def test_conv_desc_mirror_matches_c_struct_layout(tmp_path):
     import subprocess
     src = tmp_path / 'sz.c'
-    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "pgpp.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu\\n",'
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "pgpp.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu\\n",'
                    'sizeof(pgpp_conv_desc),offsetof(pgpp_conv_desc,phase_stride),offsetof(pgpp_conv_desc,dcoef),'
-                   'offsetof(pgpp_conv_desc,out),offsetof(pgpp_conv_desc,out_stride),offsetof(pgpp_conv_desc,accumulate));return 0;}\n')
+                   'offsetof(pgpp_conv_desc,out),offsetof(pgpp_conv_desc,out_stride),offsetof(pgpp_conv_desc,accumulate),'
+                   'offsetof(pgpp_conv_desc,operand_f16),offsetof(pgpp_conv_desc,stats_ws));return 0;}\n')
     exe = tmp_path / 'sz'
     subprocess.run(['gcc', '-I', os.path.join(ROOT, 'include'), str(src), '-o', str(exe)], check=True)
     c = [int(v) for v in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()]
     D = custom_ops.ConvDesc
-    assert c == [ctypes.sizeof(D), D.phase_stride.offset, D.dcoef.offset, D.out.offset, D.out_stride.offset, D.accumulate.offset]
+    assert c == [ctypes.sizeof(D), D.phase_stride.offset, D.dcoef.offset, D.out.offset, D.out_stride.offset, D.accumulate.offset,
+                 D.operand_f16.offset, D.stats_ws.offset]
 
 
 def test_wgrad_desc_mirror_matches_c_struct_layout(tmp_path):
