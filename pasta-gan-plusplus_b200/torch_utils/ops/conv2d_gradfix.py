@@ -524,20 +524,28 @@ def igemm_conv(x, pw, *, scale=None, stride=1, out_hw=None, dcoef=None, noise=No
 # ------------------------------------------------------------------------------------------------
 # public API
 
-def conv2d(input, weight, bias=None, stride=1, padding=0, dilation=1, groups=1):
+def _library_weight(input, weight, weight_scale):
+    w = weight if weight_scale == 1.0 else weight * weight_scale
+    return w if w.dtype == input.dtype else w.to(input.dtype)
+
+
+def conv2d(input, weight, bias=None, stride=1, padding=0, dilation=1, groups=1, weight_scale=1.0):
+    """`weight_scale` (extension to conv2d_gradfix.py:22-25): the result is conv2d(input, weight * weight_scale) with the constant folded
+    into the packed copy of `weight` - pass the PARAMETER itself (float32 also for float16 inputs) instead of `weight * gain` and the
+    packed copy is made once per optimizer step, not once per call."""
     if _should_use_custom_op(input):
         return _conv2d_gradfix(transpose=False, weight_shape=weight.shape, stride=stride, padding=padding, output_padding=0,
-                               dilation=dilation, groups=groups).apply(input, weight, bias)
-    return torch.nn.functional.conv2d(input=input, weight=weight, bias=bias, stride=stride, padding=padding,
+                               dilation=dilation, groups=groups, weight_scale=float(weight_scale)).apply(input, weight, bias)
+    return torch.nn.functional.conv2d(input=input, weight=_library_weight(input, weight, weight_scale), bias=bias, stride=stride, padding=padding,
                                       dilation=dilation, groups=groups)
 
 
-def conv_transpose2d(input, weight, bias=None, stride=1, padding=0, output_padding=0, groups=1, dilation=1):
+def conv_transpose2d(input, weight, bias=None, stride=1, padding=0, output_padding=0, groups=1, dilation=1, weight_scale=1.0):
     if _should_use_custom_op(input):
         return _conv2d_gradfix(transpose=True, weight_shape=weight.shape, stride=stride, padding=padding,
-                               output_padding=output_padding, groups=groups, dilation=dilation).apply(input, weight, bias)
-    return torch.nn.functional.conv_transpose2d(input=input, weight=weight, bias=bias, stride=stride, padding=padding,
-                                                output_padding=output_padding, groups=groups, dilation=dilation)
+                               output_padding=output_padding, groups=groups, dilation=dilation, weight_scale=float(weight_scale)).apply(input, weight, bias)
+    return torch.nn.functional.conv_transpose2d(input=input, weight=_library_weight(input, weight, weight_scale), bias=bias, stride=stride,
+                                                padding=padding, output_padding=output_padding, groups=groups, dilation=dilation)
 
 
 def pack_operand(x, prec=None):
@@ -548,12 +556,12 @@ def pack_operand(x, prec=None):
     return PackedAct(data, x.shape[1])
 
 
-def _forward_conv(x, weight, bias, stride, padding, keep=False):
+def _forward_conv(x, weight, bias, stride, padding, keep=False, scale=1.0):
     """F.conv2d(x, weight, bias, stride, padding) on the tensor cores.  x: tensor or PackedAct (then `keep` is moot).
     keep=True also returns the packed copy of x (for the weight gradient)."""
-    src_dtype = weight.dtype if isinstance(x, PackedAct) else x.dtype
+    src_dtype = (torch.float16 if x.data.dtype == torch.float16 else weight.dtype) if isinstance(x, PackedAct) else x.dtype   # f16 operands: fp16 layer
     prec = precision_for(src_dtype)
-    pw = packed_plain(weight, True, _PRODUCTS[prec][1], padding[0], padding[1], f16=prec == 'f16')
+    pw = packed_plain(weight, True, _PRODUCTS[prec][1], padding[0], padding[1], f16=prec == 'f16', scale=scale)
     xp, mf = x, None
     if keep and not isinstance(x, PackedAct):
         mf = torch.channels_last if (x.stride(1) == 1 and x.shape[1] > 1) else torch.contiguous_format     # the output follows the input's layout
@@ -565,7 +573,7 @@ def _forward_conv(x, weight, bias, stride, padding, keep=False):
     return (y, xp) if keep else y
 
 
-def _forward_conv_transpose(x, weight, bias, stride, padding, output_padding, keep=False):
+def _forward_conv_transpose(x, weight, bias, stride, padding, output_padding, keep=False, scale=1.0):
     """F.conv_transpose2d(x, weight[I, O, kh, kw], ...) as zero insertion + a stride-1 convolution with the
     flipped, transposed kernel (the data-gradient form; the fused up=2 layer does NOT come through here).
     x: tensor, or for stride 1 a PackedAct.  keep=True also returns the packed copy of x when the kernel consumed x itself
@@ -573,7 +581,7 @@ def _forward_conv_transpose(x, weight, bias, stride, padding, output_padding, ke
     from . import upfirdn2d as _up
     ic, oc, kh, kw = weight.shape
     sy, sx = stride
-    src_dtype = weight.dtype if isinstance(x, PackedAct) else x.dtype
+    src_dtype = (torch.float16 if x.data.dtype == torch.float16 else weight.dtype) if isinstance(x, PackedAct) else x.dtype   # f16 operands: fp16 layer
     strided = sy > 1 or sx > 1
     if strided:
         assert not isinstance(x, PackedAct)
@@ -582,7 +590,7 @@ def _forward_conv_transpose(x, weight, bias, stride, padding, output_padding, ke
     py, px = kh - 1 - padding[0], kw - 1 - padding[1]
     assert py >= 0 and px >= 0, 'conv_transpose2d padding larger than kernel_size-1 is not supported'
     prec = precision_for(src_dtype)
-    pw = packed_plain(weight, False, _PRODUCTS[prec][1], py, px, transpose_io=True, f16=prec == 'f16')    # flipped + transposed = equivalent correlation kernel
+    pw = packed_plain(weight, False, _PRODUCTS[prec][1], py, px, transpose_io=True, f16=prec == 'f16', scale=scale)    # flipped + transposed = equivalent correlation kernel
     n, _, h, w = x.shape
     out_h = h + 2 * py - kh + 1 + output_padding[0]
     out_w = w + 2 * px - kw + 1 + output_padding[1]
@@ -645,14 +653,14 @@ def weight_gradient(grad_output, input, weight_shape, stride, padding, transpose
 _conv2d_gradfix_cache = dict()
 
 
-def _conv2d_gradfix(transpose, weight_shape, stride, padding, output_padding, dilation, groups):
+def _conv2d_gradfix(transpose, weight_shape, stride, padding, output_padding, dilation, groups, weight_scale=1.0):
     ndim = 2
     weight_shape = tuple(weight_shape)
     stride = _tuple_of_ints(stride, ndim)
     padding = _tuple_of_ints(padding, ndim)
     output_padding = _tuple_of_ints(output_padding, ndim)
     dilation = _tuple_of_ints(dilation, ndim)
-    key = (transpose, weight_shape, stride, padding, output_padding, dilation, groups)
+    key = (transpose, weight_shape, stride, padding, output_padding, dilation, groups, weight_scale)
     if key in _conv2d_gradfix_cache:
         return _conv2d_gradfix_cache[key]
 
@@ -669,7 +677,7 @@ def _conv2d_gradfix(transpose, weight_shape, stride, padding, output_padding, di
         raise NotImplementedError('the sm_100a convolution supports groups=1, dilation=1, stride 1 or 2; '
                                   'set conv2d_gradfix.enabled = False to route this call to the PyTorch library op')
 
-    common_kwargs = dict(stride=stride, padding=padding, dilation=dilation, groups=groups)
+    common_kwargs = dict(stride=stride, padding=padding, dilation=dilation, groups=groups, weight_scale=weight_scale)
 
     def calc_output_padding(input_shape, output_shape):
         if transpose:
@@ -684,9 +692,9 @@ def _conv2d_gradfix(transpose, weight_shape, stride, padding, output_padding, di
             keep = keep_packed_operands and ctx.needs_input_grad[1]
             ctx.input_packed = None
             if not transpose:
-                output = _forward_conv(input, weight, bias, stride, padding, keep=keep)
+                output = _forward_conv(input, weight, bias, stride, padding, keep=keep, scale=weight_scale)
             else:
-                output = _forward_conv_transpose(input, weight, bias, stride, padding, output_padding, keep=keep)
+                output = _forward_conv_transpose(input, weight, bias, stride, padding, output_padding, keep=keep, scale=weight_scale)
             if keep:
                 output, ctx.input_packed = output
             ctx.save_for_backward(input, weight)
@@ -707,13 +715,15 @@ def _conv2d_gradfix(transpose, weight_shape, stride, padding, output_padding, di
                 if ctx.needs_input_grad[0]:
                     p = calc_output_padding(input_shape=input.shape, output_shape=grad_output.shape)
                     if transpose:       # gradient of conv_transpose2d = conv2d of grad_output with the same weight
-                        grad_input = _forward_conv(go, weight, None, stride, padding)
+                        grad_input = _forward_conv(go, weight, None, stride, padding, scale=weight_scale)
                     else:               # gradient of conv2d = conv_transpose2d (zero insertion first when strided)
-                        grad_input = _forward_conv_transpose(go if stride[0] == 1 else grad_output, weight, None, stride, padding, p)
+                        grad_input = _forward_conv_transpose(go if stride[0] == 1 else grad_output, weight, None, stride, padding, p, scale=weight_scale)
                     assert grad_input.shape == input.shape
                 if want_w:
                     xin = ctx.input_packed if ctx.input_packed is not None else input
                     grad_weight = weight_gradient(go, xin, weight_shape, stride[0], padding, transpose, precision=prec, out_dtype=weight.dtype)
+                    if weight_scale != 1.0:
+                        grad_weight = grad_weight * weight_scale
                     assert grad_weight.shape == weight_shape
                 ctx.input_packed = None
             else:
@@ -724,6 +734,8 @@ def _conv2d_gradfix(transpose, weight_shape, stride, padding, output_padding, di
                     assert grad_input.shape == input.shape
                 if want_w:
                     grad_weight = Conv2dGradWeight.apply(grad_output, input)
+                    if grad_weight.dtype != weight.dtype:
+                        grad_weight = grad_weight.to(weight.dtype)
                     assert grad_weight.shape == weight_shape
             if ctx.needs_input_grad[2]:
                 grad_bias = grad_output.sum([0, 2, 3])
@@ -733,6 +745,8 @@ def _conv2d_gradfix(transpose, weight_shape, stride, padding, output_padding, di
         @staticmethod
         def forward(ctx, grad_output, input):
             gw = weight_gradient(grad_output, input, weight_shape, stride[0], padding, transpose)
+            if weight_scale != 1.0:
+                gw = gw * weight_scale
             assert gw.shape == weight_shape
             ctx.save_for_backward(grad_output, input)
             return gw

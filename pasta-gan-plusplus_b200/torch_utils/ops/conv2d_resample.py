@@ -21,13 +21,15 @@ def _get_weight_shape(w):
     return shape
 
 
-def _conv2d_wrapper(x, w, stride=1, padding=0, groups=1, transpose=False, flip_weight=True):
+def _conv2d_wrapper(x, w, stride=1, padding=0, groups=1, transpose=False, flip_weight=True, w_scale=1.0):
     """conv2d / conv_transpose2d through conv2d_gradfix; flip_weight=False means true convolution."""
     _get_weight_shape(w)
     if not flip_weight:
         w = w.flip([2, 3])
     op = conv2d_gradfix.conv_transpose2d if transpose else conv2d_gradfix.conv2d
-    return op(x, w, stride=stride, padding=padding, groups=groups)
+    if w_scale == 1.0:
+        return op(x, w, stride=stride, padding=padding, groups=groups)
+    return op(x, w, stride=stride, padding=padding, groups=groups, weight_scale=w_scale)
 
 
 def _needs_grad(*tensors):
@@ -74,11 +76,13 @@ def _transposed_weight(w, groups):
 
 
 @misc.profiled_function
-def conv2d_resample(x, w, f=None, up=1, down=1, padding=0, groups=1, flip_weight=True, flip_filter=False):
+def conv2d_resample(x, w, f=None, up=1, down=1, padding=0, groups=1, flip_weight=True, flip_filter=False, w_scale=1.0):
     """x [N, I, H, W], w [O, I/groups, kh, kw], f from upfirdn2d.setup_filter() or None.  Padding is given
-    with respect to the upsampled image and applied once."""
+    with respect to the upsampled image and applied once.
+    `w_scale` (extension): the convolution uses w * w_scale; with it `w` may be the float32 parameter itself also for a float16 x
+    (see conv2d_gradfix.conv2d: the constant and the cast are folded into the cached packed copy of the parameter)."""
     assert isinstance(x, torch.Tensor) and (x.ndim == 4)
-    assert isinstance(w, torch.Tensor) and (w.ndim == 4) and (w.dtype == x.dtype)
+    assert isinstance(w, torch.Tensor) and (w.ndim == 4) and (w.dtype == x.dtype or (w_scale != 1.0 and w.dtype == torch.float32))
     assert f is None or (isinstance(f, torch.Tensor) and f.ndim in [1, 2] and f.dtype == torch.float32)
     assert isinstance(up, int) and (up >= 1)
     assert isinstance(down, int) and (down >= 1)
@@ -91,11 +95,13 @@ def conv2d_resample(x, w, f=None, up=1, down=1, padding=0, groups=1, flip_weight
     if (up == 2 and down == 1 and groups == 1 and (kh, kw) == (3, 3) and f is not None and f.ndim == 2 and (fw, fh) == (4, 4)
             and pad.fir == [1, 1, 1, 1] and conv2d_gradfix._should_use_custom_op(x) and not _needs_grad(x, w) and x.dtype != torch.float16):
         _, parts = conv2d_gradfix._PRODUCTS[conv2d_gradfix.precision_for(x.dtype)]
+        if w_scale != 1.0:
+            w = w * w_scale
         return conv2d_gradfix.igemm_conv(x, conv2d_gradfix.packed_up2(w, f, flip_weight, flip_filter, parts))
 
     pad.widen(fw, fh, up, down)
     fir = lambda t, **kw_: upfirdn2d.upfirdn2d(x=t, f=f, flip_filter=flip_filter, **kw_)
-    conv = lambda t, **kw_: _conv2d_wrapper(x=t, w=w, groups=groups, flip_weight=flip_weight, **kw_)
+    conv = lambda t, **kw_: _conv2d_wrapper(x=t, w=w, groups=groups, flip_weight=flip_weight, w_scale=w_scale, **kw_)
     pointwise = kh == 1 and kw == 1
 
     if up == 1 and down > 1:
@@ -111,7 +117,7 @@ def conv2d_resample(x, w, f=None, up=1, down=1, padding=0, groups=1, flip_weight
         pxt = max(min(-pad.x0, -pad.x1), 0)
         pyt = max(min(-pad.y0, -pad.y1), 0)
         x = _conv2d_wrapper(x=x, w=_transposed_weight(w, groups), stride=up, padding=[pyt, pxt], groups=groups, transpose=True,
-                            flip_weight=(not flip_weight))
+                            flip_weight=(not flip_weight), w_scale=w_scale)
         x = fir(x, padding=pad.shift(pxt, pxt, pyt, pyt).fir, gain=up ** 2)
         return fir(x, down=down) if down > 1 else x
 

@@ -260,6 +260,9 @@ class Spade_Conv2dLayer(torch.nn.Module):
             parts = conv2d_gradfix._PRODUCTS[conv2d_gradfix.precision_for(x.dtype)][1]
             pw = conv2d_gradfix.packed_plain(self.weight, True, parts, self.padding, self.padding, scale=self.weight_gain)
             return conv2d_gradfix.igemm_conv(x, pw)
+        if conv2d_gradfix._should_use_custom_op(x) and self.weight.dtype == torch.float32:
+            return conv2d_resample.conv2d_resample(x=x, w=self.weight, f=self.resample_filter, padding=self.padding, flip_weight=True,
+                                                   w_scale=float(self.weight_gain))
         w = self.weight * self.weight_gain
         return conv2d_resample.conv2d_resample(x=x, w=w.to(x.dtype), f=self.resample_filter, padding=self.padding, flip_weight=True)
 

@@ -162,10 +162,16 @@ class Conv2dLayer(torch.nn.Module):
             x = upfirdn2d._plugin.upfirdn2d(x, self.resample_filter, 1, 1, 1, 1, p0, p1, p0, p1, False, 1.0, row_align=4)
             return conv2d_gradfix.igemm_conv(x, pw, stride=2, out_packed=out_packed, **epi)
         assert out_packed is None and not isinstance(x, PackedAct)
-        w = self.weight * self.weight_gain
         b = self.bias.to(x.dtype) if self.bias is not None else None
-        x = conv2d_resample.conv2d_resample(x=x, w=w.to(x.dtype), f=self.resample_filter, up=self.up, down=self.down,
-                                            padding=self.padding, flip_weight=(self.up == 1))
+        if conv2d_gradfix._should_use_custom_op(x) and self.weight.dtype == torch.float32:
+            # kernel path (training): the runtime gain and the cast are folded into the packed copy of the PARAMETER, which is then made
+            # once per optimizer step instead of once per call from the temporary `weight * gain` (networks.py:169)
+            x = conv2d_resample.conv2d_resample(x=x, w=self.weight, f=self.resample_filter, up=self.up, down=self.down,
+                                                padding=self.padding, flip_weight=(self.up == 1), w_scale=float(self.weight_gain))
+        else:
+            w = self.weight * self.weight_gain
+            x = conv2d_resample.conv2d_resample(x=x, w=w.to(x.dtype), f=self.resample_filter, up=self.up, down=self.down,
+                                                padding=self.padding, flip_weight=(self.up == 1))
         return bias_act.bias_act(x, b, act=self.activation, gain=act_gain, clamp=act_clamp, impl=impl)
 
 
