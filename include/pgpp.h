@@ -138,6 +138,9 @@ PGPP_API int pgpp_up2_weight_adjoint(const float* grad_polyphase, const float* f
  *   out_scaled[n,c,hw] = a[n,c,hw] * scale[n,c]                                      (out_scaled NULL: skipped; may alias a)
  * (a, b, sub) = (grad_y, y, noise): gradient of the demodulation coefficients (times dcoef);
  * (a, b, scale) = (grad of the modulated input, x, styles): style gradient and grad_x in one pass. */
+/* r[n, c] = sum_{hw} a[n, c, hw] with float32 accumulation; a NCHW-contiguous float32 / float16 / bfloat16 (dtype: pgpp_dtype).
+ * The bias gradients `dx.sum([0, 2, 3])` of bias_act.py:135,156 and conv2d_gradfix.py:130 are the sum over n of this. */
+PGPP_API int pgpp_sum_hw(const void* a, int dtype, float* r, int n, int c, int64_t hw, void* stream);
 PGPP_API int pgpp_mul_reduce_hw(const float* a, const float* b, const float* sub, int64_t sub_stride_n, const float* scale,
                        float* out_scaled, float* r, int n, int c, int64_t hw, void* stream);
 

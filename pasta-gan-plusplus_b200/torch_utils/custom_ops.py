@@ -87,6 +87,8 @@ def load_library():
     lib.pgpp_pack_weights.argtypes = [vp, i32, c_i64x4, c_i64x4, i32, i32, f32, i32, i32, vp, i32, vp, vp, i32, i32, i32, i32, i32, vp]
     lib.pgpp_up2_weight_adjoint.restype = i32
     lib.pgpp_up2_weight_adjoint.argtypes = [vp, vp, i32, i32, i32, i32, vp, vp]
+    lib.pgpp_sum_hw.restype = i32
+    lib.pgpp_sum_hw.argtypes = [vp, i32, vp, i32, i32, i64, vp]
     lib.pgpp_mul_reduce_hw.restype = i32
     lib.pgpp_mul_reduce_hw.argtypes = [vp, vp, vp, i64, vp, vp, vp, i32, i32, i64, vp]
     lib.pgpp_modulate_weights.restype = i32
@@ -128,7 +130,7 @@ def load_library():
 
 EXPORTED_SYMBOLS = ('pgpp_version', 'pgpp_last_error', 'pgpp_launch_count', 'pgpp_refresh_env', 'pgpp_bias_act', 'pgpp_upfirdn2d',
                     'pgpp_modconv_demod_coefs', 'pgpp_pack_activations', 'pgpp_pack_activations_slice', 'pgpp_pack_activations_f16',
-                    'pgpp_pack_weights', 'pgpp_up2_weight_adjoint', 'pgpp_mul_reduce_hw', 'pgpp_modulate_weights',
+                    'pgpp_pack_weights', 'pgpp_up2_weight_adjoint', 'pgpp_mul_reduce_hw', 'pgpp_sum_hw', 'pgpp_modulate_weights',
                     'pgpp_spade_modulate_pack', 'pgpp_mix_pack', 'pgpp_conv2d_direct', 'pgpp_fir_pack', 'pgpp_fir_packed', 'pgpp_conv1x1_thin', 'pgpp_pack_im2col', 'pgpp_conv2d_igemm', 'pgpp_conv2d_igemm_stats_rows', 'pgpp_instnorm_finalize', 'pgpp_conv2d_wgrad', 'pgpp_u8_to_f32',
                     'pgpp_image_to_u8', 'pgpp_grid_sample_2d', 'pgpp_grid_sample_2d_backward')
 
@@ -324,6 +326,16 @@ class _ConvPlugin:
                                          _ptr(out), _ptr(master), int(parts), int(bool(f16)), int(out.shape[2]), int(o_off), int(out.shape[3]),
                                          _stream(w)))
         return out
+
+    @staticmethod
+    def sum_hw(a):
+        """a [N, C, H, W] contiguous float32 / float16 / bfloat16 -> float32 [N, C] plane sums; see pgpp_sum_hw"""
+        lib = load_library()
+        n, c, h, w = a.shape
+        r = torch.empty([n, c], dtype=torch.float32, device=a.device)
+        with torch.cuda.device(a.device):
+            _check(lib.pgpp_sum_hw(_ptr(a), dtype_code(a.dtype), _ptr(r), n, c, h * w, _stream(a)))
+        return r
 
     @staticmethod
     def mul_reduce_hw(a, b=None, sub=None, scale=None, out_scaled=False, reduce=True):

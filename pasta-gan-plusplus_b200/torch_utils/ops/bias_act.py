@@ -111,6 +111,14 @@ def _bias_act_cuda(dim=1, act='linear', alpha=None, gain=None, clamp=None):
     keep_y = 'y' in spec.ref or (act == 'linear' and clamp >= 0)
     other_dims = lambda t: [i for i in range(t.ndim) if i != dim]
 
+    def bias_grad(t):
+        """t.sum(over every dimension but `dim`) (bias_act.py:135,156); for NCHW-contiguous CUDA images one pass of pgpp_sum_hw
+        (float32 accumulation) + a [N, C] column sum instead of the library's generic reduction"""
+        if (t.is_cuda and t.ndim == 4 and dim == 1 and t.dtype in (torch.float32, torch.float16, torch.bfloat16) and t.is_contiguous()
+                and t.shape[2] * t.shape[3] >= 1024 and not (torch.is_grad_enabled() and t.requires_grad)):
+            return custom_ops.get_plugin('conv2d_plugin').sum_hw(t).sum(0).to(t.dtype)
+        return t.sum(other_dims(t))
+
     class BiasActCuda(torch.autograd.Function):
         @staticmethod
         def forward(ctx, x, b):
@@ -132,7 +140,7 @@ def _bias_act_cuda(dim=1, act='linear', alpha=None, gain=None, clamp=None):
             if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
                 dx = dy if is_identity else BiasActCudaGrad.apply(dy, x, b, y)
             if ctx.needs_input_grad[1]:
-                db = dx.sum(other_dims(dx))
+                db = bias_grad(dx)
             return dx, db
 
     class BiasActCudaGrad(torch.autograd.Function):
@@ -153,7 +161,7 @@ def _bias_act_cuda(dim=1, act='linear', alpha=None, gain=None, clamp=None):
             if spec.has_2nd_grad and (ctx.needs_input_grad[1] or ctx.needs_input_grad[2]):
                 d_x = _plugin.bias_act(d_dx, b, x, y, dy, 2, dim, idx, alpha, gain, clamp)
             if spec.has_2nd_grad and ctx.needs_input_grad[2]:
-                d_b = d_x.sum(other_dims(d_x))
+                d_b = bias_grad(d_x)
             return d_dy, d_x, d_b, None
 
     _bias_act_cuda_cache[key] = BiasActCuda

@@ -738,7 +738,11 @@ def _conv2d_gradfix(transpose, weight_shape, stride, padding, output_padding, di
                         grad_weight = grad_weight.to(weight.dtype)
                     assert grad_weight.shape == weight_shape
             if ctx.needs_input_grad[2]:
-                grad_bias = grad_output.sum([0, 2, 3])
+                if (grad_output.is_contiguous() and grad_output.dtype in (torch.float32, torch.float16, torch.bfloat16) and
+                        grad_output.shape[2] * grad_output.shape[3] >= 1024 and not (torch.is_grad_enabled() and grad_output.requires_grad)):
+                    grad_bias = _plugin.sum_hw(grad_output).sum(0).to(grad_output.dtype)
+                else:
+                    grad_bias = grad_output.sum([0, 2, 3])
             return grad_input, grad_weight, grad_bias
 
     class Conv2dGradWeight(torch.autograd.Function):

@@ -11,7 +11,7 @@ REQUIRED = ('metric', 'value', 'unit', 'n_gpus', 'steps', 'warmup', 'ms_per_step
 
 
 def test_committed_bench_line_has_the_contract_keys():
-    line = json.load(open(os.path.join(ROOT, 'profiles', 'r01_bench_v19.json')))
+    line = json.load(open(os.path.join(ROOT, 'profiles', 'r02_bench_v3.json')))
     assert all(k in line for k in REQUIRED), [k for k in REQUIRED if k not in line]
     assert line['metric'] == 'generator_512px_images_per_sec' and line['unit'] == 'images/s' and line['higher_is_better'] is True
     assert line['n_gpus'] == 1 and line['warmup'] >= 3 and line['scaling'] == 'weak' and line['vs_baseline'] is None
@@ -22,6 +22,9 @@ def test_committed_bench_line_has_the_contract_keys():
     e2e = line['e2e']
     assert e2e['h2d_bytes_per_step'] > 0 and e2e['d2h_bytes_per_step'] > 0 and e2e['value'] != line['value']
     assert line['gpu_launches'] > 0 and 'sm_mhz' in line['clocks'] and 'reasons' in line['clocks']
+    assert line['eager']['ms_per_step'] > 0 and 'launch' in line['config']          # graph replay is the timed entry; eager figure beside it
+    assert set(('modulated_conv2d', 'upfirdn2d', 'bias_act', 'conv2d_gradfix_train')) <= set(line['ops'])       # BASELINE configs[3]
+    assert line['train']['ms_per_step'] > 0 and line['train']['batch_per_gpu'] == 8                            # BASELINE configs[4]
 
 
 def test_reference_arm_prints_one_contract_line():
