@@ -24,6 +24,9 @@ struct FirPackedArgs {
     int n, h, w, oh, ow, cg;
     int fw, fh, padx0, pady0;
     float k[16];            // k[jy * 4 + jx]: flipped, gain folded in, zero beyond (fh, fw)
+    // optional epilogue (pgpp_fir_packed_act, tiled kernel only): v = clamp(act(v + noise[n?, oy, ox] + bias[c]) * act_gain)
+    const float* noise; long long noise_stride_n; const float* bias;
+    int act; float alpha, act_gain, clamp;
 };
 
 template <int D, int R>
@@ -154,7 +157,7 @@ __device__ __forceinline__ void fir_tile_store(float* dst, const uint4 (&u)[PART
     *reinterpret_cast<ulonglong2*>(dst + 32) = make_ulonglong2(v[2], v[3]);     // half 1: channels 4..7, 32 floats further
 }
 
-template <int PARTS>
+template <int PARTS, bool EPI = false>
 __global__ void __launch_bounds__(FT_THREADS, 4) fir_tile_packed_kernel(const FirTileArgs t, long long total_tiles) {
     extern __shared__ __align__(16) float sm[];
     const FirPackedArgs& p = t.a;
@@ -242,6 +245,9 @@ __global__ void __launch_bounds__(FT_THREADS, 4) fir_tile_packed_kernel(const Fi
         }
         const int ox = ox0 + px;
         if (cg < cgs && ox < p.ow) {
+            float bias8[8];
+            #pragma unroll
+            for (int j = 0; j < 8; j++) bias8[j] = (EPI && p.bias) ? __ldg(p.bias + cb * 64 + cg * 8 + j) : 0.f;
             __nv_bfloat16* const out_n = p.out + ((long long)n * p.oh * p.ow) * p.out_ct + cb * 64 + cg * 8;
             #pragma unroll
             for (int rr = 0; rr < FT_H; rr++) {
@@ -251,6 +257,18 @@ __global__ void __launch_bounds__(FT_THREADS, 4) fir_tile_packed_kernel(const Fi
                 float v[8];
                 #pragma unroll
                 for (int j = 0; j < 4; j++) { v[2 * j] = __uint_as_float((unsigned)acc[rr][j]); v[2 * j + 1] = __uint_as_float((unsigned)(acc[rr][j] >> 32)); }
+                if (EPI) {
+                    const float nz = p.noise ? __ldg(p.noise + n * p.noise_stride_n + (long long)oy * p.ow + ox) : 0.f;
+                    #pragma unroll
+                    for (int j = 0; j < 8; j++) {
+                        float r = v[j] + nz + bias8[j];
+                        if (p.act == PGPP_ACT_RELU) r = fmaxf(r, 0.f);
+                        else if (p.act == PGPP_ACT_LRELU) r = r > 0.f ? r : r * p.alpha;
+                        r *= p.act_gain;
+                        if (p.clamp >= 0.f) r = fminf(fmaxf(r, -p.clamp), p.clamp);
+                        v[j] = r;
+                    }
+                }
                 for (int part = 0; part < p.out_parts; part++) {
                     const bool more = part + 1 < p.out_parts;
                     uint32_t w4[4];
@@ -285,9 +303,34 @@ __global__ void __launch_bounds__(256) copy_packed_kernel(const FirPackedArgs p,
 
 } // namespace pgpp
 
+namespace pgpp {
+struct FirEpilogue { const float* noise; long long noise_stride_n; const float* bias; int act; float alpha, gain, clamp; };
+static int fir_packed_launch(const void* in, int in_parts, int64_t in_part_stride, int n, int h, int w, int c, int in_c_total,
+                             const float* f_host, int fw, int fh, int down, int padx0, int padx1, int pady0, int pady1, int flip, float gain,
+                             void* out, int out_parts, int64_t out_part_stride, int out_c_total, const FirEpilogue* epi, void* stream);
+}
+
 extern "C" int pgpp_fir_packed(const void* in, int in_parts, int64_t in_part_stride, int n, int h, int w, int c, int in_c_total,
                                const float* f_host, int fw, int fh, int down, int padx0, int padx1, int pady0, int pady1, int flip, float gain,
                                void* out, int out_parts, int64_t out_part_stride, int out_c_total, void* stream) {
+    return pgpp::fir_packed_launch(in, in_parts, in_part_stride, n, h, w, c, in_c_total, f_host, fw, fh, down, padx0, padx1, pady0, pady1, flip, gain,
+                                   out, out_parts, out_part_stride, out_c_total, nullptr, stream);
+}
+
+extern "C" int pgpp_fir_packed_act(const void* in, int in_parts, int64_t in_part_stride, int n, int h, int w, int c, int in_c_total,
+                                   const float* f_host, int fw, int fh, int padx0, int padx1, int pady0, int pady1, int flip, float gain,
+                                   const float* noise, int64_t noise_stride_n, const float* bias, int act_fn, float alpha, float act_gain, float clamp,
+                                   void* out, int out_parts, int64_t out_part_stride, int out_c_total, void* stream) {
+    using namespace pgpp;
+    PGPP_REQUIRE(act_fn == PGPP_ACT_LINEAR || act_fn == PGPP_ACT_RELU || act_fn == PGPP_ACT_LRELU, "fir_packed_act: linear, relu or lrelu");
+    const FirEpilogue epi{noise, noise_stride_n, bias, act_fn, alpha, act_gain, clamp};
+    return fir_packed_launch(in, in_parts, in_part_stride, n, h, w, c, in_c_total, f_host, fw, fh, 1, padx0, padx1, pady0, pady1, flip, gain,
+                             out, out_parts, out_part_stride, out_c_total, &epi, stream);
+}
+
+static int pgpp::fir_packed_launch(const void* in, int in_parts, int64_t in_part_stride, int n, int h, int w, int c, int in_c_total,
+                                   const float* f_host, int fw, int fh, int down, int padx0, int padx1, int pady0, int pady1, int flip, float gain,
+                                   void* out, int out_parts, int64_t out_part_stride, int out_c_total, const FirEpilogue* epi, void* stream) {
     using namespace pgpp;
     PGPP_REQUIRE(in && out, "in and out must be device pointers");
     PGPP_REQUIRE(n >= 1 && h >= 1 && w >= 1 && c >= 8 && c % 8 == 0, "fir_packed: empty tensor or channel count not a multiple of 8");
@@ -304,13 +347,15 @@ extern "C" int pgpp_fir_packed(const void* in, int in_parts, int64_t in_part_str
     a.out = (__nv_bfloat16*)out; a.out_part_stride = out_part_stride; a.out_parts = out_parts; a.out_ct = out_c_total;
     a.n = n; a.h = h; a.w = w; a.oh = oh; a.ow = ow; a.cg = c / 8;
     a.fw = fw; a.fh = fh; a.padx0 = padx0; a.pady0 = pady0;
+    a.noise = epi ? epi->noise : nullptr; a.noise_stride_n = epi ? epi->noise_stride_n : 0; a.bias = epi ? epi->bias : nullptr;
+    a.act = epi ? epi->act : PGPP_ACT_LINEAR; a.alpha = epi ? epi->alpha : 0.f; a.act_gain = epi ? epi->gain : 1.f; a.clamp = epi ? epi->clamp : -1.f;
     for (int i = 0; i < 16; i++) a.k[i] = 0.f;
     for (int jy = 0; jy < fh; jy++)
         for (int jx = 0; jx < fw; jx++) {
             const int sy = flip ? jy : fh - 1 - jy, sx = flip ? jx : fw - 1 - jx;
             a.k[jy * 4 + jx] = (f_host ? f_host[sy * fw + sx] : 1.f) * gain;
         }
-    if (down == 1 && fw * fh == 1 && a.k[0] == 1.f && padx0 == 0 && pady0 == 0 && in_parts == out_parts) {
+    if (!epi && down == 1 && fw * fh == 1 && a.k[0] == 1.f && padx0 == 0 && pady0 == 0 && in_parts == out_parts) {
         const long long pixels = (long long)n * h * w, total_v = pixels * a.cg;
         long long blocks = (total_v + 255) / 256;
         const long long cap = (long long)sm_count() * 16;
@@ -320,7 +365,7 @@ extern "C" int pgpp_fir_packed(const void* in, int in_parts, int64_t in_part_str
         PGPP_CUDA_OK(cudaGetLastError());
         return PGPP_OK;
     }
-    if (down == 1 && !env_flags().fir_packed_no_tile) {
+    if (down == 1 && (epi || !env_flags().fir_packed_no_tile)) {
         // separable?  f = outer(ky, kx) with the pivot at the largest tap
         int pj = 0;
         for (int i = 1; i < 16; i++) if (fabsf(a.k[i]) > fabsf(a.k[pj])) pj = i;
@@ -344,12 +389,20 @@ extern "C" int pgpp_fir_packed(const void* in, int in_parts, int64_t in_part_str
                 PGPP_CUDA_OK(cudaFuncSetAttribute(fir_tile_packed_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FT_SMEM));
                 PGPP_CUDA_OK(cudaFuncSetAttribute(fir_tile_packed_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, FT_SMEM));
                 PGPP_CUDA_OK(cudaFuncSetAttribute(fir_tile_packed_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, FT_SMEM));
+                PGPP_CUDA_OK(cudaFuncSetAttribute(fir_tile_packed_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FT_SMEM));
+                PGPP_CUDA_OK(cudaFuncSetAttribute(fir_tile_packed_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FT_SMEM));
+                PGPP_CUDA_OK(cudaFuncSetAttribute(fir_tile_packed_kernel<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FT_SMEM));
                 if (dev >= 0 && dev < 64) attr_done[dev].store(true, std::memory_order_release);
             }
             long long blocks = tiles;
             const long long cap = (long long)sm_count() * 4;
             if (blocks > cap) blocks = cap;
-            if (in_parts == 1) fir_tile_packed_kernel<1><<<(unsigned)blocks, FT_THREADS, FT_SMEM, (cudaStream_t)stream>>>(ta, tiles);
+            if (epi) {
+                if (in_parts == 1) fir_tile_packed_kernel<1, true><<<(unsigned)blocks, FT_THREADS, FT_SMEM, (cudaStream_t)stream>>>(ta, tiles);
+                else if (in_parts == 2) fir_tile_packed_kernel<2, true><<<(unsigned)blocks, FT_THREADS, FT_SMEM, (cudaStream_t)stream>>>(ta, tiles);
+                else fir_tile_packed_kernel<3, true><<<(unsigned)blocks, FT_THREADS, FT_SMEM, (cudaStream_t)stream>>>(ta, tiles);
+            }
+            else if (in_parts == 1) fir_tile_packed_kernel<1><<<(unsigned)blocks, FT_THREADS, FT_SMEM, (cudaStream_t)stream>>>(ta, tiles);
             else if (in_parts == 2) fir_tile_packed_kernel<2><<<(unsigned)blocks, FT_THREADS, FT_SMEM, (cudaStream_t)stream>>>(ta, tiles);
             else fir_tile_packed_kernel<3><<<(unsigned)blocks, FT_THREADS, FT_SMEM, (cudaStream_t)stream>>>(ta, tiles);
             count_launch();
@@ -357,6 +410,7 @@ extern "C" int pgpp_fir_packed(const void* in, int in_parts, int64_t in_part_str
             return PGPP_OK;
         }
     }
+    PGPP_REQUIRE(!epi, "fir_packed_act needs a separable filter (outer product of two 1-D tap lists)");
     const int R = down == 1 ? 8 : 4;
     const int strips = (oh + R - 1) / R;
     const long long total = (long long)n * strips * ow * a.cg;

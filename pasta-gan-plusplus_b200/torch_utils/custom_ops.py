@@ -104,6 +104,9 @@ def load_library():
     lib.pgpp_fir_packed.restype = i32
     lib.pgpp_fir_packed.argtypes = [vp, i32, i64, i32, i32, i32, i32, i32, ctypes.POINTER(ctypes.c_float), i32, i32, i32, i32, i32, i32, i32, i32, f32,
                                     vp, i32, i64, i32, vp]
+    lib.pgpp_fir_packed_act.restype = i32
+    lib.pgpp_fir_packed_act.argtypes = [vp, i32, i64, i32, i32, i32, i32, i32, ctypes.POINTER(ctypes.c_float), i32, i32, i32, i32, i32, i32, i32, f32,
+                                        vp, i64, vp, i32, f32, f32, f32, vp, i32, i64, i32, vp]
     lib.pgpp_conv1x1_thin.restype = i32
     lib.pgpp_conv1x1_thin.argtypes = [vp, i32, i64, i32, i32, i32, i64, vp, vp, i32, vp, i32, vp, vp, i32, vp, vp, i32, f32, f32, f32, vp]
     lib.pgpp_conv2d_direct.restype = i32
@@ -131,7 +134,7 @@ def load_library():
 EXPORTED_SYMBOLS = ('pgpp_version', 'pgpp_last_error', 'pgpp_launch_count', 'pgpp_refresh_env', 'pgpp_bias_act', 'pgpp_upfirdn2d',
                     'pgpp_modconv_demod_coefs', 'pgpp_pack_activations', 'pgpp_pack_activations_slice', 'pgpp_pack_activations_f16',
                     'pgpp_pack_weights', 'pgpp_up2_weight_adjoint', 'pgpp_mul_reduce_hw', 'pgpp_sum_hw', 'pgpp_modulate_weights',
-                    'pgpp_spade_modulate_pack', 'pgpp_mix_pack', 'pgpp_conv2d_direct', 'pgpp_fir_pack', 'pgpp_fir_packed', 'pgpp_conv1x1_thin', 'pgpp_pack_im2col', 'pgpp_conv2d_igemm', 'pgpp_conv2d_igemm_stats_rows', 'pgpp_instnorm_finalize', 'pgpp_conv2d_wgrad', 'pgpp_u8_to_f32',
+                    'pgpp_spade_modulate_pack', 'pgpp_mix_pack', 'pgpp_conv2d_direct', 'pgpp_fir_pack', 'pgpp_fir_packed', 'pgpp_fir_packed_act', 'pgpp_conv1x1_thin', 'pgpp_pack_im2col', 'pgpp_conv2d_igemm', 'pgpp_conv2d_igemm_stats_rows', 'pgpp_instnorm_finalize', 'pgpp_conv2d_wgrad', 'pgpp_u8_to_f32',
                     'pgpp_image_to_u8', 'pgpp_grid_sample_2d', 'pgpp_grid_sample_2d_backward')
 
 
@@ -517,6 +520,31 @@ class _ConvPlugin:
             _check(lib.pgpp_fir_packed(src.data_ptr() + 2 * c_off, int(sp), int(src[0].numel()), n, h, w, int(c), int(ct), f, int(fw), int(fh), int(down),
                                        int(padx0), int(padx1), int(pady0), int(pady1), int(bool(flip)), float(gain),
                                        dst.data_ptr() + 2 * dst_c_off, int(dst.shape[0]), int(dst[0].numel()), int(dst.shape[4]), _stream(src)))
+        return dst
+
+    @staticmethod
+    def fir_packed_act(src, c, c_off, taps, fw, fh, padx0, padx1, pady0, pady1, flip, gain, noise, bias, act_idx, alpha, act_gain, clamp, dst, dst_c_off=0):
+        """fir_packed (down = 1, separable filter) followed by clamp(act(v + noise + bias) * act_gain), written into channels
+        [dst_c_off, dst_c_off + c) of `dst`; noise float32 [oh, ow] or [N, oh, ow] or None, bias float32 [c] or None; see pgpp_fir_packed_act"""
+        lib = load_library()
+        _torch_check(src.is_cuda and src.dtype == torch.bfloat16 and src.dim() == 5 and src.is_contiguous(), 'fir_packed_act: src must be a contiguous bf16 [parts,N,H,W,C] tensor')
+        sp, n, h, w, ct = src.shape
+        oh, ow = h + pady0 + pady1 - fh + 1, w + padx0 + padx1 - fw + 1
+        _torch_check(dst.dtype == torch.bfloat16 and dst.is_contiguous() and tuple(dst.shape[1:4]) == (n, oh, ow), 'fir_packed_act: dst has the wrong shape')
+        nz_stride = 0
+        if noise is not None:
+            noise = noise.detach().to(torch.float32).contiguous()
+            _torch_check(noise.numel() in (oh * ow, n * oh * ow), 'fir_packed_act: noise must be [oh, ow] or [N, oh, ow]')
+            nz_stride = oh * ow if (noise.numel() == n * oh * ow and n > 1) else 0
+        if bias is not None:
+            bias = bias.detach().to(torch.float32).contiguous()
+            _torch_check(bias.numel() == c, 'fir_packed_act: bias must have c elements')
+        f = (ctypes.c_float * (fw * fh))(*[float(t) for t in taps])
+        with torch.cuda.device(src.device):
+            _check(lib.pgpp_fir_packed_act(src.data_ptr() + 2 * c_off, int(sp), int(src[0].numel()), n, h, w, int(c), int(ct), f, int(fw), int(fh),
+                                           int(padx0), int(padx1), int(pady0), int(pady1), int(bool(flip)), float(gain),
+                                           _ptr(noise), int(nz_stride), _ptr(bias), int(act_idx), float(alpha), float(act_gain), float(clamp),
+                                           dst.data_ptr() + 2 * dst_c_off, int(dst.shape[0]), int(dst[0].numel()), int(dst.shape[4]), _stream(src)))
         return dst
 
     @staticmethod

@@ -307,6 +307,45 @@ def packed_plain(weight, flip_weight, parts, pad_y, pad_x, transpose_io=False, s
     return _cached(weight, ('plain', bool(flip_weight), parts, pad_y, pad_x, bool(transpose_io), float(scale), bool(allow_im2col), bool(f16)), build)
 
 
+_UP2_TAPS = ((2, 0), (1,))      # phase r of a stride-2 transposed 3-tap convolution: T[2j + r] = sum_t x[j + t - pad_r] * w[_UP2_TAPS[r][t]], pad_0 = 1, pad_1 = 0
+
+
+def packed_up2_phase(weight, ry, rx, flip_weight, parts):
+    """Phase (ry, rx) of `conv_transpose2d(x, w', stride=2)` for a 3 x 3 kernel as a correlation over the INPUT grid (w' = the kernel as
+    conv_transpose2d sees it, conv2d_resample.py:131-132):  T[2j + ry, 2i + rx] = sum_{ty, tx} x[j + ty - (1 - ry), i + tx - (1 - rx)] * w'[KY[ty], KX[tx]]
+    with KY = (2, 0) for ry = 0 and (1,) for ry = 1: 2 x 2, 2 x 1, 1 x 2 and 1 x 1 taps - the nine taps of the kernel, each used once."""
+    def build():
+        assert tuple(weight.shape[2:]) == (3, 3)
+        w = weight.detach()
+        if flip_weight:
+            w = w.flip([2, 3])
+        ky = torch.tensor(_UP2_TAPS[ry], device=w.device)
+        kx = torch.tensor(_UP2_TAPS[rx], device=w.device)
+        sub = w.index_select(2, ky).index_select(3, kx).contiguous()
+        return pack_weights_native(sub, len(_UP2_TAPS[ry]), len(_UP2_TAPS[rx]), parts, 1 - ry, 1 - rx)
+    return _cached(weight, ('up2_phase', ry, rx, bool(flip_weight), parts), build)
+
+
+def up2_modconv_packed(xp, weight, styles, dcoef, f, flip_weight, out_packed, *, noise=None, bias=None, act='linear', alpha=0.0, gain=1.0, clamp=-1.0):
+    """The StyleGAN2 up = 2 modulated layer at the algorithmic MAC count, operand format in and out: the transposed convolution as four
+    per-phase implicit GEMMs (demodulation in their epilogue) writing the (2H + 1) x (2W + 1) intermediate in the operand format, then ONE
+    pass `pgpp_fir_packed_act` = 4 x 4 blur (gain 4) + noise + bias + activation + clamp into `out_packed`.  Against the polyphase form
+    (`packed_up2`, one launch at 4x the MACs) this wins on the tensor-bound layers (C >= 128)."""
+    _init()
+    n, _, h, w = xp.shape
+    parts = xp.data.shape[0]
+    o = weight.shape[0]
+    t = PackedAct(PackedAct.empty(n, 2 * h + 1, 2 * w + 1, o, parts, xp.device), o)
+    for ry in (0, 1):
+        for rx in (0, 1):
+            pw = packed_up2_phase(weight, ry, rx, flip_weight, parts)
+            igemm_conv(xp, pw, scale=styles, dcoef=dcoef, out_hw=(h + 1 - ry, w + 1 - rx), out_packed=t, out_phase=(ry, rx))
+    taps, fw, fh = host_filter(f)
+    _plugin.fir_packed_act(t.data, o, 0, taps, fw, fh, 1, 1, 1, 1, False, 4.0, noise, bias, _ACT_IDX[act], alpha, gain, clamp,
+                           out_packed.data, dst_c_off=out_packed.c_off)
+    return out_packed
+
+
 def packed_up2(weight, f, flip_weight, flip_filter, parts):
     """Polyphase form of `conv_transpose2d(stride=2)` followed by the 4x4 FIR with gain 4
     (conv2d_resample.py:125-139, the StyleGAN2 up=2 layer): for output pixel (2y+py, 2x+px)
@@ -361,7 +400,7 @@ def fir_packed(xp, f, down=1, padding=(0, 0, 0, 0), flip_filter=False, gain=1.0,
 
 def igemm_conv(x, pw, *, scale=None, stride=1, out_hw=None, dcoef=None, noise=None, bias=None, act='linear',
                alpha=0.0, gain=1.0, clamp=-1.0, out=None, out_dtype=None, accumulate=False, precision=None,
-               memory_format=None, out_packed=None, spade=None, instnorm_eps=None):
+               memory_format=None, out_packed=None, spade=None, instnorm_eps=None, out_phase=None):
     """Run one fused convolution.
     x          [N, I, H, W] tensor (any float dtype / layout; packed here, `scale` [N, I] = style modulation folded into the
                packing pass) or a PackedAct (no packing pass; `scale` is then folded into per-sample weights).
@@ -369,6 +408,8 @@ def igemm_conv(x, pw, *, scale=None, stride=1, out_hw=None, dcoef=None, noise=No
                PackedAct view -> the epilogue writes the bf16 operand format of the next conv into that channel slice.
     spade      (x_norm [N, C, H, W] float32, mean [N, C], rstd [N, C], pre_gain): the GEMM's O = 2C columns are gamma | beta and the
                epilogue writes pre_act((x_norm - mean) * rstd * (1 + gamma) + beta) into `out_packed` (C channels).
+    out_phase  (ry, rx) with `out_packed` a PackedAct over a (2 * conv_h' + 1) x (2 * conv_w' + 1) grid: the result pixel (j, i) is written to
+               (2 j + ry, 2 i + rx) of it - one phase of a stride-2 transposed convolution (conv2d_resample.py:125-139) at 1x its MACs.
     instnorm_eps  not None -> returns (y, mean [N, O], rstd [N, O]): the instance-norm statistics of the float32 NCHW result
                (torch.var_mean(y, (2, 3), unbiased=False), rstd = rsqrt(var + eps)), from partial sums the epilogue leaves per warp and a
                small float64 merge kernel - no second pass over y.  Launches that cannot produce them fall back to torch.var_mean."""
@@ -420,7 +461,19 @@ def igemm_conv(x, pw, *, scale=None, stride=1, out_hw=None, dcoef=None, noise=No
     else:
         conv_h, conv_w = out_hw
     out_h, out_w = conv_h * up, conv_w * up
-    if out_packed is not None:
+    if out_packed is not None and out_phase is not None:
+        ry, rx = out_phase
+        th_, tw_ = int(out_packed.data.shape[2]), int(out_packed.data.shape[3])
+        assert out_packed.data.shape[1] == n and 2 * (out_h - 1) + ry < th_ and 2 * (out_w - 1) + rx < tw_ and out_packed.c == pw.o
+        assert pw.o % 16 == 0 and out_packed.c_off % 8 == 0 and up == 1 and spade is None
+        c_total = out_packed.data.shape[4]
+        d.out = out_packed.data.data_ptr() + 2 * (out_packed.c_off + (ry * tw_ + rx) * c_total)
+        d.out_dtype = custom_ops.dtype_code(torch.bfloat16)
+        d.out_stride = (ctypes.c_int64 * 4)(th_ * tw_ * c_total, 1, 2 * tw_ * c_total, 2 * c_total)
+        d.out_parts = out_packed.data.shape[0]
+        d.out_part_stride = out_packed.data[0].numel()
+        result = out_packed
+    elif out_packed is not None:
         assert tuple(out_packed.data.shape[1:4]) == (n, out_h, out_w) and out_packed.c == (pw.o // 2 if spade is not None else pw.o)
         assert pw.o % 16 == 0 and out_packed.c_off % 8 == 0
         c_total = out_packed.data.shape[4]

@@ -143,3 +143,54 @@ def test_mix_pack_matches_the_masked_feature_composition(shape, terms):
         got = data.float().sum(0).permute(0, 3, 1, 2).cpu()
         assert torch.all(got[:, c:] == 0)
         assert (got[:, :c] - want).abs().max().item() <= tol * want.abs().max().item(), (parts, (got[:, :c] - want).abs().max().item())
+
+
+@pytest.mark.parametrize('prec,tol', [('bf16x2', 8e-5), ('bf16x3', 5e-5), ('bf16', 2e-2)])
+@pytest.mark.parametrize('n,ic,oc,h,w,noise_kind', [(2, 64, 64, 16, 16, 'const'), (3, 128, 32, 9, 20, 'per_sample'), (1, 64, 48, 32, 8, None)], ids=str)
+def test_up2_layer_as_phase_gemms_plus_blur_pass(n, ic, oc, h, w, noise_kind, prec, tol):
+    """The up = 2 synthesis layer on operand-format tensors: transposed convolution at 1x its MACs as four per-phase implicit GEMMs
+    (conv2d_resample.py:125-139) + pgpp_fir_packed_act (blur, noise, bias, lrelu, gain, clamp) - against the CPU oracle's
+    `synthesis_layer(up=2)` and against the one-launch polyphase form it replaces."""
+    nets = importlib.import_module('pgpp_b200.training.networks')
+    upf = importlib.import_module('pgpp_b200.torch_utils.ops.upfirdn2d')
+    from oracle import ref_ops
+    old, old_flag, old_min = cg.fp32_precision, nets.UP2_PHASES, nets.UP2_PHASES_MIN_IO
+    cg.fp32_precision = prec
+    nets.UP2_PHASES_MIN_IO = 0
+    try:
+        cg._init()
+        g = torch.Generator().manual_seed(43)
+        x = torch.randn(n, ic, h, w, generator=g); wt = torch.randn(oc, ic, 3, 3, generator=g)
+        s = torch.rand(n, ic, generator=g) + 0.5; b = torch.randn(oc, generator=g)
+        f = upf.setup_filter([1, 3, 3, 1])
+        noise = None
+        if noise_kind == 'const':
+            noise = torch.randn(2 * h, 2 * w, generator=g) * 0.3
+        elif noise_kind == 'per_sample':
+            noise = torch.randn(n, 1, 2 * h, 2 * w, generator=g) * 0.3
+        want = ref_ops.synthesis_layer(x, s, wt, b, noise, 2, f)
+        parts = cg._PRODUCTS[prec][1]
+        xp = cg.PackedAct(cg._plugin.pack_activations(x.to(DEV), None, -(-ic // 64) * 64, parts), ic)
+        outs = {}
+        for flag in (True, False):
+            nets.UP2_PHASES = flag
+            out = cg.PackedAct(torch.zeros(parts, n, 2 * h, 2 * w, 128, dtype=torch.bfloat16, device=DEV), oc, 64)      # a channel slice of a wider buffer
+            before = custom_ops.launch_count()
+            with torch.no_grad():
+                nets.modulated_conv2d_fused_act(xp, wt.to(DEV), s.to(DEV), noise=None if noise is None else noise.to(DEV), up=2, padding=1,
+                                                resample_filter=f.to(DEV), flip_weight=False, bias=b.to(DEV), act='lrelu', clamp=256.0, out_packed=out)
+            launches = custom_ops.launch_count() - before
+            assert launches >= (9 if flag else 2), (flag, launches)          # demod + 4 x (modulate weights + GEMM) + blur pass  vs  demod + modulate + GEMM
+            outs[flag] = out.to_nchw()
+            assert torch.all(out.data[..., :64] == 0) and torch.all(out.data[..., 64 + oc:] == 0)       # neighbours of the slice untouched
+            assert rel_l2(outs[flag], want) < tol, (prec, flag, rel_l2(outs[flag], want))
+        assert rel_l2(outs[True], outs[False]) < 2 * tol
+        # NCHW float32 input: packed once with the style scale folded in, phase GEMMs on shared weights
+        nets.UP2_PHASES = True
+        out = cg.PackedAct(torch.zeros(parts, n, 2 * h, 2 * w, 128, dtype=torch.bfloat16, device=DEV), oc, 64)
+        with torch.no_grad():
+            nets.modulated_conv2d_fused_act(x.to(DEV), wt.to(DEV), s.to(DEV), noise=None if noise is None else noise.to(DEV), up=2, padding=1,
+                                            resample_filter=f.to(DEV), flip_weight=False, bias=b.to(DEV), act='lrelu', clamp=256.0, out_packed=out)
+        assert rel_l2(out.to_nchw(), want) < tol
+    finally:
+        cg.fp32_precision, nets.UP2_PHASES, nets.UP2_PHASES_MIN_IO = old, old_flag, old_min
