@@ -276,11 +276,12 @@ PGPP_API int pgpp_fir_packed(const void* in, int in_parts, int64_t in_part_strid
 /* The same FIR (down = 1, separable filter) followed by  v = clamp(act(v + noise[n?, y, x] + bias[c]) * act_gain):  the blur + noise + bias_act tail of
  * the StyleGAN2 up = 2 layer (conv2d_resample.py:125-139 transposed convolution -> upfirdn2d, then networks.py:1925-1935) when the transposed
  * convolution wrote its (2H + 1) x (2W + 1) result in the operand format.  noise float32 [oh, ow] (noise_stride_n = 0) or [N, oh, ow], or NULL;
- * bias float32 [c] or NULL; act_fn linear / relu / lrelu. */
+ * bias float32 [c] or NULL; act_fn linear / relu / lrelu.  The result goes EITHER to out (operand format) OR, with out == NULL, to out_nchw
+ * (float32 [N, c_out, oh, ow] contiguous, c_out <= c: the low-resolution blocks hand tensors over). */
 PGPP_API int pgpp_fir_packed_act(const void* in, int in_parts, int64_t in_part_stride, int n, int h, int w, int c, int in_c_total,
                     const float* f_host, int fw, int fh, int padx0, int padx1, int pady0, int pady1, int flip, float gain,
                     const float* noise, int64_t noise_stride_n, const float* bias, int act_fn, float alpha, float act_gain, float clamp,
-                    void* out, int out_parts, int64_t out_part_stride, int out_c_total, void* stream);
+                    void* out, int out_parts, int64_t out_part_stride, int out_c_total, float* out_nchw, int c_out, void* stream);
 
 /* ---- weight gradient (conv2d_gradfix.py:135-142, Conv2dGradWeight.forward: replaces
  * aten::cudnn_convolution_backward_weight / cudnn_convolution_transpose_backward_weight) ----

@@ -21,12 +21,13 @@ namespace pgpp {
 struct FirPackedArgs {
     const __nv_bfloat16* in; long long in_part_stride; int in_parts; int in_ct;
     __nv_bfloat16* out; long long out_part_stride; int out_parts; int out_ct;
-    int n, h, w, oh, ow, cg;
+    int n, h, w, oh, ow, cg, c_out;
     int fw, fh, padx0, pady0;
     float k[16];            // k[jy * 4 + jx]: flipped, gain folded in, zero beyond (fh, fw)
     // optional epilogue (pgpp_fir_packed_act, tiled kernel only): v = clamp(act(v + noise[n?, oy, ox] + bias[c]) * act_gain)
     const float* noise; long long noise_stride_n; const float* bias;
     int act; float alpha, act_gain, clamp;
+    float* out_nchw;        // pgpp_fir_packed_act: float32 [N, C, oh, ow] contiguous result instead of the operand format (out == NULL)
 };
 
 template <int D, int R>
@@ -269,6 +270,15 @@ __global__ void __launch_bounds__(FT_THREADS, 4) fir_tile_packed_kernel(const Fi
                         v[j] = r;
                     }
                 }
+                if (EPI && p.out_nchw) {
+                    // float32 NCHW result (the low-resolution blocks hand tensors over): 8 channel planes, one element each
+                    const int c0 = cb * 64 + cg * 8, c_real = p.cg * 8;
+                    float* o = p.out_nchw + (((long long)n * p.c_out + c0) * p.oh + oy) * p.ow + ox;
+                    #pragma unroll
+                    for (int j = 0; j < 8; j++)
+                        if (c0 + j < p.c_out && c0 + j < c_real) o[(long long)j * p.oh * p.ow] = v[j];
+                    continue;
+                }
                 for (int part = 0; part < p.out_parts; part++) {
                     const bool more = part + 1 < p.out_parts;
                     uint32_t w4[4];
@@ -304,7 +314,7 @@ __global__ void __launch_bounds__(256) copy_packed_kernel(const FirPackedArgs p,
 } // namespace pgpp
 
 namespace pgpp {
-struct FirEpilogue { const float* noise; long long noise_stride_n; const float* bias; int act; float alpha, gain, clamp; };
+struct FirEpilogue { const float* noise; long long noise_stride_n; const float* bias; int act; float alpha, gain, clamp; float* out_nchw; int c_out; };
 static int fir_packed_launch(const void* in, int in_parts, int64_t in_part_stride, int n, int h, int w, int c, int in_c_total,
                              const float* f_host, int fw, int fh, int down, int padx0, int padx1, int pady0, int pady1, int flip, float gain,
                              void* out, int out_parts, int64_t out_part_stride, int out_c_total, const FirEpilogue* epi, void* stream);
@@ -320,12 +330,14 @@ extern "C" int pgpp_fir_packed(const void* in, int in_parts, int64_t in_part_str
 extern "C" int pgpp_fir_packed_act(const void* in, int in_parts, int64_t in_part_stride, int n, int h, int w, int c, int in_c_total,
                                    const float* f_host, int fw, int fh, int padx0, int padx1, int pady0, int pady1, int flip, float gain,
                                    const float* noise, int64_t noise_stride_n, const float* bias, int act_fn, float alpha, float act_gain, float clamp,
-                                   void* out, int out_parts, int64_t out_part_stride, int out_c_total, void* stream) {
+                                   void* out, int out_parts, int64_t out_part_stride, int out_c_total, float* out_nchw, int c_out, void* stream) {
     using namespace pgpp;
     PGPP_REQUIRE(act_fn == PGPP_ACT_LINEAR || act_fn == PGPP_ACT_RELU || act_fn == PGPP_ACT_LRELU, "fir_packed_act: linear, relu or lrelu");
-    const FirEpilogue epi{noise, noise_stride_n, bias, act_fn, alpha, act_gain, clamp};
+    PGPP_REQUIRE((out != nullptr) != (out_nchw != nullptr), "fir_packed_act: exactly one of out (operand format) and out_nchw (float32 NCHW)");
+    PGPP_REQUIRE(!out_nchw || (c_out >= 1 && c_out <= c), "fir_packed_act: c_out must be in [1, c]");
+    const FirEpilogue epi{noise, noise_stride_n, bias, act_fn, alpha, act_gain, clamp, out_nchw, c_out};
     return fir_packed_launch(in, in_parts, in_part_stride, n, h, w, c, in_c_total, f_host, fw, fh, 1, padx0, padx1, pady0, pady1, flip, gain,
-                             out, out_parts, out_part_stride, out_c_total, &epi, stream);
+                             out ? out : (void*)in, out ? out_parts : in_parts, out ? out_part_stride : in_part_stride, out ? out_c_total : in_c_total, &epi, stream);
 }
 
 static int pgpp::fir_packed_launch(const void* in, int in_parts, int64_t in_part_stride, int n, int h, int w, int c, int in_c_total,
@@ -349,6 +361,7 @@ static int pgpp::fir_packed_launch(const void* in, int in_parts, int64_t in_part
     a.fw = fw; a.fh = fh; a.padx0 = padx0; a.pady0 = pady0;
     a.noise = epi ? epi->noise : nullptr; a.noise_stride_n = epi ? epi->noise_stride_n : 0; a.bias = epi ? epi->bias : nullptr;
     a.act = epi ? epi->act : PGPP_ACT_LINEAR; a.alpha = epi ? epi->alpha : 0.f; a.act_gain = epi ? epi->gain : 1.f; a.clamp = epi ? epi->clamp : -1.f;
+    a.out_nchw = epi ? epi->out_nchw : nullptr; a.c_out = epi ? epi->c_out : c;
     for (int i = 0; i < 16; i++) a.k[i] = 0.f;
     for (int jy = 0; jy < fh; jy++)
         for (int jx = 0; jx < fw; jx++) {

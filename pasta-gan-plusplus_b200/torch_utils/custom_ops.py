@@ -106,7 +106,7 @@ def load_library():
                                     vp, i32, i64, i32, vp]
     lib.pgpp_fir_packed_act.restype = i32
     lib.pgpp_fir_packed_act.argtypes = [vp, i32, i64, i32, i32, i32, i32, i32, ctypes.POINTER(ctypes.c_float), i32, i32, i32, i32, i32, i32, i32, f32,
-                                        vp, i64, vp, i32, f32, f32, f32, vp, i32, i64, i32, vp]
+                                        vp, i64, vp, i32, f32, f32, f32, vp, i32, i64, i32, vp, i32, vp]
     lib.pgpp_conv1x1_thin.restype = i32
     lib.pgpp_conv1x1_thin.argtypes = [vp, i32, i64, i32, i32, i32, i64, vp, vp, i32, vp, i32, vp, vp, i32, vp, vp, i32, f32, f32, f32, vp]
     lib.pgpp_conv2d_direct.restype = i32
@@ -523,14 +523,19 @@ class _ConvPlugin:
         return dst
 
     @staticmethod
-    def fir_packed_act(src, c, c_off, taps, fw, fh, padx0, padx1, pady0, pady1, flip, gain, noise, bias, act_idx, alpha, act_gain, clamp, dst, dst_c_off=0):
+    def fir_packed_act(src, c, c_off, taps, fw, fh, padx0, padx1, pady0, pady1, flip, gain, noise, bias, act_idx, alpha, act_gain, clamp, dst, dst_c_off=0,
+                       dst_nchw=None):
         """fir_packed (down = 1, separable filter) followed by clamp(act(v + noise + bias) * act_gain), written into channels
         [dst_c_off, dst_c_off + c) of `dst`; noise float32 [oh, ow] or [N, oh, ow] or None, bias float32 [c] or None; see pgpp_fir_packed_act"""
         lib = load_library()
         _torch_check(src.is_cuda and src.dtype == torch.bfloat16 and src.dim() == 5 and src.is_contiguous(), 'fir_packed_act: src must be a contiguous bf16 [parts,N,H,W,C] tensor')
         sp, n, h, w, ct = src.shape
         oh, ow = h + pady0 + pady1 - fh + 1, w + padx0 + padx1 - fw + 1
-        _torch_check(dst.dtype == torch.bfloat16 and dst.is_contiguous() and tuple(dst.shape[1:4]) == (n, oh, ow), 'fir_packed_act: dst has the wrong shape')
+        if dst_nchw is not None:
+            _torch_check(dst is None and dst_nchw.dtype == torch.float32 and dst_nchw.is_contiguous() and tuple(dst_nchw.shape) == (n, c, oh, ow),
+                         'fir_packed_act: dst_nchw must be a contiguous float32 [N, c, oh, ow] tensor')
+        else:
+            _torch_check(dst.dtype == torch.bfloat16 and dst.is_contiguous() and tuple(dst.shape[1:4]) == (n, oh, ow), 'fir_packed_act: dst has the wrong shape')
         nz_stride = 0
         if noise is not None:
             noise = noise.detach().to(torch.float32).contiguous()
@@ -544,8 +549,10 @@ class _ConvPlugin:
             _check(lib.pgpp_fir_packed_act(src.data_ptr() + 2 * c_off, int(sp), int(src[0].numel()), n, h, w, int(c), int(ct), f, int(fw), int(fh),
                                            int(padx0), int(padx1), int(pady0), int(pady1), int(bool(flip)), float(gain),
                                            _ptr(noise), int(nz_stride), _ptr(bias), int(act_idx), float(alpha), float(act_gain), float(clamp),
-                                           dst.data_ptr() + 2 * dst_c_off, int(dst.shape[0]), int(dst[0].numel()), int(dst.shape[4]), _stream(src)))
-        return dst
+                                           None if dst is None else dst.data_ptr() + 2 * dst_c_off, 0 if dst is None else int(dst.shape[0]),
+                                           0 if dst is None else int(dst[0].numel()), 0 if dst is None else int(dst.shape[4]),
+                                           _ptr(dst_nchw), int(c), _stream(src)))
+        return dst if dst is not None else dst_nchw
 
     @staticmethod
     def mix_pack(terms, c_pad, parts):

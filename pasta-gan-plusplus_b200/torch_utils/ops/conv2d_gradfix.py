@@ -329,7 +329,7 @@ def packed_up2_phase(weight, ry, rx, flip_weight, parts):
 def up2_modconv_packed(xp, weight, styles, dcoef, f, flip_weight, out_packed, *, noise=None, bias=None, act='linear', alpha=0.0, gain=1.0, clamp=-1.0):
     """The StyleGAN2 up = 2 modulated layer at the algorithmic MAC count, operand format in and out: the transposed convolution as four
     per-phase implicit GEMMs (demodulation in their epilogue) writing the (2H + 1) x (2W + 1) intermediate in the operand format, then ONE
-    pass `pgpp_fir_packed_act` = 4 x 4 blur (gain 4) + noise + bias + activation + clamp into `out_packed`.  Against the polyphase form
+    pass `pgpp_fir_packed_act` = 4 x 4 blur (gain 4) + noise + bias + activation + clamp into `out_packed` (None: a float32 NCHW tensor is returned).  Against the polyphase form
     (`packed_up2`, one launch at 4x the MACs) this wins on the tensor-bound layers (C >= 128)."""
     _init()
     n, _, h, w = xp.shape
@@ -341,6 +341,9 @@ def up2_modconv_packed(xp, weight, styles, dcoef, f, flip_weight, out_packed, *,
             pw = packed_up2_phase(weight, ry, rx, flip_weight, parts)
             igemm_conv(xp, pw, scale=styles, dcoef=dcoef, out_hw=(h + 1 - ry, w + 1 - rx), out_packed=t, out_phase=(ry, rx))
     taps, fw, fh = host_filter(f)
+    if out_packed is None:          # float32 NCHW result
+        y = torch.empty([n, o, 2 * h, 2 * w], dtype=torch.float32, device=xp.device)
+        return _plugin.fir_packed_act(t.data, o, 0, taps, fw, fh, 1, 1, 1, 1, False, 4.0, noise, bias, _ACT_IDX[act], alpha, gain, clamp, None, dst_nchw=y)
     _plugin.fir_packed_act(t.data, o, 0, taps, fw, fh, 1, 1, 1, 1, False, 4.0, noise, bias, _ACT_IDX[act], alpha, gain, clamp,
                            out_packed.data, dst_c_off=out_packed.c_off)
     return out_packed

@@ -42,7 +42,7 @@ def _kernel_path_ok(x, weight, styles, noise, up, down, padding, resample_filter
     return False
 
 
-# up = 2 layers with an operand-format output: per-phase transposed convolution (1x the MACs) + blur / noise / activation pass instead of the one-launch
+# up = 2 layers: per-phase transposed convolution (1x the MACs) + blur / noise / activation pass instead of the one-launch
 # 4x-MAC polyphase GEMM, for layers with at least this many (out channels x in channels).  Measured at batch 32 (tools/up2_bench.py, bf16x2):
 # 512->512 @32 0.91 vs 1.78 ms, 512->256 @64 1.32 vs 2.52 ms, 256->128 @128 2.26 vs 2.32 ms, 128->64 @256 3.53 vs 2.35 ms (the four passes over the
 # input and the (2H+1)^2 intermediate cost more than the MACs saved once the layer is HBM-bound).
@@ -72,9 +72,10 @@ def modulated_conv2d_fused_act(x, weight, styles, noise=None, up=1, padding=0, r
     if up == 2:
         if f16:
             raise NotImplementedError('the fused up=2 layer takes float32 / bfloat16 tensors; call modulated_conv2d for float16')
-        if (UP2_PHASES and out_packed is not None and out is None and not accumulate and padding == 1 and x.shape[2] * x.shape[3] >= 128 and
+        if (UP2_PHASES and out is None and not accumulate and padding == 1 and x.shape[2] * x.shape[3] >= 128 and
+                (out_packed is not None or (out_dtype in (None, torch.float32) and memory_format in (None, torch.contiguous_format) and src_dtype == torch.float32)) and
                 tuple(weight.shape[2:]) == (3, 3) and weight.shape[0] % 16 == 0 and act in ('linear', 'relu', 'lrelu') and
-                (x.data.shape[0] == parts if isinstance(x, conv2d_gradfix.PackedAct) else x.dtype == torch.float32) and
+                (x.data.shape[0] == parts if isinstance(x, conv2d_gradfix.PackedAct) else (x.dtype == torch.float32 and x.is_contiguous())) and
                 resample_filter is not None and tuple(resample_filter.shape) == (4, 4) and weight.shape[0] * weight.shape[1] >= UP2_PHASES_MIN_IO):
             # transposed convolution at 1x its MACs (four per-phase GEMMs) + one blur / noise / bias / activation pass on the operand format;
             # a tensor input is packed once with the style scale folded in (then the phase GEMMs use the shared weights)

@@ -192,5 +192,11 @@ def test_up2_layer_as_phase_gemms_plus_blur_pass(n, ic, oc, h, w, noise_kind, pr
             nets.modulated_conv2d_fused_act(x.to(DEV), wt.to(DEV), s.to(DEV), noise=None if noise is None else noise.to(DEV), up=2, padding=1,
                                             resample_filter=f.to(DEV), flip_weight=False, bias=b.to(DEV), act='lrelu', clamp=256.0, out_packed=out)
         assert rel_l2(out.to_nchw(), want) < tol
+        # float32 NCHW output (the low-resolution blocks hand tensors over), tensor and operand-format input
+        for src in (x.to(DEV), xp):
+            with torch.no_grad():
+                y = nets.modulated_conv2d_fused_act(src, wt.to(DEV), s.to(DEV), noise=None if noise is None else noise.to(DEV), up=2, padding=1,
+                                                    resample_filter=f.to(DEV), flip_weight=False, bias=b.to(DEV), act='lrelu', clamp=256.0)
+            assert y.dtype == torch.float32 and y.is_contiguous() and tuple(y.shape) == tuple(want.shape) and rel_l2(y, want) < tol
     finally:
         cg.fp32_precision, nets.UP2_PHASES, nets.UP2_PHASES_MIN_IO = old, old_flag, old_min
