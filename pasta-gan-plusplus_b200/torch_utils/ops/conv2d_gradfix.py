@@ -326,7 +326,32 @@ def packed_up2_phase(weight, ry, rx, flip_weight, parts):
     return _cached(weight, ('up2_phase', ry, rx, bool(flip_weight), parts), build)
 
 
-def up2_modconv_packed(xp, weight, styles, dcoef, f, flip_weight, out_packed, *, noise=None, bias=None, act='linear', alpha=0.0, gain=1.0, clamp=-1.0):
+def packed_up2_taps4(weight, flip_weight, parts):
+    """`conv_transpose2d(x, w', stride=2)` for a 3 x 3 kernel as ONE 2 x 2 correlation over the input grid with 4 * O GEMM columns (phase-major,
+    phase = 2 ry + rx writes T[2j + ry, 2i + rx]): tap (dy, dx) of the 2 x 2 window (padding 1) carries w'[KY, KX] for the phases that use that
+    input offset and zeros for the others - 16 instead of the algorithmic 9 MACs per input pixel and (output, input) channel pair (the polyphase
+    form with the blur folded in needs 36), but the input is read once and the four phases leave in one launch."""
+    def build():
+        assert tuple(weight.shape[2:]) == (3, 3)
+        w = weight.detach().to(torch.float32)
+        if flip_weight:
+            w = w.flip([2, 3])
+        o, ic = w.shape[:2]
+        assert o % 16 == 0
+        w4 = torch.zeros([4, o, ic, 2, 2], dtype=torch.float32, device=w.device)
+        for ry in (0, 1):
+            for rx in (0, 1):
+                for ty, ky in enumerate(_UP2_TAPS[ry]):
+                    for tx, kx in enumerate(_UP2_TAPS[rx]):
+                        w4[2 * ry + rx, :, :, ty + ry, tx + rx] = w[:, :, ky, kx]      # odd phases use only the window offset 1 (the pixel itself)
+        pw = pack_weights_native(w4.reshape(4 * o, ic, 2, 2), 2, 2, parts, 1, 1)
+        pw.phases, pw.o, pw.phase_stride = 4, o, o
+        return pw
+    return _cached(weight, ('up2_taps4', bool(flip_weight), parts), build)
+
+
+def up2_modconv_packed(xp, weight, styles, dcoef, f, flip_weight, out_packed, *, noise=None, bias=None, act='linear', alpha=0.0, gain=1.0, clamp=-1.0,
+                       taps4=False):
     """The StyleGAN2 up = 2 modulated layer at the algorithmic MAC count, operand format in and out: the transposed convolution as four
     per-phase implicit GEMMs (demodulation in their epilogue) writing the (2H + 1) x (2W + 1) intermediate in the operand format, then ONE
     pass `pgpp_fir_packed_act` = 4 x 4 blur (gain 4) + noise + bias + activation + clamp into `out_packed` (None: a float32 NCHW tensor is returned).  Against the polyphase form
@@ -335,16 +360,25 @@ def up2_modconv_packed(xp, weight, styles, dcoef, f, flip_weight, out_packed, *,
     n, _, h, w = xp.shape
     parts = xp.data.shape[0]
     o = weight.shape[0]
-    t = PackedAct(PackedAct.empty(n, 2 * h + 1, 2 * w + 1, o, parts, xp.device), o)
-    for ry in (0, 1):
-        for rx in (0, 1):
-            pw = packed_up2_phase(weight, ry, rx, flip_weight, parts)
-            igemm_conv(xp, pw, scale=styles, dcoef=dcoef, out_hw=(h + 1 - ry, w + 1 - rx), out_packed=t, out_phase=(ry, rx))
+    if taps4:
+        # `taps4`: the four phases as ONE 2 x 2 GEMM with 4 * O columns (16 / 9 of the algorithmic MACs, the input read once) - for the layers
+        # where four passes over the input cost more than the extra MACs.  Its grid is (H + 1) x (W + 1), so the intermediate has 2H + 2 rows, the
+        # last one zero (x[H] is outside the image): it stands in for the blur's bottom / right padding.
+        t = PackedAct(PackedAct.empty(n, 2 * h + 2, 2 * w + 2, o, parts, xp.device), o)
+        igemm_conv(xp, packed_up2_taps4(weight, flip_weight, parts), scale=styles, dcoef=dcoef, out_hw=(h + 1, w + 1), out_packed=t)
+        pad = (1, 0, 1, 0)
+    else:
+        t = PackedAct(PackedAct.empty(n, 2 * h + 1, 2 * w + 1, o, parts, xp.device), o)
+        for ry in (0, 1):
+            for rx in (0, 1):
+                pw = packed_up2_phase(weight, ry, rx, flip_weight, parts)
+                igemm_conv(xp, pw, scale=styles, dcoef=dcoef, out_hw=(h + 1 - ry, w + 1 - rx), out_packed=t, out_phase=(ry, rx))
+        pad = (1, 1, 1, 1)
     taps, fw, fh = host_filter(f)
     if out_packed is None:          # float32 NCHW result
         y = torch.empty([n, o, 2 * h, 2 * w], dtype=torch.float32, device=xp.device)
-        return _plugin.fir_packed_act(t.data, o, 0, taps, fw, fh, 1, 1, 1, 1, False, 4.0, noise, bias, _ACT_IDX[act], alpha, gain, clamp, None, dst_nchw=y)
-    _plugin.fir_packed_act(t.data, o, 0, taps, fw, fh, 1, 1, 1, 1, False, 4.0, noise, bias, _ACT_IDX[act], alpha, gain, clamp,
+        return _plugin.fir_packed_act(t.data, o, 0, taps, fw, fh, *pad, False, 4.0, noise, bias, _ACT_IDX[act], alpha, gain, clamp, None, dst_nchw=y)
+    _plugin.fir_packed_act(t.data, o, 0, taps, fw, fh, *pad, False, 4.0, noise, bias, _ACT_IDX[act], alpha, gain, clamp,
                            out_packed.data, dst_c_off=out_packed.c_off)
     return out_packed
 

@@ -48,6 +48,9 @@ def _kernel_path_ok(x, weight, styles, noise, up, down, padding, resample_filter
 # input and the (2H+1)^2 intermediate cost more than the MACs saved once the layer is HBM-bound).
 UP2_PHASES = True
 UP2_PHASES_MIN_IO = 512 * 256
+# below UP2_PHASES_MIN_IO and at least this: the four phases as ONE 2 x 2 GEMM with 4 * O columns (16 / 9 of the algorithmic MACs, input read once) + the
+# blur pass: 256->128 @128 1.94 ms (phases 2.10, polyphase 2.35); 128->64 @256 2.80 ms (polyphase 2.43: that layer keeps the polyphase form)
+UP2_TAPS4_MIN_IO = 256 * 128
 
 
 def modulated_conv2d_fused_act(x, weight, styles, noise=None, up=1, padding=0, resample_filter=None, demodulate=True,
@@ -76,7 +79,8 @@ def modulated_conv2d_fused_act(x, weight, styles, noise=None, up=1, padding=0, r
                 (out_packed is not None or (out_dtype in (None, torch.float32) and memory_format in (None, torch.contiguous_format) and src_dtype == torch.float32)) and
                 tuple(weight.shape[2:]) == (3, 3) and weight.shape[0] % 16 == 0 and act in ('linear', 'relu', 'lrelu') and
                 (x.data.shape[0] == parts if isinstance(x, conv2d_gradfix.PackedAct) else (x.dtype == torch.float32 and x.is_contiguous())) and
-                resample_filter is not None and tuple(resample_filter.shape) == (4, 4) and weight.shape[0] * weight.shape[1] >= UP2_PHASES_MIN_IO):
+                resample_filter is not None and tuple(resample_filter.shape) == (4, 4) and
+                weight.shape[0] * weight.shape[1] >= min(UP2_PHASES_MIN_IO, UP2_TAPS4_MIN_IO)):
             # transposed convolution at 1x its MACs (four per-phase GEMMs) + one blur / noise / bias / activation pass on the operand format;
             # a tensor input is packed once with the style scale folded in (then the phase GEMMs use the shared weights)
             xp, st = x, styles
@@ -86,7 +90,8 @@ def modulated_conv2d_fused_act(x, weight, styles, noise=None, up=1, padding=0, r
                 xp = conv2d_gradfix.PackedAct(conv2d_gradfix._plugin.pack_activations(x, styles, -(-ic // 64) * 64, parts), ic)
                 st = None
             return conv2d_gradfix.up2_modconv_packed(xp, weight, st, dcoef, resample_filter, flip_weight, out_packed, noise=noise, bias=bias,
-                                                     act=act, alpha=alpha, gain=gain, clamp=clamp)
+                                                     act=act, alpha=alpha, gain=gain, clamp=clamp,
+                                                     taps4=weight.shape[0] * weight.shape[1] < UP2_PHASES_MIN_IO)
         pw = conv2d_gradfix.packed_up2(weight, resample_filter, flip_weight, False, parts)
     else:
         pw = conv2d_gradfix.packed_plain(weight, flip_weight, parts, padding, padding, f16=f16)

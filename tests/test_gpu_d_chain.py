@@ -154,7 +154,7 @@ def test_up2_layer_as_phase_gemms_plus_blur_pass(n, ic, oc, h, w, noise_kind, pr
     nets = importlib.import_module('pgpp_b200.training.networks')
     upf = importlib.import_module('pgpp_b200.torch_utils.ops.upfirdn2d')
     from oracle import ref_ops
-    old, old_flag, old_min = cg.fp32_precision, nets.UP2_PHASES, nets.UP2_PHASES_MIN_IO
+    old, old_flag, old_min, old_t4 = cg.fp32_precision, nets.UP2_PHASES, nets.UP2_PHASES_MIN_IO, nets.UP2_TAPS4_MIN_IO
     cg.fp32_precision = prec
     nets.UP2_PHASES_MIN_IO = 0
     try:
@@ -172,19 +172,21 @@ def test_up2_layer_as_phase_gemms_plus_blur_pass(n, ic, oc, h, w, noise_kind, pr
         parts = cg._PRODUCTS[prec][1]
         xp = cg.PackedAct(cg._plugin.pack_activations(x.to(DEV), None, -(-ic // 64) * 64, parts), ic)
         outs = {}
-        for flag in (True, False):
-            nets.UP2_PHASES = flag
+        for flag in (True, 'taps4', False):
+            nets.UP2_PHASES = bool(flag)
+            nets.UP2_PHASES_MIN_IO, nets.UP2_TAPS4_MIN_IO = ((1 << 30), 0) if flag == 'taps4' else (0, 1 << 30)
             out = cg.PackedAct(torch.zeros(parts, n, 2 * h, 2 * w, 128, dtype=torch.bfloat16, device=DEV), oc, 64)      # a channel slice of a wider buffer
             before = custom_ops.launch_count()
             with torch.no_grad():
                 nets.modulated_conv2d_fused_act(xp, wt.to(DEV), s.to(DEV), noise=None if noise is None else noise.to(DEV), up=2, padding=1,
                                                 resample_filter=f.to(DEV), flip_weight=False, bias=b.to(DEV), act='lrelu', clamp=256.0, out_packed=out)
             launches = custom_ops.launch_count() - before
-            assert launches >= (9 if flag else 2), (flag, launches)          # demod + 4 x (modulate weights + GEMM) + blur pass  vs  demod + modulate + GEMM
+            assert launches >= {True: 9, 'taps4': 3, False: 2}[flag], (flag, launches)          # demod + 4 x (modulate weights + GEMM) + blur pass  vs  demod + modulate + GEMM
             outs[flag] = out.to_nchw()
             assert torch.all(out.data[..., :64] == 0) and torch.all(out.data[..., 64 + oc:] == 0)       # neighbours of the slice untouched
             assert rel_l2(outs[flag], want) < tol, (prec, flag, rel_l2(outs[flag], want))
-        assert rel_l2(outs[True], outs[False]) < 2 * tol
+        assert rel_l2(outs[True], outs[False]) < 2 * tol and rel_l2(outs['taps4'], outs[False]) < 2 * tol
+        nets.UP2_PHASES_MIN_IO, nets.UP2_TAPS4_MIN_IO = 0, 1 << 30
         # NCHW float32 input: packed once with the style scale folded in, phase GEMMs on shared weights
         nets.UP2_PHASES = True
         out = cg.PackedAct(torch.zeros(parts, n, 2 * h, 2 * w, 128, dtype=torch.bfloat16, device=DEV), oc, 64)
@@ -199,4 +201,4 @@ def test_up2_layer_as_phase_gemms_plus_blur_pass(n, ic, oc, h, w, noise_kind, pr
                                                     resample_filter=f.to(DEV), flip_weight=False, bias=b.to(DEV), act='lrelu', clamp=256.0)
             assert y.dtype == torch.float32 and y.is_contiguous() and tuple(y.shape) == tuple(want.shape) and rel_l2(y, want) < tol
     finally:
-        cg.fp32_precision, nets.UP2_PHASES, nets.UP2_PHASES_MIN_IO = old, old_flag, old_min
+        cg.fp32_precision, nets.UP2_PHASES, nets.UP2_PHASES_MIN_IO, nets.UP2_TAPS4_MIN_IO = old, old_flag, old_min, old_t4

@@ -23,8 +23,9 @@ for ic, oc, res in [(512, 512, 32), (512, 256, 64), (256, 128, 128), (128, 64, 2
     out = cg.PackedAct(cg.PackedAct.empty(n, 2 * res, 2 * res, oc, parts, dev), oc)
     del x
     res_ms = {}
-    for flag in (True, False):
-        nets.UP2_PHASES = flag
+    for flag in (True, 'taps4', False):
+        nets.UP2_PHASES = bool(flag)
+        nets.UP2_PHASES_MIN_IO, nets.UP2_TAPS4_MIN_IO = ((1 << 30), 0) if flag == 'taps4' else (0, 1 << 30)
         def run():
             with torch.no_grad():
                 nets.modulated_conv2d_fused_act(xp, w, s, noise=nz, up=2, padding=1, resample_filter=f, flip_weight=False, bias=b, act='lrelu', clamp=256.0, out_packed=out)
@@ -38,5 +39,5 @@ for ic, oc, res in [(512, 512, 32), (512, 256, 64), (256, 128, 128), (128, 64, 2
             ts.append(a.elapsed_time(c))
         res_ms[flag] = sorted(ts)[2]
     gf = 2.0 * n * oc * ic * 9 * res * res / 1e9
-    print(f'{ic}->{oc} @{res}->{2 * res} n{n} {cg.fp32_precision}: phases + blur {res_ms[True]:.3f} ms ({gf / res_ms[True]:.0f} TF/s alg.)   polyphase {res_ms[False]:.3f} ms ({gf / res_ms[False]:.0f} TF/s alg.)', flush=True)
+    print(f'{ic}->{oc} @{res}->{2 * res} n{n} {cg.fp32_precision}: phases + blur {res_ms[True]:.3f} ms ({gf / res_ms[True]:.0f} TF/s alg.)   2x2 4-phase GEMM + blur {res_ms['taps4']:.3f} ms   polyphase {res_ms[False]:.3f} ms ({gf / res_ms[False]:.0f} TF/s alg.)', flush=True)
     del xp, out
