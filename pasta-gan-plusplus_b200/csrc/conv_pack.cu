@@ -324,7 +324,8 @@ constexpr int kDirectMaxTaps = 16;
 // KH, CIN > 0: compile-time filter height / input channels (fully unrolled tap loops); 0: runtime values.
 // The 8 channels of a thread are accumulated as 4 packed float32 pairs (FFMA2): the kernel is bound by instruction issue, not by
 // its 2 GB of output (ncu: profiles/r02_ncu_small_kernels.md).
-template <int KW, int KH, int CIN>
+// ACT > 0: compile-time activation (pgpp_act; then the clamp is compile-time too: CLAMP) - the epilogue is a large part of the issue-bound kernel
+template <int KW, int KH, int CIN, int ACT = 0, bool CLAMP = true>
 __global__ void __launch_bounds__(256) conv_direct_kernel(DirectArgs p, TileGeom g, long long total_tiles) {
     extern __shared__ uint4 sm_packets[];
     __shared__ __align__(16) float sw[kDirectMaxTaps * 64];      // [tap][channel of the 64-channel tile]
@@ -353,6 +354,8 @@ __global__ void __launch_bounds__(256) conv_direct_kernel(DirectArgs p, TileGeom
             __syncthreads();
         }
         const int y = y0 + ((4 * lane) >> g.log_tw), x = x0 + ((4 * lane) & tw_mask);
+        const int tile_rows = 128 >> g.log_tw, tile_w = 1 << g.log_tw;
+        const bool interior = y0 - p.pad_y >= 0 && y0 + tile_rows - 1 + (kh - 1 - p.pad_y) < p.h && x0 - KW / 2 >= 0 && x0 + tile_w - 1 + KW / 2 < p.wd;
         f32x2 acc[4][4];                        // [channel pair][pixel]
         #pragma unroll
         for (int i = 0; i < 4; i++)
@@ -371,11 +374,19 @@ __global__ void __launch_bounds__(256) conv_direct_kernel(DirectArgs p, TileGeom
                         const bool row_ok = iy >= 0 && iy < p.h;
                         const float* row = src + (long long)ci * plane + (long long)iy * p.wd;
                         f32x2 in2[4 + KW - 1];
-                        #pragma unroll
-                        for (int j = 0; j < 4 + KW - 1; j++) {
-                            const int ix = x + j - KW / 2;
-                            const float v = (row_ok && ix >= 0 && ix < p.wd) ? __ldg(row + ix) : 0.f;
-                            in2[j] = pack2(v, v);
+                        if (interior) {         // the tile's halo lies inside the image: no per-element bounds tests
+                            #pragma unroll
+                            for (int j = 0; j < 4 + KW - 1; j++) {
+                                const float v = __ldg(row + x + j - KW / 2);
+                                in2[j] = pack2(v, v);
+                            }
+                        } else {
+                            #pragma unroll
+                            for (int j = 0; j < 4 + KW - 1; j++) {
+                                const int ix = x + j - KW / 2;
+                                const float v = (row_ok && ix >= 0 && ix < p.wd) ? __ldg(row + ix) : 0.f;
+                                in2[j] = pack2(v, v);
+                            }
                         }
                         const float* wt = wrow + ((ci * kh + kyr) * KW) * 64;
                         #pragma unroll
@@ -407,10 +418,11 @@ __global__ void __launch_bounds__(256) conv_direct_kernel(DirectArgs p, TileGeom
             #pragma unroll
             for (int k = 0; k < 4; k++) {
                 float r = v[i][k] + bb;
-                if (p.act == PGPP_ACT_RELU) r = fmaxf(r, 0.f);
-                else if (p.act == PGPP_ACT_LRELU) r = r > 0.f ? r : r * p.alpha;
+                const int act = ACT ? ACT : p.act;
+                if (act == PGPP_ACT_RELU) r = fmaxf(r, 0.f);
+                else if (act == PGPP_ACT_LRELU) r = r > 0.f ? r : r * p.alpha;
                 r *= p.gain;
-                if (p.clamp >= 0.f) r = fminf(fmaxf(r, -p.clamp), p.clamp);
+                if ((ACT ? CLAMP : true) && p.clamp >= 0.f) r = fminf(fmaxf(r, -p.clamp), p.clamp);
                 v[i][k] = r;
             }
         }
@@ -801,7 +813,8 @@ extern "C" int pgpp_conv2d_direct(const float* x, const float* w, const float* b
         kernel<<<(unsigned)blocks, 256, smem, (cudaStream_t)stream>>>(p, g, total);
         return PGPP_OK;
     };
-    const int rc = (kw == 3 && kh == 3 && c == 1) ? launch(conv_direct_kernel<3, 3, 1>)
+    const int rc = (kw == 3 && kh == 3 && c == 1 && act_fn == PGPP_ACT_RELU && clamp < 0.f) ? launch(conv_direct_kernel<3, 3, 1, PGPP_ACT_RELU, false>)
+                 : (kw == 3 && kh == 3 && c == 1) ? launch(conv_direct_kernel<3, 3, 1>)
                  : (kw == 1 && kh == 1) ? launch(conv_direct_kernel<1, 1, 0>)
                  : kw == 1 ? launch(conv_direct_kernel<1, 0, 0>) : launch(conv_direct_kernel<3, 0, 0>);
     if (rc != PGPP_OK) return rc;
