@@ -1153,39 +1153,47 @@ extern "C" int64_t pgpp_conv2d_igemm_stats_rows(const pgpp_conv_desc* d) {
 // count, so  mean = avg(mean_w),  M2 = sum M2_w + 32 * sum (mean_w - mean)^2  with  mean_w = pivot + s1 / 32,  M2_w = s2 - s1^2 / 32;
 // accumulated in float64 (the between-partial term is formed from sums of mean_w and mean_w^2).
 namespace pgpp {
-__global__ void __launch_bounds__(1024) instnorm_finalize_kernel(const float* ws, long long rows, long long rows_per_sample, int c, float eps,
+__global__ void __launch_bounds__(512) instnorm_finalize_kernel(const float* ws, long long rows, long long rows_per_sample, int c, float eps,
                                                                  float* mean, float* rstd) {
-    __shared__ double sh[3][32][33];
-    const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;        // 32 channels x 32 row slices per CTA, 4 rows in flight per thread
-    const int ch = blockIdx.x * 32 + lane, n = blockIdx.y;
+    // 8 channels x 64 row slices per CTA (a warp reads four 32-byte row segments per load), 8 rows in flight per thread: also at batch 1
+    // (a handful of CTAs) the walk over the 8192 partials of a 512 x 512 sample takes a few microseconds
+    __shared__ double sh[3][64][9];
+    const int chl = threadIdx.x & 7, slice = threadIdx.x >> 3;
+    const int ch = blockIdx.x * 8 + chl, n = blockIdx.y;
     const long long plane = rows * c;
     double a = 0.0, b = 0.0, m2 = 0.0;
     if (ch < c) {
         const float* base = ws + (long long)n * rows_per_sample * c + ch;
-        for (long long r0 = slice; r0 < rows_per_sample; r0 += 128) {
-            float pv[4], s1[4], s2[4];
+        for (long long r0 = slice; r0 < rows_per_sample; r0 += 64 * 8) {
+            float pv[8], s1[8], s2[8];
             #pragma unroll
-            for (int k = 0; k < 4; k++) {
-                const long long r = r0 + 32 * k;
+            for (int k = 0; k < 8; k++) {
+                const long long r = r0 + 64 * k;
                 const bool ok = r < rows_per_sample;
                 pv[k] = ok ? __ldg(base + r * c) : 0.f;
                 s1[k] = ok ? __ldg(base + plane + r * c) : 0.f;
                 s2[k] = ok ? __ldg(base + 2 * plane + r * c) : 0.f;
             }
             #pragma unroll
-            for (int k = 0; k < 4; k++) {
-                if (r0 + 32 * k >= rows_per_sample) break;
+            for (int k = 0; k < 8; k++) {
+                if (r0 + 64 * k >= rows_per_sample) break;
                 const double mw = (double)pv[k] + (double)s1[k] * (1.0 / 32.0);
                 a += mw; b += mw * mw;
                 m2 += (double)s2[k] - (double)s1[k] * (double)s1[k] * (1.0 / 32.0);
             }
         }
     }
-    sh[0][slice][lane] = a; sh[1][slice][lane] = b; sh[2][slice][lane] = m2;
+    sh[0][slice][chl] = a; sh[1][slice][chl] = b; sh[2][slice][chl] = m2;
     __syncthreads();
+    // fixed-order tree over the 64 slices (deterministic)
+    for (int step = 32; step > 0; step >>= 1) {
+        if (slice < step) {
+            sh[0][slice][chl] += sh[0][slice + step][chl]; sh[1][slice][chl] += sh[1][slice + step][chl]; sh[2][slice][chl] += sh[2][slice + step][chl];
+        }
+        __syncthreads();
+    }
     if (slice == 0 && ch < c) {
-        #pragma unroll 1
-        for (int k = 1; k < 32; k++) { a += sh[0][k][lane]; b += sh[1][k][lane]; m2 += sh[2][k][lane]; }
+        a = sh[0][0][chl]; b = sh[1][0][chl]; m2 = sh[2][0][chl];
         const double w = (double)rows_per_sample;
         const double mu = a / w;
         double var = (m2 + 32.0 * (b - a * a / w)) / (32.0 * w);
@@ -1200,8 +1208,8 @@ extern "C" int pgpp_instnorm_finalize(const float* ws, int64_t rows, int n, int 
     using namespace pgpp;
     PGPP_REQUIRE(ws && mean && rstd, "ws, mean and rstd must be device pointers");
     PGPP_REQUIRE(n >= 1 && c >= 1 && rows >= n && rows % n == 0, "rows must be a positive multiple of n");
-    dim3 grid((unsigned)((c + 31) / 32), (unsigned)n);
-    instnorm_finalize_kernel<<<grid, 1024, 0, (cudaStream_t)stream>>>(ws, rows, rows / n, c, eps, mean, rstd);
+    dim3 grid((unsigned)((c + 7) / 8), (unsigned)n);
+    instnorm_finalize_kernel<<<grid, 512, 0, (cudaStream_t)stream>>>(ws, rows, rows / n, c, eps, mean, rstd);
     count_launch();
     PGPP_CUDA_OK(cudaGetLastError());
     return PGPP_OK;
