@@ -21,3 +21,7 @@ for e in prof.key_averages():
     names[k][0] += e.count; names[k][1] += e.device_time_total / 1e3
 for k, (c, ms) in sorted(names.items()):
     print(f'{k:14s} {c:5d} launches  {ms:8.3f} ms')
+print('top non-pgpp kernels:')
+rows = sorted(((e.count, e.key) for e in prof.key_averages() if e.device_time_total > 0 and 'pgpp::' not in e.key), reverse=True)[:14]
+for c, k in rows:
+    print(f'  {c:4d}  {k[:120]}')
