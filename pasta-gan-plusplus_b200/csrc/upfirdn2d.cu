@@ -457,6 +457,112 @@ __global__ void __launch_bounds__(256) fir_up2_kernel(UpfirdnArgs p, int tiles_x
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// One-dimensional filters of up to 16 taps with up = 2, down = 2 or neither along the filter axis: the two passes of a separable
+// upfirdn2d (upfirdn2d.py:239-240), i.e. the 12-tap sym6 resampling of the ADA pipeline (augment.py:290,301).  Unit stride along W.
+// A thread owns 4 consecutive outputs of a row.
+//   fir_sep_x_kernel: the CTA (32 x 8 threads) stages the input span of its 128 x 8 output tile in shared memory;
+//   fir_sep_y_kernel: taps run along H, so a thread reads 4 consecutive pixels of every tap row straight from global memory (coalesced).
+constexpr int SEP_TAPS = 16, SEP_TW = 128, SEP_TH = 8;
+constexpr int SEP_SPAN = 2 * (SEP_TW - 1) + SEP_TAPS;      // widest input span of a tile row (down = 2)
+
+__device__ __forceinline__ void sep_load_taps(const UpfirdnArgs& p, int taps, long long stride, float* sk) {
+    if (threadIdx.x < SEP_TAPS) {
+        const int j = threadIdx.x;
+        float v = 0.f;
+        if (j < taps) v = p.f[(p.flip ? j : taps - 1 - j) * stride] * p.gain;
+        sk[j] = v;
+    }
+}
+
+template <class T, int UP, int DOWN>
+__global__ void __launch_bounds__(256) fir_sep_x_kernel(UpfirdnArgs p, int tiles_x, int tiles_y, long long total_tiles) {
+    __shared__ float sk[SEP_TAPS];
+    __shared__ float sx[SEP_TH][SEP_SPAN + 2];
+    sep_load_taps(p, p.fw, p.fs_x, sk);
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const T* x = (const T*)p.x;
+    T* y = (T*)p.y;
+    const long long planes = (long long)p.n * p.c;
+    for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        unsigned r = (unsigned)t;
+        const int bx = divmod_u32(r, (unsigned)tiles_x);
+        const int by = divmod_u32(r, (unsigned)tiles_y);
+        const int c = divmod_u32(r, (unsigned)p.c);
+        const int n = (int)r;
+        (void)planes;
+        const int ox0 = bx * SEP_TW, oy0 = by * SEP_TH;
+        // first input column any output of the tile can touch, and the span length
+        const int t0 = ox0 * DOWN - p.padx0;                                  // position of tap 0 of output ox0 on the (up-sampled) grid
+        const int ix0 = UP == 1 ? t0 : (t0 >= 0 ? (t0 + 1) / 2 : -((-t0) / 2));     // ceil(t0 / UP)
+        const int span = UP == 1 ? DOWN * (SEP_TW - 1) + p.fw : (SEP_TW - 1 + p.fw) / 2 + 1;
+        const T* xp = x + n * p.xs_n + c * p.xs_c;
+        __syncthreads();
+        for (int ry = 0; ry < SEP_TH; ry++) {
+            const int iy = oy0 + ry;                                          // rows are not resampled by this pass
+            const T* row = xp + (long long)iy * p.xs_h;
+            for (int k = threadIdx.x; k < span; k += 256) {
+                const int ix = ix0 + k;
+                sx[ry][k] = (iy < p.ih && ix >= 0 && ix < p.iw) ? to_acc<T>(__ldg(row + ix)) : 0.f;
+            }
+        }
+        __syncthreads();
+        const int oy = oy0 + ty;
+        if (oy >= p.oh) continue;
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        #pragma unroll
+        for (int v = 0; v < 4; v++) {
+            const int e = tx * 4 + v;                                         // output column inside the tile
+            if (UP == 1) {
+                const float* src = &sx[ty][e * DOWN];
+                for (int j = 0; j < p.fw; j++) acc[v] = fmaf(src[j], sk[j], acc[v]);
+            } else {
+                const int tt = t0 + e;                                        // tap 0 position; taps j with (tt + j) even hit input (tt + j) / 2
+                const int j0 = tt & 1;
+                const int rel = ((tt + j0) >> 1) - ix0;
+                const float* src = &sx[ty][rel];
+                for (int j = j0, i = 0; j < p.fw; j += 2, i++) acc[v] = fmaf(src[i], sk[j], acc[v]);
+            }
+        }
+        T* dst = y + n * p.ys_n + c * p.ys_c + (long long)oy * p.ys_h + ox0 + tx * 4;
+        #pragma unroll
+        for (int v = 0; v < 4; v++) if (ox0 + tx * 4 + v < p.ow) dst[v] = from_acc<T>(acc[v]);
+    }
+}
+
+template <class T, int UP, int DOWN>
+__global__ void __launch_bounds__(256) fir_sep_y_kernel(UpfirdnArgs p, long long total_quads, int quads_per_row) {
+    __shared__ float sk[SEP_TAPS];
+    sep_load_taps(p, p.fh, p.fs_y, sk);
+    __syncthreads();
+    const T* x = (const T*)p.x;
+    T* y = (T*)p.y;
+    for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < total_quads; q += (long long)gridDim.x * blockDim.x) {
+        unsigned r = (unsigned)q;
+        const int qx = divmod_u32(r, (unsigned)quads_per_row);
+        const int oy = divmod_u32(r, (unsigned)p.oh);
+        const int c = divmod_u32(r, (unsigned)p.c);
+        const int n = (int)r;
+        const int ox = qx * 4;
+        const T* xp = x + n * p.xs_n + c * p.xs_c + ox;
+        const int t0 = oy * DOWN - p.pady0;
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        const int j0 = UP == 1 ? 0 : (t0 & 1);
+        for (int j = j0; j < p.fh; j += UP) {
+            const int iy = UP == 1 ? t0 + j : (t0 + j) >> 1;
+            if (iy < 0 || iy >= p.ih) continue;
+            const T* row = xp + (long long)iy * p.xs_h;
+            const float kk = sk[j];
+            #pragma unroll
+            for (int v = 0; v < 4; v++)
+                if (ox + v < p.iw) acc[v] = fmaf(to_acc<T>(__ldg(row + v)), kk, acc[v]);
+        }
+        T* dst = y + n * p.ys_n + c * p.ys_c + (long long)oy * p.ys_h + ox;
+        #pragma unroll
+        for (int v = 0; v < 4; v++) if (ox + v < p.ow) dst[v] = from_acc<T>(acc[v]);
+    }
+}
+
 template <class T>
 static int launch_upfirdn(const UpfirdnArgs& p, cudaStream_t stream) {
     const bool tile_ok = p.upx == 1 && p.upy == 1 && p.downx == 1 && p.downy == 1 && p.fw <= 4 && p.fh <= 4 &&
@@ -465,7 +571,28 @@ static int launch_upfirdn(const UpfirdnArgs& p, cudaStream_t stream) {
                           p.xs_w == 1 && p.ys_w == 1 && sizeof(T) <= 4;
     const bool up2_ok = p.upx == 2 && p.upy == 2 && p.downx == 1 && p.downy == 1 && p.fw <= 4 && p.fh <= 4 &&
                         p.xs_w == 1 && p.ys_w == 1 && sizeof(T) <= 4;
-    if (up2_ok) {
+    const bool unit = p.xs_w == 1 && p.ys_w == 1 && sizeof(T) <= 4;
+    const bool sep_x = unit && p.fh == 1 && p.fw > 1 && p.fw <= SEP_TAPS && p.upy == 1 && p.downy == 1 && p.pady0 == 0 && p.oh == p.ih &&
+                       ((p.upx == 1 && p.downx <= 2) || (p.upx == 2 && p.downx == 1)) && !(p.upx == 1 && p.downx == 1 && p.fw <= 4);
+    const bool sep_y = unit && p.fw == 1 && p.fh > 1 && p.fh <= SEP_TAPS && p.upx == 1 && p.downx == 1 && p.padx0 == 0 && p.ow == p.iw &&
+                       ((p.upy == 1 && p.downy <= 2) || (p.upy == 2 && p.downy == 1)) && !(p.upy == 1 && p.downy == 1 && p.fh <= 4);
+    if (sep_x) {
+        const int tiles_x = (p.ow + SEP_TW - 1) / SEP_TW, tiles_y = (p.oh + SEP_TH - 1) / SEP_TH;
+        const long long total = (long long)tiles_x * tiles_y * p.c * p.n;
+        void (*kern)(UpfirdnArgs, int, int, long long) = p.upx == 2 ? fir_sep_x_kernel<T, 2, 1> : (p.downx == 2 ? fir_sep_x_kernel<T, 1, 2> : fir_sep_x_kernel<T, 1, 1>);
+        long long blocks = total;
+        const long long cap = (long long)sm_count() * occupancy_of(kern, 256, 0);
+        if (blocks > cap) blocks = cap;
+        kern<<<(unsigned)blocks, 256, 0, stream>>>(p, tiles_x, tiles_y, total);
+    } else if (sep_y) {
+        const int quads_per_row = (p.ow + 3) / 4;
+        const long long total = (long long)quads_per_row * p.oh * p.c * p.n;
+        void (*kern)(UpfirdnArgs, long long, int) = p.upy == 2 ? fir_sep_y_kernel<T, 2, 1> : (p.downy == 2 ? fir_sep_y_kernel<T, 1, 2> : fir_sep_y_kernel<T, 1, 1>);
+        long long blocks = (total + 255) / 256;
+        const long long cap = (long long)sm_count() * occupancy_of(kern, 256, 0);
+        if (blocks > cap) blocks = cap;
+        kern<<<(unsigned)blocks, 256, 0, stream>>>(p, total, quads_per_row);
+    } else if (up2_ok) {
         const int tiles_x = (p.ow + U2_TILE_W - 1) / U2_TILE_W, tiles_y = (p.oh + U2_TILE_H - 1) / U2_TILE_H;
         const long long total = (long long)tiles_x * tiles_y * p.c * p.n;
         void (*kern)(UpfirdnArgs, int, int, long long) =

@@ -108,6 +108,26 @@ def test_up2_is_the_adjoint_of_down2():
     assert float((dx - want).abs().max()) < 2e-5
 
 
+# one-dimensional (separable) filters: the 12-tap sym6 passes of the ADA pipeline (augment.py:290,301) and other tap counts, up = 2 / down = 2 / neither
+# along the filter axis, positive, zero and negative (cropping) padding, ragged sizes, both flip conventions
+@pytest.mark.parametrize('dtype,tol', [(torch.float32, 3e-6), (torch.float16, 2e-3)])
+@pytest.mark.parametrize('taps', [12, 8, 16, 5])
+@pytest.mark.parametrize('shape', [(2, 3, 40, 52), (1, 2, 131, 259), (1, 1, 9, 7)], ids=str)
+def test_separable_passes_vs_oracle(shape, taps, dtype, tol):
+    g = torch.Generator().manual_seed(29 + taps)
+    x = torch.randn(*shape, generator=g, dtype=torch.float64).to(dtype)
+    f = torch.randn(taps, generator=g)
+    for up, down, pad in [(2, 1, [taps // 2 + 1, taps // 2 - 1] * 2), (1, 2, [taps // 2 - 1, taps // 2] * 2), (1, 2, [-2, -1, -2, -1]), (1, 1, [3, 2, 0, 5]),
+                          (2, 1, [0, 0, 0, 0])]:
+        for flip in (False, True):
+            if shape[3] * up + pad[0] + pad[1] - taps + 1 < down or shape[2] * up + pad[2] + pad[3] - taps + 1 < down:
+                continue
+            want = ref_ops.upfirdn2d(x.double(), f, up=up, down=down, padding=pad, flip_filter=flip, gain=up ** 2)
+            got = upfirdn2d.upfirdn2d(x.to(DEV), f.to(DEV), up=up, down=down, padding=pad, flip_filter=flip, gain=up ** 2)
+            assert got.dtype == dtype and tuple(got.shape) == tuple(want.shape), (up, down, pad)
+            assert max_abs(got, want) <= tol * 8 * max(1.0, float(want.abs().max())), (up, down, pad, flip, max_abs(got, want))
+
+
 def test_channels_last_and_strided_inputs():
     g = torch.Generator().manual_seed(22)
     x = torch.randn(2, 8, 20, 24, generator=g)
