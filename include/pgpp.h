@@ -308,6 +308,8 @@ typedef struct pgpp_wgrad_desc {
     float* out;                     /* G: float32 [ca][cb][kh][kw], overwritten */
     float* workspace;               /* float32 [kh*kw][ca][cb_pad] scratch (split-K partial sums land here), 16-byte aligned */
     int32_t operand_f16;            /* nonzero: S and L hold IEEE half (one part, products == 1) instead of bfloat16 parts */
+    int32_t dil_y;                  /* vertical tap spacing (0 or 1 = dense): tap ky reads L row y + ky * dil_y - pad_y; > 1 with stride 1 only - the
+                                       weight gradient of a convolution that ran on a row-group im2col operand (pgpp_pack_im2col) */
 } pgpp_wgrad_desc;
 
 /* Split-K GEMM over the pixels on the 5th-gen tensor cores (tcgen05.mma, TMEM accumulators, TMA operand loads). */

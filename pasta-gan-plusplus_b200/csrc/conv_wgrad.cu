@@ -44,7 +44,7 @@ __device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t lbo_bytes, uint32
 
 struct WgradParams {
     int n, ca, cb;
-    int taps, kw, pad_y, pad_x, stride;
+    int taps, kw, pad_y, pad_x, stride, dil_y;
     int tw, th, tn, tiles_x, tiles_y, tiles_n;
     long long kblocks;
     int parts;
@@ -149,7 +149,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap map_s, const __grid_constant__ 
                             const int tap = j.tap0 + t;
                             const int ky = tap / p.kw, kx = tap - ky * p.kw;
                             const int lx = x0 * p.stride + kx - p.pad_x;
-                            const int ly = y0 * p.stride + ky - p.pad_y;
+                            const int ly = y0 * p.stride + ky * p.dil_y - p.pad_y;
                             for (int pb = 0; pb < p.parts; pb++) {
                                 mbar_wait(bempty_bar(sb), phb ^ 1);
                                 mbar_expect_tx(bfull_bar(sb), p.b_bytes);
@@ -329,6 +329,8 @@ extern "C" int pgpp_conv2d_wgrad(const pgpp_wgrad_desc* d, void* stream) {
     WgradParams p;
     p.n = d->n; p.ca = d->ca; p.cb = d->cb;
     p.taps = d->kh * d->kw; p.kw = d->kw; p.pad_y = d->pad_y; p.pad_x = d->pad_x; p.stride = d->stride;
+    p.dil_y = d->dil_y > 1 ? d->dil_y : 1;
+    PGPP_REQUIRE(p.dil_y == 1 || d->stride == 1, "wgrad: dil_y > 1 needs stride 1");
     int bn = d->cb_pad >= 128 ? 128 : 64;
     if (p.taps == 1 && d->cb_pad >= 256) bn = 256;
     p.block_n = bn;
@@ -336,7 +338,7 @@ extern "C" int pgpp_conv2d_wgrad(const pgpp_wgrad_desc* d, void* stream) {
     // K block = 64 pixels of S.  Stride-1 filters with kh > 1 on images of at least 64 pixels take a 16 (or 8) wide box so
     // that one L slab of th + kh - 1 rows serves all vertical taps of a filter column (the ky shift is a whole number of
     // 8-pixel swizzle atoms); everything else takes the widest box that fits the image, then rows, then samples.
-    p.reuse = (d->stride == 1 && d->kh > 1 && d->kh * bn <= 512 && d->ws >= 8 && (long long)d->ws * d->hs >= 64) ? 1 : 0;
+    p.reuse = (d->stride == 1 && d->kh > 1 && d->kh * bn <= 512 && d->ws >= 8 && (long long)d->ws * d->hs >= 64 && p.dil_y == 1) ? 1 : 0;
     if (env_flags().wgrad_no_reuse) p.reuse = 0;
     if (p.reuse) {
         p.tw = d->ws >= 16 ? 16 : 8; p.th = 64 / p.tw; p.tn = 1;

@@ -151,7 +151,7 @@ class WgradDesc(ctypes.Structure):
         ('kh', ctypes.c_int32), ('kw', ctypes.c_int32), ('pad_y', ctypes.c_int32), ('pad_x', ctypes.c_int32),
         ('stride', ctypes.c_int32), ('products', ctypes.c_int32),
         ('out', ctypes.c_void_p), ('workspace', ctypes.c_void_p),
-        ('operand_f16', ctypes.c_int32),
+        ('operand_f16', ctypes.c_int32), ('dil_y', ctypes.c_int32),
     ]
 
 

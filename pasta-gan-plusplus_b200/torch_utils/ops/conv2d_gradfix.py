@@ -109,11 +109,12 @@ class PackedAct:
     """Activations in the tensor-core operand format: data [parts, N, H, W, c_total] bf16, channels innermost; the
     logical tensor is channels [c_off, c_off + c) of every pixel.  Convolutions can write this format directly from
     their epilogue (`out_packed=`) and read it without a packing pass."""
-    __slots__ = ('data', 'c', 'c_off', 'logical_hw')
+    __slots__ = ('data', 'c', 'c_off', 'logical_hw', 'im2col')
 
     def __init__(self, data, c, c_off=0, logical_hw=None):
         self.data, self.c, self.c_off = data, c, c_off
         self.logical_hw = logical_hw        # (H, W) of the source image for row-group im2col operands (data has H + pad_y rows)
+        self.im2col = None                  # im2col parameters when this operand was kept for the weight gradient (_forward_conv)
 
     @staticmethod
     def empty(n, h, w, c_total, parts, device):
@@ -646,11 +647,52 @@ def pack_operand(x, prec=None):
     return PackedAct(data, x.shape[1])
 
 
+def _im2col_plan(x, weight, stride, padding):
+    """row-group im2col parameters for a few-channel convolution on an NCHW tensor (None: take the plain operand): C * kw <= 21, 'same' or any
+    symmetric padding, stride 1, images of at least 8 x 16 - the 7 x 7 RGB stems and the 3 x 3 convolutions on 1..6-channel maps, whose
+    64-channel operand rows would otherwise be 95 % padding"""
+    if isinstance(x, PackedAct) or tuple(stride) != (1, 1) or x.dtype not in (torch.float32, torch.bfloat16):
+        return None
+    o, ic, kh, kw = weight.shape
+    if x.shape[2] < 8 or x.shape[3] < 16 or o % 16 != 0:
+        return None
+    r = im2col_rows(ic, kh, kw)
+    return dict(r=r, kh=kh, kw=kw, ic=ic, pad_y=int(padding[0]), pad_x=int(padding[1])) if r else None
+
+
+def _weight_gradient_im2col(go, xim, weight_shape, im, precision, out_dtype):
+    """dW of a convolution that ran on the row-group im2col operand `xim` ([parts, N, H + pad_y, W, 64]: channel (ry * kw + kx) * ic + c of row
+    yy holds x[c, yy - pad_y + ry, x + kx - pad_x]): the weight gradient of the equivalent (groups x 1)-tap convolution with vertical tap spacing
+    r, G[o, ch, g] = sum gy[o, y, x] * xim[y + g * r, x, ch], scattered back to [O, I, kh, kw] (ky = g * r + ry)."""
+    o, ic, kh, kw = (int(v) for v in weight_shape)
+    r = im['r']
+    groups = -(-kh // r)
+    g = weight_gradient(go, xim, (o, r * kw * ic, groups, 1), 1, (0, 0), False, precision=precision, out_dtype=torch.float32, dil_y=r)
+    g = g.reshape(o, r, kw, ic, groups).permute(0, 3, 4, 1, 2).reshape(o, ic, groups * r, kw)[:, :, :kh]
+    return g.contiguous().to(out_dtype)
+
+
 def _forward_conv(x, weight, bias, stride, padding, keep=False, scale=1.0):
     """F.conv2d(x, weight, bias, stride, padding) on the tensor cores.  x: tensor or PackedAct (then `keep` is moot).
     keep=True also returns the packed copy of x (for the weight gradient)."""
     src_dtype = (torch.float16 if x.data.dtype == torch.float16 else weight.dtype) if isinstance(x, PackedAct) else x.dtype   # f16 operands: fp16 layer
     prec = precision_for(src_dtype)
+    im = _im2col_plan(x, weight, stride, padding) if prec != 'f16' else None
+    if im is not None:
+        # few-channel convolution: all taps of r filter rows go into the channel dimension (pgpp_pack_im2col); the operand is kept for the
+        # weight gradient, which runs on it too
+        _init()
+        parts = _PRODUCTS[prec][1]
+        pw = packed_plain(weight, True, parts, padding[0], padding[1], scale=scale, allow_im2col=True)
+        assert pw.im2col is not None
+        xp = PackedAct(_plugin.pack_im2col(x, None, im['kw'], im['r'], im['pad_x'], im['pad_y'], parts), im['r'] * im['kw'] * im['ic'], 0,
+                       logical_hw=(int(x.shape[2]), int(x.shape[3])))
+        mf = torch.channels_last if (x.stride(1) == 1 and x.shape[1] > 1) else torch.contiguous_format
+        y = igemm_conv(xp, pw, bias=bias, precision=prec, out_dtype=src_dtype, memory_format=mf)
+        if keep:
+            xp.im2col = im
+            return y, xp
+        return y
     pw = packed_plain(weight, True, _PRODUCTS[prec][1], padding[0], padding[1], f16=prec == 'f16', scale=scale)
     xp, mf = x, None
     if keep and not isinstance(x, PackedAct):
@@ -697,7 +739,7 @@ def _forward_conv_transpose(x, weight, bias, stride, padding, output_padding, ke
     return y
 
 
-def weight_gradient(grad_output, input, weight_shape, stride, padding, transpose, precision=None, out_dtype=None):
+def weight_gradient(grad_output, input, weight_shape, stride, padding, transpose, precision=None, out_dtype=None, dil_y=1):
     """dW of conv2d (transpose=False, weight [O, I, kh, kw]) or conv_transpose2d (transpose=True, weight [I, O, kh, kw]):
     what Conv2dGradWeight.forward (conv2d_gradfix.py:135-142) gets from cuDNN, computed by pgpp_conv2d_wgrad as
     G[a, b, ky, kx] = sum S[n, a, y, x] * L[n, b, y*s + ky - p, x*s + kx - p] with (S, L) = (grad_output, input) for the
@@ -726,7 +768,7 @@ def weight_gradient(grad_output, input, weight_shape, stride, padding, transpose
     d.ca = ca; d.ca_pad = ca_pad; d.s_pixel_stride = s_op.data.shape[4]; d.hs = int(small.shape[2]); d.ws = int(small.shape[3])
     d.cb = cb; d.cb_pad = cb_pad; d.l_pixel_stride = l_op.data.shape[4]; d.hl = int(large.shape[2]); d.wl = int(large.shape[3])
     d.kh = kh; d.kw = kw; d.pad_y = int(padding[0]); d.pad_x = int(padding[1])
-    d.stride = int(stride); d.products = products; d.operand_f16 = int(f16)
+    d.stride = int(stride); d.products = products; d.operand_f16 = int(f16); d.dil_y = int(dil_y)
     workspace = torch.empty([kh * kw, ca, cb_pad], dtype=torch.float32, device=device)
     d.out = out.data_ptr(); d.workspace = workspace.data_ptr()
     if trace is not None:
@@ -811,7 +853,10 @@ def _conv2d_gradfix(transpose, weight_shape, stride, padding, output_padding, di
                     assert grad_input.shape == input.shape
                 if want_w:
                     xin = ctx.input_packed if ctx.input_packed is not None else input
-                    grad_weight = weight_gradient(go, xin, weight_shape, stride[0], padding, transpose, precision=prec, out_dtype=weight.dtype)
+                    if isinstance(xin, PackedAct) and xin.im2col is not None:
+                        grad_weight = _weight_gradient_im2col(go, xin, weight_shape, xin.im2col, prec, weight.dtype)
+                    else:
+                        grad_weight = weight_gradient(go, xin, weight_shape, stride[0], padding, transpose, precision=prec, out_dtype=weight.dtype)
                     if weight_scale != 1.0:
                         grad_weight = grad_weight * weight_scale
                     assert grad_weight.shape == weight_shape

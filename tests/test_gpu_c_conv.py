@@ -377,3 +377,27 @@ def test_direct_convolution_rejects_what_it_does_not_cover():
         cg.direct_conv(x, torch.randn(8, 2, 3, 3, device=DEV))
     with pytest.raises(RuntimeError, match='channel mismatch'):
         cg.direct_conv(x, torch.randn(8, 1, 3, 3, device=DEV))
+
+
+@pytest.mark.parametrize('prec', FP32_MODES)
+@pytest.mark.parametrize('ic,oc,k,pad,h,w', [(3, 64, 7, 3, 40, 24), (1, 64, 3, 1, 33, 47), (6, 64, 3, 1, 16, 64), (3, 32, 7, 3, 64, 96), (2, 48, 5, 2, 24, 40)])
+def test_few_channel_convs_training_path_forward_and_gradients(ic, oc, k, pad, h, w, prec):
+    """conv2d_gradfix.conv2d with gradients on a few-channel input (the 7x7 RGB stems, 3x3 convs on 1..6-channel maps in G's training
+    pass): forward through the row-group im2col operand, weight gradient on the same operand (pgpp_conv2d_wgrad with vertical tap spacing),
+    data gradient through the transposed convolution, incl. the weight_scale extension - against float64 autograd of the library ops."""
+    cg.fp32_precision = prec
+    g = torch.Generator().manual_seed(91)
+    x = torch.randn(2, ic, h, w, generator=g); wt = torch.randn(oc, ic, k, k, generator=g); b = torch.randn(oc, generator=g)
+    gy = torch.randn(2, oc, h, w, generator=g)
+    scale = 1.0 / (ic * k * k) ** 0.5
+    xr = x.double().requires_grad_(True); wr = wt.double().requires_grad_(True); br = b.double().requires_grad_(True)
+    yr = torch.nn.functional.conv2d(xr, wr * scale, br, padding=pad)
+    gxr, gwr, gbr = torch.autograd.grad(yr, [xr, wr, br], gy.double())
+    xd = x.to(DEV).requires_grad_(True); wd = wt.to(DEV).requires_grad_(True); bd = b.to(DEV).requires_grad_(True)
+    before = custom_ops.launch_count()
+    y = cg.conv2d(xd, wd, bd, padding=pad, weight_scale=scale)
+    gx, gw, gb = torch.autograd.grad(y, [xd, wd, bd], gy.to(DEV))
+    assert custom_ops.launch_count() > before
+    for got, want, name in ((y, yr, 'y'), (gx, gxr, 'grad_x'), (gw, gwr, 'grad_w'), (gb, gbr, 'grad_b')):
+        assert tuple(got.shape) == tuple(want.shape) and got.dtype == torch.float32
+        assert rel_l2(got, want.detach()) < TOL[prec], (name, rel_l2(got, want.detach()))
