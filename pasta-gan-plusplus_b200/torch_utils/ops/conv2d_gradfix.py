@@ -705,6 +705,52 @@ def _forward_conv(x, weight, bias, stride, padding, keep=False, scale=1.0):
     return (y, xp) if keep else y
 
 
+TCONV_PHASES = True      # stride-2 transposed convolutions (the data gradient of every down-sampling convolution) as four per-phase convolutions of
+                         # the un-stuffed input at 1x the MACs; False: zero insertion + one convolution over the 4x larger tensor (the round-1 form)
+
+
+def _conv_transpose_stride2_phases(x, weight, bias, padding, output_padding, scale):
+    """F.conv_transpose2d(x, weight[I, O, kh, kw], stride=2, ...):  y[i] = sum_{j, t: 2 j + t - p = i} x[j] * w[t].  Output phase r = i & 1 only sees
+    the taps t = t0 + 2 m with t0 = (r + p) & 1, at inputs j = q + s - m (i = 2 q + r, s = (r + p - t0) / 2): a stride-1 correlation of x with the
+    flipped sub-kernel w[t0::2], padding (T - 1) - s, written to every second pixel of y (strided output view of the implicit GEMM).  Four launches on
+    ONE packed copy of x instead of a zero-insertion pass, a packing pass over the 4x larger tensor and a convolution that multiplies 75 % zeros."""
+    _init()
+    ic, oc, kh, kw = (int(v) for v in weight.shape)
+    src_dtype = (torch.float16 if x.data.dtype == torch.float16 else weight.dtype) if isinstance(x, PackedAct) else x.dtype
+    prec = precision_for(src_dtype)
+    parts, f16 = _PRODUCTS[prec][1], prec == 'f16'
+    xp = x if isinstance(x, PackedAct) else pack_operand(x, prec)
+    n, _, h, w = xp.shape
+    out_h = (h - 1) * 2 - 2 * padding[0] + kh + output_padding[0]
+    out_w = (w - 1) * 2 - 2 * padding[1] + kw + output_padding[1]
+    out_dtype = src_dtype if src_dtype != torch.float64 else torch.float32
+    y = torch.empty([n, oc, out_h, out_w], dtype=out_dtype, device=xp.device)
+    for ry in (0, 1):
+        t0y = (ry + padding[0]) & 1
+        ty = max(0, (kh - t0y + 1) // 2)
+        for rx in (0, 1):
+            t0x = (rx + padding[1]) & 1
+            tx = max(0, (kw - t0x + 1) // 2)
+            view = y[:, :, ry::2, rx::2]
+            if view.numel() == 0:
+                continue
+            if ty == 0 or tx == 0:          # no tap of the kernel reaches this phase (1-tap kernels)
+                view.zero_()
+                if bias is not None:
+                    view += bias.to(out_dtype).reshape(1, -1, 1, 1)
+                continue
+            pad_y = (ty - 1) - (ry + padding[0] - t0y) // 2
+            pad_x = (tx - 1) - (rx + padding[1] - t0x) // 2
+            def build(t0y=t0y, t0x=t0x, ty=ty, tx=tx, pad_y=pad_y, pad_x=pad_x):
+                sub = weight.detach()[:, :, t0y::2, t0x::2].contiguous()
+                return pack_weights_native(sub, ty, tx, parts, pad_y, pad_x, transpose_io=True, flip=True, scale=float(scale), f16=f16)
+            pw = _cached(weight, ('tconv_phase', ry, rx, int(padding[0]), int(padding[1]), parts, f16, float(scale)), build)
+            igemm_conv(xp, pw, out_hw=(int(view.shape[2]), int(view.shape[3])), out=view, bias=bias, precision=prec)
+    if src_dtype == torch.float64:
+        y = y.to(torch.float64)
+    return y, xp
+
+
 def _forward_conv_transpose(x, weight, bias, stride, padding, output_padding, keep=False, scale=1.0):
     """F.conv_transpose2d(x, weight[I, O, kh, kw], ...) as zero insertion + a stride-1 convolution with the
     flipped, transposed kernel (the data-gradient form; the fused up=2 layer does NOT come through here).
@@ -713,6 +759,9 @@ def _forward_conv_transpose(x, weight, bias, stride, padding, output_padding, ke
     from . import upfirdn2d as _up
     ic, oc, kh, kw = weight.shape
     sy, sx = stride
+    if TCONV_PHASES and sy == 2 and sx == 2 and padding[0] <= kh - 1 and padding[1] <= kw - 1:
+        y, xp = _conv_transpose_stride2_phases(x, weight, bias, padding, output_padding, scale)
+        return (y, xp) if keep else y
     src_dtype = (torch.float16 if x.data.dtype == torch.float16 else weight.dtype) if isinstance(x, PackedAct) else x.dtype   # f16 operands: fp16 layer
     strided = sy > 1 or sx > 1
     if strided:
@@ -842,14 +891,15 @@ def _conv2d_gradfix(transpose, weight_shape, stride, padding, output_padding, di
                 # the weight-gradient kernel; the weight gradient reads the input operand the forward pass kept
                 prec = precision_for(grad_output.dtype)
                 go = None
-                if want_w or (ctx.needs_input_grad[0] and (transpose or stride[0] == 1)):
+                if want_w or (ctx.needs_input_grad[0] and (transpose or stride[0] == 1 or (TCONV_PHASES and stride[0] == 2))):
                     go = pack_operand(grad_output, prec)
                 if ctx.needs_input_grad[0]:
                     p = calc_output_padding(input_shape=input.shape, output_shape=grad_output.shape)
                     if transpose:       # gradient of conv_transpose2d = conv2d of grad_output with the same weight
                         grad_input = _forward_conv(go, weight, None, stride, padding, scale=weight_scale)
                     else:               # gradient of conv2d = conv_transpose2d (zero insertion first when strided)
-                        grad_input = _forward_conv_transpose(go if stride[0] == 1 else grad_output, weight, None, stride, padding, p, scale=weight_scale)
+                        grad_input = _forward_conv_transpose(go if (stride[0] == 1 or (TCONV_PHASES and go is not None)) else grad_output, weight, None,
+                                                             stride, padding, p, scale=weight_scale)
                     assert grad_input.shape == input.shape
                 if want_w:
                     xin = ctx.input_packed if ctx.input_packed is not None else input
