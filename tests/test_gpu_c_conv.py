@@ -234,6 +234,31 @@ def test_conv_transpose2d_vs_oracle(stride, pad, opad, prec):
     assert tuple(got.shape) == tuple(want.shape) and rel_l2(got, want) < TOL[prec], rel_l2(got, want)
 
 
+@pytest.mark.parametrize('dtype', [torch.float32, torch.float16])
+@pytest.mark.parametrize('k,pad,opad', [(1, 0, 0), (1, 0, 1), (2, 0, 0), (2, 1, 1), (3, 0, 1), (3, 2, 1), (4, 1, 0), (5, 2, 1), (5, 3, 0), (7, 3, 1)])
+def test_conv_transpose2d_stride2_phase_form(k, pad, opad, dtype):
+    """stride-2 transposed convolution as four per-phase convolutions (conv2d_gradfix.TCONV_PHASES; the data gradient of the reference's
+    down-sampling convolutions, conv2d_gradfix.py:128-150 there) against float64 of the oracle and against the zero-insertion form"""
+    cg.fp32_precision = 'bf16x3'
+    g = torch.Generator().manual_seed(320 + k)
+    x = torch.randn(2, 24, 10, 13, generator=g)
+    wt = torch.randn(24, 20, k, k, generator=g) * 0.2
+    b = torch.randn(20, generator=g)
+    want = ref_ops.conv_transpose2d(x.double(), wt.double(), stride=2, padding=pad, output_padding=opad) + b.double().reshape(1, -1, 1, 1)
+    tol = 2e-3 if dtype == torch.float16 else 1e-5
+    assert cg.TCONV_PHASES
+    try:
+        with torch.no_grad():
+            got = cg.conv_transpose2d(x.to(DEV, dtype), wt.to(DEV, dtype), b.to(DEV, dtype), stride=2, padding=pad, output_padding=opad)
+            cg.TCONV_PHASES = False
+            old = cg.conv_transpose2d(x.to(DEV, dtype), wt.to(DEV, dtype), b.to(DEV, dtype), stride=2, padding=pad, output_padding=opad)
+    finally:
+        cg.TCONV_PHASES = True
+    assert got.dtype == dtype and tuple(got.shape) == tuple(want.shape)
+    assert rel_l2(got.float(), want) < tol, rel_l2(got.float(), want)
+    assert rel_l2(got.float(), old.float().cpu()) < tol
+
+
 @pytest.mark.parametrize('prec', FP32_MODES)
 @pytest.mark.parametrize('stride', [1, 2])
 def test_gradients_and_r1_double_backward(stride, prec):
