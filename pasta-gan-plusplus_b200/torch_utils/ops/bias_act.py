@@ -164,5 +164,6 @@ def _bias_act_cuda(dim=1, act='linear', alpha=None, gain=None, clamp=None):
                 d_b = bias_grad(d_x)
             return d_dy, d_x, d_b, None
 
+    BiasActCuda.Grad, BiasActCuda.is_identity, BiasActCuda.keep_y = BiasActCudaGrad, is_identity, keep_y
     _bias_act_cuda_cache[key] = BiasActCuda
     return BiasActCuda

@@ -620,13 +620,24 @@ def _library_weight(input, weight, weight_scale):
     return w if w.dtype == input.dtype else w.to(input.dtype)
 
 
-def conv2d(input, weight, bias=None, stride=1, padding=0, dilation=1, groups=1, weight_scale=1.0):
+FUSED_EPILOGUE_ACTS = ('linear', 'relu', 'lrelu')     # activations whose gradient needs the OUTPUT only (bias_act.py:24-34 `ref='y'` / '')
+
+
+def conv2d(input, weight, bias=None, stride=1, padding=0, dilation=1, groups=1, weight_scale=1.0, epilogue=None):
     """`weight_scale` (extension to conv2d_gradfix.py:22-25): the result is conv2d(input, weight * weight_scale) with the constant folded
     into the packed copy of `weight` - pass the PARAMETER itself (float32 also for float16 inputs) instead of `weight * gain` and the
-    packed copy is made once per optimizer step, not once per call."""
+    packed copy is made once per optimizer step, not once per call.
+    `epilogue` (extension, kernel path only): (act, alpha, gain, clamp) of the bias_act call that would follow - clamp(act(conv + bias) * gain)
+    comes out of the convolution's epilogue instead of a second pass over the result; its gradient is bias_act's own gradient op on the
+    saved output, so first and second order gradients are those of conv2d followed by bias_act."""
     if _should_use_custom_op(input):
+        if epilogue is not None:
+            act, alpha, gain, clamp = epilogue
+            assert act in FUSED_EPILOGUE_ACTS
+            epilogue = (act, float(alpha), float(gain), float(clamp))
         return _conv2d_gradfix(transpose=False, weight_shape=weight.shape, stride=stride, padding=padding, output_padding=0,
-                               dilation=dilation, groups=groups, weight_scale=float(weight_scale)).apply(input, weight, bias)
+                               dilation=dilation, groups=groups, weight_scale=float(weight_scale), epilogue=epilogue).apply(input, weight, bias)
+    assert epilogue is None, 'epilogue= needs the kernel path'
     return torch.nn.functional.conv2d(input=input, weight=_library_weight(input, weight, weight_scale), bias=bias, stride=stride, padding=padding,
                                       dilation=dilation, groups=groups)
 
@@ -672,9 +683,10 @@ def _weight_gradient_im2col(go, xim, weight_shape, im, precision, out_dtype):
     return g.contiguous().to(out_dtype)
 
 
-def _forward_conv(x, weight, bias, stride, padding, keep=False, scale=1.0):
+def _forward_conv(x, weight, bias, stride, padding, keep=False, scale=1.0, epi=None):
     """F.conv2d(x, weight, bias, stride, padding) on the tensor cores.  x: tensor or PackedAct (then `keep` is moot).
-    keep=True also returns the packed copy of x (for the weight gradient)."""
+    keep=True also returns the packed copy of x (for the weight gradient).  epi: dict(act, alpha, gain, clamp) applied by the epilogue."""
+    epi = epi or {}
     src_dtype = (torch.float16 if x.data.dtype == torch.float16 else weight.dtype) if isinstance(x, PackedAct) else x.dtype   # f16 operands: fp16 layer
     prec = precision_for(src_dtype)
     im = _im2col_plan(x, weight, stride, padding) if prec != 'f16' else None
@@ -688,7 +700,7 @@ def _forward_conv(x, weight, bias, stride, padding, keep=False, scale=1.0):
         xp = PackedAct(_plugin.pack_im2col(x, None, im['kw'], im['r'], im['pad_x'], im['pad_y'], parts), im['r'] * im['kw'] * im['ic'], 0,
                        logical_hw=(int(x.shape[2]), int(x.shape[3])))
         mf = torch.channels_last if (x.stride(1) == 1 and x.shape[1] > 1) else torch.contiguous_format
-        y = igemm_conv(xp, pw, bias=bias, precision=prec, out_dtype=src_dtype, memory_format=mf)
+        y = igemm_conv(xp, pw, bias=bias, precision=prec, out_dtype=src_dtype, memory_format=mf, **epi)
         if keep:
             xp.im2col = im
             return y, xp
@@ -699,7 +711,7 @@ def _forward_conv(x, weight, bias, stride, padding, keep=False, scale=1.0):
         mf = torch.channels_last if (x.stride(1) == 1 and x.shape[1] > 1) else torch.contiguous_format     # the output follows the input's layout
         xp = pack_operand(x, prec)
     y = igemm_conv(xp, pw, stride=stride[0], bias=bias, precision=prec, out_dtype=src_dtype if src_dtype != torch.float64 else None,
-                   memory_format=mf)
+                   memory_format=mf, **epi)
     if src_dtype == torch.float64 and y.dtype != torch.float64:
         y = y.to(torch.float64)
     return (y, xp) if keep else y
@@ -834,14 +846,14 @@ def weight_gradient(grad_output, input, weight_shape, stride, padding, transpose
 _conv2d_gradfix_cache = dict()
 
 
-def _conv2d_gradfix(transpose, weight_shape, stride, padding, output_padding, dilation, groups, weight_scale=1.0):
+def _conv2d_gradfix(transpose, weight_shape, stride, padding, output_padding, dilation, groups, weight_scale=1.0, epilogue=None):
     ndim = 2
     weight_shape = tuple(weight_shape)
     stride = _tuple_of_ints(stride, ndim)
     padding = _tuple_of_ints(padding, ndim)
     output_padding = _tuple_of_ints(output_padding, ndim)
     dilation = _tuple_of_ints(dilation, ndim)
-    key = (transpose, weight_shape, stride, padding, output_padding, dilation, groups, weight_scale)
+    key = (transpose, weight_shape, stride, padding, output_padding, dilation, groups, weight_scale, epilogue)
     if key in _conv2d_gradfix_cache:
         return _conv2d_gradfix_cache[key]
 
@@ -859,6 +871,16 @@ def _conv2d_gradfix(transpose, weight_shape, stride, padding, output_padding, di
                                   'set conv2d_gradfix.enabled = False to route this call to the PyTorch library op')
 
     common_kwargs = dict(stride=stride, padding=padding, dilation=dilation, groups=groups, weight_scale=weight_scale)
+    epi = epi_grad = None
+    if epilogue is not None:
+        assert not transpose
+        from . import bias_act as _ba
+        e_act, e_alpha, e_gain, e_clamp = epilogue
+        epi = dict(act=e_act, alpha=e_alpha, gain=e_gain, clamp=e_clamp)
+        _ba._init()
+        fn = _ba._bias_act_cuda(dim=1, act=e_act, alpha=e_alpha, gain=e_gain, clamp=e_clamp if e_clamp >= 0 else None)
+        epi_grad = None if fn.is_identity else fn.Grad      # d(pre-activation) = Grad(dy; y): linear in dy, differentiable once more
+        epi_null, epi_keep_y = _ba._null_tensor, fn.keep_y
 
     def calc_output_padding(input_shape, output_shape):
         if transpose:
@@ -873,18 +895,25 @@ def _conv2d_gradfix(transpose, weight_shape, stride, padding, output_padding, di
             keep = keep_packed_operands and ctx.needs_input_grad[1]
             ctx.input_packed = None
             if not transpose:
-                output = _forward_conv(input, weight, bias, stride, padding, keep=keep, scale=weight_scale)
+                output = _forward_conv(input, weight, bias, stride, padding, keep=keep, scale=weight_scale, epi=epi)
             else:
                 output = _forward_conv_transpose(input, weight, bias, stride, padding, output_padding, keep=keep, scale=weight_scale)
             if keep:
                 output, ctx.input_packed = output
-            ctx.save_for_backward(input, weight)
+            if epi_grad is not None and epi_keep_y:
+                ctx.save_for_backward(input, weight, output)
+            else:
+                ctx.save_for_backward(input, weight)
             return output
 
         @staticmethod
         def backward(ctx, grad_output):
-            input, weight = ctx.saved_tensors
+            input, weight = ctx.saved_tensors[:2]
             grad_input = grad_weight = grad_bias = None
+            if epi_grad is not None:        # through the fused bias_act first: everything below sees the gradient of the pre-activation
+                y = ctx.saved_tensors[2] if epi_keep_y else epi_null
+                mf = torch.channels_last if (epi_keep_y and y.stride(1) == 1 and y.shape[1] > 1) else torch.contiguous_format
+                grad_output = epi_grad.apply(grad_output.contiguous(memory_format=mf), epi_null, epi_null, y)
             want_w = ctx.needs_input_grad[1] and not weight_gradients_disabled
             if not torch.is_grad_enabled() and keep_packed_operands:
                 # plain backward pass (no graph is being recorded): grad_output is packed once and feeds both the data-gradient and

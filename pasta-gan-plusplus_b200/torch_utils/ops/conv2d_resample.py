@@ -21,12 +21,15 @@ def _get_weight_shape(w):
     return shape
 
 
-def _conv2d_wrapper(x, w, stride=1, padding=0, groups=1, transpose=False, flip_weight=True, w_scale=1.0):
+def _conv2d_wrapper(x, w, stride=1, padding=0, groups=1, transpose=False, flip_weight=True, w_scale=1.0, bias=None, epilogue=None):
     """conv2d / conv_transpose2d through conv2d_gradfix; flip_weight=False means true convolution."""
     _get_weight_shape(w)
     if not flip_weight:
         w = w.flip([2, 3])
     op = conv2d_gradfix.conv_transpose2d if transpose else conv2d_gradfix.conv2d
+    if epilogue is not None:
+        assert not transpose
+        return op(x, w, bias, stride=stride, padding=padding, groups=groups, weight_scale=w_scale, epilogue=epilogue)
     if w_scale == 1.0:
         return op(x, w, stride=stride, padding=padding, groups=groups)
     return op(x, w, stride=stride, padding=padding, groups=groups, weight_scale=w_scale)
@@ -76,11 +79,33 @@ def _transposed_weight(w, groups):
 
 
 @misc.profiled_function
-def conv2d_resample(x, w, f=None, up=1, down=1, padding=0, groups=1, flip_weight=True, flip_filter=False, w_scale=1.0):
+def conv2d_resample(x, w, f=None, up=1, down=1, padding=0, groups=1, flip_weight=True, flip_filter=False, w_scale=1.0, bias_act_args=None):
     """x [N, I, H, W], w [O, I/groups, kh, kw], f from upfirdn2d.setup_filter() or None.  Padding is given
     with respect to the upsampled image and applied once.
     `w_scale` (extension): the convolution uses w * w_scale; with it `w` may be the float32 parameter itself also for a float16 x
-    (see conv2d_gradfix.conv2d: the constant and the cast are folded into the cached packed copy of the parameter)."""
+    (see conv2d_gradfix.conv2d: the constant and the cast are folded into the cached packed copy of the parameter).
+    `bias_act_args` (extension): dict(b, act, gain, clamp) of the `bias_act.bias_act` call the reference's layers make on the result
+    (networks.py:172-176); the result is then that call's.  Where the decomposition ends in a convolution on the kernel path and the
+    activation's gradient needs its output only, the bias / activation / gain / clamp run in that convolution's epilogue."""
+    if bias_act_args is not None:
+        from . import bias_act
+        ba = dict(bias_act_args)
+        spec = bias_act.activation_funcs[ba.get('act', 'linear')]
+        # up == 1: every branch of the decomposition ends in the convolution
+        if (FUSE_BIAS_ACT and up == 1 and groups == 1 and ba.get('act', 'linear') in conv2d_gradfix.FUSED_EPILOGUE_ACTS
+                and conv2d_gradfix._should_use_custom_op(x)):
+            epilogue = (ba.get('act', 'linear'), spec.def_alpha, spec.def_gain if ba.get('gain') is None else ba['gain'],
+                        -1 if ba.get('clamp') is None else ba['clamp'])
+            return _conv2d_resample(x, w, f, up, down, padding, groups, flip_weight, flip_filter, w_scale, ba.get('b'), epilogue)
+        y = _conv2d_resample(x, w, f, up, down, padding, groups, flip_weight, flip_filter, w_scale, None, None)
+        return bias_act.bias_act(y, ba.get('b'), act=ba.get('act', 'linear'), gain=ba.get('gain'), clamp=ba.get('clamp'))
+    return _conv2d_resample(x, w, f, up, down, padding, groups, flip_weight, flip_filter, w_scale, None, None)
+
+
+FUSE_BIAS_ACT = True        # False: bias_act as its own pass after the convolution (the reference's form), for comparison / tests
+
+
+def _conv2d_resample(x, w, f, up, down, padding, groups, flip_weight, flip_filter, w_scale, bias, epilogue):
     assert isinstance(x, torch.Tensor) and (x.ndim == 4)
     assert isinstance(w, torch.Tensor) and (w.ndim == 4) and (w.dtype == x.dtype or (w_scale != 1.0 and w.dtype == torch.float32))
     assert f is None or (isinstance(f, torch.Tensor) and f.ndim in [1, 2] and f.dtype == torch.float32)
@@ -101,7 +126,7 @@ def conv2d_resample(x, w, f=None, up=1, down=1, padding=0, groups=1, flip_weight
 
     pad.widen(fw, fh, up, down)
     fir = lambda t, **kw_: upfirdn2d.upfirdn2d(x=t, f=f, flip_filter=flip_filter, **kw_)
-    conv = lambda t, **kw_: _conv2d_wrapper(x=t, w=w, groups=groups, flip_weight=flip_weight, w_scale=w_scale, **kw_)
+    conv = lambda t, **kw_: _conv2d_wrapper(x=t, w=w, groups=groups, flip_weight=flip_weight, w_scale=w_scale, bias=bias, epilogue=epilogue, **kw_)
     pointwise = kh == 1 and kw == 1
 
     if up == 1 and down > 1:

@@ -166,6 +166,10 @@ class Conv2dLayer(torch.nn.Module):
         if conv2d_gradfix._should_use_custom_op(x) and self.weight.dtype == torch.float32:
             # kernel path (training): the runtime gain and the cast are folded into the packed copy of the PARAMETER, which is then made
             # once per optimizer step instead of once per call from the temporary `weight * gain` (networks.py:169)
+            if impl == 'cuda':      # bias / activation / gain / clamp in the convolution's epilogue where the decomposition allows
+                return conv2d_resample.conv2d_resample(x=x, w=self.weight, f=self.resample_filter, up=self.up, down=self.down,
+                                                       padding=self.padding, flip_weight=(self.up == 1), w_scale=float(self.weight_gain),
+                                                       bias_act_args=dict(b=b, act=self.activation, gain=act_gain, clamp=act_clamp))
             x = conv2d_resample.conv2d_resample(x=x, w=self.weight, f=self.resample_filter, up=self.up, down=self.down,
                                                 padding=self.padding, flip_weight=(self.up == 1), w_scale=float(self.weight_gain))
         else:

@@ -426,3 +426,57 @@ def test_few_channel_convs_training_path_forward_and_gradients(ic, oc, k, pad, h
     for got, want, name in ((y, yr, 'y'), (gx, gxr, 'grad_x'), (gw, gwr, 'grad_w'), (gb, gbr, 'grad_b')):
         assert tuple(got.shape) == tuple(want.shape) and got.dtype == torch.float32
         assert rel_l2(got, want.detach()) < TOL[prec], (name, rel_l2(got, want.detach()))
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.float16])
+@pytest.mark.parametrize('k,down,act,clamp,bias', [(3, 1, 'lrelu', None, True), (3, 2, 'lrelu', 256, True), (1, 2, 'linear', None, False),
+                                                 (1, 1, 'linear', 256, True), (3, 1, 'relu', None, True), (3, 1, 'linear', None, True)])
+def test_training_conv_with_fused_bias_act(k, down, act, clamp, bias, dtype):
+    """Conv2dLayer on the training route (networks.py:160-176: conv2d_resample, then bias_act) with the bias / activation / gain / clamp in
+    the convolution's epilogue (conv2d_gradfix.conv2d(epilogue=)): output, first-order gradients and the R1 pattern (gradient of the
+    input-gradient norm w.r.t. weight and bias) against the two-pass form on the same kernels and against float64 of the reference ops"""
+    syn = importlib.import_module('pgpp_b200.training.synthesis')
+    cg.fp32_precision = 'bf16x3'
+    torch.manual_seed(70 + k + down)
+    layer = syn.Conv2dLayer(16, 32, k, bias=bias, activation=act, down=down, conv_clamp=clamp).to(DEV)
+    if bias:
+        with torch.no_grad():
+            layer.bias.copy_(torch.randn(32) * 0.5)
+    x0 = (torch.randn(2, 16, 40, 36, device=DEV) * (40.0 if clamp else 1.0)).to(dtype)
+
+    def run(fuse):
+        cr.FUSE_BIAS_ACT = fuse
+        x = x0.clone().requires_grad_(True)
+        params = [layer.weight] + ([layer.bias] if bias else [])
+        y = layer(x, gain=0.7, fused=False)
+        gx, = torch.autograd.grad(y.float().sum() + y.float().square().sum() * 0.01, [x], create_graph=True)
+        loss = gx.float().square().sum() * 1e-3 + y.float().mean()
+        gp = torch.autograd.grad(loss, params)
+        return [y, gx] + list(gp)
+
+    try:
+        fused = run(True)
+        plain = run(False)
+    finally:
+        cr.FUSE_BIAS_ACT = True
+    # fp16: the two-pass form rounds the convolution to fp16 before the bias and the activation; where that rounding moves a pre-activation
+    # across zero the lrelu slope differs between the two forms (a 1e-4 fraction of the pixels, an O(1) change each) - the fused form is
+    # the one that follows the float64 result
+    tols = [2e-3] + [3e-2] * 3 if dtype == torch.float16 else [2e-5] * 4
+    names = ['y', 'grad_x', 'r1_grad_w', 'r1_grad_b']
+    for a, b_, tol, name in zip(fused, plain, tols, names):
+        assert a.dtype == b_.dtype and a.shape == b_.shape
+        assert rel_l2(a.float(), b_.float()) < tol, ('two-pass', name, rel_l2(a.float(), b_.float()))
+
+    if True:                        # float64 of the reference's decomposition, with its own autograd
+        ftol = [1e-3, 3e-2, 3e-2, 3e-2] if dtype == torch.float16 else [1e-4] * 4
+        w64 = layer.weight.detach().double().cpu().requires_grad_(True)
+        b64 = layer.bias.detach().double().cpu().requires_grad_(True) if bias else None
+        x64 = x0.double().cpu().requires_grad_(True)
+        yr = ref_ops.conv2d_resample(x64, w64 * layer.weight_gain, layer.resample_filter.detach().cpu().float(), down=down, padding=layer.padding)
+        yr = ref_ops.bias_act(yr, b64, act=act, gain=layer.act_gain * 0.7, clamp=None if clamp is None else clamp * 0.7)
+        gx, = torch.autograd.grad(yr.sum() + yr.square().sum() * 0.01, [x64], create_graph=True)
+        loss = gx.square().sum() * 1e-3 + yr.mean()
+        gp = torch.autograd.grad(loss, [w64] + ([b64] if bias else []))
+        for a, r, tol, name in zip(fused, [yr, gx] + list(gp), ftol, names):
+            assert rel_l2(a, r) < tol, ('float64', name, rel_l2(a, r))
