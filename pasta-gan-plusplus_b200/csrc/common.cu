@@ -23,6 +23,7 @@ static EnvFlags read_env() {
     f.igemm_no_tma_store = getenv("PGPP_IGEMM_NO_TMA_STORE") != nullptr;
     f.igemm_slab9 = getenv("PGPP_IGEMM_SLAB9") != nullptr;
     f.wgrad_no_reuse = getenv("PGPP_WGRAD_NO_REUSE") != nullptr;
+    f.wgrad_no_pair = getenv("PGPP_WGRAD_NO_PAIR") != nullptr;
     f.ba_nostream = getenv("PGPP_BA_NOSTREAM") != nullptr;
     f.fir_packed_no_tile = getenv("PGPP_FIR_PACKED_NO_TILE") != nullptr;
     const char* e = getenv("PGPP_IGEMM_DEBUG");

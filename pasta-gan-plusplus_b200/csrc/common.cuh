@@ -20,7 +20,7 @@ inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_
 // pgpp_refresh_env() re-reads them (timing tools that flip a switch between launches call it).
 struct EnvFlags {
     bool igemm_no_reuse, igemm_no_slab2, igemm_no_resident, igemm_no_stack, igemm_no_lean_epilogue, igemm_no_tma_store, igemm_slab9;
-    bool wgrad_no_reuse, ba_nostream, fir_packed_no_tile;
+    bool wgrad_no_reuse, wgrad_no_pair, ba_nostream, fir_packed_no_tile;
     int igemm_debug;
 };
 const EnvFlags& env_flags();

@@ -21,6 +21,15 @@
 // Work decomposition: job = (a block, b block, tap group, K split); persistent CTAs loop over jobs, each job ends with
 // an atomicAdd epilogue into the fp32 [Ca][Cb][kh][kw] gradient (zeroed by this call).
 //
+// Pair mode (at most 64 channels a, stride 1, kh > 1, kw <= 4): 64 channels would fill half of the 128 accumulator lanes, so the
+// taps move into the tile instead.  With the pixel index (y', x') = (L row, S column),
+//   G[a, b, ky, kx] = sum S[a, y' - ky + pad_y, x'] * L[b, y', x' + kx - pad_x]:
+// the vertical tap shifts S, the horizontal tap shifts L.  One S slab of th + 2 * ceil(kh / 2) - 1 rows serves all ky as
+// row-shifted views, and the A descriptor's leading byte offset (distance of the "next 64 channels") is ONE ROW of that slab:
+// lanes 0-63 of an MMA see the view of tap ky, lanes 64-127 the view of tap ky - 1, from the same bytes.  The B tile is kw boxes
+// of L, one per kx (N = kw * 64 columns).  A 3x3 filter is 2 MMAs of 128 x 192 per K step instead of 9 of 128 x 64 with half of
+// the lanes idle: 1.5x less tensor time, 4.5x fewer instructions, 2.2x less shared-memory fill per K block.
+//
 // Warp roles (320 threads, 1 CTA per SM): warp 0 TMA producer, warp 1 TMEM owner + MMA issuer, warps 2-9 epilogue.
 #include <stdlib.h>
 #include "tc_ptx.cuh"
@@ -54,6 +63,7 @@ struct WgradParams {
     int a_stages, b_stages;
     int b_chunks;                       // 64-channel boxes per B tile (block_n / 64)
     int reuse;                          // 1: one L slab of th + kh - 1 rows per (kx, K block), vertical taps are row-shifted views
+    int pair, kh, npairs;               // pair mode (see above): npairs = ceil(kh / 2) accumulators of kw * 64 columns
     unsigned b_chunk_bytes;             // bytes of one L box (= leading byte offset of the B descriptor)
     unsigned ky_step_bytes;             // tw * 128: shift of the slab view per vertical tap
     unsigned a_part_bytes, a_stage_bytes, b_bytes;
@@ -70,7 +80,8 @@ __device__ __forceinline__ WgJob decode_job(const WgradParams& p, long long job)
     const int tg = (int)(job % p.n_groups); job /= p.n_groups;
     j.bb = (int)(job % p.b_blks);
     j.ab = (int)(job / p.b_blks);
-    if (p.reuse) { j.tap0 = tg; j.tap_step = p.kw; j.nt = p.t_group; }      // group = one kx, all ky
+    if (p.pair) { j.tap0 = 0; j.tap_step = 0; j.nt = p.npairs; }              // all taps: accumulator t = the ky pair (kh-1-2t, kh-2-2t), every kx
+    else if (p.reuse) { j.tap0 = tg; j.tap_step = p.kw; j.nt = p.t_group; } // group = one kx, all ky
     else { j.tap0 = tg * p.t_group; j.tap_step = 1; j.nt = min(p.t_group, p.taps - j.tap0); }
     j.k_begin = p.kblocks * ks / p.ksplit;
     j.k_end = p.kblocks * (ks + 1) / p.ksplit;
@@ -129,12 +140,27 @@ wgrad_kernel(const __grid_constant__ CUtensorMap map_s, const __grid_constant__ 
                     const int x0 = tx * p.tw, y0 = ty * p.th, n0 = tz * p.tn;
                     mbar_wait(aempty_bar(sa), pha ^ 1);
                     mbar_expect_tx(afull_bar(sa), p.parts * p.a_part_bytes);
-                    for (int pa = 0; pa < p.parts; pa++)
-                        for (int ch = 0; ch < 2; ch++)
-                            tma_load_5d(smem_base + sa * p.a_stage_bytes + pa * p.a_part_bytes + ch * kChunkBytes, &map_s, afull_bar(sa),
-                                        j.ab * 128 + ch * 64, x0, y0, n0, pa);
+                    if (p.pair) {
+                        for (int pa = 0; pa < p.parts; pa++)        // S slab: the view of tap ky starts kh - 1 - ky rows into it
+                            tma_load_5d(smem_base + sa * p.a_stage_bytes + pa * p.a_part_bytes, &map_s, afull_bar(sa),
+                                        0, x0, y0 + p.pad_y - (p.kh - 1), n0, pa);
+                    } else {
+                        for (int pa = 0; pa < p.parts; pa++)
+                            for (int ch = 0; ch < 2; ch++)
+                                tma_load_5d(smem_base + sa * p.a_stage_bytes + pa * p.a_part_bytes + ch * kChunkBytes, &map_s, afull_bar(sa),
+                                            j.ab * 128 + ch * 64, x0, y0, n0, pa);
+                    }
                     if (++sa == SA) { sa = 0; pha ^= 1; }
-                    if (p.reuse) {
+                    if (p.pair) {
+                        for (int pb = 0; pb < p.parts; pb++) {
+                            mbar_wait(bempty_bar(sb), phb ^ 1);
+                            mbar_expect_tx(bfull_bar(sb), p.b_bytes);
+                            for (int kx = 0; kx < p.kw; kx++)       // one L box per horizontal tap
+                                tma_load_5d(b_base + sb * p.b_bytes + kx * p.b_chunk_bytes, &map_l, bfull_bar(sb),
+                                            j.bb * 64, x0 + kx - p.pad_x, y0, n0, pb);
+                            if (++sb == SB) { sb = 0; phb ^= 1; }
+                        }
+                    } else if (p.reuse) {
                         const int lx = x0 + j.tap0 - p.pad_x, ly = y0 - p.pad_y;
                         for (int pb = 0; pb < p.parts; pb++) {
                             mbar_wait(bempty_bar(sb), phb ^ 1);
@@ -167,7 +193,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap map_s, const __grid_constant__ 
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
         const bool leader = elect_one();
-        const uint64_t desc_hi = make_smem_desc_mn(kChunkBytes, 1024u);
+        const uint64_t desc_hi = make_smem_desc_mn(p.pair ? p.ky_step_bytes : kChunkBytes, 1024u);
         const uint64_t desc_b_hi = make_smem_desc_mn(p.b_chunk_bytes, 1024u);
         const uint32_t ky16 = p.ky_step_bytes >> 4;
         const uint32_t part16 = p.a_part_bytes >> 4;
@@ -184,7 +210,31 @@ wgrad_kernel(const __grid_constant__ CUtensorMap map_s, const __grid_constant__ 
                 tc_fence_after();
                 const uint32_t a16 = (smem_base + sa * p.a_stage_bytes) >> 4;
                 const uint32_t not_first = kb > j.k_begin ? 1u : 0u;
-                if (p.reuse) {
+                if (p.pair) {
+                    #pragma unroll
+                    for (int pb = 0; pb < 3; pb++) {
+                        if (pb >= parts) break;
+                        mbar_wait(bfull_bar(sb), phb);
+                        tc_fence_after();
+                        const uint64_t db = desc_b_hi | (uint64_t)(((b_base + sb * p.b_bytes) >> 4) & 0x3FFF);
+                        for (int t = 0; t < j.nt; t++) {
+                            const uint32_t tmem_d = tmem_base + (uint32_t)(t * p.block_n);
+                            #pragma unroll
+                            for (int pa = 0; pa < 3; pa++) {
+                                if (pa + pb >= parts) break;
+                                const uint64_t da = desc_hi | (uint64_t)((a16 + pa * part16 + 2 * t * ky16) & 0x3FFF);
+                                if (leader) {
+                                    umma_bf16(tmem_d, da, db, p.idesc, (pb | pa) ? 1u : not_first);
+                                    umma_bf16(tmem_d, da + 128, db + 128, p.idesc, 1);
+                                    umma_bf16(tmem_d, da + 256, db + 256, p.idesc, 1);
+                                    umma_bf16(tmem_d, da + 384, db + 384, p.idesc, 1);
+                                }
+                            }
+                        }
+                        if (leader) umma_commit(bempty_bar(sb));
+                        if (++sb == SB) { sb = 0; phb ^= 1; }
+                    }
+                } else if (p.reuse) {
                     #pragma unroll
                     for (int pb = 0; pb < 3; pb++) {
                         if (pb >= parts) break;
@@ -262,6 +312,22 @@ wgrad_kernel(const __grid_constant__ CUtensorMap map_s, const __grid_constant__ 
                 tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(c * 16), v);
                 const int col = c * 16;
                 const int t = col / p.block_n;
+                if (p.pair) {
+                    // lanes 0-63: tap row kh-1-2t, lanes 64-127: the row above it; columns = kx * 64 + b
+                    const int within = col - t * p.block_n;
+                    const int kx = within >> 6;
+                    const int ky = p.kh - 1 - 2 * t - (quarter >> 1);
+                    const int ap = (quarter & 1) * 32 + lane;
+                    const int b0 = j.bb * 64 + (within & 63);
+                    if (ky >= 0 && ap < p.ca) {
+                        float* dst = p.ws + ((long long)(ky * p.kw + kx) * p.ca + ap) * p.cb_pad + b0;
+                        #pragma unroll
+                        for (int i = 0; i < 16; i += 4)
+                            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};"
+                                         ::"l"(dst + i), "f"(v[i]), "f"(v[i + 1]), "f"(v[i + 2]), "f"(v[i + 3]) : "memory");
+                    }
+                    continue;
+                }
                 const int b0 = j.bb * p.block_n + (col - t * p.block_n);
                 if (a < p.ca && b0 < p.cb_pad) {
                     // workspace [tap][ca][cb_pad]: the 16 columns of this chunk are 64 contiguous bytes -> 4 vector reductions
@@ -340,7 +406,15 @@ extern "C" int pgpp_conv2d_wgrad(const pgpp_wgrad_desc* d, void* stream) {
     // 8-pixel swizzle atoms); everything else takes the widest box that fits the image, then rows, then samples.
     p.reuse = (d->stride == 1 && d->kh > 1 && d->kh * bn <= 512 && d->ws >= 8 && (long long)d->ws * d->hs >= 64 && p.dil_y == 1) ? 1 : 0;
     if (env_flags().wgrad_no_reuse) p.reuse = 0;
-    if (p.reuse) {
+    p.kh = d->kh; p.npairs = (d->kh + 1) / 2;
+    p.pair = (d->ca_pad == 64 && d->stride == 1 && d->kh > 1 && p.dil_y == 1 && d->kw * 64 <= 256 && p.npairs * d->kw * 64 <= 512 &&
+              d->ws >= 8 && (long long)d->ws * d->hl >= 64 && !env_flags().wgrad_no_pair) ? 1 : 0;
+    if (p.pair) {
+        p.reuse = 0;
+        bn = d->kw * 64; p.block_n = bn; p.b_chunks = d->kw;
+        p.tw = d->ws >= 16 ? 16 : 8; p.th = 64 / p.tw; p.tn = 1;
+        p.t_group = p.npairs; p.n_groups = 1;
+    } else if (p.reuse) {
         p.tw = d->ws >= 16 ? 16 : 8; p.th = 64 / p.tw; p.tn = 1;
         p.t_group = d->kh; p.n_groups = d->kw;
     } else {
@@ -353,15 +427,16 @@ extern "C" int pgpp_conv2d_wgrad(const pgpp_wgrad_desc* d, void* stream) {
         p.n_groups = (p.taps + p.t_group - 1) / p.t_group;
     }
     p.tiles_x = (d->ws + p.tw - 1) / p.tw;
-    p.tiles_y = (d->hs + p.th - 1) / p.th;
+    p.tiles_y = ((p.pair ? d->hl : d->hs) + p.th - 1) / p.th;       // pair mode walks the rows of L (see the header)
     p.tiles_n = (d->n + p.tn - 1) / p.tn;
     p.kblocks = (long long)p.tiles_n * p.tiles_x * p.tiles_y;
     p.parts = parts;
     const int l_rows = p.reuse ? p.th + d->kh - 1 : p.th;       // rows of one L box (after the element stride)
+    const int s_rows = p.pair ? p.th + 2 * p.npairs - 1 : p.th; // rows of one S box
     p.b_chunk_bytes = (unsigned)(l_rows * p.tw * p.tn) * 128u;
     p.ky_step_bytes = (unsigned)p.tw * 128u;
     p.a_blks = (d->ca + 127) / 128;
-    p.b_blks = (d->cb + bn - 1) / bn;
+    p.b_blks = p.pair ? (d->cb + 63) / 64 : (d->cb + bn - 1) / bn;
     const long long base_jobs = (long long)p.a_blks * p.b_blks * p.n_groups;
     const int sms = sm_count();
     {
@@ -378,7 +453,7 @@ extern "C" int pgpp_conv2d_wgrad(const pgpp_wgrad_desc* d, void* stream) {
         p.ksplit = best;
     }
     p.total_jobs = base_jobs * p.ksplit;
-    p.a_part_bytes = 2u * kChunkBytes;
+    p.a_part_bytes = p.pair ? (unsigned)(s_rows * p.tw) * 128u : 2u * kChunkBytes;
     p.a_stage_bytes = (unsigned)parts * p.a_part_bytes;
     p.b_bytes = (unsigned)p.b_chunks * p.b_chunk_bytes;
     // instruction descriptor: fp32 accumulate, bf16 A / B, both MN-major (bits 15, 16), N = block_n, M = 128
@@ -395,7 +470,7 @@ extern "C" int pgpp_conv2d_wgrad(const pgpp_wgrad_desc* d, void* stream) {
     const long long smem_max = 227 * 1024;
     p.a_stages = 2; p.b_stages = 2;
     if (smem_need(2, 2) > smem_max) { set_error("tile does not fit shared memory"); return PGPP_ERR_UNSUPPORTED; }
-    const int b_want = 2 * (p.reuse ? 1 : p.t_group) * parts;      // two K blocks of L tiles in flight
+    const int b_want = 2 * ((p.reuse || p.pair) ? 1 : p.t_group) * parts;      // two K blocks of L tiles in flight
     while (p.b_stages < b_want && p.b_stages < 24 && smem_need(p.a_stages, p.b_stages + 1) <= smem_max) p.b_stages++;
     while (p.a_stages < 4 && smem_need(p.a_stages + 1, p.b_stages) <= smem_max) p.a_stages++;
     while (p.b_stages < 24 && smem_need(p.a_stages, p.b_stages + 1) <= smem_max) p.b_stages++;
@@ -408,7 +483,7 @@ extern "C" int pgpp_conv2d_wgrad(const pgpp_wgrad_desc* d, void* stream) {
         const cuuint64_t sp = (cuuint64_t)s_stride * 2;
         const cuuint64_t dims[5] = {(cuuint64_t)d->ca_pad, (cuuint64_t)d->ws, (cuuint64_t)d->hs, (cuuint64_t)d->n, (cuuint64_t)d->s_parts};
         const cuuint64_t strides[4] = {sp, sp * d->ws, sp * d->ws * d->hs, sp * d->ws * d->hs * d->n};
-        const cuuint32_t box[5] = {64, (cuuint32_t)p.tw, (cuuint32_t)p.th, (cuuint32_t)p.tn, 1};
+        const cuuint32_t box[5] = {64, (cuuint32_t)p.tw, (cuuint32_t)s_rows, (cuuint32_t)p.tn, 1};
         const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
         CUresult r = encode(&map_s, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(d->small), dims, strides, box, estr,
                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,

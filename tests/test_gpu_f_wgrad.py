@@ -66,6 +66,56 @@ def test_weight_gradient_vs_float64_autograd(case, prec):
     assert rel_l2(got, want) < TOL[prec], rel_l2(got, want)
 
 
+# n, o, i, h, w, (kh, kw), (pad_y, pad_x), transpose, f16
+PAIR_CASES = [
+    (2, 64, 64, 40, 36, (3, 3), (1, 1), False, False),      # the 64 -> 64 layers: two taps per accumulator, three kx per tile
+    (2, 24, 20, 13, 11, (3, 3), (1, 1), False, False),      # ragged channels and tiles, 8-wide K blocks
+    (1, 64, 192, 20, 48, (3, 3), (1, 1), False, False),     # three column blocks of the larger operand
+    (2, 48, 64, 17, 33, (3, 3), (0, 0), False, False),      # valid convolution: L has more rows / columns than S
+    (2, 64, 64, 16, 16, (3, 3), (2, 2), False, False),      # 'full' padding
+    (2, 32, 32, 24, 16, (3, 1), (1, 0), False, False),      # one filter column
+    (2, 32, 32, 24, 16, (2, 2), (1, 0), False, False),      # even filter: one tap pair, no idle half
+    (2, 32, 32, 24, 20, (4, 2), (1, 1), False, False),      # two full pairs
+    (2, 16, 64, 24, 20, (3, 4), (1, 2), False, False),      # four kx: 256 columns
+    (2, 64, 64, 24, 24, (3, 3), (1, 1), True, False),       # conv_transpose2d: S is the input
+    (2, 64, 64, 40, 36, (3, 3), (1, 1), False, True),       # f16 operands (fp16 layers of the discriminator)
+    (8, 8, 8, 8, 8, (3, 3), (1, 1), False, False),          # smallest image that takes the pair form
+]
+
+
+@pytest.mark.parametrize('case', PAIR_CASES, ids=[str(c) for c in PAIR_CASES])
+@pytest.mark.parametrize('prec', ['bf16x2', 'bf16x3'])
+def test_weight_gradient_tap_pair_form(case, prec):
+    """at most 64 channels on the accumulator-lane side: two vertical taps share the 128 lanes (the A descriptor's leading byte offset is one
+    row of the S slab) and the horizontal taps sit side by side in the tile - against float64 autograd and against the one-tap-per-accumulator
+    form of the same kernel (PGPP_WGRAD_NO_PAIR)"""
+    import os
+    n, o, i, h, w, (kh, kw), (py, px), tr, f16 = case
+    if f16 and prec != 'bf16x2':
+        pytest.skip('f16 operands have one precision')
+    g = torch.Generator().manual_seed(45)
+    x = torch.randn(n, i, h, w, generator=g)
+    wshape = (i, o, kh, kw) if tr else (o, i, kh, kw)
+    wt = torch.zeros(*wshape, dtype=torch.float64, requires_grad=True)
+    dt = torch.float16 if f16 else torch.float32
+    x = x.to(dt)
+    y = F.conv_transpose2d(x.double(), wt, padding=(py, px)) if tr else F.conv2d(x.double(), wt, padding=(py, px))
+    dy = torch.randn(y.shape, generator=g).to(dt)
+    want = torch.autograd.grad(y, wt, dy.double())[0]
+    kw_ = dict(precision='f16' if f16 else prec, out_dtype=torch.float32)
+    got = cg.weight_gradient(dy.to(DEV), x.to(DEV), wshape, 1, (py, px), tr, **kw_)
+    os.environ['PGPP_WGRAD_NO_PAIR'] = '1'
+    custom_ops.refresh_env()
+    try:
+        old = cg.weight_gradient(dy.to(DEV), x.to(DEV), wshape, 1, (py, px), tr, **kw_)
+    finally:
+        del os.environ['PGPP_WGRAD_NO_PAIR']
+        custom_ops.refresh_env()
+    tol = 1e-5 if f16 else TOL[prec]      # f16 operands are exact inputs here: only the fp32 accumulation order differs
+    assert tuple(got.shape) == wshape and rel_l2(got.float(), want) < tol, rel_l2(got.float(), want)
+    assert rel_l2(got.float(), old.float()) < tol, rel_l2(got.float(), old.float())
+
+
 def test_weight_gradient_is_linear_and_matches_library_at_full_size():
     """Full-size layer (128 -> 128 channels, 3x3, 256 x 256, batch 8: the generator's dominant layer): compared with the
     library's fp32 weight gradient (TF32 off) and checked for linearity dW(a*dy1 + dy2) = a*dW(dy1) + dW(dy2)."""
