@@ -106,6 +106,18 @@ PGPP_API int pgpp_pack_activations_slice(const void* x, const int64_t size[4], c
 PGPP_API int pgpp_pack_activations_f16(const void* x, const int64_t size[4], const int64_t stride[4], int dtype,
                           const float* scale, void* out, int c_pad, int c_total, int c_off, void* stream);
 
+/* Gradient of a bias_act that was fused into a convolution's epilogue, written straight into the operand format of the data- /
+ * weight-gradient kernels: out = pgpp_pack_activations(dy * act'(.) * gain, zero where the clamp was active), act'(.) and the clamp
+ * gate taken from the saved OUTPUT y - what BiasActCudaGrad.forward (bias_act.py:170-186, bias_act.cu:38-146 with grad = 1)
+ * followed by a packing pass produce, bit for bit (the value is rounded through the tensor's dtype like the stored gradient is),
+ * without the NCHW intermediate.  linear / relu / lrelu only (derivative from the output).  dy and y: same dtype (f32 / f16 / bf16),
+ * same NCHW-like strides (pixel-contiguous).  csum (optional): float32 [N][C][pgpp_pack_act_gradient_tiles(H, W)] per-tile channel
+ * sums of that gradient; their sum over N and tiles is the bias gradient (bias_act.py:135), deterministic.  f16: one IEEE-half part. */
+PGPP_API int pgpp_pack_act_gradient(const void* dy, const void* y, const int64_t size[4], const int64_t stride[4], int dtype,
+                          int act_fn, float alpha, float gain, float clamp, void* out, int c_pad, int parts, int f16,
+                          float* csum, void* stream);
+PGPP_API int pgpp_pack_act_gradient_tiles(int h, int w);
+
 /* Per-sample modulated weights: out[n][p][row][c] = part p of bf16-split(master[row][c] * s[n][c]) for c < c_in,
  * zero for c_in <= c < c_pad (training/networks.py:65-66, w * styles).  master float32 [rows][c_pad], s float32 [N][c_in]. */
 PGPP_API int pgpp_modulate_weights(const float* master, const float* s, void* out, int n, int64_t rows, int c_pad, int c_in,

@@ -13,6 +13,9 @@ struct PackArgs {
     long long s_n, s_c, s_h, s_w;
     long long part_stride;      // elements between parts = n*h*w*c_pad
     int f16;                    // 1: the operand is IEEE half (one part) instead of the bf16 expansion (fp16 layers, native f16 MMA)
+    // gradient of a fused bias_act (pgpp_pack_act_gradient): x = dy, gate = the saved output y (same dtype and strides)
+    const void* gate; int act; float alpha, gain, clamp;
+    float* csum;                // [N][C][x_tiles * y_tiles] per-tile channel sums of the packed gradient (the bias gradient), or NULL
 };
 
 __device__ __forceinline__ void split_store(float v, __nv_bfloat16* dst, long long part_stride, int parts, int f16 = 0) {
@@ -105,7 +108,23 @@ static TileGeom tile_geometry(int h, int w, int c_pad) {
 }
 
 // VEC: float source, W % 4 == 0, all strides and the base pointer 16-byte aligned -> one 128-bit load per channel
-template <class T, bool VEC>
+// the stored value of the stand-alone gradient kernel (rounded to the tensor's dtype), so that the fused pass is bit-identical to it
+template <class T> __device__ __forceinline__ float round_through(float v) { return v; }
+template <> __device__ __forceinline__ float round_through<__half>(float v) { return __half2float(__float2half_rn(v)); }
+template <> __device__ __forceinline__ float round_through<__nv_bfloat16>(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
+
+// dy -> dy * act'(.) * gain with the clamp gate, from the saved OUTPUT y (act.cuh, G == 1; linear / relu / lrelu)
+__device__ __forceinline__ float act_gradient_from_output(float dy, float y, int act, float alpha, float gain, float clamp) {
+    const float yy = (gain != 0.f) ? y / gain : 0.f;
+    float v = dy;
+    if (act == PGPP_ACT_RELU) v = yy > 0.f ? dy : 0.f;
+    else if (act == PGPP_ACT_LRELU) v = yy > 0.f ? dy : dy * alpha;
+    v *= gain;
+    if (clamp >= 0.f) v = (y > -clamp && y < clamp) ? v : 0.f;
+    return v;
+}
+
+template <class T, bool VEC, bool GATE = false>
 __global__ void __launch_bounds__(256) pack_nchw_kernel(PackArgs p, TileGeom g) {
     extern __shared__ uint4 sm_packets[];
     int xt, yt, ct, n;
@@ -144,6 +163,39 @@ __global__ void __launch_bounds__(256) pack_nchw_kernel(PackArgs p, TileGeom g) 
                 #pragma unroll
                 for (int k = 0; k < 4; k++) v[i][k] *= sc;
             }
+            if constexpr (GATE) {
+                const T* gsrc = (const T*)p.gate + n * p.s_n + y * p.s_h + x + c * p.s_c;
+                float gq[4] = {0.f, 0.f, 0.f, 0.f};
+                if (VEC) {
+                    if (x < p.w) {
+                        if constexpr (sizeof(T) == 4) {
+                            const float4 q = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(gsrc));
+                            gq[0] = q.x; gq[1] = q.y; gq[2] = q.z; gq[3] = q.w;
+                        } else if constexpr (sizeof(T) == 2) {
+                            const uint2 q = *reinterpret_cast<const uint2*>(gsrc);
+                            const T* h4 = reinterpret_cast<const T*>(&q);
+                            #pragma unroll
+                            for (int k = 0; k < 4; k++) gq[k] = (float)to_acc<T>(h4[k]);
+                        }
+                    }
+                } else {
+                    #pragma unroll
+                    for (int k = 0; k < 4; k++)
+                        if (x + k < p.w) gq[k] = (float)to_acc<T>(gsrc[k]);
+                }
+                #pragma unroll
+                for (int k = 0; k < 4; k++)
+                    v[i][k] = round_through<T>(act_gradient_from_output(v[i][k], gq[k], p.act, p.alpha, p.gain, p.clamp));
+            }
+        }
+        if constexpr (GATE) {
+            if (p.csum) {       // pixels outside the image and channels beyond C hold zeros
+                float sum = (v[i][0] + v[i][1]) + (v[i][2] + v[i][3]);
+                #pragma unroll
+                for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+                if (lane == 0 && c < p.c)
+                    p.csum[((long long)n * p.c + c) * ((long long)g.x_tiles * g.y_tiles) + (long long)yt * g.x_tiles + xt] = sum;
+            }
         }
     }
     emit_tile(v, sm_packets, p.parts, p.out, p.part_stride, n, p.h, p.w, y0, x0, g.log_tw, c0, p.c_pad, p.c_total, p.c_off, p.f16);
@@ -177,9 +229,13 @@ static int launch_pack(const PackArgs& p, cudaStream_t stream) {
         // 128-bit loads: rows 16-byte aligned and either W % 4 == 0 or a row pitch that covers the last (partial) group of 4
         const bool vec = sizeof(T) <= 4 && (p.w % 4 == 0 || p.s_h >= (p.w + 3) / 4 * 4) && p.s_c % 4 == 0 && p.s_h % 4 == 0 && p.s_n % 4 == 0 &&
                          ((uintptr_t)p.x & (4 * sizeof(T) - 1)) == 0;
-        if (vec) pack_nchw_kernel<T, true><<<(unsigned)blocks, 256, smem, stream>>>(p, g);
+        if (p.gate) {
+            if (vec) pack_nchw_kernel<T, true, true><<<(unsigned)blocks, 256, smem, stream>>>(p, g);
+            else pack_nchw_kernel<T, false, true><<<(unsigned)blocks, 256, smem, stream>>>(p, g);
+        } else if (vec) pack_nchw_kernel<T, true><<<(unsigned)blocks, 256, smem, stream>>>(p, g);
         else pack_nchw_kernel<T, false><<<(unsigned)blocks, 256, smem, stream>>>(p, g);
     } else {
+        PGPP_REQUIRE(!p.gate, "pgpp_pack_act_gradient needs pixel-contiguous (NCHW) tensors");
         const long long total = (long long)p.n * p.h * p.w * p.c_pad;
         long long blocks = (total + 255) / 256;
         const long long cap = (long long)sm_count() * occupancy_of(pack_generic_kernel<T>, 256, 0);
@@ -649,8 +705,30 @@ extern "C" int pgpp_modulate_weights(const float* master, const float* s, void* 
     return PGPP_OK;
 }
 
-namespace pgpp { static int pack_slice(const void* x, const int64_t size[4], const int64_t stride[4], int dtype, const float* scale, void* out,
-                                       int c_pad, int c_total, int c_off, int parts, int f16, void* stream); }
+namespace pgpp {
+struct PackGate { const void* y; int act; float alpha, gain, clamp; float* csum; };
+static int pack_slice(const void* x, const int64_t size[4], const int64_t stride[4], int dtype, const float* scale, void* out,
+                      int c_pad, int c_total, int c_off, int parts, int f16, void* stream, const PackGate* gate = nullptr);
+}
+
+extern "C" int pgpp_pack_act_gradient_tiles(int h, int w) {
+    const pgpp::TileGeom g = pgpp::tile_geometry(h, w, 64);
+    return g.x_tiles * g.y_tiles;
+}
+
+extern "C" int pgpp_pack_act_gradient(const void* dy, const void* y, const int64_t size[4], const int64_t stride[4], int dtype,
+                                      int act_fn, float alpha, float gain, float clamp, void* out, int c_pad, int parts, int f16,
+                                      float* csum, void* stream) {
+    using namespace pgpp;
+    PGPP_REQUIRE(dy && y, "dy and y must be device pointers");
+    PGPP_REQUIRE(act_fn == PGPP_ACT_LINEAR || act_fn == PGPP_ACT_RELU || act_fn == PGPP_ACT_LRELU,
+                 "pgpp_pack_act_gradient: the activation's derivative must depend on its output only (linear, relu, lrelu)");
+    PGPP_REQUIRE(dtype == PGPP_F32 || dtype == PGPP_F16 || dtype == PGPP_BF16, "pgpp_pack_act_gradient: dtype must be f32, f16 or bf16");
+    PGPP_REQUIRE(stride[3] == 1 && stride[1] != 1, "pgpp_pack_act_gradient needs pixel-contiguous (NCHW) tensors");
+    PGPP_REQUIRE(!f16 || parts == 1, "fp16 operands are a single part");
+    PackGate gate{y, act_fn, alpha, gain, clamp, csum};
+    return pack_slice(dy, size, stride, dtype, nullptr, out, c_pad, c_pad, 0, parts, f16, stream, &gate);
+}
 
 extern "C" int pgpp_pack_activations_slice(const void* x, const int64_t size[4], const int64_t stride[4], int dtype,
                                            const float* scale, void* out, int c_pad, int c_total, int c_off, int parts, void* stream) {
@@ -663,7 +741,7 @@ extern "C" int pgpp_pack_activations_f16(const void* x, const int64_t size[4], c
 }
 
 int pgpp::pack_slice(const void* x, const int64_t size[4], const int64_t stride[4], int dtype, const float* scale, void* out,
-                     int c_pad, int c_total, int c_off, int parts, int f16, void* stream) {
+                     int c_pad, int c_total, int c_off, int parts, int f16, void* stream, const PackGate* gate) {
     PGPP_REQUIRE(x && out, "x and out must be device pointers");
     PGPP_REQUIRE(parts >= 1 && parts <= 3, "parts must be 1, 2 or 3");
     PGPP_REQUIRE(c_pad >= size[1] && c_pad % 16 == 0, "c_pad must be a multiple of 16 and >= C");
@@ -675,6 +753,8 @@ int pgpp::pack_slice(const void* x, const int64_t size[4], const int64_t stride[
     p.c_pad = c_pad; p.parts = parts; p.f16 = f16;
     p.s_n = stride[0]; p.s_c = stride[1]; p.s_h = stride[2]; p.s_w = stride[3];
     p.part_stride = (long long)p.n * p.h * p.w * c_total;
+    p.gate = nullptr; p.act = PGPP_ACT_LINEAR; p.alpha = 0.f; p.gain = 1.f; p.clamp = -1.f; p.csum = nullptr;
+    if (gate) { p.gate = gate->y; p.act = gate->act; p.alpha = gate->alpha; p.gain = gate->gain; p.clamp = gate->clamp; p.csum = gate->csum; }
     if (p.part_stride == 0) return PGPP_OK;
     cudaStream_t s = (cudaStream_t)stream;
     switch (dtype) {

@@ -87,6 +87,10 @@ def load_library():
     lib.pgpp_pack_weights.argtypes = [vp, i32, c_i64x4, c_i64x4, i32, i32, f32, i32, i32, vp, i32, vp, vp, i32, i32, i32, i32, i32, vp]
     lib.pgpp_up2_weight_adjoint.restype = i32
     lib.pgpp_up2_weight_adjoint.argtypes = [vp, vp, i32, i32, i32, i32, vp, vp]
+    lib.pgpp_pack_act_gradient.restype = i32
+    lib.pgpp_pack_act_gradient.argtypes = [vp, vp, c_i64x4, c_i64x4, i32, i32, f32, f32, f32, vp, i32, i32, i32, vp, vp]
+    lib.pgpp_pack_act_gradient_tiles.restype = i32
+    lib.pgpp_pack_act_gradient_tiles.argtypes = [i32, i32]
     lib.pgpp_sum_hw.restype = i32
     lib.pgpp_sum_hw.argtypes = [vp, i32, vp, i32, i32, i64, vp]
     lib.pgpp_mul_reduce_hw.restype = i32
@@ -132,7 +136,7 @@ def load_library():
 
 
 EXPORTED_SYMBOLS = ('pgpp_version', 'pgpp_last_error', 'pgpp_launch_count', 'pgpp_refresh_env', 'pgpp_bias_act', 'pgpp_upfirdn2d',
-                    'pgpp_modconv_demod_coefs', 'pgpp_pack_activations', 'pgpp_pack_activations_slice', 'pgpp_pack_activations_f16',
+                    'pgpp_modconv_demod_coefs', 'pgpp_pack_activations', 'pgpp_pack_activations_slice', 'pgpp_pack_activations_f16', 'pgpp_pack_act_gradient', 'pgpp_pack_act_gradient_tiles',
                     'pgpp_pack_weights', 'pgpp_up2_weight_adjoint', 'pgpp_mul_reduce_hw', 'pgpp_sum_hw', 'pgpp_modulate_weights',
                     'pgpp_spade_modulate_pack', 'pgpp_mix_pack', 'pgpp_conv2d_direct', 'pgpp_fir_pack', 'pgpp_fir_packed', 'pgpp_fir_packed_act', 'pgpp_conv1x1_thin', 'pgpp_pack_im2col', 'pgpp_conv2d_igemm', 'pgpp_conv2d_igemm_stats_rows', 'pgpp_instnorm_finalize', 'pgpp_conv2d_wgrad', 'pgpp_u8_to_f32',
                     'pgpp_image_to_u8', 'pgpp_grid_sample_2d', 'pgpp_grid_sample_2d_backward')
@@ -306,6 +310,22 @@ class _ConvPlugin:
             _check(lib.pgpp_pack_activations(_ptr(x), c_i64x4(*x.shape), c_i64x4(*x.stride()), dtype_code(x.dtype),
                                              _ptr(scale), _ptr(out), int(c_pad), int(parts), _stream(x)))
         return out
+
+    @staticmethod
+    def pack_act_gradient(dy, y, act_idx, alpha, gain, clamp, c_pad, parts, f16=False, want_sums=False):
+        """operand-format copy of the gradient of a fused bias_act, from dy and the saved output y (see pgpp_pack_act_gradient);
+        -> (packed [parts, N, H, W, c_pad], per-tile channel sums float32 [N, C, tiles] or None)"""
+        lib = load_library()
+        _torch_check(dy.is_cuda and dy.dim() == 4 and dy.shape == y.shape and dy.dtype == y.dtype and dy.stride() == y.stride(),
+                     'dy and y must be rank-4 CUDA tensors of the same shape, dtype and strides')
+        n, c, h, w = dy.shape
+        out = torch.empty([1 if f16 else parts, n, h, w, c_pad], dtype=torch.float16 if f16 else torch.bfloat16, device=dy.device)
+        sums = torch.empty([n, c, lib.pgpp_pack_act_gradient_tiles(h, w)], dtype=torch.float32, device=dy.device) if want_sums else None
+        with torch.cuda.device(dy.device):
+            _check(lib.pgpp_pack_act_gradient(_ptr(dy), _ptr(y), c_i64x4(*dy.shape), c_i64x4(*dy.stride()), dtype_code(dy.dtype), int(act_idx),
+                                              float(alpha), float(gain), float(clamp), _ptr(out), int(c_pad), 1 if f16 else int(parts), int(bool(f16)),
+                                              _ptr(sums), _stream(dy)))
+        return out, sums
 
     @staticmethod
     def pack_weights(weight, out, master, *, transpose_io=False, flip=False, scale=1.0, phases=1, phase_stride=0, fir=None, flip_filter=False,

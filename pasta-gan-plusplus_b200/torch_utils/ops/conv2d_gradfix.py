@@ -717,6 +717,8 @@ def _forward_conv(x, weight, bias, stride, padding, keep=False, scale=1.0, epi=N
     return (y, xp) if keep else y
 
 
+FUSE_ACT_GRAD_PACK = True      # plain backward of a convolution with a fused bias_act: dy * act'(y) straight into the operand format (pgpp_pack_act_gradient)
+
 TCONV_PHASES = True      # stride-2 transposed convolutions (the data gradient of every down-sampling convolution) as four per-phase convolutions of
                          # the un-stuffed input at 1x the MACs; False: zero insertion + one convolution over the 4x larger tensor (the round-1 form)
 
@@ -910,24 +912,42 @@ def _conv2d_gradfix(transpose, weight_shape, stride, padding, output_padding, di
         def backward(ctx, grad_output):
             input, weight = ctx.saved_tensors[:2]
             grad_input = grad_weight = grad_bias = None
+            want_w = ctx.needs_input_grad[1] and not weight_gradients_disabled
+            plain = not torch.is_grad_enabled() and keep_packed_operands
+            go_shape, go_dtype = grad_output.shape, grad_output.dtype
+            # the packed copy of grad_output feeds the data-gradient kernel where that one reads the operand format, and the weight gradient
+            go_feeds_dgrad = ctx.needs_input_grad[0] and (transpose or stride[0] == 1 or (TCONV_PHASES and stride[0] == 2))
+            go = None
             if epi_grad is not None:        # through the fused bias_act first: everything below sees the gradient of the pre-activation
                 y = ctx.saved_tensors[2] if epi_keep_y else epi_null
-                mf = torch.channels_last if (epi_keep_y and y.stride(1) == 1 and y.shape[1] > 1) else torch.contiguous_format
-                grad_output = epi_grad.apply(grad_output.contiguous(memory_format=mf), epi_null, epi_null, y)
-            want_w = ctx.needs_input_grad[1] and not weight_gradients_disabled
-            if not torch.is_grad_enabled() and keep_packed_operands:
+                if (plain and FUSE_ACT_GRAD_PACK and epi_keep_y and (want_w or go_feeds_dgrad) and (go_feeds_dgrad or not ctx.needs_input_grad[0])
+                        and grad_output.dtype in (torch.float32, torch.float16, torch.bfloat16) and y.dtype == grad_output.dtype
+                        and y.is_contiguous() and y.shape[1] > 1):
+                    # plain backward pass: dy * act'(y) goes straight into the operand format (one pass over dy and y; the NCHW gradient of
+                    # the pre-activation is never written), the bias gradient from the same pass
+                    prec = precision_for(go_dtype)
+                    data, sums = _plugin.pack_act_gradient(grad_output.contiguous(), y, _ACT_IDX[epi['act']], epi['alpha'], epi['gain'], epi['clamp'],
+                                                           _round_up(go_shape[1], 64), _PRODUCTS[prec][1], f16=prec == 'f16',
+                                                           want_sums=ctx.needs_input_grad[2])
+                    go = PackedAct(data, go_shape[1])
+                    if ctx.needs_input_grad[2]:
+                        grad_bias = sums.sum([0, 2]).to(go_dtype)
+                    grad_output = None
+                else:
+                    mf = torch.channels_last if (epi_keep_y and y.stride(1) == 1 and y.shape[1] > 1) else torch.contiguous_format
+                    grad_output = epi_grad.apply(grad_output.contiguous(memory_format=mf), epi_null, epi_null, y)
+            if plain:
                 # plain backward pass (no graph is being recorded): grad_output is packed once and feeds both the data-gradient and
                 # the weight-gradient kernel; the weight gradient reads the input operand the forward pass kept
-                prec = precision_for(grad_output.dtype)
-                go = None
-                if want_w or (ctx.needs_input_grad[0] and (transpose or stride[0] == 1 or (TCONV_PHASES and stride[0] == 2))):
+                prec = precision_for(go_dtype)
+                if go is None and (want_w or go_feeds_dgrad):
                     go = pack_operand(grad_output, prec)
                 if ctx.needs_input_grad[0]:
-                    p = calc_output_padding(input_shape=input.shape, output_shape=grad_output.shape)
+                    p = calc_output_padding(input_shape=input.shape, output_shape=go_shape)
                     if transpose:       # gradient of conv_transpose2d = conv2d of grad_output with the same weight
                         grad_input = _forward_conv(go, weight, None, stride, padding, scale=weight_scale)
                     else:               # gradient of conv2d = conv_transpose2d (zero insertion first when strided)
-                        grad_input = _forward_conv_transpose(go if (stride[0] == 1 or (TCONV_PHASES and go is not None)) else grad_output, weight, None,
+                        grad_input = _forward_conv_transpose(go if go_feeds_dgrad else grad_output, weight, None,
                                                              stride, padding, p, scale=weight_scale)
                     assert grad_input.shape == input.shape
                 if want_w:
@@ -951,7 +971,7 @@ def _conv2d_gradfix(transpose, weight_shape, stride, padding, output_padding, di
                     if grad_weight.dtype != weight.dtype:
                         grad_weight = grad_weight.to(weight.dtype)
                     assert grad_weight.shape == weight_shape
-            if ctx.needs_input_grad[2]:
+            if ctx.needs_input_grad[2] and grad_bias is None:
                 if (grad_output.is_contiguous() and grad_output.dtype in (torch.float32, torch.float16, torch.bfloat16) and
                         grad_output.shape[2] * grad_output.shape[3] >= 1024 and not (torch.is_grad_enabled() and grad_output.requires_grad)):
                     grad_bias = _plugin.sum_hw(grad_output).sum(0).to(grad_output.dtype)

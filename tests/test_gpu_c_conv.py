@@ -480,3 +480,36 @@ def test_training_conv_with_fused_bias_act(k, down, act, clamp, bias, dtype):
         gp = torch.autograd.grad(loss, [w64] + ([b64] if bias else []))
         for a, r, tol, name in zip(fused, [yr, gx] + list(gp), ftol, names):
             assert rel_l2(a, r) < tol, ('float64', name, rel_l2(a, r))
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.float16])
+@pytest.mark.parametrize('k,down,act,clamp,hw', [(3, 1, 'lrelu', None, (40, 36)), (3, 2, 'lrelu', 256, (40, 36)), (1, 1, 'linear', 256, (33, 19)),
+                                                (3, 1, 'relu', None, (16, 128)), (3, 1, 'linear', None, (9, 7))])
+def test_act_gradient_packed_in_one_pass_is_bit_identical(k, down, act, clamp, hw, dtype):
+    """plain backward of a convolution with a fused bias_act: pgpp_pack_act_gradient (dy * act'(y) straight into the operand format, bias
+    gradient from per-tile channel sums of the same pass) against bias_act's gradient kernel + packing pass + pgpp_sum_hw: the operand is
+    the same bit for bit, so the input gradient is identical; the weight and bias gradients differ by summation order only"""
+    syn = importlib.import_module('pgpp_b200.training.synthesis')
+    cg.fp32_precision = 'bf16x2'
+    torch.manual_seed(90 + k + down)
+    layer = syn.Conv2dLayer(24, 40, k, activation=act, down=down, conv_clamp=clamp).to(DEV)
+    with torch.no_grad():
+        layer.bias.copy_(torch.randn(40) * 0.5)
+    x0 = (torch.randn(3, 24, *hw, device=DEV) * (60.0 if clamp else 1.0)).to(dtype)
+    res = {}
+    for fuse in (None, True, False):        # first pass: fills the packed-weight caches, so that the launch counts below compare like with like
+        cg.FUSE_ACT_GRAD_PACK = bool(fuse)
+        try:
+            x = x0.clone().requires_grad_(True)
+            before = custom_ops.launch_count()
+            y = layer(x, fused=False)
+            probe = torch.randn(y.shape, device=DEV, generator=torch.Generator(DEV).manual_seed(5)).to(dtype)
+            gx, gw, gb = torch.autograd.grad((y * probe).float().sum(), [x, layer.weight, layer.bias])
+            res[fuse] = (gx, gw, gb, custom_ops.launch_count() - before)
+        finally:
+            cg.FUSE_ACT_GRAD_PACK = True
+    assert torch.equal(res[True][0], res[False][0])
+    assert rel_l2(res[True][1], res[False][1]) < 1e-6       # split-K partial sums meet in fp32 atomics: same operands, free summation order
+    assert rel_l2(res[True][2].float(), res[False][2].float()) < (2e-3 if dtype == torch.float16 else 1e-5)
+    identity = act == 'linear' and clamp is None        # nothing to fuse: the gradient of the pre-activation is dy
+    assert res[True][3] < res[False][3] or (identity and res[True][3] == res[False][3])
