@@ -113,16 +113,31 @@ template <class T> __device__ __forceinline__ float round_through(float v) { ret
 template <> __device__ __forceinline__ float round_through<__half>(float v) { return __half2float(__float2half_rn(v)); }
 template <> __device__ __forceinline__ float round_through<__nv_bfloat16>(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
 
-// dy -> dy * act'(.) * gain with the clamp gate, from the saved OUTPUT y (act.cuh, G == 1; linear / relu / lrelu)
-__device__ __forceinline__ float act_gradient_from_output(float dy, float y, int act, float alpha, float gain, float clamp) {
-    const float yy = (gain != 0.f) ? y / gain : 0.f;
-    float v = dy;
-    if (act == PGPP_ACT_RELU) v = yy > 0.f ? dy : 0.f;
-    else if (act == PGPP_ACT_LRELU) v = yy > 0.f ? dy : dy * alpha;
-    v *= gain;
-    if (clamp >= 0.f) v = (y > -clamp && y < clamp) ? v : 0.f;
-    return v;
+// dy -> dy * act'(.) * gain with the clamp gate, from the saved OUTPUT y (act.cuh, G == 1; linear / relu / lrelu), branch-free.
+// neg_slope = 1 / 0 / alpha for linear / relu / lrelu.  The kernel's test `y / gain > 0` is taken from the signs of y and gain (no
+// division per element; they differ only where y / gain underflows to zero).
+struct GateConsts { float neg_slope, gain, clamp; bool gain_pos, gain_neg, clamped; };
+__device__ __forceinline__ GateConsts gate_consts(int act, float alpha, float gain, float clamp) {
+    GateConsts k;
+    k.neg_slope = act == PGPP_ACT_RELU ? 0.f : (act == PGPP_ACT_LRELU ? alpha : 1.f);
+    k.gain = gain; k.clamp = clamp; k.gain_pos = gain > 0.f; k.gain_neg = gain < 0.f; k.clamped = clamp >= 0.f;
+    return k;
 }
+__device__ __forceinline__ float act_gradient_from_output(float dy, float y, const GateConsts& k) {
+    const bool pos = k.gain_pos ? y > 0.f : (k.gain_neg && y < 0.f);
+    float v = (pos ? dy : dy * k.neg_slope) * k.gain;
+    const bool inside = !k.clamped || (y > -k.clamp && y < k.clamp);
+    return inside ? v : 0.f;
+}
+
+template <class T> struct RawVec4 { typedef uint2 type; };          // 4 consecutive pixels of a 16-bit tensor
+template <> struct RawVec4<float> { typedef float4 type; };
+template <> struct RawVec4<double> { typedef float4 type; };        // never loaded (VEC is false for 64-bit sources)
+template <class T> __device__ __forceinline__ float raw_get(const typename RawVec4<T>::type& q, int k) {
+    return (float)to_acc<T>(reinterpret_cast<const T*>(&q)[k]);
+}
+template <> __device__ __forceinline__ float raw_get<float>(const float4& q, int k) { return reinterpret_cast<const float*>(&q)[k]; }
+template <> __device__ __forceinline__ float raw_get<double>(const float4& q, int k) { return reinterpret_cast<const float*>(&q)[k]; }
 
 template <class T, bool VEC, bool GATE = false>
 __global__ void __launch_bounds__(256) pack_nchw_kernel(PackArgs p, TileGeom g) {
@@ -135,67 +150,101 @@ __global__ void __launch_bounds__(256) pack_nchw_kernel(PackArgs p, TileGeom g) 
     const int y = y0 + ((4 * lane) >> g.log_tw), x = x0 + ((4 * lane) & tw_mask);
     const T* src = (const T*)p.x + n * p.s_n + y * p.s_h + x;
     float v[8][4];
-    #pragma unroll
-    for (int i = 0; i < 8; i++) {
-        const int c = c0 + warp * 8 + i;
+    if constexpr (VEC) {
+        // vector loads: ALL loads of a channel group are issued before the first use - no branch, no conversion and no store between them
+        // (a load per basic block, converted on arrival, is eight dependent round trips per thread; with the gate operand sixteen) -
+        // then, for the gradient pass, dy * act'(y) * gain without a branch
+        typedef typename RawVec4<T>::type Raw;
+        constexpr int GROUP = (GATE && sizeof(T) == 4) ? 4 : 8;         // channels per load phase (registers)
+        const GateConsts gk = gate_consts(p.act, p.alpha, p.gain, p.clamp);
+        const T* gsrc = GATE ? (const T*)p.gate + n * p.s_n + y * p.s_h + x : nullptr;
+        const float* scp = p.scale ? p.scale + (long long)n * p.c : nullptr;
+        const bool px_ok = y < p.h && x < p.w;
         #pragma unroll
-        for (int k = 0; k < 4; k++) v[i][k] = 0.f;
-        if (c < p.c && y < p.h) {
-            if (VEC) {
-                if (x < p.w) {
-                    if constexpr (sizeof(T) == 4) {
-                        const float4 q = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(src) + c * p.s_c);
-                        v[i][0] = q.x; v[i][1] = q.y; v[i][2] = q.z; v[i][3] = q.w;
-                    } else if constexpr (sizeof(T) == 2) {            // 16-bit source: 4 pixels = one 64-bit load
-                        const uint2 q = *reinterpret_cast<const uint2*>(src + c * p.s_c);
-                        const T* h4 = reinterpret_cast<const T*>(&q);
-                        #pragma unroll
-                        for (int k = 0; k < 4; k++) v[i][k] = (float)to_acc<T>(h4[k]);
-                    }
-                }
-            } else {
-                #pragma unroll
-                for (int k = 0; k < 4; k++)
-                    if (x + k < p.w) v[i][k] = (float)to_acc<T>(src[c * p.s_c + k]);
+        for (int i0 = 0; i0 < 8; i0 += GROUP) {
+            Raw rd[GROUP], rg[GATE ? GROUP : 1];
+            float sc[GROUP];
+            #pragma unroll
+            for (int i = 0; i < GROUP; i++) {
+                const int c = c0 + warp * 8 + i0 + i;
+                const bool ok = px_ok && c < p.c;
+                const long long off = ok ? c * p.s_c : 0;
+                rd[i] = *reinterpret_cast<const Raw*>(ok ? src + off : (const T*)p.x);       // always a valid address; masked below
+                if constexpr (GATE) rg[i] = *reinterpret_cast<const Raw*>(ok ? gsrc + off : (const T*)p.gate);
+                sc[i] = (scp != nullptr && ok) ? scp[c] : 1.f;
             }
-            if (p.scale) {
-                const float sc = p.scale[n * p.c + c];
+            #pragma unroll
+            for (int i = 0; i < GROUP; i++) {
+                const bool ok = px_ok && c0 + warp * 8 + i0 + i < p.c;
                 #pragma unroll
-                for (int k = 0; k < 4; k++) v[i][k] *= sc;
-            }
-            if constexpr (GATE) {
-                const T* gsrc = (const T*)p.gate + n * p.s_n + y * p.s_h + x + c * p.s_c;
-                float gq[4] = {0.f, 0.f, 0.f, 0.f};
-                if (VEC) {
-                    if (x < p.w) {
-                        if constexpr (sizeof(T) == 4) {
-                            const float4 q = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(gsrc));
-                            gq[0] = q.x; gq[1] = q.y; gq[2] = q.z; gq[3] = q.w;
-                        } else if constexpr (sizeof(T) == 2) {
-                            const uint2 q = *reinterpret_cast<const uint2*>(gsrc);
-                            const T* h4 = reinterpret_cast<const T*>(&q);
-                            #pragma unroll
-                            for (int k = 0; k < 4; k++) gq[k] = (float)to_acc<T>(h4[k]);
-                        }
-                    }
-                } else {
-                    #pragma unroll
-                    for (int k = 0; k < 4; k++)
-                        if (x + k < p.w) gq[k] = (float)to_acc<T>(gsrc[k]);
+                for (int k = 0; k < 4; k++) {
+                    float val = raw_get<T>(rd[i], k) * sc[i];
+                    if constexpr (GATE) val = round_through<T>(act_gradient_from_output(val, raw_get<T>(rg[i], k), gk));
+                    v[i0 + i][k] = ok ? val : 0.f;
                 }
-                #pragma unroll
-                for (int k = 0; k < 4; k++)
-                    v[i][k] = round_through<T>(act_gradient_from_output(v[i][k], gq[k], p.act, p.alpha, p.gain, p.clamp));
             }
         }
-        if constexpr (GATE) {
-            if (p.csum) {       // pixels outside the image and channels beyond C hold zeros
-                float sum = (v[i][0] + v[i][1]) + (v[i][2] + v[i][3]);
+    } else {
+        // rows that are not 16-byte aligned (the odd-width blurred images of the down = 2 layers): element loads, same two phases
+        constexpr int GROUP = sizeof(T) == 8 ? 2 : (GATE ? 4 : 8);
+        const GateConsts gk = gate_consts(p.act, p.alpha, p.gain, p.clamp);
+        const T* gsrc = GATE ? (const T*)p.gate + n * p.s_n + y * p.s_h + x : nullptr;
+        const float* scp = p.scale ? p.scale + (long long)n * p.c : nullptr;
+        #pragma unroll
+        for (int i0 = 0; i0 < 8; i0 += GROUP) {
+            T rd[GROUP][4], rg[GATE ? GROUP : 1][4];
+            float sc[GROUP];
+            #pragma unroll
+            for (int i = 0; i < GROUP; i++) {
+                const int c = c0 + warp * 8 + i0 + i;
+                const bool row_ok = y < p.h && c < p.c;
                 #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-                if (lane == 0 && c < p.c)
-                    p.csum[((long long)n * p.c + c) * ((long long)g.x_tiles * g.y_tiles) + (long long)yt * g.x_tiles + xt] = sum;
+                for (int k = 0; k < 4; k++) {
+                    const bool ok = row_ok && x + k < p.w;
+                    const long long off = ok ? c * p.s_c + k : 0;
+                    rd[i][k] = ok ? src[off] : *(const T*)p.x;          // always a valid address; masked below
+                    if constexpr (GATE) rg[i][k] = ok ? gsrc[off] : *(const T*)p.gate;
+                }
+                sc[i] = (scp != nullptr && row_ok) ? scp[c] : 1.f;
             }
+            #pragma unroll
+            for (int i = 0; i < GROUP; i++) {
+                const bool row_ok = y < p.h && c0 + warp * 8 + i0 + i < p.c;
+                #pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    float val = (float)to_acc<T>(rd[i][k]) * sc[i];
+                    if constexpr (GATE) val = round_through<T>(act_gradient_from_output(val, (float)to_acc<T>(rg[i][k]), gk));
+                    v[i0 + i][k] = (row_ok && x + k < p.w) ? val : 0.f;
+                }
+            }
+        }
+    }
+    if constexpr (GATE) {
+        if (p.csum) {
+            // per-channel sums of the tile (pixels outside the image and channels beyond C hold zeros), after ALL loads were issued (a store
+            // inside the loop would order the loads behind it).  8 values x 32 lanes, transposed butterfly: 9 shuffles instead of 40;
+            // lane l ends with the total of channel 4 * bit4(l) + 2 * bit3(l) + bit2(l)
+            float s8[8];
+            #pragma unroll
+            for (int i = 0; i < 8; i++) s8[i] = (v[i][0] + v[i][1]) + (v[i][2] + v[i][3]);
+            float s4[4], s2[2];
+            #pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const bool hi = lane & 16;
+                s4[j] = (hi ? s8[j + 4] : s8[j]) + __shfl_xor_sync(0xffffffffu, hi ? s8[j] : s8[j + 4], 16);
+            }
+            #pragma unroll
+            for (int j = 0; j < 2; j++) {
+                const bool hi = lane & 8;
+                s2[j] = (hi ? s4[j + 2] : s4[j]) + __shfl_xor_sync(0xffffffffu, hi ? s4[j] : s4[j + 2], 8);
+            }
+            const bool hi = lane & 4;
+            float s1 = (hi ? s2[1] : s2[0]) + __shfl_xor_sync(0xffffffffu, hi ? s2[0] : s2[1], 4);
+            s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
+            s1 += __shfl_xor_sync(0xffffffffu, s1, 1);
+            const int c = c0 + warp * 8 + ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+            if ((lane & 3) == 0 && c < p.c)
+                p.csum[((long long)n * p.c + c) * ((long long)g.x_tiles * g.y_tiles) + (long long)yt * g.x_tiles + xt] = s1;
         }
     }
     emit_tile(v, sm_packets, p.parts, p.out, p.part_stride, n, p.h, p.w, y0, x0, g.log_tw, c0, p.c_pad, p.c_total, p.c_off, p.f16);
