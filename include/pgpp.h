@@ -322,6 +322,9 @@ typedef struct pgpp_wgrad_desc {
     int32_t operand_f16;            /* nonzero: S and L hold IEEE half (one part, products == 1) instead of bfloat16 parts */
     int32_t dil_y;                  /* vertical tap spacing (0 or 1 = dense): tap ky reads L row y + ky * dil_y - pad_y; > 1 with stride 1 only - the
                                        weight gradient of a convolution that ran on a row-group im2col operand (pgpp_pack_im2col) */
+    float out_scale;                /* G is multiplied by this on its way out of the workspace (0 = 1): the runtime weight gain of the reference's
+                                       layers, d(w * gain)/dw (networks.py:169), without a pass of its own */
+    int32_t reserved0;
 } pgpp_wgrad_desc;
 
 /* Split-K GEMM over the pixels on the 5th-gen tensor cores (tcgen05.mma, TMEM accumulators, TMA operand loads). */

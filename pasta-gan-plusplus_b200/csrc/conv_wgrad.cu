@@ -356,7 +356,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap map_s, const __grid_constant__ 
 // workspace [taps][ca][cb_pad] -> G [ca][cb][taps]: one thread per (a, b) reads its taps (coalesced along b) and writes
 // taps consecutive floats
 __global__ void __launch_bounds__(256)
-wgrad_finalize_kernel(const float* __restrict__ ws, float* __restrict__ out, int ca, int cb, int cb_pad, int taps) {
+wgrad_finalize_kernel(const float* __restrict__ ws, float* __restrict__ out, int ca, int cb, int cb_pad, int taps, float scale) {
     const long long total = (long long)ca * cb;
     const long long plane = (long long)ca * cb_pad;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -364,7 +364,7 @@ wgrad_finalize_kernel(const float* __restrict__ ws, float* __restrict__ out, int
         const long long a = i / cb;
         const float* src = ws + a * cb_pad + b;
         float* dst = out + i * taps;
-        for (int t = 0; t < taps; t++) dst[t] = src[t * plane];
+        for (int t = 0; t < taps; t++) dst[t] = src[t * plane] * scale;
     }
 }
 
@@ -518,7 +518,8 @@ extern "C" int pgpp_conv2d_wgrad(const pgpp_wgrad_desc* d, void* stream) {
         const long long total = (long long)d->ca * d->cb;
         long long blocks = (total + 255) / 256;
         if (blocks > 8ll * sms) blocks = 8ll * sms;
-        wgrad_finalize_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(d->workspace, d->out, d->ca, d->cb, d->cb_pad, p.taps);
+        wgrad_finalize_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(d->workspace, d->out, d->ca, d->cb, d->cb_pad, p.taps,
+                                                                                    d->out_scale != 0.f ? d->out_scale : 1.f);
         count_launch();
         PGPP_CUDA_OK(cudaGetLastError());
     }

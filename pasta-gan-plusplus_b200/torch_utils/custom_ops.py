@@ -156,6 +156,7 @@ class WgradDesc(ctypes.Structure):
         ('stride', ctypes.c_int32), ('products', ctypes.c_int32),
         ('out', ctypes.c_void_p), ('workspace', ctypes.c_void_p),
         ('operand_f16', ctypes.c_int32), ('dil_y', ctypes.c_int32),
+        ('out_scale', ctypes.c_float), ('reserved0', ctypes.c_int32),
     ]
 
 

@@ -802,7 +802,7 @@ def _forward_conv_transpose(x, weight, bias, stride, padding, output_padding, ke
     return y
 
 
-def weight_gradient(grad_output, input, weight_shape, stride, padding, transpose, precision=None, out_dtype=None, dil_y=1):
+def weight_gradient(grad_output, input, weight_shape, stride, padding, transpose, precision=None, out_dtype=None, dil_y=1, out_scale=1.0):
     """dW of conv2d (transpose=False, weight [O, I, kh, kw]) or conv_transpose2d (transpose=True, weight [I, O, kh, kw]):
     what Conv2dGradWeight.forward (conv2d_gradfix.py:135-142) gets from cuDNN, computed by pgpp_conv2d_wgrad as
     G[a, b, ky, kx] = sum S[n, a, y, x] * L[n, b, y*s + ky - p, x*s + kx - p] with (S, L) = (grad_output, input) for the
@@ -831,7 +831,7 @@ def weight_gradient(grad_output, input, weight_shape, stride, padding, transpose
     d.ca = ca; d.ca_pad = ca_pad; d.s_pixel_stride = s_op.data.shape[4]; d.hs = int(small.shape[2]); d.ws = int(small.shape[3])
     d.cb = cb; d.cb_pad = cb_pad; d.l_pixel_stride = l_op.data.shape[4]; d.hl = int(large.shape[2]); d.wl = int(large.shape[3])
     d.kh = kh; d.kw = kw; d.pad_y = int(padding[0]); d.pad_x = int(padding[1])
-    d.stride = int(stride); d.products = products; d.operand_f16 = int(f16); d.dil_y = int(dil_y)
+    d.stride = int(stride); d.products = products; d.operand_f16 = int(f16); d.dil_y = int(dil_y); d.out_scale = float(out_scale)
     workspace = torch.empty([kh * kw, ca, cb_pad], dtype=torch.float32, device=device)
     d.out = out.data_ptr(); d.workspace = workspace.data_ptr()
     if trace is not None:
@@ -954,10 +954,11 @@ def _conv2d_gradfix(transpose, weight_shape, stride, padding, output_padding, di
                     xin = ctx.input_packed if ctx.input_packed is not None else input
                     if isinstance(xin, PackedAct) and xin.im2col is not None:
                         grad_weight = _weight_gradient_im2col(go, xin, weight_shape, xin.im2col, prec, weight.dtype)
-                    else:
-                        grad_weight = weight_gradient(go, xin, weight_shape, stride[0], padding, transpose, precision=prec, out_dtype=weight.dtype)
-                    if weight_scale != 1.0:
-                        grad_weight = grad_weight * weight_scale
+                        if weight_scale != 1.0:
+                            grad_weight = grad_weight * weight_scale
+                    else:       # the runtime weight gain leaves with the gradient (pgpp_wgrad_desc.out_scale)
+                        grad_weight = weight_gradient(go, xin, weight_shape, stride[0], padding, transpose, precision=prec, out_dtype=weight.dtype,
+                                                      out_scale=weight_scale)
                     assert grad_weight.shape == weight_shape
                 ctx.input_packed = None
             else:
@@ -982,9 +983,7 @@ def _conv2d_gradfix(transpose, weight_shape, stride, padding, output_padding, di
     class Conv2dGradWeight(torch.autograd.Function):
         @staticmethod
         def forward(ctx, grad_output, input):
-            gw = weight_gradient(grad_output, input, weight_shape, stride[0], padding, transpose)
-            if weight_scale != 1.0:
-                gw = gw * weight_scale
+            gw = weight_gradient(grad_output, input, weight_shape, stride[0], padding, transpose, out_scale=weight_scale)
             assert gw.shape == weight_shape
             ctx.save_for_backward(grad_output, input)
             return gw

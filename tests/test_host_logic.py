@@ -173,14 +173,14 @@ def test_conv_desc_mirror_matches_c_struct_layout(tmp_path):
 def test_wgrad_desc_mirror_matches_c_struct_layout(tmp_path):
     import subprocess
     src = tmp_path / 'szw.c'
-    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "pgpp.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu\\n",'
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "pgpp.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu\\n",'
                    'sizeof(pgpp_wgrad_desc),offsetof(pgpp_wgrad_desc,n),offsetof(pgpp_wgrad_desc,cb),'
-                   'offsetof(pgpp_wgrad_desc,products),offsetof(pgpp_wgrad_desc,out),offsetof(pgpp_wgrad_desc,workspace));return 0;}\n')
+                   'offsetof(pgpp_wgrad_desc,products),offsetof(pgpp_wgrad_desc,out),offsetof(pgpp_wgrad_desc,workspace),offsetof(pgpp_wgrad_desc,out_scale));return 0;}\n')
     exe = tmp_path / 'szw'
     subprocess.run(['gcc', '-I', os.path.join(ROOT, 'include'), str(src), '-o', str(exe)], check=True)
     c = [int(v) for v in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()]
     D = custom_ops.WgradDesc
-    assert c == [ctypes.sizeof(D), D.n.offset, D.cb.offset, D.products.offset, D.out.offset, D.workspace.offset]
+    assert c == [ctypes.sizeof(D), D.n.offset, D.cb.offset, D.products.offset, D.out.offset, D.workspace.offset, D.out_scale.offset]
 
 
 def test_synthesis_chain_composition_path_matches_oracle_chain_on_cpu():
