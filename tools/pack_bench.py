@@ -1,5 +1,13 @@
-import importlib, os, sys, torch
-sys.path.insert(0, '/root/repo'); sys.path.insert(0, '/root/repo/tests')
+"""packing pass (pgpp_pack_activations) at the training shapes: ms and algorithmic GB/s.  Usage: python tools/pack_bench.py"""
+import importlib
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, 'tests'))
 from conftest import load_pkg
 load_pkg()
 cg = importlib.import_module('pgpp_b200.torch_utils.ops.conv2d_gradfix')
