@@ -271,3 +271,11 @@ def test_c_abi_argument_validation_needs_no_gpu():
     size = custom_ops.c_i64x4(1, 8, 8, 8); stride = custom_ops.c_i64x4(512, 64, 8, 1)
     assert lib.pgpp_fir_pack(p, size, stride, taps, 5, 5, 2, 2, 2, 2, 0, 1.0, p, 64, 2, None) != 0 and 'filter up to 4 x 4' in err()
     assert lib.pgpp_mix_pack(p, p, p, p, p, None, None, None, p, 1, 8, 8, 8, 64, 2, None) != 0 and 'second term' in err()
+    # gradient of a fused bias_act straight into the operand format: activation, dtype and layout checks; tile count is pure host arithmetic
+    assert lib.pgpp_pack_act_gradient(p, p, size, stride, 0, 4, 0.0, 1.0, -1.0, p, 64, 2, 0, None, None) != 0 and 'linear, relu, lrelu' in err()
+    assert lib.pgpp_pack_act_gradient(p, p, size, stride, 3, 3, 0.2, 1.0, -1.0, p, 64, 2, 0, None, None) != 0 and 'f32, f16 or bf16' in err()
+    cl = custom_ops.c_i64x4(512, 1, 64, 8)
+    assert lib.pgpp_pack_act_gradient(p, p, size, cl, 0, 3, 0.2, 1.0, -1.0, p, 64, 2, 0, None, None) != 0 and 'pixel-contiguous' in err()
+    assert lib.pgpp_pack_act_gradient(p, None, size, stride, 0, 3, 0.2, 1.0, -1.0, p, 64, 2, 0, None, None) != 0 and 'device pointers' in err()
+    assert lib.pgpp_pack_act_gradient_tiles(512, 512) == 2048 and lib.pgpp_pack_act_gradient_tiles(513, 513) == 5 * 513
+    assert lib.pgpp_pack_act_gradient_tiles(9, 7) == 2 and lib.pgpp_pack_act_gradient_tiles(40, 36) == 1 * 20
