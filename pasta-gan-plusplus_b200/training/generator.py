@@ -251,7 +251,9 @@ class Spade_Conv2dLayer(torch.nn.Module):
                                          allow_im2col=xp.logical_hw is not None)
         return conv2d_gradfix.igemm_conv(xp, pw, act=act, gain=gain, out_packed=out_packed, out=out, accumulate=accumulate, instnorm_eps=instnorm_eps)
 
-    def forward(self, x, gain=1, no_act=False, fused=True, impl='cuda'):
+    def forward(self, x, gain=1, no_act=False, fused=True, impl='cuda', relu_after=False):
+        """`relu_after`: torch.relu of the result (the `nn.ReLU` that follows `conv_mlp`, networks.py:1709-1711) - in the convolution's epilogue on the
+        kernel routes, a separate op elsewhere"""
         b = self.bias.to(x.dtype) if self.bias is not None else None
         if not no_act:
             act_clamp = self.conv_clamp * gain if self.conv_clamp is not None else None
@@ -259,14 +261,18 @@ class Spade_Conv2dLayer(torch.nn.Module):
         if fused and S._can_fuse(x, self.weight):
             parts = conv2d_gradfix._PRODUCTS[conv2d_gradfix.precision_for(x.dtype)][1]
             pw = conv2d_gradfix.packed_plain(self.weight, True, parts, self.padding, self.padding, scale=self.weight_gain)
-            return conv2d_gradfix.igemm_conv(x, pw)
+            return conv2d_gradfix.igemm_conv(x, pw, act='relu' if relu_after else 'linear')
         if conv2d_gradfix._should_use_custom_op(x) and self.weight.dtype == torch.float32:
-            return conv2d_resample.conv2d_resample(x=x, w=self.weight, f=self.resample_filter, padding=self.padding, flip_weight=True,
-                                                   w_scale=float(self.weight_gain))
+            y = conv2d_resample.conv2d_resample(x=x, w=self.weight, f=self.resample_filter, padding=self.padding, flip_weight=True,
+                                                w_scale=float(self.weight_gain),
+                                                bias_act_args=dict(b=None, act='relu', gain=1.0, clamp=None) if (relu_after and impl == 'cuda') else None)
+            return torch.relu(y) if (relu_after and impl != 'cuda') else y
         w = self.weight * self.weight_gain
-        return conv2d_resample.conv2d_resample(x=x, w=w.to(x.dtype), f=self.resample_filter, padding=self.padding, flip_weight=True)
+        y = conv2d_resample.conv2d_resample(x=x, w=w.to(x.dtype), f=self.resample_filter, padding=self.padding, flip_weight=True)
+        return torch.relu(y) if relu_after else y
 
 
+FUSE_MLP_RELU = True            # Spade_Norm_Block: the ReLU after conv_mlp in that convolution's epilogue (False: nn.ReLU as its own op)
 FUSE_INSTNORM_STATS = True      # False: torch.var_mean over the float32 NCHW tensor (a second pass over it; kept for comparison / tests)
 FUSE_SPADE_EPILOGUE = True      # False: gamma|beta GEMM -> float32 NCHW, then pgpp_spade_modulate_pack (kept for comparison / tests)
 
@@ -311,7 +317,12 @@ class Spade_Norm_Block(torch.nn.Module):
 
     def forward(self, x, denorm_feats, fused=True, impl='cuda'):
         normalized = self.param_free_norm(x)
-        actv = self.conv_mlp_act(self.conv_mlp(denorm_feats, no_act=True, fused=fused, impl=impl))
+        if FUSE_MLP_RELU:
+            actv = self.conv_mlp(denorm_feats, no_act=True, fused=fused, impl=impl, relu_after=True)        # conv_mlp_act in the epilogue
+        else:
+            actv = self.conv_mlp_act(self.conv_mlp(denorm_feats, no_act=True, fused=fused, impl=impl))
+        # (conv_gamma | conv_beta as ONE training convolution with 2C outputs was measured: 36 launches fewer, 3 ms SLOWER per G phase - the
+        # concatenated weight is a temporary, so its packed copy and the split / concatenation of the gradients are paid on every call)
         gamma = self.conv_gamma(actv, no_act=True, fused=fused, impl=impl)
         beta = self.conv_beta(actv, no_act=True, fused=fused, impl=impl)
         return torch.addcmul(beta, normalized, 1 + gamma)

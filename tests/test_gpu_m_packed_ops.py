@@ -275,3 +275,42 @@ def test_spade_block_with_fused_statistics_equals_the_var_mean_route():
         finally:
             gen.FUSE_INSTNORM_STATS = old
     assert rel_l2(a, b) < 2e-6
+
+
+@pytest.mark.parametrize('prec', ['bf16x2', 'bf16x3'])
+def test_spade_norm_block_training_route_with_fused_relu(prec):
+    """training route of Spade_Norm_Block (networks.py:1702-1723) with conv_mlp's ReLU in the convolution's epilogue - output and every gradient
+    against the route with nn.ReLU as its own op (generator.FUSE_MLP_RELU = False) and against float64 of the same module on the CPU (library
+    convolutions)"""
+    import copy
+    cg.fp32_precision = prec
+    torch.manual_seed(77)
+    blk = gen.Spade_Norm_Block(24, 32).to(DEV)
+    x0 = torch.randn(2, 32, 20, 28, device=DEV)
+    f0 = torch.randn(2, 24, 20, 28, device=DEV)
+    probe = torch.randn(2, 32, 20, 28, device=DEV)
+
+    def run(module, x0_, f0_, probe_, **kw):
+        x, f = x0_.clone().requires_grad_(True), f0_.clone().requires_grad_(True)
+        y = module(x, f, **kw)
+        grads = torch.autograd.grad((y * probe_).sum() + 0.1 * y.square().sum(), [x, f] + list(module.parameters()))
+        return [y] + list(grads)
+
+    try:
+        fused_relu = run(blk, x0, f0, probe, fused=False)
+        gen.FUSE_MLP_RELU = False
+        plain = run(blk, x0, f0, probe, fused=False)
+    finally:
+        gen.FUSE_MLP_RELU = True
+    ref = copy.deepcopy(blk).double().cpu()
+    for m in ref.modules():         # the FIR taps stay float32, as upfirdn2d.setup_filter leaves them (upfirdn2d.py:91)
+        if isinstance(getattr(m, 'resample_filter', None), torch.Tensor):
+            m.resample_filter = m.resample_filter.float()
+    want = run(ref, x0.double().cpu(), f0.double().cpu(), probe.double().cpu(), fused=False, impl='ref')
+    tol = {'bf16x2': 2e-4, 'bf16x3': 1e-4}[prec]
+    assert len(fused_relu) == len(plain) == len(want)
+    for i, (a, b, r) in enumerate(zip(fused_relu, plain, want)):
+        assert a.shape == b.shape and rel_l2(a, b) < tol, (i, rel_l2(a, b))
+        # gradients that pass the ReLU gate (denorm_feats, conv_mlp.weight) see it flip where the pre-activation is within rounding of zero:
+        # a 1e-5 fraction of the pixels, an O(1) change each - in any finite precision
+        assert rel_l2(a, r) < (tol if i < 2 else 1e-2), (i, rel_l2(a, r))
