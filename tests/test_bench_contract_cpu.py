@@ -11,7 +11,7 @@ REQUIRED = ('metric', 'value', 'unit', 'n_gpus', 'steps', 'warmup', 'ms_per_step
 
 
 def test_committed_bench_line_has_the_contract_keys():
-    line = json.load(open(os.path.join(ROOT, 'profiles', 'r02_bench_v6.json')))
+    line = json.load(open(os.path.join(ROOT, 'profiles', 'r02_bench_v7.json')))
     assert all(k in line for k in REQUIRED), [k for k in REQUIRED if k not in line]
     assert line['metric'] == 'generator_512px_images_per_sec' and line['unit'] == 'images/s' and line['higher_is_better'] is True
     assert line['n_gpus'] == 1 and line['warmup'] >= 3 and line['scaling'] == 'weak' and line['vs_baseline'] is None
