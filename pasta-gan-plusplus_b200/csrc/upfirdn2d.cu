@@ -170,7 +170,8 @@ __global__ void __launch_bounds__(256, 4) fir_tile_kernel(UpfirdnArgs p, int til
         {
             const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
             constexpr int ROWS = (SM_H + 7) / 8, COLS = (SM_W + 31) / 32;
-            S v[ROWS][COLS];
+            T v[ROWS][COLS];        // kept in the source type until the staging store: a conversion between two loads makes the later load wait for the earlier one's data
+            const T zero = from_acc<T>(0.f);
             const bool interior = iy0 >= 0 && iy0 + SM_H <= p.ih && ix0 >= 0 && ix0 + SM_W <= p.iw;
             if (interior) {
                 #pragma unroll
@@ -181,7 +182,7 @@ __global__ void __launch_bounds__(256, 4) fir_tile_kernel(UpfirdnArgs p, int til
                     #pragma unroll
                     for (int k = 0; k < COLS; k++) {
                         const bool ok = row_ok && (k < COLS - 1 || lane + 32 * k < SM_W);
-                        v[r][k] = ok ? to_acc<T>(__ldg(row + 32 * k)) : (S)0;
+                        v[r][k] = ok ? __ldg(row + 32 * k) : zero;
                     }
                 }
             } else {
@@ -195,7 +196,7 @@ __global__ void __launch_bounds__(256, 4) fir_tile_kernel(UpfirdnArgs p, int til
                     for (int k = 0; k < COLS; k++) {
                         const int rx = lane + 32 * k;
                         const int ix = ix0 + rx;
-                        v[r][k] = (row_ok && rx < SM_W && ix >= 0 && ix < p.iw) ? to_acc<T>(__ldg(row + rx)) : (S)0;
+                        v[r][k] = (row_ok && rx < SM_W && ix >= 0 && ix < p.iw) ? __ldg(row + rx) : zero;
                     }
                 }
             }
@@ -205,7 +206,7 @@ __global__ void __launch_bounds__(256, 4) fir_tile_kernel(UpfirdnArgs p, int til
                 #pragma unroll
                 for (int k = 0; k < COLS; k++) {
                     const int rx = lane + 32 * k;
-                    if (ry < SM_H && rx < SM_W) sx[ry][rx] = v[r][k];
+                    if (ry < SM_H && rx < SM_W) sx[ry][rx] = to_acc<T>(v[r][k]);
                 }
             }
         }
@@ -294,7 +295,8 @@ __global__ void __launch_bounds__(256) fir_down2_kernel(UpfirdnArgs p, int tiles
         __syncthreads();
         {
             constexpr int ROWS = (D2_SM_H + 7) / 8, COLS = (D2_SM_W + 31) / 32;
-            S v[ROWS][COLS];
+            T v[ROWS][COLS];        // source type until the staging store (see fir_tile_kernel)
+            const T zero = from_acc<T>(0.f);
             #pragma unroll
             for (int rr = 0; rr < ROWS; rr++) {
                 const int ry = warp + 8 * rr;
@@ -305,7 +307,7 @@ __global__ void __launch_bounds__(256) fir_down2_kernel(UpfirdnArgs p, int tiles
                 for (int kk = 0; kk < COLS; kk++) {
                     const int rx = lane + 32 * kk;
                     const int ix = ix0 + rx;
-                    v[rr][kk] = (row_ok && ix >= 0 && ix < p.iw) ? to_acc<T>(__ldg(row + rx)) : (S)0;
+                    v[rr][kk] = (row_ok && ix >= 0 && ix < p.iw) ? __ldg(row + rx) : zero;
                 }
             }
             #pragma unroll
@@ -314,7 +316,7 @@ __global__ void __launch_bounds__(256) fir_down2_kernel(UpfirdnArgs p, int tiles
                 #pragma unroll
                 for (int kk = 0; kk < COLS; kk++) {
                     const int rx = lane + 32 * kk;
-                    if (ry < D2_SM_H && rx < D2_SM_W) sx[ry][rx] = v[rr][kk];
+                    if (ry < D2_SM_H && rx < D2_SM_W) sx[ry][rx] = to_acc<T>(v[rr][kk]);
                 }
             }
         }
@@ -395,20 +397,21 @@ __global__ void __launch_bounds__(256) fir_up2_kernel(UpfirdnArgs p, int tiles_x
         __syncthreads();
         {
             constexpr int USED_W = 66, PER = (U2_SM_H * USED_W + 255) / 256;
-            S v[PER];
+            T v[PER];               // source type until the staging store (see fir_tile_kernel)
+            const T zero = from_acc<T>(0.f);
             #pragma unroll
             for (int i = 0; i < PER; i++) {
                 const int idx = threadIdx.x + 256 * i;
                 const int ry = idx / USED_W, rx = idx - ry * USED_W;
                 const int iy = iy0 + ry, ix = ix0 + rx;
                 const bool ok = ry < U2_SM_H && iy >= 0 && iy < p.ih && ix >= 0 && ix < p.iw;
-                v[i] = ok ? to_acc<T>(__ldg(xp + (long long)iy * p.xs_h + ix)) : (S)0;
+                v[i] = ok ? __ldg(xp + (long long)iy * p.xs_h + ix) : zero;
             }
             #pragma unroll
             for (int i = 0; i < PER; i++) {
                 const int idx = threadIdx.x + 256 * i;
                 const int ry = idx / USED_W, rx = idx - ry * USED_W;
-                if (ry < U2_SM_H) sx[ry][rx] = v[i];
+                if (ry < U2_SM_H) sx[ry][rx] = to_acc<T>(v[i]);
             }
         }
         __syncthreads();
