@@ -723,11 +723,28 @@ TCONV_PHASES = True      # stride-2 transposed convolutions (the data gradient o
                          # the un-stuffed input at 1x the MACs; False: zero insertion + one convolution over the 4x larger tensor (the round-1 form)
 
 
+def tconv_stride2_phase_plan(kh, kw, padding):
+    """Stride-2 transposed convolution as four stride-1 correlations (pure arithmetic, no tensors):
+    y[i] = sum_{j, t: 2 j + t - p = i} x[j] * w[t].  Output phase r = i & 1 only sees the taps t = t0 + 2 m with t0 = (r + p) & 1, at inputs
+    j = q + s - m (i = 2 q + r, s = (r + p - t0) / 2): a stride-1 correlation of x with the flipped sub-kernel w[t0::2], padding (T - 1) - s
+    (may be negative = a crop), whose result is every second pixel of y.  -> one entry per (ry, rx):
+    dict(ry, rx, t0y, t0x, ty, tx, pad_y, pad_x); ty == 0 or tx == 0: no tap reaches that phase (the output there is the bias)."""
+    plan = []
+    for ry in (0, 1):
+        t0y = (ry + padding[0]) & 1
+        ty = max(0, (kh - t0y + 1) // 2)
+        for rx in (0, 1):
+            t0x = (rx + padding[1]) & 1
+            tx = max(0, (kw - t0x + 1) // 2)
+            plan.append(dict(ry=ry, rx=rx, t0y=t0y, t0x=t0x, ty=ty, tx=tx,
+                             pad_y=(ty - 1) - (ry + padding[0] - t0y) // 2, pad_x=(tx - 1) - (rx + padding[1] - t0x) // 2))
+    return plan
+
+
 def _conv_transpose_stride2_phases(x, weight, bias, padding, output_padding, scale):
-    """F.conv_transpose2d(x, weight[I, O, kh, kw], stride=2, ...):  y[i] = sum_{j, t: 2 j + t - p = i} x[j] * w[t].  Output phase r = i & 1 only sees
-    the taps t = t0 + 2 m with t0 = (r + p) & 1, at inputs j = q + s - m (i = 2 q + r, s = (r + p - t0) / 2): a stride-1 correlation of x with the
-    flipped sub-kernel w[t0::2], padding (T - 1) - s, written to every second pixel of y (strided output view of the implicit GEMM).  Four launches on
-    ONE packed copy of x instead of a zero-insertion pass, a packing pass over the 4x larger tensor and a convolution that multiplies 75 % zeros."""
+    """F.conv_transpose2d(x, weight[I, O, kh, kw], stride=2, ...) by `tconv_stride2_phase_plan`: four launches on ONE packed copy of x, each
+    writing a strided output view of the implicit GEMM, instead of a zero-insertion pass, a packing pass over the 4x larger tensor and a
+    convolution that multiplies 75 % zeros."""
     _init()
     ic, oc, kh, kw = (int(v) for v in weight.shape)
     src_dtype = (torch.float16 if x.data.dtype == torch.float16 else weight.dtype) if isinstance(x, PackedAct) else x.dtype
@@ -739,27 +756,20 @@ def _conv_transpose_stride2_phases(x, weight, bias, padding, output_padding, sca
     out_w = (w - 1) * 2 - 2 * padding[1] + kw + output_padding[1]
     out_dtype = src_dtype if src_dtype != torch.float64 else torch.float32
     y = torch.empty([n, oc, out_h, out_w], dtype=out_dtype, device=xp.device)
-    for ry in (0, 1):
-        t0y = (ry + padding[0]) & 1
-        ty = max(0, (kh - t0y + 1) // 2)
-        for rx in (0, 1):
-            t0x = (rx + padding[1]) & 1
-            tx = max(0, (kw - t0x + 1) // 2)
-            view = y[:, :, ry::2, rx::2]
-            if view.numel() == 0:
-                continue
-            if ty == 0 or tx == 0:          # no tap of the kernel reaches this phase (1-tap kernels)
-                view.zero_()
-                if bias is not None:
-                    view += bias.to(out_dtype).reshape(1, -1, 1, 1)
-                continue
-            pad_y = (ty - 1) - (ry + padding[0] - t0y) // 2
-            pad_x = (tx - 1) - (rx + padding[1] - t0x) // 2
-            def build(t0y=t0y, t0x=t0x, ty=ty, tx=tx, pad_y=pad_y, pad_x=pad_x):
-                sub = weight.detach()[:, :, t0y::2, t0x::2].contiguous()
-                return pack_weights_native(sub, ty, tx, parts, pad_y, pad_x, transpose_io=True, flip=True, scale=float(scale), f16=f16)
-            pw = _cached(weight, ('tconv_phase', ry, rx, int(padding[0]), int(padding[1]), parts, f16, float(scale)), build)
-            igemm_conv(xp, pw, out_hw=(int(view.shape[2]), int(view.shape[3])), out=view, bias=bias, precision=prec)
+    for ph in tconv_stride2_phase_plan(kh, kw, padding):
+        view = y[:, :, ph['ry']::2, ph['rx']::2]
+        if view.numel() == 0:
+            continue
+        if ph['ty'] == 0 or ph['tx'] == 0:          # no tap of the kernel reaches this phase (1-tap kernels)
+            view.zero_()
+            if bias is not None:
+                view += bias.to(out_dtype).reshape(1, -1, 1, 1)
+            continue
+        def build(ph=ph):
+            sub = weight.detach()[:, :, ph['t0y']::2, ph['t0x']::2].contiguous()
+            return pack_weights_native(sub, ph['ty'], ph['tx'], parts, ph['pad_y'], ph['pad_x'], transpose_io=True, flip=True, scale=float(scale), f16=f16)
+        pw = _cached(weight, ('tconv_phase', ph['ry'], ph['rx'], int(padding[0]), int(padding[1]), parts, f16, float(scale)), build)
+        igemm_conv(xp, pw, out_hw=(int(view.shape[2]), int(view.shape[3])), out=view, bias=bias, precision=prec)
     if src_dtype == torch.float64:
         y = y.to(torch.float64)
     return y, xp

@@ -279,3 +279,32 @@ def test_c_abi_argument_validation_needs_no_gpu():
     assert lib.pgpp_pack_act_gradient(p, None, size, stride, 0, 3, 0.2, 1.0, -1.0, p, 64, 2, 0, None, None) != 0 and 'device pointers' in err()
     assert lib.pgpp_pack_act_gradient_tiles(512, 512) == 2048 and lib.pgpp_pack_act_gradient_tiles(513, 513) == 5 * 513
     assert lib.pgpp_pack_act_gradient_tiles(9, 7) == 2 and lib.pgpp_pack_act_gradient_tiles(40, 36) == 1 * 20
+
+
+@pytest.mark.parametrize('k,pad,opad', [(1, 0, 0), (1, 0, 1), (2, 0, 0), (2, 1, 1), (3, 0, 0), (3, 1, 1), (3, 2, 1), (4, 1, 0), (5, 2, 1), (5, 4, 0), (7, 3, 1)])
+def test_stride2_transposed_convolution_phase_plan(k, pad, opad):
+    """the arithmetic behind conv2d_gradfix.TCONV_PHASES (sub-kernels, paddings, output phases) executed with library convolutions on the
+    CPU: equal to F.conv_transpose2d(stride=2) for every kernel size / padding / output padding the GPU path accepts"""
+    import torch.nn.functional as F
+    cg = importlib.import_module('pgpp_b200.torch_utils.ops.conv2d_gradfix')
+    g = torch.Generator().manual_seed(500 + k)
+    x = torch.randn(2, 5, 6, 7, generator=g, dtype=torch.float64)
+    w = torch.randn(5, 4, k, k + (1 if k in (2, 4) else 0), generator=g, dtype=torch.float64)      # [I, O, kh, kw], also non-square
+    kh, kw = w.shape[2:]
+    want = F.conv_transpose2d(x, w, stride=2, padding=pad, output_padding=opad)
+    y = torch.full_like(want, float('nan'))
+    for ph in cg.tconv_stride2_phase_plan(kh, kw, (pad, pad)):
+        view = y[:, :, ph['ry']::2, ph['rx']::2]
+        if view.numel() == 0:
+            continue
+        if ph['ty'] == 0 or ph['tx'] == 0:
+            view.zero_()
+            continue
+        sub = w[:, :, ph['t0y']::2, ph['t0x']::2]
+        assert tuple(sub.shape[2:]) == (ph['ty'], ph['tx'])
+        kern = sub.transpose(0, 1).flip([2, 3])                                     # correlation kernel [O, I, ty, tx]
+        # the kernel's view of a padding p (negative = crop, rows past the input = zeros): out[q] = sum_m kern[m] * x[q + m - p]
+        py, px, big = ph['pad_y'], ph['pad_x'], 12
+        full = F.conv2d(F.pad(x, [big] * 4), kern)                                 # full[i] = sum_m kern[m] * x[i + m - big]
+        view.copy_(full[:, :, big - py: big - py + view.shape[2], big - px: big - px + view.shape[3]])
+    assert not torch.isnan(y).any() and torch.allclose(y, want, atol=1e-12), float((y - want).abs().max())
